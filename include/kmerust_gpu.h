@@ -1,0 +1,186 @@
+/*
+ * kmerust_gpu.h -- C ABI (v1) of the B200-native canonical k-mer counting engine.
+ *
+ * This is the drop-in boundary for kmerust's counting path.  The reference
+ * (crate kmerust v0.3.1, paths below relative to its repository root) has no FFI of its own; its
+ * de-facto operator interface is Rust-internal:
+ *     in : Iterator<Item = Bytes> / IntoIter<SequenceWithQuality> + KmerLength + Option<u8> min_quality
+ *     out: HashMap<u64, u64>  (packed canonical k-mer -> count)
+ * (src/streaming.rs:198-204 count_kmers_from_sequences, :158-167 count_kmers_streaming_packed,
+ *  src/run.rs:491-583 KmerMap, src/reader.rs:13-16 SequenceWithQuality).
+ * Each entry point below names the reference item it replaces.  INTEGRATION.md shows the Rust
+ * `-sys` binding a maintainer would add.
+ *
+ * Conventions
+ *  - plain C, no exceptions cross the boundary; every call returns a kmg_status;
+ *    kmg_last_error() returns a UTF-8 message for the last failing call on that context.
+ *  - keys and counts are u64 little-endian, exactly the (packed_bits, count) pairs of
+ *    HashMap<u64,u64> and of the .kmix DATA section (src/index.rs:7-23).
+ *  - a context is driven by ONE feeder thread at a time (Rust wrapper: Send + !Sync).
+ *  - ownership: the context, its pinned staging buffers and all device memory belong to the
+ *    library; every result array belongs to the caller.
+ *  - there is NO CPU fallback: without a CUDA device kmg_create() fails with KMG_ERR_CUDA.
+ */
+#ifndef KMERUST_GPU_H
+#define KMERUST_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMG_ABI_VERSION 1u
+
+typedef enum kmg_status {
+  KMG_OK = 0,
+  KMG_ERR_INVALID_K = 1,   /* maps to KmerLengthError{k,min:1,max:32}  (src/kmer.rs:100-111, src/error.rs:88) */
+  KMG_ERR_INVALID_ARG = 2,
+  KMG_ERR_CUDA = 3,        /* no device / driver error; message carries cudaGetErrorString */
+  KMG_ERR_OOM = 4,         /* device or pinned allocation failed */
+  KMG_ERR_TABLE_FULL = 5,  /* table cannot grow any further; nothing is ever silently dropped */
+  KMG_ERR_STATE = 6,       /* call not valid in the context's current state */
+  KMG_ERR_IO = 7,          /* maps to KmeRustError::IndexWrite / SequenceRead (src/error.rs:20-60) */
+  KMG_ERR_ABI = 8,         /* abi_version mismatch */
+  KMG_ERR_CAPACITY = 9,    /* caller's output arrays are too small; *n_out holds the needed size */
+  KMG_ERR_PARSE = 10       /* maps to KmeRustError::SequenceParse{details} (src/error.rs:27-30) */
+} kmg_status;
+
+enum {
+  KMG_FLAG_FORCE_HASH = 1u,    /* use the open-addressing HBM table even for small k */
+  KMG_FLAG_FORCE_DIRECT = 2u,  /* use the direct-indexed 4^k array (k <= 14 only) */
+  KMG_FLAG_NO_PREAGG = 4u      /* disable in-warp duplicate pre-aggregation (for A/B measurements) */
+};
+
+/* Replaces: KmerLength::new (src/kmer.rs:100) + the Option<u8> min_quality argument of
+ * KmerMap::build_with_quality (src/run.rs:505-520) + capacity planning DashMap does implicitly. */
+typedef struct kmg_config {
+  uint32_t abi_version;       /* KMG_ABI_VERSION */
+  uint32_t k;                 /* 1..=32 */
+  int32_t device;             /* CUDA device ordinal; -1 = current device */
+  uint32_t flags;             /* KMG_FLAG_* */
+  uint8_t has_min_quality;    /* 0 = None */
+  uint8_t min_quality;        /* Phred; a base passes iff qual_byte >= saturating_add(min_quality, 33) (src/run.rs:538) */
+  uint8_t reserved[6];
+  uint64_t expected_distinct; /* capacity hint (distinct canonical k-mers); 0 = start small and grow */
+  uint64_t batch_bases;       /* capacity of each pinned staging buffer in bases; 0 = default */
+  void *stream;               /* cudaStream_t to run on; NULL = library-owned stream */
+} kmg_config;
+
+typedef struct kmg_ctx kmg_ctx;
+
+/* What the reference reports through Progress{sequences_processed, bases_processed}
+ * (src/progress.rs:26-31) plus what HashMap::len() / values().sum() would give. */
+typedef struct kmg_summary {
+  uint64_t n_records;
+  uint64_t n_bases;
+  uint64_t n_windows;       /* counted windows == sum of all counts */
+  uint64_t n_distinct;      /* distinct canonical k-mers in the table */
+  uint64_t max_count;
+  uint64_t table_capacity;  /* slots (hash path) or 4^k (direct path) */
+  uint32_t path;            /* 0 = hash table, 1 = direct-indexed array */
+  uint32_t n_grows;         /* number of rehash/grow events */
+  uint64_t kernel_ns;       /* device time spent in scan/insert kernels (CUDA events) */
+  uint64_t h2d_bytes;
+} kmg_summary;
+
+/* One pinned, library-owned staging buffer for the pre-packed feed (the Rust reader packs
+ * straight into it).  Layout: base j of the batch lives in bases2bit[j/32] at bit shift
+ * 62 - 2*(j%32) (MSB first, i.e. a full word read as an integer is the reference's packed
+ * 32-mer, src/kmer.rs:467-471); valid_bits[j/32] bit 31-(j%32) is 1 iff base j may be part of
+ * a counted window (ACGTacgt and quality >= threshold).  Record boundaries are expressed by
+ * start_bits (same bit layout; 1 on the first base of every record) so that windows never
+ * span records (src/run.rs:500-503 processes each record separately). */
+typedef struct kmg_batch {
+  uint64_t *bases2bit;
+  uint32_t *valid_bits;
+  uint32_t *start_bits;
+  uint64_t capacity_bases;
+  uint64_t n_bases;    /* filled by the producer */
+  uint64_t n_records;  /* filled by the producer (progress accounting only) */
+  uint32_t slot;       /* which of the double buffers this is (library-private) */
+} kmg_batch;
+
+uint32_t kmg_abi_version(void);
+const char *kmg_status_string(kmg_status s);
+/* Message of the last failure on `ctx` (or of the last failing kmg_create when ctx == NULL). */
+const char *kmg_last_error(const kmg_ctx *ctx);
+
+/* Replaces KmerMap::new / StreamingKmerCounter::new (src/run.rs:494-498, src/streaming.rs:838-843). */
+kmg_status kmg_create(const kmg_config *cfg, kmg_ctx **out);
+void kmg_destroy(kmg_ctx *ctx);
+/* Forget all counts but keep the allocations (benchmark steps, repeated use). */
+kmg_status kmg_reset(kmg_ctx *ctx);
+
+/* Replaces KmerMap::build_with_quality / StreamingKmerCounter::count_sequences over a batch of
+ * records (src/run.rs:505-520, src/streaming.rs:1058-1066): `seq` holds n_records ASCII records
+ * back to back, record r = seq[offsets[r] .. offsets[r+1]); `qual` (same layout, Phred+33) may be
+ * NULL (FASTA: the quality filter is then ignored, tests/quality_tests.rs:88-114).  HOST pointers;
+ * the call stages through pinned double buffers, overlapping H2D copies with the kernels, and
+ * returns when everything is queued (results are complete after kmg_finalize). */
+kmg_status kmg_count_ascii(kmg_ctx *ctx, const uint8_t *seq, const uint8_t *qual,
+                           const uint64_t *offsets, uint64_t n_records);
+
+/* Pre-packed, zero-copy feed for the Rust reader layer (src/reader.rs, src/streaming.rs, src/mmap.rs). */
+kmg_status kmg_acquire_batch(kmg_ctx *ctx, kmg_batch *batch);
+kmg_status kmg_submit_batch(kmg_ctx *ctx, const kmg_batch *batch);
+
+/* Same work with inputs already resident in HBM (device pointers).  d_offsets may be NULL when
+ * the buffer is one record.  d_seq must be 16-byte aligned. */
+kmg_status kmg_count_ascii_device(kmg_ctx *ctx, const uint8_t *d_seq, const uint8_t *d_qual,
+                                  const uint64_t *d_offsets, uint64_t n_records, uint64_t n_bytes);
+/* Weighted upsert of already-canonical keys (device pointers; d_counts NULL = 1 each): the
+ * receive side of the multi-GPU exchange.  Replaces process_valid_kmer (src/run.rs:565-571). */
+kmg_status kmg_insert_keys_device(kmg_ctx *ctx, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n);
+/* Scan only: emit the canonical key of every counted window, bucketed by owner shard
+ * (owner = kmg_owner_of(key, n_shards)); d_keys_out has room for cap keys in total and is laid
+ * out shard-major; shard_counts_out[n_shards] (HOST) receives the bucket sizes. */
+kmg_status kmg_extract_keys_device(kmg_ctx *ctx, const uint8_t *d_seq, const uint8_t *d_qual,
+                                   const uint64_t *d_offsets, uint64_t n_records, uint64_t n_bytes,
+                                   uint32_t n_shards, uint64_t *d_keys_out, uint64_t cap,
+                                   uint64_t *shard_counts_out);
+uint32_t kmg_owner_of(uint64_t canonical_key, uint32_t n_shards);
+
+/* Waits for all queued work; replaces into_hashmap()'s barrier role (src/run.rs:573-582). */
+kmg_status kmg_finalize(kmg_ctx *ctx, kmg_summary *summary);
+
+/* Replaces the HashMap<u64,u64> result + the min-count retain (src/run.rs:447-450,
+ * src/builder.rs:251-258).  Two-call protocol: with keys == NULL only *n_out is written.
+ * sorted != 0 gives ascending key order (== lexicographic order of the k-mer strings). */
+kmg_status kmg_export_counts(kmg_ctx *ctx, uint64_t min_count, int sorted, uint64_t *keys,
+                             uint64_t *counts, uint64_t cap, uint64_t *n_out);
+kmg_status kmg_export_counts_device(kmg_ctx *ctx, uint64_t min_count, int sorted, uint64_t *d_keys,
+                                    uint64_t *d_counts, uint64_t cap, uint64_t *n_out);
+
+/* Replaces compute_histogram_packed after the min-count filter (src/histogram.rs:110-116,
+ * src/run.rs:471-481): ascending (count, number of distinct k-mers with that count). */
+kmg_status kmg_histogram(kmg_ctx *ctx, uint64_t min_count, uint64_t *count_vals, uint64_t *freqs,
+                         uint64_t cap, uint64_t *n_out);
+
+/* Replaces counts_to_packed + KmerIndex::new + save_index (src/main.rs:155-202, :284-299,
+ * src/index.rs:156-196, :222-279).  Writes ALL k-mers (the index is never min-count filtered). */
+kmg_status kmg_save_kmix(kmg_ctx *ctx, const char *path);
+
+/* Replaces ProgressTracker::snapshot (src/progress.rs). */
+kmg_status kmg_progress(const kmg_ctx *ctx, uint64_t *records, uint64_t *bases);
+
+/* Diagnostics: number of this library's own CUDA kernels launched so far in this process. */
+uint64_t kmg_kernel_launches(void);
+
+/* Test/bench helper: fill d_out[n] with the deterministic synthetic base stream
+ * (same generator as oracle/kmer_oracle.c orc_synth_uniform). */
+kmg_status kmg_synth_uniform_device(kmg_ctx *ctx, uint64_t seed, uint64_t first_base, uint64_t n, uint8_t *d_out);
+
+/* Host utility (no CUDA): FASTA/FASTQ record splitter for hosts without the Rust reader layer; stands
+ * in for bio::io::{fasta,fastq}::Reader as used by src/reader.rs:91,96,176,181.  seq_out (and
+ * qual_out for FASTQ, may be NULL) need room for `len` bytes, offsets_out for max_records+1
+ * entries.  Errors map to KmeRustError::SequenceParse{details} with the message in errbuf. */
+kmg_status kmg_parse_fastx(const uint8_t *buf, uint64_t len, int is_fastq, uint8_t *seq_out, uint8_t *qual_out,
+                           uint64_t *offsets_out, uint64_t max_records, uint64_t *n_records_out, char *errbuf,
+                           size_t errbuf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMERUST_GPU_H */

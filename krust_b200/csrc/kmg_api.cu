@@ -1,0 +1,797 @@
+// C-ABI layer of libkmerust_gpu (include/kmerust_gpu.h): context, memory management, pinned
+// double-buffered staging, capacity planning / growth of the HBM table, result export.
+// The counting itself happens in the sm_100a kernels of kmg_kernels.cu.  There is no CPU fallback:
+// every entry point needs a CUDA device.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/kmerust_gpu.h"
+#include "kmg_device.cuh"
+#include "kmg_kernels.h"
+
+using namespace kmg;
+
+#define KMG_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr double LOAD_TARGET = 0.60;  // sizing goal when memory allows
+constexpr double LOAD_SOFT = 0.70;    // grow after a batch if exceeded and memory allows
+constexpr double LOAD_HARD = 0.90;    // never start a batch that could exceed this
+constexpr uint64_t DEFAULT_BATCH_BASES = 256ull << 20;
+constexpr uint64_t MIN_TABLE_SLOTS = 1ull << 16;
+
+struct Staging {
+  uint8_t *h_seq = nullptr, *h_qual = nullptr;  // pinned (lazily allocated; skipped for pinned callers)
+  uint64_t *h_off = nullptr;
+  uint8_t *d_seq = nullptr, *d_qual = nullptr;
+  uint64_t *d_off = nullptr;
+  uint64_t off_cap = 0;
+  cudaEvent_t h2d_done = nullptr, compute_done = nullptr;
+  bool h2d_pending = false, compute_pending = false;
+  // pre-packed feed (kmg_acquire_batch)
+  uint64_t *hp_bases = nullptr;
+  uint32_t *hp_valid = nullptr, *hp_start = nullptr;
+};
+
+}  // namespace
+
+struct kmg_ctx {
+  kmg_config cfg{};
+  int device = 0;
+  int k = 0;
+  bool use_dense = false;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  // table
+  HashTable table{nullptr, 0};
+  unsigned long long *dense = nullptr;
+  uint64_t dense_n = 0;
+  uint64_t distinct_ub = 0;  // upper bound of distinct keys currently in the table
+  uint32_t n_grows = 0;
+
+  unsigned long long *d_counters = nullptr;  // CTR_N
+  unsigned long long *h_counters = nullptr;  // pinned mirror
+  unsigned long long *d_stats = nullptr;     // 3 + cursor + overflow_n
+
+  // packed stream buffers (grown on demand)
+  uint64_t *d_bases = nullptr;
+  uint32_t *d_valid = nullptr, *d_start = nullptr;
+  uint64_t packed_words = 0;  // capacity in words (excluding lead-in)
+
+  uint64_t batch_bases = DEFAULT_BATCH_BASES;
+  Staging st[2];
+  bool staging_ready = false, packed_feed_ready = false;
+  uint32_t next_slot = 0;
+
+  uint64_t n_records = 0, n_bases = 0, h2d_bytes = 0;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  double kernel_ms = 0.0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_timers;
+};
+
+namespace {
+
+kmg_status fail(kmg_ctx *ctx, kmg_status s, const std::string &msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return s;
+}
+kmg_status cuda_fail(kmg_ctx *ctx, cudaError_t e, const char *what) {
+  kmg_status s = (e == cudaErrorMemoryAllocation) ? KMG_ERR_OOM : KMG_ERR_CUDA;
+  return fail(ctx, s, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(ctx, call)                                            \
+  do {                                                           \
+    cudaError_t _e = (call);                                     \
+    if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call);     \
+  } while (0)
+
+inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+TableView view_of(const kmg_ctx *c) {
+  TableView v;
+  if (c->use_dense) { v.slots = nullptr; v.dense = c->dense; v.n = c->dense_n; }
+  else { v.slots = c->table.slots; v.dense = nullptr; v.n = c->table.cap; }
+  return v;
+}
+
+kmg_status alloc_table(kmg_ctx *c, uint64_t cap, HashTable *out) {
+  cap = std::max<uint64_t>(cap, MIN_TABLE_SLOTS);
+  cap = round_up(cap, 2);
+  uint64_t *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, cap * 16);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(c, KMG_ERR_OOM, "cudaMalloc(table) failed: " + std::string(cudaGetErrorString(e))); }
+  out->slots = p; out->cap = cap;
+  CU(c, launch_table_init(*out, c->stream));
+  return KMG_OK;
+}
+
+// Try target loads from generous to tight until an allocation succeeds.
+kmg_status alloc_table_for(kmg_ctx *c, uint64_t need_keys, HashTable *out) {
+  const double loads[3] = {LOAD_TARGET, 0.75, LOAD_HARD};
+  kmg_status s = KMG_ERR_OOM;
+  for (double l : loads) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    uint64_t cap = (uint64_t)((double)need_keys / l) + 2;
+    if (cap * 16 > (uint64_t)free_b) continue;
+    s = alloc_table(c, cap, out);
+    if (s == KMG_OK) return s;
+  }
+  return fail(c, KMG_ERR_TABLE_FULL, "cannot allocate a table for " + std::to_string(need_keys) + " keys");
+}
+
+kmg_status read_counters(kmg_ctx *c) {
+  CU(c, cudaMemcpyAsync(c->h_counters, c->d_counters, CTR_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (c->h_counters[CTR_FULL]) return fail(c, KMG_ERR_TABLE_FULL, "hash table filled up during a batch (capacity planning bug)");
+  return KMG_OK;
+}
+
+kmg_status grow_table(kmg_ctx *c, uint64_t need_keys) {
+  HashTable nt{nullptr, 0};
+  kmg_status s = alloc_table_for(c, need_keys, &nt);
+  if (s != KMG_OK) return s;
+  if (nt.cap <= c->table.cap) { cudaFree(nt.slots); return fail(c, KMG_ERR_TABLE_FULL, "table cannot grow any further"); }
+  CU(c, launch_rehash(c->table, nt, c->d_counters, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->table.slots);
+  c->table = nt;
+  c->n_grows++;
+  return KMG_OK;
+}
+
+// Make sure `incoming` more upserts cannot push the load above LOAD_HARD.  Returns how many of them
+// may be issued now (>= 1 tile's worth or an error).
+kmg_status reserve_capacity(kmg_ctx *c, uint64_t incoming, uint64_t *granted) {
+  *granted = incoming;
+  if (c->use_dense) return KMG_OK;
+  auto room = [&]() -> uint64_t {
+    uint64_t lim = (uint64_t)(LOAD_HARD * (double)c->table.cap);
+    return lim > c->distinct_ub ? lim - c->distinct_ub : 0;
+  };
+  if (incoming <= room()) { c->distinct_ub += incoming; return KMG_OK; }
+  kmg_status s = read_counters(c);  // exact distinct count
+  if (s != KMG_OK) return s;
+  c->distinct_ub = c->h_counters[CTR_DISTINCT];
+  if (incoming <= room() && (double)c->distinct_ub <= LOAD_SOFT * (double)c->table.cap) { c->distinct_ub += incoming; return KMG_OK; }
+  // grow: enough for what is there plus the incoming batch
+  s = grow_table(c, c->distinct_ub + incoming);
+  if (s != KMG_OK) {
+    // could not grow: hand out whatever room is left (caller splits the batch)
+    uint64_t r = room();
+    if (r < (uint64_t)TILE_WORDS * 32) return s;
+    c->err.clear();
+    *granted = std::min(incoming, r);
+  }
+  c->distinct_ub += *granted;
+  return KMG_OK;
+}
+
+kmg_status ensure_packed(kmg_ctx *c, uint64_t n_words_total) {
+  if (n_words_total <= c->packed_words) return KMG_OK;
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_bases); cudaFree(c->d_valid); cudaFree(c->d_start);
+  c->d_bases = nullptr; c->d_valid = c->d_start = nullptr; c->packed_words = 0;
+  CU(c, cudaMalloc(&c->d_bases, (LEAD_BASE_WORDS + n_words_total) * 8));
+  CU(c, cudaMalloc(&c->d_valid, (LEAD_MASK_WORDS + n_words_total) * 4));
+  CU(c, cudaMalloc(&c->d_start, (LEAD_MASK_WORDS + n_words_total) * 4));
+  CU(c, cudaMemsetAsync(c->d_bases, 0, LEAD_BASE_WORDS * 8, c->stream));
+  CU(c, cudaMemsetAsync(c->d_valid, 0, LEAD_MASK_WORDS * 4, c->stream));
+  CU(c, cudaMemsetAsync(c->d_start, 0, LEAD_MASK_WORDS * 4, c->stream));
+  c->packed_words = n_words_total;
+  return KMG_OK;
+}
+
+void timer_begin(kmg_ctx *c) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a, c->stream);
+  c->pending_timers.emplace_back(a, b);
+}
+void timer_end(kmg_ctx *c) { cudaEventRecord(c->pending_timers.back().second, c->stream); }
+void timers_collect(kmg_ctx *c) {
+  for (auto &p : c->pending_timers) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) c->kernel_ms += ms;
+    cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+  }
+  c->pending_timers.clear();
+}
+
+// Run the counting scan over a packed stream of n_words_total words (already in d_bases/d_valid/d_start).
+kmg_status scan_packed(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
+  const uint64_t n_tiles = n_words_total / TILE_WORDS;
+  uint64_t tile0 = 0;
+  timer_begin(c);
+  while (tile0 < n_tiles) {
+    uint64_t want = (n_tiles - tile0) * TILE_WORDS * 32, granted = 0;
+    kmg_status s = reserve_capacity(c, want, &granted);
+    if (s != KMG_OK) return s;
+    uint64_t tiles = granted >= want ? n_tiles - tile0 : granted / ((uint64_t)TILE_WORDS * 32);
+    if (tiles == 0) return fail(c, KMG_ERR_TABLE_FULL, "no table capacity left for even one tile");
+    ScanInput in;
+    in.bases = c->d_bases + tile0 * TILE_WORDS;
+    in.valid = c->d_valid + tile0 * TILE_WORDS;
+    in.start = has_start ? c->d_start + tile0 * TILE_WORDS : nullptr;
+    in.n_tiles = tiles;
+    in.k = c->k;
+    if (c->use_dense) CU(c, launch_scan_dense(in, c->dense, c->d_counters, c->cfg.flags, c->stream));
+    else CU(c, launch_scan_hash(in, c->table, c->d_counters, c->cfg.flags, c->stream));
+    tile0 += tiles;
+  }
+  timer_end(c);
+  return KMG_OK;
+}
+
+// ingest raw ASCII already on the device into the packed buffers and scan it.
+// d_starts[n_starts] are byte offsets (minus base_offset) of record starts inside this chunk.
+kmg_status count_device_chunk(kmg_ctx *c, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_starts,
+                              uint64_t n_starts, uint64_t base_offset, uint64_t n_bytes) {
+  if (n_bytes == 0) return KMG_OK;
+  const uint64_t n_words_total = round_up((n_bytes + 31) / 32, TILE_WORDS);
+  kmg_status s = ensure_packed(c, n_words_total);
+  if (s != KMG_OK) return s;
+  const bool use_q = c->cfg.has_min_quality && d_qual != nullptr;
+  const uint32_t thr = std::min<uint32_t>(255u, (uint32_t)c->cfg.min_quality + 33u);  // saturating_add (src/run.rs:538)
+  CU(c, launch_ingest(d_seq, use_q ? d_qual : nullptr, n_bytes, thr, n_words_total, c->d_bases, c->d_valid, c->stream));
+  const bool has_start = d_starts != nullptr && n_starts > 0;
+  if (has_start) CU(c, launch_start_bits(d_starts, n_starts, base_offset, n_bytes, n_words_total, c->d_start, c->stream));
+  return scan_packed(c, n_words_total, has_start);
+}
+
+kmg_status ensure_staging(kmg_ctx *c, bool need_pinned) {
+  const uint64_t cap = c->batch_bases + 64;
+  for (int i = 0; i < 2; ++i) {
+    Staging &s = c->st[i];
+    if (!s.d_seq) {
+      CU(c, cudaMalloc(&s.d_seq, cap));
+      CU(c, cudaMalloc(&s.d_qual, cap));
+      CU(c, cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+      CU(c, cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
+    }
+    if (need_pinned && !s.h_seq) {
+      CU(c, cudaHostAlloc(&s.h_seq, cap, cudaHostAllocDefault));
+      CU(c, cudaHostAlloc(&s.h_qual, cap, cudaHostAllocDefault));
+    }
+  }
+  c->staging_ready = true;
+  return KMG_OK;
+}
+
+kmg_status ensure_offsets(kmg_ctx *c, Staging &s, uint64_t n) {
+  if (n <= s.off_cap) return KMG_OK;
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaStreamSynchronize(c->copy_stream));
+  if (s.h_off) cudaFreeHost(s.h_off);
+  if (s.d_off) cudaFree(s.d_off);
+  s.h_off = nullptr; s.d_off = nullptr; s.off_cap = 0;
+  uint64_t cap = std::max<uint64_t>(n, 1024) * 2;
+  CU(c, cudaHostAlloc(&s.h_off, cap * 8, cudaHostAllocDefault));
+  CU(c, cudaMalloc(&s.d_off, cap * 8));
+  s.off_cap = cap;
+  return KMG_OK;
+}
+
+bool is_pinned_host(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// ---- CRC32 (IEEE, reflected 0xEDB88320; src/index.rs:404-431), slicing-by-8 ----------------------------
+struct Crc32 {
+  uint32_t t[8][256];
+  Crc32() {
+    for (uint32_t i = 0; i < 256; i++) {
+      uint32_t c = i;
+      for (int j = 0; j < 8; j++) c = (c & 1) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+      t[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; i++)
+      for (int s = 1; s < 8; s++) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xFF];
+  }
+  uint32_t update(uint32_t crc, const uint8_t *p, size_t n) const {
+    while (n >= 8) {
+      uint32_t a, b;
+      memcpy(&a, p, 4); memcpy(&b, p + 4, 4);
+      a ^= crc;
+      crc = t[7][a & 0xFF] ^ t[6][(a >> 8) & 0xFF] ^ t[5][(a >> 16) & 0xFF] ^ t[4][a >> 24] ^
+            t[3][b & 0xFF] ^ t[2][(b >> 8) & 0xFF] ^ t[1][(b >> 16) & 0xFF] ^ t[0][b >> 24];
+      p += 8; n -= 8;
+    }
+    while (n--) crc = t[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8);
+    return crc;
+  }
+};
+const Crc32 &crc_tables() { static Crc32 c; return c; }
+
+}  // namespace
+
+// =================================================================================================
+KMG_EXPORT uint32_t kmg_abi_version(void) { return KMG_ABI_VERSION; }
+
+KMG_EXPORT const char *kmg_status_string(kmg_status s) {
+  switch (s) {
+    case KMG_OK: return "ok";
+    case KMG_ERR_INVALID_K: return "invalid k-mer length (must be 1..=32)";
+    case KMG_ERR_INVALID_ARG: return "invalid argument";
+    case KMG_ERR_CUDA: return "CUDA error";
+    case KMG_ERR_OOM: return "out of memory";
+    case KMG_ERR_TABLE_FULL: return "k-mer table full";
+    case KMG_ERR_STATE: return "invalid state";
+    case KMG_ERR_IO: return "I/O error";
+    case KMG_ERR_ABI: return "ABI version mismatch";
+    case KMG_ERR_CAPACITY: return "output capacity too small";
+    case KMG_ERR_PARSE: return "sequence parse error";
+  }
+  return "unknown";
+}
+
+KMG_EXPORT const char *kmg_last_error(const kmg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+KMG_EXPORT uint32_t kmg_owner_of(uint64_t canonical_key, uint32_t n_shards) { return n_shards <= 1 ? 0 : part_of(canonical_key, n_shards); }
+
+KMG_EXPORT void kmg_destroy(kmg_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  timers_collect(c);
+  cudaFree(c->table.slots); cudaFree(c->dense); cudaFree(c->d_counters); cudaFree(c->d_stats);
+  cudaFree(c->d_bases); cudaFree(c->d_valid); cudaFree(c->d_start);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  for (auto &s : c->st) {
+    if (s.h_seq) cudaFreeHost(s.h_seq);
+    if (s.h_qual) cudaFreeHost(s.h_qual);
+    if (s.h_off) cudaFreeHost(s.h_off);
+    if (s.hp_bases) cudaFreeHost(s.hp_bases);
+    if (s.hp_valid) cudaFreeHost(s.hp_valid);
+    if (s.hp_start) cudaFreeHost(s.hp_start);
+    cudaFree(s.d_seq); cudaFree(s.d_qual); cudaFree(s.d_off);
+    if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+    if (s.compute_done) cudaEventDestroy(s.compute_done);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+KMG_EXPORT kmg_status kmg_create(const kmg_config *cfg, kmg_ctx **out) {
+  if (!cfg || !out) return fail(nullptr, KMG_ERR_INVALID_ARG, "cfg and out must not be NULL");
+  *out = nullptr;
+  if (cfg->abi_version != KMG_ABI_VERSION)
+    return fail(nullptr, KMG_ERR_ABI, "abi_version " + std::to_string(cfg->abi_version) + " != " + std::to_string(KMG_ABI_VERSION));
+  if (cfg->k < 1 || cfg->k > 32)  // KmerLengthError (src/kmer.rs:100-111)
+    return fail(nullptr, KMG_ERR_INVALID_K, "k-mer length " + std::to_string(cfg->k) + " is out of range (must be 1-32)");
+  if ((cfg->flags & KMG_FLAG_FORCE_DIRECT) && (cfg->flags & KMG_FLAG_FORCE_HASH))
+    return fail(nullptr, KMG_ERR_INVALID_ARG, "FORCE_DIRECT and FORCE_HASH are mutually exclusive");
+  if ((cfg->flags & KMG_FLAG_FORCE_DIRECT) && cfg->k > (uint32_t)DENSE_MAX_K)
+    return fail(nullptr, KMG_ERR_INVALID_ARG, "direct-indexed path supports k <= 14");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, KMG_ERR_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                                           (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  }
+  kmg_ctx *c = new kmg_ctx();
+  c->cfg = *cfg;
+  c->k = (int)cfg->k;
+  if (cfg->device >= 0) c->device = cfg->device; else cudaGetDevice(&c->device);
+  auto bail = [&](kmg_status s) { g_create_error = c->err; kmg_destroy(c); return s; };
+#define CUC(call)                                                                  \
+  do {                                                                             \
+    cudaError_t _e = (call);                                                       \
+    if (_e != cudaSuccess) { cuda_fail(c, _e, #call); return bail(_e == cudaErrorMemoryAllocation ? KMG_ERR_OOM : KMG_ERR_CUDA); } \
+  } while (0)
+  CUC(cudaSetDevice(c->device));
+  if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
+  else { CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CUC(cudaMalloc(&c->d_counters, CTR_N * sizeof(unsigned long long)));
+  CUC(cudaMemsetAsync(c->d_counters, 0, CTR_N * sizeof(unsigned long long), c->stream));
+  CUC(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
+  CUC(cudaHostAlloc(&c->h_counters, 16 * sizeof(unsigned long long), cudaHostAllocDefault));
+  if (cfg->batch_bases) c->batch_bases = std::max<uint64_t>(round_up(cfg->batch_bases, 32), 4096);
+  c->use_dense = (cfg->flags & KMG_FLAG_FORCE_DIRECT) ||
+                 (!(cfg->flags & KMG_FLAG_FORCE_HASH) && cfg->k <= (uint32_t)DENSE_DEFAULT_MAX_K);
+  if (c->use_dense) {
+    c->dense_n = 1ull << (2 * c->k);
+    CUC(cudaMalloc(&c->dense, c->dense_n * 8));
+    CUC(cudaMemsetAsync(c->dense, 0, c->dense_n * 8, c->stream));
+  } else {
+    kmg_status s;
+    if (cfg->expected_distinct) s = alloc_table_for(c, cfg->expected_distinct, &c->table);
+    else s = alloc_table(c, 1ull << 22, &c->table);
+    if (s != KMG_OK) return bail(s);
+  }
+  CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+  *out = c;
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_reset(kmg_ctx *c) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->copy_stream));
+  if (c->use_dense) CU(c, cudaMemsetAsync(c->dense, 0, c->dense_n * 8, c->stream));
+  else CU(c, launch_table_init(c->table, c->stream));
+  CU(c, cudaMemsetAsync(c->d_counters, 0, CTR_N * sizeof(unsigned long long), c->stream));
+  c->distinct_ub = 0; c->n_records = c->n_bases = c->h2d_bytes = 0; c->kernel_ms = 0.0;
+  CU(c, cudaStreamSynchronize(c->stream));
+  timers_collect(c);
+  c->kernel_ms = 0.0;
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_count_ascii_device(kmg_ctx *c, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_offsets,
+                                             uint64_t n_records, uint64_t n_bytes) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  if (n_bytes && !d_seq) return fail(c, KMG_ERR_INVALID_ARG, "d_seq is NULL");
+  if (((uintptr_t)d_seq & 15) || ((uintptr_t)d_qual & 15)) return fail(c, KMG_ERR_INVALID_ARG, "d_seq / d_qual must be 16-byte aligned");
+  CU(c, cudaSetDevice(c->device));
+  // offsets[0] (== 0) needs no start bit; a single record needs none at all
+  kmg_status s = count_device_chunk(c, d_seq, d_qual, n_records > 1 ? d_offsets : nullptr, n_records, 0, n_bytes);
+  if (s != KMG_OK) return s;
+  c->n_records += n_records; c->n_bases += n_bytes;
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets, uint64_t n_records) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  if (n_records == 0) return KMG_OK;
+  if (!offsets || !seq) {
+    if (offsets && offsets[n_records] == offsets[0]) { c->n_records += n_records; return KMG_OK; }
+    return fail(c, KMG_ERR_INVALID_ARG, "seq / offsets must not be NULL");
+  }
+  for (uint64_t r = 0; r < n_records; ++r)
+    if (offsets[r + 1] < offsets[r]) return fail(c, KMG_ERR_INVALID_ARG, "offsets must be non-decreasing");
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t begin = offsets[0], end = offsets[n_records];
+  const bool use_q = c->cfg.has_min_quality && qual != nullptr;
+  const bool src_pinned = is_pinned_host(seq + begin) && (!use_q || is_pinned_host(qual + begin));
+  kmg_status s = ensure_staging(c, !src_pinned);
+  if (s != KMG_OK) return s;
+  const uint64_t K1 = (uint64_t)c->k - 1;
+  const uint64_t B = c->batch_bases;  // bytes per chunk including the k-1 overlap
+  const uint64_t step = B - K1;
+  uint64_t r_lo = 0;
+  for (uint64_t pos = begin; pos < end; pos += step) {
+    const uint64_t len = std::min<uint64_t>(B, end - pos);
+    if (pos != begin && len <= K1) break;  // only the overlap is left: no new windows
+    // records with a start strictly inside (pos, pos+len)
+    while (r_lo < n_records && offsets[r_lo] <= pos) ++r_lo;
+    uint64_t r_hi = r_lo;
+    while (r_hi < n_records && offsets[r_hi] < pos + len) ++r_hi;
+    const uint64_t nrec = r_hi - r_lo;
+
+    Staging &st = c->st[c->next_slot];
+    c->next_slot ^= 1;
+    if (st.h2d_pending) { CU(c, cudaEventSynchronize(st.h2d_done)); st.h2d_pending = false; }
+    if (st.compute_pending) { CU(c, cudaStreamWaitEvent(c->copy_stream, st.compute_done, 0)); }
+    if ((s = ensure_offsets(c, st, nrec)) != KMG_OK) return s;
+    const uint8_t *src_seq = seq + pos, *src_qual = use_q ? qual + pos : nullptr;
+    if (!src_pinned) {
+      memcpy(st.h_seq, src_seq, len); src_seq = st.h_seq;
+      if (use_q) { memcpy(st.h_qual, src_qual, len); src_qual = st.h_qual; }
+    }
+    CU(c, cudaMemcpyAsync(st.d_seq, src_seq, len, cudaMemcpyHostToDevice, c->copy_stream));
+    if (use_q) CU(c, cudaMemcpyAsync(st.d_qual, src_qual, len, cudaMemcpyHostToDevice, c->copy_stream));
+    if (nrec) {
+      memcpy(st.h_off, offsets + r_lo, nrec * 8);
+      CU(c, cudaMemcpyAsync(st.d_off, st.h_off, nrec * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    c->h2d_bytes += len * (use_q ? 2 : 1) + nrec * 8;
+    CU(c, cudaEventRecord(st.h2d_done, c->copy_stream));
+    st.h2d_pending = true;
+    CU(c, cudaStreamWaitEvent(c->stream, st.h2d_done, 0));
+    s = count_device_chunk(c, st.d_seq, use_q ? st.d_qual : nullptr, nrec ? st.d_off : nullptr, nrec, pos, len);
+    if (s != KMG_OK) return s;
+    CU(c, cudaEventRecord(st.compute_done, c->stream));
+    st.compute_pending = true;
+  }
+  c->n_records += n_records; c->n_bases += end - begin;
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_acquire_batch(kmg_ctx *c, kmg_batch *b) {
+  if (!c || !b) return KMG_ERR_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t words = round_up((c->batch_bases + 31) / 32, TILE_WORDS);
+  if (!c->packed_feed_ready) {
+    for (auto &s : c->st) {
+      CU(c, cudaHostAlloc(&s.hp_bases, words * 8, cudaHostAllocDefault));
+      CU(c, cudaHostAlloc(&s.hp_valid, words * 4, cudaHostAllocDefault));
+      CU(c, cudaHostAlloc(&s.hp_start, words * 4, cudaHostAllocDefault));
+      if (!s.h2d_done) {
+        CU(c, cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
+      }
+    }
+    c->packed_feed_ready = true;
+  }
+  Staging &s = c->st[c->next_slot];
+  if (s.h2d_pending) { CU(c, cudaEventSynchronize(s.h2d_done)); s.h2d_pending = false; }
+  memset(s.hp_bases, 0, words * 8); memset(s.hp_valid, 0, words * 4); memset(s.hp_start, 0, words * 4);
+  b->bases2bit = s.hp_bases; b->valid_bits = s.hp_valid; b->start_bits = s.hp_start;
+  b->capacity_bases = c->batch_bases; b->n_bases = 0; b->n_records = 0; b->slot = c->next_slot;
+  c->next_slot ^= 1;
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_submit_batch(kmg_ctx *c, const kmg_batch *b) {
+  if (!c || !b) return KMG_ERR_INVALID_ARG;
+  if (b->slot > 1 || !c->packed_feed_ready || b->bases2bit != c->st[b->slot].hp_bases)
+    return fail(c, KMG_ERR_STATE, "batch was not obtained from kmg_acquire_batch");
+  if (b->n_bases > b->capacity_bases) return fail(c, KMG_ERR_INVALID_ARG, "n_bases exceeds the batch capacity");
+  if (b->n_bases == 0) return KMG_OK;
+  CU(c, cudaSetDevice(c->device));
+  Staging &s = c->st[b->slot];
+  const uint64_t n_words = (b->n_bases + 31) / 32, n_words_total = round_up(n_words, TILE_WORDS);
+  kmg_status st = ensure_packed(c, n_words_total);
+  if (st != KMG_OK) return st;
+  // single compute stream: the packed device buffers are reused by every batch, so the copy is ordered behind
+  // the previous scan; the pinned buffer is free again once h2d_done fires.
+  CU(c, cudaMemcpyAsync(c->d_bases + LEAD_BASE_WORDS, s.hp_bases, n_words_total * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_valid + LEAD_MASK_WORDS, s.hp_valid, n_words_total * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_start + LEAD_MASK_WORDS, s.hp_start, n_words_total * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaEventRecord(s.h2d_done, c->stream));
+  s.h2d_pending = true;
+  c->h2d_bytes += n_words_total * 16;
+  st = scan_packed(c, n_words_total, true);
+  if (st != KMG_OK) return st;
+  c->n_records += b->n_records; c->n_bases += b->n_bases;
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_insert_keys_device(kmg_ctx *c, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  if (n == 0) return KMG_OK;
+  if (!d_keys) return fail(c, KMG_ERR_INVALID_ARG, "d_keys is NULL");
+  CU(c, cudaSetDevice(c->device));
+  if (c->use_dense) { CU(c, launch_insert_keys_dense(c->dense, d_keys, d_counts, n, c->d_counters, c->stream)); return KMG_OK; }
+  uint64_t done = 0;
+  while (done < n) {
+    uint64_t granted = 0;
+    kmg_status s = reserve_capacity(c, n - done, &granted);
+    if (s != KMG_OK) return s;
+    CU(c, launch_insert_keys(c->table, d_keys + done, d_counts ? d_counts + done : nullptr, granted, c->d_counters, c->stream));
+    done += granted;
+  }
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_extract_keys_device(kmg_ctx *c, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_offsets,
+                                              uint64_t n_records, uint64_t n_bytes, uint32_t n_shards, uint64_t *d_keys_out,
+                                              uint64_t cap, uint64_t *shard_counts_out) {
+  if (!c || !shard_counts_out) return KMG_ERR_INVALID_ARG;
+  if (n_shards < 1 || n_shards > 4096) return fail(c, KMG_ERR_INVALID_ARG, "n_shards must be in 1..=4096");
+  if (((uintptr_t)d_seq & 15) || ((uintptr_t)d_qual & 15)) return fail(c, KMG_ERR_INVALID_ARG, "d_seq / d_qual must be 16-byte aligned");
+  CU(c, cudaSetDevice(c->device));
+  for (uint32_t i = 0; i < n_shards; ++i) shard_counts_out[i] = 0;
+  if (n_bytes == 0) return KMG_OK;
+  const uint64_t n_words_total = round_up((n_bytes + 31) / 32, TILE_WORDS);
+  kmg_status s = ensure_packed(c, n_words_total);
+  if (s != KMG_OK) return s;
+  const bool use_q = c->cfg.has_min_quality && d_qual != nullptr;
+  const uint32_t thr = std::min<uint32_t>(255u, (uint32_t)c->cfg.min_quality + 33u);
+  CU(c, launch_ingest(d_seq, use_q ? d_qual : nullptr, n_bytes, thr, n_words_total, c->d_bases, c->d_valid, c->stream));
+  const bool has_start = d_offsets != nullptr && n_records > 1;
+  if (has_start) CU(c, launch_start_bits(d_offsets, n_records, 0, n_bytes, n_words_total, c->d_start, c->stream));
+  unsigned long long *d_pc = nullptr;
+  CU(c, cudaMalloc(&d_pc, 2 * (size_t)n_shards * 8 + 64));
+  unsigned long long *d_cur = d_pc + n_shards;
+  unsigned long long *d_ctr = d_cur + n_shards;  // scratch counters (windows of this call only)
+  CU(c, cudaMemsetAsync(d_pc, 0, 2 * (size_t)n_shards * 8 + 64, c->stream));
+  ScanInput in{c->d_bases, c->d_valid, has_start ? c->d_start : nullptr, n_words_total / TILE_WORDS, c->k};
+  cudaError_t e = launch_scan_partition(in, n_shards, false, d_pc, d_cur, nullptr, d_ctr, c->stream);
+  std::vector<unsigned long long> h(n_shards);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), d_pc, n_shards * 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) { cudaFree(d_pc); return cuda_fail(c, e, "partition count pass"); }
+  uint64_t total = 0;
+  std::vector<unsigned long long> prefix(n_shards);
+  for (uint32_t i = 0; i < n_shards; ++i) { prefix[i] = total; total += h[i]; shard_counts_out[i] = h[i]; }
+  if (total > cap || (total && !d_keys_out)) { cudaFree(d_pc); return fail(c, KMG_ERR_CAPACITY, "d_keys_out too small: need " + std::to_string(total)); }
+  e = cudaMemcpyAsync(d_cur, prefix.data(), n_shards * 8, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = launch_scan_partition(in, n_shards, true, d_pc, d_cur, d_keys_out, d_ctr, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_pc);
+  if (e != cudaSuccess) return cuda_fail(c, e, "partition scatter pass");
+  c->n_records += n_records; c->n_bases += n_bytes;
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_finalize(kmg_ctx *c, kmg_summary *out) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->copy_stream));
+  kmg_status s = read_counters(c);
+  if (s != KMG_OK) return s;
+  for (auto &st : c->st) { st.h2d_pending = false; st.compute_pending = false; }
+  timers_collect(c);
+  if (!c->use_dense) c->distinct_ub = c->h_counters[CTR_DISTINCT];
+  if (!out) return KMG_OK;
+  memset(out, 0, sizeof *out);
+  CU(c, launch_table_stats(view_of(c), 1, c->d_stats, c->stream));
+  unsigned long long h[3];
+  CU(c, cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  out->n_records = c->n_records; out->n_bases = c->n_bases;
+  out->n_windows = h[2];
+  out->n_distinct = h[0]; out->max_count = h[1];
+  out->table_capacity = c->use_dense ? c->dense_n : c->table.cap;
+  out->path = c->use_dense ? 1 : 0;
+  out->n_grows = c->n_grows;
+  out->kernel_ns = (uint64_t)(c->kernel_ms * 1e6);
+  out->h2d_bytes = c->h2d_bytes;
+  return KMG_OK;
+}
+
+namespace {
+kmg_status count_filtered(kmg_ctx *c, uint64_t min_count, uint64_t *n) {
+  CU(c, cudaStreamSynchronize(c->copy_stream));
+  CU(c, launch_table_stats(view_of(c), min_count, c->d_stats, c->stream));
+  unsigned long long h[3];
+  CU(c, cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  *n = h[0];
+  return KMG_OK;
+}
+}  // namespace
+
+KMG_EXPORT kmg_status kmg_export_counts_device(kmg_ctx *c, uint64_t min_count, int sorted, uint64_t *d_keys, uint64_t *d_counts,
+                                               uint64_t cap, uint64_t *n_out) {
+  if (!c || !n_out) return KMG_ERR_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  uint64_t n = 0;
+  kmg_status s = count_filtered(c, min_count, &n);
+  if (s != KMG_OK) return s;
+  *n_out = n;
+  if (!d_keys || !d_counts) return KMG_OK;
+  if (cap < n) return fail(c, KMG_ERR_CAPACITY, "output arrays hold " + std::to_string(cap) + " entries, need " + std::to_string(n));
+  CU(c, launch_compact(view_of(c), min_count, d_keys, d_counts, cap, c->d_stats + 3, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (sorted) CU(c, sort_pairs(d_keys, d_counts, n, 2 * c->k, c->stream));
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_export_counts(kmg_ctx *c, uint64_t min_count, int sorted, uint64_t *keys, uint64_t *counts, uint64_t cap,
+                                        uint64_t *n_out) {
+  if (!c || !n_out) return KMG_ERR_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  uint64_t n = 0;
+  kmg_status s = count_filtered(c, min_count, &n);
+  if (s != KMG_OK) return s;
+  *n_out = n;
+  if (!keys || !counts) return KMG_OK;
+  if (cap < n) return fail(c, KMG_ERR_CAPACITY, "output arrays hold " + std::to_string(cap) + " entries, need " + std::to_string(n));
+  if (n == 0) return KMG_OK;
+  uint64_t *dk = nullptr, *dc = nullptr;
+  CU(c, cudaMalloc(&dk, n * 8));
+  cudaError_t e = cudaMalloc(&dc, n * 8);
+  if (e != cudaSuccess) { cudaFree(dk); return cuda_fail(c, e, "cudaMalloc(export)"); }
+  uint64_t n2 = 0;
+  s = kmg_export_counts_device(c, min_count, sorted, dk, dc, n, &n2);
+  if (s == KMG_OK) {
+    e = cudaMemcpyAsync(keys, dk, n * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts, dc, n * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) s = cuda_fail(c, e, "D2H export");
+  }
+  cudaFree(dk); cudaFree(dc);
+  return s;
+}
+
+KMG_EXPORT kmg_status kmg_histogram(kmg_ctx *c, uint64_t min_count, uint64_t *count_vals, uint64_t *freqs, uint64_t cap, uint64_t *n_out) {
+  if (!c || !n_out) return KMG_ERR_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->copy_stream));
+  kmg_status s = read_counters(c);
+  if (s != KMG_OK) return s;
+  // counts >= HIST_DENSE_BINS: at most windows / HIST_DENSE_BINS distinct keys can reach that
+  const uint64_t ov_cap = c->h_counters[CTR_WINDOWS] / HIST_DENSE_BINS + 16;
+  unsigned long long *d_bins = nullptr;
+  uint64_t *d_ov = nullptr;
+  CU(c, cudaMalloc(&d_bins, HIST_DENSE_BINS * 8));
+  cudaError_t e = cudaMalloc(&d_ov, ov_cap * 8);
+  if (e != cudaSuccess) { cudaFree(d_bins); return cuda_fail(c, e, "cudaMalloc(histogram overflow)"); }
+  std::vector<unsigned long long> bins(HIST_DENSE_BINS);
+  std::vector<uint64_t> ov;
+  unsigned long long ov_n = 0;
+  e = launch_histogram(view_of(c), min_count, d_bins, d_ov, ov_cap, c->d_stats + 4, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(bins.data(), d_bins, HIST_DENSE_BINS * 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&ov_n, c->d_stats + 4, 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess && ov_n > ov_cap) { cudaFree(d_bins); cudaFree(d_ov); return fail(c, KMG_ERR_STATE, "histogram overflow list exceeded its bound"); }
+  if (e == cudaSuccess && ov_n) { ov.resize(ov_n); e = cudaMemcpy(ov.data(), d_ov, ov_n * 8, cudaMemcpyDeviceToHost); }
+  cudaFree(d_bins); cudaFree(d_ov);
+  if (e != cudaSuccess) return cuda_fail(c, e, "histogram");
+  // assemble ascending (count, frequency) pairs: dense bins first, then the (tiny) overflow tail
+  std::sort(ov.begin(), ov.end());
+  uint64_t n = 0;
+  for (uint64_t b = 0; b < HIST_DENSE_BINS; ++b) if (bins[b]) ++n;
+  for (size_t i = 0; i < ov.size(); ++i) if (i == 0 || ov[i] != ov[i - 1]) ++n;
+  *n_out = n;
+  if (!count_vals || !freqs) return KMG_OK;
+  if (cap < n) return fail(c, KMG_ERR_CAPACITY, "histogram arrays hold " + std::to_string(cap) + " bins, need " + std::to_string(n));
+  uint64_t o = 0;
+  for (uint64_t b = 0; b < HIST_DENSE_BINS; ++b) if (bins[b]) { count_vals[o] = b; freqs[o] = bins[b]; ++o; }
+  for (size_t i = 0; i < ov.size();) {
+    size_t j = i;
+    while (j < ov.size() && ov[j] == ov[i]) ++j;
+    count_vals[o] = ov[i]; freqs[o] = j - i; ++o;
+    i = j;
+  }
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_save_kmix(kmg_ctx *c, const char *path) {
+  if (!c || !path) return KMG_ERR_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  uint64_t n = 0;
+  kmg_status s = count_filtered(c, 0, &n);
+  if (s != KMG_OK) return s;
+  uint64_t *dk = nullptr, *dc = nullptr;
+  if (n) {
+    CU(c, cudaMalloc(&dk, n * 8));
+    cudaError_t e = cudaMalloc(&dc, n * 8);
+    if (e != cudaSuccess) { cudaFree(dk); return cuda_fail(c, e, "cudaMalloc(kmix)"); }
+    uint64_t n2 = 0;
+    s = kmg_export_counts_device(c, 0, /*sorted=*/1, dk, dc, n, &n2);  // sorted => byte-reproducible files
+    if (s == KMG_ERR_OOM || s == KMG_ERR_CUDA) { cudaGetLastError(); s = kmg_export_counts_device(c, 0, 0, dk, dc, n, &n2); }
+    if (s != KMG_OK) { cudaFree(dk); cudaFree(dc); return s; }
+  }
+  FILE *f = fopen(path, "wb");
+  if (!f) { cudaFree(dk); cudaFree(dc); return fail(c, KMG_ERR_IO, std::string("cannot open ") + path + " for writing"); }
+  const Crc32 &T = crc_tables();
+  uint32_t crc = ~0u;
+  uint8_t hdr[14] = {'K', 'M', 'I', 'X', 1, (uint8_t)c->k};
+  for (int b = 0; b < 8; ++b) hdr[6 + b] = (uint8_t)(n >> (8 * b));
+  bool ok = fwrite(hdr, 1, 14, f) == 14;
+  crc = T.update(crc, hdr, 14);
+  const uint64_t CH = 1ull << 20;
+  std::vector<uint64_t> hk(CH), hc(CH), pairs(2 * CH);
+  for (uint64_t i = 0; ok && i < n; i += CH) {
+    const uint64_t m = std::min(CH, n - i);
+    cudaError_t e = cudaMemcpy(hk.data(), dk + i, m * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(hc.data(), dc + i, m * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { fclose(f); cudaFree(dk); cudaFree(dc); return cuda_fail(c, e, "D2H kmix"); }
+    for (uint64_t j = 0; j < m; ++j) { pairs[2 * j] = hk[j]; pairs[2 * j + 1] = hc[j]; }  // x86-64/aarch64: little endian
+    ok = fwrite(pairs.data(), 16, m, f) == m;
+    crc = T.update(crc, reinterpret_cast<const uint8_t *>(pairs.data()), m * 16);
+  }
+  crc = ~crc;
+  uint8_t tail[4] = {(uint8_t)crc, (uint8_t)(crc >> 8), (uint8_t)(crc >> 16), (uint8_t)(crc >> 24)};
+  ok = ok && fwrite(tail, 1, 4, f) == 4;
+  ok = (fclose(f) == 0) && ok;
+  cudaFree(dk); cudaFree(dc);
+  if (!ok) return fail(c, KMG_ERR_IO, std::string("short write to ") + path);
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_progress(const kmg_ctx *c, uint64_t *records, uint64_t *bases) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  if (records) *records = c->n_records;
+  if (bases) *bases = c->n_bases;
+  return KMG_OK;
+}
+
+KMG_EXPORT uint64_t kmg_kernel_launches(void) { return kernel_launches(); }
+
+KMG_EXPORT kmg_status kmg_synth_uniform_device(kmg_ctx *c, uint64_t seed, uint64_t first_base, uint64_t n, uint8_t *d_out) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  if (n) CU(c, launch_synth_uniform(seed, first_base, n, d_out, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return KMG_OK;
+}

@@ -1,0 +1,111 @@
+// Device-side building blocks shared by the sm_100a kernels of libkmerust_gpu.
+// Nothing in here is derived from the reference's code; citations name the reference
+// behaviour (paths relative to the kmerust repository) each helper must reproduce.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kmg {
+
+constexpr uint64_t EMPTY_KEY = ~0ull;  // never a canonical key for any k (k<32: bits above 2k set;
+                                       // k=32: TTT..T, whose reverse complement AAA..A = 0 is smaller)
+
+// ---- packed-stream layout -------------------------------------------------------------------
+// bases : u64 words, base j at word j/32, shift 62-2*(j%32)  (MSB first == src/kmer.rs:467-471 fold)
+// valid : u32 words, base j at word j/32, bit 31-(j%32)
+// start : same layout as valid; 1 on the first base of each record
+// All three arrays carry a zero-filled lead-in so that "word -1" can be read unconditionally and
+// TMA bulk copies stay 16-byte aligned.
+constexpr int LEAD_BASE_WORDS = 2;  // 16 bytes
+constexpr int LEAD_MASK_WORDS = 4;  // 16 bytes
+constexpr int TILE_WORDS = 1024;    // 32768 bases per tile
+constexpr int SCAN_THREADS = 256;
+constexpr int WORDS_PER_THREAD = TILE_WORDS / SCAN_THREADS;
+
+__host__ __device__ __forceinline__ uint64_t kmer_mask(int k) { return k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull); }
+
+// murmur3 finaliser: bijective 64-bit mix.  Low bits pick the table slot, high bits the owner shard.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+// owner shard / partition of a canonical key among n parts (uses the HIGH half of the mix, the
+// table slot uses a multiply-shift of the full mix, so the two are independent enough).
+__host__ __device__ __forceinline__ uint32_t part_of(uint64_t key, uint32_t n_parts) {
+  uint64_t h = mix64(key) >> 32;
+  return (uint32_t)((h * (uint64_t)n_parts) >> 32);
+}
+
+#ifdef __CUDACC__
+// slot in [0, cap) for arbitrary (not power-of-two) capacities: multiply-shift range reduction.
+__device__ __forceinline__ uint64_t slot_of(uint64_t key, uint64_t cap) {
+  return __umul64hi(mix64(key) * 0x9E3779B97F4A7C15ull, cap);
+}
+
+// reverse complement of the low 2k bits of x (complement = 3 - code, src/kmer.rs:36-47).
+__device__ __forceinline__ uint64_t revcomp(uint64_t x, int k) {
+  uint64_t y = __brevll(~x);                                                  // reverses bits, swaps within pairs
+  y = ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);  // undo the in-pair swap
+  return y >> (64 - 2 * k);
+}
+
+// bit b of the result is set iff bits b .. b+len-1 of v are all set (len in 1..32, bits above 63 read as 0).
+__device__ __forceinline__ uint64_t run_and(uint64_t v, int len) {
+  uint64_t r = v;
+  int n = 1;
+  for (int bit = 30 - __clz(len); bit >= 0; --bit) {  // bits of len below its top bit
+    r &= r >> n; n <<= 1;
+    if ((len >> bit) & 1) { r &= v >> n; n += 1; }
+  }
+  return r;
+}
+
+// 32-bit mask (bit 31-e <-> position e of the current word) of windows ENDING at position e that
+// may be counted: all k bases valid (ACGT + quality, src/run.rs:543-560) and no record start
+// strictly inside the window (records are processed separately, src/run.rs:500-503).
+__device__ __forceinline__ uint32_t window_ok_mask(uint32_t vprev, uint32_t vcur, uint32_t sprev, uint32_t scur,
+                                                   int k, bool has_start) {
+  uint64_t v = ((uint64_t)vprev << 32) | vcur;
+  uint64_t ok = run_and(v, k);
+  if (has_start && k > 1) {
+    uint64_t ns = ~(((uint64_t)sprev << 32) | scur);
+    ok &= run_and(ns, k - 1);
+  }
+  return (uint32_t)ok;
+}
+
+// ---- TMA (bulk async copy) + mbarrier, raw PTX -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace kmg

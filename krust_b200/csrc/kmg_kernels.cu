@@ -1,0 +1,712 @@
+// sm_100a kernels of libkmerust_gpu: ingest (ASCII -> 2-bit + masks), tile scan with rolling
+// forward / reverse-complement words, open-addressing HBM table upsert, direct-indexed 4^k
+// counters, owner bucketing, compaction, count-of-counts histogram.
+//
+// Reference behaviour reproduced (paths relative to the kmerust repository):
+//   src/kmer.rs:21-47, :266-286, :304-312, :348-390   validate / pack / canonical
+//   src/run.rs:526-571                                  window predicate + upsert
+//   src/run.rs:447-450, src/histogram.rs:88-116         min-count filter, histogram
+// All arithmetic is integer; results are bit-exact by construction (tests/ prove it against oracle/).
+#include "kmg_kernels.h"
+
+#include <atomic>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kmg_device.cuh"
+
+namespace kmg {
+
+// =================================================================================================
+// K8 ingest: ASCII (+ Phred+33 quality) -> packed bases + valid mask.  One thread per 32-base word.
+// =================================================================================================
+__device__ __forceinline__ void ingest4(uint32_t x, uint32_t q, bool use_q, uint32_t thr4, uint64_t &bases, uint32_t &valid) {
+  // x: 4 ASCII bytes, byte 0 = earliest base.  code = ((b>>1)^(b>>2))&3 maps A/a,C/c,G/g,T/t -> 0,1,2,3
+  // (src/kmer.rs:21-32); validity = upper-cased byte is one of A C G T (src/kmer.rs:270-277).
+  uint32_t c = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+  uint32_t u = x & 0xDFDFDFDFu;
+  uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+  if (use_q) ok &= __vcmpgeu4(q, thr4);  // q >= saturating_add(min_quality, 33)  (src/run.rs:538, :544)
+  uint32_t packed8 = (c * 0x40100401u) >> 24;                    // c0<<6 | c1<<4 | c2<<2 | c3
+  uint32_t nib = ((ok & 0x01010101u) * 0x80402010u) >> 28;        // v0<<3 | v1<<2 | v2<<1 | v3
+  bases = (bases << 8) | packed8;
+  valid = (valid << 4) | nib;
+}
+
+__global__ void __launch_bounds__(256) ingest_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
+                                                     uint64_t n_bytes, uint32_t thr, uint64_t n_words_total,
+                                                     uint64_t *__restrict__ bases_out, uint32_t *__restrict__ valid_out) {
+  const bool use_q = qual != nullptr;
+  const uint32_t thr4 = thr * 0x01010101u;
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words_total;
+       w += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t b0 = w * 32;
+    uint64_t bases = 0;
+    uint32_t valid = 0;
+    if (b0 + 32 <= n_bytes) {
+      const uint4 *p = reinterpret_cast<const uint4 *>(seq + b0);
+      uint4 s0 = __ldg(p), s1 = __ldg(p + 1);
+      uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+      if (use_q) {
+        const uint4 *qp = reinterpret_cast<const uint4 *>(qual + b0);
+        q0 = __ldg(qp); q1 = __ldg(qp + 1);
+      }
+      ingest4(s0.x, q0.x, use_q, thr4, bases, valid); ingest4(s0.y, q0.y, use_q, thr4, bases, valid);
+      ingest4(s0.z, q0.z, use_q, thr4, bases, valid); ingest4(s0.w, q0.w, use_q, thr4, bases, valid);
+      ingest4(s1.x, q1.x, use_q, thr4, bases, valid); ingest4(s1.y, q1.y, use_q, thr4, bases, valid);
+      ingest4(s1.z, q1.z, use_q, thr4, bases, valid); ingest4(s1.w, q1.w, use_q, thr4, bases, valid);
+    } else if (b0 < n_bytes) {
+      for (int g = 0; g < 8; ++g) {
+        uint32_t x = 0, q = 0;
+        for (int j = 0; j < 4; ++j) {
+          uint64_t i = b0 + g * 4 + j;
+          if (i < n_bytes) {
+            x |= (uint32_t)seq[i] << (8 * j);
+            if (use_q) q |= (uint32_t)qual[i] << (8 * j);
+          }
+        }
+        ingest4(x, q, use_q, thr4, bases, valid);  // bytes past the end are 0 -> invalid
+      }
+    }
+    bases_out[LEAD_BASE_WORDS + w] = bases;
+    valid_out[LEAD_MASK_WORDS + w] = valid;
+  }
+}
+
+__global__ void start_bits_kernel(const uint64_t *__restrict__ offsets, uint64_t n_records, uint64_t base_offset,
+                                  uint64_t n_bytes, uint32_t *__restrict__ start_out) {
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_records;
+       r += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t o = offsets[r];
+    if (o < base_offset) continue;
+    o -= base_offset;
+    if (o == 0 || o >= n_bytes) continue;  // position 0 has no predecessor; trailing empty records
+    atomicOr(&start_out[LEAD_MASK_WORDS + (o >> 5)], 1u << (31 - (uint32_t)(o & 31)));
+  }
+}
+
+__global__ void synth_uniform_kernel(uint64_t seed, uint64_t first_base, uint64_t n, uint8_t *__restrict__ out) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t g = first_base + i;
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + (g >> 5);
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    out[i] = "ACGT"[(x >> (62 - 2 * (g & 31))) & 3];
+  }
+}
+
+// =================================================================================================
+// Tile pipeline: double-buffered TMA bulk copies of the packed stream into shared memory.
+// =================================================================================================
+struct TileSmem {
+  uint64_t bases[TILE_WORDS + LEAD_BASE_WORDS];
+  uint32_t valid[TILE_WORDS + LEAD_MASK_WORDS];
+  uint32_t start[TILE_WORDS + LEAD_MASK_WORDS];
+};
+constexpr uint32_t TILE_BASE_BYTES = (TILE_WORDS + LEAD_BASE_WORDS) * 8;
+constexpr uint32_t TILE_MASK_BYTES = (TILE_WORDS + LEAD_MASK_WORDS) * 4;
+
+__device__ __forceinline__ void issue_tile(const ScanInput &in, TileSmem *dst, uint64_t *bar, uint64_t tile) {
+  // arrays carry LEAD_* zero words, so word index (tile*TILE_WORDS - lead) is array index tile*TILE_WORDS
+  const uint64_t w0 = tile * TILE_WORDS;
+  uint32_t bytes = TILE_BASE_BYTES + TILE_MASK_BYTES + (in.start ? TILE_MASK_BYTES : 0);
+  mbar_expect_tx(bar, bytes);
+  tma_load_1d(dst->bases, in.bases + w0, TILE_BASE_BYTES, bar);
+  tma_load_1d(dst->valid, in.valid + w0, TILE_MASK_BYTES, bar);
+  if (in.start) tma_load_1d(dst->start, in.start + w0, TILE_MASK_BYTES, bar);
+}
+
+// Walk the 32 windows ending in word `i` of the staged tile, handing groups of G canonical keys to
+// the emitter.  fwd/rc are rolled one base at a time; canonical = min(fwd, rc) which equals the
+// reference's bytewise lexicographic choice (src/kmer.rs:348-365) because A<C<G<T in both orders.
+template <int G, class Emit>
+__device__ __forceinline__ uint32_t scan_word(const TileSmem *ts, int i, int k, bool has_start, Emit &emit) {
+  const uint64_t prev = ts->bases[LEAD_BASE_WORDS + i - 1];
+  const uint64_t cur = ts->bases[LEAD_BASE_WORDS + i];
+  const uint32_t vprev = ts->valid[LEAD_MASK_WORDS + i - 1], vcur = ts->valid[LEAD_MASK_WORDS + i];
+  uint32_t sprev = 0, scur = 0;
+  if (has_start) { sprev = ts->start[LEAD_MASK_WORDS + i - 1]; scur = ts->start[LEAD_MASK_WORDS + i]; }
+  const uint32_t ok = window_ok_mask(vprev, vcur, sprev, scur, k, has_start);
+  if (ok == 0) return 0;
+  const uint64_t mask = kmer_mask(k);
+  const int rc_shift = 2 * (k - 1);
+  uint64_t fwd = prev & mask;
+  uint64_t rc = revcomp(fwd, k);
+#pragma unroll
+  for (int g = 0; g < 32 / G; ++g) {
+    uint64_t key[G];
+    uint32_t okg = 0;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int e = g * G + j;
+      const uint64_t c = (cur >> (62 - 2 * e)) & 3ull;
+      fwd = ((fwd << 2) | c) & mask;
+      rc = (rc >> 2) | ((3ull - c) << rc_shift);
+      key[j] = fwd < rc ? fwd : rc;
+      okg |= ((ok >> (31 - e)) & 1u) << j;
+    }
+    if (okg) emit.template group<G>(key, okg);
+  }
+  return __popc(ok);
+}
+
+// In-thread pre-aggregation: adjacent (distance 1 and 2) equal keys inside a group are merged, which
+// collapses homopolymer and dinucleotide-repeat runs before they reach the atomics.
+template <int G>
+__device__ __forceinline__ void preaggregate(const uint64_t (&key)[G], uint32_t okg, uint32_t (&cnt)[G], bool enable) {
+#pragma unroll
+  for (int j = 0; j < G; ++j) cnt[j] = (okg >> j) & 1u;
+  if (!enable) return;
+#pragma unroll
+  for (int j = 1; j < G; ++j)
+    if (cnt[j] && cnt[j - 1] && key[j] == key[j - 1]) { cnt[j] += cnt[j - 1]; cnt[j - 1] = 0; }
+#pragma unroll
+  for (int j = 2; j < G; ++j)
+    if (cnt[j] && cnt[j - 2] && key[j] == key[j - 2]) { cnt[j] += cnt[j - 2]; cnt[j - 2] = 0; }
+}
+
+// ---- K2: open-addressing table upsert (AoS 16-byte slots: key, count) ---------------------------------
+__device__ __forceinline__ void table_add_slow(HashTable t, uint64_t key, uint64_t add, uint64_t slot, uint32_t &new_keys,
+                                               unsigned long long *full_flag) {
+  for (uint64_t probe = 1; probe < t.cap; ++probe) {
+    slot = slot + 1 == t.cap ? 0 : slot + 1;
+    unsigned long long *kp = reinterpret_cast<unsigned long long *>(t.slots + 2 * slot);
+    uint64_t cur = *reinterpret_cast<volatile unsigned long long *>(kp);
+    if (cur == EMPTY_KEY) cur = atomicCAS(kp, EMPTY_KEY, key);
+    if (cur == EMPTY_KEY) { ++new_keys; atomicAdd(kp + 1, add); return; }
+    if (cur == key) { atomicAdd(kp + 1, add); return; }
+  }
+  atomicExch(full_flag, 1ull);
+}
+
+__device__ __forceinline__ void table_add(HashTable t, uint64_t key, uint64_t add, uint32_t &new_keys,
+                                          unsigned long long *full_flag) {
+  uint64_t slot = slot_of(key, t.cap);
+  unsigned long long *kp = reinterpret_cast<unsigned long long *>(t.slots + 2 * slot);
+  uint64_t old = atomicCAS(kp, EMPTY_KEY, key);
+  if (old == EMPTY_KEY) { ++new_keys; atomicAdd(kp + 1, add); }
+  else if (old == key) atomicAdd(kp + 1, add);
+  else table_add_slow(t, key, add, slot, new_keys, full_flag);
+}
+
+struct HashEmit {
+  HashTable t;
+  unsigned long long *full_flag;
+  uint32_t new_keys;
+  bool preagg;
+  template <int G>
+  __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
+    uint32_t cnt[G];
+    preaggregate<G>(key, okg, cnt, preagg);
+    uint64_t slot[G], old[G];
+    // phase 1: all first probes in flight together (memory-level parallelism G per thread)
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      old[j] = 0;
+      slot[j] = slot_of(key[j], t.cap);
+      if (cnt[j]) old[j] = atomicCAS(reinterpret_cast<unsigned long long *>(t.slots + 2 * slot[j]), EMPTY_KEY, key[j]);
+    }
+    // phase 2: resolve
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      if (!cnt[j]) continue;
+      unsigned long long *cp = reinterpret_cast<unsigned long long *>(t.slots + 2 * slot[j] + 1);
+      if (old[j] == EMPTY_KEY) { ++new_keys; atomicAdd(cp, (unsigned long long)cnt[j]); }
+      else if (old[j] == key[j]) atomicAdd(cp, (unsigned long long)cnt[j]);
+      else table_add_slow(t, key[j], cnt[j], slot[j], new_keys, full_flag);
+    }
+  }
+};
+
+// ---- K3: direct-indexed counters ----------------------------------------------------------------------
+struct DenseGlobalEmit {
+  unsigned long long *dense;
+  bool preagg;
+  template <int G>
+  __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
+    uint32_t cnt[G];
+    preaggregate<G>(key, okg, cnt, preagg);
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+      if (cnt[j]) atomicAdd(dense + key[j], (unsigned long long)cnt[j]);
+  }
+};
+struct DenseSmemEmit {
+  uint32_t *hist;  // 4^k u32 counters in shared memory
+  template <int G>
+  __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+      if ((okg >> j) & 1u) atomicAdd(hist + (uint32_t)key[j], 1u);
+  }
+};
+
+__device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+enum ScanMode { MODE_HASH = 0, MODE_DENSE_GLOBAL = 1, MODE_DENSE_SMEM = 2 };
+
+template <int MODE, int G>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_count_kernel(ScanInput in, HashTable table, unsigned long long *dense,
+                                                                  unsigned long long *counters, uint32_t flags) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[2];
+  uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw + 2 * sizeof(TileSmem));
+  const int tid = threadIdx.x;
+  const bool has_start = in.start != nullptr;
+  const bool preagg = !(flags & 4u);
+
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  if (MODE == MODE_DENSE_SMEM) {
+    const uint32_t nbins = 1u << (2 * in.k);
+    for (uint32_t b = tid; b < nbins; b += SCAN_THREADS) hist[b] = 0;
+  }
+  __syncthreads();
+
+  uint64_t windows = 0;
+  uint32_t new_keys = 0;
+  uint64_t tile = blockIdx.x;
+  int stage = 0;
+  uint32_t phase0 = 0, phase1 = 0;
+  if (tile < in.n_tiles && tid == 0) issue_tile(in, &stages[0], &bars[0], tile);
+  for (; tile < in.n_tiles; tile += gridDim.x) {
+    const uint64_t next = tile + gridDim.x;
+    if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
+    if (stage == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+    const TileSmem *ts = &stages[stage];
+#pragma unroll 1
+    for (int r = 0; r < WORDS_PER_THREAD; ++r) {
+      const int i = r * SCAN_THREADS + tid;
+      if (MODE == MODE_HASH) {
+        HashEmit e{table, counters + CTR_FULL, 0, preagg};
+        windows += scan_word<G>(ts, i, in.k, has_start, e);
+        new_keys += e.new_keys;
+      } else if (MODE == MODE_DENSE_GLOBAL) {
+        DenseGlobalEmit e{dense, preagg};
+        windows += scan_word<G>(ts, i, in.k, has_start, e);
+      } else {
+        DenseSmemEmit e{hist};
+        windows += scan_word<G>(ts, i, in.k, has_start, e);
+      }
+    }
+    __syncthreads();  // everyone is done with this stage before it is refilled
+    stage ^= 1;
+  }
+
+  if (MODE == MODE_DENSE_SMEM) {
+    const uint32_t nbins = 1u << (2 * in.k);
+    for (uint32_t b = tid; b < nbins; b += SCAN_THREADS) {
+      uint32_t c = hist[b];
+      if (c) atomicAdd(dense + b, (unsigned long long)c);
+    }
+  }
+  windows = warp_sum(windows);
+  uint64_t nk = warp_sum(new_keys);
+  if ((tid & 31) == 0) {
+    if (windows) atomicAdd(counters + CTR_WINDOWS, (unsigned long long)windows);
+    if (nk) atomicAdd(counters + CTR_DISTINCT, (unsigned long long)nk);
+  }
+}
+
+// ---- K4: owner / partition bucketing ------------------------------------------------------------------
+struct PartCountEmit {
+  uint32_t *hist;
+  uint32_t n_parts;
+  template <int G>
+  __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+      if ((okg >> j) & 1u) atomicAdd(hist + part_of(key[j], n_parts), 1u);
+  }
+};
+struct PartScatterEmit {
+  uint32_t *cursor;            // smem: running offset inside this tile's reservation
+  const uint64_t *tile_base;   // smem: global index where this tile's keys of partition p start
+  uint64_t *out;
+  uint32_t n_parts;
+  template <int G>
+  __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+      if ((okg >> j) & 1u) {
+        const uint32_t p = part_of(key[j], n_parts);
+        const uint32_t o = atomicAdd(cursor + p, 1u);
+        out[tile_base[p] + o] = key[j];
+      }
+  }
+};
+
+// pass 1 (SCATTER == false): per-partition totals into part_counts[].
+// pass 2 (SCATTER == true) : part_cursor[] must hold the exclusive prefix of part_counts; each tile
+// histograms its keys in shared memory, reserves one contiguous range per partition with a single
+// global atomic, then re-derives the keys and writes them into that range.
+template <bool SCATTER>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_partition_kernel(ScanInput in, uint32_t n_parts,
+                                                                      unsigned long long *part_counts,
+                                                                      unsigned long long *part_cursor, uint64_t *out,
+                                                                      unsigned long long *counters) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[2];
+  uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw + 2 * sizeof(TileSmem));
+  uint64_t *tile_base = reinterpret_cast<uint64_t *>(hist + n_parts + (n_parts & 1));
+  const int tid = threadIdx.x;
+  const bool has_start = in.start != nullptr;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) hist[p] = 0;
+  __syncthreads();
+
+  uint64_t windows = 0;
+  uint64_t tile = blockIdx.x;
+  int stage = 0;
+  uint32_t phase0 = 0, phase1 = 0;
+  if (tile < in.n_tiles && tid == 0) issue_tile(in, &stages[0], &bars[0], tile);
+  for (; tile < in.n_tiles; tile += gridDim.x) {
+    const uint64_t next = tile + gridDim.x;
+    if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
+    if (stage == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+    const TileSmem *ts = &stages[stage];
+    {
+      PartCountEmit e{hist, n_parts};
+#pragma unroll 1
+      for (int r = 0; r < WORDS_PER_THREAD; ++r) windows += scan_word<8>(ts, r * SCAN_THREADS + tid, in.k, has_start, e);
+    }
+    if (SCATTER) {
+      __syncthreads();
+      for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) {
+        const uint32_t c = hist[p];
+        tile_base[p] = c ? atomicAdd(part_cursor + p, (unsigned long long)c) : 0;
+        hist[p] = 0;
+      }
+      __syncthreads();
+      PartScatterEmit e{hist, tile_base, out, n_parts};
+#pragma unroll 1
+      for (int r = 0; r < WORDS_PER_THREAD; ++r) scan_word<8>(ts, r * SCAN_THREADS + tid, in.k, has_start, e);
+      __syncthreads();
+      for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) hist[p] = 0;
+    }
+    __syncthreads();
+    stage ^= 1;
+  }
+  if (!SCATTER) {
+    for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) {
+      const uint32_t c = hist[p];
+      if (c) atomicAdd(part_counts + p, (unsigned long long)c);
+    }
+    windows = warp_sum(windows);
+    if ((tid & 31) == 0 && windows) atomicAdd(counters + CTR_WINDOWS, (unsigned long long)windows);
+  }
+}
+
+// =================================================================================================
+// Table maintenance, weighted inserts, compaction (K5), histogram (K6)
+// =================================================================================================
+__global__ void table_init_kernel(uint64_t *slots, uint64_t cap) {
+  ulonglong2 *p = reinterpret_cast<ulonglong2 *>(slots);
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
+    p[i] = make_ulonglong2(EMPTY_KEY, 0ull);
+}
+
+__global__ void insert_keys_kernel(HashTable t, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ counts,
+                                   uint64_t n, unsigned long long *counters) {
+  uint32_t new_keys = 0;
+  uint64_t windows = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t c = counts ? counts[i] : 1ull;
+    if (c == 0) continue;
+    table_add(t, keys[i], c, new_keys, counters + CTR_FULL);
+    windows += c;
+  }
+  windows = warp_sum(windows);
+  uint64_t nk = warp_sum(new_keys);
+  if ((threadIdx.x & 31) == 0) {
+    if (windows) atomicAdd(counters + CTR_WINDOWS, (unsigned long long)windows);
+    if (nk) atomicAdd(counters + CTR_DISTINCT, (unsigned long long)nk);
+  }
+}
+
+__global__ void insert_keys_dense_kernel(unsigned long long *dense, const uint64_t *__restrict__ keys,
+                                         const uint64_t *__restrict__ counts, uint64_t n, unsigned long long *counters) {
+  uint64_t windows = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t c = counts ? counts[i] : 1ull;
+    if (c == 0) continue;
+    atomicAdd(dense + keys[i], (unsigned long long)c);
+    windows += c;
+  }
+  windows = warp_sum(windows);
+  if ((threadIdx.x & 31) == 0 && windows) atomicAdd(counters + CTR_WINDOWS, (unsigned long long)windows);
+}
+
+// re-insert every occupied slot of `from` into `to` (grow / rehash)
+__global__ void rehash_kernel(HashTable from, HashTable to, unsigned long long *counters) {
+  uint32_t new_keys = 0;
+  const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(from.slots);
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < from.cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    ulonglong2 s = p[i];
+    if (s.x != EMPTY_KEY) table_add(to, s.x, s.y, new_keys, counters + CTR_FULL);
+  }
+}
+
+// A "view" unifies both table kinds for the read-side kernels: entry i is (key, count); empty if count == 0.
+__device__ __forceinline__ bool view_get(const TableView &v, uint64_t i, uint64_t &key, uint64_t &count) {
+  if (v.dense) { key = i; count = v.dense[i]; return count != 0; }
+  ulonglong2 s = reinterpret_cast<const ulonglong2 *>(v.slots)[i];
+  key = s.x; count = s.y;
+  return s.x != EMPTY_KEY;
+}
+
+// stats[0] += #entries with count >= min_count ; stats[1] = max count ; stats[2] += sum of counts (all entries)
+__global__ void table_stats_kernel(TableView v, uint64_t min_count, unsigned long long *stats) {
+  uint64_t n = 0, mx = 0, sum = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < v.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t key, c;
+    if (view_get(v, i, key, c)) {
+      sum += c;
+      if (c >= min_count) ++n;
+      mx = c > mx ? c : mx;
+    }
+  }
+  n = warp_sum(n); sum = warp_sum(sum);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { uint64_t other = __shfl_xor_sync(0xffffffffu, mx, o); mx = other > mx ? other : mx; }
+  if ((threadIdx.x & 31) == 0) {
+    if (n) atomicAdd(stats + 0, (unsigned long long)n);
+    if (mx) atomicMax(stats + 1, (unsigned long long)mx);
+    if (sum) atomicAdd(stats + 2, (unsigned long long)sum);
+  }
+}
+
+// K5: stream-compact entries with count >= min_count into (keys_out, counts_out).  Warp-aggregated
+// reservation: one atomic per warp per 32 entries.
+__global__ void compact_kernel(TableView v, uint64_t min_count, uint64_t *__restrict__ keys_out,
+                               uint64_t *__restrict__ counts_out, uint64_t cap_out, unsigned long long *cursor) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t n_round = (v.n + 31) & ~31ull;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    uint64_t key = 0, c = 0;
+    bool take = i < v.n && view_get(v, i, key, c) && c >= min_count;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, take);
+    if (ballot == 0) continue;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) {
+      const uint64_t o = base + __popc(ballot & ((1u << lane) - 1u));
+      if (o < cap_out) { keys_out[o] = key; counts_out[o] = c; }
+    }
+  }
+}
+
+// K6: count-of-counts.  Counts below HIST_DENSE_BINS go to dense bins (the first HIST_SMEM_BINS of them
+// privatised in shared memory); larger counts are appended to an overflow list (at most
+// total_windows / HIST_DENSE_BINS entries can ever land there).
+__global__ void __launch_bounds__(256) histogram_kernel(TableView v, uint64_t min_count, unsigned long long *bins,
+                                                        uint64_t *overflow, uint64_t overflow_cap,
+                                                        unsigned long long *overflow_n) {
+  __shared__ uint32_t sh[HIST_SMEM_BINS];
+  for (int b = threadIdx.x; b < HIST_SMEM_BINS; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < v.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t key, c;
+    if (!view_get(v, i, key, c) || c < min_count) continue;
+    if (c < HIST_SMEM_BINS) atomicAdd(&sh[c], 1u);
+    else if (c < HIST_DENSE_BINS) atomicAdd(bins + c, 1ull);
+    else {
+      unsigned long long o = atomicAdd(overflow_n, 1ull);
+      if (o < overflow_cap) overflow[o] = c;
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < HIST_SMEM_BINS; b += blockDim.x)
+    if (sh[b]) atomicAdd(bins + b, (unsigned long long)sh[b]);
+}
+
+// =================================================================================================
+// Host-side launch wrappers
+// =================================================================================================
+static std::atomic<uint64_t> g_launches{0};
+uint64_t kernel_launches() { return g_launches.load(std::memory_order_relaxed); }
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+static inline unsigned grid_for(uint64_t n_items, int threads, int ctas_per_sm) {
+  uint64_t want = (n_items + threads - 1) / threads;
+  uint64_t cap = (uint64_t)num_sms() * ctas_per_sm;
+  if (want < 1) want = 1;
+  return (unsigned)(want < cap ? want : cap);
+}
+
+cudaError_t launch_ingest(const uint8_t *d_seq, const uint8_t *d_qual, uint64_t n_bytes, uint32_t thr, uint64_t n_words_total,
+                          uint64_t *d_bases, uint32_t *d_valid, cudaStream_t s) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  ingest_kernel<<<grid_for(n_words_total, 256, 8), 256, 0, s>>>(d_seq, d_qual, n_bytes, thr, n_words_total, d_bases, d_valid);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_start_bits(const uint64_t *d_offsets, uint64_t n_records, uint64_t base_offset, uint64_t n_bytes,
+                              uint64_t n_words_total, uint32_t *d_start, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(d_start, 0, (LEAD_MASK_WORDS + n_words_total) * sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  start_bits_kernel<<<grid_for(n_records, 256, 8), 256, 0, s>>>(d_offsets, n_records, base_offset, n_bytes, d_start);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_synth_uniform(uint64_t seed, uint64_t first_base, uint64_t n, uint8_t *d_out, cudaStream_t s) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  synth_uniform_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(seed, first_base, n, d_out);
+  return cudaGetLastError();
+}
+
+template <class K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+cudaError_t launch_scan_hash(const ScanInput &in, HashTable t, unsigned long long *counters, uint32_t flags, cudaStream_t s) {
+  const size_t smem = 2 * sizeof(TileSmem);
+  auto kern = scan_count_kernel<MODE_HASH, 8>;
+  cudaError_t e = set_smem(kern, smem);
+  if (e != cudaSuccess) return e;
+  unsigned grid = (unsigned)(in.n_tiles < (uint64_t)num_sms() * SCAN_CTAS_PER_SM ? in.n_tiles : (uint64_t)num_sms() * SCAN_CTAS_PER_SM);
+  if (grid == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  kern<<<grid, SCAN_THREADS, smem, s>>>(in, t, nullptr, counters, flags);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, unsigned long long *counters, uint32_t flags,
+                              cudaStream_t s) {
+  unsigned grid = (unsigned)(in.n_tiles < (uint64_t)num_sms() * SCAN_CTAS_PER_SM ? in.n_tiles : (uint64_t)num_sms() * SCAN_CTAS_PER_SM);
+  if (grid == 0) return cudaSuccess;
+  HashTable none{nullptr, 0};
+  if (in.k <= DENSE_SMEM_MAX_K) {
+    const size_t smem = 2 * sizeof(TileSmem) + (sizeof(uint32_t) << (2 * in.k));
+    auto kern = scan_count_kernel<MODE_DENSE_SMEM, 8>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    kern<<<grid, SCAN_THREADS, smem, s>>>(in, none, dense, counters, flags);
+  } else {
+    const size_t smem = 2 * sizeof(TileSmem);
+    auto kern = scan_count_kernel<MODE_DENSE_GLOBAL, 8>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    kern<<<grid, SCAN_THREADS, smem, s>>>(in, none, dense, counters, flags);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool scatter, unsigned long long *part_counts,
+                                  unsigned long long *part_cursor, uint64_t *out, unsigned long long *counters, cudaStream_t s) {
+  unsigned grid = (unsigned)(in.n_tiles < (uint64_t)num_sms() * SCAN_CTAS_PER_SM ? in.n_tiles : (uint64_t)num_sms() * SCAN_CTAS_PER_SM);
+  if (grid == 0) return cudaSuccess;
+  const size_t smem = 2 * sizeof(TileSmem) + (n_parts + (n_parts & 1)) * sizeof(uint32_t) + n_parts * sizeof(uint64_t);
+  cudaError_t e;
+  if (scatter) {
+    auto kern = scan_partition_kernel<true>;
+    if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    kern<<<grid, SCAN_THREADS, smem, s>>>(in, n_parts, part_counts, part_cursor, out, counters);
+  } else {
+    auto kern = scan_partition_kernel<false>;
+    if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    kern<<<grid, SCAN_THREADS, smem, s>>>(in, n_parts, part_counts, part_cursor, out, counters);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_table_init(HashTable t, cudaStream_t s) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  table_init_kernel<<<grid_for(t.cap, 256, 8), 256, 0, s>>>(t.slots, t.cap);
+  return cudaGetLastError();
+}
+cudaError_t launch_insert_keys(HashTable t, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n,
+                               unsigned long long *counters, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  insert_keys_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(t, d_keys, d_counts, n, counters);
+  return cudaGetLastError();
+}
+cudaError_t launch_insert_keys_dense(unsigned long long *dense, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n,
+                                     unsigned long long *counters, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  insert_keys_dense_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(dense, d_keys, d_counts, n, counters);
+  return cudaGetLastError();
+}
+cudaError_t launch_rehash(HashTable from, HashTable to, unsigned long long *counters, cudaStream_t s) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  rehash_kernel<<<grid_for(from.cap, 256, 8), 256, 0, s>>>(from, to, counters);
+  return cudaGetLastError();
+}
+cudaError_t launch_table_stats(const TableView &v, uint64_t min_count, unsigned long long *d_stats3, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(d_stats3, 0, 3 * sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  if (v.n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  table_stats_kernel<<<grid_for(v.n, 256, 8), 256, 0, s>>>(v, min_count, d_stats3);
+  return cudaGetLastError();
+}
+cudaError_t launch_compact(const TableView &v, uint64_t min_count, uint64_t *d_keys, uint64_t *d_counts, uint64_t cap_out,
+                           unsigned long long *d_cursor, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  if (v.n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  compact_kernel<<<grid_for(v.n, 256, 8), 256, 0, s>>>(v, min_count, d_keys, d_counts, cap_out, d_cursor);
+  return cudaGetLastError();
+}
+cudaError_t launch_histogram(const TableView &v, uint64_t min_count, unsigned long long *d_bins, uint64_t *d_overflow,
+                             uint64_t overflow_cap, unsigned long long *d_overflow_n, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(d_bins, 0, HIST_DENSE_BINS * sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(d_overflow_n, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
+  if (v.n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  histogram_kernel<<<grid_for(v.n, 256, 4), 256, 0, s>>>(v, min_count, d_bins, d_overflow, overflow_cap, d_overflow_n);
+  return cudaGetLastError();
+}
+
+// K7: ascending key order == lexicographic order of the unpacked strings (A<C<G<T <-> 0<1<2<3).
+// Library radix sort (CUB, ships with the CUDA toolkit) on the already-compacted pairs; not on the
+// counting hot path.
+cudaError_t sort_pairs(uint64_t *d_keys, uint64_t *d_counts, uint64_t n, int key_bits, cudaStream_t s) {
+  if (n < 2) return cudaSuccess;
+  uint64_t *alt_k = nullptr, *alt_c = nullptr;
+  void *tmp = nullptr;
+  size_t tmp_bytes = 0;
+  cudaError_t e;
+  if ((e = cudaMalloc(&alt_k, n * 8)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&alt_c, n * 8)) != cudaSuccess) { cudaFree(alt_k); return e; }
+  cub::DoubleBuffer<uint64_t> kb(d_keys, alt_k), cb(d_counts, alt_c);
+  e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, cb, n, 0, key_bits, s);
+  if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kb, cb, n, 0, key_bits, s);
+  if (e == cudaSuccess && kb.Current() != d_keys) {
+    e = cudaMemcpyAsync(d_keys, kb.Current(), n * 8, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_counts, cb.Current(), n * 8, cudaMemcpyDeviceToDevice, s);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(tmp); cudaFree(alt_k); cudaFree(alt_c);
+  return e != cudaSuccess ? e : e2;
+}
+
+}  // namespace kmg

@@ -1,0 +1,159 @@
+"""Hash-sharded multi-GPU counting: one process per GPU, torch.distributed for the plumbing.
+
+The count table shards by k-mer hash: owner = kmg_owner_of(canonical key, world).
+Every rank scans its slice of the input, buckets the canonical keys by owner
+(kmg_extract_keys_device), exchanges the buckets with ONE all-to-all (NCCL over NVLink on GPUs,
+gloo in the CPU tests), and upserts what it receives into its local shard
+(kmg_insert_keys_device).  Shards are disjoint, so the global result is the concatenation of the
+shards; the histogram is the element-wise sum of the shard histograms.
+
+The reference has no distributed mode; this replaces the single shared DashMap of
+src/run.rs:489-583 by `world` disjoint tables.
+
+The engine behind a rank is duck-typed (`extract`, `insert`, `finalize`, `export`, `histogram`) so
+that the exchange logic can be exercised on CPU with gloo (tests/test_dist_gloo.py) while the
+product engine (`GpuShardEngine`) runs the CUDA kernels.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def slice_for_rank(total: int, world: int, rank: int, k: int) -> Tuple[int, int]:
+    """Byte range [a, b) of a `total`-byte stream that `rank` scans: equal cuts, each extended by the
+    k-1 halo so that every window is seen by exactly one rank (windows are assigned to the rank
+    that owns their first base)."""
+    a = total * rank // world
+    b = total * (rank + 1) // world
+    if rank + 1 < world:
+        b = min(total, b + k - 1)
+    return a, b
+
+
+def merge_histograms(parts: List[Tuple[np.ndarray, np.ndarray]]) -> Tuple[np.ndarray, np.ndarray]:
+    """Element-wise sum of (count value -> frequency) maps; ascending by count value."""
+    acc: Dict[int, int] = {}
+    for vals, freqs in parts:
+        for v, f in zip(vals.tolist(), freqs.tolist()):
+            acc[v] = acc.get(v, 0) + f
+    keys = sorted(acc)
+    return np.array(keys, dtype=np.uint64), np.array([acc[x] for x in keys], dtype=np.uint64)
+
+
+class GpuShardEngine:
+    """One rank's CUDA engine: thin adapter from torch tensors to the raw-pointer C ABI."""
+
+    def __init__(self, k: int, device: torch.device, min_quality: Optional[int] = None, expected_distinct: int = 0,
+                 flags: int = 0):
+        from .api import GpuKmerCounter
+        self.device = device
+        torch.cuda.set_device(device)
+        self.stream = torch.cuda.current_stream(device)
+        self.counter = GpuKmerCounter(k, min_quality=min_quality, expected_distinct=expected_distinct, flags=flags,
+                                      device=device.index, stream=self.stream.cuda_stream)
+        self.k = k
+
+    def count_local(self, seq: torch.Tensor, offsets: Optional[torch.Tensor] = None, qual: Optional[torch.Tensor] = None):
+        n_rec = 1 if offsets is None else offsets.numel() - 1
+        self.counter.count_device(seq.data_ptr(), seq.numel(), qual.data_ptr() if qual is not None else 0,
+                                  offsets.data_ptr() if offsets is not None else 0, n_rec)
+
+    def extract(self, seq: torch.Tensor, n_shards: int, offsets: Optional[torch.Tensor] = None,
+                qual: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, np.ndarray]:
+        """Canonical keys of every counted window, bucketed shard-major.  Returns (keys int64[n], counts[n_shards])."""
+        n_rec = 1 if offsets is None else offsets.numel() - 1
+        cap = max(int(seq.numel()), 1)
+        out = torch.empty(cap, dtype=torch.int64, device=self.device)
+        counts = self.counter.extract_keys_device(seq.data_ptr(), seq.numel(), n_shards, out.data_ptr(), cap,
+                                                  qual.data_ptr() if qual is not None else 0,
+                                                  offsets.data_ptr() if offsets is not None else 0, n_rec)
+        return out[: int(counts.sum())], counts
+
+    def insert(self, keys: torch.Tensor, counts: Optional[torch.Tensor] = None):
+        if keys.numel():
+            self.counter.insert_keys_device(keys.data_ptr(), keys.numel(), counts.data_ptr() if counts is not None else 0)
+
+    def finalize(self, want_summary: bool = True):
+        return self.counter.finalize(want_summary)
+
+    def export(self, min_count: int = 1):
+        return self.counter.export(min_count, sorted=True)
+
+    def histogram(self, min_count: int = 1):
+        return self.counter.histogram(min_count)
+
+    def reset(self):
+        self.counter.reset()
+
+    def close(self):
+        self.counter.close()
+
+
+class ShardedKmerCounter:
+    """Drives one engine per rank through scan -> bucket -> all-to-all -> local upsert."""
+
+    def __init__(self, engine, group=None):
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.sent_keys = 0
+        self.recv_keys = 0
+
+    def count(self, seq, offsets=None, qual=None):
+        """`seq` is THIS rank's slice (see slice_for_rank); offsets/qual are relative to it."""
+        if self.world == 1:
+            self.engine.count_local(seq, offsets, qual)
+            return
+        keys, send_counts = self.engine.extract(seq, self.world, offsets, qual)
+        dev = keys.device
+        send_t = torch.as_tensor(send_counts.astype(np.int64), device=dev)
+        recv_t = torch.empty_like(send_t)
+        dist.all_to_all_single(recv_t, send_t, group=self.group)  # bucket sizes
+        recv_counts = recv_t.cpu().tolist()
+        send_list = [int(x) for x in send_counts.tolist()]
+        recv = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv, keys, output_split_sizes=recv_counts, input_split_sizes=send_list, group=self.group)
+        self.sent_keys += int(sum(send_list)) - send_list[self.rank]
+        self.recv_keys += int(sum(recv_counts)) - recv_counts[self.rank]
+        self.engine.insert(recv)
+
+    def finalize(self) -> dict:
+        """Global summary: sums over shards (shards are disjoint), max of max_count."""
+        s = self.engine.finalize(True)
+        if self.world == 1:
+            return s
+        dev = getattr(self.engine, "device", torch.device("cpu"))
+        sums = torch.tensor([s["n_windows"], s["n_distinct"], s["n_records"], s["n_bases"]], dtype=torch.int64, device=dev)
+        mx = torch.tensor([s["max_count"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+        out = dict(s)
+        out["n_windows"], out["n_distinct"], out["n_records"], out["n_bases"] = [int(x) for x in sums.cpu().tolist()]
+        out["max_count"] = int(mx.item())
+        out["local"] = s
+        return out
+
+    def histogram(self, min_count: int = 1):
+        """Count-of-counts over all shards (every rank gets the merged result)."""
+        vals, freqs = self.engine.histogram(min_count)
+        if self.world == 1:
+            return vals, freqs
+        parts: List = [None] * self.world
+        dist.all_gather_object(parts, (vals, freqs), group=self.group)
+        return merge_histograms(parts)
+
+    def export_gathered(self, min_count: int = 1):
+        """All shards' (key, count) lists concatenated and key-sorted on every rank (tests / small outputs)."""
+        keys, counts = self.engine.export(min_count)
+        if self.world == 1:
+            return keys, counts
+        parts: List = [None] * self.world
+        dist.all_gather_object(parts, (keys, counts), group=self.group)
+        k = np.concatenate([p[0] for p in parts]); c = np.concatenate([p[1] for p in parts])
+        order = np.argsort(k, kind="stable")
+        return k[order], c[order]

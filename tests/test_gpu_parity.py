@@ -1,0 +1,347 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+inputs (bit-exact: integer work).  All of these need a GPU (`-m gpu`)."""
+import os
+
+import numpy as np
+import pytest
+
+import krust_b200 as kb
+from krust_b200 import _lib
+from oracle import oracle as orc
+from tests import kats
+
+pytestmark = pytest.mark.gpu
+
+FLAG_SETS = {"auto": 0, "hash": _lib.KMG_FLAG_FORCE_HASH, "hash_nopreagg": _lib.KMG_FLAG_FORCE_HASH | _lib.KMG_FLAG_NO_PREAGG}
+
+
+def gpu_count(k, records, quals=None, min_quality=None, flags=0, batch_bases=0, min_count=1, expected_distinct=0):
+    with kb.GpuKmerCounter(k, min_quality=min_quality, flags=flags, batch_bases=batch_bases,
+                           expected_distinct=expected_distinct) as c:
+        c.count_records(records, quals)
+        s = c.finalize()
+        keys, counts = c.export(min_count, sorted=True)
+        return keys, counts, s
+
+
+def assert_same(gpu, oracle):
+    gk, gc = gpu[0], gpu[1]
+    ok, oc = oracle[0], oracle[1]
+    assert len(gk) == len(ok), (len(gk), len(ok))
+    assert (gk == ok).all() and (gc == oc).all()
+
+
+@pytest.mark.parametrize("flags", list(FLAG_SETS), ids=list(FLAG_SETS))
+@pytest.mark.parametrize("kat", kats.COUNT_KATS, ids=[k[0] for k in kats.COUNT_KATS])
+def test_reference_kats_through_c_abi(kat, flags):
+    _, _, k, records, quals, q, expected = kat
+    keys, counts, s = gpu_count(k, records, quals, q, FLAG_SETS[flags])
+    got = {kb.unpack_to_string(a, k): int(b) for a, b in zip(keys.tolist(), counts.tolist())}
+    assert got == expected
+    assert s["n_windows"] == sum(expected.values()) and s["n_distinct"] == len(expected)
+    assert s["n_records"] == len(records)
+
+
+def _random_records(rng, n_rec, max_len, alphabet, min_len=0):
+    recs, quals = [], []
+    for _ in range(n_rec):
+        n = int(rng.integers(min_len, max_len))
+        recs.append(bytes(rng.choice(alphabet, size=n).tolist()))
+        quals.append(bytes((rng.integers(0, 42, size=n) + 33).astype(np.uint8).tolist()))
+    return recs, quals
+
+
+@pytest.mark.parametrize("flags", ["auto", "hash"])
+def test_randomised_differential_all_k(flags):
+    """Random records with N / IUPAC / blanks / lower case, quality thresholds, every k in 1..32."""
+    rng = np.random.default_rng(77)
+    alphabet = list(b"ACGT" * 12 + b"acgtNnRY -")
+    for k in range(1, 33):
+        recs, quals = _random_records(rng, int(rng.integers(1, 40)), 400, alphabet)
+        q = [None, 0, 19, 20, 30, 93, 250][k % 7]
+        use_qual = k % 3 != 0
+        oracle = orc.count_records(k, recs, quals if use_qual else None, q, mode="literal")
+        gpu = gpu_count(k, recs, quals if use_qual else None, q, FLAG_SETS[flags])
+        assert_same(gpu, oracle)
+        assert gpu[2]["n_windows"] == oracle[2]
+
+
+@pytest.mark.parametrize("k", [1, 2, 13, 21, 31, 32])
+def test_chunked_feed_equals_single_shot(k):
+    """Tiny staging buffers force many chunks (record-spanning, k-1 overlap) -- results must not change."""
+    rng = np.random.default_rng(k)
+    recs, quals = _random_records(rng, 60, 3000, list(b"ACGT" * 30 + b"N"), min_len=0)
+    recs.append(bytes(rng.choice(list(b"ACGT"), size=50_000).tolist()))  # one record much longer than a chunk
+    quals.append(b"I" * 50_000)
+    oracle = orc.count_records(k, recs, quals, 20, mode="rolling")
+    for bb in (4096, 10_000):
+        gpu = gpu_count(k, recs, quals, 20, _lib.KMG_FLAG_FORCE_HASH, batch_bases=bb)
+        assert_same(gpu, oracle)
+
+
+def test_many_short_reads_record_boundaries():
+    """150 bp reads back to back: windows must never span records (src/run.rs:500-503)."""
+    rng = np.random.default_rng(150)
+    genome = rng.choice(list(b"ACGT"), size=20_000).astype(np.uint8)
+    recs = []
+    for _ in range(3000):
+        s = int(rng.integers(0, len(genome) - 150))
+        r = genome[s:s + 150].copy()
+        if rng.random() < 0.2:
+            r[int(rng.integers(0, 150))] = ord("N")
+        recs.append(r.tobytes())
+    for k in (21, 31):
+        oracle = orc.count_records(k, recs, mode="rolling")
+        assert_same(gpu_count(k, recs, flags=_lib.KMG_FLAG_FORCE_HASH), oracle)
+        assert_same(gpu_count(k, recs, flags=_lib.KMG_FLAG_FORCE_HASH, batch_bases=8192), oracle)
+
+
+def test_k32_poly_t_and_empty_sentinel():
+    """EMPTY = ~0 is TTT..T for k=32, which is never canonical; key 0 (AAA..A) is a real key."""
+    recs = [b"T" * 40, b"A" * 35, b"ACGT" * 20]
+    oracle = orc.count_records(32, recs, mode="literal")
+    gpu = gpu_count(32, recs)
+    assert_same(gpu, oracle)
+    assert gpu[0][0] == 0 and gpu[1][0] == 9 + 4
+
+
+def test_skewed_high_multiplicity():
+    """poly-A / dinucleotide / satellite repeats exercise the in-thread pre-aggregation and contended atomics."""
+    recs = [b"A" * 100_000, b"AC" * 50_000, b"ACGTTGCA" * 20_000, b"GATTACA" * 10_000]
+    for k in (5, 21, 32):
+        oracle = orc.count_records(k, recs, mode="rolling")
+        for f in ("auto", "hash", "hash_nopreagg"):
+            assert_same(gpu_count(k, recs, flags=FLAG_SETS[f]), oracle)
+
+
+def test_table_growth_never_drops_keys():
+    rng = np.random.default_rng(5)
+    recs = [bytes(rng.choice(list(b"ACGT"), size=300_000).tolist()) for _ in range(8)]
+    oracle = orc.count_records(25, recs, mode="rolling")
+    with kb.GpuKmerCounter(25, batch_bases=200_000) as c:  # starts at 4 Mi slots... force growth with a tiny hint
+        pass
+    with kb.GpuKmerCounter(25, batch_bases=100_000, expected_distinct=1000) as c:
+        for r in recs:
+            c.count_records([r])
+        s = c.finalize()
+        keys, counts = c.export(1, True)
+    assert s["n_grows"] >= 1
+    assert_same((keys, counts), oracle)
+    assert s["n_distinct"] == len(oracle[0]) and s["n_windows"] == oracle[2]
+
+
+def test_min_count_histogram_and_kmix(tmp_path):
+    rng = np.random.default_rng(8)
+    genome = bytes(rng.choice(list(b"ACGT"), size=5000).tolist())
+    recs = [genome[i:i + 200] for i in rng.integers(0, 4800, size=2000)]
+    for k, flags in ((12, 0), (21, _lib.KMG_FLAG_FORCE_HASH)):
+        okeys, ocounts, _ = orc.count_records(k, recs, mode="rolling")
+        with kb.GpuKmerCounter(k, flags=flags) as c:
+            c.count_records(recs)
+            s = c.finalize()
+            assert s["max_count"] == int(ocounts.max())
+            for m in (0, 1, 2, 5, 10**9):
+                fk, fc = orc.filter_min_count(okeys, ocounts, m)
+                assert_same(c.export(m, True), (fk, fc))
+                hv, hf = c.histogram(m)
+                ov, of = orc.histogram(ocounts, m)
+                assert (hv == ov).all() and (hf == of).all()
+                text = b"".join(b"%d\t%d\n" % (int(a), int(b)) for a, b in zip(hv, hf))
+                assert text == b"".join(b"%d\t%d\n" % (int(a), int(b)) for a, b in zip(ov, of))
+            # unsorted export is the same multiset
+            uk, uc = c.export(1, False)
+            order = np.argsort(uk)
+            assert_same((uk[order], uc[order]), (okeys, ocounts))
+            p = tmp_path / f"k{k}.kmix"
+            c.save_kmix(p)
+        blob = p.read_bytes()
+        kk, ikeys, icounts = orc.kmix_decode(blob)  # header + CRC valid, record set equal (parity definition v)
+        order = np.argsort(ikeys)
+        assert kk == k and len(blob) == 18 + 16 * len(okeys)
+        assert_same((ikeys[order], icounts[order]), (okeys, ocounts))
+        assert kb.load_index(p).counts() == dict(zip(okeys.tolist(), ocounts.tolist()))
+        assert blob == orc.kmix_encode(k, okeys, ocounts)  # sorted writer => byte-identical to a sorted reference-format file
+
+
+def test_histogram_overflow_tail():
+    """counts >= 65536 leave the dense bins and go through the overflow list."""
+    recs = [b"A" * 70_000, b"C" * 200_000, b"ACGT" * 10]
+    okeys, ocounts, _ = orc.count_records(4, recs, mode="rolling")
+    for flags in (0, _lib.KMG_FLAG_FORCE_HASH):
+        with kb.GpuKmerCounter(4, flags=flags) as c:
+            c.count_records(recs)
+            c.finalize()
+            hv, hf = c.histogram(1)
+        ov, of = orc.histogram(ocounts, 1)
+        assert (hv == ov).all() and (hf == of).all() and hv.max() >= 65536
+
+
+def test_reference_named_entry_points(golden_dir, tmp_path):
+    fx = os.path.join(golden_dir, "fixtures")
+    # tests/library_tests.rs:36-52, :262-270 and the derived fixture answers
+    assert kb.count_kmers(os.path.join(fx, "simple.fa"), 3) == {"AAT": 1, "ACA": 1, "ACG": 4, "ATC": 1, "GTA": 3, "TAA": 1}
+    assert kb.count_kmers(os.path.join(fx, "soft_masked.fa"), 3) == {"AAA": 2}
+    assert kb.count_kmers(os.path.join(fx, "with_n.fa"), 4) == {"AATC": 1, "ACGT": 2, "ATTA": 1, "GTAA": 1, "TACA": 1}
+    # FASTA == FASTQ (tests/integration_tests.rs:486-523)
+    assert kb.count_kmers(os.path.join(fx, "simple.fa"), 3) == kb.count_kmers(os.path.join(fx, "simple.fq"), 3)
+    assert kb.count_kmers_streaming(os.path.join(fx, "with_n.fq"), 3) == kb.count_kmers(os.path.join(fx, "with_n.fa"), 3)
+    # quality (tests/quality_tests.rs; src/streaming.rs:1165-1189)
+    lq = os.path.join(fx, "low_quality.fq")
+    assert kb.count_kmers_with_quality(lq, 4, "auto", 20) == {"AATC": 1, "ACGT": 1, "ATTA": 1, "GTAA": 1, "TACA": 1}
+    assert kb.count_kmers_with_quality(lq, 4, "auto", None) == kb.count_kmers(os.path.join(fx, "simple.fa"), 4)
+    assert kb.count_kmers_with_quality(os.path.join(fx, "simple.fa"), 4, "auto", 40) == kb.count_kmers(os.path.join(fx, "simple.fa"), 4)
+    # packed seams
+    packed = kb.count_kmers_from_sequences(iter([b"ACGTACGT", b"TGCATGCA"]), kb.KmerLength(4))
+    okeys, ocounts, _ = orc.count_records(4, [b"ACGTACGT", b"TGCATGCA"])
+    assert packed == dict(zip(okeys.tolist(), ocounts.tolist()))
+    assert kb.count_kmers_streaming_packed(os.path.join(fx, "simple.fa"), kb.KmerLength(3)) == kb.count_kmers_sequential(os.path.join(fx, "simple.fa"), 3)
+    with pytest.raises(kb.KmerLengthError):
+        kb.count_kmers(os.path.join(fx, "simple.fa"), 0)
+    with pytest.raises(kb.KmerLengthError):
+        kb.count_kmers(os.path.join(fx, "simple.fa"), 33)
+    # builder (src/builder.rs): min_count, histogram, writer
+    b = kb.KmerCounter.new().k(3).min_count(2)
+    assert b.count(os.path.join(fx, "simple.fa")) == {"ACG": 4, "GTA": 3}
+    assert b.histogram(os.path.join(fx, "simple.fa")) == {3: 1, 4: 1}
+    a8 = tmp_path / "a8.fa"; a8.write_bytes(b">s\nAAAAAAAA\n")
+    assert kb.KmerCounter.new().k(3).histogram(a8) == {6: 1}  # tests/integration_tests.rs:767-799
+    import io
+    out = io.BytesIO()
+    kb.KmerCounter.new().k(3).format("tsv").count_to_writer(os.path.join(fx, "soft_masked.fa"), out)
+    assert out.getvalue() == b"AAA\t2\n"  # tests/integration_tests.rs:263-281
+    out = io.BytesIO()
+    kb.KmerCounter.new().k(3).format("histogram").count_to_writer(a8, out)
+    assert out.getvalue() == b"6\t1\n"
+    empty = tmp_path / "empty.fa"; empty.write_bytes(b"")
+    assert kb.count_kmers(empty, 3) == {}
+    seen = []
+    kb.KmerCounter.new().k(3).count_with_progress(os.path.join(fx, "simple.fa"), seen.append)
+    assert seen and seen[-1] == {"sequences_processed": 2, "bases_processed": 15}
+
+
+def test_prepacked_batch_feed():
+    """kmg_acquire_batch / kmg_submit_batch: the Rust reader's zero-copy path (2-bit words + valid/start bits)."""
+    rng = np.random.default_rng(31)
+    recs = [bytes(rng.choice(list(b"ACGTN"), p=[.24, .24, .24, .24, .04], size=int(rng.integers(1, 900))).tolist()) for _ in range(50)]
+    k = 17
+    oracle = orc.count_records(k, recs, mode="rolling")
+    code = np.full(256, 255, dtype=np.uint8)
+    for ch, v in zip(b"ACGTacgt", [0, 1, 2, 3, 0, 1, 2, 3]):
+        code[ch] = v
+    with kb.GpuKmerCounter(k, batch_bases=65536, flags=_lib.KMG_FLAG_FORCE_HASH) as c:
+        b = c.acquire_batch()
+        words = (b.capacity_bases + 31) // 32
+        bases = np.ctypeslib.as_array(b.bases2bit, shape=(words,))
+        valid = np.ctypeslib.as_array(b.valid_bits, shape=(words,))
+        start = np.ctypeslib.as_array(b.start_bits, shape=(words,))
+        pos = 0
+        for r in recs:
+            start[pos // 32] |= np.uint32(1 << (31 - pos % 32))
+            for ch in r:
+                cd = code[ch]
+                if cd != 255:
+                    bases[pos // 32] |= np.uint64(int(cd) << (62 - 2 * (pos % 32)))
+                    valid[pos // 32] |= np.uint32(1 << (31 - pos % 32))
+                pos += 1
+        b.n_bases = pos
+        b.n_records = len(recs)
+        c.submit_batch(b)
+        s = c.finalize()
+        assert_same(c.export(1, True), oracle)
+        assert s["n_windows"] == oracle[2] and s["n_records"] == len(recs)
+
+
+def test_device_resident_path_and_synthetic_generator():
+    """kmg_count_ascii_device on a synthetic genome generated on the device; the generator must agree with
+    the oracle's host generator, and the counts with the oracle's."""
+    import torch
+    n = 3_000_000
+    dev = torch.device("cuda:0")
+    buf = torch.empty(n, dtype=torch.uint8, device=dev)
+    for k, flags in ((21, 0), (12, 0), (5, 0), (31, 0), (9, _lib.KMG_FLAG_FORCE_HASH)):
+        with kb.GpuKmerCounter(k, flags=flags) as c:
+            c.synth_uniform_device(42, 0, n, buf.data_ptr())
+            host = buf.cpu().numpy()
+            assert (host == orc.synth_uniform(42, 0, n)).all()
+            offsets = torch.tensor([0, 1_000_000, 1_000_000, 2_500_000, n], dtype=torch.int64, device=dev)  # incl. an empty record
+            c.count_device(buf.data_ptr(), n, d_offsets=offsets.data_ptr(), n_records=4)
+            s = c.finalize()
+            gpu = c.export(1, True)
+        oracle = orc.count_batch(k, host, None, offsets.cpu().numpy().astype(np.uint64), mode="rolling")
+        assert_same(gpu, oracle)
+        assert s["n_windows"] == oracle[2] and s["n_windows"] == n - 3 * (k - 1)
+
+
+def test_extract_and_insert_equal_direct_count():
+    """Owner bucketing (K4) + weighted upsert: the multi-GPU data path on one device."""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(12)
+    host = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), p=[.245, .245, .245, .245, .02], size=1_500_000).astype(np.uint8)
+    seq = torch.from_numpy(host).to(dev)
+    offsets_np = np.array([0, 400_000, 900_000, len(host)], dtype=np.uint64)
+    offsets = torch.from_numpy(offsets_np.astype(np.int64)).to(dev)
+    for k in (11, 21, 32):
+        oracle = orc.count_batch(k, host, None, offsets_np, mode="rolling")
+        for n_shards in (1, 2, 8, 64):
+            out = torch.empty(len(host), dtype=torch.int64, device=dev)
+            with kb.GpuKmerCounter(k) as c:
+                counts = c.extract_keys_device(seq.data_ptr(), len(host), n_shards, out.data_ptr(), len(host),
+                                               d_offsets=offsets.data_ptr(), n_records=3)
+            assert int(counts.sum()) == oracle[2]
+            keys = out[: int(counts.sum())].cpu().numpy().view(np.uint64)
+            # every key sits in its owner's bucket
+            bounds = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+            for p in range(n_shards):
+                sample = keys[bounds[p]:bounds[p + 1]][:50]
+                assert all(kb.owner_of(int(x), n_shards) == p for x in sample)
+            uk, uc = np.unique(keys, return_counts=True)
+            assert_same((uk, uc.astype(np.uint64)), oracle)
+            # upsert the buckets into a fresh table, half of them as (key, count) pairs
+            with kb.GpuKmerCounter(k, flags=_lib.KMG_FLAG_FORCE_HASH) as c2:
+                half = len(keys) // 2
+                c2.insert_keys_device(out.data_ptr(), half)
+                k2 = torch.from_numpy(uk.view(np.int64)).to(dev)
+                rest_k, rest_c = np.unique(keys[half:], return_counts=True)
+                rk = torch.from_numpy(rest_k.view(np.int64)).to(dev); rc = torch.from_numpy(rest_c.astype(np.int64)).to(dev)
+                c2.insert_keys_device(rk.data_ptr(), len(rest_k), rc.data_ptr())
+                c2.finalize()
+                assert_same(c2.export(1, True), oracle)
+
+
+@pytest.mark.parametrize("k,flags", [(21, 0), (12, 0), (5, 0)])
+def test_full_size_properties_100mbp(k, flags):
+    """BASELINE configs 1-2 at full size (100 Mbp, 100 records): properties that need no oracle --
+    sum of counts == windows, reverse-complement invariance of the whole table, linearity (counting the
+    genome twice doubles every count), histogram consistency."""
+    import torch
+    dev = torch.device("cuda:0")
+    n, n_rec = 100_000_000, 100
+    buf = torch.empty(n, dtype=torch.uint8, device=dev)
+    offsets = torch.arange(0, n + 1, n // n_rec, dtype=torch.int64, device=dev)
+    with kb.GpuKmerCounter(k, flags=flags, expected_distinct=n if k > 13 else 0) as c:
+        c.synth_uniform_device(42, 0, n, buf.data_ptr())
+        c.count_device(buf.data_ptr(), n, d_offsets=offsets.data_ptr(), n_records=n_rec)
+        s = c.finalize()
+        assert s["n_windows"] == n - n_rec * (k - 1)
+        keys, counts = c.export(1, True)
+        assert int(counts.sum()) == s["n_windows"] and len(keys) == s["n_distinct"]
+        assert (np.diff(keys.astype(np.int64)) > 0).all()  # sorted, no duplicates
+        hv, hf = c.histogram(1)
+        assert int(hf.sum()) == s["n_distinct"] and int((hv * hf).sum()) == s["n_windows"]
+        assert (np.diff(hv.astype(np.int64)) > 0).all()
+        # linearity
+        c.count_device(buf.data_ptr(), n, d_offsets=offsets.data_ptr(), n_records=n_rec)
+        c.finalize()
+        keys2, counts2 = c.export(1, True)
+        assert (keys2 == keys).all() and (counts2 == 2 * counts).all()
+    # reverse complement of every record gives the identical table
+    lut = torch.zeros(256, dtype=torch.uint8, device=dev)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        lut[a] = b
+    rc = lut[buf.view(n_rec, n // n_rec).flip(1).long()].contiguous().view(-1)
+    with kb.GpuKmerCounter(k, flags=flags, expected_distinct=n if k > 13 else 0) as c:
+        c.count_device(rc.data_ptr(), n, d_offsets=offsets.data_ptr(), n_records=n_rec)
+        c.finalize()
+        keys3, counts3 = c.export(1, True)
+    assert (keys3 == keys).all() and (counts3 == counts).all()

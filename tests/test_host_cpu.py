@@ -1,0 +1,171 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the host FASTA/FASTQ splitter agrees with the oracle's, the .kmix host helpers follow the
+reference format, and creating a counter without a GPU fails loudly (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import krust_b200 as kb
+from krust_b200 import _lib
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "kmerust_gpu.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(kmg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    L = _lib.load()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/kmerust_gpu.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert L.kmg_abi_version() == 1
+    assert b"1..=32" in L.kmg_status_string(_lib.KMG_ERR_INVALID_K)
+
+
+def test_struct_layouts_match_header():
+    import ctypes as C
+    assert C.sizeof(_lib.KmgConfig) == 48
+    assert C.sizeof(_lib.KmgSummary) == 72
+    assert C.sizeof(_lib.KmgBatch) == 56
+
+
+def test_kmer_length_errors_like_reference():
+    # src/kmer.rs:100-111; tests/library_tests.rs:155-170
+    for bad in (0, 33, 100):
+        with pytest.raises(kb.KmerLengthError) as e:
+            kb.KmerLength(bad)
+        assert e.value.k == bad and e.value.min == 1 and e.value.max == 32
+    assert kb.KmerLength(1).get() == 1 and kb.KmerLength(32).as_u8() == 32
+    with pytest.raises(kb.KmerLengthError):
+        kb.KmerCounter.new().k(0)
+    with pytest.raises(kb.BuilderError):
+        kb.KmerCounter.new().count("nonexistent.fa")  # k not set is reported first (src/builder.rs:246)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_gpu():
+    with pytest.raises(kb.GpuError) as e:
+        kb.GpuKmerCounter(21)
+    assert e.value.status == _lib.KMG_ERR_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(kb.KmeRustError):
+        kb.count_kmers_from_sequences([b"ACGT"], kb.KmerLength(3))
+
+
+def test_create_rejects_bad_config_before_touching_cuda():
+    import ctypes as C
+    L = _lib.load()
+    ctx = C.c_void_p()
+    cfg = _lib.KmgConfig(abi_version=1, k=0, device=-1)
+    assert L.kmg_create(C.byref(cfg), C.byref(ctx)) == _lib.KMG_ERR_INVALID_K
+    assert b"out of range" in L.kmg_last_error(None)
+    cfg = _lib.KmgConfig(abi_version=7, k=21, device=-1)
+    assert L.kmg_create(C.byref(cfg), C.byref(ctx)) == _lib.KMG_ERR_ABI
+    cfg = _lib.KmgConfig(abi_version=1, k=21, device=-1, flags=_lib.KMG_FLAG_FORCE_DIRECT)
+    assert L.kmg_create(C.byref(cfg), C.byref(ctx)) == _lib.KMG_ERR_INVALID_ARG
+
+
+def test_unpack_matches_oracle():
+    rng = np.random.default_rng(0)
+    for k in (1, 5, 21, 31, 32):
+        keys = rng.integers(0, 2**63, size=64, dtype=np.uint64)
+        if k < 32:
+            keys &= np.uint64((1 << (2 * k)) - 1)
+        names = kb.unpack_many(keys, k)
+        for key, name in zip(keys.tolist(), names.tolist()):
+            assert name == orc.unpack(key, k) and kb.unpack_to_string(key, k) == name.decode()
+
+
+PARSER_CASES = [
+    (b">seq1\nACGTACGT\n>seq2\nGATTACA\n", False),
+    (b">s desc\nACGT\r\nACGT\n>t\nGG\n\n", False),
+    (b">a\n>b\nAC\n", False),
+    (b"", False),
+    (b">only\n", False),
+    (b">x\nAC GT \nNN\n", False),
+    (b"@r1\nACGT\n+\nIIII\n@r2\nGG\nTT\n+r2\n!!\n##\n", True),
+    (b"@r1\nACGT\n+\nIIII", True),
+    (b"", True),
+]
+
+
+@pytest.mark.parametrize("data,is_fastq", PARSER_CASES)
+def test_host_parser_equals_oracle_parser(data, is_fastq):
+    a = kb.parse_fastx(data, is_fastq)
+    b = orc.parse_fastx(data, is_fastq)
+    assert a[0].tobytes() == b[0].tobytes() and a[2].tolist() == b[2].tolist()
+    if is_fastq:
+        assert a[1].tobytes() == b[1].tobytes()
+
+
+def test_host_parser_errors_and_fixtures(golden_dir):
+    with pytest.raises(kb.SequenceParseError):
+        kb.parse_fastx(b"ACGT\n", False)
+    with pytest.raises(kb.SequenceParseError):
+        kb.parse_fastx(b"@r\nACGT\n+\nII\n", True)
+    with pytest.raises(kb.SequenceParseError):
+        kb.parse_fastx(b"@r\nACGT\n", True)
+    fx = os.path.join(golden_dir, "fixtures")
+    seq, qual, off = kb.read_records(os.path.join(fx, "low_quality.fq"))
+    assert seq.tobytes() == b"ACGTACGTGATTACA" and qual.tobytes() == b"IIII!!!!IIIIIII" and off.tolist() == [0, 8, 15]
+    assert kb.SequenceFormat.from_extension("reads.fastq.gz") == "fastq"
+    assert kb.SequenceFormat.from_extension("genome.fa.gz") == "fasta"
+    assert kb.SequenceFormat.from_extension("noext") == "fasta"
+    assert kb.SequenceFormat.resolve("auto", None) == "fasta"
+    with pytest.raises(kb.KmeRustError):
+        kb.read_records("/nonexistent/file.fa")
+
+
+def test_index_host_round_trip_and_rejects(tmp_path):
+    # src/index.rs:510-573; tests/property_tests.rs:244-261
+    rng = np.random.default_rng(9)
+    for k in (1, 5, 16, 21, 32):
+        counts = {int(a): int(b) for a, b in zip(rng.integers(0, 2**63, 40, dtype=np.uint64), rng.integers(1, 2**40, 40))}
+        p = tmp_path / f"t{k}.kmix"
+        kb.save_index(kb.KmerIndex(kb.KmerLength(k), counts), p)
+        blob = p.read_bytes()
+        k2, keys, cnts = orc.kmix_decode(blob)  # the oracle's reader accepts our writer's bytes
+        assert k2 == k and dict(zip(keys.tolist(), cnts.tolist())) == counts
+        idx = kb.load_index(p)
+        assert idx.k() == k and idx.counts() == counts and len(idx) == len(counts)
+        pz = tmp_path / f"t{k}.kmix.gz"
+        kb.save_index(kb.KmerIndex(kb.KmerLength(k), counts), pz)
+        assert kb.load_index(pz).counts() == counts
+    (tmp_path / "small").write_bytes(b"KMIX")
+    with pytest.raises(kb.InvalidIndexError, match="too small"):
+        kb.load_index(tmp_path / "small")
+    (tmp_path / "magic").write_bytes(b"XXXX" + blob[4:])
+    with pytest.raises(kb.InvalidIndexError, match="magic"):
+        kb.load_index(tmp_path / "magic")
+    bad = bytearray(blob); bad[30] ^= 1
+    (tmp_path / "crc").write_bytes(bytes(bad))
+    with pytest.raises(kb.InvalidIndexError, match="checksum"):
+        kb.load_index(tmp_path / "crc")
+    # the oracle's writer is readable by our loader too
+    (tmp_path / "o.kmix").write_bytes(orc.kmix_encode(21, np.array([5, 9], dtype=np.uint64), np.array([1, 2], dtype=np.uint64)))
+    assert kb.load_index(tmp_path / "o.kmix").counts() == {5: 1, 9: 2}
+
+
+def test_histogram_host_helpers():
+    assert kb.compute_histogram_packed({1: 1, 2: 1, 3: 2, 4: 2}) == {1: 2, 2: 2}
+    st = kb.histogram_stats({1: 2, 2: 2})
+    assert st["distinct_kmers"] == 4 and st["total_kmers"] == 6 and st["mean_count"] == 1.5
+    assert kb.histogram_stats({})["mean_count"] == 0.0
+
+
+def test_owner_of_is_a_partition():
+    keys = np.random.default_rng(4).integers(0, 2**42, 2000, dtype=np.uint64)
+    for n in (1, 2, 4, 8):
+        owners = [kb.owner_of(int(x), n) for x in keys]
+        assert all(0 <= o < n for o in owners)
+        if n > 1:
+            assert len(set(owners)) == n
