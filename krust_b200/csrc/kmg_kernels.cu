@@ -167,7 +167,10 @@ __device__ __forceinline__ void preaggregate(const uint64_t (&key)[G], uint32_t 
     if (cnt[j] && cnt[j - 2] && key[j] == key[j - 2]) { cnt[j] += cnt[j - 2]; cnt[j - 2] = 0; }
 }
 
-// ---- K2: open-addressing table upsert (AoS 16-byte slots: key, count) ---------------------------------
+// ---- K2: open-addressing table upsert (AoS 16-byte slots: key, count-1) -------------------------------
+// A slot stores (key, occurrences - 1): the CAS that claims an empty slot IS the first count, so a new
+// key costs one atomic instead of two (the measured HBM-resident ceiling is ~20 G single atomics/s but
+// only ~10.5 G CAS+RED pairs/s, profiles/microbench_r1.jsonl).  Duplicates add with one more RED.
 __device__ __forceinline__ void table_add_slow(HashTable t, uint64_t key, uint64_t add, uint64_t slot, uint32_t &new_keys,
                                                unsigned long long *full_flag) {
   for (uint64_t probe = 1; probe < t.cap; ++probe) {
@@ -175,7 +178,7 @@ __device__ __forceinline__ void table_add_slow(HashTable t, uint64_t key, uint64
     unsigned long long *kp = reinterpret_cast<unsigned long long *>(t.slots + 2 * slot);
     uint64_t cur = *reinterpret_cast<volatile unsigned long long *>(kp);
     if (cur == EMPTY_KEY) cur = atomicCAS(kp, EMPTY_KEY, key);
-    if (cur == EMPTY_KEY) { ++new_keys; atomicAdd(kp + 1, add); return; }
+    if (cur == EMPTY_KEY) { ++new_keys; if (add > 1) atomicAdd(kp + 1, add - 1); return; }
     if (cur == key) { atomicAdd(kp + 1, add); return; }
   }
   atomicExch(full_flag, 1ull);
@@ -186,7 +189,7 @@ __device__ __forceinline__ void table_add(HashTable t, uint64_t key, uint64_t ad
   uint64_t slot = slot_of(key, t.cap);
   unsigned long long *kp = reinterpret_cast<unsigned long long *>(t.slots + 2 * slot);
   uint64_t old = atomicCAS(kp, EMPTY_KEY, key);
-  if (old == EMPTY_KEY) { ++new_keys; atomicAdd(kp + 1, add); }
+  if (old == EMPTY_KEY) { ++new_keys; if (add > 1) atomicAdd(kp + 1, add - 1); }
   else if (old == key) atomicAdd(kp + 1, add);
   else table_add_slow(t, key, add, slot, new_keys, full_flag);
 }
@@ -213,7 +216,7 @@ struct HashEmit {
     for (int j = 0; j < G; ++j) {
       if (!cnt[j]) continue;
       unsigned long long *cp = reinterpret_cast<unsigned long long *>(t.slots + 2 * slot[j] + 1);
-      if (old[j] == EMPTY_KEY) { ++new_keys; atomicAdd(cp, (unsigned long long)cnt[j]); }
+      if (old[j] == EMPTY_KEY) { ++new_keys; if (cnt[j] > 1) atomicAdd(cp, (unsigned long long)(cnt[j] - 1)); }
       else if (old[j] == key[j]) atomicAdd(cp, (unsigned long long)cnt[j]);
       else table_add_slow(t, key[j], cnt[j], slot[j], new_keys, full_flag);
     }
@@ -450,7 +453,7 @@ __global__ void rehash_kernel(HashTable from, HashTable to, unsigned long long *
   const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(from.slots);
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < from.cap; i += (uint64_t)gridDim.x * blockDim.x) {
     ulonglong2 s = p[i];
-    if (s.x != EMPTY_KEY) table_add(to, s.x, s.y, new_keys, counters + CTR_FULL);
+    if (s.x != EMPTY_KEY) table_add(to, s.x, s.y + 1, new_keys, counters + CTR_FULL);
   }
 }
 
@@ -458,7 +461,7 @@ __global__ void rehash_kernel(HashTable from, HashTable to, unsigned long long *
 __device__ __forceinline__ bool view_get(const TableView &v, uint64_t i, uint64_t &key, uint64_t &count) {
   if (v.dense) { key = i; count = v.dense[i]; return count != 0; }
   ulonglong2 s = reinterpret_cast<const ulonglong2 *>(v.slots)[i];
-  key = s.x; count = s.y;
+  key = s.x; count = s.y + 1;  // slots store occurrences - 1
   return s.x != EMPTY_KEY;
 }
 

@@ -114,7 +114,9 @@ float time_ms(F f, int reps = 3) {
   return best;
 }
 
-int main() {
+int main(int argc, char **argv) {
+  const bool only_scatter = argc > 1 && argv[1][0] == 's';
+  const int nlog = argc > 2 ? atoi(argv[2]) : 28;
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
@@ -124,6 +126,7 @@ int main() {
   const int grid = sms * 8, threads = 256;
   const double sizes_mb[] = {16, 32, 48, 64, 96, 128, 256, 1024, 8192, 65536};
   for (double mb : sizes_mb) {
+    if (only_scatter) break;
     uint64_t cap = (uint64_t)(mb * 1048576.0 / 16.0);
     unsigned long long *tab;
     if (cudaMalloc(&tab, cap * 16) != cudaSuccess) { printf("{\"skip_mb\": %.0f}\n", mb); cudaGetLastError(); continue; }
@@ -146,7 +149,7 @@ int main() {
   }
   // scatter into P streams
   {
-    const uint64_t n = 1ull << 28;
+    const uint64_t n = 1ull << nlog;
     uint64_t *keys, *out;
     CK(cudaMalloc(&keys, n * 8));
     gen_keys<<<grid, threads>>>(keys, n, 99);
