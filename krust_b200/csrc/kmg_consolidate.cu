@@ -1,0 +1,281 @@
+// Phase B of the partitioned pipeline: count every hash partition in an L2-RESIDENT table.
+//
+// Why: an upsert into an HBM-resident table is bounded by ~20 G random atomics/s on a B200, but the
+// same atomics run at 127-200 G/s when the table fits the 126 MB L2 (profiles/microbench_r1.jsonl).
+// So keys are first scattered into P hash partitions with streaming writes (phase A,
+// scan_partition_kernel), and here each partition (a few hundred thousand keys) is upserted into a
+// small table that lives in L2, compacted into the output run and the table is handed to a later
+// partition.  HBM sees only streaming traffic: 8 B/key in, 16 B/distinct key out.
+//
+// One persistent kernel, no grid-wide barriers: CTAs draw tickets from a global counter; the ticket
+// order I(0) I(1) C(0) I(2) C(1) ... I(P-1) C(P-2) C(P-1) (I = insert chunk, C = compact chunk)
+// interleaves three table buffers so that every dependency points at least two phases back:
+//     I(p) needs C(p-3) finished (its buffer is free again),  C(p) needs I(p) finished.
+// Dependencies only ever point to lower tickets, which are held by CTAs that are already running,
+// so the scheme cannot deadlock and needs no cooperative launch.
+//
+// Replaces the DashMap upsert + iteration of src/run.rs:565-582 for large inputs; results are the
+// same multiset of (canonical key, count) pairs.
+#include <atomic>
+
+#include "kmg_device.cuh"
+#include "kmg_kernels.h"
+
+namespace kmg {
+
+namespace {
+
+constexpr unsigned long long BASE_UNSET = ~0ull;
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *scratch /*>= 32 entries*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  uint32_t t = 0;
+  for (int w = 0; w < CONS_THREADS / 32; ++w) t += scratch[w];
+  return t;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(CONS_THREADS) consolidate_kernel(ConsParams P) {
+  __shared__ uint64_t seg_begin[CONS_MAX_RUNS];
+  __shared__ uint32_t seg_prefix[CONS_MAX_RUNS + 1];
+  __shared__ uint32_t scratch[64];
+  __shared__ uint32_t s_ticket, s_phase;
+  __shared__ unsigned long long s_base;
+  const int tid = threadIdx.x;
+  uint32_t phase_idx = 0;  // monotone per CTA (tickets only grow)
+
+  for (;;) {
+    if (tid == 0) {
+      const uint32_t t = atomicAdd(P.ticket, 1u);
+      if (t < P.total_tickets)
+        while (P.phases[phase_idx + 1].first_ticket <= t) ++phase_idx;
+      s_ticket = t; s_phase = phase_idx;
+    }
+    __syncthreads();
+    const uint32_t ticket = s_ticket;
+    if (ticket >= P.total_tickets) break;
+    const ConsPhase ph = P.phases[s_phase];
+    const uint32_t chunk = ticket - ph.first_ticket;
+    const uint32_t p = ph.part_and_type & 0x7fffffffu;
+    const bool is_compact = ph.part_and_type >> 31;
+    const uint32_t cap_log2 = P.part_cap_log2[p];
+    const uint64_t mask = (1ull << cap_log2) - 1;
+    unsigned long long *table = reinterpret_cast<unsigned long long *>(P.tables) + (uint64_t)(p % CONS_NBUF) * P.table_stride_slots * 2;
+
+    if (!is_compact) {
+      // ------------------------------------------------------------------ I(p): upsert one chunk of partition p
+      if (tid < (int)P.R) {
+        const uint64_t b = P.runs[tid].offsets[p], e = P.runs[tid].offsets[p + 1];
+        seg_begin[tid] = b;
+        scratch[tid] = (uint32_t)(e - b);
+      }
+      if (tid == 0 && p >= CONS_NBUF) {  // the buffer must have been drained by C(p - NBUF)
+        const uint32_t need = P.part_nC[p - CONS_NBUF];
+        while (ld_acquire_u32(P.done_C + (p - CONS_NBUF)) < need) __nanosleep(200);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t acc = 0;
+        for (uint32_t r = 0; r < P.R; ++r) { seg_prefix[r] = acc; acc += scratch[r]; }
+        seg_prefix[P.R] = acc;
+      }
+      __syncthreads();
+      const uint32_t n_p = seg_prefix[P.R];
+      const uint32_t lo = chunk * CONS_INSERT_CHUNK;
+      constexpr int KPT = CONS_INSERT_CHUNK / CONS_THREADS;
+      uint64_t key[KPT], old[KPT], slot[KPT], w[KPT];
+      uint32_t new_keys = 0;
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        const uint32_t idx = lo + j * CONS_THREADS + tid;
+        w[j] = 0;
+        if (idx < n_p) {
+          uint32_t r = 0;
+          while (r + 1 < P.R && idx >= seg_prefix[r + 1]) ++r;
+          const uint64_t src = seg_begin[r] + (idx - seg_prefix[r]);
+          key[j] = __ldcs(P.runs[r].keys + src);
+          w[j] = P.runs[r].counts ? __ldcs(P.runs[r].counts + src) : 1ull;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {  // all first probes in flight together
+        old[j] = 0;
+        if (w[j]) {
+          slot[j] = mix64(key[j]) & mask;  // low mix bits; the partition index used the high ones
+          old[j] = atomicCAS(table + 2 * slot[j], EMPTY_KEY, key[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        if (!w[j]) continue;
+        uint64_t s = slot[j], cur = old[j];
+        uint64_t probes = 0;
+        while (cur != EMPTY_KEY && cur != key[j]) {  // linear probing inside the partition's table
+          if (++probes > mask) { atomicExch(P.error_flag, 1u); break; }
+          s = (s + 1) & mask;
+          cur = *reinterpret_cast<volatile unsigned long long *>(table + 2 * s);
+          if (cur == EMPTY_KEY) cur = atomicCAS(table + 2 * s, EMPTY_KEY, key[j]);
+        }
+        if (cur == EMPTY_KEY) { ++new_keys; if (w[j] > 1) atomicAdd(table + 2 * s + 1, (unsigned long long)(w[j] - 1)); }
+        else if (cur == key[j]) atomicAdd(table + 2 * s + 1, (unsigned long long)w[j]);
+      }
+      const uint32_t total_new = block_sum_u32(new_keys, scratch);
+      if (tid == 0 && total_new) atomicAdd(P.distinct + p, total_new);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t done = atomicAdd(P.done_I + p, 1u) + 1;
+        if (done == P.part_nI[p]) {  // last inserter of p: its distinct count is final -> publish where p+1 starts
+          __threadfence();
+          unsigned long long b;
+          while ((b = ld_acquire_u64(P.out_base + p)) == BASE_UNSET) __nanosleep(200);
+          const uint32_t d = atomicAdd(P.distinct + p, 0u);
+          st_release_u64(P.out_base + p + 1, b + d);
+        }
+      }
+    } else {
+      // ------------------------------------------------------------------ C(p): drain one chunk of p's table
+      if (tid == 0) {
+        while (ld_acquire_u64(P.out_base + p + 1) == BASE_UNSET) __nanosleep(200);  // implies I(p) complete
+        s_base = ld_acquire_u64(P.out_base + p);
+      }
+      __syncthreads();
+      constexpr int SPT = CONS_COMPACT_CHUNK / CONS_THREADS;
+      const uint64_t lo = (uint64_t)chunk * CONS_COMPACT_CHUNK;
+      ulonglong2 s[SPT];
+      uint32_t mine = 0;
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) {
+        const uint64_t i = lo + j * CONS_THREADS + tid;
+        s[j] = make_ulonglong2(EMPTY_KEY, 0ull);
+        if (i <= mask) s[j] = __ldcg(reinterpret_cast<const ulonglong2 *>(table) + i);  // L2, never a stale L1 line
+        mine += s[j].x != EMPTY_KEY;
+      }
+      // block-wide exclusive scan of `mine`
+      const int lane = tid & 31, warp = tid >> 5;
+      uint32_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (lane == 31) scratch[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t v = lane < CONS_THREADS / 32 ? scratch[lane] : 0, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        scratch[32 + lane] = inc - v;  // exclusive warp offsets
+        if (lane == 31) {
+          const uint32_t total = inc;
+          scratch[31] = total ? atomicAdd(P.out_cursor + p, total) : 0;  // this chunk's range inside partition p
+        }
+      }
+      __syncthreads();
+      uint64_t o = s_base + scratch[31] + scratch[32 + warp] + (incl - mine);
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) {
+        if (s[j].x == EMPTY_KEY) continue;
+        __stcs(P.out_keys + o, s[j].x);
+        __stcs(P.out_counts + o, s[j].y + 1);  // slots store occurrences - 1
+        ++o;
+        const uint64_t i = lo + j * CONS_THREADS + tid;
+        reinterpret_cast<ulonglong2 *>(table)[i] = make_ulonglong2(EMPTY_KEY, 0ull);  // hand the slot back clean
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(P.done_C + p, 1u);
+    }
+    __syncthreads();
+  }
+}
+
+// scatter already-extracted keys (optionally weighted) into partitions: the receive side of the
+// multi-GPU exchange and re-partitioning of foreign runs.  pass 0 counts, pass 1 scatters.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) partition_keys_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ counts,
+                                                             uint64_t n, uint32_t n_parts, unsigned long long *part_counts,
+                                                             const unsigned long long *part_start, unsigned long long *part_cursor,
+                                                             uint64_t *out_keys, uint64_t *out_counts) {
+  extern __shared__ uint32_t sm[];
+  uint32_t *hist = sm, *toff = sm + n_parts;
+  constexpr uint32_t TILE = 8192;
+  for (uint32_t p = threadIdx.x; p < n_parts; p += blockDim.x) hist[p] = 0;
+  __syncthreads();
+  for (uint64_t t0 = (uint64_t)blockIdx.x * TILE; t0 < n; t0 += (uint64_t)gridDim.x * TILE) {
+    const uint32_t m = (uint32_t)(n - t0 < TILE ? n - t0 : TILE);
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) atomicAdd(hist + part_of(keys[t0 + i], n_parts), 1u);
+    if (SCATTER) {
+      __syncthreads();
+      for (uint32_t p = threadIdx.x; p < n_parts; p += blockDim.x) {
+        const uint32_t c = hist[p];
+        toff[p] = c ? (uint32_t)atomicAdd(part_cursor + p, (unsigned long long)c) : 0;
+        hist[p] = 0;
+      }
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        const uint64_t key = keys[t0 + i];
+        const uint32_t p = part_of(key, n_parts);
+        const uint64_t o = __ldg(part_start + p) + toff[p] + atomicAdd(hist + p, 1u);
+        out_keys[o] = key;
+        if (out_counts) out_counts[o] = counts ? counts[t0 + i] : 1ull;
+      }
+      __syncthreads();
+      for (uint32_t p = threadIdx.x; p < n_parts; p += blockDim.x) hist[p] = 0;
+      __syncthreads();
+    }
+  }
+  if (!SCATTER) {
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < n_parts; p += blockDim.x)
+      if (hist[p]) atomicAdd(part_counts + p, (unsigned long long)hist[p]);
+  }
+}
+
+extern std::atomic<uint64_t> g_launches;
+
+cudaError_t launch_consolidate(const ConsParams &P, int num_sms, cudaStream_t s) {
+  if (P.total_tickets == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  consolidate_kernel<<<num_sms * CONS_CTAS_PER_SM, CONS_THREADS, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_partition_keys(const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n, uint32_t n_parts, bool scatter,
+                                  unsigned long long *part_counts, const unsigned long long *part_start,
+                                  unsigned long long *part_cursor, uint64_t *out_keys, uint64_t *out_counts, int num_sms,
+                                  cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const size_t smem = 2 * (size_t)n_parts * sizeof(uint32_t);
+  uint64_t want = (n + 8191) / 8192;
+  unsigned grid = (unsigned)(want < (uint64_t)num_sms * 4 ? want : (uint64_t)num_sms * 4);
+  cudaError_t e;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (scatter) {
+    if ((e = cudaFuncSetAttribute(partition_keys_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    partition_keys_kernel<true><<<grid, 256, smem, s>>>(d_keys, d_counts, n, n_parts, part_counts, part_start, part_cursor, out_keys, out_counts);
+  } else {
+    if ((e = cudaFuncSetAttribute(partition_keys_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    partition_keys_kernel<false><<<grid, 256, smem, s>>>(d_keys, d_counts, n, n_parts, part_counts, part_start, part_cursor, out_keys, out_counts);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace kmg
