@@ -256,7 +256,20 @@ def main():
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on its launching stream
     peak, peak_src = peaks()
-    if world == 1:
+    pipeline = None
+    if world == 1 and local["path"] == 2:
+        # partitioned pipeline: phase A (two scan passes + scatter) and phase B (consolidate_kernel); reset() clears the timers,
+        # so these are the last step's kernels.  Algorithmic bytes: A = 0.375 in + 8 out, B = 8 in + 16 out per k-mer.
+        a_ms, b_ms = local["scan_ns"] / 1e6, local["consolidate_ns"] / 1e6
+        pipeline = {"phase_a_ms": a_ms, "phase_b_ms": b_ms, "phase_a_gbs": exp_windows * 8.375 / (a_ms * 1e-3) / 1e9 if a_ms else 0.0,
+                    "phase_b_gbs": exp_windows * 24.0 / (b_ms * 1e-3) / 1e9 if b_ms else 0.0,
+                    "whole_gbs": exp_windows * B_ALG_HASH_NEW / ((a_ms + b_ms) * 1e-3) / 1e9 if a_ms + b_ms else 0.0}
+        if b_ms >= a_ms:
+            kern_ms, per_unit, kern_name = b_ms, 24.0, "consolidate_kernel (phase B: upsert each hash partition into an L2-resident table, compact)"
+        else:
+            kern_ms, per_unit, kern_name = a_ms, 8.375, "scan_partition_kernel x2 (phase A: tile scan, count pass + scatter pass into hash partitions)"
+        alg_bytes = exp_windows * per_unit
+    elif world == 1:
         kern_ms = local["kernel_ns"] / 1e6          # scan_count_kernel<HASH> of the last step (reset() clears the timer)
         alg_bytes = exp_windows * B_ALG_HASH_NEW
         kern_name = "scan_count_kernel<MODE_HASH> (tile scan + open-addressing upsert)"
@@ -270,7 +283,8 @@ def main():
         per_unit = B_ALG_INSERT
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": kern_name, "kernel_ms": kern_ms, "alg_bytes_per_kmer": per_unit, "peak_source": peak_src}
+                "kernel": kern_name, "kernel_ms": kern_ms, "alg_bytes_per_kmer": per_unit, "peak_source": peak_src,
+                "pipeline": pipeline}
 
     # ---- end to end: HOST (pinned) ASCII in, histogram + summary out, through the public C-ABI call
     e2e = None
@@ -331,7 +345,8 @@ def main():
                 "config": {"workload": "C4: k=21 canonical k-mer counting, 3.1 Gbp uniform-random FASTA (31 records x 100 Mbp), "
                                        "hash-sharded across N GPUs",
                            "k": k, "bases": total, "records": args.records, "windows": exp_windows,
-                           "distinct": summary["n_distinct"], "table_slots_per_gpu": local["table_capacity"],
+                           "distinct": summary["n_distinct"], "path": {0: "hbm-table", 1: "direct-4^k", 2: "partitioned"}[local["path"]],
+                           "table_slots_or_partitions_per_gpu": local["table_capacity"],
                            "l2_policy": "inputs and table are far larger than L2 (no flush needed)",
                            "step": "table clear + ingest + scan/upsert (+ bucket, all-to-all, upsert for N>1) + finalize",
                            "parallelism": f"hash-shard x{world}" if world > 1 else "single GPU"},

@@ -11,19 +11,20 @@ LIB_PATH = os.path.join(HERE, "libkmerust_gpu.so")
 KMG_ABI_VERSION = 1
 KMG_OK, KMG_ERR_INVALID_K, KMG_ERR_INVALID_ARG, KMG_ERR_CUDA, KMG_ERR_OOM, KMG_ERR_TABLE_FULL, KMG_ERR_STATE, \
     KMG_ERR_IO, KMG_ERR_ABI, KMG_ERR_CAPACITY, KMG_ERR_PARSE = range(11)
-KMG_FLAG_FORCE_HASH, KMG_FLAG_FORCE_DIRECT, KMG_FLAG_NO_PREAGG = 1, 2, 4
+KMG_FLAG_FORCE_HASH, KMG_FLAG_FORCE_DIRECT, KMG_FLAG_NO_PREAGG, KMG_FLAG_FORCE_PARTITIONED = 1, 2, 4, 8
 
 
 class KmgConfig(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("k", C.c_uint32), ("device", C.c_int32), ("flags", C.c_uint32),
-                ("has_min_quality", C.c_uint8), ("min_quality", C.c_uint8), ("reserved", C.c_uint8 * 6),
+                ("has_min_quality", C.c_uint8), ("min_quality", C.c_uint8), ("parts_log2", C.c_uint8), ("reserved", C.c_uint8 * 5),
                 ("expected_distinct", C.c_uint64), ("batch_bases", C.c_uint64), ("stream", C.c_void_p)]
 
 
 class KmgSummary(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_bases", C.c_uint64), ("n_windows", C.c_uint64),
                 ("n_distinct", C.c_uint64), ("max_count", C.c_uint64), ("table_capacity", C.c_uint64),
-                ("path", C.c_uint32), ("n_grows", C.c_uint32), ("kernel_ns", C.c_uint64), ("h2d_bytes", C.c_uint64)]
+                ("path", C.c_uint32), ("n_grows", C.c_uint32), ("kernel_ns", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("scan_ns", C.c_uint64), ("consolidate_ns", C.c_uint64)]
 
 
 class KmgBatch(C.Structure):

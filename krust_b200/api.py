@@ -183,7 +183,7 @@ class GpuKmerCounter:
     src/streaming.rs:833-1114) behind the same feed -> finalize -> results life cycle."""
 
     def __init__(self, k, min_quality: Optional[int] = None, expected_distinct: int = 0, batch_bases: int = 0,
-                 flags: int = 0, device: int = -1, stream: Optional[int] = None):
+                 flags: int = 0, device: int = -1, stream: Optional[int] = None, parts_log2: int = 0):
         self.k = _k(k)
         self._L = _lib.load()
         cfg = KmgConfig()
@@ -195,6 +195,7 @@ class GpuKmerCounter:
         cfg.min_quality = int(min_quality or 0)
         cfg.expected_distinct = int(expected_distinct)
         cfg.batch_bases = int(batch_bases)
+        cfg.parts_log2 = int(parts_log2)
         cfg.stream = stream
         self._ctx = C.c_void_p()
         _check(self._L.kmg_create(C.byref(cfg), C.byref(self._ctx)), None)

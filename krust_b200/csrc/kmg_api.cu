@@ -41,6 +41,14 @@ struct Staging {
 
 }  // namespace
 
+// A run is a partition-ordered list of keys (phase A output, every key counts 1) or of (key, count)
+// pairs (phase B output / weighted inserts).  All runs of a context share the same partition count.
+struct Run {
+  uint64_t *d_keys = nullptr, *d_counts = nullptr, *d_offsets = nullptr;
+  std::vector<uint64_t> h_offsets;  // n_parts + 1
+  uint64_t n = 0;
+};
+
 struct kmg_ctx {
   kmg_config cfg{};
   int device = 0;
@@ -71,10 +79,22 @@ struct kmg_ctx {
   bool staging_ready = false, packed_feed_ready = false;
   uint32_t next_slot = 0;
 
+  // partitioned pipeline (v2)
+  enum Mode { MODE_UNDECIDED, MODE_DENSE, MODE_TABLE, MODE_PARTITIONED } mode = MODE_UNDECIDED;
+  uint32_t n_parts = 0;
+  std::vector<Run> runs;      // pending, not yet consolidated
+  Run result;                 // consolidated (key, count) run
+  bool has_result = false;
+  uint64_t pending_bytes = 0;
+  unsigned long long *d_part = nullptr;  // 3 * MAX_PARTS scratch: counts, starts, cursors
+  uint32_t n_consolidations = 0;
+
   uint64_t n_records = 0, n_bases = 0, h2d_bytes = 0;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   double kernel_ms = 0.0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_timers;
+  double cat_ms[2] = {0.0, 0.0};  // 0: scan / partition kernels, 1: consolidation kernel
+  struct Timer { cudaEvent_t a, b; int cat; };
+  std::vector<Timer> pending_timers;
 };
 
 namespace {
@@ -96,10 +116,16 @@ kmg_status cuda_fail(kmg_ctx *ctx, cudaError_t e, const char *what) {
 inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
 TableView view_of(const kmg_ctx *c) {
-  TableView v;
-  if (c->use_dense) { v.slots = nullptr; v.dense = c->dense; v.n = c->dense_n; }
-  else { v.slots = c->table.slots; v.dense = nullptr; v.n = c->table.cap; }
+  TableView v{nullptr, nullptr, nullptr, nullptr, 0};
+  if (c->mode == kmg_ctx::MODE_PARTITIONED) { v.pair_keys = c->result.d_keys; v.pair_counts = c->result.d_counts; v.n = c->has_result ? c->result.n : 0; }
+  else if (c->use_dense) { v.dense = c->dense; v.n = c->dense_n; }
+  else { v.slots = c->table.slots; v.n = c->table.slots ? c->table.cap : 0; }
   return v;
+}
+
+void free_run(Run &r) {
+  cudaFree(r.d_keys); cudaFree(r.d_counts); cudaFree(r.d_offsets);
+  r = Run();
 }
 
 kmg_status alloc_table(kmg_ctx *c, uint64_t cap, HashTable *out) {
@@ -190,25 +216,265 @@ kmg_status ensure_packed(kmg_ctx *c, uint64_t n_words_total) {
   return KMG_OK;
 }
 
-void timer_begin(kmg_ctx *c) {
+void timer_begin(kmg_ctx *c, int cat = 0) {
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
   cudaEventRecord(a, c->stream);
-  c->pending_timers.emplace_back(a, b);
+  c->pending_timers.push_back(kmg_ctx::Timer{a, b, cat});
 }
-void timer_end(kmg_ctx *c) { cudaEventRecord(c->pending_timers.back().second, c->stream); }
+void timer_end(kmg_ctx *c) { cudaEventRecord(c->pending_timers.back().b, c->stream); }
 void timers_collect(kmg_ctx *c) {
   for (auto &p : c->pending_timers) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) c->kernel_ms += ms;
-    cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { c->kernel_ms += ms; c->cat_ms[p.cat] += ms; }
+    cudaEventDestroy(p.a); cudaEventDestroy(p.b);
   }
   c->pending_timers.clear();
+}
+
+
+// =================================================================================================
+// Partitioned pipeline (v2): phase A scatters keys into hash partitions (streaming writes), phase B
+// counts each partition in an L2-resident table (kmg_consolidate.cu).
+// =================================================================================================
+inline uint32_t pow2_ceil_log2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) ++l; return l; }
+
+// Decide how this context counts.  Called at the first feeding call, when the input size is known.
+kmg_status decide_mode(kmg_ctx *c, uint64_t first_call_windows) {
+  if (c->mode != kmg_ctx::MODE_UNDECIDED) return KMG_OK;
+  if (c->use_dense) { c->mode = kmg_ctx::MODE_DENSE; return KMG_OK; }
+  const uint32_t f = c->cfg.flags;
+  const uint64_t hint = std::max<uint64_t>(c->cfg.expected_distinct, first_call_windows);
+  const bool part = (f & KMG_FLAG_FORCE_PARTITIONED) || (!(f & KMG_FLAG_FORCE_HASH) && hint >= (1ull << 25));
+  if (!part) {
+    c->mode = kmg_ctx::MODE_TABLE;
+    if (!c->table.slots) {
+      kmg_status s = c->cfg.expected_distinct ? alloc_table_for(c, c->cfg.expected_distinct, &c->table) : alloc_table(c, 1ull << 22, &c->table);
+      if (s != KMG_OK) return s;
+    }
+    return KMG_OK;
+  }
+  c->mode = kmg_ctx::MODE_PARTITIONED;
+  uint32_t lg = c->cfg.parts_log2;
+  if (lg == 0) {
+    // aim for <= ~420 K keys per partition so that a 2^20-slot (16 MiB) table holds it at load <= 0.4
+    lg = pow2_ceil_log2((hint + 419999) / 420000);
+    lg = std::max<uint32_t>(lg, 4);
+  }
+  lg = std::min<uint32_t>(lg, pow2_ceil_log2(MAX_PARTS));
+  c->n_parts = 1u << lg;
+  CU(c, cudaMalloc(&c->d_part, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long)));
+  return KMG_OK;
+}
+
+// host prefix of per-partition counts -> Run offsets (host + device copy)
+kmg_status finish_run_offsets(kmg_ctx *c, Run &r, const std::vector<unsigned long long> &counts) {
+  r.h_offsets.assign(c->n_parts + 1, 0);
+  for (uint32_t p = 0; p < c->n_parts; ++p) r.h_offsets[p + 1] = r.h_offsets[p] + counts[p];
+  r.n = r.h_offsets[c->n_parts];
+  CU(c, cudaMalloc(&r.d_offsets, (c->n_parts + 1) * 8));
+  CU(c, cudaMemcpyAsync(r.d_offsets, r.h_offsets.data(), (c->n_parts + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  return KMG_OK;
+}
+
+kmg_status consolidate(kmg_ctx *c);
+
+kmg_status add_run(kmg_ctx *c, Run &&r) {
+  if (r.n == 0) { free_run(r); return KMG_OK; }
+  c->pending_bytes += r.n * (r.d_counts ? 16 : 8);
+  c->runs.push_back(std::move(r));
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  // consolidate early when the pending runs get numerous or large (keeps streaming inputs bounded in memory)
+  if (c->runs.size() + (c->has_result ? 1 : 0) >= (size_t)CONS_MAX_RUNS - 1 || c->pending_bytes > (uint64_t)total_b * 35 / 100)
+    return consolidate(c);
+  return KMG_OK;
+}
+
+// phase A over the packed stream: count pass, exact offsets, scatter pass -> one keys-run
+kmg_status scan_to_run(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
+  const uint64_t n_tiles = n_words_total / TILE_WORDS;
+  const uint64_t max_tiles = ((1ull << 32) - 1) / ((uint64_t)TILE_WORDS * 32);  // < 2^32 windows per launch
+  unsigned long long *d_cnt = c->d_part, *d_start = c->d_part + MAX_PARTS, *d_cur = c->d_part + 2 * MAX_PARTS;
+  for (uint64_t tile0 = 0; tile0 < n_tiles; tile0 += max_tiles) {
+    ScanInput in;
+    in.bases = c->d_bases + tile0 * TILE_WORDS;
+    in.valid = c->d_valid + tile0 * TILE_WORDS;
+    in.start = has_start ? c->d_start + tile0 * TILE_WORDS : nullptr;
+    in.n_tiles = std::min(max_tiles, n_tiles - tile0);
+    in.k = c->k;
+    timer_begin(c);
+    CU(c, cudaMemsetAsync(c->d_part, 0, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
+    CU(c, launch_scan_partition(in, c->n_parts, false, d_cnt, d_start, d_cur, nullptr, c->d_counters, c->stream));
+    std::vector<unsigned long long> counts(c->n_parts);
+    CU(c, cudaMemcpyAsync(counts.data(), d_cnt, c->n_parts * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    Run r;
+    kmg_status s = finish_run_offsets(c, r, counts);
+    if (s != KMG_OK) { free_run(r); return s; }
+    if (r.n) {
+      cudaError_t e = cudaMalloc(&r.d_keys, r.n * 8);
+      if (e != cudaSuccess) {  // make room by consolidating what is pending, then retry once
+        cudaGetLastError();
+        if ((s = consolidate(c)) != KMG_OK) { free_run(r); return s; }
+        e = cudaMalloc(&r.d_keys, r.n * 8);
+        if (e != cudaSuccess) { free_run(r); return cuda_fail(c, e, "cudaMalloc(partition buffer)"); }
+      }
+      CU(c, cudaMemcpyAsync(d_start, r.d_offsets, c->n_parts * 8, cudaMemcpyDeviceToDevice, c->stream));
+      CU(c, launch_scan_partition(in, c->n_parts, true, d_cnt, d_start, d_cur, r.d_keys, c->d_counters, c->stream));
+    }
+    timer_end(c);
+    if ((s = add_run(c, std::move(r))) != KMG_OK) return s;
+  }
+  return KMG_OK;
+}
+
+// weighted keys (device) -> one run (the receive side of the multi-GPU exchange)
+kmg_status keys_to_run(kmg_ctx *c, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n) {
+  unsigned long long *d_cnt = c->d_part, *d_start = c->d_part + MAX_PARTS, *d_cur = c->d_part + 2 * MAX_PARTS;
+  const uint64_t max_n = (1ull << 32) - 1;
+  for (uint64_t i0 = 0; i0 < n; i0 += max_n) {
+    const uint64_t m = std::min(max_n, n - i0);
+    CU(c, cudaMemsetAsync(c->d_part, 0, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
+    CU(c, launch_partition_keys(d_keys + i0, d_counts ? d_counts + i0 : nullptr, m, c->n_parts, false, d_cnt, d_start, d_cur, nullptr, nullptr,
+                                num_sms(), c->stream));
+    std::vector<unsigned long long> counts(c->n_parts);
+    CU(c, cudaMemcpyAsync(counts.data(), d_cnt, c->n_parts * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    Run r;
+    kmg_status s = finish_run_offsets(c, r, counts);
+    if (s != KMG_OK) { free_run(r); return s; }
+    cudaError_t e = cudaMalloc(&r.d_keys, r.n * 8);
+    if (e == cudaSuccess && d_counts) e = cudaMalloc(&r.d_counts, r.n * 8);
+    if (e != cudaSuccess) { free_run(r); return cuda_fail(c, e, "cudaMalloc(run)"); }
+    CU(c, cudaMemcpyAsync(d_start, r.d_offsets, c->n_parts * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, launch_partition_keys(d_keys + i0, d_counts ? d_counts + i0 : nullptr, m, c->n_parts, true, d_cnt, d_start, d_cur, r.d_keys, r.d_counts,
+                                num_sms(), c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));  // the caller may reuse d_keys right after we return
+    if ((s = add_run(c, std::move(r))) != KMG_OK) return s;
+  }
+  return KMG_OK;
+}
+
+// phase B: merge the consolidated result (if any) and all pending runs into a new consolidated run
+kmg_status consolidate(kmg_ctx *c) {
+  if (c->runs.empty()) return KMG_OK;
+  std::vector<Run *> in;
+  if (c->has_result && c->result.n) in.push_back(&c->result);
+  for (auto &r : c->runs) in.push_back(&r);
+  const uint32_t P = c->n_parts, R = (uint32_t)in.size();
+  if (R > (uint32_t)CONS_MAX_RUNS) return fail(c, KMG_ERR_STATE, "too many pending runs");
+  std::vector<uint64_t> n_p(P, 0);
+  uint64_t total = 0, max_np = 0;
+  for (uint32_t p = 0; p < P; ++p) {
+    for (auto *r : in) n_p[p] += r->h_offsets[p + 1] - r->h_offsets[p];
+    total += n_p[p];
+    max_np = std::max(max_np, n_p[p]);
+  }
+  if (max_np >= (1ull << 32)) return fail(c, KMG_ERR_STATE, "a partition holds more than 2^32 entries; use more partitions");
+  // per-partition table capacity: 2.2x its entries, capped at cap_limit (skewed partitions hold few DISTINCT keys);
+  // if a table does fill up the kernel raises error_flag and we retry with a doubled cap.
+  uint32_t cap_limit_log2 = std::max<uint32_t>(10, pow2_ceil_log2((uint64_t)(2.2 * 1.25 * (double)total / P) + 1));
+  Run out;
+  cudaError_t e = cudaMalloc(&out.d_keys, std::max<uint64_t>(total, 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&out.d_counts, std::max<uint64_t>(total, 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&out.d_offsets, (P + 1) * 8);
+  if (e != cudaSuccess) { free_run(out); return cuda_fail(c, e, "cudaMalloc(consolidated run)"); }
+
+  kmg_status st = KMG_OK;
+  for (int attempt = 0;; ++attempt) {
+    std::vector<uint32_t> cap_log2(P), nI(P), nC(P);
+    std::vector<ConsPhase> phases;
+    phases.reserve(2 * P + 1);
+    uint64_t tickets = 0;
+    uint32_t max_cap_log2 = 10;
+    for (uint32_t p = 0; p < P; ++p) {
+      cap_log2[p] = std::min(cap_limit_log2, std::max<uint32_t>(10, pow2_ceil_log2((uint64_t)(2.2 * (double)n_p[p]) + 1)));
+      max_cap_log2 = std::max(max_cap_log2, cap_log2[p]);
+      nI[p] = (uint32_t)std::max<uint64_t>(1, (n_p[p] + CONS_INSERT_CHUNK - 1) / CONS_INSERT_CHUNK);
+      nC[p] = n_p[p] ? (uint32_t)std::max<uint64_t>(1, (1ull << cap_log2[p]) / CONS_COMPACT_CHUNK) : 0;
+    }
+    auto push = [&](uint32_t p, bool compact) {
+      phases.push_back(ConsPhase{(uint32_t)tickets, p | (compact ? 0x80000000u : 0u)});
+      tickets += compact ? nC[p] : nI[p];
+    };
+    push(0, false);
+    for (uint32_t p = 1; p < P; ++p) { push(p, false); push(p - 1, true); }
+    push(P - 1, true);
+    if (tickets >= (1ull << 32)) { st = fail(c, KMG_ERR_STATE, "consolidation schedule too long"); break; }
+    phases.push_back(ConsPhase{(uint32_t)tickets, 0});  // sentinel
+
+    const uint64_t stride = 1ull << max_cap_log2;
+    uint64_t *d_tables = nullptr;
+    uint8_t *d_meta = nullptr;
+    const size_t meta_u32 = (size_t)P * 7 + 8;  // cap_log2, nI, nC, done_I, done_C, distinct, out_cursor, ticket, error
+    const size_t phases_bytes = phases.size() * sizeof(ConsPhase);
+    e = cudaMalloc(&d_tables, (size_t)CONS_NBUF * stride * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&d_meta, meta_u32 * 4 + phases_bytes + 16);
+    if (e != cudaSuccess) { cudaFree(d_tables); cudaFree(d_meta); st = cuda_fail(c, e, "cudaMalloc(consolidation tables)"); break; }
+    uint32_t *m = reinterpret_cast<uint32_t *>(d_meta);
+    ConsParams prm{};
+    prm.n_parts = P; prm.R = R; prm.total_tickets = (uint32_t)tickets; prm.preagg = !(c->cfg.flags & KMG_FLAG_NO_PREAGG);
+    for (uint32_t r = 0; r < R; ++r) prm.runs[r] = ConsRun{in[r]->d_keys, in[r]->d_counts, in[r]->d_offsets};
+    prm.part_cap_log2 = m; prm.part_nI = m + P; prm.part_nC = m + 2 * P;
+    prm.done_I = m + 3 * P; prm.done_C = m + 4 * P; prm.distinct = m + 5 * P; prm.out_cursor = m + 6 * P;
+    prm.ticket = m + 7 * P; prm.error_flag = m + 7 * P + 1;
+    prm.phases = reinterpret_cast<const ConsPhase *>(m + meta_u32);
+    prm.tables = d_tables; prm.table_stride_slots = stride;
+    prm.out_keys = out.d_keys; prm.out_counts = out.d_counts;
+    prm.out_base = reinterpret_cast<unsigned long long *>(out.d_offsets);
+    cudaStream_t s = c->stream;
+    e = cudaMemsetAsync(d_meta, 0, meta_u32 * 4, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m, cap_log2.data(), P * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m + P, nI.data(), P * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m + 2 * P, nC.data(), P * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m + meta_u32, phases.data(), phases_bytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(out.d_offsets, 0xFF, (P + 1) * 8, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(out.d_offsets, 0, 8, s);
+    if (e == cudaSuccess) e = launch_table_init(HashTable{d_tables, (uint64_t)CONS_NBUF * stride}, s);
+    timer_begin(c, 1);
+    if (e == cudaSuccess) e = launch_consolidate(prm, num_sms(), s);
+    timer_end(c);
+    uint32_t err_flag = 0;
+    out.h_offsets.assign(P + 1, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&err_flag, prm.error_flag, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out.h_offsets.data(), out.d_offsets, (P + 1) * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_tables); cudaFree(d_meta);
+    if (e != cudaSuccess) { st = cuda_fail(c, e, "consolidate"); break; }
+    if (!err_flag) break;
+    if (attempt >= 12 || cap_limit_log2 >= 34) { st = fail(c, KMG_ERR_TABLE_FULL, "partition table overflow could not be resolved"); break; }
+    ++cap_limit_log2;  // some partition had more distinct keys than its capped table: retry with larger tables
+  }
+  if (st != KMG_OK) { free_run(out); return st; }
+  out.n = out.h_offsets[P];
+  if (c->has_result) free_run(c->result);
+  for (auto &r : c->runs) free_run(r);
+  c->runs.clear();
+  c->pending_bytes = 0;
+  // give back the slack (upper bound was one slot per input entry) when it is worth a copy
+  if (out.n && out.n < total / 2) {
+    uint64_t *k2 = nullptr, *c2 = nullptr;
+    if (cudaMalloc(&k2, out.n * 8) == cudaSuccess && cudaMalloc(&c2, out.n * 8) == cudaSuccess) {
+      cudaMemcpyAsync(k2, out.d_keys, out.n * 8, cudaMemcpyDeviceToDevice, c->stream);
+      cudaMemcpyAsync(c2, out.d_counts, out.n * 8, cudaMemcpyDeviceToDevice, c->stream);
+      cudaStreamSynchronize(c->stream);
+      cudaFree(out.d_keys); cudaFree(out.d_counts);
+      out.d_keys = k2; out.d_counts = c2;
+    } else { cudaGetLastError(); cudaFree(k2); cudaFree(c2); }
+  }
+  c->result = std::move(out);
+  c->has_result = true;
+  c->n_consolidations++;
+  return KMG_OK;
 }
 
 // Run the counting scan over a packed stream of n_words_total words (already in d_bases/d_valid/d_start).
 kmg_status scan_packed(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
   const uint64_t n_tiles = n_words_total / TILE_WORDS;
+  kmg_status ms = decide_mode(c, n_words_total * 32);
+  if (ms != KMG_OK) return ms;
+  if (c->mode == kmg_ctx::MODE_PARTITIONED) return scan_to_run(c, n_words_total, has_start);
   uint64_t tile0 = 0;
   timer_begin(c);
   while (tile0 < n_tiles) {
@@ -345,6 +611,9 @@ KMG_EXPORT void kmg_destroy(kmg_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   timers_collect(c);
+  for (auto &r : c->runs) free_run(r);
+  if (c->has_result) free_run(c->result);
+  cudaFree(c->d_part);
   cudaFree(c->table.slots); cudaFree(c->dense); cudaFree(c->d_counters); cudaFree(c->d_stats);
   cudaFree(c->d_bases); cudaFree(c->d_valid); cudaFree(c->d_start);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -402,17 +671,20 @@ KMG_EXPORT kmg_status kmg_create(const kmg_config *cfg, kmg_ctx **out) {
   CUC(cudaHostAlloc(&c->h_counters, 16 * sizeof(unsigned long long), cudaHostAllocDefault));
   if (cfg->batch_bases) c->batch_bases = std::max<uint64_t>(round_up(cfg->batch_bases, 32), 4096);
   c->use_dense = (cfg->flags & KMG_FLAG_FORCE_DIRECT) ||
-                 (!(cfg->flags & KMG_FLAG_FORCE_HASH) && cfg->k <= (uint32_t)DENSE_DEFAULT_MAX_K);
+                 (!(cfg->flags & (KMG_FLAG_FORCE_HASH | KMG_FLAG_FORCE_PARTITIONED)) && cfg->k <= (uint32_t)DENSE_DEFAULT_MAX_K);
   if (c->use_dense) {
     c->dense_n = 1ull << (2 * c->k);
     CUC(cudaMalloc(&c->dense, c->dense_n * 8));
     CUC(cudaMemsetAsync(c->dense, 0, c->dense_n * 8, c->stream));
-  } else {
-    kmg_status s;
-    if (cfg->expected_distinct) s = alloc_table_for(c, cfg->expected_distinct, &c->table);
-    else s = alloc_table(c, 1ull << 22, &c->table);
-    if (s != KMG_OK) return bail(s);
   }
+  // hash table / partition buffers are allocated by decide_mode() at the first feeding call, when the
+  // input size is known (small inputs: one HBM table; large inputs: the partitioned pipeline)
+  if ((cfg->flags & KMG_FLAG_FORCE_PARTITIONED) && (cfg->flags & (KMG_FLAG_FORCE_HASH | KMG_FLAG_FORCE_DIRECT))) {
+    c->err = "FORCE_PARTITIONED excludes FORCE_HASH / FORCE_DIRECT";
+    return bail(KMG_ERR_INVALID_ARG);
+  }
+  if (cfg->parts_log2 > 13) { c->err = "parts_log2 must be <= 13"; return bail(KMG_ERR_INVALID_ARG); }
+  if (cfg->flags & KMG_FLAG_FORCE_PARTITIONED) c->use_dense = false;
   CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
   *out = c;
@@ -424,12 +696,19 @@ KMG_EXPORT kmg_status kmg_reset(kmg_ctx *c) {
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaStreamSynchronize(c->copy_stream));
   if (c->use_dense) CU(c, cudaMemsetAsync(c->dense, 0, c->dense_n * 8, c->stream));
-  else CU(c, launch_table_init(c->table, c->stream));
+  else if (c->mode == kmg_ctx::MODE_TABLE) CU(c, launch_table_init(c->table, c->stream));
+  else if (c->mode == kmg_ctx::MODE_PARTITIONED) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (auto &r : c->runs) free_run(r);
+    c->runs.clear();
+    if (c->has_result) free_run(c->result);
+    c->has_result = false; c->pending_bytes = 0; c->n_consolidations = 0;
+  }
   CU(c, cudaMemsetAsync(c->d_counters, 0, CTR_N * sizeof(unsigned long long), c->stream));
-  c->distinct_ub = 0; c->n_records = c->n_bases = c->h2d_bytes = 0; c->kernel_ms = 0.0;
+  c->distinct_ub = 0; c->n_records = c->n_bases = c->h2d_bytes = 0;
   CU(c, cudaStreamSynchronize(c->stream));
   timers_collect(c);
-  c->kernel_ms = 0.0;
+  c->kernel_ms = c->cat_ms[0] = c->cat_ms[1] = 0.0;
   return KMG_OK;
 }
 
@@ -558,7 +837,10 @@ KMG_EXPORT kmg_status kmg_insert_keys_device(kmg_ctx *c, const uint64_t *d_keys,
   if (n == 0) return KMG_OK;
   if (!d_keys) return fail(c, KMG_ERR_INVALID_ARG, "d_keys is NULL");
   CU(c, cudaSetDevice(c->device));
+  kmg_status ms = decide_mode(c, n);
+  if (ms != KMG_OK) return ms;
   if (c->use_dense) { CU(c, launch_insert_keys_dense(c->dense, d_keys, d_counts, n, c->d_counters, c->stream)); return KMG_OK; }
+  if (c->mode == kmg_ctx::MODE_PARTITIONED) return keys_to_run(c, d_keys, d_counts, n);
   uint64_t done = 0;
   while (done < n) {
     uint64_t granted = 0;
@@ -574,7 +856,7 @@ KMG_EXPORT kmg_status kmg_extract_keys_device(kmg_ctx *c, const uint8_t *d_seq, 
                                               uint64_t n_records, uint64_t n_bytes, uint32_t n_shards, uint64_t *d_keys_out,
                                               uint64_t cap, uint64_t *shard_counts_out) {
   if (!c || !shard_counts_out) return KMG_ERR_INVALID_ARG;
-  if (n_shards < 1 || n_shards > 4096) return fail(c, KMG_ERR_INVALID_ARG, "n_shards must be in 1..=4096");
+  if (n_shards < 1 || n_shards > (uint32_t)MAX_PARTS) return fail(c, KMG_ERR_INVALID_ARG, "n_shards must be in 1..=8192");
   if (((uintptr_t)d_seq & 15) || ((uintptr_t)d_qual & 15)) return fail(c, KMG_ERR_INVALID_ARG, "d_seq / d_qual must be 16-byte aligned");
   CU(c, cudaSetDevice(c->device));
   for (uint32_t i = 0; i < n_shards; ++i) shard_counts_out[i] = 0;
@@ -587,13 +869,15 @@ KMG_EXPORT kmg_status kmg_extract_keys_device(kmg_ctx *c, const uint8_t *d_seq, 
   CU(c, launch_ingest(d_seq, use_q ? d_qual : nullptr, n_bytes, thr, n_words_total, c->d_bases, c->d_valid, c->stream));
   const bool has_start = d_offsets != nullptr && n_records > 1;
   if (has_start) CU(c, launch_start_bits(d_offsets, n_records, 0, n_bytes, n_words_total, c->d_start, c->stream));
+  if (n_bytes >= (1ull << 32)) return fail(c, KMG_ERR_INVALID_ARG, "kmg_extract_keys_device handles < 2^32 bytes per call");
   unsigned long long *d_pc = nullptr;
-  CU(c, cudaMalloc(&d_pc, 2 * (size_t)n_shards * 8 + 64));
+  CU(c, cudaMalloc(&d_pc, 3 * (size_t)n_shards * 8 + 64));
   unsigned long long *d_cur = d_pc + n_shards;
-  unsigned long long *d_ctr = d_cur + n_shards;  // scratch counters (windows of this call only)
-  CU(c, cudaMemsetAsync(d_pc, 0, 2 * (size_t)n_shards * 8 + 64, c->stream));
+  unsigned long long *d_ps = d_cur + n_shards;
+  unsigned long long *d_ctr = d_ps + n_shards;  // scratch counters (windows of this call only)
+  CU(c, cudaMemsetAsync(d_pc, 0, 3 * (size_t)n_shards * 8 + 64, c->stream));
   ScanInput in{c->d_bases, c->d_valid, has_start ? c->d_start : nullptr, n_words_total / TILE_WORDS, c->k};
-  cudaError_t e = launch_scan_partition(in, n_shards, false, d_pc, d_cur, nullptr, d_ctr, c->stream);
+  cudaError_t e = launch_scan_partition(in, n_shards, false, d_pc, d_ps, d_cur, nullptr, d_ctr, c->stream);
   std::vector<unsigned long long> h(n_shards);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), d_pc, n_shards * 8, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -602,8 +886,8 @@ KMG_EXPORT kmg_status kmg_extract_keys_device(kmg_ctx *c, const uint8_t *d_seq, 
   std::vector<unsigned long long> prefix(n_shards);
   for (uint32_t i = 0; i < n_shards; ++i) { prefix[i] = total; total += h[i]; shard_counts_out[i] = h[i]; }
   if (total > cap || (total && !d_keys_out)) { cudaFree(d_pc); return fail(c, KMG_ERR_CAPACITY, "d_keys_out too small: need " + std::to_string(total)); }
-  e = cudaMemcpyAsync(d_cur, prefix.data(), n_shards * 8, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess) e = launch_scan_partition(in, n_shards, true, d_pc, d_cur, d_keys_out, d_ctr, c->stream);
+  e = cudaMemcpyAsync(d_ps, prefix.data(), n_shards * 8, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = launch_scan_partition(in, n_shards, true, d_pc, d_ps, d_cur, d_keys_out, d_ctr, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(d_pc);
   if (e != cudaSuccess) return cuda_fail(c, e, "partition scatter pass");
@@ -618,8 +902,9 @@ KMG_EXPORT kmg_status kmg_finalize(kmg_ctx *c, kmg_summary *out) {
   kmg_status s = read_counters(c);
   if (s != KMG_OK) return s;
   for (auto &st : c->st) { st.h2d_pending = false; st.compute_pending = false; }
+  if (c->mode == kmg_ctx::MODE_PARTITIONED && (s = consolidate(c)) != KMG_OK) return s;
   timers_collect(c);
-  if (!c->use_dense) c->distinct_ub = c->h_counters[CTR_DISTINCT];
+  if (c->mode == kmg_ctx::MODE_TABLE) c->distinct_ub = c->h_counters[CTR_DISTINCT];
   if (!out) return KMG_OK;
   memset(out, 0, sizeof *out);
   CU(c, launch_table_stats(view_of(c), 1, c->d_stats, c->stream));
@@ -629,10 +914,12 @@ KMG_EXPORT kmg_status kmg_finalize(kmg_ctx *c, kmg_summary *out) {
   out->n_records = c->n_records; out->n_bases = c->n_bases;
   out->n_windows = h[2];
   out->n_distinct = h[0]; out->max_count = h[1];
-  out->table_capacity = c->use_dense ? c->dense_n : c->table.cap;
-  out->path = c->use_dense ? 1 : 0;
-  out->n_grows = c->n_grows;
+  out->table_capacity = c->use_dense ? c->dense_n : c->mode == kmg_ctx::MODE_PARTITIONED ? c->n_parts : c->table.cap;
+  out->path = c->use_dense ? 1 : c->mode == kmg_ctx::MODE_PARTITIONED ? 2 : 0;
+  out->n_grows = c->mode == kmg_ctx::MODE_PARTITIONED ? c->n_consolidations : c->n_grows;
   out->kernel_ns = (uint64_t)(c->kernel_ms * 1e6);
+  out->scan_ns = (uint64_t)(c->cat_ms[0] * 1e6);
+  out->consolidate_ns = (uint64_t)(c->cat_ms[1] * 1e6);
   out->h2d_bytes = c->h2d_bytes;
   return KMG_OK;
 }
@@ -640,6 +927,7 @@ KMG_EXPORT kmg_status kmg_finalize(kmg_ctx *c, kmg_summary *out) {
 namespace {
 kmg_status count_filtered(kmg_ctx *c, uint64_t min_count, uint64_t *n) {
   CU(c, cudaStreamSynchronize(c->copy_stream));
+  if (c->mode == kmg_ctx::MODE_PARTITIONED) { kmg_status s = consolidate(c); if (s != KMG_OK) return s; }
   CU(c, launch_table_stats(view_of(c), min_count, c->d_stats, c->stream));
   unsigned long long h[3];
   CU(c, cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -698,8 +986,13 @@ KMG_EXPORT kmg_status kmg_histogram(kmg_ctx *c, uint64_t min_count, uint64_t *co
   CU(c, cudaStreamSynchronize(c->copy_stream));
   kmg_status s = read_counters(c);
   if (s != KMG_OK) return s;
-  // counts >= HIST_DENSE_BINS: at most windows / HIST_DENSE_BINS distinct keys can reach that
-  const uint64_t ov_cap = c->h_counters[CTR_WINDOWS] / HIST_DENSE_BINS + 16;
+  if (c->mode == kmg_ctx::MODE_PARTITIONED && (s = consolidate(c)) != KMG_OK) return s;
+  // counts >= HIST_DENSE_BINS: at most (sum of counts) / HIST_DENSE_BINS distinct keys can reach that
+  CU(c, launch_table_stats(view_of(c), 1, c->d_stats, c->stream));
+  unsigned long long hs[3];
+  CU(c, cudaMemcpyAsync(hs, c->d_stats, sizeof hs, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  const uint64_t ov_cap = hs[2] / HIST_DENSE_BINS + 16;
   unsigned long long *d_bins = nullptr;
   uint64_t *d_ov = nullptr;
   CU(c, cudaMalloc(&d_bins, HIST_DENSE_BINS * 8));

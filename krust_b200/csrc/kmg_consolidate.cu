@@ -55,7 +55,7 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *scratch 
 
 }  // namespace
 
-__global__ void __launch_bounds__(CONS_THREADS) consolidate_kernel(ConsParams P) {
+__global__ void __launch_bounds__(CONS_THREADS, 2) consolidate_kernel(ConsParams P) {
   __shared__ uint64_t seg_begin[CONS_MAX_RUNS];
   __shared__ uint32_t seg_prefix[CONS_MAX_RUNS + 1];
   __shared__ uint32_t scratch[64];
@@ -115,6 +115,24 @@ __global__ void __launch_bounds__(CONS_THREADS) consolidate_kernel(ConsParams P)
           const uint64_t src = seg_begin[r] + (idx - seg_prefix[r]);
           key[j] = __ldcs(P.runs[r].keys + src);
           w[j] = P.runs[r].counts ? __ldcs(P.runs[r].counts + src) : 1ull;
+        }
+      }
+      if (P.preagg) {
+        // Warp run-length pre-aggregation: phase A writes the keys of consecutive windows next to each other,
+        // so homopolymer / tandem-repeat runs arrive as runs of equal keys in adjacent lanes.  The head lane of
+        // each run upserts once with the run length; this bounds same-address atomic bursts on skewed inputs.
+        const int lane = tid & 31;
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) {
+          const uint64_t kk = w[j] ? key[j] : EMPTY_KEY;
+          const uint64_t kp = __shfl_up_sync(0xffffffffu, kk, 1);
+          const bool head = lane == 0 || kp != kk;
+          const uint32_t heads = __ballot_sync(0xffffffffu, head);
+          if (__all_sync(0xffffffffu, w[j] <= 1ull)) {  // unit weights only (keys-runs); pair-runs are already distinct per run
+            const uint32_t above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
+            const uint32_t end = above ? (uint32_t)__ffs(above) - 1u : 32u;
+            if (w[j]) w[j] = head ? (uint64_t)(end - lane) : 0ull;
+          }
         }
       }
 #pragma unroll

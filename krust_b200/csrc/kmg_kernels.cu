@@ -329,8 +329,9 @@ struct PartCountEmit {
   }
 };
 struct PartScatterEmit {
-  uint32_t *cursor;            // smem: running offset inside this tile's reservation
-  const uint64_t *tile_base;   // smem: global index where this tile's keys of partition p start
+  uint32_t *cursor;                      // smem: running offset inside this tile's reservation
+  const uint32_t *tile_off;              // smem: where this tile's range starts inside partition p
+  const unsigned long long *part_start;  // global: where partition p starts in `out`
   uint64_t *out;
   uint32_t n_parts;
   template <int G>
@@ -340,25 +341,27 @@ struct PartScatterEmit {
       if ((okg >> j) & 1u) {
         const uint32_t p = part_of(key[j], n_parts);
         const uint32_t o = atomicAdd(cursor + p, 1u);
-        out[tile_base[p] + o] = key[j];
+        __stcs(out + (__ldg(part_start + p) + tile_off[p] + o), key[j]);
       }
   }
 };
 
 // pass 1 (SCATTER == false): per-partition totals into part_counts[].
-// pass 2 (SCATTER == true) : part_cursor[] must hold the exclusive prefix of part_counts; each tile
-// histograms its keys in shared memory, reserves one contiguous range per partition with a single
-// global atomic, then re-derives the keys and writes them into that range.
+// pass 2 (SCATTER == true) : part_start[] holds the exclusive prefix of those totals and part_cursor[]
+// starts at zero; each tile histograms its keys in shared memory, reserves one contiguous range per
+// partition with a single global atomic, then re-derives the keys and writes them into that range
+// (a launch never carries more than 2^32-1 windows, so in-partition offsets fit 32 bits).
 template <bool SCATTER>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_partition_kernel(ScanInput in, uint32_t n_parts,
                                                                       unsigned long long *part_counts,
+                                                                      const unsigned long long *part_start,
                                                                       unsigned long long *part_cursor, uint64_t *out,
                                                                       unsigned long long *counters) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
   __shared__ __align__(8) uint64_t bars[2];
   uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw + 2 * sizeof(TileSmem));
-  uint64_t *tile_base = reinterpret_cast<uint64_t *>(hist + n_parts + (n_parts & 1));
+  uint32_t *tile_off = hist + n_parts;
   const int tid = threadIdx.x;
   const bool has_start = in.start != nullptr;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
@@ -384,11 +387,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_partition_kernel(ScanInput 
       __syncthreads();
       for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) {
         const uint32_t c = hist[p];
-        tile_base[p] = c ? atomicAdd(part_cursor + p, (unsigned long long)c) : 0;
+        tile_off[p] = c ? (uint32_t)atomicAdd(part_cursor + p, (unsigned long long)c) : 0u;
         hist[p] = 0;
       }
       __syncthreads();
-      PartScatterEmit e{hist, tile_base, out, n_parts};
+      PartScatterEmit e{hist, tile_off, part_start, out, n_parts};
 #pragma unroll 1
       for (int r = 0; r < WORDS_PER_THREAD; ++r) scan_word<8>(ts, r * SCAN_THREADS + tid, in.k, has_start, e);
       __syncthreads();
@@ -459,6 +462,7 @@ __global__ void rehash_kernel(HashTable from, HashTable to, unsigned long long *
 
 // A "view" unifies both table kinds for the read-side kernels: entry i is (key, count); empty if count == 0.
 __device__ __forceinline__ bool view_get(const TableView &v, uint64_t i, uint64_t &key, uint64_t &count) {
+  if (v.pair_keys) { key = v.pair_keys[i]; count = v.pair_counts[i]; return true; }
   if (v.dense) { key = i; count = v.dense[i]; return count != 0; }
   ulonglong2 s = reinterpret_cast<const ulonglong2 *>(v.slots)[i];
   key = s.x; count = s.y + 1;  // slots store occurrences - 1
@@ -535,10 +539,10 @@ __global__ void __launch_bounds__(256) histogram_kernel(TableView v, uint64_t mi
 // =================================================================================================
 // Host-side launch wrappers
 // =================================================================================================
-static std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_launches{0};
 uint64_t kernel_launches() { return g_launches.load(std::memory_order_relaxed); }
 static int g_num_sms = 0;
-static int num_sms() {
+int num_sms() {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -617,21 +621,22 @@ cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, un
 }
 
 cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool scatter, unsigned long long *part_counts,
-                                  unsigned long long *part_cursor, uint64_t *out, unsigned long long *counters, cudaStream_t s) {
+                                  const unsigned long long *part_start, unsigned long long *part_cursor, uint64_t *out,
+                                  unsigned long long *counters, cudaStream_t s) {
   unsigned grid = (unsigned)(in.n_tiles < (uint64_t)num_sms() * SCAN_CTAS_PER_SM ? in.n_tiles : (uint64_t)num_sms() * SCAN_CTAS_PER_SM);
   if (grid == 0) return cudaSuccess;
-  const size_t smem = 2 * sizeof(TileSmem) + (n_parts + (n_parts & 1)) * sizeof(uint32_t) + n_parts * sizeof(uint64_t);
+  const size_t smem = 2 * sizeof(TileSmem) + 2 * (size_t)n_parts * sizeof(uint32_t);
   cudaError_t e;
   if (scatter) {
     auto kern = scan_partition_kernel<true>;
     if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    kern<<<grid, SCAN_THREADS, smem, s>>>(in, n_parts, part_counts, part_cursor, out, counters);
+    kern<<<grid, SCAN_THREADS, smem, s>>>(in, n_parts, part_counts, part_start, part_cursor, out, counters);
   } else {
     auto kern = scan_partition_kernel<false>;
     if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    kern<<<grid, SCAN_THREADS, smem, s>>>(in, n_parts, part_counts, part_cursor, out, counters);
+    kern<<<grid, SCAN_THREADS, smem, s>>>(in, n_parts, part_counts, part_start, part_cursor, out, counters);
   }
   return cudaGetLastError();
 }

@@ -21,9 +21,43 @@ struct HashTable {
 
 // read-side view over either table kind
 struct TableView {
-  const uint64_t *slots;             // hash path (nullptr on the direct path)
+  const uint64_t *slots;             // v1 hash table (key, occurrences-1) slots
   const unsigned long long *dense;   // direct path: 4^k counters
-  uint64_t n;                        // slots or 4^k
+  const uint64_t *pair_keys;         // partitioned path: consolidated run, SoA
+  const uint64_t *pair_counts;
+  uint64_t n;                        // slots, 4^k or number of pairs
+};
+
+// ---- partitioned pipeline (phase B, kmg_consolidate.cu) --------------------------------------------
+constexpr int CONS_THREADS = 512;
+constexpr int CONS_CTAS_PER_SM = 2;
+constexpr int CONS_INSERT_CHUNK = 4096;   // keys per insert ticket
+constexpr int CONS_COMPACT_CHUNK = 4096;  // table slots per compact ticket
+constexpr int CONS_NBUF = 3;              // L2-resident table buffers in flight
+constexpr int CONS_MAX_RUNS = 16;
+constexpr int MAX_PARTS = 8192;
+
+struct ConsRun {
+  const uint64_t *keys;
+  const uint64_t *counts;   // nullptr: every key counts 1
+  const uint64_t *offsets;  // device, n_parts + 1 entries
+};
+struct ConsPhase {
+  uint32_t first_ticket;
+  uint32_t part_and_type;  // bit 31: 1 = compact, 0 = insert
+};
+struct ConsParams {
+  uint32_t n_parts, R, total_tickets, preagg;
+  ConsRun runs[CONS_MAX_RUNS];
+  const ConsPhase *phases;         // schedule order, terminated by a sentinel with first_ticket = total_tickets
+  const uint32_t *part_cap_log2;   // table capacity (log2 slots) of each partition
+  const uint32_t *part_nI, *part_nC;  // tickets per phase
+  uint64_t *tables;                // CONS_NBUF buffers of table_stride_slots (key, count-1) slots
+  uint64_t table_stride_slots;
+  uint64_t *out_keys, *out_counts;
+  unsigned long long *out_base;    // n_parts + 1; [0] = 0, rest ~0 until published
+  uint32_t *done_I, *done_C, *distinct, *out_cursor;  // n_parts each, zeroed
+  uint32_t *ticket, *error_flag;
 };
 
 enum { CTR_WINDOWS = 0, CTR_DISTINCT = 1, CTR_FULL = 2, CTR_SCRATCH = 3, CTR_N = 8 };
@@ -43,8 +77,17 @@ cudaError_t launch_synth_uniform(uint64_t seed, uint64_t first_base, uint64_t n,
 cudaError_t launch_scan_hash(const ScanInput &in, HashTable t, unsigned long long *counters, uint32_t flags, cudaStream_t s);
 cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, unsigned long long *counters, uint32_t flags,
                               cudaStream_t s);
+// scatter == false: part_counts[p] += keys of partition p.  scatter == true: keys are written to
+// out[part_start[p] + ...]; part_cursor[] (zeroed) hands out ranges inside each partition.
 cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool scatter, unsigned long long *part_counts,
-                                  unsigned long long *part_cursor, uint64_t *out, unsigned long long *counters, cudaStream_t s);
+                                  const unsigned long long *part_start, unsigned long long *part_cursor, uint64_t *out,
+                                  unsigned long long *counters, cudaStream_t s);
+cudaError_t launch_partition_keys(const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n, uint32_t n_parts, bool scatter,
+                                  unsigned long long *part_counts, const unsigned long long *part_start,
+                                  unsigned long long *part_cursor, uint64_t *out_keys, uint64_t *out_counts, int num_sms,
+                                  cudaStream_t s);
+cudaError_t launch_consolidate(const ConsParams &P, int num_sms, cudaStream_t s);
+int num_sms();
 cudaError_t launch_table_init(HashTable t, cudaStream_t s);
 cudaError_t launch_insert_keys(HashTable t, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n,
                                unsigned long long *counters, cudaStream_t s);

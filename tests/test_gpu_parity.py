@@ -12,12 +12,16 @@ from tests import kats
 
 pytestmark = pytest.mark.gpu
 
-FLAG_SETS = {"auto": 0, "hash": _lib.KMG_FLAG_FORCE_HASH, "hash_nopreagg": _lib.KMG_FLAG_FORCE_HASH | _lib.KMG_FLAG_NO_PREAGG}
+PART = _lib.KMG_FLAG_FORCE_PARTITIONED
+FLAG_SETS = {"auto": 0, "hash": _lib.KMG_FLAG_FORCE_HASH, "hash_nopreagg": _lib.KMG_FLAG_FORCE_HASH | _lib.KMG_FLAG_NO_PREAGG,
+             "part": PART, "part_nopreagg": PART | _lib.KMG_FLAG_NO_PREAGG}
 
 
-def gpu_count(k, records, quals=None, min_quality=None, flags=0, batch_bases=0, min_count=1, expected_distinct=0):
+def gpu_count(k, records, quals=None, min_quality=None, flags=0, batch_bases=0, min_count=1, expected_distinct=0, parts_log2=0):
+    if (flags & PART) and parts_log2 == 0:
+        parts_log2 = 1 + (k % 7)  # exercise many different partition counts (2..128) on small inputs
     with kb.GpuKmerCounter(k, min_quality=min_quality, flags=flags, batch_bases=batch_bases,
-                           expected_distinct=expected_distinct) as c:
+                           expected_distinct=expected_distinct, parts_log2=parts_log2) as c:
         c.count_records(records, quals)
         s = c.finalize()
         keys, counts = c.export(min_count, sorted=True)
@@ -51,7 +55,7 @@ def _random_records(rng, n_rec, max_len, alphabet, min_len=0):
     return recs, quals
 
 
-@pytest.mark.parametrize("flags", ["auto", "hash"])
+@pytest.mark.parametrize("flags", ["auto", "hash", "part"])
 def test_randomised_differential_all_k(flags):
     """Random records with N / IUPAC / blanks / lower case, quality thresholds, every k in 1..32."""
     rng = np.random.default_rng(77)
@@ -77,6 +81,10 @@ def test_chunked_feed_equals_single_shot(k):
     for bb in (4096, 10_000):
         gpu = gpu_count(k, recs, quals, 20, _lib.KMG_FLAG_FORCE_HASH, batch_bases=bb)
         assert_same(gpu, oracle)
+        # partitioned pipeline: every chunk becomes a run; > 15 runs force intermediate consolidations (result + runs merge)
+        gpu = gpu_count(k, recs, quals, 20, PART, batch_bases=bb, parts_log2=5)
+        assert_same(gpu, oracle)
+        assert gpu[2]["path"] == 2 and gpu[2]["n_grows"] >= 2 and gpu[2]["n_windows"] == oracle[2]
 
 
 def test_many_short_reads_record_boundaries():
@@ -94,6 +102,8 @@ def test_many_short_reads_record_boundaries():
         oracle = orc.count_records(k, recs, mode="rolling")
         assert_same(gpu_count(k, recs, flags=_lib.KMG_FLAG_FORCE_HASH), oracle)
         assert_same(gpu_count(k, recs, flags=_lib.KMG_FLAG_FORCE_HASH, batch_bases=8192), oracle)
+        assert_same(gpu_count(k, recs, flags=PART, parts_log2=6), oracle)
+        assert_same(gpu_count(k, recs, flags=PART, batch_bases=8192, parts_log2=13), oracle)
 
 
 def test_k32_poly_t_and_empty_sentinel():
@@ -110,7 +120,7 @@ def test_skewed_high_multiplicity():
     recs = [b"A" * 100_000, b"AC" * 50_000, b"ACGTTGCA" * 20_000, b"GATTACA" * 10_000]
     for k in (5, 21, 32):
         oracle = orc.count_records(k, recs, mode="rolling")
-        for f in ("auto", "hash", "hash_nopreagg"):
+        for f in ("auto", "hash", "hash_nopreagg", "part", "part_nopreagg"):
             assert_same(gpu_count(k, recs, flags=FLAG_SETS[f]), oracle)
 
 
@@ -134,9 +144,9 @@ def test_min_count_histogram_and_kmix(tmp_path):
     rng = np.random.default_rng(8)
     genome = bytes(rng.choice(list(b"ACGT"), size=5000).tolist())
     recs = [genome[i:i + 200] for i in rng.integers(0, 4800, size=2000)]
-    for k, flags in ((12, 0), (21, _lib.KMG_FLAG_FORCE_HASH)):
+    for k, flags in ((12, 0), (21, _lib.KMG_FLAG_FORCE_HASH), (21, PART), (12, PART)):
         okeys, ocounts, _ = orc.count_records(k, recs, mode="rolling")
-        with kb.GpuKmerCounter(k, flags=flags) as c:
+        with kb.GpuKmerCounter(k, flags=flags, parts_log2=4 if flags & PART else 0) as c:
             c.count_records(recs)
             s = c.finalize()
             assert s["max_count"] == int(ocounts.max())
@@ -167,7 +177,7 @@ def test_histogram_overflow_tail():
     """counts >= 65536 leave the dense bins and go through the overflow list."""
     recs = [b"A" * 70_000, b"C" * 200_000, b"ACGT" * 10]
     okeys, ocounts, _ = orc.count_records(4, recs, mode="rolling")
-    for flags in (0, _lib.KMG_FLAG_FORCE_HASH):
+    for flags in (0, _lib.KMG_FLAG_FORCE_HASH, PART):
         with kb.GpuKmerCounter(4, flags=flags) as c:
             c.count_records(recs)
             c.finalize()
@@ -258,7 +268,7 @@ def test_device_resident_path_and_synthetic_generator():
     n = 3_000_000
     dev = torch.device("cuda:0")
     buf = torch.empty(n, dtype=torch.uint8, device=dev)
-    for k, flags in ((21, 0), (12, 0), (5, 0), (31, 0), (9, _lib.KMG_FLAG_FORCE_HASH)):
+    for k, flags in ((21, 0), (12, 0), (5, 0), (31, 0), (9, _lib.KMG_FLAG_FORCE_HASH), (21, PART), (32, PART), (7, PART)):
         with kb.GpuKmerCounter(k, flags=flags) as c:
             c.synth_uniform_device(42, 0, n, buf.data_ptr())
             host = buf.cpu().numpy()
@@ -298,10 +308,10 @@ def test_extract_and_insert_equal_direct_count():
             uk, uc = np.unique(keys, return_counts=True)
             assert_same((uk, uc.astype(np.uint64)), oracle)
             # upsert the buckets into a fresh table, half of them as (key, count) pairs
-            with kb.GpuKmerCounter(k, flags=_lib.KMG_FLAG_FORCE_HASH) as c2:
+            for flags2 in (_lib.KMG_FLAG_FORCE_HASH, PART):
+              with kb.GpuKmerCounter(k, flags=flags2, parts_log2=5 if flags2 == PART else 0) as c2:
                 half = len(keys) // 2
                 c2.insert_keys_device(out.data_ptr(), half)
-                k2 = torch.from_numpy(uk.view(np.int64)).to(dev)
                 rest_k, rest_c = np.unique(keys[half:], return_counts=True)
                 rk = torch.from_numpy(rest_k.view(np.int64)).to(dev); rc = torch.from_numpy(rest_c.astype(np.int64)).to(dev)
                 c2.insert_keys_device(rk.data_ptr(), len(rest_k), rc.data_ptr())
@@ -309,7 +319,7 @@ def test_extract_and_insert_equal_direct_count():
                 assert_same(c2.export(1, True), oracle)
 
 
-@pytest.mark.parametrize("k,flags", [(21, 0), (12, 0), (5, 0)])
+@pytest.mark.parametrize("k,flags", [(21, 0), (21, _lib.KMG_FLAG_FORCE_HASH), (12, 0), (5, 0)])
 def test_full_size_properties_100mbp(k, flags):
     """BASELINE configs 1-2 at full size (100 Mbp, 100 records): properties that need no oracle --
     sum of counts == windows, reverse-complement invariance of the whole table, linearity (counting the

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.KmgConfig) == 48
-    assert C.sizeof(_lib.KmgSummary) == 72
+    assert C.sizeof(_lib.KmgSummary) == 88
     assert C.sizeof(_lib.KmgBatch) == 56
 
 
