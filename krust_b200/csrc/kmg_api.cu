@@ -255,14 +255,13 @@ kmg_status decide_mode(kmg_ctx *c, uint64_t first_call_windows) {
     return KMG_OK;
   }
   c->mode = kmg_ctx::MODE_PARTITIONED;
-  uint32_t lg = c->cfg.parts_log2;
-  if (lg == 0) {
-    // aim for <= ~420 K keys per partition so that a 2^20-slot (16 MiB) table holds it at load <= 0.4
-    lg = pow2_ceil_log2((hint + 419999) / 420000);
-    lg = std::max<uint32_t>(lg, 4);
+  if (c->cfg.parts_log2) c->n_parts = 1u << std::min<uint32_t>(c->cfg.parts_log2, pow2_ceil_log2(MAX_PARTS));
+  else {
+    // ~576 K keys per partition: a 2^20-slot (16 MiB) table then runs at load ~0.55, three of them stay L2-resident.
+    // The partition count need not be a power of two (multiply-shift partition function).
+    const uint64_t want = (hint + 575999) / 576000;
+    c->n_parts = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 16), MAX_PARTS);
   }
-  lg = std::min<uint32_t>(lg, pow2_ceil_log2(MAX_PARTS));
-  c->n_parts = 1u << lg;
   CU(c, cudaMalloc(&c->d_part, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long)));
   return KMG_OK;
 }
@@ -374,7 +373,7 @@ kmg_status consolidate(kmg_ctx *c) {
   if (max_np >= (1ull << 32)) return fail(c, KMG_ERR_STATE, "a partition holds more than 2^32 entries; use more partitions");
   // per-partition table capacity: 2.2x its entries, capped at cap_limit (skewed partitions hold few DISTINCT keys);
   // if a table does fill up the kernel raises error_flag and we retry with a doubled cap.
-  uint32_t cap_limit_log2 = std::max<uint32_t>(10, pow2_ceil_log2((uint64_t)(2.2 * 1.25 * (double)total / P) + 1));
+  uint32_t cap_limit_log2 = std::max<uint32_t>(10, pow2_ceil_log2((uint64_t)(1.6 * 1.1 * (double)total / P) + 1));
   Run out;
   cudaError_t e = cudaMalloc(&out.d_keys, std::max<uint64_t>(total, 1) * 8);
   if (e == cudaSuccess) e = cudaMalloc(&out.d_counts, std::max<uint64_t>(total, 1) * 8);
@@ -383,16 +382,24 @@ kmg_status consolidate(kmg_ctx *c) {
 
   kmg_status st = KMG_OK;
   for (int attempt = 0;; ++attempt) {
-    std::vector<uint32_t> cap_log2(P), nI(P), nC(P);
+    std::vector<uint32_t> cap_log2(P), nI(P), nC(P), wait(P, 0xffffffffu);
     std::vector<ConsPhase> phases;
     phases.reserve(2 * P + 1);
     uint64_t tickets = 0;
     uint32_t max_cap_log2 = 10;
     for (uint32_t p = 0; p < P; ++p) {
-      cap_log2[p] = std::min(cap_limit_log2, std::max<uint32_t>(10, pow2_ceil_log2((uint64_t)(2.2 * (double)n_p[p]) + 1)));
+      cap_log2[p] = std::min(cap_limit_log2, std::max<uint32_t>(10, pow2_ceil_log2((uint64_t)(1.6 * (double)n_p[p]) + 1)));
       max_cap_log2 = std::max(max_cap_log2, cap_log2[p]);
       nI[p] = (uint32_t)std::max<uint64_t>(1, (n_p[p] + CONS_INSERT_CHUNK - 1) / CONS_INSERT_CHUNK);
       nC[p] = n_p[p] ? (uint32_t)std::max<uint64_t>(1, (1ull << cap_log2[p]) / CONS_COMPACT_CHUNK) : 0;
+    }
+    {  // I(p) may only touch its table buffer after the previous NON-EMPTY user of that buffer has been drained
+      int64_t last_user[CONS_NBUF];
+      for (int b = 0; b < CONS_NBUF; ++b) last_user[b] = -1;
+      for (uint32_t p = 0; p < P; ++p) {
+        if (last_user[p % CONS_NBUF] >= 0) wait[p] = (uint32_t)last_user[p % CONS_NBUF];
+        if (n_p[p]) last_user[p % CONS_NBUF] = p;
+      }
     }
     auto push = [&](uint32_t p, bool compact) {
       phases.push_back(ConsPhase{(uint32_t)tickets, p | (compact ? 0x80000000u : 0u)});
@@ -407,7 +414,7 @@ kmg_status consolidate(kmg_ctx *c) {
     const uint64_t stride = 1ull << max_cap_log2;
     uint64_t *d_tables = nullptr;
     uint8_t *d_meta = nullptr;
-    const size_t meta_u32 = (size_t)P * 7 + 8;  // cap_log2, nI, nC, done_I, done_C, distinct, out_cursor, ticket, error
+    const size_t meta_u32 = (size_t)P * 8 + 8;  // cap_log2, nI, nC, wait, done_I, done_C, distinct, out_cursor, ticket, error
     const size_t phases_bytes = phases.size() * sizeof(ConsPhase);
     e = cudaMalloc(&d_tables, (size_t)CONS_NBUF * stride * 16);
     if (e == cudaSuccess) e = cudaMalloc(&d_meta, meta_u32 * 4 + phases_bytes + 16);
@@ -416,9 +423,9 @@ kmg_status consolidate(kmg_ctx *c) {
     ConsParams prm{};
     prm.n_parts = P; prm.R = R; prm.total_tickets = (uint32_t)tickets; prm.preagg = !(c->cfg.flags & KMG_FLAG_NO_PREAGG);
     for (uint32_t r = 0; r < R; ++r) prm.runs[r] = ConsRun{in[r]->d_keys, in[r]->d_counts, in[r]->d_offsets};
-    prm.part_cap_log2 = m; prm.part_nI = m + P; prm.part_nC = m + 2 * P;
-    prm.done_I = m + 3 * P; prm.done_C = m + 4 * P; prm.distinct = m + 5 * P; prm.out_cursor = m + 6 * P;
-    prm.ticket = m + 7 * P; prm.error_flag = m + 7 * P + 1;
+    prm.part_cap_log2 = m; prm.part_nI = m + P; prm.part_nC = m + 2 * P; prm.part_wait = m + 3 * P;
+    prm.done_I = m + 4 * P; prm.done_C = m + 5 * P; prm.distinct = m + 6 * P; prm.out_cursor = m + 7 * P;
+    prm.ticket = m + 8 * P; prm.error_flag = m + 8 * P + 1;
     prm.phases = reinterpret_cast<const ConsPhase *>(m + meta_u32);
     prm.tables = d_tables; prm.table_stride_slots = stride;
     prm.out_keys = out.d_keys; prm.out_counts = out.d_counts;
@@ -428,6 +435,7 @@ kmg_status consolidate(kmg_ctx *c) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(m, cap_log2.data(), P * 4, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(m + P, nI.data(), P * 4, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(m + 2 * P, nC.data(), P * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m + 3 * P, wait.data(), P * 4, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(m + meta_u32, phases.data(), phases_bytes, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(out.d_offsets, 0xFF, (P + 1) * 8, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(out.d_offsets, 0, 8, s);

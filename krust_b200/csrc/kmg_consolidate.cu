@@ -41,35 +41,71 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *scratch /*>= 32 entries*/) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  uint32_t t = 0;
-  for (int w = 0; w < CONS_THREADS / 32; ++w) t += scratch[w];
-  return t;
-}
-
 }  // namespace
 
-__global__ void __launch_bounds__(CONS_THREADS, 2) consolidate_kernel(ConsParams P) {
+// Ticket life cycle (per CTA): warp 0 prepares (ticket, phase decode, dependency wait, input segments) ->
+// barrier -> all warps work without further block barriers (reservations are per warp) -> fence + barrier ->
+// thread 0 signals completion.  The next ticket is drawn early so its latency hides behind the work; the
+// lowest unfinished ticket is always executing with all its dependencies done, so progress is guaranteed.
+__global__ void __launch_bounds__(CONS_THREADS, CONS_CTAS_PER_SM) consolidate_kernel(ConsParams P) {
   __shared__ uint64_t seg_begin[CONS_MAX_RUNS];
   __shared__ uint32_t seg_prefix[CONS_MAX_RUNS + 1];
-  __shared__ uint32_t scratch[64];
   __shared__ uint32_t s_ticket, s_phase;
   __shared__ unsigned long long s_base;
-  const int tid = threadIdx.x;
-  uint32_t phase_idx = 0;  // monotone per CTA (tickets only grow)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // warp-0/lane-0 private scheduling state
+  uint32_t phase_idx = 0;                          // monotone: tickets only grow
+  uint32_t next_ticket = 0;
+  int64_t known_pub = 0;                           // out_base[0..known_pub] are known to be published
+  int64_t known_done[CONS_NBUF];                   // per table buffer: last partition whose C is known complete
+#pragma unroll
+  for (int b = 0; b < CONS_NBUF; ++b) known_done[b] = -1;
+  if (tid == 0) next_ticket = atomicAdd(P.ticket, 1u);
 
   for (;;) {
-    if (tid == 0) {
-      const uint32_t t = atomicAdd(P.ticket, 1u);
-      if (t < P.total_tickets)
-        while (P.phases[phase_idx + 1].first_ticket <= t) ++phase_idx;
-      s_ticket = t; s_phase = phase_idx;
+    if (warp == 0) {
+      uint32_t t = 0, ph_idx = 0;
+      if (lane == 0) {
+        t = next_ticket;
+        if (t < P.total_tickets) {
+          while (P.phases[phase_idx + 1].first_ticket <= t) ++phase_idx;
+          next_ticket = atomicAdd(P.ticket, 1u);  // consumed one iteration later
+        }
+        ph_idx = phase_idx;
+      }
+      t = __shfl_sync(0xffffffffu, t, 0);
+      ph_idx = __shfl_sync(0xffffffffu, ph_idx, 0);
+      if (t < P.total_tickets) {
+        const ConsPhase ph = P.phases[ph_idx];
+        const uint32_t p = ph.part_and_type & 0x7fffffffu;
+        if (!(ph.part_and_type >> 31)) {
+          // insert ticket: input segments of partition p across the runs, and the table buffer must be free
+          uint32_t len = 0;
+          uint64_t b = 0;
+          if (lane < (int)P.R) { b = P.runs[lane].offsets[p]; len = (uint32_t)(P.runs[lane].offsets[p + 1] - b); }
+          uint32_t incl = len;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+          if (lane < (int)P.R) { seg_begin[lane] = b; seg_prefix[lane] = incl - len; }
+          if (lane == (int)P.R - 1) seg_prefix[P.R] = incl;
+          if (lane == 0) {
+            const uint32_t q = P.part_wait[p];  // previous non-empty user of this table buffer
+            if (q != 0xffffffffu && (int64_t)q > known_done[p % CONS_NBUF]) {
+              const uint32_t need = P.part_nC[q];
+              while (ld_acquire_u32(P.done_C + q) < need) __nanosleep(100);
+              known_done[p % CONS_NBUF] = q;
+            }
+          }
+        } else if (lane == 0) {
+          // compact ticket: partition p must be completely inserted and its output offset known
+          if ((int64_t)p + 1 > known_pub) {
+            while (ld_acquire_u64(P.out_base + p + 1) == BASE_UNSET) __nanosleep(100);
+            known_pub = (int64_t)p + 1;
+          }
+          s_base = __ldcg(P.out_base + p);
+        }
+      }
+      if (lane == 0) { s_ticket = t; s_phase = ph_idx; }
     }
     __syncthreads();
     const uint32_t ticket = s_ticket;
@@ -78,87 +114,71 @@ __global__ void __launch_bounds__(CONS_THREADS, 2) consolidate_kernel(ConsParams
     const uint32_t chunk = ticket - ph.first_ticket;
     const uint32_t p = ph.part_and_type & 0x7fffffffu;
     const bool is_compact = ph.part_and_type >> 31;
-    const uint32_t cap_log2 = P.part_cap_log2[p];
-    const uint64_t mask = (1ull << cap_log2) - 1;
+    const uint64_t mask = (1ull << P.part_cap_log2[p]) - 1;
     unsigned long long *table = reinterpret_cast<unsigned long long *>(P.tables) + (uint64_t)(p % CONS_NBUF) * P.table_stride_slots * 2;
 
     if (!is_compact) {
       // ------------------------------------------------------------------ I(p): upsert one chunk of partition p
-      if (tid < (int)P.R) {
-        const uint64_t b = P.runs[tid].offsets[p], e = P.runs[tid].offsets[p + 1];
-        seg_begin[tid] = b;
-        scratch[tid] = (uint32_t)(e - b);
-      }
-      if (tid == 0 && p >= CONS_NBUF) {  // the buffer must have been drained by C(p - NBUF)
-        const uint32_t need = P.part_nC[p - CONS_NBUF];
-        while (ld_acquire_u32(P.done_C + (p - CONS_NBUF)) < need) __nanosleep(200);
-      }
-      __syncthreads();
-      if (tid == 0) {
-        uint32_t acc = 0;
-        for (uint32_t r = 0; r < P.R; ++r) { seg_prefix[r] = acc; acc += scratch[r]; }
-        seg_prefix[P.R] = acc;
-      }
-      __syncthreads();
       const uint32_t n_p = seg_prefix[P.R];
       const uint32_t lo = chunk * CONS_INSERT_CHUNK;
-      constexpr int KPT = CONS_INSERT_CHUNK / CONS_THREADS;
-      uint64_t key[KPT], old[KPT], slot[KPT], w[KPT];
+      constexpr int G = 8, ROUNDS = CONS_INSERT_CHUNK / (CONS_THREADS * G);
       uint32_t new_keys = 0;
+#pragma unroll 1
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        if (lo + (uint32_t)rd * G * CONS_THREADS >= n_p) break;  // block-uniform
+        uint64_t key[G], old[G], slot[G], w[G];
 #pragma unroll
-      for (int j = 0; j < KPT; ++j) {
-        const uint32_t idx = lo + j * CONS_THREADS + tid;
-        w[j] = 0;
-        if (idx < n_p) {
-          uint32_t r = 0;
-          while (r + 1 < P.R && idx >= seg_prefix[r + 1]) ++r;
-          const uint64_t src = seg_begin[r] + (idx - seg_prefix[r]);
-          key[j] = __ldcs(P.runs[r].keys + src);
-          w[j] = P.runs[r].counts ? __ldcs(P.runs[r].counts + src) : 1ull;
-        }
-      }
-      if (P.preagg) {
-        // Warp run-length pre-aggregation: phase A writes the keys of consecutive windows next to each other,
-        // so homopolymer / tandem-repeat runs arrive as runs of equal keys in adjacent lanes.  The head lane of
-        // each run upserts once with the run length; this bounds same-address atomic bursts on skewed inputs.
-        const int lane = tid & 31;
-#pragma unroll
-        for (int j = 0; j < KPT; ++j) {
-          const uint64_t kk = w[j] ? key[j] : EMPTY_KEY;
-          const uint64_t kp = __shfl_up_sync(0xffffffffu, kk, 1);
-          const bool head = lane == 0 || kp != kk;
-          const uint32_t heads = __ballot_sync(0xffffffffu, head);
-          if (__all_sync(0xffffffffu, w[j] <= 1ull)) {  // unit weights only (keys-runs); pair-runs are already distinct per run
-            const uint32_t above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
-            const uint32_t end = above ? (uint32_t)__ffs(above) - 1u : 32u;
-            if (w[j]) w[j] = head ? (uint64_t)(end - lane) : 0ull;
+        for (int j = 0; j < G; ++j) {
+          const uint32_t idx = lo + (rd * G + j) * CONS_THREADS + tid;
+          w[j] = 0; key[j] = EMPTY_KEY;
+          if (idx < n_p) {
+            uint32_t r = 0;
+            while (r + 1 < P.R && idx >= seg_prefix[r + 1]) ++r;
+            const uint64_t src = seg_begin[r] + (idx - seg_prefix[r]);
+            key[j] = __ldcs(P.runs[r].keys + src);
+            w[j] = P.runs[r].counts ? __ldcs(P.runs[r].counts + src) : 1ull;
           }
         }
-      }
+        if (P.preagg) {
+          // Warp run-length pre-aggregation: phase A writes the keys of consecutive windows next to each other,
+          // so homopolymer / tandem-repeat runs arrive as runs of equal keys in adjacent lanes.  The head lane of
+          // each run upserts once with the run length; this bounds same-address atomic bursts on skewed inputs.
 #pragma unroll
-      for (int j = 0; j < KPT; ++j) {  // all first probes in flight together
-        old[j] = 0;
-        if (w[j]) {
+          for (int j = 0; j < G; ++j) {
+            const uint64_t kk = w[j] ? key[j] : EMPTY_KEY;
+            const uint64_t kp = __shfl_up_sync(0xffffffffu, kk, 1);
+            const bool head = lane == 0 || kp != kk;
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            if (__all_sync(0xffffffffu, w[j] <= 1ull)) {  // unit weights only (keys-runs); pair-runs are distinct per run
+              const uint32_t above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
+              const uint32_t end = above ? (uint32_t)__ffs(above) - 1u : 32u;
+              if (w[j]) w[j] = head ? (uint64_t)(end - lane) : 0ull;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {  // all first probes in flight together
+          old[j] = 0;
           slot[j] = mix64(key[j]) & mask;  // low mix bits; the partition index used the high ones
-          old[j] = atomicCAS(table + 2 * slot[j], EMPTY_KEY, key[j]);
+          if (w[j]) old[j] = atomicCAS(table + 2 * slot[j], EMPTY_KEY, key[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          if (!w[j]) continue;
+          uint64_t sl = slot[j], cur = old[j], probes = 0;
+          while (cur != EMPTY_KEY && cur != key[j]) {  // linear probing inside the partition's table
+            if (++probes > mask) { atomicExch(P.error_flag, 1u); break; }
+            sl = (sl + 1) & mask;
+            cur = *reinterpret_cast<volatile unsigned long long *>(table + 2 * sl);
+            if (cur == EMPTY_KEY) cur = atomicCAS(table + 2 * sl, EMPTY_KEY, key[j]);
+          }
+          if (cur == EMPTY_KEY) { ++new_keys; if (w[j] > 1) atomicAdd(table + 2 * sl + 1, (unsigned long long)(w[j] - 1)); }
+          else if (cur == key[j]) atomicAdd(table + 2 * sl + 1, (unsigned long long)w[j]);
         }
       }
 #pragma unroll
-      for (int j = 0; j < KPT; ++j) {
-        if (!w[j]) continue;
-        uint64_t s = slot[j], cur = old[j];
-        uint64_t probes = 0;
-        while (cur != EMPTY_KEY && cur != key[j]) {  // linear probing inside the partition's table
-          if (++probes > mask) { atomicExch(P.error_flag, 1u); break; }
-          s = (s + 1) & mask;
-          cur = *reinterpret_cast<volatile unsigned long long *>(table + 2 * s);
-          if (cur == EMPTY_KEY) cur = atomicCAS(table + 2 * s, EMPTY_KEY, key[j]);
-        }
-        if (cur == EMPTY_KEY) { ++new_keys; if (w[j] > 1) atomicAdd(table + 2 * s + 1, (unsigned long long)(w[j] - 1)); }
-        else if (cur == key[j]) atomicAdd(table + 2 * s + 1, (unsigned long long)w[j]);
-      }
-      const uint32_t total_new = block_sum_u32(new_keys, scratch);
-      if (tid == 0 && total_new) atomicAdd(P.distinct + p, total_new);
+      for (int o = 16; o > 0; o >>= 1) new_keys += __shfl_xor_sync(0xffffffffu, new_keys, o);
+      if (lane == 0 && new_keys) atomicAdd(P.distinct + p, new_keys);
       __threadfence();
       __syncthreads();
       if (tid == 0) {
@@ -166,64 +186,55 @@ __global__ void __launch_bounds__(CONS_THREADS, 2) consolidate_kernel(ConsParams
         if (done == P.part_nI[p]) {  // last inserter of p: its distinct count is final -> publish where p+1 starts
           __threadfence();
           unsigned long long b;
-          while ((b = ld_acquire_u64(P.out_base + p)) == BASE_UNSET) __nanosleep(200);
+          while ((b = ld_acquire_u64(P.out_base + p)) == BASE_UNSET) __nanosleep(100);
           const uint32_t d = atomicAdd(P.distinct + p, 0u);
           st_release_u64(P.out_base + p + 1, b + d);
+          if ((int64_t)p + 1 > known_pub) known_pub = (int64_t)p + 1;
         }
       }
     } else {
       // ------------------------------------------------------------------ C(p): drain one chunk of p's table
-      if (tid == 0) {
-        while (ld_acquire_u64(P.out_base + p + 1) == BASE_UNSET) __nanosleep(200);  // implies I(p) complete
-        s_base = ld_acquire_u64(P.out_base + p);
-      }
-      __syncthreads();
-      constexpr int SPT = CONS_COMPACT_CHUNK / CONS_THREADS;
+      const unsigned long long base = s_base;
+      constexpr int G = 8, ROUNDS = CONS_COMPACT_CHUNK / (CONS_THREADS * G);
       const uint64_t lo = (uint64_t)chunk * CONS_COMPACT_CHUNK;
-      ulonglong2 s[SPT];
-      uint32_t mine = 0;
+#pragma unroll 1
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        if (lo + (uint64_t)rd * G * CONS_THREADS > mask) break;  // block-uniform
+        ulonglong2 sl[G];
+        uint32_t mine = 0;
 #pragma unroll
-      for (int j = 0; j < SPT; ++j) {
-        const uint64_t i = lo + j * CONS_THREADS + tid;
-        s[j] = make_ulonglong2(EMPTY_KEY, 0ull);
-        if (i <= mask) s[j] = __ldcg(reinterpret_cast<const ulonglong2 *>(table) + i);  // L2, never a stale L1 line
-        mine += s[j].x != EMPTY_KEY;
-      }
-      // block-wide exclusive scan of `mine`
-      const int lane = tid & 31, warp = tid >> 5;
-      uint32_t incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      if (lane == 31) scratch[warp] = incl;
-      __syncthreads();
-      if (warp == 0) {
-        uint32_t v = lane < CONS_THREADS / 32 ? scratch[lane] : 0, inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-        scratch[32 + lane] = inc - v;  // exclusive warp offsets
-        if (lane == 31) {
-          const uint32_t total = inc;
-          scratch[31] = total ? atomicAdd(P.out_cursor + p, total) : 0;  // this chunk's range inside partition p
+        for (int j = 0; j < G; ++j) {
+          const uint64_t i = lo + (uint64_t)(rd * G + j) * CONS_THREADS + tid;
+          sl[j] = make_ulonglong2(EMPTY_KEY, 0ull);
+          if (i <= mask) sl[j] = __ldcg(reinterpret_cast<const ulonglong2 *>(table) + i);  // L2, never a stale L1 line
+          mine += sl[j].x != EMPTY_KEY;
         }
-      }
-      __syncthreads();
-      uint64_t o = s_base + scratch[31] + scratch[32 + warp] + (incl - mine);
+        uint32_t incl = mine;  // warp-level reservation: one atomic per warp per round, no block barrier
 #pragma unroll
-      for (int j = 0; j < SPT; ++j) {
-        if (s[j].x == EMPTY_KEY) continue;
-        __stcs(P.out_keys + o, s[j].x);
-        __stcs(P.out_counts + o, s[j].y + 1);  // slots store occurrences - 1
-        ++o;
-        const uint64_t i = lo + j * CONS_THREADS + tid;
-        reinterpret_cast<ulonglong2 *>(table)[i] = make_ulonglong2(EMPTY_KEY, 0ull);  // hand the slot back clean
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        uint32_t wbase = 0;
+        if (lane == 31 && incl) wbase = atomicAdd(P.out_cursor + p, incl);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        uint64_t o = base + wbase + (incl - mine);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          if (sl[j].x == EMPTY_KEY) continue;
+          __stcs(P.out_keys + o, sl[j].x);
+          __stcs(P.out_counts + o, sl[j].y + 1);  // slots store occurrences - 1
+          ++o;
+          const uint64_t i = lo + (uint64_t)(rd * G + j) * CONS_THREADS + tid;
+          reinterpret_cast<ulonglong2 *>(table)[i] = make_ulonglong2(EMPTY_KEY, 0ull);  // hand the slot back clean
+        }
       }
       __threadfence();
       __syncthreads();
       if (tid == 0) atomicAdd(P.done_C + p, 1u);
     }
-    __syncthreads();
   }
 }
+
+namespace {
+}  // namespace
 
 // scatter already-extracted keys (optionally weighted) into partitions: the receive side of the
 // multi-GPU exchange and re-partitioning of foreign runs.  pass 0 counts, pass 1 scatters.

@@ -9,6 +9,7 @@
 // All arithmetic is integer; results are bit-exact by construction (tests/ prove it against oracle/).
 #include "kmg_kernels.h"
 
+#include <algorithm>
 #include <atomic>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -329,9 +330,8 @@ struct PartCountEmit {
   }
 };
 struct PartScatterEmit {
-  uint32_t *cursor;                      // smem: running offset inside this tile's reservation
-  const uint32_t *tile_off;              // smem: where this tile's range starts inside partition p
-  const unsigned long long *part_start;  // global: where partition p starts in `out`
+  uint32_t *cursor;          // smem: running offset inside this super-tile's reservation
+  const uint32_t *tile_abs;  // smem: index in `out` where this super-tile's keys of partition p start
   uint64_t *out;
   uint32_t n_parts;
   template <int G>
@@ -341,33 +341,29 @@ struct PartScatterEmit {
       if ((okg >> j) & 1u) {
         const uint32_t p = part_of(key[j], n_parts);
         const uint32_t o = atomicAdd(cursor + p, 1u);
-        __stcs(out + (__ldg(part_start + p) + tile_off[p] + o), key[j]);
+        __stcs(out + ((uint64_t)tile_abs[p] + o), key[j]);
       }
   }
 };
 
-// pass 1 (SCATTER == false): per-partition totals into part_counts[].
-// pass 2 (SCATTER == true) : part_start[] holds the exclusive prefix of those totals and part_cursor[]
-// starts at zero; each tile histograms its keys in shared memory, reserves one contiguous range per
-// partition with a single global atomic, then re-derives the keys and writes them into that range
-// (a launch never carries more than 2^32-1 windows, so in-partition offsets fit 32 bits).
-template <bool SCATTER>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_partition_kernel(ScanInput in, uint32_t n_parts,
-                                                                      unsigned long long *part_counts,
-                                                                      const unsigned long long *part_start,
-                                                                      unsigned long long *part_cursor, uint64_t *out,
-                                                                      unsigned long long *counters) {
+// Synchronously stage one tile (used at pass boundaries where there is nothing to overlap with).
+__device__ __forceinline__ void wait_stage(uint64_t *bars, int stage, uint32_t &phase0, uint32_t &phase1) {
+  if (stage == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+}
+
+// pass 1 (count_pass_kernel): per-partition totals of the whole launch into part_counts[].
+__global__ void __launch_bounds__(SCAN_THREADS) partition_count_kernel(ScanInput in, uint32_t n_parts,
+                                                                       unsigned long long *part_counts,
+                                                                       unsigned long long *counters) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
   __shared__ __align__(8) uint64_t bars[2];
   uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw + 2 * sizeof(TileSmem));
-  uint32_t *tile_off = hist + n_parts;
   const int tid = threadIdx.x;
   const bool has_start = in.start != nullptr;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
   for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) hist[p] = 0;
   __syncthreads();
-
   uint64_t windows = 0;
   uint64_t tile = blockIdx.x;
   int stage = 0;
@@ -376,37 +372,75 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_partition_kernel(ScanInput 
   for (; tile < in.n_tiles; tile += gridDim.x) {
     const uint64_t next = tile + gridDim.x;
     if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
-    if (stage == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
-    const TileSmem *ts = &stages[stage];
-    {
-      PartCountEmit e{hist, n_parts};
+    wait_stage(bars, stage, phase0, phase1);
+    PartCountEmit e{hist, n_parts};
 #pragma unroll 1
-      for (int r = 0; r < WORDS_PER_THREAD; ++r) windows += scan_word<8>(ts, r * SCAN_THREADS + tid, in.k, has_start, e);
-    }
-    if (SCATTER) {
-      __syncthreads();
-      for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) {
-        const uint32_t c = hist[p];
-        tile_off[p] = c ? (uint32_t)atomicAdd(part_cursor + p, (unsigned long long)c) : 0u;
-        hist[p] = 0;
-      }
-      __syncthreads();
-      PartScatterEmit e{hist, tile_off, part_start, out, n_parts};
-#pragma unroll 1
-      for (int r = 0; r < WORDS_PER_THREAD; ++r) scan_word<8>(ts, r * SCAN_THREADS + tid, in.k, has_start, e);
-      __syncthreads();
-      for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) hist[p] = 0;
-    }
+    for (int r = 0; r < WORDS_PER_THREAD; ++r) windows += scan_word<8>(&stages[stage], r * SCAN_THREADS + tid, in.k, has_start, e);
     __syncthreads();
     stage ^= 1;
   }
-  if (!SCATTER) {
-    for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) {
-      const uint32_t c = hist[p];
-      if (c) atomicAdd(part_counts + p, (unsigned long long)c);
+  for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) {
+    const uint32_t c = hist[p];
+    if (c) atomicAdd(part_counts + p, (unsigned long long)c);
+  }
+  windows = warp_sum(windows);
+  if ((tid & 31) == 0 && windows && counters) atomicAdd(counters + CTR_WINDOWS, (unsigned long long)windows);
+}
+
+// pass 2: scatter.  part_start[] holds the exclusive prefix of the totals, part_cursor[] starts at zero.
+// A CTA works on SUPER consecutive tiles at a time: it histograms them in shared memory, reserves ONE
+// contiguous range per partition for the whole super-tile (a single global atomic), then re-scans the
+// same tiles (they come from L2 now) and writes the keys into those ranges.  Long per-partition runs
+// keep the 8-byte stores mergeable into full sectors in L2; keys are re-derived rather than staged.
+// A launch never carries more than 2^32-1 windows, so indices into `out` fit 32 bits.
+constexpr int SUPER_TILES = 8;
+__global__ void __launch_bounds__(SCAN_THREADS) partition_scatter_kernel(ScanInput in, uint32_t n_parts,
+                                                                         const unsigned long long *part_start,
+                                                                         unsigned long long *part_cursor, uint64_t *out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[2];
+  uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw + 2 * sizeof(TileSmem));
+  uint32_t *tile_abs = hist + n_parts;
+  const int tid = threadIdx.x;
+  const bool has_start = in.start != nullptr;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) hist[p] = 0;
+  __syncthreads();
+  uint32_t phase0 = 0, phase1 = 0;
+  const uint64_t n_super = (in.n_tiles + SUPER_TILES - 1) / SUPER_TILES;
+  for (uint64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+    const uint64_t t0 = st * SUPER_TILES;
+    const int nt = (int)(in.n_tiles - t0 < (uint64_t)SUPER_TILES ? in.n_tiles - t0 : (uint64_t)SUPER_TILES);
+    for (int pass = 0; pass < 2; ++pass) {
+      int stage = 0;
+      if (tid == 0) issue_tile(in, &stages[0], &bars[0], t0);
+      for (int t = 0; t < nt; ++t) {
+        if (t + 1 < nt && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], t0 + t + 1);
+        wait_stage(bars, stage, phase0, phase1);
+        if (pass == 0) {
+          PartCountEmit e{hist, n_parts};
+#pragma unroll 1
+          for (int r = 0; r < WORDS_PER_THREAD; ++r) scan_word<8>(&stages[stage], r * SCAN_THREADS + tid, in.k, has_start, e);
+        } else {
+          PartScatterEmit e{hist, tile_abs, out, n_parts};
+#pragma unroll 1
+          for (int r = 0; r < WORDS_PER_THREAD; ++r) scan_word<8>(&stages[stage], r * SCAN_THREADS + tid, in.k, has_start, e);
+        }
+        __syncthreads();
+        stage ^= 1;
+      }
+      if (pass == 0) {
+        for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) {
+          const uint32_t c = hist[p];
+          tile_abs[p] = c ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)c)) : 0u;
+          hist[p] = 0;
+        }
+      } else {
+        for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) hist[p] = 0;
+      }
+      __syncthreads();
     }
-    windows = warp_sum(windows);
-    if ((tid & 31) == 0 && windows) atomicAdd(counters + CTR_WINDOWS, (unsigned long long)windows);
   }
 }
 
@@ -623,20 +657,19 @@ cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, un
 cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool scatter, unsigned long long *part_counts,
                                   const unsigned long long *part_start, unsigned long long *part_cursor, uint64_t *out,
                                   unsigned long long *counters, cudaStream_t s) {
-  unsigned grid = (unsigned)(in.n_tiles < (uint64_t)num_sms() * SCAN_CTAS_PER_SM ? in.n_tiles : (uint64_t)num_sms() * SCAN_CTAS_PER_SM);
-  if (grid == 0) return cudaSuccess;
+  if (in.n_tiles == 0) return cudaSuccess;
   const size_t smem = 2 * sizeof(TileSmem) + 2 * (size_t)n_parts * sizeof(uint32_t);
+  const uint64_t max_ctas = (uint64_t)num_sms() * (smem > 100 * 1024 ? 1 : smem > 72 * 1024 ? 2 : SCAN_CTAS_PER_SM);
   cudaError_t e;
   if (scatter) {
-    auto kern = scan_partition_kernel<true>;
-    if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
+    const uint64_t n_super = (in.n_tiles + SUPER_TILES - 1) / SUPER_TILES;
+    if ((e = set_smem(partition_scatter_kernel, smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    kern<<<grid, SCAN_THREADS, smem, s>>>(in, n_parts, part_counts, part_start, part_cursor, out, counters);
+    partition_scatter_kernel<<<(unsigned)std::min(n_super, max_ctas), SCAN_THREADS, smem, s>>>(in, n_parts, part_start, part_cursor, out);
   } else {
-    auto kern = scan_partition_kernel<false>;
-    if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
+    if ((e = set_smem(partition_count_kernel, smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    kern<<<grid, SCAN_THREADS, smem, s>>>(in, n_parts, part_counts, part_start, part_cursor, out, counters);
+    partition_count_kernel<<<(unsigned)std::min(in.n_tiles, max_ctas), SCAN_THREADS, smem, s>>>(in, n_parts, part_counts, counters);
   }
   return cudaGetLastError();
 }

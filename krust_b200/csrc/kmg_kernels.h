@@ -29,10 +29,10 @@ struct TableView {
 };
 
 // ---- partitioned pipeline (phase B, kmg_consolidate.cu) --------------------------------------------
-constexpr int CONS_THREADS = 512;
-constexpr int CONS_CTAS_PER_SM = 2;
-constexpr int CONS_INSERT_CHUNK = 4096;   // keys per insert ticket
-constexpr int CONS_COMPACT_CHUNK = 4096;  // table slots per compact ticket
+constexpr int CONS_THREADS = 256;
+constexpr int CONS_CTAS_PER_SM = 4;
+constexpr int CONS_INSERT_CHUNK = 8192;   // keys per insert ticket (32 per thread, 4 rounds of 8)
+constexpr int CONS_COMPACT_CHUNK = 8192;  // table slots per compact ticket
 constexpr int CONS_NBUF = 3;              // L2-resident table buffers in flight
 constexpr int CONS_MAX_RUNS = 16;
 constexpr int MAX_PARTS = 8192;
@@ -52,6 +52,7 @@ struct ConsParams {
   const ConsPhase *phases;         // schedule order, terminated by a sentinel with first_ticket = total_tickets
   const uint32_t *part_cap_log2;   // table capacity (log2 slots) of each partition
   const uint32_t *part_nI, *part_nC;  // tickets per phase
+  const uint32_t *part_wait;       // previous NON-EMPTY partition that used the same table buffer (~0: none)
   uint64_t *tables;                // CONS_NBUF buffers of table_stride_slots (key, count-1) slots
   uint64_t table_stride_slots;
   uint64_t *out_keys, *out_counts;
