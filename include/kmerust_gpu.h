@@ -63,7 +63,7 @@ typedef struct kmg_config {
   uint32_t flags;             /* KMG_FLAG_* */
   uint8_t has_min_quality;    /* 0 = None */
   uint8_t min_quality;        /* Phred; a base passes iff qual_byte >= saturating_add(min_quality, 33) (src/run.rs:538) */
-  uint8_t parts_log2;         /* partitioned pipeline: log2(#partitions), 0 = choose from the input size (max 13) */
+  uint8_t parts_log2;         /* partitioned pipeline: log2(#partitions), 0 = choose from the input size (max 20) */
   uint8_t reserved[5];
   uint64_t expected_distinct; /* capacity hint (distinct canonical k-mers); 0 = start small and grow */
   uint64_t batch_bases;       /* capacity of each pinned staging buffer in bases; 0 = default */

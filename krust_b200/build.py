@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkmerust_gpu.so")
-SOURCES = ["kmg_kernels.cu", "kmg_consolidate.cu", "kmg_api.cu", "kmg_fastx.cpp"]
+SOURCES = ["kmg_kernels.cu", "kmg_partition.cu", "kmg_api.cu", "kmg_fastx.cpp"]
 HEADERS = ["kmg_device.cuh", "kmg_kernels.h", os.path.join("..", "..", "include", "kmerust_gpu.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -41,11 +41,11 @@ struct Staging {
 
 }  // namespace
 
-// A run is a partition-ordered list of keys (phase A output, every key counts 1) or of (key, count)
-// pairs (phase B output / weighted inserts).  All runs of a context share the same partition count.
+// A run is a partition-indexed list of keys (phase A output, every key counts 1) or of (key, count)
+// pairs (phase B output / weighted inserts).  All runs of a context share the same partition count;
+// partition p of a run is entries [seg_start[p], seg_start[p] + seg_len[p]).
 struct Run {
-  uint64_t *d_keys = nullptr, *d_counts = nullptr, *d_offsets = nullptr;
-  std::vector<uint64_t> h_offsets;  // n_parts + 1
+  uint64_t *d_keys = nullptr, *d_counts = nullptr, *d_seg_start = nullptr, *d_seg_len = nullptr;
   uint64_t n = 0;
 };
 
@@ -81,12 +81,13 @@ struct kmg_ctx {
 
   // partitioned pipeline (v2)
   enum Mode { MODE_UNDECIDED, MODE_DENSE, MODE_TABLE, MODE_PARTITIONED } mode = MODE_UNDECIDED;
-  uint32_t n_parts = 0;
+  uint32_t n_parts = 0, n_coarse = 0, n_sub = 0, scratch_log2 = 13;
   std::vector<Run> runs;      // pending, not yet consolidated
   Run result;                 // consolidated (key, count) run
   bool has_result = false;
   uint64_t pending_bytes = 0;
-  unsigned long long *d_part = nullptr;  // 3 * MAX_PARTS scratch: counts, starts, cursors
+  unsigned long long *d_part = nullptr;  // 3 * MAX_PARTS scratch: coarse counts, starts, cursors
+  unsigned long long *d_fine_cursor = nullptr;  // n_parts
   uint32_t n_consolidations = 0;
 
   uint64_t n_records = 0, n_bases = 0, h2d_bytes = 0;
@@ -124,7 +125,7 @@ TableView view_of(const kmg_ctx *c) {
 }
 
 void free_run(Run &r) {
-  cudaFree(r.d_keys); cudaFree(r.d_counts); cudaFree(r.d_offsets);
+  cudaFree(r.d_keys); cudaFree(r.d_counts); cudaFree(r.d_seg_start); cudaFree(r.d_seg_len);
   r = Run();
 }
 
@@ -216,13 +217,14 @@ kmg_status ensure_packed(kmg_ctx *c, uint64_t n_words_total) {
   return KMG_OK;
 }
 
-void timer_begin(kmg_ctx *c, int cat = 0) {
+size_t timer_begin(kmg_ctx *c, int cat = 0) {
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
   cudaEventRecord(a, c->stream);
   c->pending_timers.push_back(kmg_ctx::Timer{a, b, cat});
+  return c->pending_timers.size() - 1;
 }
-void timer_end(kmg_ctx *c) { cudaEventRecord(c->pending_timers.back().b, c->stream); }
+void timer_end(kmg_ctx *c, size_t idx) { cudaEventRecord(c->pending_timers[idx].b, c->stream); }
 void timers_collect(kmg_ctx *c) {
   for (auto &p : c->pending_timers) {
     float ms = 0.f;
@@ -234,10 +236,11 @@ void timers_collect(kmg_ctx *c) {
 
 
 // =================================================================================================
-// Partitioned pipeline (v2): phase A scatters keys into hash partitions (streaming writes), phase B
-// counts each partition in an L2-resident table (kmg_consolidate.cu).
+// Partitioned pipeline: A1 coarse scatter, A2 refine to fine partitions, B per-CTA counting
+// (kernels and rationale: kmg_partition.cu).
 // =================================================================================================
 inline uint32_t pow2_ceil_log2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) ++l; return l; }
+constexpr uint64_t TARGET_KEYS_PER_PART = 4400;  // 2^13-slot scratch tables then run at load ~0.54
 
 // Decide how this context counts.  Called at the first feeding call, when the input size is known.
 kmg_status decide_mode(kmg_ctx *c, uint64_t first_call_windows) {
@@ -255,24 +258,21 @@ kmg_status decide_mode(kmg_ctx *c, uint64_t first_call_windows) {
     return KMG_OK;
   }
   c->mode = kmg_ctx::MODE_PARTITIONED;
-  if (c->cfg.parts_log2) c->n_parts = 1u << std::min<uint32_t>(c->cfg.parts_log2, pow2_ceil_log2(MAX_PARTS));
-  else {
-    // ~576 K keys per partition: a 2^20-slot (16 MiB) table then runs at load ~0.55, three of them stay L2-resident.
-    // The partition count need not be a power of two (multiply-shift partition function).
-    const uint64_t want = (hint + 575999) / 576000;
-    c->n_parts = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 16), MAX_PARTS);
+  if (c->cfg.parts_log2) {
+    const uint32_t lg = std::min<uint32_t>(c->cfg.parts_log2, 20);
+    c->n_coarse = 1u << (lg / 2);
+    c->n_sub = 1u << (lg - lg / 2);
+  } else {
+    const uint64_t want = std::max<uint64_t>(4, (hint + TARGET_KEYS_PER_PART - 1) / TARGET_KEYS_PER_PART);
+    uint64_t p1 = 1;
+    while (p1 * p1 < want) ++p1;
+    p1 = std::min<uint64_t>(p1, 2048);
+    c->n_coarse = (uint32_t)p1;
+    c->n_sub = (uint32_t)std::min<uint64_t>((want + p1 - 1) / p1, 2048);
   }
+  c->n_parts = c->n_coarse * c->n_sub;
   CU(c, cudaMalloc(&c->d_part, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long)));
-  return KMG_OK;
-}
-
-// host prefix of per-partition counts -> Run offsets (host + device copy)
-kmg_status finish_run_offsets(kmg_ctx *c, Run &r, const std::vector<unsigned long long> &counts) {
-  r.h_offsets.assign(c->n_parts + 1, 0);
-  for (uint32_t p = 0; p < c->n_parts; ++p) r.h_offsets[p + 1] = r.h_offsets[p] + counts[p];
-  r.n = r.h_offsets[c->n_parts];
-  CU(c, cudaMalloc(&r.d_offsets, (c->n_parts + 1) * 8));
-  CU(c, cudaMemcpyAsync(r.d_offsets, r.h_offsets.data(), (c->n_parts + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMalloc(&c->d_fine_cursor, (size_t)c->n_parts * sizeof(unsigned long long)));
   return KMG_OK;
 }
 
@@ -290,10 +290,65 @@ kmg_status add_run(kmg_ctx *c, Run &&r) {
   return KMG_OK;
 }
 
-// phase A over the packed stream: count pass, exact offsets, scatter pass -> one keys-run
+// allocate with one retry after consolidating what is pending (frees the pending runs' buffers)
+kmg_status alloc_or_consolidate(kmg_ctx *c, void **p, size_t bytes, const char *what) {
+  cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+  if (e == cudaSuccess) return KMG_OK;
+  cudaGetLastError();
+  kmg_status s = consolidate(c);
+  if (s != KMG_OK) return s;
+  e = cudaMalloc(p, bytes ? bytes : 1);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(c, KMG_ERR_OOM, std::string("cudaMalloc(") + what + ") failed"); }
+  return KMG_OK;
+}
+
+// A2: coarse-partitioned keys (+counts) -> fine-partitioned run.  Takes ownership of the coarse buffers.
+kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, const std::vector<uint64_t> &coarse_off) {
+  const uint32_t P1 = c->n_coarse, P = c->n_parts;
+  const uint64_t n = coarse_off[P1];
+  Run r;
+  uint64_t *d_cstart = nullptr;
+  uint32_t *d_tprefix = nullptr;
+  auto cleanup = [&]() { cudaFree(d_ckeys); cudaFree(d_ccounts); cudaFree(d_cstart); cudaFree(d_tprefix); };
+  std::vector<uint32_t> tprefix(P1 + 1, 0);
+  uint64_t tiles = 0;
+  for (uint32_t p = 0; p < P1; ++p) { tprefix[p] = (uint32_t)tiles; tiles += (coarse_off[p + 1] - coarse_off[p] + REFINE_TILE - 1) / REFINE_TILE; }
+  tprefix[P1] = (uint32_t)tiles;
+  cudaError_t e = cudaMalloc(&d_cstart, (P1 + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_tprefix, (P1 + 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&r.d_seg_start, (size_t)P * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&r.d_seg_len, (size_t)P * 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_cstart, coarse_off.data(), (P1 + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_tprefix, tprefix.data(), (P1 + 1) * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(r.d_seg_len, 0, (size_t)P * 8, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->d_fine_cursor, 0, (size_t)P * 8, c->stream);
+  if (e != cudaSuccess) { cleanup(); free_run(r); return cuda_fail(c, e, "refine setup"); }
+  RefineParams rp{};
+  rp.keys = d_ckeys; rp.counts = d_ccounts; rp.coarse_start = d_cstart; rp.tile_prefix = d_tprefix;
+  rp.n_coarse = P1; rp.n_sub = c->n_sub; rp.n_tiles = (uint32_t)tiles;
+  rp.fine_counts = reinterpret_cast<unsigned long long *>(r.d_seg_len);
+  rp.fine_start = reinterpret_cast<const unsigned long long *>(r.d_seg_start);
+  rp.fine_cursor = c->d_fine_cursor;
+  e = launch_refine(rp, false, c->stream);
+  if (e == cudaSuccess) e = exclusive_sum_u64(r.d_seg_len, r.d_seg_start, P, c->stream);
+  if (e != cudaSuccess) { cleanup(); free_run(r); return cuda_fail(c, e, "refine count"); }
+  kmg_status s = alloc_or_consolidate(c, reinterpret_cast<void **>(&r.d_keys), n * 8, "fine keys");
+  if (s == KMG_OK && d_ccounts) s = alloc_or_consolidate(c, reinterpret_cast<void **>(&r.d_counts), n * 8, "fine counts");
+  if (s != KMG_OK) { cleanup(); free_run(r); return s; }
+  rp.out_keys = r.d_keys; rp.out_counts = r.d_counts;
+  e = launch_refine(rp, true, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cleanup();
+  if (e != cudaSuccess) { free_run(r); return cuda_fail(c, e, "refine scatter"); }
+  r.n = n;
+  return add_run(c, std::move(r));
+}
+
+// A1 over the packed stream: coarse count pass, exact offsets, coarse scatter; then A2.
 kmg_status scan_to_run(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
   const uint64_t n_tiles = n_words_total / TILE_WORDS;
   const uint64_t max_tiles = ((1ull << 32) - 1) / ((uint64_t)TILE_WORDS * 32);  // < 2^32 windows per launch
+  const uint32_t P1 = c->n_coarse;
   unsigned long long *d_cnt = c->d_part, *d_start = c->d_part + MAX_PARTS, *d_cur = c->d_part + 2 * MAX_PARTS;
   for (uint64_t tile0 = 0; tile0 < n_tiles; tile0 += max_tiles) {
     ScanInput in;
@@ -302,55 +357,52 @@ kmg_status scan_to_run(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
     in.start = has_start ? c->d_start + tile0 * TILE_WORDS : nullptr;
     in.n_tiles = std::min(max_tiles, n_tiles - tile0);
     in.k = c->k;
-    timer_begin(c);
+    const size_t tmr = timer_begin(c, 0);
     CU(c, cudaMemsetAsync(c->d_part, 0, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
-    CU(c, launch_scan_partition(in, c->n_parts, false, d_cnt, d_start, d_cur, nullptr, c->d_counters, c->stream));
-    std::vector<unsigned long long> counts(c->n_parts);
-    CU(c, cudaMemcpyAsync(counts.data(), d_cnt, c->n_parts * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, launch_scan_partition(in, P1, false, d_cnt, d_start, d_cur, nullptr, c->d_counters, c->stream));
+    std::vector<unsigned long long> counts(P1);
+    CU(c, cudaMemcpyAsync(counts.data(), d_cnt, P1 * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
-    Run r;
-    kmg_status s = finish_run_offsets(c, r, counts);
-    if (s != KMG_OK) { free_run(r); return s; }
-    if (r.n) {
-      cudaError_t e = cudaMalloc(&r.d_keys, r.n * 8);
-      if (e != cudaSuccess) {  // make room by consolidating what is pending, then retry once
-        cudaGetLastError();
-        if ((s = consolidate(c)) != KMG_OK) { free_run(r); return s; }
-        e = cudaMalloc(&r.d_keys, r.n * 8);
-        if (e != cudaSuccess) { free_run(r); return cuda_fail(c, e, "cudaMalloc(partition buffer)"); }
-      }
-      CU(c, cudaMemcpyAsync(d_start, r.d_offsets, c->n_parts * 8, cudaMemcpyDeviceToDevice, c->stream));
-      CU(c, launch_scan_partition(in, c->n_parts, true, d_cnt, d_start, d_cur, r.d_keys, c->d_counters, c->stream));
-    }
-    timer_end(c);
-    if ((s = add_run(c, std::move(r))) != KMG_OK) return s;
+    std::vector<uint64_t> off(P1 + 1, 0);
+    for (uint32_t p = 0; p < P1; ++p) off[p + 1] = off[p] + counts[p];
+    const uint64_t n = off[P1];
+    if (n == 0) { timer_end(c, tmr); continue; }
+    uint64_t *d_ckeys = nullptr;
+    kmg_status s = alloc_or_consolidate(c, reinterpret_cast<void **>(&d_ckeys), n * 8, "coarse keys");
+    if (s != KMG_OK) return s;
+    CU(c, cudaMemcpyAsync(d_start, off.data(), P1 * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, launch_scan_partition(in, P1, true, d_cnt, d_start, d_cur, d_ckeys, c->d_counters, c->stream));
+    s = refine_to_run(c, d_ckeys, nullptr, off);
+    timer_end(c, tmr);
+    if (s != KMG_OK) return s;
   }
   return KMG_OK;
 }
 
 // weighted keys (device) -> one run (the receive side of the multi-GPU exchange)
 kmg_status keys_to_run(kmg_ctx *c, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n) {
+  const uint32_t P1 = c->n_coarse;
   unsigned long long *d_cnt = c->d_part, *d_start = c->d_part + MAX_PARTS, *d_cur = c->d_part + 2 * MAX_PARTS;
   const uint64_t max_n = (1ull << 32) - 1;
   for (uint64_t i0 = 0; i0 < n; i0 += max_n) {
     const uint64_t m = std::min(max_n, n - i0);
+    const size_t tmr = timer_begin(c, 0);
     CU(c, cudaMemsetAsync(c->d_part, 0, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
-    CU(c, launch_partition_keys(d_keys + i0, d_counts ? d_counts + i0 : nullptr, m, c->n_parts, false, d_cnt, d_start, d_cur, nullptr, nullptr,
-                                num_sms(), c->stream));
-    std::vector<unsigned long long> counts(c->n_parts);
-    CU(c, cudaMemcpyAsync(counts.data(), d_cnt, c->n_parts * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, launch_keys_coarse(d_keys + i0, d_counts ? d_counts + i0 : nullptr, m, P1, false, d_cnt, d_start, d_cur, nullptr, nullptr, c->stream));
+    std::vector<unsigned long long> counts(P1);
+    CU(c, cudaMemcpyAsync(counts.data(), d_cnt, P1 * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
-    Run r;
-    kmg_status s = finish_run_offsets(c, r, counts);
-    if (s != KMG_OK) { free_run(r); return s; }
-    cudaError_t e = cudaMalloc(&r.d_keys, r.n * 8);
-    if (e == cudaSuccess && d_counts) e = cudaMalloc(&r.d_counts, r.n * 8);
-    if (e != cudaSuccess) { free_run(r); return cuda_fail(c, e, "cudaMalloc(run)"); }
-    CU(c, cudaMemcpyAsync(d_start, r.d_offsets, c->n_parts * 8, cudaMemcpyDeviceToDevice, c->stream));
-    CU(c, launch_partition_keys(d_keys + i0, d_counts ? d_counts + i0 : nullptr, m, c->n_parts, true, d_cnt, d_start, d_cur, r.d_keys, r.d_counts,
-                                num_sms(), c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));  // the caller may reuse d_keys right after we return
-    if ((s = add_run(c, std::move(r))) != KMG_OK) return s;
+    std::vector<uint64_t> off(P1 + 1, 0);
+    for (uint32_t p = 0; p < P1; ++p) off[p + 1] = off[p] + counts[p];
+    uint64_t *d_ckeys = nullptr, *d_ccounts = nullptr;
+    kmg_status s = alloc_or_consolidate(c, reinterpret_cast<void **>(&d_ckeys), m * 8, "coarse keys");
+    if (s == KMG_OK && d_counts) s = alloc_or_consolidate(c, reinterpret_cast<void **>(&d_ccounts), m * 8, "coarse counts");
+    if (s != KMG_OK) { cudaFree(d_ckeys); return s; }
+    CU(c, cudaMemcpyAsync(d_start, off.data(), P1 * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, launch_keys_coarse(d_keys + i0, d_counts ? d_counts + i0 : nullptr, m, P1, true, d_cnt, d_start, d_cur, d_ckeys, d_ccounts, c->stream));
+    s = refine_to_run(c, d_ckeys, d_ccounts, off);  // synchronises: the caller may reuse d_keys when we return
+    timer_end(c, tmr);
+    if (s != KMG_OK) return s;
   }
   return KMG_OK;
 }
@@ -363,99 +415,78 @@ kmg_status consolidate(kmg_ctx *c) {
   for (auto &r : c->runs) in.push_back(&r);
   const uint32_t P = c->n_parts, R = (uint32_t)in.size();
   if (R > (uint32_t)CONS_MAX_RUNS) return fail(c, KMG_ERR_STATE, "too many pending runs");
-  std::vector<uint64_t> n_p(P, 0);
-  uint64_t total = 0, max_np = 0;
-  for (uint32_t p = 0; p < P; ++p) {
-    for (auto *r : in) n_p[p] += r->h_offsets[p + 1] - r->h_offsets[p];
-    total += n_p[p];
-    max_np = std::max(max_np, n_p[p]);
+  uint64_t total = 0;
+  for (auto *r : in) total += r->n;
+
+  CountParams prm{};
+  prm.n_parts = P; prm.R = R; prm.preagg = !(c->cfg.flags & KMG_FLAG_NO_PREAGG);
+  for (uint32_t r = 0; r < R; ++r) prm.runs[r] = ConsRun{in[r]->d_keys, in[r]->d_counts, in[r]->d_seg_start, in[r]->d_seg_len};
+
+  // processing order: partitions with many entries first (a partition is counted by ONE CTA)
+  unsigned long long *d_totals = nullptr;
+  uint32_t *d_order = nullptr;
+  std::vector<unsigned long long> totals(P);
+  cudaError_t e = cudaMalloc(&d_totals, (size_t)P * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_order, (size_t)P * 4);
+  if (e == cudaSuccess) e = launch_sum_lens(prm, d_totals, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(totals.data(), d_totals, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_totals);
+  if (e != cudaSuccess) { cudaFree(d_order); return cuda_fail(c, e, "consolidate setup"); }
+  std::vector<uint32_t> order;
+  order.reserve(P);
+  {
+    const uint64_t heavy = 8 * std::max<uint64_t>(total / P, 1024);
+    std::vector<uint32_t> big;
+    for (uint32_t p = 0; p < P; ++p) if (totals[p] > heavy) big.push_back(p);
+    std::sort(big.begin(), big.end(), [&](uint32_t a, uint32_t b) { return totals[a] > totals[b]; });
+    order = big;
+    for (uint32_t p = 0; p < P; ++p) if (totals[p] <= heavy) order.push_back(p);
   }
-  if (max_np >= (1ull << 32)) return fail(c, KMG_ERR_STATE, "a partition holds more than 2^32 entries; use more partitions");
-  // per-partition table capacity: 2.2x its entries, capped at cap_limit (skewed partitions hold few DISTINCT keys);
-  // if a table does fill up the kernel raises error_flag and we retry with a doubled cap.
-  uint32_t cap_limit_log2 = std::max<uint32_t>(10, pow2_ceil_log2((uint64_t)(1.6 * 1.1 * (double)total / P) + 1));
+  e = cudaMemcpyAsync(d_order, order.data(), (size_t)P * 4, cudaMemcpyHostToDevice, c->stream);
+  prm.order = d_order;
+
   Run out;
-  cudaError_t e = cudaMalloc(&out.d_keys, std::max<uint64_t>(total, 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&out.d_keys, std::max<uint64_t>(total, 1) * 8);
   if (e == cudaSuccess) e = cudaMalloc(&out.d_counts, std::max<uint64_t>(total, 1) * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&out.d_offsets, (P + 1) * 8);
-  if (e != cudaSuccess) { free_run(out); return cuda_fail(c, e, "cudaMalloc(consolidated run)"); }
+  if (e == cudaSuccess) e = cudaMalloc(&out.d_seg_start, (size_t)P * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&out.d_seg_len, (size_t)P * 8);
+  if (e != cudaSuccess) { cudaFree(d_order); free_run(out); return cuda_fail(c, e, "cudaMalloc(consolidated run)"); }
+  prm.out_keys = out.d_keys; prm.out_counts = out.d_counts;
+  prm.out_seg_start = out.d_seg_start; prm.out_seg_len = out.d_seg_len;
 
+  const unsigned grid = (unsigned)std::min<uint64_t>(P, (uint64_t)num_sms() * COUNT_CTAS_PER_SM);
   kmg_status st = KMG_OK;
+  unsigned long long n_out = 0;
   for (int attempt = 0;; ++attempt) {
-    std::vector<uint32_t> cap_log2(P), nI(P), nC(P), wait(P, 0xffffffffu);
-    std::vector<ConsPhase> phases;
-    phases.reserve(2 * P + 1);
-    uint64_t tickets = 0;
-    uint32_t max_cap_log2 = 10;
-    for (uint32_t p = 0; p < P; ++p) {
-      cap_log2[p] = std::min(cap_limit_log2, std::max<uint32_t>(10, pow2_ceil_log2((uint64_t)(1.6 * (double)n_p[p]) + 1)));
-      max_cap_log2 = std::max(max_cap_log2, cap_log2[p]);
-      nI[p] = (uint32_t)std::max<uint64_t>(1, (n_p[p] + CONS_INSERT_CHUNK - 1) / CONS_INSERT_CHUNK);
-      nC[p] = n_p[p] ? (uint32_t)std::max<uint64_t>(1, (1ull << cap_log2[p]) / CONS_COMPACT_CHUNK) : 0;
-    }
-    {  // I(p) may only touch its table buffer after the previous NON-EMPTY user of that buffer has been drained
-      int64_t last_user[CONS_NBUF];
-      for (int b = 0; b < CONS_NBUF; ++b) last_user[b] = -1;
-      for (uint32_t p = 0; p < P; ++p) {
-        if (last_user[p % CONS_NBUF] >= 0) wait[p] = (uint32_t)last_user[p % CONS_NBUF];
-        if (n_p[p]) last_user[p % CONS_NBUF] = p;
-      }
-    }
-    auto push = [&](uint32_t p, bool compact) {
-      phases.push_back(ConsPhase{(uint32_t)tickets, p | (compact ? 0x80000000u : 0u)});
-      tickets += compact ? nC[p] : nI[p];
-    };
-    push(0, false);
-    for (uint32_t p = 1; p < P; ++p) { push(p, false); push(p - 1, true); }
-    push(P - 1, true);
-    if (tickets >= (1ull << 32)) { st = fail(c, KMG_ERR_STATE, "consolidation schedule too long"); break; }
-    phases.push_back(ConsPhase{(uint32_t)tickets, 0});  // sentinel
-
-    const uint64_t stride = 1ull << max_cap_log2;
-    uint64_t *d_tables = nullptr;
-    uint8_t *d_meta = nullptr;
-    const size_t meta_u32 = (size_t)P * 8 + 8;  // cap_log2, nI, nC, wait, done_I, done_C, distinct, out_cursor, ticket, error
-    const size_t phases_bytes = phases.size() * sizeof(ConsPhase);
-    e = cudaMalloc(&d_tables, (size_t)CONS_NBUF * stride * 16);
-    if (e == cudaSuccess) e = cudaMalloc(&d_meta, meta_u32 * 4 + phases_bytes + 16);
-    if (e != cudaSuccess) { cudaFree(d_tables); cudaFree(d_meta); st = cuda_fail(c, e, "cudaMalloc(consolidation tables)"); break; }
-    uint32_t *m = reinterpret_cast<uint32_t *>(d_meta);
-    ConsParams prm{};
-    prm.n_parts = P; prm.R = R; prm.total_tickets = (uint32_t)tickets; prm.preagg = !(c->cfg.flags & KMG_FLAG_NO_PREAGG);
-    for (uint32_t r = 0; r < R; ++r) prm.runs[r] = ConsRun{in[r]->d_keys, in[r]->d_counts, in[r]->d_offsets};
-    prm.part_cap_log2 = m; prm.part_nI = m + P; prm.part_nC = m + 2 * P; prm.part_wait = m + 3 * P;
-    prm.done_I = m + 4 * P; prm.done_C = m + 5 * P; prm.distinct = m + 6 * P; prm.out_cursor = m + 7 * P;
-    prm.ticket = m + 8 * P; prm.error_flag = m + 8 * P + 1;
-    prm.phases = reinterpret_cast<const ConsPhase *>(m + meta_u32);
-    prm.tables = d_tables; prm.table_stride_slots = stride;
-    prm.out_keys = out.d_keys; prm.out_counts = out.d_counts;
-    prm.out_base = reinterpret_cast<unsigned long long *>(out.d_offsets);
-    cudaStream_t s = c->stream;
-    e = cudaMemsetAsync(d_meta, 0, meta_u32 * 4, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(m, cap_log2.data(), P * 4, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(m + P, nI.data(), P * 4, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(m + 2 * P, nC.data(), P * 4, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(m + 3 * P, wait.data(), P * 4, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(m + meta_u32, phases.data(), phases_bytes, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(out.d_offsets, 0xFF, (P + 1) * 8, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(out.d_offsets, 0, 8, s);
-    if (e == cudaSuccess) e = launch_table_init(HashTable{d_tables, (uint64_t)CONS_NBUF * stride}, s);
-    timer_begin(c, 1);
-    if (e == cudaSuccess) e = launch_consolidate(prm, num_sms(), s);
-    timer_end(c);
-    uint32_t err_flag = 0;
-    out.h_offsets.assign(P + 1, 0);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&err_flag, prm.error_flag, 4, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out.h_offsets.data(), out.d_offsets, (P + 1) * 8, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(d_tables); cudaFree(d_meta);
-    if (e != cudaSuccess) { st = cuda_fail(c, e, "consolidate"); break; }
-    if (!err_flag) break;
-    if (attempt >= 12 || cap_limit_log2 >= 34) { st = fail(c, KMG_ERR_TABLE_FULL, "partition table overflow could not be resolved"); break; }
-    ++cap_limit_log2;  // some partition had more distinct keys than its capped table: retry with larger tables
+    uint64_t *d_scratch = nullptr;
+    unsigned long long *d_sync = nullptr;  // [0] out_cursor, [1] next (u32), [1]+4 error (u32)
+    const uint64_t slots = (uint64_t)grid << c->scratch_log2;
+    e = cudaMalloc(&d_scratch, slots * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&d_sync, 16);
+    if (e != cudaSuccess) { cudaFree(d_scratch); cudaFree(d_sync); st = cuda_fail(c, e, "cudaMalloc(count scratch)"); break; }
+    prm.scratch = d_scratch; prm.scratch_log2 = c->scratch_log2;
+    prm.out_cursor = d_sync;
+    prm.next = reinterpret_cast<uint32_t *>(d_sync + 1);
+    prm.error_flag = reinterpret_cast<uint32_t *>(d_sync + 1) + 1;
+    e = cudaMemsetAsync(d_sync, 0, 16, c->stream);
+    if (e == cudaSuccess) e = launch_table_init(HashTable{d_scratch, slots}, c->stream);
+    const size_t tmr = timer_begin(c, 1);
+    if (e == cudaSuccess) e = launch_count_partitions(prm, grid, c->stream);
+    timer_end(c, tmr);
+    unsigned long long h_sync[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 16, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_scratch); cudaFree(d_sync);
+    if (e != cudaSuccess) { st = cuda_fail(c, e, "count_partitions"); break; }
+    n_out = h_sync[0];
+    if (!(h_sync[1] >> 32)) break;  // no overflow
+    if (attempt >= 10 || c->scratch_log2 >= 30) { st = fail(c, KMG_ERR_TABLE_FULL, "partition table overflow could not be resolved"); break; }
+    ++c->scratch_log2;  // a partition held more DISTINCT keys than its scratch table: retry with larger tables
   }
+  cudaFree(d_order);
   if (st != KMG_OK) { free_run(out); return st; }
-  out.n = out.h_offsets[P];
+  out.n = n_out;
   if (c->has_result) free_run(c->result);
   for (auto &r : c->runs) free_run(r);
   c->runs.clear();
@@ -484,7 +515,7 @@ kmg_status scan_packed(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
   if (ms != KMG_OK) return ms;
   if (c->mode == kmg_ctx::MODE_PARTITIONED) return scan_to_run(c, n_words_total, has_start);
   uint64_t tile0 = 0;
-  timer_begin(c);
+  const size_t tmr = timer_begin(c);
   while (tile0 < n_tiles) {
     uint64_t want = (n_tiles - tile0) * TILE_WORDS * 32, granted = 0;
     kmg_status s = reserve_capacity(c, want, &granted);
@@ -501,7 +532,7 @@ kmg_status scan_packed(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
     else CU(c, launch_scan_hash(in, c->table, c->d_counters, c->cfg.flags, c->stream));
     tile0 += tiles;
   }
-  timer_end(c);
+  timer_end(c, tmr);
   return KMG_OK;
 }
 
@@ -621,7 +652,7 @@ KMG_EXPORT void kmg_destroy(kmg_ctx *c) {
   timers_collect(c);
   for (auto &r : c->runs) free_run(r);
   if (c->has_result) free_run(c->result);
-  cudaFree(c->d_part);
+  cudaFree(c->d_part); cudaFree(c->d_fine_cursor);
   cudaFree(c->table.slots); cudaFree(c->dense); cudaFree(c->d_counters); cudaFree(c->d_stats);
   cudaFree(c->d_bases); cudaFree(c->d_valid); cudaFree(c->d_start);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -691,7 +722,7 @@ KMG_EXPORT kmg_status kmg_create(const kmg_config *cfg, kmg_ctx **out) {
     c->err = "FORCE_PARTITIONED excludes FORCE_HASH / FORCE_DIRECT";
     return bail(KMG_ERR_INVALID_ARG);
   }
-  if (cfg->parts_log2 > 13) { c->err = "parts_log2 must be <= 13"; return bail(KMG_ERR_INVALID_ARG); }
+  if (cfg->parts_log2 > 20) { c->err = "parts_log2 must be <= 20"; return bail(KMG_ERR_INVALID_ARG); }
   if (cfg->flags & KMG_FLAG_FORCE_PARTITIONED) c->use_dense = false;
   CUC(cudaStreamSynchronize(c->stream));
 #undef CUC

@@ -32,12 +32,26 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 
-// owner shard / partition of a canonical key among n parts (uses the HIGH half of the mix, the
-// table slot uses a multiply-shift of the full mix, so the two are independent enough).
-__host__ __device__ __forceinline__ uint32_t part_of(uint64_t key, uint32_t n_parts) {
-  uint64_t h = mix64(key) >> 32;
-  return (uint32_t)((h * (uint64_t)n_parts) >> 32);
+// Multiply-shift range reduction of a 32-bit hash to [0, n).  On the device this MUST be the __umulhi
+// intrinsic: nvcc 12.9 miscompiled the equivalent 64-bit expression when it indexed a shared-memory
+// atomic (the IMAD.HI term vanished and every key landed in bin 0; tools/test_partkeys.cu).
+__host__ __device__ __forceinline__ uint32_t reduce32(uint32_t h, uint32_t n) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(h, n);
+#else
+  return (uint32_t)(((uint64_t)h * (uint64_t)n) >> 32);
+#endif
 }
+
+// owner shard / coarse partition of a canonical key among n parts: HIGH half of the mix.
+__host__ __device__ __forceinline__ uint32_t part_of(uint64_t key, uint32_t n_parts) {
+  return reduce32((uint32_t)(mix64(key) >> 32), n_parts);
+}
+// Two-level partition index used by the partitioned pipeline: coarse from the high half of the mix, sub-bin
+// from the top bits of the LOW half (the per-partition table slot uses the lowest bits, so all three are
+// independent).  fine = coarse * n_sub + sub.
+__host__ __device__ __forceinline__ uint32_t coarse_of_mix(uint64_t m, uint32_t n_coarse) { return reduce32((uint32_t)(m >> 32), n_coarse); }
+__host__ __device__ __forceinline__ uint32_t sub_of_mix(uint64_t m, uint32_t n_sub) { return reduce32((uint32_t)m, n_sub); }
 
 #ifdef __CUDACC__
 // slot in [0, cap) for arbitrary (not power-of-two) capacities: multiply-shift range reduction.

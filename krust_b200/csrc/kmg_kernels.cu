@@ -13,6 +13,7 @@
 #include <atomic>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "kmg_device.cuh"
 
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) partition_count_kernel(ScanInput
 // same tiles (they come from L2 now) and writes the keys into those ranges.  Long per-partition runs
 // keep the 8-byte stores mergeable into full sectors in L2; keys are re-derived rather than staged.
 // A launch never carries more than 2^32-1 windows, so indices into `out` fit 32 bits.
-constexpr int SUPER_TILES = 8;
+constexpr int SUPER_TILES = 1;
 __global__ void __launch_bounds__(SCAN_THREADS) partition_scatter_kernel(ScanInput in, uint32_t n_parts,
                                                                          const unsigned long long *part_start,
                                                                          unsigned long long *part_cursor, uint64_t *out) {
@@ -665,7 +666,9 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
     const uint64_t n_super = (in.n_tiles + SUPER_TILES - 1) / SUPER_TILES;
     if ((e = set_smem(partition_scatter_kernel, smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    partition_scatter_kernel<<<(unsigned)std::min(n_super, max_ctas), SCAN_THREADS, smem, s>>>(in, n_parts, part_start, part_cursor, out);
+    // at most 2 CTAs/SM: a CTA keeps one tile's worth of output (256 KiB) open for write merging in L2
+    const uint64_t scatter_ctas = std::min<uint64_t>(max_ctas, (uint64_t)num_sms() * 2);
+    partition_scatter_kernel<<<(unsigned)std::min(n_super, scatter_ctas), SCAN_THREADS, smem, s>>>(in, n_parts, part_start, part_cursor, out);
   } else {
     if ((e = set_smem(partition_count_kernel, smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -747,6 +750,20 @@ cudaError_t sort_pairs(uint64_t *d_keys, uint64_t *d_counts, uint64_t n, int key
   }
   cudaError_t e2 = cudaStreamSynchronize(s);
   cudaFree(tmp); cudaFree(alt_k); cudaFree(alt_c);
+  return e != cudaSuccess ? e : e2;
+}
+
+
+// exclusive prefix sum of per-partition sizes (library scan, bookkeeping only)
+cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  void *tmp = nullptr;
+  size_t bytes = 0;
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, bytes, d_in, d_out, n, s);
+  if (e == cudaSuccess) e = cudaMalloc(&tmp, bytes ? bytes : 1);
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, bytes, d_in, d_out, n, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(tmp);
   return e != cudaSuccess ? e : e2;
 }
 

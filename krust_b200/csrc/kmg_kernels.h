@@ -28,37 +28,41 @@ struct TableView {
   uint64_t n;                        // slots, 4^k or number of pairs
 };
 
-// ---- partitioned pipeline (phase B, kmg_consolidate.cu) --------------------------------------------
-constexpr int CONS_THREADS = 256;
-constexpr int CONS_CTAS_PER_SM = 4;
-constexpr int CONS_INSERT_CHUNK = 8192;   // keys per insert ticket (32 per thread, 4 rounds of 8)
-constexpr int CONS_COMPACT_CHUNK = 8192;  // table slots per compact ticket
-constexpr int CONS_NBUF = 3;              // L2-resident table buffers in flight
+// ---- partitioned pipeline (kmg_partition.cu) ----------------------------------------------------------
 constexpr int CONS_MAX_RUNS = 16;
-constexpr int MAX_PARTS = 8192;
+constexpr int MAX_PARTS = 8192;        // bins of ONE scatter level (shared-memory histogram)
+constexpr int REFINE_THREADS = 512;
+constexpr int REFINE_TILE = 16384;     // keys per level-2 tile
+constexpr int COUNT_THREADS = 512;
+constexpr int COUNT_CTAS_PER_SM = 2;
 
+// A run: partition-indexed keys (every key counts 1) or (key, count) pairs.  Partition p of the run is
+// entries [seg_start[p], seg_start[p] + seg_len[p]).
 struct ConsRun {
   const uint64_t *keys;
-  const uint64_t *counts;   // nullptr: every key counts 1
-  const uint64_t *offsets;  // device, n_parts + 1 entries
+  const uint64_t *counts;     // nullptr: every key counts 1
+  const uint64_t *seg_start;  // device, n_parts entries
+  const uint64_t *seg_len;    // device, n_parts entries
 };
-struct ConsPhase {
-  uint32_t first_ticket;
-  uint32_t part_and_type;  // bit 31: 1 = compact, 0 = insert
-};
-struct ConsParams {
-  uint32_t n_parts, R, total_tickets, preagg;
-  ConsRun runs[CONS_MAX_RUNS];
-  const ConsPhase *phases;         // schedule order, terminated by a sentinel with first_ticket = total_tickets
-  const uint32_t *part_cap_log2;   // table capacity (log2 slots) of each partition
-  const uint32_t *part_nI, *part_nC;  // tickets per phase
-  const uint32_t *part_wait;       // previous NON-EMPTY partition that used the same table buffer (~0: none)
-  uint64_t *tables;                // CONS_NBUF buffers of table_stride_slots (key, count-1) slots
-  uint64_t table_stride_slots;
+struct RefineParams {
+  const uint64_t *keys, *counts;          // coarse-partitioned input (counts may be nullptr)
+  const uint64_t *coarse_start;           // n_coarse + 1
+  const uint32_t *tile_prefix;            // n_coarse + 1: first global tile number of each coarse partition
+  uint32_t n_coarse, n_sub, n_tiles, pad;
+  unsigned long long *fine_counts;        // count pass
+  const unsigned long long *fine_start;   // scatter pass: exclusive prefix of fine_counts
+  unsigned long long *fine_cursor;        // scatter pass: zeroed
   uint64_t *out_keys, *out_counts;
-  unsigned long long *out_base;    // n_parts + 1; [0] = 0, rest ~0 until published
-  uint32_t *done_I, *done_C, *distinct, *out_cursor;  // n_parts each, zeroed
-  uint32_t *ticket, *error_flag;
+};
+struct CountParams {
+  uint32_t n_parts, R, scratch_log2, preagg;
+  ConsRun runs[CONS_MAX_RUNS];
+  const uint32_t *order;             // partitions in processing order (largest first)
+  uint64_t *scratch;                 // gridDim.x private tables of 2^scratch_log2 (key, count-1) slots, clean
+  uint64_t *out_keys, *out_counts;
+  unsigned long long *out_cursor;    // zeroed; ends up = number of distinct keys
+  uint64_t *out_seg_start, *out_seg_len;  // n_parts each: where partition p landed in the output
+  uint32_t *next, *error_flag;       // zeroed
 };
 
 enum { CTR_WINDOWS = 0, CTR_DISTINCT = 1, CTR_FULL = 2, CTR_SCRATCH = 3, CTR_N = 8 };
@@ -83,11 +87,13 @@ cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, un
 cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool scatter, unsigned long long *part_counts,
                                   const unsigned long long *part_start, unsigned long long *part_cursor, uint64_t *out,
                                   unsigned long long *counters, cudaStream_t s);
-cudaError_t launch_partition_keys(const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n, uint32_t n_parts, bool scatter,
-                                  unsigned long long *part_counts, const unsigned long long *part_start,
-                                  unsigned long long *part_cursor, uint64_t *out_keys, uint64_t *out_counts, int num_sms,
-                                  cudaStream_t s);
-cudaError_t launch_consolidate(const ConsParams &P, int num_sms, cudaStream_t s);
+cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n, uint32_t n_coarse, bool scatter,
+                               unsigned long long *coarse_counts, const unsigned long long *coarse_start,
+                               unsigned long long *coarse_cursor, uint64_t *out_keys, uint64_t *out_counts, cudaStream_t s);
+cudaError_t launch_refine(const RefineParams &P, bool scatter, cudaStream_t s);
+cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, cudaStream_t s);
+cudaError_t launch_count_partitions(const CountParams &P, unsigned grid, cudaStream_t s);
+cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, cudaStream_t s);
 int num_sms();
 cudaError_t launch_table_init(HashTable t, cudaStream_t s);
 cudaError_t launch_insert_keys(HashTable t, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n,
