@@ -240,7 +240,7 @@ void timers_collect(kmg_ctx *c) {
 // (kernels and rationale: kmg_partition.cu).
 // =================================================================================================
 inline uint32_t pow2_ceil_log2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) ++l; return l; }
-constexpr uint64_t TARGET_KEYS_PER_PART = 4400;  // 2^13-slot scratch tables then run at load ~0.54
+constexpr uint64_t TARGET_KEYS_PER_PART = 3600;  // <= 4096 with 8 sigma to spare: one upsert round per partition; load ~0.44
 
 // Decide how this context counts.  Called at the first feeding call, when the input size is known.
 kmg_status decide_mode(kmg_ctx *c, uint64_t first_call_windows) {
@@ -458,21 +458,24 @@ kmg_status consolidate(kmg_ctx *c) {
   const unsigned grid = (unsigned)std::min<uint64_t>(P, (uint64_t)num_sms() * COUNT_CTAS_PER_SM);
   kmg_status st = KMG_OK;
   unsigned long long n_out = 0;
+  // attempt 0: shared-memory tables (primary).  If a partition holds more distinct keys than such a table
+  // (inputs much larger than the partition plan), fall back to L2-resident scratch tables of growing size.
   for (int attempt = 0;; ++attempt) {
+    const bool use_smem = attempt == 0;
     uint64_t *d_scratch = nullptr;
-    unsigned long long *d_sync = nullptr;  // [0] out_cursor, [1] next (u32), [1]+4 error (u32)
-    const uint64_t slots = (uint64_t)grid << c->scratch_log2;
-    e = cudaMalloc(&d_scratch, slots * 16);
-    if (e == cudaSuccess) e = cudaMalloc(&d_sync, 16);
+    unsigned long long *d_sync = nullptr;  // [0] out_cursor, [1] next (u32) | error (u32)
+    const uint64_t slots = use_smem ? 0 : (uint64_t)grid << c->scratch_log2;
+    e = cudaMalloc(&d_sync, 16);
+    if (e == cudaSuccess && slots) e = cudaMalloc(&d_scratch, slots * 16);
     if (e != cudaSuccess) { cudaFree(d_scratch); cudaFree(d_sync); st = cuda_fail(c, e, "cudaMalloc(count scratch)"); break; }
     prm.scratch = d_scratch; prm.scratch_log2 = c->scratch_log2;
     prm.out_cursor = d_sync;
     prm.next = reinterpret_cast<uint32_t *>(d_sync + 1);
     prm.error_flag = reinterpret_cast<uint32_t *>(d_sync + 1) + 1;
     e = cudaMemsetAsync(d_sync, 0, 16, c->stream);
-    if (e == cudaSuccess) e = launch_table_init(HashTable{d_scratch, slots}, c->stream);
+    if (e == cudaSuccess && slots) e = launch_table_init(HashTable{d_scratch, slots}, c->stream);
     const size_t tmr = timer_begin(c, 1);
-    if (e == cudaSuccess) e = launch_count_partitions(prm, grid, c->stream);
+    if (e == cudaSuccess) e = use_smem ? launch_count_partitions_smem(prm, c->stream) : launch_count_partitions(prm, grid, c->stream);
     timer_end(c, tmr);
     unsigned long long h_sync[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 16, cudaMemcpyDeviceToHost, c->stream);
@@ -481,8 +484,9 @@ kmg_status consolidate(kmg_ctx *c) {
     if (e != cudaSuccess) { st = cuda_fail(c, e, "count_partitions"); break; }
     n_out = h_sync[0];
     if (!(h_sync[1] >> 32)) break;  // no overflow
-    if (attempt >= 10 || c->scratch_log2 >= 30) { st = fail(c, KMG_ERR_TABLE_FULL, "partition table overflow could not be resolved"); break; }
-    ++c->scratch_log2;  // a partition held more DISTINCT keys than its scratch table: retry with larger tables
+    if (attempt >= 12 || c->scratch_log2 >= 30) { st = fail(c, KMG_ERR_TABLE_FULL, "partition table overflow could not be resolved"); break; }
+    if (!use_smem) ++c->scratch_log2;  // retry with larger tables
+    else c->scratch_log2 = std::max<uint32_t>(c->scratch_log2, 14);
   }
   cudaFree(d_order);
   if (st != KMG_OK) { free_run(out); return st; }

@@ -395,9 +395,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) partition_count_kernel(ScanInput
 // keep the 8-byte stores mergeable into full sectors in L2; keys are re-derived rather than staged.
 // A launch never carries more than 2^32-1 windows, so indices into `out` fit 32 bits.
 constexpr int SUPER_TILES = 1;
-__global__ void __launch_bounds__(SCAN_THREADS) partition_scatter_kernel(ScanInput in, uint32_t n_parts,
-                                                                         const unsigned long long *part_start,
-                                                                         unsigned long long *part_cursor, uint64_t *out) {
+constexpr int SCATTER_THREADS = 512;  // 2 CTAs/SM x 16 warps: the pass is latency-bound (shared-memory atomics feed the stores)
+__global__ void __launch_bounds__(SCATTER_THREADS) partition_scatter_kernel(ScanInput in, uint32_t n_parts,
+                                                                            const unsigned long long *part_start,
+                                                                            unsigned long long *part_cursor, uint64_t *out) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
   __shared__ __align__(8) uint64_t bars[2];
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) partition_scatter_kernel(ScanInp
   const int tid = threadIdx.x;
   const bool has_start = in.start != nullptr;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-  for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) hist[p] = 0;
+  for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) hist[p] = 0;
   __syncthreads();
   uint32_t phase0 = 0, phase1 = 0;
   const uint64_t n_super = (in.n_tiles + SUPER_TILES - 1) / SUPER_TILES;
@@ -422,23 +423,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) partition_scatter_kernel(ScanInp
         if (pass == 0) {
           PartCountEmit e{hist, n_parts};
 #pragma unroll 1
-          for (int r = 0; r < WORDS_PER_THREAD; ++r) scan_word<8>(&stages[stage], r * SCAN_THREADS + tid, in.k, has_start, e);
+          for (int r = 0; r < TILE_WORDS / SCATTER_THREADS; ++r) scan_word<8>(&stages[stage], r * SCATTER_THREADS + tid, in.k, has_start, e);
         } else {
           PartScatterEmit e{hist, tile_abs, out, n_parts};
 #pragma unroll 1
-          for (int r = 0; r < WORDS_PER_THREAD; ++r) scan_word<8>(&stages[stage], r * SCAN_THREADS + tid, in.k, has_start, e);
+          for (int r = 0; r < TILE_WORDS / SCATTER_THREADS; ++r) scan_word<8>(&stages[stage], r * SCATTER_THREADS + tid, in.k, has_start, e);
         }
         __syncthreads();
         stage ^= 1;
       }
       if (pass == 0) {
-        for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) {
+        for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) {
           const uint32_t c = hist[p];
           tile_abs[p] = c ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)c)) : 0u;
           hist[p] = 0;
         }
       } else {
-        for (uint32_t p = tid; p < n_parts; p += SCAN_THREADS) hist[p] = 0;
+        for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) hist[p] = 0;
       }
       __syncthreads();
     }
@@ -668,7 +669,7 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
     g_launches.fetch_add(1, std::memory_order_relaxed);
     // at most 2 CTAs/SM: a CTA keeps one tile's worth of output (256 KiB) open for write merging in L2
     const uint64_t scatter_ctas = std::min<uint64_t>(max_ctas, (uint64_t)num_sms() * 2);
-    partition_scatter_kernel<<<(unsigned)std::min(n_super, scatter_ctas), SCAN_THREADS, smem, s>>>(in, n_parts, part_start, part_cursor, out);
+    partition_scatter_kernel<<<(unsigned)std::min(n_super, scatter_ctas), SCATTER_THREADS, smem, s>>>(in, n_parts, part_start, part_cursor, out);
   } else {
     if ((e = set_smem(partition_count_kernel, smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -35,6 +35,8 @@ constexpr int REFINE_THREADS = 512;
 constexpr int REFINE_TILE = 16384;     // keys per level-2 tile
 constexpr int COUNT_THREADS = 512;
 constexpr int COUNT_CTAS_PER_SM = 2;
+constexpr int SMEM_COUNT_THREADS = 1024;   // phase B primary variant: table in shared memory
+constexpr int SMEM_TABLE_SLOTS = 8192;      // 128 KiB of (key, count-1) slots
 
 // A run: partition-indexed keys (every key counts 1) or (key, count) pairs.  Partition p of the run is
 // entries [seg_start[p], seg_start[p] + seg_len[p]).
@@ -93,6 +95,7 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
 cudaError_t launch_refine(const RefineParams &P, bool scatter, cudaStream_t s);
 cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, cudaStream_t s);
 cudaError_t launch_count_partitions(const CountParams &P, unsigned grid, cudaStream_t s);
+cudaError_t launch_count_partitions_smem(const CountParams &P, cudaStream_t s);
 cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, cudaStream_t s);
 int num_sms();
 cudaError_t launch_table_init(HashTable t, cudaStream_t s);

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
     const uint64_t begin = P.coarse_start[c] + (uint64_t)(g - P.tile_prefix[c]) * REFINE_TILE;
     const uint64_t end_c = P.coarse_start[c + 1];
     const uint32_t m = (uint32_t)(end_c - begin < (uint64_t)REFINE_TILE ? end_c - begin : (uint64_t)REFINE_TILE);
-    for (uint32_t i = threadIdx.x; i < m; i += REFINE_THREADS) atomicAdd(hist + sub_of_mix(mix64(__ldcs(P.keys + begin + i)), P.n_sub), 1u);
+    for (uint32_t i = threadIdx.x; i < m; i += REFINE_THREADS) atomicAdd(hist + sub_of_mix(mix64(SCATTER ? P.keys[begin + i] : __ldcs(P.keys + begin + i)), P.n_sub), 1u);
     __syncthreads();
     const uint64_t f0 = (uint64_t)c * P.n_sub;
     if (!SCATTER) {
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
       }
       __syncthreads();
       for (uint32_t i = threadIdx.x; i < m; i += REFINE_THREADS) {  // second read of the tile comes from L2
-        const uint64_t key = P.keys[begin + i];
+        const uint64_t key = __ldcs(P.keys + begin + i);  // last use of this tile
         const uint32_t s = sub_of_mix(mix64(key), P.n_sub);
         const uint64_t o = (uint64_t)tile_abs[s] + atomicAdd(hist + s, 1u);
         P.out_keys[o] = key;
@@ -331,6 +331,156 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
     }
     __syncthreads();  // table clean (same-CTA visibility) before the next partition's upserts
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// phase B, primary variant: the partition's table lives in SHARED memory.  A probe step then costs tens
+// of cycles instead of an L2 round trip, which is what gated the L2-scratch variant above (its CTA-wide
+// time per partition was set by the longest probe chain).  One 1024-thread CTA per SM, 8192 x 16-byte
+// slots (128 KiB); a partition of <= 4096 entries is upserted in a single round of 4 keys per thread.
+// Output is compacted per warp (ballot + popc) so that a warp writes one contiguous run.
+// If a partition ever holds more distinct keys than the table (cannot happen for hash-uniform partitions
+// of the planned size) error_flag is raised and the host re-runs phase B with the L2-scratch variant.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SMEM_COUNT_THREADS, 1) count_partitions_smem_kernel(CountParams P) {
+  extern __shared__ __align__(16) unsigned long long stab[];  // SMEM_TABLE_SLOTS x (key, count-1)
+  __shared__ uint64_t seg_begin[CONS_MAX_RUNS];
+  __shared__ uint64_t seg_prefix[CONS_MAX_RUNS + 1];
+  __shared__ uint32_t s_work, s_warp[SMEM_COUNT_THREADS / 32 + 1];
+  __shared__ unsigned long long s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr uint32_t SLOTS = SMEM_TABLE_SLOTS;
+  constexpr int NW = SMEM_COUNT_THREADS / 32;
+  for (uint32_t i = tid; i < SLOTS; i += SMEM_COUNT_THREADS) { stab[2 * i] = EMPTY_KEY; stab[2 * i + 1] = 0; }
+  uint32_t next_work = 0;
+  if (tid == 0) next_work = atomicAdd(P.next, 1u);
+  __syncthreads();
+
+  for (;;) {
+    if (warp == 0) {
+      uint32_t w = 0;
+      if (lane == 0) { w = next_work; if (w < P.n_parts) next_work = atomicAdd(P.next, 1u); }
+      w = __shfl_sync(0xffffffffu, w, 0);
+      if (w < P.n_parts) {
+        const uint32_t p = P.order[w];
+        uint64_t b = 0, len = 0;
+        if (lane < (int)P.R) { b = P.runs[lane].seg_start[p]; len = P.runs[lane].seg_len[p]; }
+        uint64_t incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint64_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane < (int)P.R) { seg_begin[lane] = b; seg_prefix[lane] = incl - len; }
+        if (lane == (int)P.R - 1) seg_prefix[P.R] = incl;
+      }
+      if (lane == 0) s_work = w;
+    }
+    __syncthreads();
+    const uint32_t work = s_work;
+    if (work >= P.n_parts) break;
+    const uint32_t p = P.order[work];
+    const uint64_t n_p = seg_prefix[P.R];
+    if (n_p == 0) {
+      if (tid == 0) { P.out_seg_start[p] = 0; P.out_seg_len[p] = 0; }
+      __syncthreads();
+      continue;
+    }
+    uint32_t cap_log2 = 8;  // small partitions use a prefix of the table: less to compact
+    while ((1u << cap_log2) < SLOTS && (1ull << cap_log2) * 5 < n_p * 8) ++cap_log2;
+    const uint32_t mask = (1u << cap_log2) - 1;
+
+    constexpr int G = 4;
+    uint32_t new_keys = 0;
+#pragma unroll 1
+    for (uint64_t base = 0; base < n_p; base += (uint64_t)SMEM_COUNT_THREADS * G) {
+      uint64_t key[G], w[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const uint64_t idx = base + (uint64_t)j * SMEM_COUNT_THREADS + tid;
+        w[j] = 0; key[j] = EMPTY_KEY;
+        if (idx < n_p) {
+          uint32_t r = 0;
+          while (r + 1 < P.R && idx >= seg_prefix[r + 1]) ++r;
+          const uint64_t src = seg_begin[r] + (idx - seg_prefix[r]);
+          key[j] = __ldcs(P.runs[r].keys + src);
+          w[j] = P.runs[r].counts ? __ldcs(P.runs[r].counts + src) : 1ull;
+        }
+      }
+      if (P.preagg) {  // warp run-length pre-aggregation (see count_partitions_kernel)
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const uint64_t kk = w[j] ? key[j] : EMPTY_KEY;
+          const uint64_t kp = __shfl_up_sync(0xffffffffu, kk, 1);
+          const bool head = lane == 0 || kp != kk;
+          const uint32_t heads = __ballot_sync(0xffffffffu, head);
+          if (__all_sync(0xffffffffu, w[j] <= 1ull)) {
+            const uint32_t above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
+            const uint32_t end = above ? (uint32_t)__ffs(above) - 1u : 32u;
+            if (w[j]) w[j] = head ? (uint64_t)(end - lane) : 0ull;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        if (!w[j]) continue;
+        uint32_t sl = (uint32_t)mix64(key[j]) & mask;
+        for (uint32_t tries = 0;; ++tries) {  // linear probing in shared memory: a step is tens of cycles
+          unsigned long long cur = stab[2 * sl];
+          if (cur == EMPTY_KEY) cur = atomicCAS(&stab[2 * sl], EMPTY_KEY, key[j]);
+          if (cur == EMPTY_KEY) { ++new_keys; if (w[j] > 1) atomicAdd(&stab[2 * sl + 1], (unsigned long long)(w[j] - 1)); break; }
+          if (cur == key[j]) { atomicAdd(&stab[2 * sl + 1], (unsigned long long)w[j]); break; }
+          if (tries > mask) { atomicExch(P.error_flag, 1u); break; }
+          sl = (sl + 1) & mask;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) new_keys += __shfl_xor_sync(0xffffffffu, new_keys, o);
+    if (lane == 0) s_warp[warp] = new_keys;
+    __syncthreads();  // all upserts done
+    // ---- compact: warp w owns the contiguous slot range [w*chunk, (w+1)*chunk); its occupied slots go out as one run
+    const uint32_t chunk = (mask + 1) / NW > 32 ? (mask + 1) / NW : 32;
+    const uint32_t lo = warp * chunk, hi = lo + chunk <= mask + 1 ? lo + chunk : (lo < mask + 1 ? mask + 1 : lo);
+    uint32_t wcount = 0;
+    for (uint32_t i = lo + lane; i < hi; i += 32) wcount += __popc(__ballot_sync(0xffffffffu, stab[2 * i] != EMPTY_KEY));
+    // (the ballot is warp-uniform; every lane now holds the warp's total)
+    if (tid == 0) {
+      uint32_t d = 0;
+      for (int w2 = 0; w2 < NW; ++w2) d += s_warp[w2];
+      const unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);
+      P.out_seg_start[p] = b; P.out_seg_len[p] = d;
+      s_base = b;
+    }
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = wcount;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w2 = 0; w2 < warp; ++w2) woff += s_warp[w2];
+    uint64_t o = s_base + woff;
+    for (uint32_t i = lo + lane; i < hi; i += 32) {
+      const unsigned long long k = stab[2 * i], cnt = stab[2 * i + 1];
+      const bool occ = k != EMPTY_KEY;
+      const uint32_t m = __ballot_sync(0xffffffffu, occ);
+      if (occ) {
+        const uint64_t dst = o + __popc(m & ((1u << lane) - 1u));
+        __stcs(P.out_keys + dst, (uint64_t)k);
+        __stcs(P.out_counts + dst, (uint64_t)cnt + 1);  // slots store occurrences - 1
+        stab[2 * i] = EMPTY_KEY; stab[2 * i + 1] = 0;
+      }
+      o += __popc(m);
+    }
+    __syncthreads();  // table clean before the next partition
+  }
+}
+
+cudaError_t launch_count_partitions_smem(const CountParams &P, cudaStream_t s) {
+  if (P.n_parts == 0) return cudaSuccess;
+  const size_t smem = (size_t)SMEM_TABLE_SLOTS * 16;
+  cudaError_t e = cudaFuncSetAttribute(count_partitions_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const unsigned grid = (unsigned)std::min<uint64_t>(P.n_parts, (uint64_t)num_sms());
+  count_partitions_smem_kernel<<<grid, SMEM_COUNT_THREADS, smem, s>>>(P);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_count_partitions(const CountParams &P, unsigned grid, cudaStream_t s) {
