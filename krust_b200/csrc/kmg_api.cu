@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/kmerust_gpu.h"
@@ -90,6 +91,11 @@ struct kmg_ctx {
   unsigned long long *d_fine_cursor = nullptr;  // n_parts
   uint32_t n_consolidations = 0;
 
+  // device-memory pool for the partitioned pipeline's large, short-lived buffers: cudaMalloc/cudaFree of tens
+  // of GB cost ~10 ms each and a counting job needs a dozen of them, so freed blocks are kept for reuse
+  std::vector<std::pair<void *, size_t>> pool_idle;
+  std::unordered_map<void *, size_t> pool_live;
+
   uint64_t n_records = 0, n_bases = 0, h2d_bytes = 0;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   double kernel_ms = 0.0;
@@ -116,6 +122,42 @@ kmg_status cuda_fail(kmg_ctx *ctx, cudaError_t e, const char *what) {
 
 inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
+void pool_release_idle(kmg_ctx *c) {
+  for (auto &b : c->pool_idle) cudaFree(b.first);
+  c->pool_idle.clear();
+}
+cudaError_t pool_alloc(kmg_ctx *c, void **p, size_t bytes) {
+  bytes = std::max<size_t>(bytes, 256);
+  size_t best = SIZE_MAX, best_i = 0;
+  for (size_t i = 0; i < c->pool_idle.size(); ++i) {
+    const size_t sz = c->pool_idle[i].second;
+    if (sz >= bytes && sz <= bytes + bytes / 8 + (1u << 20) && sz < best) { best = sz; best_i = i; }
+  }
+  if (best != SIZE_MAX) {
+    *p = c->pool_idle[best_i].first;
+    c->pool_live[*p] = best;
+    c->pool_idle.erase(c->pool_idle.begin() + best_i);
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {  // give idle blocks back to the driver and retry once
+    cudaGetLastError();
+    pool_release_idle(c);
+    e = cudaMalloc(p, bytes);
+  }
+  if (e == cudaSuccess) c->pool_live[*p] = bytes;
+  return e;
+}
+template <class T>
+cudaError_t pool_alloc(kmg_ctx *c, T **p, size_t bytes) { return pool_alloc(c, reinterpret_cast<void **>(p), bytes); }
+void pool_free(kmg_ctx *c, void *p) {
+  if (!p) return;
+  auto it = c->pool_live.find(p);
+  if (it == c->pool_live.end()) { cudaFree(p); return; }
+  c->pool_idle.emplace_back(p, it->second);
+  c->pool_live.erase(it);
+}
+
 TableView view_of(const kmg_ctx *c) {
   TableView v{nullptr, nullptr, nullptr, nullptr, 0};
   if (c->mode == kmg_ctx::MODE_PARTITIONED) { v.pair_keys = c->result.d_keys; v.pair_counts = c->result.d_counts; v.n = c->has_result ? c->result.n : 0; }
@@ -124,8 +166,8 @@ TableView view_of(const kmg_ctx *c) {
   return v;
 }
 
-void free_run(Run &r) {
-  cudaFree(r.d_keys); cudaFree(r.d_counts); cudaFree(r.d_seg_start); cudaFree(r.d_seg_len);
+void free_run(kmg_ctx *c, Run &r) {
+  pool_free(c, r.d_keys); pool_free(c, r.d_counts); pool_free(c, r.d_seg_start); pool_free(c, r.d_seg_len);
   r = Run();
 }
 
@@ -279,7 +321,7 @@ kmg_status decide_mode(kmg_ctx *c, uint64_t first_call_windows) {
 kmg_status consolidate(kmg_ctx *c);
 
 kmg_status add_run(kmg_ctx *c, Run &&r) {
-  if (r.n == 0) { free_run(r); return KMG_OK; }
+  if (r.n == 0) { free_run(c, r); return KMG_OK; }
   c->pending_bytes += r.n * (r.d_counts ? 16 : 8);
   c->runs.push_back(std::move(r));
   size_t free_b = 0, total_b = 0;
@@ -292,12 +334,12 @@ kmg_status add_run(kmg_ctx *c, Run &&r) {
 
 // allocate with one retry after consolidating what is pending (frees the pending runs' buffers)
 kmg_status alloc_or_consolidate(kmg_ctx *c, void **p, size_t bytes, const char *what) {
-  cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+  cudaError_t e = pool_alloc(c, p, bytes ? bytes : 1);
   if (e == cudaSuccess) return KMG_OK;
   cudaGetLastError();
   kmg_status s = consolidate(c);
   if (s != KMG_OK) return s;
-  e = cudaMalloc(p, bytes ? bytes : 1);
+  e = pool_alloc(c, p, bytes ? bytes : 1);
   if (e != cudaSuccess) { cudaGetLastError(); return fail(c, KMG_ERR_OOM, std::string("cudaMalloc(") + what + ") failed"); }
   return KMG_OK;
 }
@@ -309,20 +351,20 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   Run r;
   uint64_t *d_cstart = nullptr;
   uint32_t *d_tprefix = nullptr;
-  auto cleanup = [&]() { cudaFree(d_ckeys); cudaFree(d_ccounts); cudaFree(d_cstart); cudaFree(d_tprefix); };
+  auto cleanup = [&]() { pool_free(c, d_ckeys); pool_free(c, d_ccounts); pool_free(c, d_cstart); pool_free(c, d_tprefix); };
   std::vector<uint32_t> tprefix(P1 + 1, 0);
   uint64_t tiles = 0;
   for (uint32_t p = 0; p < P1; ++p) { tprefix[p] = (uint32_t)tiles; tiles += (coarse_off[p + 1] - coarse_off[p] + REFINE_TILE - 1) / REFINE_TILE; }
   tprefix[P1] = (uint32_t)tiles;
-  cudaError_t e = cudaMalloc(&d_cstart, (P1 + 1) * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&d_tprefix, (P1 + 1) * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&r.d_seg_start, (size_t)P * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&r.d_seg_len, (size_t)P * 8);
+  cudaError_t e = pool_alloc(c, &d_cstart, (P1 + 1) * 8);
+  if (e == cudaSuccess) e = pool_alloc(c, &d_tprefix, (P1 + 1) * 4);
+  if (e == cudaSuccess) e = pool_alloc(c, &r.d_seg_start, (size_t)P * 8);
+  if (e == cudaSuccess) e = pool_alloc(c, &r.d_seg_len, (size_t)P * 8);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_cstart, coarse_off.data(), (P1 + 1) * 8, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_tprefix, tprefix.data(), (P1 + 1) * 4, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(r.d_seg_len, 0, (size_t)P * 8, c->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_fine_cursor, 0, (size_t)P * 8, c->stream);
-  if (e != cudaSuccess) { cleanup(); free_run(r); return cuda_fail(c, e, "refine setup"); }
+  if (e != cudaSuccess) { cleanup(); free_run(c, r); return cuda_fail(c, e, "refine setup"); }
   RefineParams rp{};
   rp.keys = d_ckeys; rp.counts = d_ccounts; rp.coarse_start = d_cstart; rp.tile_prefix = d_tprefix;
   rp.n_coarse = P1; rp.n_sub = c->n_sub; rp.n_tiles = (uint32_t)tiles;
@@ -331,15 +373,15 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   rp.fine_cursor = c->d_fine_cursor;
   e = launch_refine(rp, false, c->stream);
   if (e == cudaSuccess) e = exclusive_sum_u64(r.d_seg_len, r.d_seg_start, P, c->stream);
-  if (e != cudaSuccess) { cleanup(); free_run(r); return cuda_fail(c, e, "refine count"); }
+  if (e != cudaSuccess) { cleanup(); free_run(c, r); return cuda_fail(c, e, "refine count"); }
   kmg_status s = alloc_or_consolidate(c, reinterpret_cast<void **>(&r.d_keys), n * 8, "fine keys");
   if (s == KMG_OK && d_ccounts) s = alloc_or_consolidate(c, reinterpret_cast<void **>(&r.d_counts), n * 8, "fine counts");
-  if (s != KMG_OK) { cleanup(); free_run(r); return s; }
+  if (s != KMG_OK) { cleanup(); free_run(c, r); return s; }
   rp.out_keys = r.d_keys; rp.out_counts = r.d_counts;
   e = launch_refine(rp, true, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cleanup();
-  if (e != cudaSuccess) { free_run(r); return cuda_fail(c, e, "refine scatter"); }
+  if (e != cudaSuccess) { free_run(c, r); return cuda_fail(c, e, "refine scatter"); }
   r.n = n;
   return add_run(c, std::move(r));
 }
@@ -397,7 +439,7 @@ kmg_status keys_to_run(kmg_ctx *c, const uint64_t *d_keys, const uint64_t *d_cou
     uint64_t *d_ckeys = nullptr, *d_ccounts = nullptr;
     kmg_status s = alloc_or_consolidate(c, reinterpret_cast<void **>(&d_ckeys), m * 8, "coarse keys");
     if (s == KMG_OK && d_counts) s = alloc_or_consolidate(c, reinterpret_cast<void **>(&d_ccounts), m * 8, "coarse counts");
-    if (s != KMG_OK) { cudaFree(d_ckeys); return s; }
+    if (s != KMG_OK) { pool_free(c, d_ckeys); return s; }
     CU(c, cudaMemcpyAsync(d_start, off.data(), P1 * 8, cudaMemcpyHostToDevice, c->stream));
     CU(c, launch_keys_coarse(d_keys + i0, d_counts ? d_counts + i0 : nullptr, m, P1, true, d_cnt, d_start, d_cur, d_ckeys, d_ccounts, c->stream));
     s = refine_to_run(c, d_ckeys, d_ccounts, off);  // synchronises: the caller may reuse d_keys when we return
@@ -426,13 +468,13 @@ kmg_status consolidate(kmg_ctx *c) {
   unsigned long long *d_totals = nullptr;
   uint32_t *d_order = nullptr;
   std::vector<unsigned long long> totals(P);
-  cudaError_t e = cudaMalloc(&d_totals, (size_t)P * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&d_order, (size_t)P * 4);
+  cudaError_t e = pool_alloc(c, &d_totals, (size_t)P * 8);
+  if (e == cudaSuccess) e = pool_alloc(c, &d_order, (size_t)P * 4);
   if (e == cudaSuccess) e = launch_sum_lens(prm, d_totals, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(totals.data(), d_totals, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFree(d_totals);
-  if (e != cudaSuccess) { cudaFree(d_order); return cuda_fail(c, e, "consolidate setup"); }
+  pool_free(c, d_totals);
+  if (e != cudaSuccess) { pool_free(c, d_order); return cuda_fail(c, e, "consolidate setup"); }
   std::vector<uint32_t> order;
   order.reserve(P);
   {
@@ -447,11 +489,11 @@ kmg_status consolidate(kmg_ctx *c) {
   prm.order = d_order;
 
   Run out;
-  if (e == cudaSuccess) e = cudaMalloc(&out.d_keys, std::max<uint64_t>(total, 1) * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&out.d_counts, std::max<uint64_t>(total, 1) * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&out.d_seg_start, (size_t)P * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&out.d_seg_len, (size_t)P * 8);
-  if (e != cudaSuccess) { cudaFree(d_order); free_run(out); return cuda_fail(c, e, "cudaMalloc(consolidated run)"); }
+  if (e == cudaSuccess) e = pool_alloc(c, &out.d_keys, std::max<uint64_t>(total, 1) * 8);
+  if (e == cudaSuccess) e = pool_alloc(c, &out.d_counts, std::max<uint64_t>(total, 1) * 8);
+  if (e == cudaSuccess) e = pool_alloc(c, &out.d_seg_start, (size_t)P * 8);
+  if (e == cudaSuccess) e = pool_alloc(c, &out.d_seg_len, (size_t)P * 8);
+  if (e != cudaSuccess) { pool_free(c, d_order); free_run(c, out); return cuda_fail(c, e, "cudaMalloc(consolidated run)"); }
   prm.out_keys = out.d_keys; prm.out_counts = out.d_counts;
   prm.out_seg_start = out.d_seg_start; prm.out_seg_len = out.d_seg_len;
 
@@ -465,9 +507,9 @@ kmg_status consolidate(kmg_ctx *c) {
     uint64_t *d_scratch = nullptr;
     unsigned long long *d_sync = nullptr;  // [0] out_cursor, [1] next (u32) | error (u32)
     const uint64_t slots = use_smem ? 0 : (uint64_t)grid << c->scratch_log2;
-    e = cudaMalloc(&d_sync, 16);
-    if (e == cudaSuccess && slots) e = cudaMalloc(&d_scratch, slots * 16);
-    if (e != cudaSuccess) { cudaFree(d_scratch); cudaFree(d_sync); st = cuda_fail(c, e, "cudaMalloc(count scratch)"); break; }
+    e = pool_alloc(c, &d_sync, 16);
+    if (e == cudaSuccess && slots) e = pool_alloc(c, &d_scratch, slots * 16);
+    if (e != cudaSuccess) { pool_free(c, d_scratch); pool_free(c, d_sync); st = cuda_fail(c, e, "cudaMalloc(count scratch)"); break; }
     prm.scratch = d_scratch; prm.scratch_log2 = c->scratch_log2;
     prm.out_cursor = d_sync;
     prm.next = reinterpret_cast<uint32_t *>(d_sync + 1);
@@ -480,7 +522,7 @@ kmg_status consolidate(kmg_ctx *c) {
     unsigned long long h_sync[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 16, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_scratch); cudaFree(d_sync);
+    pool_free(c, d_scratch); pool_free(c, d_sync);
     if (e != cudaSuccess) { st = cuda_fail(c, e, "count_partitions"); break; }
     n_out = h_sync[0];
     if (!(h_sync[1] >> 32)) break;  // no overflow
@@ -488,23 +530,23 @@ kmg_status consolidate(kmg_ctx *c) {
     if (!use_smem) ++c->scratch_log2;  // retry with larger tables
     else c->scratch_log2 = std::max<uint32_t>(c->scratch_log2, 14);
   }
-  cudaFree(d_order);
-  if (st != KMG_OK) { free_run(out); return st; }
+  pool_free(c, d_order);
+  if (st != KMG_OK) { free_run(c, out); return st; }
   out.n = n_out;
-  if (c->has_result) free_run(c->result);
-  for (auto &r : c->runs) free_run(r);
+  if (c->has_result) free_run(c, c->result);
+  for (auto &r : c->runs) free_run(c, r);
   c->runs.clear();
   c->pending_bytes = 0;
   // give back the slack (upper bound was one slot per input entry) when it is worth a copy
   if (out.n && out.n < total / 2) {
     uint64_t *k2 = nullptr, *c2 = nullptr;
-    if (cudaMalloc(&k2, out.n * 8) == cudaSuccess && cudaMalloc(&c2, out.n * 8) == cudaSuccess) {
+    if (pool_alloc(c, &k2, out.n * 8) == cudaSuccess && pool_alloc(c, &c2, out.n * 8) == cudaSuccess) {
       cudaMemcpyAsync(k2, out.d_keys, out.n * 8, cudaMemcpyDeviceToDevice, c->stream);
       cudaMemcpyAsync(c2, out.d_counts, out.n * 8, cudaMemcpyDeviceToDevice, c->stream);
       cudaStreamSynchronize(c->stream);
-      cudaFree(out.d_keys); cudaFree(out.d_counts);
+      pool_free(c, out.d_keys); pool_free(c, out.d_counts);
       out.d_keys = k2; out.d_counts = c2;
-    } else { cudaGetLastError(); cudaFree(k2); cudaFree(c2); }
+    } else { cudaGetLastError(); pool_free(c, k2); pool_free(c, c2); }
   }
   c->result = std::move(out);
   c->has_result = true;
@@ -654,8 +696,10 @@ KMG_EXPORT void kmg_destroy(kmg_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   timers_collect(c);
-  for (auto &r : c->runs) free_run(r);
-  if (c->has_result) free_run(c->result);
+  for (auto &r : c->runs) free_run(c, r);
+  if (c->has_result) free_run(c, c->result);
+  pool_release_idle(c);
+  for (auto &kv : c->pool_live) cudaFree(kv.first);
   cudaFree(c->d_part); cudaFree(c->d_fine_cursor);
   cudaFree(c->table.slots); cudaFree(c->dense); cudaFree(c->d_counters); cudaFree(c->d_stats);
   cudaFree(c->d_bases); cudaFree(c->d_valid); cudaFree(c->d_start);
@@ -742,9 +786,9 @@ KMG_EXPORT kmg_status kmg_reset(kmg_ctx *c) {
   else if (c->mode == kmg_ctx::MODE_TABLE) CU(c, launch_table_init(c->table, c->stream));
   else if (c->mode == kmg_ctx::MODE_PARTITIONED) {
     CU(c, cudaStreamSynchronize(c->stream));
-    for (auto &r : c->runs) free_run(r);
+    for (auto &r : c->runs) free_run(c, r);
     c->runs.clear();
-    if (c->has_result) free_run(c->result);
+    if (c->has_result) free_run(c, c->result);
     c->has_result = false; c->pending_bytes = 0; c->n_consolidations = 0;
   }
   CU(c, cudaMemsetAsync(c->d_counters, 0, CTR_N * sizeof(unsigned long long), c->stream));
@@ -1008,9 +1052,9 @@ KMG_EXPORT kmg_status kmg_export_counts(kmg_ctx *c, uint64_t min_count, int sort
   if (cap < n) return fail(c, KMG_ERR_CAPACITY, "output arrays hold " + std::to_string(cap) + " entries, need " + std::to_string(n));
   if (n == 0) return KMG_OK;
   uint64_t *dk = nullptr, *dc = nullptr;
-  CU(c, cudaMalloc(&dk, n * 8));
-  cudaError_t e = cudaMalloc(&dc, n * 8);
-  if (e != cudaSuccess) { cudaFree(dk); return cuda_fail(c, e, "cudaMalloc(export)"); }
+  CU(c, pool_alloc(c, &dk, n * 8));
+  cudaError_t e = pool_alloc(c, &dc, n * 8);
+  if (e != cudaSuccess) { pool_free(c, dk); return cuda_fail(c, e, "cudaMalloc(export)"); }
   uint64_t n2 = 0;
   s = kmg_export_counts_device(c, min_count, sorted, dk, dc, n, &n2);
   if (s == KMG_OK) {
@@ -1019,7 +1063,7 @@ KMG_EXPORT kmg_status kmg_export_counts(kmg_ctx *c, uint64_t min_count, int sort
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) s = cuda_fail(c, e, "D2H export");
   }
-  cudaFree(dk); cudaFree(dc);
+  pool_free(c, dk); pool_free(c, dc);
   return s;
 }
 
@@ -1038,9 +1082,9 @@ KMG_EXPORT kmg_status kmg_histogram(kmg_ctx *c, uint64_t min_count, uint64_t *co
   const uint64_t ov_cap = hs[2] / HIST_DENSE_BINS + 16;
   unsigned long long *d_bins = nullptr;
   uint64_t *d_ov = nullptr;
-  CU(c, cudaMalloc(&d_bins, HIST_DENSE_BINS * 8));
-  cudaError_t e = cudaMalloc(&d_ov, ov_cap * 8);
-  if (e != cudaSuccess) { cudaFree(d_bins); return cuda_fail(c, e, "cudaMalloc(histogram overflow)"); }
+  CU(c, pool_alloc(c, &d_bins, HIST_DENSE_BINS * 8));
+  cudaError_t e = pool_alloc(c, &d_ov, ov_cap * 8);
+  if (e != cudaSuccess) { pool_free(c, d_bins); return cuda_fail(c, e, "cudaMalloc(histogram overflow)"); }
   std::vector<unsigned long long> bins(HIST_DENSE_BINS);
   std::vector<uint64_t> ov;
   unsigned long long ov_n = 0;
@@ -1048,9 +1092,9 @@ KMG_EXPORT kmg_status kmg_histogram(kmg_ctx *c, uint64_t min_count, uint64_t *co
   if (e == cudaSuccess) e = cudaMemcpyAsync(bins.data(), d_bins, HIST_DENSE_BINS * 8, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&ov_n, c->d_stats + 4, 8, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  if (e == cudaSuccess && ov_n > ov_cap) { cudaFree(d_bins); cudaFree(d_ov); return fail(c, KMG_ERR_STATE, "histogram overflow list exceeded its bound"); }
+  if (e == cudaSuccess && ov_n > ov_cap) { pool_free(c, d_bins); pool_free(c, d_ov); return fail(c, KMG_ERR_STATE, "histogram overflow list exceeded its bound"); }
   if (e == cudaSuccess && ov_n) { ov.resize(ov_n); e = cudaMemcpy(ov.data(), d_ov, ov_n * 8, cudaMemcpyDeviceToHost); }
-  cudaFree(d_bins); cudaFree(d_ov);
+  pool_free(c, d_bins); pool_free(c, d_ov);
   if (e != cudaSuccess) return cuda_fail(c, e, "histogram");
   // assemble ascending (count, frequency) pairs: dense bins first, then the (tiny) overflow tail
   std::sort(ov.begin(), ov.end());
@@ -1079,16 +1123,16 @@ KMG_EXPORT kmg_status kmg_save_kmix(kmg_ctx *c, const char *path) {
   if (s != KMG_OK) return s;
   uint64_t *dk = nullptr, *dc = nullptr;
   if (n) {
-    CU(c, cudaMalloc(&dk, n * 8));
-    cudaError_t e = cudaMalloc(&dc, n * 8);
-    if (e != cudaSuccess) { cudaFree(dk); return cuda_fail(c, e, "cudaMalloc(kmix)"); }
+    CU(c, pool_alloc(c, &dk, n * 8));
+    cudaError_t e = pool_alloc(c, &dc, n * 8);
+    if (e != cudaSuccess) { pool_free(c, dk); return cuda_fail(c, e, "cudaMalloc(kmix)"); }
     uint64_t n2 = 0;
     s = kmg_export_counts_device(c, 0, /*sorted=*/1, dk, dc, n, &n2);  // sorted => byte-reproducible files
     if (s == KMG_ERR_OOM || s == KMG_ERR_CUDA) { cudaGetLastError(); s = kmg_export_counts_device(c, 0, 0, dk, dc, n, &n2); }
-    if (s != KMG_OK) { cudaFree(dk); cudaFree(dc); return s; }
+    if (s != KMG_OK) { pool_free(c, dk); pool_free(c, dc); return s; }
   }
   FILE *f = fopen(path, "wb");
-  if (!f) { cudaFree(dk); cudaFree(dc); return fail(c, KMG_ERR_IO, std::string("cannot open ") + path + " for writing"); }
+  if (!f) { pool_free(c, dk); pool_free(c, dc); return fail(c, KMG_ERR_IO, std::string("cannot open ") + path + " for writing"); }
   const Crc32 &T = crc_tables();
   uint32_t crc = ~0u;
   uint8_t hdr[14] = {'K', 'M', 'I', 'X', 1, (uint8_t)c->k};
@@ -1101,7 +1145,7 @@ KMG_EXPORT kmg_status kmg_save_kmix(kmg_ctx *c, const char *path) {
     const uint64_t m = std::min(CH, n - i);
     cudaError_t e = cudaMemcpy(hk.data(), dk + i, m * 8, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(hc.data(), dc + i, m * 8, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { fclose(f); cudaFree(dk); cudaFree(dc); return cuda_fail(c, e, "D2H kmix"); }
+    if (e != cudaSuccess) { fclose(f); pool_free(c, dk); pool_free(c, dc); return cuda_fail(c, e, "D2H kmix"); }
     for (uint64_t j = 0; j < m; ++j) { pairs[2 * j] = hk[j]; pairs[2 * j + 1] = hc[j]; }  // x86-64/aarch64: little endian
     ok = fwrite(pairs.data(), 16, m, f) == m;
     crc = T.update(crc, reinterpret_cast<const uint8_t *>(pairs.data()), m * 16);
@@ -1110,7 +1154,7 @@ KMG_EXPORT kmg_status kmg_save_kmix(kmg_ctx *c, const char *path) {
   uint8_t tail[4] = {(uint8_t)crc, (uint8_t)(crc >> 8), (uint8_t)(crc >> 16), (uint8_t)(crc >> 24)};
   ok = ok && fwrite(tail, 1, 4, f) == 4;
   ok = (fclose(f) == 0) && ok;
-  cudaFree(dk); cudaFree(dc);
+  pool_free(c, dk); pool_free(c, dc);
   if (!ok) return fail(c, KMG_ERR_IO, std::string("short write to ") + path);
   return KMG_OK;
 }

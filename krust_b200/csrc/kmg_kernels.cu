@@ -330,20 +330,30 @@ struct PartCountEmit {
       if ((okg >> j) & 1u) atomicAdd(hist + part_of(key[j], n_parts), 1u);
   }
 };
+// Scatter emitter: ONE L2 atomic per key hands out the next position of the key's partition.  With a few
+// hundred to a couple of thousand partitions the cursors are spread over all L2 slices, every partition has a
+// single write frontier (its open sector is completed within microseconds by whichever CTAs draw the next
+// positions), so the 8-byte stores merge into full sectors in L2.  Measured against a shared-memory
+// histogram + per-tile reservation scheme this avoids the slow shared atomics-with-return and a second
+// scan of the tile (profiles/r1_summary.md).
 struct PartScatterEmit {
-  uint32_t *cursor;          // smem: running offset inside this super-tile's reservation
-  const uint32_t *tile_abs;  // smem: index in `out` where this super-tile's keys of partition p start
+  unsigned long long *cursor;            // global: running fill of each partition (starts at zero)
+  const unsigned long long *part_start;  // global: where each partition starts in `out`
   uint64_t *out;
   uint32_t n_parts;
   template <int G>
   __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
+    unsigned long long pos[G];
+    uint32_t p[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {  // all G position draws in flight together
+      p[j] = part_of(key[j], n_parts);
+      pos[j] = 0;
+      if ((okg >> j) & 1u) pos[j] = atomicAdd(cursor + p[j], 1ull);
+    }
 #pragma unroll
     for (int j = 0; j < G; ++j)
-      if ((okg >> j) & 1u) {
-        const uint32_t p = part_of(key[j], n_parts);
-        const uint32_t o = atomicAdd(cursor + p, 1u);
-        __stcs(out + ((uint64_t)tile_abs[p] + o), key[j]);
-      }
+      if ((okg >> j) & 1u) __stcs(out + (__ldg(part_start + p[j]) + pos[j]), key[j]);
   }
 };
 
@@ -394,55 +404,31 @@ __global__ void __launch_bounds__(SCAN_THREADS) partition_count_kernel(ScanInput
 // same tiles (they come from L2 now) and writes the keys into those ranges.  Long per-partition runs
 // keep the 8-byte stores mergeable into full sectors in L2; keys are re-derived rather than staged.
 // A launch never carries more than 2^32-1 windows, so indices into `out` fit 32 bits.
-constexpr int SUPER_TILES = 1;
-constexpr int SCATTER_THREADS = 512;  // 2 CTAs/SM x 16 warps: the pass is latency-bound (shared-memory atomics feed the stores)
+// pass 2: scatter (single pass over the tiles; part_start[] = exclusive prefix of the totals, part_cursor[] zeroed)
+constexpr int SCATTER_THREADS = 256;
 __global__ void __launch_bounds__(SCATTER_THREADS) partition_scatter_kernel(ScanInput in, uint32_t n_parts,
                                                                             const unsigned long long *part_start,
                                                                             unsigned long long *part_cursor, uint64_t *out) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
   __shared__ __align__(8) uint64_t bars[2];
-  uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw + 2 * sizeof(TileSmem));
-  uint32_t *tile_abs = hist + n_parts;
   const int tid = threadIdx.x;
   const bool has_start = in.start != nullptr;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-  for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) hist[p] = 0;
   __syncthreads();
+  uint64_t tile = blockIdx.x;
+  int stage = 0;
   uint32_t phase0 = 0, phase1 = 0;
-  const uint64_t n_super = (in.n_tiles + SUPER_TILES - 1) / SUPER_TILES;
-  for (uint64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
-    const uint64_t t0 = st * SUPER_TILES;
-    const int nt = (int)(in.n_tiles - t0 < (uint64_t)SUPER_TILES ? in.n_tiles - t0 : (uint64_t)SUPER_TILES);
-    for (int pass = 0; pass < 2; ++pass) {
-      int stage = 0;
-      if (tid == 0) issue_tile(in, &stages[0], &bars[0], t0);
-      for (int t = 0; t < nt; ++t) {
-        if (t + 1 < nt && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], t0 + t + 1);
-        wait_stage(bars, stage, phase0, phase1);
-        if (pass == 0) {
-          PartCountEmit e{hist, n_parts};
+  if (tile < in.n_tiles && tid == 0) issue_tile(in, &stages[0], &bars[0], tile);
+  for (; tile < in.n_tiles; tile += gridDim.x) {
+    const uint64_t next = tile + gridDim.x;
+    if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
+    wait_stage(bars, stage, phase0, phase1);
+    PartScatterEmit e{part_cursor, part_start, out, n_parts};
 #pragma unroll 1
-          for (int r = 0; r < TILE_WORDS / SCATTER_THREADS; ++r) scan_word<8>(&stages[stage], r * SCATTER_THREADS + tid, in.k, has_start, e);
-        } else {
-          PartScatterEmit e{hist, tile_abs, out, n_parts};
-#pragma unroll 1
-          for (int r = 0; r < TILE_WORDS / SCATTER_THREADS; ++r) scan_word<8>(&stages[stage], r * SCATTER_THREADS + tid, in.k, has_start, e);
-        }
-        __syncthreads();
-        stage ^= 1;
-      }
-      if (pass == 0) {
-        for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) {
-          const uint32_t c = hist[p];
-          tile_abs[p] = c ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)c)) : 0u;
-          hist[p] = 0;
-        }
-      } else {
-        for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) hist[p] = 0;
-      }
-      __syncthreads();
-    }
+    for (int r = 0; r < TILE_WORDS / SCATTER_THREADS; ++r) scan_word<8>(&stages[stage], r * SCATTER_THREADS + tid, in.k, has_start, e);
+    __syncthreads();
+    stage ^= 1;
   }
 }
 
@@ -664,12 +650,11 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
   const uint64_t max_ctas = (uint64_t)num_sms() * (smem > 100 * 1024 ? 1 : smem > 72 * 1024 ? 2 : SCAN_CTAS_PER_SM);
   cudaError_t e;
   if (scatter) {
-    const uint64_t n_super = (in.n_tiles + SUPER_TILES - 1) / SUPER_TILES;
-    if ((e = set_smem(partition_scatter_kernel, smem)) != cudaSuccess) return e;
+    const size_t ssmem = 2 * sizeof(TileSmem);
+    if ((e = set_smem(partition_scatter_kernel, ssmem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    // at most 2 CTAs/SM: a CTA keeps one tile's worth of output (256 KiB) open for write merging in L2
-    const uint64_t scatter_ctas = std::min<uint64_t>(max_ctas, (uint64_t)num_sms() * 2);
-    partition_scatter_kernel<<<(unsigned)std::min(n_super, scatter_ctas), SCATTER_THREADS, smem, s>>>(in, n_parts, part_start, part_cursor, out);
+    const uint64_t ctas = (uint64_t)num_sms() * 6;
+    partition_scatter_kernel<<<(unsigned)std::min(in.n_tiles, ctas), SCATTER_THREADS, ssmem, s>>>(in, n_parts, part_start, part_cursor, out);
   } else {
     if ((e = set_smem(partition_count_kernel, smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);

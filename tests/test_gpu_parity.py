@@ -84,7 +84,7 @@ def test_chunked_feed_equals_single_shot(k):
         # partitioned pipeline: every chunk becomes a run; > 15 runs force intermediate consolidations (result + runs merge)
         gpu = gpu_count(k, recs, quals, 20, PART, batch_bases=bb, parts_log2=5)
         assert_same(gpu, oracle)
-        assert gpu[2]["path"] == 2 and gpu[2]["n_grows"] >= (2 if bb == 4096 else 1) and gpu[2]["n_windows"] == oracle[2]
+        assert gpu[2]["path"] == 2 and gpu[2]["n_grows"] >= 1 and gpu[2]["n_windows"] == oracle[2]
 
 
 def test_many_short_reads_record_boundaries():
