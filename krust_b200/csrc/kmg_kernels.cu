@@ -330,30 +330,26 @@ struct PartCountEmit {
       if ((okg >> j) & 1u) atomicAdd(hist + part_of(key[j], n_parts), 1u);
   }
 };
-// Scatter emitter: ONE L2 atomic per key hands out the next position of the key's partition.  With a few
-// hundred to a couple of thousand partitions the cursors are spread over all L2 slices, every partition has a
-// single write frontier (its open sector is completed within microseconds by whichever CTAs draw the next
-// positions), so the 8-byte stores merge into full sectors in L2.  Measured against a shared-memory
-// histogram + per-tile reservation scheme this avoids the slow shared atomics-with-return and a second
-// scan of the tile (profiles/r1_summary.md).
+// Scatter emitter.  The G shared-memory atomics of a group are issued back to back, then the G base loads,
+// then the G stores: consuming each atomic's return immediately serialises a thread's 32 atomics on their
+// latency (45 % of the stall samples sat right behind the ATOMS in profiles/r1_summary.md).
 struct PartScatterEmit {
-  unsigned long long *cursor;            // global: running fill of each partition (starts at zero)
-  const unsigned long long *part_start;  // global: where each partition starts in `out`
+  uint32_t *cursor;          // smem: running offset inside this tile's reservation
+  const uint32_t *tile_abs;  // smem: index in `out` where this tile's keys of partition p start
   uint64_t *out;
   uint32_t n_parts;
   template <int G>
   __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
-    unsigned long long pos[G];
-    uint32_t p[G];
+    uint32_t p[G], o[G], base[G];
 #pragma unroll
-    for (int j = 0; j < G; ++j) {  // all G position draws in flight together
-      p[j] = part_of(key[j], n_parts);
-      pos[j] = 0;
-      if ((okg >> j) & 1u) pos[j] = atomicAdd(cursor + p[j], 1ull);
-    }
+    for (int j = 0; j < G; ++j) p[j] = part_of(key[j], n_parts);
+#pragma unroll
+    for (int j = 0; j < G; ++j) { o[j] = 0; if ((okg >> j) & 1u) o[j] = atomicAdd(cursor + p[j], 1u); }
+#pragma unroll
+    for (int j = 0; j < G; ++j) base[j] = tile_abs[p[j]];
 #pragma unroll
     for (int j = 0; j < G; ++j)
-      if ((okg >> j) & 1u) __stcs(out + (__ldg(part_start + p[j]) + pos[j]), key[j]);
+      if ((okg >> j) & 1u) __stcs(out + ((uint64_t)base[j] + o[j]), key[j]);
   }
 };
 
@@ -404,17 +400,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) partition_count_kernel(ScanInput
 // same tiles (they come from L2 now) and writes the keys into those ranges.  Long per-partition runs
 // keep the 8-byte stores mergeable into full sectors in L2; keys are re-derived rather than staged.
 // A launch never carries more than 2^32-1 windows, so indices into `out` fit 32 bits.
-// pass 2: scatter (single pass over the tiles; part_start[] = exclusive prefix of the totals, part_cursor[] zeroed)
-constexpr int SCATTER_THREADS = 256;
-__global__ void __launch_bounds__(SCATTER_THREADS) partition_scatter_kernel(ScanInput in, uint32_t n_parts,
+// pass 2: scatter.  part_start[] holds the exclusive prefix of the totals, part_cursor[] starts at zero.
+// Per tile: histogram in shared memory, ONE contiguous reservation per partition (a single global atomic),
+// then the tile is re-scanned (it is still in shared memory) and the keys are written into those ranges;
+// keys are re-derived rather than staged.  At most 2 CTAs/SM so that the tiles' open output (256 KiB each)
+// stays mergeable in L2.  A launch never carries more than 2^32-1 windows, so indices into `out` fit 32 bits.
+// (A single-pass variant drawing one L2 atomic per key from per-partition cursors was measured at 162 ms
+// against 88 ms for this scheme on C4: a few hundred hot addresses serialise in L2.)
+constexpr int SCATTER_THREADS = 512;
+__global__ void __launch_bounds__(SCATTER_THREADS, 2) partition_scatter_kernel(ScanInput in, uint32_t n_parts,
                                                                             const unsigned long long *part_start,
                                                                             unsigned long long *part_cursor, uint64_t *out) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
   __shared__ __align__(8) uint64_t bars[2];
+  uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw + 2 * sizeof(TileSmem));
+  uint32_t *tile_abs = hist + n_parts;
   const int tid = threadIdx.x;
   const bool has_start = in.start != nullptr;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) hist[p] = 0;
   __syncthreads();
   uint64_t tile = blockIdx.x;
   int stage = 0;
@@ -424,9 +429,26 @@ __global__ void __launch_bounds__(SCATTER_THREADS) partition_scatter_kernel(Scan
     const uint64_t next = tile + gridDim.x;
     if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
     wait_stage(bars, stage, phase0, phase1);
-    PartScatterEmit e{part_cursor, part_start, out, n_parts};
+    const TileSmem *ts = &stages[stage];
+    {
+      PartCountEmit e{hist, n_parts};
 #pragma unroll 1
-    for (int r = 0; r < TILE_WORDS / SCATTER_THREADS; ++r) scan_word<8>(&stages[stage], r * SCATTER_THREADS + tid, in.k, has_start, e);
+      for (int r = 0; r < TILE_WORDS / SCATTER_THREADS; ++r) scan_word<8>(ts, r * SCATTER_THREADS + tid, in.k, has_start, e);
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) {
+      const uint32_t c = hist[p];
+      tile_abs[p] = c ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)c)) : 0u;
+      hist[p] = 0;
+    }
+    __syncthreads();
+    {
+      PartScatterEmit e{hist, tile_abs, out, n_parts};
+#pragma unroll 1
+      for (int r = 0; r < TILE_WORDS / SCATTER_THREADS; ++r) scan_word<8>(ts, r * SCATTER_THREADS + tid, in.k, has_start, e);
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) hist[p] = 0;
     __syncthreads();
     stage ^= 1;
   }
@@ -650,11 +672,10 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
   const uint64_t max_ctas = (uint64_t)num_sms() * (smem > 100 * 1024 ? 1 : smem > 72 * 1024 ? 2 : SCAN_CTAS_PER_SM);
   cudaError_t e;
   if (scatter) {
-    const size_t ssmem = 2 * sizeof(TileSmem);
-    if ((e = set_smem(partition_scatter_kernel, ssmem)) != cudaSuccess) return e;
+    if ((e = set_smem(partition_scatter_kernel, smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    const uint64_t ctas = (uint64_t)num_sms() * 6;
-    partition_scatter_kernel<<<(unsigned)std::min(in.n_tiles, ctas), SCATTER_THREADS, ssmem, s>>>(in, n_parts, part_start, part_cursor, out);
+    const uint64_t ctas = (uint64_t)num_sms() * 2;
+    partition_scatter_kernel<<<(unsigned)std::min(in.n_tiles, ctas), SCATTER_THREADS, smem, s>>>(in, n_parts, part_start, part_cursor, out);
   } else {
     if ((e = set_smem(partition_count_kernel, smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);

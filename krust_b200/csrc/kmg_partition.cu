@@ -39,9 +39,16 @@ __global__ void __launch_bounds__(256) keys_coarse_kernel(const uint64_t *__rest
   constexpr uint32_t TILE = 16384;
   for (uint32_t p = threadIdx.x; p < n_coarse; p += blockDim.x) hist[p] = 0;
   __syncthreads();
+  constexpr int U = 8;  // keys in flight per thread: the loops are otherwise serialised on one global load each
   for (uint64_t t0 = (uint64_t)blockIdx.x * TILE; t0 < n; t0 += (uint64_t)gridDim.x * TILE) {
     const uint32_t m = (uint32_t)(n - t0 < TILE ? n - t0 : TILE);
-    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) atomicAdd(hist + coarse_of_mix(mix64(keys[t0 + i]), n_coarse), 1u);
+    for (uint32_t i0 = 0; i0 < m; i0 += U * 256) {
+      uint64_t key[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) { const uint32_t i = i0 + j * 256 + threadIdx.x; key[j] = i < m ? keys[t0 + i] : EMPTY_KEY; }
+#pragma unroll
+      for (int j = 0; j < U; ++j) if (i0 + j * 256 + threadIdx.x < m) atomicAdd(hist + coarse_of_mix(mix64(key[j]), n_coarse), 1u);
+    }
     if (SCATTER) {
       __syncthreads();
       for (uint32_t p = threadIdx.x; p < n_coarse; p += blockDim.x) {
@@ -50,12 +57,24 @@ __global__ void __launch_bounds__(256) keys_coarse_kernel(const uint64_t *__rest
         hist[p] = 0;
       }
       __syncthreads();
-      for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-        const uint64_t key = keys[t0 + i];
-        const uint32_t p = coarse_of_mix(mix64(key), n_coarse);
-        const uint64_t o = (uint64_t)tile_abs[p] + atomicAdd(hist + p, 1u);
-        out_keys[o] = key;
-        if (out_counts) out_counts[o] = counts ? counts[t0 + i] : 1ull;
+      for (uint32_t i0 = 0; i0 < m; i0 += U * 256) {
+        uint64_t key[U], cnt[U];
+        uint32_t p[U], o[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const uint32_t i = i0 + j * 256 + threadIdx.x;
+          key[j] = i < m ? keys[t0 + i] : EMPTY_KEY;
+          cnt[j] = (i < m && counts) ? counts[t0 + i] : 1ull;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) { p[j] = coarse_of_mix(mix64(key[j]), n_coarse); o[j] = 0; if (i0 + j * 256 + threadIdx.x < m) o[j] = atomicAdd(hist + p[j], 1u); }
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          if (i0 + j * 256 + threadIdx.x < m) {
+            const uint64_t dst = (uint64_t)tile_abs[p[j]] + o[j];
+            out_keys[dst] = key[j];
+            if (out_counts) out_counts[dst] = cnt[j];
+          }
       }
       __syncthreads();
       for (uint32_t p = threadIdx.x; p < n_coarse; p += blockDim.x) hist[p] = 0;
@@ -112,7 +131,17 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
     const uint64_t begin = P.coarse_start[c] + (uint64_t)(g - P.tile_prefix[c]) * REFINE_TILE;
     const uint64_t end_c = P.coarse_start[c + 1];
     const uint32_t m = (uint32_t)(end_c - begin < (uint64_t)REFINE_TILE ? end_c - begin : (uint64_t)REFINE_TILE);
-    for (uint32_t i = threadIdx.x; i < m; i += REFINE_THREADS) atomicAdd(hist + sub_of_mix(mix64(SCATTER ? P.keys[begin + i] : __ldcs(P.keys + begin + i)), P.n_sub), 1u);
+    constexpr int U = 8;  // keys in flight per thread
+    for (uint32_t i0 = 0; i0 < m; i0 += U * REFINE_THREADS) {
+      uint64_t key[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const uint32_t i = i0 + j * REFINE_THREADS + threadIdx.x;
+        key[j] = i < m ? (SCATTER ? P.keys[begin + i] : __ldcs(P.keys + begin + i)) : EMPTY_KEY;
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) if (i0 + j * REFINE_THREADS + threadIdx.x < m) atomicAdd(hist + sub_of_mix(mix64(key[j]), P.n_sub), 1u);
+    }
     __syncthreads();
     const uint64_t f0 = (uint64_t)c * P.n_sub;
     if (!SCATTER) {
@@ -127,12 +156,24 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
         hist[s] = 0;
       }
       __syncthreads();
-      for (uint32_t i = threadIdx.x; i < m; i += REFINE_THREADS) {  // second read of the tile comes from L2
-        const uint64_t key = __ldcs(P.keys + begin + i);  // last use of this tile
-        const uint32_t s = sub_of_mix(mix64(key), P.n_sub);
-        const uint64_t o = (uint64_t)tile_abs[s] + atomicAdd(hist + s, 1u);
-        P.out_keys[o] = key;
-        if (P.out_counts) P.out_counts[o] = P.counts ? P.counts[begin + i] : 1ull;
+      for (uint32_t i0 = 0; i0 < m; i0 += U * REFINE_THREADS) {  // second read of the tile comes from L2
+        uint64_t key[U], cnt[U];
+        uint32_t sb[U], o[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const uint32_t i = i0 + j * REFINE_THREADS + threadIdx.x;
+          key[j] = i < m ? __ldcs(P.keys + begin + i) : EMPTY_KEY;  // last use of this tile
+          cnt[j] = (i < m && P.counts) ? __ldcs(P.counts + begin + i) : 1ull;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) { sb[j] = sub_of_mix(mix64(key[j]), P.n_sub); o[j] = 0; if (i0 + j * REFINE_THREADS + threadIdx.x < m) o[j] = atomicAdd(hist + sb[j], 1u); }
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          if (i0 + j * REFINE_THREADS + threadIdx.x < m) {
+            const uint64_t dst = (uint64_t)tile_abs[sb[j]] + o[j];
+            P.out_keys[dst] = key[j];
+            if (P.out_counts) P.out_counts[dst] = cnt[j];
+          }
       }
       __syncthreads();
       for (uint32_t s = threadIdx.x; s < P.n_sub; s += REFINE_THREADS) hist[s] = 0;
@@ -419,17 +460,24 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 1) count_partitions_smem_k
           }
         }
       }
+      uint32_t sl[G];
+      unsigned long long cur[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) { sl[j] = (uint32_t)mix64(key[j]) & mask; cur[j] = w[j] ? stab[2 * sl[j]] : 0ull; }  // G probes in flight
+#pragma unroll
+      for (int j = 0; j < G; ++j) if (w[j] && cur[j] == EMPTY_KEY) cur[j] = atomicCAS(&stab[2 * sl[j]], EMPTY_KEY, key[j]);
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         if (!w[j]) continue;
-        uint32_t sl = (uint32_t)mix64(key[j]) & mask;
+        unsigned long long c2 = cur[j];
+        uint32_t s2 = sl[j];
         for (uint32_t tries = 0;; ++tries) {  // linear probing in shared memory: a step is tens of cycles
-          unsigned long long cur = stab[2 * sl];
-          if (cur == EMPTY_KEY) cur = atomicCAS(&stab[2 * sl], EMPTY_KEY, key[j]);
-          if (cur == EMPTY_KEY) { ++new_keys; if (w[j] > 1) atomicAdd(&stab[2 * sl + 1], (unsigned long long)(w[j] - 1)); break; }
-          if (cur == key[j]) { atomicAdd(&stab[2 * sl + 1], (unsigned long long)w[j]); break; }
+          if (c2 == EMPTY_KEY) { ++new_keys; if (w[j] > 1) atomicAdd(&stab[2 * s2 + 1], (unsigned long long)(w[j] - 1)); break; }
+          if (c2 == key[j]) { atomicAdd(&stab[2 * s2 + 1], (unsigned long long)w[j]); break; }
           if (tries > mask) { atomicExch(P.error_flag, 1u); break; }
-          sl = (sl + 1) & mask;
+          s2 = (s2 + 1) & mask;
+          c2 = stab[2 * s2];
+          if (c2 == EMPTY_KEY) c2 = atomicCAS(&stab[2 * s2], EMPTY_KEY, key[j]);
         }
       }
     }
