@@ -35,8 +35,8 @@ constexpr int REFINE_THREADS = 512;
 constexpr int REFINE_TILE = 16384;     // keys per level-2 tile
 constexpr int COUNT_THREADS = 512;
 constexpr int COUNT_CTAS_PER_SM = 2;
-constexpr int SMEM_COUNT_THREADS = 1024;   // phase B primary variant: table in shared memory
-constexpr int SMEM_TABLE_SLOTS = 8192;      // 128 KiB of (key, count-1) slots
+constexpr int SMEM_COUNT_THREADS = 512;    // phase B primary variant: table in shared memory, 2 CTAs/SM
+constexpr int SMEM_TABLE_SLOTS = 8192;      // 64 KiB of u64 keys + 32 KiB of u32 (count-1)
 
 // A run: partition-indexed keys (every key counts 1) or (key, count) pairs.  Partition p of the run is
 // entries [seg_start[p], seg_start[p] + seg_len[p]).

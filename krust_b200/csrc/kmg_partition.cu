@@ -378,14 +378,16 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
 // ---------------------------------------------------------------------------------------------------
 // phase B, primary variant: the partition's table lives in SHARED memory.  A probe step then costs tens
 // of cycles instead of an L2 round trip, which is what gated the L2-scratch variant above (its CTA-wide
-// time per partition was set by the longest probe chain).  One 1024-thread CTA per SM, 8192 x 16-byte
-// slots (128 KiB); a partition of <= 4096 entries is upserted in a single round of 4 keys per thread.
-// Output is compacted per warp (ballot + popc) so that a warp writes one contiguous run.
-// If a partition ever holds more distinct keys than the table (cannot happen for hash-uniform partitions
-// of the planned size) error_flag is raised and the host re-runs phase B with the L2-scratch variant.
+// time per partition was set by the longest probe chain).  Layout: SoA, 8192 x u64 keys + 8192 x u32
+// (occurrences - 1) = 96 KiB, so TWO 512-thread CTAs fit per SM and one CTA's latency bubbles (metadata,
+// key loads, output reservation) overlap with the other's work.  Output is compacted per warp (ballot +
+// popc) so that a warp writes one contiguous run.
+// If a partition holds more distinct keys than the table, or a count does not fit 32 bits, error_flag is
+// raised and the host re-runs phase B with the L2-scratch variant (u64 counts, larger tables).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SMEM_COUNT_THREADS, 1) count_partitions_smem_kernel(CountParams P) {
-  extern __shared__ __align__(16) unsigned long long stab[];  // SMEM_TABLE_SLOTS x (key, count-1)
+__global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_kernel(CountParams P) {
+  extern __shared__ __align__(16) unsigned long long skeys[];  // SMEM_TABLE_SLOTS keys, then SMEM_TABLE_SLOTS u32 counts
+  uint32_t *scnt = reinterpret_cast<uint32_t *>(skeys + SMEM_TABLE_SLOTS);
   __shared__ uint64_t seg_begin[CONS_MAX_RUNS];
   __shared__ uint64_t seg_prefix[CONS_MAX_RUNS + 1];
   __shared__ uint32_t s_work, s_warp[SMEM_COUNT_THREADS / 32 + 1];
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 1) count_partitions_smem_k
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t SLOTS = SMEM_TABLE_SLOTS;
   constexpr int NW = SMEM_COUNT_THREADS / 32;
-  for (uint32_t i = tid; i < SLOTS; i += SMEM_COUNT_THREADS) { stab[2 * i] = EMPTY_KEY; stab[2 * i + 1] = 0; }
+  for (uint32_t i = tid; i < SLOTS; i += SMEM_COUNT_THREADS) { skeys[i] = EMPTY_KEY; scnt[i] = 0; }
   uint32_t next_work = 0;
   if (tid == 0) next_work = atomicAdd(P.next, 1u);
   __syncthreads();
@@ -463,21 +465,26 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 1) count_partitions_smem_k
       uint32_t sl[G];
       unsigned long long cur[G];
 #pragma unroll
-      for (int j = 0; j < G; ++j) { sl[j] = (uint32_t)mix64(key[j]) & mask; cur[j] = w[j] ? stab[2 * sl[j]] : 0ull; }  // G probes in flight
+      for (int j = 0; j < G; ++j) { sl[j] = (uint32_t)mix64(key[j]) & mask; cur[j] = w[j] ? skeys[sl[j]] : 0ull; }  // G probes in flight
 #pragma unroll
-      for (int j = 0; j < G; ++j) if (w[j] && cur[j] == EMPTY_KEY) cur[j] = atomicCAS(&stab[2 * sl[j]], EMPTY_KEY, key[j]);
+      for (int j = 0; j < G; ++j) if (w[j] && cur[j] == EMPTY_KEY) cur[j] = atomicCAS(&skeys[sl[j]], EMPTY_KEY, key[j]);
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         if (!w[j]) continue;
+        if (w[j] > 0xffffffffull) { atomicExch(P.error_flag, 1u); continue; }  // needs the u64 variant
         unsigned long long c2 = cur[j];
         uint32_t s2 = sl[j];
         for (uint32_t tries = 0;; ++tries) {  // linear probing in shared memory: a step is tens of cycles
-          if (c2 == EMPTY_KEY) { ++new_keys; if (w[j] > 1) atomicAdd(&stab[2 * s2 + 1], (unsigned long long)(w[j] - 1)); break; }
-          if (c2 == key[j]) { atomicAdd(&stab[2 * s2 + 1], (unsigned long long)w[j]); break; }
+          if (c2 == EMPTY_KEY || c2 == key[j]) {
+            const uint32_t add = (uint32_t)w[j] - (c2 == EMPTY_KEY ? 1u : 0u);  // slots store occurrences - 1
+            new_keys += c2 == EMPTY_KEY;
+            if (add) { const uint32_t old = atomicAdd(&scnt[s2], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
+            break;
+          }
           if (tries > mask) { atomicExch(P.error_flag, 1u); break; }
           s2 = (s2 + 1) & mask;
-          c2 = stab[2 * s2];
-          if (c2 == EMPTY_KEY) c2 = atomicCAS(&stab[2 * s2], EMPTY_KEY, key[j]);
+          c2 = skeys[s2];
+          if (c2 == EMPTY_KEY) c2 = atomicCAS(&skeys[s2], EMPTY_KEY, key[j]);
         }
       }
     }
@@ -488,31 +495,30 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 1) count_partitions_smem_k
     // ---- compact: warp w owns the contiguous slot range [w*chunk, (w+1)*chunk); its occupied slots go out as one run
     const uint32_t chunk = (mask + 1) / NW > 32 ? (mask + 1) / NW : 32;
     const uint32_t lo = warp * chunk, hi = lo + chunk <= mask + 1 ? lo + chunk : (lo < mask + 1 ? mask + 1 : lo);
-    uint32_t wcount = 0;
-    for (uint32_t i = lo + lane; i < hi; i += 32) wcount += __popc(__ballot_sync(0xffffffffu, stab[2 * i] != EMPTY_KEY));
-    // (the ballot is warp-uniform; every lane now holds the warp's total)
-    if (tid == 0) {
+    if (tid == 0) {  // reserve the partition's output range; the atomic's latency overlaps the count pass below
       uint32_t d = 0;
       for (int w2 = 0; w2 < NW; ++w2) d += s_warp[w2];
       const unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);
       P.out_seg_start[p] = b; P.out_seg_len[p] = d;
       s_base = b;
     }
-    __syncthreads();
+    uint32_t wcount = 0;
+    for (uint32_t i = lo + lane; i < hi; i += 32) wcount += __popc(__ballot_sync(0xffffffffu, skeys[i] != EMPTY_KEY));
+    __syncthreads();  // s_warp (new keys) consumed by thread 0, s_base published
     if (lane == 0) s_warp[warp] = wcount;
     __syncthreads();
     uint32_t woff = 0;
     for (int w2 = 0; w2 < warp; ++w2) woff += s_warp[w2];
     uint64_t o = s_base + woff;
     for (uint32_t i = lo + lane; i < hi; i += 32) {
-      const unsigned long long k = stab[2 * i], cnt = stab[2 * i + 1];
+      const unsigned long long k = skeys[i];
       const bool occ = k != EMPTY_KEY;
       const uint32_t m = __ballot_sync(0xffffffffu, occ);
       if (occ) {
         const uint64_t dst = o + __popc(m & ((1u << lane) - 1u));
         __stcs(P.out_keys + dst, (uint64_t)k);
-        __stcs(P.out_counts + dst, (uint64_t)cnt + 1);  // slots store occurrences - 1
-        stab[2 * i] = EMPTY_KEY; stab[2 * i + 1] = 0;
+        __stcs(P.out_counts + dst, (uint64_t)scnt[i] + 1);  // slots store occurrences - 1
+        skeys[i] = EMPTY_KEY; scnt[i] = 0;
       }
       o += __popc(m);
     }
@@ -522,11 +528,11 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 1) count_partitions_smem_k
 
 cudaError_t launch_count_partitions_smem(const CountParams &P, cudaStream_t s) {
   if (P.n_parts == 0) return cudaSuccess;
-  const size_t smem = (size_t)SMEM_TABLE_SLOTS * 16;
+  const size_t smem = (size_t)SMEM_TABLE_SLOTS * 12;
   cudaError_t e = cudaFuncSetAttribute(count_partitions_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  const unsigned grid = (unsigned)std::min<uint64_t>(P.n_parts, (uint64_t)num_sms());
+  const unsigned grid = (unsigned)std::min<uint64_t>(P.n_parts, (uint64_t)num_sms() * 2);
   count_partitions_smem_kernel<<<grid, SMEM_COUNT_THREADS, smem, s>>>(P);
   return cudaGetLastError();
 }

@@ -355,3 +355,28 @@ def test_full_size_properties_100mbp(k, flags):
         c.finalize()
         keys3, counts3 = c.export(1, True)
     assert (keys3 == keys).all() and (counts3 == counts).all()
+
+
+def test_partitioned_fallbacks_large_weights_and_overfull_partitions():
+    """Phase B's shared-memory tables hold 8192 distinct keys and 32-bit counts; anything beyond must take the
+    L2-scratch fallback (u64 counts, growing tables) and still be exact."""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(99)
+    k = 21
+    keys = rng.integers(0, 4**k, size=200_000, dtype=np.uint64)
+    keys[:1000] = keys[0]  # one hot key
+    weights = rng.integers(1, 5, size=len(keys), dtype=np.uint64)
+    weights[:10] = np.uint64(2**33 + 7)  # does not fit 32 bits
+    uk, inv = np.unique(keys, return_inverse=True)
+    uc = np.zeros(len(uk), dtype=np.uint64)
+    np.add.at(uc, inv, weights)
+    tk = torch.from_numpy(keys.view(np.int64)).to(dev)
+    tw = torch.from_numpy(weights.view(np.int64)).to(dev)
+    torch.cuda.synchronize()
+    for pl in (2, 6, 12):  # 4 partitions of 50 K keys overflow a shared-memory table; 4096 partitions do not
+        with kb.GpuKmerCounter(k, flags=PART, parts_log2=pl) as c:
+            c.insert_keys_device(tk.data_ptr(), len(keys), tw.data_ptr())
+            s = c.finalize()
+            assert_same(c.export(1, True), (uk, uc))
+            assert s["n_windows"] == int(uc.sum()) and s["max_count"] == int(uc.max())
