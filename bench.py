@@ -157,6 +157,9 @@ def run_reference(args, rank: int):
 
 def main():
     args = parse_args()
+    if os.environ.get("KMG_BENCH_DEBUG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["KMG_BENCH_DEBUG"]), repeat=True, file=sys.stderr)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

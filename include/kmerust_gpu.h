@@ -67,7 +67,8 @@ typedef struct kmg_config {
   uint8_t reserved[5];
   uint64_t expected_distinct; /* capacity hint (distinct canonical k-mers); 0 = start small and grow */
   uint64_t batch_bases;       /* capacity of each pinned staging buffer in bases; 0 = default */
-  void *stream;               /* cudaStream_t to run on; NULL = library-owned stream */
+  void *stream;               /* cudaStream_t to run on; NULL = library-owned stream (pass cudaStreamLegacy, 0x1, to
+                                 share the legacy default stream with e.g. a torch process) */
 } kmg_config;
 
 typedef struct kmg_ctx kmg_ctx;

@@ -53,8 +53,12 @@ class GpuShardEngine:
         self.device = device
         torch.cuda.set_device(device)
         self.stream = torch.cuda.current_stream(device)
+        # The engine must run on the SAME stream torch orders its NCCL work against.  torch's default "current
+        # stream" is the legacy default stream, whose handle is 0 -- which the C ABI reads as "use a private
+        # stream" -- so it is passed as cudaStreamLegacy (0x1) instead.
+        handle = self.stream.cuda_stream or 1
         self.counter = GpuKmerCounter(k, min_quality=min_quality, expected_distinct=expected_distinct, flags=flags,
-                                      device=device.index, stream=self.stream.cuda_stream)
+                                      device=device.index, stream=handle)
         self.k = k
 
     def count_local(self, seq: torch.Tensor, offsets: Optional[torch.Tensor] = None, qual: Optional[torch.Tensor] = None):
