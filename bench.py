@@ -28,7 +28,6 @@ METRIC = "canonical k-mers counted/sec"
 UNIT = "kmers/s"
 SEED = 44                       # G3100
 B_ALG_HASH_NEW = 0.375 + 32.0   # algorithmic bytes per counted k-mer, every key new
-B_ALG_INSERT = 8.0 + 32.0       # receive side of the exchange: read the 8-byte key + slot touch
 
 
 def parse_args():
@@ -210,32 +209,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    insert_ms = []
-
     def step_device():
         engine.reset()
-        if world == 1:
-            sharded.count(d_seq, off_arg)
-        else:
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            keys, send_counts = engine.extract(d_seq, world, off_arg)
-            send_t = torch.as_tensor(send_counts.astype(np.int64), device=dev)
-            recv_t = torch.empty_like(send_t)
-            dist.all_to_all_single(recv_t, send_t)
-            recv_counts = recv_t.cpu().tolist()
-            recv = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=dev)
-            dist.all_to_all_single(recv, keys, output_split_sizes=recv_counts, input_split_sizes=[int(x) for x in send_counts.tolist()])
-            e0.record()
-            engine.insert(recv)
-            e1.record()
-            insert_ms.append((e0, e1, recv.numel()))
-            del keys, recv
+        sharded.count(d_seq, off_arg, expected_keys_per_rank=exp_windows // world + 1024)
         engine.finalize(False)
 
     # ---- device-resident timing: W warm-up, then exactly K steps between barriers, CUDA events, max over ranks
     for _ in range(args.warmup):
         step_device()
-    insert_ms.clear()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -260,31 +241,25 @@ def main():
     # ---- roofline of the dominant kernel, timed live with CUDA events on its launching stream
     peak, peak_src = peaks()
     pipeline = None
-    if world == 1 and local["path"] == 2:
-        # partitioned pipeline: phase A (A1 scan + coarse scatter, A2 refine) and phase B (count_partitions_kernel); reset()
-        # clears the timers, so these are the last step's kernels.  Algorithmic bytes per k-mer: A1 = 0.375 in + 8 out,
+    gpu_windows = exp_windows / world   # per-GPU share (strong scaling)
+    if local["path"] == 2:
+        # partitioned pipeline: phase A (A1 scan + coarse scatter, A2 refine) and phase B (count_partitions kernel); reset()
+        # clears the timers, so these are the last step's kernels on rank 0.  Algorithmic bytes per k-mer: A1 = 0.375 in + 8 out,
         # A2 = 8 in + 8 out, B = 8 in + 16 out; design-independent figure for the whole job: 32.375.
         a_ms, b_ms = local["scan_ns"] / 1e6, local["consolidate_ns"] / 1e6
-        pipeline = {"phase_a_ms": a_ms, "phase_b_ms": b_ms, "phase_a_gbs": exp_windows * 24.375 / (a_ms * 1e-3) / 1e9 if a_ms else 0.0,
-                    "phase_b_gbs": exp_windows * 24.0 / (b_ms * 1e-3) / 1e9 if b_ms else 0.0,
-                    "whole_gbs": exp_windows * B_ALG_HASH_NEW / ((a_ms + b_ms) * 1e-3) / 1e9 if a_ms + b_ms else 0.0}
+        pipeline = {"phase_a_ms": a_ms, "phase_b_ms": b_ms, "phase_a_gbs": gpu_windows * 24.375 / (a_ms * 1e-3) / 1e9 if a_ms else 0.0,
+                    "phase_b_gbs": gpu_windows * 24.0 / (b_ms * 1e-3) / 1e9 if b_ms else 0.0,
+                    "whole_gbs": gpu_windows * B_ALG_HASH_NEW / ((a_ms + b_ms) * 1e-3) / 1e9 if a_ms + b_ms else 0.0}
         if b_ms >= a_ms:
-            kern_ms, per_unit, kern_name = b_ms, 24.0, "count_partitions_kernel (phase B: one CTA per hash partition, upsert into an L2-resident scratch table, compact)"
+            kern_ms, per_unit, kern_name = b_ms, 24.0, "count_partitions_smem_kernel (phase B: one CTA per hash partition, upsert into a shared-memory table, compact)"
         else:
             kern_ms, per_unit, kern_name = a_ms, 24.375, "phase A kernels (partition_count/scatter over the scan + refine count/scatter: two-level hash partitioning)"
-        alg_bytes = exp_windows * per_unit
-    elif world == 1:
-        kern_ms = local["kernel_ns"] / 1e6          # scan_count_kernel<HASH> of the last step (reset() clears the timer)
-        alg_bytes = exp_windows * B_ALG_HASH_NEW
-        kern_name = "scan_count_kernel<MODE_HASH> (tile scan + open-addressing upsert)"
-        per_unit = B_ALG_HASH_NEW
+        alg_bytes = gpu_windows * per_unit
     else:
-        torch.cuda.synchronize(dev)
-        per = [(e0.elapsed_time(e1), n) for e0, e1, n in insert_ms]
-        kern_ms = sum(p[0] for p in per) / max(1, len(per))
-        alg_bytes = (sum(p[1] for p in per) / max(1, len(per))) * B_ALG_INSERT
-        kern_name = "insert_keys_kernel (upsert of exchanged keys into the local shard)"
-        per_unit = B_ALG_INSERT
+        kern_ms = local["kernel_ns"] / 1e6          # scan_count_kernel of the last step (reset() clears the timer)
+        alg_bytes = gpu_windows * B_ALG_HASH_NEW
+        kern_name = "scan_count_kernel (tile scan + upsert into one HBM-resident table / direct-indexed array)"
+        per_unit = B_ALG_HASH_NEW
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel": kern_name, "kernel_ms": kern_ms, "alg_bytes_per_kmer": per_unit, "peak_source": peak_src,
@@ -306,7 +281,7 @@ def main():
                 engine.counter.count_batch(h_np, None, offsets_np)     # kmg_count_ascii: chunked H2D overlapped with the kernels
             else:
                 d_tmp = h_seq.to(dev, non_blocking=True)
-                sharded.count(d_tmp, off_arg)
+                sharded.count(d_tmp, off_arg, expected_keys_per_rank=exp_windows // world + 1024)
             engine.finalize(False)
             vals, freqs = sharded.histogram(1)                          # D2H of the result
             d2h_bytes = (vals.nbytes + freqs.nbytes) + 65536 * 8

@@ -146,6 +146,14 @@ kmg_status kmg_extract_keys_device(kmg_ctx *ctx, const uint8_t *d_seq, const uin
                                    uint32_t n_shards, uint64_t *d_keys_out, uint64_t cap,
                                    uint64_t *shard_counts_out);
 uint32_t kmg_owner_of(uint64_t canonical_key, uint32_t n_shards);
+/* Multi-GPU fast path.  kmg_partition_plan puts the context on the partitioned pipeline (sized for
+ * expected_keys) and reports its partition plan: n_coarse coarse hash bins, each split into n_sub sub-bins.
+ * A sender buckets its keys with kmg_extract_keys_device(n_shards = world * n_coarse): bins
+ * [r*n_coarse, (r+1)*n_coarse) belong to rank r, so one all-to-all moves contiguous ranges.  The owner
+ * then hands each received block to kmg_adopt_coarse_device (keys already grouped by ITS n_coarse bins,
+ * bin_counts on the HOST), which only has to refine and count them -- no re-partitioning. */
+kmg_status kmg_partition_plan(kmg_ctx *ctx, uint64_t expected_keys, uint32_t *n_coarse, uint32_t *n_sub);
+kmg_status kmg_adopt_coarse_device(kmg_ctx *ctx, const uint64_t *d_keys, const uint64_t *bin_counts, uint32_t n_bins, uint64_t n);
 
 /* Waits for all queued work; replaces into_hashmap()'s barrier role (src/run.rs:573-582). */
 kmg_status kmg_finalize(kmg_ctx *ctx, kmg_summary *summary);

@@ -49,6 +49,8 @@ SIGNATURES = {
     "kmg_insert_keys_device": (i32, [vp, vp, vp, u64]),
     "kmg_extract_keys_device": (i32, [vp, vp, vp, vp, u64, u64, u32, vp, u64, vp]),
     "kmg_owner_of": (u32, [u64, u32]),
+    "kmg_partition_plan": (i32, [vp, u64, C.POINTER(u32), C.POINTER(u32)]),
+    "kmg_adopt_coarse_device": (i32, [vp, vp, vp, u32, u64]),
     "kmg_finalize": (i32, [vp, C.POINTER(KmgSummary)]),
     "kmg_export_counts": (i32, [vp, u64, i32, vp, vp, u64, C.POINTER(u64)]),
     "kmg_export_counts_device": (i32, [vp, u64, i32, vp, vp, u64, C.POINTER(u64)]),

@@ -271,6 +271,15 @@ class GpuKmerCounter:
                                                n_shards, d_keys_out or None, cap, counts.ctypes.data), self._ctx)
         return counts
 
+    def partition_plan(self, expected_keys: int) -> Tuple[int, int]:
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        _check(self._L.kmg_partition_plan(self._ctx, int(expected_keys), C.byref(a), C.byref(b)), self._ctx)
+        return a.value, b.value
+
+    def adopt_coarse_device(self, d_keys: int, bin_counts: np.ndarray, n: int):
+        bin_counts = np.ascontiguousarray(bin_counts, dtype=np.uint64)
+        _check(self._L.kmg_adopt_coarse_device(self._ctx, d_keys or None, bin_counts.ctypes.data, len(bin_counts), int(n)), self._ctx)
+
     def synth_uniform_device(self, seed: int, first_base: int, n: int, d_out: int):
         _check(self._L.kmg_synth_uniform_device(self._ctx, seed, first_base, n, d_out), self._ctx)
 

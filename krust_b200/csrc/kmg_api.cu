@@ -344,14 +344,14 @@ kmg_status alloc_or_consolidate(kmg_ctx *c, void **p, size_t bytes, const char *
   return KMG_OK;
 }
 
-// A2: coarse-partitioned keys (+counts) -> fine-partitioned run.  Takes ownership of the coarse buffers.
-kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, const std::vector<uint64_t> &coarse_off) {
+// A2: coarse-partitioned keys (+counts) -> fine-partitioned run.  Takes ownership of the coarse buffers when `owns`.
+kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, const std::vector<uint64_t> &coarse_off, bool owns = true) {
   const uint32_t P1 = c->n_coarse, P = c->n_parts;
   const uint64_t n = coarse_off[P1];
   Run r;
   uint64_t *d_cstart = nullptr;
   uint32_t *d_tprefix = nullptr;
-  auto cleanup = [&]() { pool_free(c, d_ckeys); pool_free(c, d_ccounts); pool_free(c, d_cstart); pool_free(c, d_tprefix); };
+  auto cleanup = [&]() { if (owns) { pool_free(c, d_ckeys); pool_free(c, d_ccounts); } pool_free(c, d_cstart); pool_free(c, d_tprefix); };
   std::vector<uint32_t> tprefix(P1 + 1, 0);
   uint64_t tiles = 0;
   for (uint32_t p = 0; p < P1; ++p) { tprefix[p] = (uint32_t)tiles; tiles += (coarse_off[p + 1] - coarse_off[p] + REFINE_TILE - 1) / REFINE_TILE; }
@@ -937,6 +937,39 @@ KMG_EXPORT kmg_status kmg_insert_keys_device(kmg_ctx *c, const uint64_t *d_keys,
     done += granted;
   }
   return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_partition_plan(kmg_ctx *c, uint64_t expected_keys, uint32_t *n_coarse, uint32_t *n_sub) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  if (c->mode == kmg_ctx::MODE_UNDECIDED) {
+    if (c->use_dense) return fail(c, KMG_ERR_STATE, "context uses the direct-indexed path; create it with KMG_FLAG_FORCE_PARTITIONED");
+    c->cfg.flags |= KMG_FLAG_FORCE_PARTITIONED;
+    c->cfg.flags &= ~(uint32_t)KMG_FLAG_FORCE_HASH;
+    kmg_status s = decide_mode(c, expected_keys);
+    if (s != KMG_OK) return s;
+  }
+  if (c->mode != kmg_ctx::MODE_PARTITIONED) return fail(c, KMG_ERR_STATE, "context is not on the partitioned path");
+  if (n_coarse) *n_coarse = c->n_coarse;
+  if (n_sub) *n_sub = c->n_sub;
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_adopt_coarse_device(kmg_ctx *c, const uint64_t *d_keys, const uint64_t *bin_counts, uint32_t n_bins, uint64_t n) {
+  if (!c || !bin_counts) return KMG_ERR_INVALID_ARG;
+  if (c->mode != kmg_ctx::MODE_PARTITIONED) return fail(c, KMG_ERR_STATE, "call kmg_partition_plan first");
+  if (n_bins != c->n_coarse) return fail(c, KMG_ERR_INVALID_ARG, "n_bins must equal the context's coarse partition count");
+  if (n >= (1ull << 32)) return fail(c, KMG_ERR_INVALID_ARG, "at most 2^32-1 keys per call");
+  std::vector<uint64_t> off(n_bins + 1, 0);
+  for (uint32_t b = 0; b < n_bins; ++b) off[b + 1] = off[b] + bin_counts[b];
+  if (off[n_bins] != n) return fail(c, KMG_ERR_INVALID_ARG, "bin_counts do not add up to n");
+  if (n == 0) return KMG_OK;
+  if (!d_keys) return fail(c, KMG_ERR_INVALID_ARG, "d_keys is NULL");
+  CU(c, cudaSetDevice(c->device));
+  const size_t tmr = timer_begin(c, 0);
+  kmg_status s = refine_to_run(c, const_cast<uint64_t *>(d_keys), nullptr, off, /*owns=*/false);  // synchronises before returning
+  timer_end(c, tmr);
+  return s;
 }
 
 KMG_EXPORT kmg_status kmg_extract_keys_device(kmg_ctx *c, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_offsets,

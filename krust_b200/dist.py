@@ -57,6 +57,9 @@ class GpuShardEngine:
         # stream" is the legacy default stream, whose handle is 0 -- which the C ABI reads as "use a private
         # stream" -- so it is passed as cudaStreamLegacy (0x1) instead.
         handle = self.stream.cuda_stream or 1
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            from ._lib import KMG_FLAG_FORCE_PARTITIONED
+            flags |= KMG_FLAG_FORCE_PARTITIONED  # the exchange moves hash-partitioned keys, whatever k is
         self.counter = GpuKmerCounter(k, min_quality=min_quality, expected_distinct=expected_distinct, flags=flags,
                                       device=device.index, stream=handle)
         self.k = k
@@ -80,6 +83,15 @@ class GpuShardEngine:
     def insert(self, keys: torch.Tensor, counts: Optional[torch.Tensor] = None):
         if keys.numel():
             self.counter.insert_keys_device(keys.data_ptr(), keys.numel(), counts.data_ptr() if counts is not None else 0)
+
+    def plan(self, expected_keys: int) -> int:
+        """Put the engine on the partitioned pipeline; returns its number of coarse hash bins."""
+        return self.counter.partition_plan(expected_keys)[0]
+
+    def adopt(self, keys: torch.Tensor, bin_counts: np.ndarray):
+        """Take a block of keys that is already grouped by this engine's coarse bins (counts on the host)."""
+        if keys.numel():
+            self.counter.adopt_coarse_device(keys.data_ptr(), bin_counts, keys.numel())
 
     def finalize(self, want_summary: bool = True):
         return self.counter.finalize(want_summary)
@@ -107,24 +119,43 @@ class ShardedKmerCounter:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.sent_keys = 0
         self.recv_keys = 0
+        self._p1 = None
 
-    def count(self, seq, offsets=None, qual=None):
-        """`seq` is THIS rank's slice (see slice_for_rank); offsets/qual are relative to it."""
+    def count(self, seq, offsets=None, qual=None, expected_keys_per_rank: int = 0):
+        """`seq` is THIS rank's slice (see slice_for_rank); offsets/qual are relative to it.
+
+        Every rank buckets its keys straight into world x P1 global coarse hash bins (P1 = the engines' common
+        coarse-partition count); bins [r*P1, (r+1)*P1) belong to rank r, so ONE all-to-all moves contiguous
+        ranges and the owner adopts each received block as already coarse-partitioned input."""
         if self.world == 1:
             self.engine.count_local(seq, offsets, qual)
             return
-        keys, send_counts = self.engine.extract(seq, self.world, offsets, qual)
+        if self._p1 is None:
+            # all ranks must agree on P1: take the plan of the rank expecting the most keys
+            mine = self.engine.plan(max(int(expected_keys_per_rank), int(seq.numel()), 1))
+            dev0 = getattr(self.engine, "device", torch.device("cpu"))
+            t = torch.tensor([mine], dtype=torch.int64, device=dev0)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            self._p1 = int(t.item())
+            if self._p1 != mine:
+                raise RuntimeError(f"ranks disagree on the partition plan ({mine} vs {self._p1}); pass the same expected_keys_per_rank")
+        p1, world = self._p1, self.world
+        keys, bin_counts = self.engine.extract(seq, world * p1, offsets, qual)
         dev = keys.device
-        send_t = torch.as_tensor(send_counts.astype(np.int64), device=dev)
-        recv_t = torch.empty_like(send_t)
-        dist.all_to_all_single(recv_t, send_t, group=self.group)  # bucket sizes
-        recv_counts = recv_t.cpu().tolist()
-        send_list = [int(x) for x in send_counts.tolist()]
-        recv = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=dev)
-        dist.all_to_all_single(recv, keys, output_split_sizes=recv_counts, input_split_sizes=send_list, group=self.group)
-        self.sent_keys += int(sum(send_list)) - send_list[self.rank]
-        self.recv_keys += int(sum(recv_counts)) - recv_counts[self.rank]
-        self.engine.insert(recv)
+        send_m = torch.as_tensor(bin_counts.astype(np.int64), device=dev)       # [world * p1], owner-major
+        recv_m = torch.empty_like(send_m)
+        dist.all_to_all_single(recv_m, send_m, group=self.group)                # row s = what source s holds for my bins
+        recv_m = recv_m.cpu().numpy().reshape(world, p1)
+        send_split = bin_counts.reshape(world, p1).sum(axis=1).astype(np.int64).tolist()
+        recv_split = recv_m.sum(axis=1).astype(np.int64).tolist()
+        recv = torch.empty(int(sum(recv_split)), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv, keys, output_split_sizes=recv_split, input_split_sizes=send_split, group=self.group)
+        self.sent_keys += int(sum(send_split)) - send_split[self.rank]
+        self.recv_keys += int(sum(recv_split)) - recv_split[self.rank]
+        o = 0
+        for src in range(world):
+            self.engine.adopt(recv[o:o + recv_split[src]], recv_m[src].astype(np.uint64))
+            o += recv_split[src]
 
     def finalize(self) -> dict:
         """Global summary: sums over shards (shards are disjoint), max of max_count."""

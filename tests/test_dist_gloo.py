@@ -63,6 +63,18 @@ class OracleShardEngine:
         order = np.argsort(owner, kind="stable")
         return torch.from_numpy(flat[order].view(np.int64)), np.bincount(owner, minlength=n_shards).astype(np.uint64)
 
+    def plan(self, expected_keys):
+        return 5  # any common coarse-bin count works for the stand-in
+
+    def adopt(self, keys, bin_counts):
+        k = keys.numpy().view(np.uint64)
+        assert int(np.asarray(bin_counts).sum()) == len(k)
+        # the block must really be grouped by this rank's coarse bins, in order
+        world, rank = dist.get_world_size(), dist.get_rank()
+        bins = np_owner_of(k, world * len(bin_counts)) - rank * len(bin_counts)
+        assert (np.diff(bins) >= 0).all() and (np.bincount(bins, minlength=len(bin_counts)) == np.asarray(bin_counts)).all()
+        self._add(k, np.ones(len(k), dtype=np.uint64))
+
     def insert(self, keys, counts=None):
         k = keys.numpy().view(np.uint64)
         self._add(k, np.ones(len(k), dtype=np.uint64) if counts is None else counts.numpy().view(np.uint64))
