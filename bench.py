@@ -260,8 +260,18 @@ def main():
         alg_bytes = gpu_windows * B_ALG_HASH_NEW
         kern_name = "scan_count_kernel (tile scan + upsert into one HBM-resident table / direct-indexed array)"
         per_unit = B_ALG_HASH_NEW
+    # DRAM traffic of the dominant kernel: bytes per k-mer from the committed `ncu --set full` capture (taken on a 5e8-base
+    # slice of the same workload: the full job would make ncu save/restore ~100 GB per pass), scaled to this launch
+    traffic = None
+    try:
+        tpk = json.load(open(os.path.join(ROOT, "profiles", "traffic_per_kmer.json")))
+        for name, v in tpk.items():
+            if name in kern_name:
+                traffic = v * gpu_windows
+    except Exception:
+        traffic = None
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": kern_name, "kernel_ms": kern_ms, "alg_bytes_per_kmer": per_unit, "peak_source": peak_src,
                 "pipeline": pipeline}
 

@@ -24,7 +24,7 @@ thread_local std::string g_create_error;
 constexpr double LOAD_TARGET = 0.60;  // sizing goal when memory allows
 constexpr double LOAD_SOFT = 0.70;    // grow after a batch if exceeded and memory allows
 constexpr double LOAD_HARD = 0.90;    // never start a batch that could exceed this
-constexpr uint64_t DEFAULT_BATCH_BASES = 256ull << 20;
+constexpr uint64_t DEFAULT_BATCH_BASES = 1ull << 30;  // per staging slot; every batch becomes one run of the partitioned pipeline
 constexpr uint64_t MIN_TABLE_SLOTS = 1ull << 16;
 
 struct Staging {
@@ -78,6 +78,7 @@ struct kmg_ctx {
   uint64_t batch_bases = DEFAULT_BATCH_BASES;
   Staging st[2];
   bool staging_ready = false, packed_feed_ready = false;
+  uint64_t staging_cap = 0;
   uint32_t next_slot = 0;
 
   // partitioned pipeline (v2)
@@ -598,19 +599,35 @@ kmg_status count_device_chunk(kmg_ctx *c, const uint8_t *d_seq, const uint8_t *d
   return scan_packed(c, n_words_total, has_start);
 }
 
-kmg_status ensure_staging(kmg_ctx *c, bool need_pinned) {
-  const uint64_t cap = c->batch_bases + 64;
+kmg_status ensure_staging(kmg_ctx *c, bool need_pinned, uint64_t need_bytes) {
+  // staging slots are sized for the largest chunk seen so far (at most batch_bases), not for batch_bases up front
+  const uint64_t want = std::min<uint64_t>(c->batch_bases, std::max<uint64_t>(need_bytes, 1u << 20)) + 64;
+  if (want > c->staging_cap) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 2; ++i) {
+      Staging &s = c->st[i];
+      cudaFree(s.d_seq); cudaFree(s.d_qual); s.d_seq = s.d_qual = nullptr;
+      if (s.h_seq) cudaFreeHost(s.h_seq);
+      if (s.h_qual) cudaFreeHost(s.h_qual);
+      s.h_seq = s.h_qual = nullptr;
+      s.h2d_pending = s.compute_pending = false;
+    }
+    c->staging_cap = want;
+  }
   for (int i = 0; i < 2; ++i) {
     Staging &s = c->st[i];
     if (!s.d_seq) {
-      CU(c, cudaMalloc(&s.d_seq, cap));
-      CU(c, cudaMalloc(&s.d_qual, cap));
+      CU(c, cudaMalloc(&s.d_seq, c->staging_cap));
+      CU(c, cudaMalloc(&s.d_qual, c->staging_cap));
+    }
+    if (!s.h2d_done) {
       CU(c, cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
       CU(c, cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
     }
     if (need_pinned && !s.h_seq) {
-      CU(c, cudaHostAlloc(&s.h_seq, cap, cudaHostAllocDefault));
-      CU(c, cudaHostAlloc(&s.h_qual, cap, cudaHostAllocDefault));
+      CU(c, cudaHostAlloc(&s.h_seq, c->staging_cap, cudaHostAllocDefault));
+      CU(c, cudaHostAlloc(&s.h_qual, c->staging_cap, cudaHostAllocDefault));
     }
   }
   c->staging_ready = true;
@@ -825,7 +842,7 @@ KMG_EXPORT kmg_status kmg_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint
   const uint64_t begin = offsets[0], end = offsets[n_records];
   const bool use_q = c->cfg.has_min_quality && qual != nullptr;
   const bool src_pinned = is_pinned_host(seq + begin) && (!use_q || is_pinned_host(qual + begin));
-  kmg_status s = ensure_staging(c, !src_pinned);
+  kmg_status s = ensure_staging(c, !src_pinned, end - begin);
   if (s != KMG_OK) return s;
   const uint64_t K1 = (uint64_t)c->k - 1;
   const uint64_t B = c->batch_bases;  // bytes per chunk including the k-1 overlap
