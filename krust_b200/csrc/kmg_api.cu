@@ -847,41 +847,55 @@ KMG_EXPORT kmg_status kmg_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint
   const uint64_t K1 = (uint64_t)c->k - 1;
   const uint64_t B = c->batch_bases;  // bytes per chunk including the k-1 overlap
   const uint64_t step = B - K1;
-  uint64_t r_lo = 0;
-  for (uint64_t pos = begin; pos < end; pos += step) {
-    const uint64_t len = std::min<uint64_t>(B, end - pos);
-    if (pos != begin && len <= K1) break;  // only the overlap is left: no new windows
-    // records with a start strictly inside (pos, pos+len)
-    while (r_lo < n_records && offsets[r_lo] <= pos) ++r_lo;
-    uint64_t r_hi = r_lo;
-    while (r_hi < n_records && offsets[r_hi] < pos + len) ++r_hi;
-    const uint64_t nrec = r_hi - r_lo;
-
-    Staging &st = c->st[c->next_slot];
-    c->next_slot ^= 1;
+  // chunk plan first, then a software pipeline: the H2D copy of chunk i+1 is queued BEFORE chunk i is processed
+  // (processing contains host syncs), so copies overlap the kernels of the previous chunk.
+  struct Chunk { uint64_t pos, len, r_lo, nrec; };
+  std::vector<Chunk> chunks;
+  {
+    uint64_t r_lo = 0;
+    for (uint64_t pos = begin; pos < end; pos += step) {
+      const uint64_t len = std::min<uint64_t>(B, end - pos);
+      if (pos != begin && len <= K1) break;  // only the overlap is left: no new windows
+      while (r_lo < n_records && offsets[r_lo] <= pos) ++r_lo;  // records with a start strictly inside (pos, pos+len)
+      uint64_t r_hi = r_lo;
+      while (r_hi < n_records && offsets[r_hi] < pos + len) ++r_hi;
+      chunks.push_back(Chunk{pos, len, r_lo, r_hi - r_lo});
+    }
+  }
+  auto stage_chunk = [&](const Chunk &ch, Staging &st) -> kmg_status {
     if (st.h2d_pending) { CU(c, cudaEventSynchronize(st.h2d_done)); st.h2d_pending = false; }
     if (st.compute_pending) { CU(c, cudaStreamWaitEvent(c->copy_stream, st.compute_done, 0)); }
-    if ((s = ensure_offsets(c, st, nrec)) != KMG_OK) return s;
-    const uint8_t *src_seq = seq + pos, *src_qual = use_q ? qual + pos : nullptr;
+    kmg_status es = ensure_offsets(c, st, ch.nrec);
+    if (es != KMG_OK) return es;
+    const uint8_t *src_seq = seq + ch.pos, *src_qual = use_q ? qual + ch.pos : nullptr;
     if (!src_pinned) {
-      memcpy(st.h_seq, src_seq, len); src_seq = st.h_seq;
-      if (use_q) { memcpy(st.h_qual, src_qual, len); src_qual = st.h_qual; }
+      memcpy(st.h_seq, src_seq, ch.len); src_seq = st.h_seq;
+      if (use_q) { memcpy(st.h_qual, src_qual, ch.len); src_qual = st.h_qual; }
     }
-    CU(c, cudaMemcpyAsync(st.d_seq, src_seq, len, cudaMemcpyHostToDevice, c->copy_stream));
-    if (use_q) CU(c, cudaMemcpyAsync(st.d_qual, src_qual, len, cudaMemcpyHostToDevice, c->copy_stream));
-    if (nrec) {
-      memcpy(st.h_off, offsets + r_lo, nrec * 8);
-      CU(c, cudaMemcpyAsync(st.d_off, st.h_off, nrec * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaMemcpyAsync(st.d_seq, src_seq, ch.len, cudaMemcpyHostToDevice, c->copy_stream));
+    if (use_q) CU(c, cudaMemcpyAsync(st.d_qual, src_qual, ch.len, cudaMemcpyHostToDevice, c->copy_stream));
+    if (ch.nrec) {
+      memcpy(st.h_off, offsets + ch.r_lo, ch.nrec * 8);
+      CU(c, cudaMemcpyAsync(st.d_off, st.h_off, ch.nrec * 8, cudaMemcpyHostToDevice, c->copy_stream));
     }
-    c->h2d_bytes += len * (use_q ? 2 : 1) + nrec * 8;
+    c->h2d_bytes += ch.len * (use_q ? 2 : 1) + ch.nrec * 8;
     CU(c, cudaEventRecord(st.h2d_done, c->copy_stream));
     st.h2d_pending = true;
+    return KMG_OK;
+  };
+  const uint32_t slot0 = c->next_slot;
+  if (!chunks.empty() && (s = stage_chunk(chunks[0], c->st[slot0])) != KMG_OK) return s;
+  for (size_t i = 0; i < chunks.size(); ++i) {
+    Staging &st = c->st[(slot0 + i) & 1];
+    if (i + 1 < chunks.size() && (s = stage_chunk(chunks[i + 1], c->st[(slot0 + i + 1) & 1])) != KMG_OK) return s;
+    const Chunk &ch = chunks[i];
     CU(c, cudaStreamWaitEvent(c->stream, st.h2d_done, 0));
-    s = count_device_chunk(c, st.d_seq, use_q ? st.d_qual : nullptr, nrec ? st.d_off : nullptr, nrec, pos, len);
+    s = count_device_chunk(c, st.d_seq, use_q ? st.d_qual : nullptr, ch.nrec ? st.d_off : nullptr, ch.nrec, ch.pos, ch.len);
     if (s != KMG_OK) return s;
     CU(c, cudaEventRecord(st.compute_done, c->stream));
     st.compute_pending = true;
   }
+  c->next_slot = (slot0 + (uint32_t)chunks.size()) & 1;
   c->n_records += n_records; c->n_bases += end - begin;
   return KMG_OK;
 }

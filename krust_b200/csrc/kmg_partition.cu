@@ -431,11 +431,14 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
     while ((1u << cap_log2) < SLOTS && (1ull << cap_log2) * 5 < n_p * 8) ++cap_log2;
     const uint32_t mask = (1u << cap_log2) - 1;
 
-    constexpr int G = 4;
+    // 8 keys per thread are loaded up front (one exposed global-load latency per 4096 entries instead of two),
+    // then upserted in two batches of 4 whose first probes are in flight together.
+    constexpr int G = 8, H = 4;
     uint32_t new_keys = 0;
 #pragma unroll 1
     for (uint64_t base = 0; base < n_p; base += (uint64_t)SMEM_COUNT_THREADS * G) {
-      uint64_t key[G], w[G];
+      uint64_t key[G];
+      uint32_t w[G];
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         const uint64_t idx = base + (uint64_t)j * SMEM_COUNT_THREADS + tid;
@@ -445,7 +448,10 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
           while (r + 1 < P.R && idx >= seg_prefix[r + 1]) ++r;
           const uint64_t src = seg_begin[r] + (idx - seg_prefix[r]);
           key[j] = __ldcs(P.runs[r].keys + src);
-          w[j] = P.runs[r].counts ? __ldcs(P.runs[r].counts + src) : 1ull;
+          uint64_t w64 = 1;
+          if (P.runs[r].counts) w64 = __ldcs(P.runs[r].counts + src);
+          if (w64 > 0xffffffffull) { atomicExch(P.error_flag, 1u); w64 = 0; }  // needs the u64 (L2-scratch) variant
+          w[j] = (uint32_t)w64;
         }
       }
       if (P.preagg) {  // warp run-length pre-aggregation (see count_partitions_kernel)
@@ -455,36 +461,40 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
           const uint64_t kp = __shfl_up_sync(0xffffffffu, kk, 1);
           const bool head = lane == 0 || kp != kk;
           const uint32_t heads = __ballot_sync(0xffffffffu, head);
-          if (__all_sync(0xffffffffu, w[j] <= 1ull)) {
+          if (__all_sync(0xffffffffu, w[j] <= 1u)) {
             const uint32_t above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
             const uint32_t end = above ? (uint32_t)__ffs(above) - 1u : 32u;
-            if (w[j]) w[j] = head ? (uint64_t)(end - lane) : 0ull;
+            if (w[j]) w[j] = head ? end - lane : 0u;
           }
         }
       }
-      uint32_t sl[G];
-      unsigned long long cur[G];
 #pragma unroll
-      for (int j = 0; j < G; ++j) { sl[j] = (uint32_t)mix64(key[j]) & mask; cur[j] = w[j] ? skeys[sl[j]] : 0ull; }  // G probes in flight
+      for (int h0 = 0; h0 < G; h0 += H) {
+        uint32_t sl[H];
+        unsigned long long cur[H];
 #pragma unroll
-      for (int j = 0; j < G; ++j) if (w[j] && cur[j] == EMPTY_KEY) cur[j] = atomicCAS(&skeys[sl[j]], EMPTY_KEY, key[j]);
+        for (int j = 0; j < H; ++j) { sl[j] = (uint32_t)mix64(key[h0 + j]) & mask; cur[j] = w[h0 + j] ? skeys[sl[j]] : 0ull; }  // H probes in flight
 #pragma unroll
-      for (int j = 0; j < G; ++j) {
-        if (!w[j]) continue;
-        if (w[j] > 0xffffffffull) { atomicExch(P.error_flag, 1u); continue; }  // needs the u64 variant
-        unsigned long long c2 = cur[j];
-        uint32_t s2 = sl[j];
-        for (uint32_t tries = 0;; ++tries) {  // linear probing in shared memory: a step is tens of cycles
-          if (c2 == EMPTY_KEY || c2 == key[j]) {
-            const uint32_t add = (uint32_t)w[j] - (c2 == EMPTY_KEY ? 1u : 0u);  // slots store occurrences - 1
-            new_keys += c2 == EMPTY_KEY;
-            if (add) { const uint32_t old = atomicAdd(&scnt[s2], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
-            break;
+        for (int j = 0; j < H; ++j) if (w[h0 + j] && cur[j] == EMPTY_KEY) cur[j] = atomicCAS(&skeys[sl[j]], EMPTY_KEY, key[h0 + j]);
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          const uint32_t wj = w[h0 + j];
+          if (!wj) continue;
+          const uint64_t kj = key[h0 + j];
+          unsigned long long c2 = cur[j];
+          uint32_t s2 = sl[j];
+          for (uint32_t tries = 0;; ++tries) {  // linear probing in shared memory: a step is tens of cycles
+            if (c2 == EMPTY_KEY || c2 == kj) {
+              const uint32_t add = wj - (c2 == EMPTY_KEY ? 1u : 0u);  // slots store occurrences - 1
+              new_keys += c2 == EMPTY_KEY;
+              if (add) { const uint32_t old = atomicAdd(&scnt[s2], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
+              break;
+            }
+            if (tries > mask) { atomicExch(P.error_flag, 1u); break; }
+            s2 = (s2 + 1) & mask;
+            c2 = skeys[s2];
+            if (c2 == EMPTY_KEY) c2 = atomicCAS(&skeys[s2], EMPTY_KEY, kj);
           }
-          if (tries > mask) { atomicExch(P.error_flag, 1u); break; }
-          s2 = (s2 + 1) & mask;
-          c2 = skeys[s2];
-          if (c2 == EMPTY_KEY) c2 = atomicCAS(&skeys[s2], EMPTY_KEY, key[j]);
         }
       }
     }
