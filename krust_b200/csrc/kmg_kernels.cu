@@ -332,24 +332,23 @@ struct PartCountEmit {
 };
 // Scatter emitter.  The G shared-memory atomics of a group are issued back to back, then the G base loads,
 // then the G stores: consuming each atomic's return immediately serialises a thread's 32 atomics on their
-// latency (45 % of the stall samples sat right behind the ATOMS in profiles/r1_summary.md).
+// latency (45 % of the stall samples sat right behind the ATOMS in profiles/r1_summary.md).  The cursors hold
+// absolute output indices, so the atomic's return value IS the destination: no second shared-memory lookup
+// (the scatter kernels are bound by the shared-memory pipe: every access costs ~2.5 wavefronts of bank conflicts).
 struct PartScatterEmit {
-  uint32_t *cursor;          // smem: running offset inside this tile's reservation
-  const uint32_t *tile_abs;  // smem: index in `out` where this tile's keys of partition p start
+  uint32_t *cursor;  // smem: ABSOLUTE next index in `out` for each partition (seeded with the tile's reservation)
   uint64_t *out;
   uint32_t n_parts;
   template <int G>
   __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
-    uint32_t p[G], o[G], base[G];
+    uint32_t p[G], o[G];
 #pragma unroll
     for (int j = 0; j < G; ++j) p[j] = part_of(key[j], n_parts);
 #pragma unroll
     for (int j = 0; j < G; ++j) { o[j] = 0; if ((okg >> j) & 1u) o[j] = atomicAdd(cursor + p[j], 1u); }
 #pragma unroll
-    for (int j = 0; j < G; ++j) base[j] = tile_abs[p[j]];
-#pragma unroll
     for (int j = 0; j < G; ++j)
-      if ((okg >> j) & 1u) __stcs(out + ((uint64_t)base[j] + o[j]), key[j]);
+      if ((okg >> j) & 1u) __stcs(out + o[j], key[j]);
   }
 };
 
@@ -415,7 +414,6 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 2) partition_scatter_kernel(S
   TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
   __shared__ __align__(8) uint64_t bars[2];
   uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw + 2 * sizeof(TileSmem));
-  uint32_t *tile_abs = hist + n_parts;
   const int tid = threadIdx.x;
   const bool has_start = in.start != nullptr;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
@@ -436,14 +434,13 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 2) partition_scatter_kernel(S
       for (int r = 0; r < TILE_WORDS / SCATTER_THREADS; ++r) scan_word<8>(ts, r * SCATTER_THREADS + tid, in.k, has_start, e);
     }
     __syncthreads();
-    for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) {
+    for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) {  // histogram -> absolute cursors
       const uint32_t c = hist[p];
-      tile_abs[p] = c ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)c)) : 0u;
-      hist[p] = 0;
+      hist[p] = c ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)c)) : 0u;
     }
     __syncthreads();
     {
-      PartScatterEmit e{hist, tile_abs, out, n_parts};
+      PartScatterEmit e{hist, out, n_parts};
 #pragma unroll 1
       for (int r = 0; r < TILE_WORDS / SCATTER_THREADS; ++r) scan_word<8>(ts, r * SCATTER_THREADS + tid, in.k, has_start, e);
     }
@@ -668,7 +665,7 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
                                   const unsigned long long *part_start, unsigned long long *part_cursor, uint64_t *out,
                                   unsigned long long *counters, cudaStream_t s) {
   if (in.n_tiles == 0) return cudaSuccess;
-  const size_t smem = 2 * sizeof(TileSmem) + 2 * (size_t)n_parts * sizeof(uint32_t);
+  const size_t smem = 2 * sizeof(TileSmem) + (size_t)n_parts * sizeof(uint32_t);
   const uint64_t max_ctas = (uint64_t)num_sms() * (smem > 100 * 1024 ? 1 : smem > 72 * 1024 ? 2 : SCAN_CTAS_PER_SM);
   cudaError_t e;
   if (scatter) {

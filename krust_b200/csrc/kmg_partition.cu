@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) keys_coarse_kernel(const uint64_t *__rest
                                                           const unsigned long long *coarse_start, unsigned long long *coarse_cursor,
                                                           uint64_t *out_keys, uint64_t *out_counts) {
   extern __shared__ uint32_t sm[];
-  uint32_t *hist = sm, *tile_abs = sm + n_coarse;
+  uint32_t *hist = sm;  // histogram, then ABSOLUTE output cursors (the atomic's return value is the destination)
   constexpr uint32_t TILE = 16384;
   for (uint32_t p = threadIdx.x; p < n_coarse; p += blockDim.x) hist[p] = 0;
   __syncthreads();
@@ -53,8 +53,7 @@ __global__ void __launch_bounds__(256) keys_coarse_kernel(const uint64_t *__rest
       __syncthreads();
       for (uint32_t p = threadIdx.x; p < n_coarse; p += blockDim.x) {
         const uint32_t c = hist[p];
-        tile_abs[p] = c ? (uint32_t)(coarse_start[p] + atomicAdd(coarse_cursor + p, (unsigned long long)c)) : 0u;
-        hist[p] = 0;
+        hist[p] = c ? (uint32_t)(coarse_start[p] + atomicAdd(coarse_cursor + p, (unsigned long long)c)) : 0u;
       }
       __syncthreads();
       for (uint32_t i0 = 0; i0 < m; i0 += U * 256) {
@@ -71,9 +70,8 @@ __global__ void __launch_bounds__(256) keys_coarse_kernel(const uint64_t *__rest
 #pragma unroll
         for (int j = 0; j < U; ++j)
           if (i0 + j * 256 + threadIdx.x < m) {
-            const uint64_t dst = (uint64_t)tile_abs[p[j]] + o[j];
-            out_keys[dst] = key[j];
-            if (out_counts) out_counts[dst] = cnt[j];
+            out_keys[o[j]] = key[j];
+            if (out_counts) out_counts[o[j]] = cnt[j];
           }
       }
       __syncthreads();
@@ -92,7 +90,7 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
                                unsigned long long *coarse_counts, const unsigned long long *coarse_start,
                                unsigned long long *coarse_cursor, uint64_t *out_keys, uint64_t *out_counts, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
-  const size_t smem = 2 * (size_t)n_coarse * sizeof(uint32_t);
+  const size_t smem = (size_t)n_coarse * sizeof(uint32_t);
   const uint64_t want = (n + 16383) / 16384, cap = (uint64_t)num_sms() * 2;
   const unsigned grid = (unsigned)std::min(want, cap);
   cudaError_t e;
@@ -116,7 +114,7 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
 template <bool SCATTER>
 __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) {
   extern __shared__ uint32_t sm[];
-  uint32_t *hist = sm, *tile_abs = sm + P.n_sub;
+  uint32_t *hist = sm;  // histogram, then ABSOLUTE output cursors
   __shared__ uint32_t s_c;
   for (uint32_t s = threadIdx.x; s < P.n_sub; s += REFINE_THREADS) hist[s] = 0;
   __syncthreads();
@@ -152,8 +150,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
     } else {
       for (uint32_t s = threadIdx.x; s < P.n_sub; s += REFINE_THREADS) {
         const uint32_t h = hist[s];
-        tile_abs[s] = h ? (uint32_t)(P.fine_start[f0 + s] + atomicAdd(P.fine_cursor + f0 + s, (unsigned long long)h)) : 0u;
-        hist[s] = 0;
+        hist[s] = h ? (uint32_t)(P.fine_start[f0 + s] + atomicAdd(P.fine_cursor + f0 + s, (unsigned long long)h)) : 0u;
       }
       __syncthreads();
       for (uint32_t i0 = 0; i0 < m; i0 += U * REFINE_THREADS) {  // second read of the tile comes from L2
@@ -170,9 +167,8 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
 #pragma unroll
         for (int j = 0; j < U; ++j)
           if (i0 + j * REFINE_THREADS + threadIdx.x < m) {
-            const uint64_t dst = (uint64_t)tile_abs[sb[j]] + o[j];
-            P.out_keys[dst] = key[j];
-            if (P.out_counts) P.out_counts[dst] = cnt[j];
+            P.out_keys[o[j]] = key[j];
+            if (P.out_counts) P.out_counts[o[j]] = cnt[j];
           }
       }
       __syncthreads();
@@ -184,7 +180,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
 
 cudaError_t launch_refine(const RefineParams &P, bool scatter, cudaStream_t s) {
   if (P.n_tiles == 0) return cudaSuccess;
-  const size_t smem = 2 * (size_t)P.n_sub * sizeof(uint32_t);
+  const size_t smem = (size_t)P.n_sub * sizeof(uint32_t);
   const unsigned grid = (unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms() * 2);
   cudaError_t e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
