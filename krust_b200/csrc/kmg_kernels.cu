@@ -123,7 +123,7 @@ __device__ __forceinline__ void issue_tile(const ScanInput &in, TileSmem *dst, u
 // Walk the 32 windows ending in word `i` of the staged tile, handing groups of G canonical keys to
 // the emitter.  fwd/rc are rolled one base at a time; canonical = min(fwd, rc) which equals the
 // reference's bytewise lexicographic choice (src/kmer.rs:348-365) because A<C<G<T in both orders.
-template <int G, class Emit>
+template <int G, class Emit, bool UNIFORM = false>
 __device__ __forceinline__ uint32_t scan_word(const TileSmem *ts, int i, int k, bool has_start, Emit &emit) {
   const uint64_t prev = ts->bases[LEAD_BASE_WORDS + i - 1];
   const uint64_t cur = ts->bases[LEAD_BASE_WORDS + i];
@@ -131,7 +131,7 @@ __device__ __forceinline__ uint32_t scan_word(const TileSmem *ts, int i, int k, 
   uint32_t sprev = 0, scur = 0;
   if (has_start) { sprev = ts->start[LEAD_MASK_WORDS + i - 1]; scur = ts->start[LEAD_MASK_WORDS + i]; }
   const uint32_t ok = window_ok_mask(vprev, vcur, sprev, scur, k, has_start);
-  if (ok == 0) return 0;
+  if (!UNIFORM && ok == 0) return 0;  // UNIFORM: every lane of the warp walks all groups (the emitter uses warp collectives)
   const uint64_t mask = kmer_mask(k);
   const int rc_shift = 2 * (k - 1);
   uint64_t fwd = prev & mask;
@@ -149,7 +149,7 @@ __device__ __forceinline__ uint32_t scan_word(const TileSmem *ts, int i, int k, 
       key[j] = fwd < rc ? fwd : rc;
       okg |= ((ok >> (31 - e)) & 1u) << j;
     }
-    if (okg) emit.template group<G>(key, okg);
+    if (UNIFORM || okg) emit.template group<G>(key, okg);
   }
   return __popc(ok);
 }
@@ -352,6 +352,33 @@ struct PartScatterEmit {
   }
 };
 
+// Warp-level multisplit emitter (the scheme radix sorts use): every warp owns a private cursor per partition, lanes
+// that hit the same partition find each other with __match_any_sync, the lowest of them advances the cursor by
+// the group size with a plain load/store, everybody takes base + (number of lower peers).  No returning shared
+// atomics: those execute lane-serially (~2 cycles per lane) and bounded the ATOMS-based scatter at ~8 cycles
+// per key per SM.  Must be called by all 32 lanes (scan_word<..., UNIFORM = true>).
+struct PartWarpScatterEmit {
+  uint32_t *wcur;  // smem: THIS warp's absolute next index in `out` per partition
+  uint64_t *out;
+  uint32_t n_parts;
+  template <int G>
+  __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const bool ok = (okg >> j) & 1u;
+      const uint32_t p = ok ? part_of(key[j], n_parts) : (0x80000000u | lane);  // invalid lanes match only themselves
+      const uint32_t peers = __match_any_sync(0xffffffffu, p);
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (ok && (int)lane == leader) { base = wcur[p]; wcur[p] = base + __popc(peers); }
+      base = __shfl_sync(0xffffffffu, base, leader);
+      __syncwarp();  // the leader's cursor update is visible to the next group's leaders
+      if (ok) __stcs(out + (base + __popc(peers & lt)), key[j]);
+    }
+  }
+};
+
 // Synchronously stage one tile (used at pass boundaries where there is nothing to overlap with).
 __device__ __forceinline__ void wait_stage(uint64_t *bars, int stage, uint32_t &phase0, uint32_t &phase1) {
   if (stage == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
@@ -446,6 +473,61 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 2) partition_scatter_kernel(S
     }
     __syncthreads();
     for (uint32_t p = tid; p < n_parts; p += SCATTER_THREADS) hist[p] = 0;
+    __syncthreads();
+    stage ^= 1;
+  }
+}
+
+// pass 2, warp-multisplit variant (used when NW x n_parts cursors fit in shared memory): per tile, every warp
+// histograms ITS windows into a private array, a per-partition prefix over the warps turns the counts into
+// absolute cursors (one global reservation per (tile, partition)), then the tile is re-scanned and scattered
+// with PartWarpScatterEmit.
+constexpr int WSCATTER_THREADS = 256;
+constexpr int WSCATTER_WARPS = WSCATTER_THREADS / 32;
+__global__ void __launch_bounds__(WSCATTER_THREADS) partition_scatter_warp_kernel(ScanInput in, uint32_t n_parts,
+                                                                                  const unsigned long long *part_start,
+                                                                                  unsigned long long *part_cursor, uint64_t *out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[2];
+  uint32_t *whist = reinterpret_cast<uint32_t *>(smem_raw + 2 * sizeof(TileSmem));  // [WSCATTER_WARPS][n_parts]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint32_t *mine = whist + (size_t)warp * n_parts;
+  const bool has_start = in.start != nullptr;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  for (uint32_t i = tid; i < n_parts * WSCATTER_WARPS; i += WSCATTER_THREADS) whist[i] = 0;
+  __syncthreads();
+  uint64_t tile = blockIdx.x;
+  int stage = 0;
+  uint32_t phase0 = 0, phase1 = 0;
+  if (tile < in.n_tiles && tid == 0) issue_tile(in, &stages[0], &bars[0], tile);
+  for (; tile < in.n_tiles; tile += gridDim.x) {
+    const uint64_t next = tile + gridDim.x;
+    if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
+    wait_stage(bars, stage, phase0, phase1);
+    const TileSmem *ts = &stages[stage];
+    {
+      PartCountEmit e{mine, n_parts};  // warp-private histogram (ATOMS.POPC.INC, no return value)
+#pragma unroll 1
+      for (int r = 0; r < TILE_WORDS / WSCATTER_THREADS; ++r) scan_word<8>(ts, r * WSCATTER_THREADS + tid, in.k, has_start, e);
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < n_parts; p += WSCATTER_THREADS) {  // counts -> absolute cursors, warp after warp
+      uint32_t cnt[WSCATTER_WARPS], total = 0;
+#pragma unroll
+      for (int w = 0; w < WSCATTER_WARPS; ++w) { cnt[w] = whist[(size_t)w * n_parts + p]; total += cnt[w]; }
+      uint32_t run = total ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)total)) : 0u;
+#pragma unroll
+      for (int w = 0; w < WSCATTER_WARPS; ++w) { whist[(size_t)w * n_parts + p] = run; run += cnt[w]; }
+    }
+    __syncthreads();
+    {
+      PartWarpScatterEmit e{mine, out, n_parts};
+#pragma unroll 1
+      for (int r = 0; r < TILE_WORDS / WSCATTER_THREADS; ++r) scan_word<8, PartWarpScatterEmit, true>(ts, r * WSCATTER_THREADS + tid, in.k, has_start, e);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n_parts * WSCATTER_WARPS; i += WSCATTER_THREADS) whist[i] = 0;
     __syncthreads();
     stage ^= 1;
   }
@@ -668,7 +750,13 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
   const size_t smem = 2 * sizeof(TileSmem) + (size_t)n_parts * sizeof(uint32_t);
   const uint64_t max_ctas = (uint64_t)num_sms() * (smem > 100 * 1024 ? 1 : smem > 72 * 1024 ? 2 : SCAN_CTAS_PER_SM);
   cudaError_t e;
-  if (scatter) {
+  const size_t wsmem = 2 * sizeof(TileSmem) + (size_t)WSCATTER_WARPS * n_parts * sizeof(uint32_t);
+  if (scatter && wsmem <= 110 * 1024) {  // warp-multisplit variant: >= 2 CTAs/SM
+    if ((e = set_smem(partition_scatter_warp_kernel, wsmem)) != cudaSuccess) return e;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const uint64_t ctas = (uint64_t)num_sms() * (wsmem <= 72 * 1024 ? 3 : 2);
+    partition_scatter_warp_kernel<<<(unsigned)std::min(in.n_tiles, ctas), WSCATTER_THREADS, wsmem, s>>>(in, n_parts, part_start, part_cursor, out);
+  } else if (scatter) {
     if ((e = set_smem(partition_scatter_kernel, smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const uint64_t ctas = (uint64_t)num_sms() * 2;

@@ -114,12 +114,17 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
 template <bool SCATTER>
 __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) {
   extern __shared__ uint32_t sm[];
-  uint32_t *hist = sm;  // histogram, then ABSOLUTE output cursors
+  // count pass: one histogram.  scatter pass: one histogram per WARP (turned into that warp's absolute cursors),
+  // ranking by warp multisplit -- see PartWarpScatterEmit in kmg_kernels.cu for why not shared atomics with return.
+  constexpr int NW = REFINE_THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t *hist = SCATTER ? sm + (size_t)warp * P.n_sub : sm;
+  const uint32_t n_hist = SCATTER ? NW * P.n_sub : P.n_sub;
   __shared__ uint32_t s_c;
-  for (uint32_t s = threadIdx.x; s < P.n_sub; s += REFINE_THREADS) hist[s] = 0;
+  for (uint32_t s = tid; s < n_hist; s += REFINE_THREADS) sm[s] = 0;
   __syncthreads();
   for (uint32_t g = blockIdx.x; g < P.n_tiles; g += gridDim.x) {
-    if (threadIdx.x == 0) {  // which coarse partition owns tile g: largest c with tile_prefix[c] <= g
+    if (tid == 0) {  // which coarse partition owns tile g: largest c with tile_prefix[c] <= g
       uint32_t lo = 0, hi = P.n_coarse;
       while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.tile_prefix[mid] <= g) lo = mid; else hi = mid; }
       s_c = lo;
@@ -134,45 +139,57 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
       uint64_t key[U];
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        const uint32_t i = i0 + j * REFINE_THREADS + threadIdx.x;
+        const uint32_t i = i0 + j * REFINE_THREADS + tid;
         key[j] = i < m ? (SCATTER ? P.keys[begin + i] : __ldcs(P.keys + begin + i)) : EMPTY_KEY;
       }
 #pragma unroll
-      for (int j = 0; j < U; ++j) if (i0 + j * REFINE_THREADS + threadIdx.x < m) atomicAdd(hist + sub_of_mix(mix64(key[j]), P.n_sub), 1u);
+      for (int j = 0; j < U; ++j) if (i0 + j * REFINE_THREADS + tid < m) atomicAdd(hist + sub_of_mix(mix64(key[j]), P.n_sub), 1u);
     }
     __syncthreads();
     const uint64_t f0 = (uint64_t)c * P.n_sub;
     if (!SCATTER) {
-      for (uint32_t s = threadIdx.x; s < P.n_sub; s += REFINE_THREADS) {
-        const uint32_t h = hist[s];
-        if (h) { atomicAdd(P.fine_counts + f0 + s, (unsigned long long)h); hist[s] = 0; }
+      for (uint32_t s = tid; s < P.n_sub; s += REFINE_THREADS) {
+        const uint32_t h = sm[s];
+        if (h) { atomicAdd(P.fine_counts + f0 + s, (unsigned long long)h); sm[s] = 0; }
       }
     } else {
-      for (uint32_t s = threadIdx.x; s < P.n_sub; s += REFINE_THREADS) {
-        const uint32_t h = hist[s];
-        hist[s] = h ? (uint32_t)(P.fine_start[f0 + s] + atomicAdd(P.fine_cursor + f0 + s, (unsigned long long)h)) : 0u;
+      for (uint32_t s = tid; s < P.n_sub; s += REFINE_THREADS) {  // counts -> absolute cursors, warp after warp
+        uint32_t cnt[NW], total = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { cnt[w] = sm[(size_t)w * P.n_sub + s]; total += cnt[w]; }
+        uint32_t run = total ? (uint32_t)(P.fine_start[f0 + s] + atomicAdd(P.fine_cursor + f0 + s, (unsigned long long)total)) : 0u;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { sm[(size_t)w * P.n_sub + s] = run; run += cnt[w]; }
       }
       __syncthreads();
+      const uint32_t lt = (1u << lane) - 1u;
       for (uint32_t i0 = 0; i0 < m; i0 += U * REFINE_THREADS) {  // second read of the tile comes from L2
         uint64_t key[U], cnt[U];
-        uint32_t sb[U], o[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-          const uint32_t i = i0 + j * REFINE_THREADS + threadIdx.x;
+          const uint32_t i = i0 + j * REFINE_THREADS + tid;
           key[j] = i < m ? __ldcs(P.keys + begin + i) : EMPTY_KEY;  // last use of this tile
           cnt[j] = (i < m && P.counts) ? __ldcs(P.counts + begin + i) : 1ull;
         }
 #pragma unroll
-        for (int j = 0; j < U; ++j) { sb[j] = sub_of_mix(mix64(key[j]), P.n_sub); o[j] = 0; if (i0 + j * REFINE_THREADS + threadIdx.x < m) o[j] = atomicAdd(hist + sb[j], 1u); }
-#pragma unroll
-        for (int j = 0; j < U; ++j)
-          if (i0 + j * REFINE_THREADS + threadIdx.x < m) {
-            P.out_keys[o[j]] = key[j];
-            if (P.out_counts) P.out_counts[o[j]] = cnt[j];
+        for (int j = 0; j < U; ++j) {  // warp multisplit: all 32 lanes take part (the i0 loop is warp-uniform)
+          const bool ok = i0 + j * REFINE_THREADS + tid < m;
+          const uint32_t sb = ok ? sub_of_mix(mix64(key[j]), P.n_sub) : (0x80000000u | lane);
+          const uint32_t peers = __match_any_sync(0xffffffffu, sb);
+          const int leader = __ffs(peers) - 1;
+          uint32_t base = 0;
+          if (ok && lane == leader) { base = hist[sb]; hist[sb] = base + __popc(peers); }
+          base = __shfl_sync(0xffffffffu, base, leader);
+          __syncwarp();
+          if (ok) {
+            const uint32_t dst = base + __popc(peers & lt);
+            P.out_keys[dst] = key[j];
+            if (P.out_counts) P.out_counts[dst] = cnt[j];
           }
+        }
       }
       __syncthreads();
-      for (uint32_t s = threadIdx.x; s < P.n_sub; s += REFINE_THREADS) hist[s] = 0;
+      for (uint32_t s = tid; s < n_hist; s += REFINE_THREADS) sm[s] = 0;
     }
     __syncthreads();
   }
@@ -180,7 +197,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
 
 cudaError_t launch_refine(const RefineParams &P, bool scatter, cudaStream_t s) {
   if (P.n_tiles == 0) return cudaSuccess;
-  const size_t smem = (size_t)P.n_sub * sizeof(uint32_t);
+  const size_t smem = (size_t)P.n_sub * sizeof(uint32_t) * (scatter ? REFINE_THREADS / 32 : 1);
   const unsigned grid = (unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms() * 2);
   cudaError_t e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
