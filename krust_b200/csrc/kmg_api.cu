@@ -4,6 +4,7 @@
 // every entry point needs a CUDA device.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -766,6 +767,7 @@ KMG_EXPORT kmg_status kmg_create(const kmg_config *cfg, kmg_ctx **out) {
     if (_e != cudaSuccess) { cuda_fail(c, _e, #call); return bail(_e == cudaErrorMemoryAllocation ? KMG_ERR_OOM : KMG_ERR_CUDA); } \
   } while (0)
   CUC(cudaSetDevice(c->device));
+  if (const char *dbg = getenv("KMG_DEBUG")) set_debug((uint32_t)atoi(dbg));
   if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
   else { CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));

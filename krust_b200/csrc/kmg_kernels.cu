@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -18,6 +19,9 @@
 #include "kmg_device.cuh"
 
 namespace kmg {
+
+__constant__ uint32_t g_dbg = 0;  // ablation switches for tools/ablate.py (KMG_DEBUG env): 1 no stores, 2 no histogram pass, 4 no scatter pass
+void set_debug(uint32_t v) { cudaMemcpyToSymbol(g_dbg, &v, sizeof v); }
 
 // =================================================================================================
 // K8 ingest: ASCII (+ Phred+33 quality) -> packed bases + valid mask.  One thread per 32-base word.
@@ -374,7 +378,7 @@ struct PartWarpScatterEmit {
       if (ok && (int)lane == leader) { base = wcur[p]; wcur[p] = base + __popc(peers); }
       base = __shfl_sync(0xffffffffu, base, leader);
       __syncwarp();  // the leader's cursor update is visible to the next group's leaders
-      if (ok) __stcs(out + (base + __popc(peers & lt)), key[j]);
+      if (ok && !(g_dbg & 1u)) __stcs(out + (base + __popc(peers & lt)), key[j]);
     }
   }
 };
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(WSCATTER_THREADS) partition_scatter_warp_kerne
     if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
     wait_stage(bars, stage, phase0, phase1);
     const TileSmem *ts = &stages[stage];
-    {
+    if (!(g_dbg & 2u)) {
       PartCountEmit e{mine, n_parts};  // warp-private histogram (ATOMS.POPC.INC, no return value)
 #pragma unroll 1
       for (int r = 0; r < TILE_WORDS / WSCATTER_THREADS; ++r) scan_word<8>(ts, r * WSCATTER_THREADS + tid, in.k, has_start, e);
@@ -521,7 +525,7 @@ __global__ void __launch_bounds__(WSCATTER_THREADS) partition_scatter_warp_kerne
       for (int w = 0; w < WSCATTER_WARPS; ++w) { whist[(size_t)w * n_parts + p] = run; run += cnt[w]; }
     }
     __syncthreads();
-    {
+    if (!(g_dbg & 4u)) {
       PartWarpScatterEmit e{mine, out, n_parts};
 #pragma unroll 1
       for (int r = 0; r < TILE_WORDS / WSCATTER_THREADS; ++r) scan_word<8, PartWarpScatterEmit, true>(ts, r * WSCATTER_THREADS + tid, in.k, has_start, e);
@@ -529,6 +533,112 @@ __global__ void __launch_bounds__(WSCATTER_THREADS) partition_scatter_warp_kerne
     __syncthreads();
     for (uint32_t i = tid; i < n_parts * WSCATTER_WARPS; i += WSCATTER_THREADS) whist[i] = 0;
     __syncthreads();
+    stage ^= 1;
+  }
+}
+
+// pass 2, STAGED variant (default): measured with ablation switches (tools/ablate.py), 60 % of the scatter pass
+// was the stores themselves -- a warp store of 32 keys to 32 different partitions is 32 separate L2 transactions.
+// Here each sub-tile's keys are first ranked into a shared-memory staging buffer in partition order, then copied
+// out by consecutive lanes: a warp instruction now covers a few contiguous runs (one sector per ~4 keys).
+//   per sub-tile: histogram (POPC.INC) -> exclusive prefix over the partitions (staging offsets) + ONE global
+//   reservation per partition -> rank pass (shared atomic returns the staging slot) -> coalesced copy-out, the
+//   destination recomputed from the staged key itself.
+constexpr int STAGE_THREADS = 512;
+constexpr int STAGE_SUB_WORDS = 512;                 // 16384 windows per sub-tile
+constexpr int STAGE_KEYS = STAGE_SUB_WORDS * 32;     // staging capacity (128 KiB)
+struct StageEmit {
+  uint32_t *cursor;   // smem: next staging slot of each partition
+  uint64_t *staging;  // smem
+  uint32_t n_parts;
+  template <int G>
+  __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
+    uint32_t p[G], o[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) p[j] = part_of(key[j], n_parts);
+#pragma unroll
+    for (int j = 0; j < G; ++j) { o[j] = 0; if ((okg >> j) & 1u) o[j] = atomicAdd(cursor + p[j], 1u); }
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+      if ((okg >> j) & 1u) staging[o[j]] = key[j];
+  }
+};
+__global__ void __launch_bounds__(STAGE_THREADS, 1) partition_scatter_staged_kernel(ScanInput in, uint32_t n_parts,
+                                                                                     const unsigned long long *part_start,
+                                                                                     unsigned long long *part_cursor, uint64_t *out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t s_scan[STAGE_THREADS / 32 + 1];
+  uint64_t *staging = reinterpret_cast<uint64_t *>(smem_raw + 2 * sizeof(TileSmem));
+  uint32_t *hist = reinterpret_cast<uint32_t *>(staging + STAGE_KEYS);  // histogram, then staging cursors
+  uint32_t *s_off = hist + n_parts;                                     // staging offset of each partition
+  uint32_t *g_base = s_off + n_parts;                                   // index in `out` of the partition's reservation
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool has_start = in.start != nullptr;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  for (uint32_t p = tid; p < n_parts; p += STAGE_THREADS) hist[p] = 0;
+  __syncthreads();
+  uint64_t tile = blockIdx.x;
+  int stage = 0;
+  uint32_t phase0 = 0, phase1 = 0;
+  if (tile < in.n_tiles && tid == 0) issue_tile(in, &stages[0], &bars[0], tile);
+  for (; tile < in.n_tiles; tile += gridDim.x) {
+    const uint64_t next = tile + gridDim.x;
+    if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
+    wait_stage(bars, stage, phase0, phase1);
+    const TileSmem *ts = &stages[stage];
+    for (int sub = 0; sub < TILE_WORDS / STAGE_SUB_WORDS; ++sub) {
+      const int w0 = sub * STAGE_SUB_WORDS;
+      {
+        PartCountEmit e{hist, n_parts};
+#pragma unroll 1
+        for (int r = 0; r < STAGE_SUB_WORDS / STAGE_THREADS; ++r) scan_word<8>(ts, w0 + r * STAGE_THREADS + tid, in.k, has_start, e);
+      }
+      __syncthreads();
+      // exclusive prefix over the partitions: thread t owns the contiguous chunk [t*per, (t+1)*per)
+      const uint32_t per = (n_parts + STAGE_THREADS - 1) / STAGE_THREADS;
+      const uint32_t b0 = tid * per, b1 = b0 + per < n_parts ? b0 + per : n_parts;
+      uint32_t mine = 0;
+      for (uint32_t p = b0; p < b1; ++p) mine += hist[p];
+      uint32_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (lane == 31) s_scan[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t v = lane < STAGE_THREADS / 32 ? s_scan[lane] : 0, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane < STAGE_THREADS / 32) s_scan[lane] = inc - v;
+        if (lane == 31) s_scan[STAGE_THREADS / 32] = inc;  // keys in this sub-tile
+      }
+      __syncthreads();
+      uint32_t run = s_scan[warp] + (incl - mine);
+      for (uint32_t p = b0; p < b1; ++p) {
+        const uint32_t c = hist[p];
+        s_off[p] = run;
+        g_base[p] = c ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)c)) : 0u;
+        hist[p] = run;  // becomes the staging cursor
+        run += c;
+      }
+      const uint32_t n_sub = s_scan[STAGE_THREADS / 32];
+      __syncthreads();
+      {
+        StageEmit e{hist, staging, n_parts};
+#pragma unroll 1
+        for (int r = 0; r < STAGE_SUB_WORDS / STAGE_THREADS; ++r) scan_word<8>(ts, w0 + r * STAGE_THREADS + tid, in.k, has_start, e);
+      }
+      __syncthreads();
+      for (uint32_t i = tid; i < n_sub; i += STAGE_THREADS) {  // coalesced copy-out
+        const uint64_t key = staging[i];
+        const uint32_t p = part_of(key, n_parts);
+        __stcs(out + ((uint64_t)g_base[p] + (i - s_off[p])), key);
+      }
+      __syncthreads();
+      for (uint32_t p = tid; p < n_parts; p += STAGE_THREADS) hist[p] = 0;
+      __syncthreads();
+    }
     stage ^= 1;
   }
 }
@@ -751,7 +861,12 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
   const uint64_t max_ctas = (uint64_t)num_sms() * (smem > 100 * 1024 ? 1 : smem > 72 * 1024 ? 2 : SCAN_CTAS_PER_SM);
   cudaError_t e;
   const size_t wsmem = 2 * sizeof(TileSmem) + (size_t)WSCATTER_WARPS * n_parts * sizeof(uint32_t);
-  if (scatter && wsmem <= 110 * 1024) {  // warp-multisplit variant: >= 2 CTAs/SM
+  const size_t stsmem = 2 * sizeof(TileSmem) + (size_t)STAGE_KEYS * 8 + 3 * (size_t)n_parts * sizeof(uint32_t);
+  if (scatter && stsmem <= 220 * 1024 && !(getenv("KMG_SCATTER") && atoi(getenv("KMG_SCATTER")) != 0)) {  // staged variant (default)
+    if ((e = set_smem(partition_scatter_staged_kernel, stsmem)) != cudaSuccess) return e;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    partition_scatter_staged_kernel<<<(unsigned)std::min<uint64_t>(in.n_tiles, (uint64_t)num_sms()), STAGE_THREADS, stsmem, s>>>(in, n_parts, part_start, part_cursor, out);
+  } else if (scatter && wsmem <= 110 * 1024 && !(getenv("KMG_SCATTER") && atoi(getenv("KMG_SCATTER")) == 2)) {  // warp-multisplit variant: >= 2 CTAs/SM
     if ((e = set_smem(partition_scatter_warp_kernel, wsmem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const uint64_t ctas = (uint64_t)num_sms() * (wsmem <= 72 * 1024 ? 3 : 2);

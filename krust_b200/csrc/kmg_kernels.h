@@ -32,7 +32,7 @@ struct TableView {
 constexpr int CONS_MAX_RUNS = 16;
 constexpr int MAX_PARTS = 8192;        // bins of ONE scatter level (shared-memory histogram)
 constexpr int REFINE_THREADS = 512;
-constexpr int REFINE_TILE = 16384;     // keys per level-2 tile
+constexpr int REFINE_TILE = 8192;      // keys per level-2 tile (staged in shared memory: 64 KiB, 128 KiB with counts)
 constexpr int COUNT_THREADS = 512;
 constexpr int COUNT_CTAS_PER_SM = 2;
 constexpr int SMEM_COUNT_THREADS = 512;    // phase B primary variant: table in shared memory, 2 CTAs/SM
@@ -98,6 +98,7 @@ cudaError_t launch_count_partitions(const CountParams &P, unsigned grid, cudaStr
 cudaError_t launch_count_partitions_smem(const CountParams &P, cudaStream_t s);
 cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, cudaStream_t s);
 int num_sms();
+void set_debug(uint32_t v);  // ablation switches (tools/ablate.py)
 cudaError_t launch_table_init(HashTable t, cudaStream_t s);
 cudaError_t launch_insert_keys(HashTable t, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n,
                                unsigned long long *counters, cudaStream_t s);

@@ -113,15 +113,17 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
 // ---------------------------------------------------------------------------------------------------
 template <bool SCATTER>
 __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) {
-  extern __shared__ uint32_t sm[];
-  // count pass: one histogram.  scatter pass: one histogram per WARP (turned into that warp's absolute cursors),
-  // ranking by warp multisplit -- see PartWarpScatterEmit in kmg_kernels.cu for why not shared atomics with return.
-  constexpr int NW = REFINE_THREADS / 32;
+  extern __shared__ __align__(16) uint8_t rsm[];
+  // count pass: one histogram.  scatter pass: the tile's keys are ranked into a shared-memory staging buffer in
+  // sub-bin order and copied out by consecutive lanes (see partition_scatter_staged_kernel: scattered 8-byte
+  // stores, one L2 transaction each, were 60 % of the unstaged kernels).
+  uint64_t *staging = reinterpret_cast<uint64_t *>(rsm);                                // SCATTER only: REFINE_TILE keys
+  uint64_t *staging_c = staging + REFINE_TILE;                                          // SCATTER with counts only
+  uint32_t *hist = reinterpret_cast<uint32_t *>(rsm + (SCATTER ? (size_t)REFINE_TILE * 8 * (P.counts ? 2 : 1) : 0));
+  uint32_t *s_off = hist + P.n_sub, *g_base = s_off + P.n_sub;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t *hist = SCATTER ? sm + (size_t)warp * P.n_sub : sm;
-  const uint32_t n_hist = SCATTER ? NW * P.n_sub : P.n_sub;
-  __shared__ uint32_t s_c;
-  for (uint32_t s = tid; s < n_hist; s += REFINE_THREADS) sm[s] = 0;
+  __shared__ uint32_t s_c, s_scan[REFINE_THREADS / 32 + 1];
+  for (uint32_t s = tid; s < P.n_sub; s += REFINE_THREADS) hist[s] = 0;
   __syncthreads();
   for (uint32_t g = blockIdx.x; g < P.n_tiles; g += gridDim.x) {
     if (tid == 0) {  // which coarse partition owns tile g: largest c with tile_prefix[c] <= g
@@ -149,22 +151,39 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
     const uint64_t f0 = (uint64_t)c * P.n_sub;
     if (!SCATTER) {
       for (uint32_t s = tid; s < P.n_sub; s += REFINE_THREADS) {
-        const uint32_t h = sm[s];
-        if (h) { atomicAdd(P.fine_counts + f0 + s, (unsigned long long)h); sm[s] = 0; }
+        const uint32_t h = hist[s];
+        if (h) { atomicAdd(P.fine_counts + f0 + s, (unsigned long long)h); hist[s] = 0; }
       }
     } else {
-      for (uint32_t s = tid; s < P.n_sub; s += REFINE_THREADS) {  // counts -> absolute cursors, warp after warp
-        uint32_t cnt[NW], total = 0;
+      // exclusive prefix over the sub-bins (staging offsets) + one global reservation per sub-bin
+      const uint32_t per = (P.n_sub + REFINE_THREADS - 1) / REFINE_THREADS;
+      const uint32_t b0 = tid * per, b1 = b0 + per < P.n_sub ? b0 + per : P.n_sub;
+      uint32_t mine = 0;
+      for (uint32_t s = b0; s < b1; ++s) mine += hist[s];
+      uint32_t incl = mine;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) { cnt[w] = sm[(size_t)w * P.n_sub + s]; total += cnt[w]; }
-        uint32_t run = total ? (uint32_t)(P.fine_start[f0 + s] + atomicAdd(P.fine_cursor + f0 + s, (unsigned long long)total)) : 0u;
+      for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (lane == 31) s_scan[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t v = lane < REFINE_THREADS / 32 ? s_scan[lane] : 0, inc = v;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) { sm[(size_t)w * P.n_sub + s] = run; run += cnt[w]; }
+        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane < REFINE_THREADS / 32) s_scan[lane] = inc - v;
       }
       __syncthreads();
-      const uint32_t lt = (1u << lane) - 1u;
+      uint32_t run = s_scan[warp] + (incl - mine);
+      for (uint32_t s = b0; s < b1; ++s) {
+        const uint32_t h = hist[s];
+        s_off[s] = run;
+        g_base[s] = h ? (uint32_t)(P.fine_start[f0 + s] + atomicAdd(P.fine_cursor + f0 + s, (unsigned long long)h)) : 0u;
+        hist[s] = run;  // becomes the staging cursor
+        run += h;
+      }
+      __syncthreads();
       for (uint32_t i0 = 0; i0 < m; i0 += U * REFINE_THREADS) {  // second read of the tile comes from L2
         uint64_t key[U], cnt[U];
+        uint32_t sb[U], o[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
           const uint32_t i = i0 + j * REFINE_THREADS + tid;
@@ -172,24 +191,21 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
           cnt[j] = (i < m && P.counts) ? __ldcs(P.counts + begin + i) : 1ull;
         }
 #pragma unroll
-        for (int j = 0; j < U; ++j) {  // warp multisplit: all 32 lanes take part (the i0 loop is warp-uniform)
-          const bool ok = i0 + j * REFINE_THREADS + tid < m;
-          const uint32_t sb = ok ? sub_of_mix(mix64(key[j]), P.n_sub) : (0x80000000u | lane);
-          const uint32_t peers = __match_any_sync(0xffffffffu, sb);
-          const int leader = __ffs(peers) - 1;
-          uint32_t base = 0;
-          if (ok && lane == leader) { base = hist[sb]; hist[sb] = base + __popc(peers); }
-          base = __shfl_sync(0xffffffffu, base, leader);
-          __syncwarp();
-          if (ok) {
-            const uint32_t dst = base + __popc(peers & lt);
-            P.out_keys[dst] = key[j];
-            if (P.out_counts) P.out_counts[dst] = cnt[j];
-          }
-        }
+        for (int j = 0; j < U; ++j) { sb[j] = sub_of_mix(mix64(key[j]), P.n_sub); o[j] = 0; if (i0 + j * REFINE_THREADS + tid < m) o[j] = atomicAdd(hist + sb[j], 1u); }
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          if (i0 + j * REFINE_THREADS + tid < m) { staging[o[j]] = key[j]; if (P.counts) staging_c[o[j]] = cnt[j]; }
       }
       __syncthreads();
-      for (uint32_t s = tid; s < n_hist; s += REFINE_THREADS) sm[s] = 0;
+      for (uint32_t i = tid; i < m; i += REFINE_THREADS) {  // coalesced copy-out; destination recomputed from the key
+        const uint64_t key = staging[i];
+        const uint32_t sbin = sub_of_mix(mix64(key), P.n_sub);
+        const uint64_t dst = (uint64_t)g_base[sbin] + (i - s_off[sbin]);
+        P.out_keys[dst] = key;
+        if (P.out_counts) P.out_counts[dst] = P.counts ? staging_c[i] : 1ull;
+      }
+      __syncthreads();
+      for (uint32_t s = tid; s < P.n_sub; s += REFINE_THREADS) hist[s] = 0;
     }
     __syncthreads();
   }
@@ -197,8 +213,8 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
 
 cudaError_t launch_refine(const RefineParams &P, bool scatter, cudaStream_t s) {
   if (P.n_tiles == 0) return cudaSuccess;
-  const size_t smem = (size_t)P.n_sub * sizeof(uint32_t) * (scatter ? REFINE_THREADS / 32 : 1);
-  const unsigned grid = (unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms() * 2);
+  const size_t smem = scatter ? (size_t)REFINE_TILE * 8 * (P.counts ? 2 : 1) + 3 * (size_t)P.n_sub * sizeof(uint32_t) : (size_t)P.n_sub * sizeof(uint32_t);
+  const unsigned grid = (unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms() * ((scatter && smem > 110 * 1024) ? 1 : 2));
   cudaError_t e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (scatter) {
