@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
           w[j] = (uint32_t)w64;
         }
       }
-      if (P.preagg) {  // warp run-length pre-aggregation (see count_partitions_kernel)
+      if (P.preagg && n_p > 2 * SMEM_COUNT_THREADS * G) {  // warp run-length pre-aggregation, only for oversized (= skewed) partitions
 #pragma unroll
         for (int j = 0; j < G; ++j) {
           const uint64_t kk = w[j] ? key[j] : EMPTY_KEY;
@@ -531,35 +531,32 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
     for (int o = 16; o > 0; o >>= 1) new_keys += __shfl_xor_sync(0xffffffffu, new_keys, o);
     if (lane == 0) s_warp[warp] = new_keys;
     __syncthreads();  // all upserts done
-    // ---- compact: warp w owns the contiguous slot range [w*chunk, (w+1)*chunk); its occupied slots go out as one run
-    const uint32_t chunk = (mask + 1) / NW > 32 ? (mask + 1) / NW : 32;
-    const uint32_t lo = warp * chunk, hi = lo + chunk <= mask + 1 ? lo + chunk : (lo < mask + 1 ? mask + 1 : lo);
-    if (tid == 0) {  // reserve the partition's output range; the atomic's latency overlaps the count pass below
+    // ---- compact in ONE pass: the partition's output range is reserved with one global atomic (its size, the number
+    // of new keys, is known); inside it every warp iteration (32 slots) takes the next run from a shared cursor.
+    if (tid == 0) {
       uint32_t d = 0;
       for (int w2 = 0; w2 < NW; ++w2) d += s_warp[w2];
       const unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);
       P.out_seg_start[p] = b; P.out_seg_len[p] = d;
       s_base = b;
+      s_work = 0;  // reused as the running cursor inside the partition's range (re-written by warp 0 at the loop top)
     }
-    uint32_t wcount = 0;
-    for (uint32_t i = lo + lane; i < hi; i += 32) wcount += __popc(__ballot_sync(0xffffffffu, skeys[i] != EMPTY_KEY));
-    __syncthreads();  // s_warp (new keys) consumed by thread 0, s_base published
-    if (lane == 0) s_warp[warp] = wcount;
     __syncthreads();
-    uint32_t woff = 0;
-    for (int w2 = 0; w2 < warp; ++w2) woff += s_warp[w2];
-    uint64_t o = s_base + woff;
-    for (uint32_t i = lo + lane; i < hi; i += 32) {
+    const unsigned long long out0 = s_base;
+    for (uint32_t i = warp * 32 + lane; i <= mask; i += SMEM_COUNT_THREADS) {  // mask + 1 is a multiple of 32: warp-uniform
       const unsigned long long k = skeys[i];
       const bool occ = k != EMPTY_KEY;
       const uint32_t m = __ballot_sync(0xffffffffu, occ);
+      if (m == 0) continue;
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&s_work, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
       if (occ) {
-        const uint64_t dst = o + __popc(m & ((1u << lane) - 1u));
+        const uint64_t dst = out0 + base + __popc(m & ((1u << lane) - 1u));
         __stcs(P.out_keys + dst, (uint64_t)k);
         __stcs(P.out_counts + dst, (uint64_t)scnt[i] + 1);  // slots store occurrences - 1
         skeys[i] = EMPTY_KEY; scnt[i] = 0;
       }
-      o += __popc(m);
     }
     __syncthreads();  // table clean before the next partition
   }
