@@ -283,7 +283,6 @@ void timers_collect(kmg_ctx *c) {
 // Partitioned pipeline: A1 coarse scatter, A2 refine to fine partitions, B per-CTA counting
 // (kernels and rationale: kmg_partition.cu).
 // =================================================================================================
-inline uint32_t pow2_ceil_log2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) ++l; return l; }
 constexpr uint64_t TARGET_KEYS_PER_PART = 3600;  // <= 4096 with 8 sigma to spare: one upsert round per partition; load ~0.44
 
 // Decide how this context counts.  Called at the first feeding call, when the input size is known.

@@ -415,18 +415,19 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
 // raised and the host re-runs phase B with the L2-scratch variant (u64 counts, larger tables).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_kernel(CountParams P) {
-  extern __shared__ __align__(16) unsigned long long skeys[];  // SMEM_TABLE_SLOTS keys, then SMEM_TABLE_SLOTS u32 counts
+  extern __shared__ __align__(16) unsigned long long skeys[];  // SMEM_TABLE_SLOTS keys, u32 counts, u16 occupied-slot list
   uint32_t *scnt = reinterpret_cast<uint32_t *>(skeys + SMEM_TABLE_SLOTS);
+  uint16_t *slist = reinterpret_cast<uint16_t *>(scnt + SMEM_TABLE_SLOTS);  // slots claimed for this partition, in claim order
+  __shared__ uint32_t s_list_n;
   __shared__ uint64_t seg_begin[CONS_MAX_RUNS];
   __shared__ uint64_t seg_prefix[CONS_MAX_RUNS + 1];
-  __shared__ uint32_t s_work, s_warp[SMEM_COUNT_THREADS / 32 + 1];
+  __shared__ uint32_t s_work;
   __shared__ unsigned long long s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t SLOTS = SMEM_TABLE_SLOTS;
-  constexpr int NW = SMEM_COUNT_THREADS / 32;
   for (uint32_t i = tid; i < SLOTS; i += SMEM_COUNT_THREADS) { skeys[i] = EMPTY_KEY; scnt[i] = 0; }
   uint32_t next_work = 0;
-  if (tid == 0) next_work = atomicAdd(P.next, 1u);
+  if (tid == 0) { next_work = atomicAdd(P.next, 1u); s_list_n = 0; }
   __syncthreads();
 
   for (;;) {
@@ -463,7 +464,6 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
     // 8 keys per thread are loaded up front (one exposed global-load latency per 4096 entries instead of two),
     // then upserted in two batches of 4 whose first probes are in flight together.
     constexpr int G = 8, H = 4;
-    uint32_t new_keys = 0;
 #pragma unroll 1
     for (uint64_t base = 0; base < n_p; base += (uint64_t)SMEM_COUNT_THREADS * G) {
       uint64_t key[G];
@@ -508,63 +508,66 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
 #pragma unroll
         for (int j = 0; j < H; ++j) {
           const uint32_t wj = w[h0 + j];
-          if (!wj) continue;
-          const uint64_t kj = key[h0 + j];
-          unsigned long long c2 = cur[j];
-          uint32_t s2 = sl[j];
-          for (uint32_t tries = 0;; ++tries) {  // linear probing in shared memory: a step is tens of cycles
-            if (c2 == EMPTY_KEY || c2 == kj) {
-              const uint32_t add = wj - (c2 == EMPTY_KEY ? 1u : 0u);  // slots store occurrences - 1
-              new_keys += c2 == EMPTY_KEY;
-              if (add) { const uint32_t old = atomicAdd(&scnt[s2], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
-              break;
+          bool is_new = false;
+          uint32_t fslot = 0;
+          if (wj) {
+            const uint64_t kj = key[h0 + j];
+            unsigned long long c2 = cur[j];
+            uint32_t s2 = sl[j];
+            for (uint32_t tries = 0;; ++tries) {  // linear probing in shared memory: a step is tens of cycles
+              if (c2 == EMPTY_KEY || c2 == kj) {
+                is_new = c2 == EMPTY_KEY;
+                fslot = s2;
+                const uint32_t add = wj - (is_new ? 1u : 0u);  // slots store occurrences - 1
+                if (add) { const uint32_t old = atomicAdd(&scnt[s2], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
+                break;
+              }
+              if (tries > mask) { atomicExch(P.error_flag, 1u); break; }
+              s2 = (s2 + 1) & mask;
+              c2 = skeys[s2];
+              if (c2 == EMPTY_KEY) c2 = atomicCAS(&skeys[s2], EMPTY_KEY, kj);
             }
-            if (tries > mask) { atomicExch(P.error_flag, 1u); break; }
-            s2 = (s2 + 1) & mask;
-            c2 = skeys[s2];
-            if (c2 == EMPTY_KEY) c2 = atomicCAS(&skeys[s2], EMPTY_KEY, kj);
+          }
+          // remember which slots this partition claimed (warp-aggregated append): compaction then visits only those
+          const uint32_t nm = __ballot_sync(0xffffffffu, is_new);
+          if (nm) {
+            const int leader = __ffs(nm) - 1;
+            uint32_t lb = 0;
+            if (lane == leader) lb = atomicAdd(&s_list_n, (uint32_t)__popc(nm));
+            lb = __shfl_sync(0xffffffffu, lb, leader);
+            if (is_new) slist[lb + __popc(nm & ((1u << lane) - 1u))] = (uint16_t)fslot;
           }
         }
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) new_keys += __shfl_xor_sync(0xffffffffu, new_keys, o);
-    if (lane == 0) s_warp[warp] = new_keys;
-    __syncthreads();  // all upserts done
-    // ---- compact in ONE pass: the partition's output range is reserved with one global atomic (its size, the number
-    // of new keys, is known); inside it every warp iteration (32 slots) takes the next run from a shared cursor.
+    __syncthreads();  // all upserts done; s_list_n = number of distinct keys of this partition
+    // ---- compact: reserve the partition's output range with one global atomic, then walk the claimed-slot list:
+    // entry i goes to out[base + i] (perfectly coalesced) and its slot is handed back clean.
     if (tid == 0) {
-      uint32_t d = 0;
-      for (int w2 = 0; w2 < NW; ++w2) d += s_warp[w2];
+      const uint32_t d = s_list_n;
       const unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);
       P.out_seg_start[p] = b; P.out_seg_len[p] = d;
       s_base = b;
-      s_work = 0;  // reused as the running cursor inside the partition's range (re-written by warp 0 at the loop top)
     }
     __syncthreads();
-    const unsigned long long out0 = s_base;
-    for (uint32_t i = warp * 32 + lane; i <= mask; i += SMEM_COUNT_THREADS) {  // mask + 1 is a multiple of 32: warp-uniform
-      const unsigned long long k = skeys[i];
-      const bool occ = k != EMPTY_KEY;
-      const uint32_t m = __ballot_sync(0xffffffffu, occ);
-      if (m == 0) continue;
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&s_work, (uint32_t)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (occ) {
-        const uint64_t dst = out0 + base + __popc(m & ((1u << lane) - 1u));
-        __stcs(P.out_keys + dst, (uint64_t)k);
-        __stcs(P.out_counts + dst, (uint64_t)scnt[i] + 1);  // slots store occurrences - 1
-        skeys[i] = EMPTY_KEY; scnt[i] = 0;
+    {
+      const unsigned long long out0 = s_base;
+      const uint32_t d = s_list_n;
+      for (uint32_t i = tid; i < d; i += SMEM_COUNT_THREADS) {
+        const uint32_t slot = slist[i];
+        __stcs(P.out_keys + out0 + i, (uint64_t)skeys[slot]);
+        __stcs(P.out_counts + out0 + i, (uint64_t)scnt[slot] + 1);  // slots store occurrences - 1
+        skeys[slot] = EMPTY_KEY; scnt[slot] = 0;
       }
     }
     __syncthreads();  // table clean before the next partition
+    if (tid == 0) s_list_n = 0;
   }
 }
 
 cudaError_t launch_count_partitions_smem(const CountParams &P, cudaStream_t s) {
   if (P.n_parts == 0) return cudaSuccess;
-  const size_t smem = (size_t)SMEM_TABLE_SLOTS * 12;
+  const size_t smem = (size_t)SMEM_TABLE_SLOTS * 14;  // u64 keys + u32 counts + u16 slot list
   cudaError_t e = cudaFuncSetAttribute(count_partitions_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
