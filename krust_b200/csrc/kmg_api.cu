@@ -88,6 +88,13 @@ struct kmg_ctx {
   std::vector<Run> runs;      // pending, not yet consolidated
   Run result;                 // consolidated (key, count) run
   bool has_result = false;
+  // count-of-counts of `result`, produced by phase B itself (consolidate)
+  unsigned long long *d_hist = nullptr;      // HIST_DENSE_BINS bins + overflow counter
+  uint64_t *d_hist_ov = nullptr;             // HIST_OVERFLOW_CAP counts >= HIST_DENSE_BINS
+  bool fused_valid = false, fused_cached = false;
+  std::vector<unsigned long long> h_bins;    // host copy, bins[1] filled in
+  std::vector<uint64_t> h_ov;                // ascending
+  uint64_t fused_sum = 0, fused_max = 0;
   uint64_t pending_bytes = 0;
   unsigned long long *d_part = nullptr;  // 3 * MAX_PARTS scratch: coarse counts, starts, cursors
   unsigned long long *d_fine_cursor = nullptr;  // n_parts
@@ -498,6 +505,14 @@ kmg_status consolidate(kmg_ctx *c) {
   prm.out_keys = out.d_keys; prm.out_counts = out.d_counts;
   prm.out_seg_start = out.d_seg_start; prm.out_seg_len = out.d_seg_len;
 
+  if (!c->d_hist) {
+    e = cudaMalloc(&c->d_hist, (HIST_DENSE_BINS + 1) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_hist_ov, HIST_OVERFLOW_CAP * 8);
+    if (e != cudaSuccess) { pool_free(c, d_order); free_run(c, out); return cuda_fail(c, e, "cudaMalloc(histogram)"); }
+  }
+  prm.hist = c->d_hist; prm.hist_overflow = c->d_hist_ov; prm.hist_overflow_cap = HIST_OVERFLOW_CAP;
+  c->fused_valid = c->fused_cached = false;
+
   const unsigned grid = (unsigned)std::min<uint64_t>(P, (uint64_t)num_sms() * COUNT_CTAS_PER_SM);
   kmg_status st = KMG_OK;
   unsigned long long n_out = 0;
@@ -516,6 +531,7 @@ kmg_status consolidate(kmg_ctx *c) {
     prm.next = reinterpret_cast<uint32_t *>(d_sync + 1);
     prm.error_flag = reinterpret_cast<uint32_t *>(d_sync + 1) + 1;
     e = cudaMemsetAsync(d_sync, 0, 16, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_hist, 0, (HIST_DENSE_BINS + 1) * sizeof(unsigned long long), c->stream);
     if (e == cudaSuccess && slots) e = launch_table_init(HashTable{d_scratch, slots}, c->stream);
     const size_t tmr = timer_begin(c, 1);
     if (e == cudaSuccess) e = use_smem ? launch_count_partitions_smem(prm, c->stream) : launch_count_partitions(prm, grid, c->stream);
@@ -551,8 +567,36 @@ kmg_status consolidate(kmg_ctx *c) {
   }
   c->result = std::move(out);
   c->has_result = true;
+  c->fused_valid = true;
   c->n_consolidations++;
   return KMG_OK;
+}
+
+// Host copy of the count-of-counts phase B left behind for `result`.  false: not available (no consolidated
+// result, or more than HIST_OVERFLOW_CAP counts >= HIST_DENSE_BINS) -- the caller then runs the table kernels.
+bool fetch_fused_hist(kmg_ctx *c) {
+  if (c->mode != kmg_ctx::MODE_PARTITIONED || !c->has_result || !c->runs.empty() || !c->fused_valid) return false;
+  if (c->fused_cached) return true;
+  c->h_bins.assign(HIST_DENSE_BINS + 1, 0);
+  if (cudaMemcpyAsync(c->h_bins.data(), c->d_hist, (HIST_DENSE_BINS + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+      cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaGetLastError(); c->fused_valid = false; return false; }
+  const uint64_t ov_n = c->h_bins[HIST_DENSE_BINS];
+  if (ov_n > HIST_OVERFLOW_CAP) { c->fused_valid = false; return false; }
+  c->h_ov.resize(ov_n);
+  if (ov_n && cudaMemcpy(c->h_ov.data(), c->d_hist_ov, ov_n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); c->fused_valid = false; return false; }
+  std::sort(c->h_ov.begin(), c->h_ov.end());
+  c->h_bins.resize(HIST_DENSE_BINS);
+  uint64_t others = ov_n, sum = 0, mx = 0;
+  for (uint64_t b = 2; b < (uint64_t)HIST_DENSE_BINS; ++b) if (c->h_bins[b]) { others += c->h_bins[b]; sum += b * c->h_bins[b]; mx = b; }
+  c->h_bins[0] = 0;
+  c->h_bins[1] = c->result.n - others;  // counts of 1 are not recorded by the kernel
+  sum += c->h_bins[1];
+  if (c->h_bins[1] && mx < 1) mx = 1;
+  for (uint64_t v : c->h_ov) sum += v;
+  if (ov_n) mx = c->h_ov.back();
+  c->fused_sum = sum; c->fused_max = mx;
+  c->fused_cached = true;
+  return true;
 }
 
 // Run the counting scan over a packed stream of n_words_total words (already in d_bases/d_valid/d_start).
@@ -718,7 +762,7 @@ KMG_EXPORT void kmg_destroy(kmg_ctx *c) {
   pool_release_idle(c);
   for (auto &kv : c->pool_live) cudaFree(kv.first);
   cudaFree(c->d_part); cudaFree(c->d_fine_cursor);
-  cudaFree(c->table.slots); cudaFree(c->dense); cudaFree(c->d_counters); cudaFree(c->d_stats);
+  cudaFree(c->table.slots); cudaFree(c->dense); cudaFree(c->d_counters); cudaFree(c->d_stats); cudaFree(c->d_hist); cudaFree(c->d_hist_ov);
   cudaFree(c->d_bases); cudaFree(c->d_valid); cudaFree(c->d_start);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   for (auto &s : c->st) {
@@ -808,6 +852,7 @@ KMG_EXPORT kmg_status kmg_reset(kmg_ctx *c) {
     c->runs.clear();
     if (c->has_result) free_run(c, c->result);
     c->has_result = false; c->pending_bytes = 0; c->n_consolidations = 0;
+    c->fused_valid = c->fused_cached = false;
   }
   CU(c, cudaMemsetAsync(c->d_counters, 0, CTR_N * sizeof(unsigned long long), c->stream));
   c->distinct_ub = 0; c->n_records = c->n_bases = c->h2d_bytes = 0;
@@ -1059,10 +1104,13 @@ KMG_EXPORT kmg_status kmg_finalize(kmg_ctx *c, kmg_summary *out) {
   if (c->mode == kmg_ctx::MODE_TABLE) c->distinct_ub = c->h_counters[CTR_DISTINCT];
   if (!out) return KMG_OK;
   memset(out, 0, sizeof *out);
-  CU(c, launch_table_stats(view_of(c), 1, c->d_stats, c->stream));
   unsigned long long h[3];
-  CU(c, cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  if (fetch_fused_hist(c)) { h[0] = c->result.n; h[1] = c->fused_max; h[2] = c->fused_sum; }
+  else {
+    CU(c, launch_table_stats(view_of(c), 1, c->d_stats, c->stream));
+    CU(c, cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
   out->n_records = c->n_records; out->n_bases = c->n_bases;
   out->n_windows = h[2];
   out->n_distinct = h[0]; out->max_count = h[1];
@@ -1080,6 +1128,13 @@ namespace {
 kmg_status count_filtered(kmg_ctx *c, uint64_t min_count, uint64_t *n) {
   CU(c, cudaStreamSynchronize(c->copy_stream));
   if (c->mode == kmg_ctx::MODE_PARTITIONED) { kmg_status s = consolidate(c); if (s != KMG_OK) return s; }
+  if (fetch_fused_hist(c)) {
+    uint64_t m = 0;
+    for (uint64_t b = std::max<uint64_t>(min_count, 1); b < (uint64_t)HIST_DENSE_BINS; ++b) m += c->h_bins[b];
+    m += c->h_ov.end() - std::lower_bound(c->h_ov.begin(), c->h_ov.end(), min_count);
+    *n = m;
+    return KMG_OK;
+  }
   CU(c, launch_table_stats(view_of(c), min_count, c->d_stats, c->stream));
   unsigned long long h[3];
   CU(c, cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -1139,6 +1194,25 @@ KMG_EXPORT kmg_status kmg_histogram(kmg_ctx *c, uint64_t min_count, uint64_t *co
   kmg_status s = read_counters(c);
   if (s != KMG_OK) return s;
   if (c->mode == kmg_ctx::MODE_PARTITIONED && (s = consolidate(c)) != KMG_OK) return s;
+  if (fetch_fused_hist(c)) {  // phase B already built it
+    const uint64_t lo = std::max<uint64_t>(min_count, 1);
+    const auto ov0 = std::lower_bound(c->h_ov.begin(), c->h_ov.end(), min_count);
+    uint64_t n = 0;
+    for (uint64_t b = lo; b < (uint64_t)HIST_DENSE_BINS; ++b) if (c->h_bins[b]) ++n;
+    for (auto it = ov0; it != c->h_ov.end(); ++it) if (it == ov0 || *it != *(it - 1)) ++n;
+    *n_out = n;
+    if (!count_vals || !freqs) return KMG_OK;
+    if (cap < n) return fail(c, KMG_ERR_CAPACITY, "histogram arrays hold " + std::to_string(cap) + " bins, need " + std::to_string(n));
+    uint64_t o = 0;
+    for (uint64_t b = lo; b < (uint64_t)HIST_DENSE_BINS; ++b) if (c->h_bins[b]) { count_vals[o] = b; freqs[o] = c->h_bins[b]; ++o; }
+    for (auto it = ov0; it != c->h_ov.end();) {
+      auto j = it;
+      while (j != c->h_ov.end() && *j == *it) ++j;
+      count_vals[o] = *it; freqs[o] = (uint64_t)(j - it); ++o;
+      it = j;
+    }
+    return KMG_OK;
+  }
   // counts >= HIST_DENSE_BINS: at most (sum of counts) / HIST_DENSE_BINS distinct keys can reach that
   CU(c, launch_table_stats(view_of(c), 1, c->d_stats, c->stream));
   unsigned long long hs[3];

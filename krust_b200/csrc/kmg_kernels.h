@@ -65,6 +65,12 @@ struct CountParams {
   unsigned long long *out_cursor;    // zeroed; ends up = number of distinct keys
   uint64_t *out_seg_start, *out_seg_len;  // n_parts each: where partition p landed in the output
   uint32_t *next, *error_flag;       // zeroed
+  // count-of-counts of the OUTPUT, built while compacting (zeroed by the host; nullptr = skip):
+  // hist[c] for 2 <= c < HIST_DENSE_BINS, hist[HIST_DENSE_BINS] = number of overflow entries;
+  // counts >= HIST_DENSE_BINS are appended to hist_overflow.  hist[1] is implied (distinct - the rest).
+  unsigned long long *hist;
+  uint64_t *hist_overflow;
+  uint64_t hist_overflow_cap;
 };
 
 enum { CTR_WINDOWS = 0, CTR_DISTINCT = 1, CTR_FULL = 2, CTR_SCRATCH = 3, CTR_N = 8 };
@@ -75,6 +81,8 @@ constexpr int DENSE_MAX_K = 14;          // 4^14 u64 = 2 GiB
 constexpr int DENSE_DEFAULT_MAX_K = 13;  // automatic choice of the direct path
 constexpr int HIST_SMEM_BINS = 2048;
 constexpr int HIST_DENSE_BINS = 65536;
+constexpr int HIST_CTA_BINS = 32;        // phase B keeps the lowest bins per CTA in shared memory
+constexpr uint64_t HIST_OVERFLOW_CAP = 1 << 16;
 
 cudaError_t launch_ingest(const uint8_t *d_seq, const uint8_t *d_qual, uint64_t n_bytes, uint32_t thr, uint64_t n_words_total,
                           uint64_t *d_bases, uint32_t *d_valid, cudaStream_t s);

@@ -241,6 +241,32 @@ cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, 
   return cudaGetLastError();
 }
 
+// Count-of-counts while compacting (src/histogram.rs:88-116 computes it from the finished map; here it falls out
+// of phase B for free).  Must be called by all 32 lanes together.  Counts of 1 -- the bulk on most inputs -- are
+// not recorded at all: hist[1] = distinct - everything else.  Equal counts within the warp are merged first, so
+// a popular count value costs one atomic per warp; the lowest bins live in shared memory until the CTA retires.
+__device__ __forceinline__ void hist_note(bool ok, unsigned long long cnt, uint32_t *s_hist, const CountParams &P, int lane) {
+  const bool agg = ok && cnt > 1 && cnt < (unsigned long long)HIST_DENSE_BINS;
+  uint32_t pending = __ballot_sync(0xffffffffu, agg);
+  while (pending) {
+    const int leader = __ffs(pending) - 1;
+    const uint32_t v = __shfl_sync(0xffffffffu, (uint32_t)cnt, leader);
+    const uint32_t same = __ballot_sync(0xffffffffu, agg && (uint32_t)cnt == v);
+    if (lane == leader) {
+      if (v < (uint32_t)HIST_CTA_BINS) atomicAdd(&s_hist[v], (uint32_t)__popc(same));
+      else atomicAdd(P.hist + v, (unsigned long long)__popc(same));
+    }
+    pending &= ~same;
+  }
+  if (ok && cnt >= (unsigned long long)HIST_DENSE_BINS) {
+    const unsigned long long o = atomicAdd(P.hist + HIST_DENSE_BINS, 1ull);
+    if (o < P.hist_overflow_cap) P.hist_overflow[o] = cnt;
+  }
+}
+__device__ __forceinline__ void hist_flush(const uint32_t *s_hist, const CountParams &P, int tid) {
+  if (tid < HIST_CTA_BINS && s_hist[tid]) atomicAdd(P.hist + tid, (unsigned long long)s_hist[tid]);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // phase B: one CTA counts one fine partition at a time in its private scratch table (L2-resident: the whole
 // grid's scratch is ~39 MB), then compacts it into the output run and hands the slots back clean.
@@ -253,9 +279,10 @@ cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, 
 __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partitions_kernel(CountParams P) {
   __shared__ uint64_t seg_begin[CONS_MAX_RUNS];
   __shared__ uint64_t seg_prefix[CONS_MAX_RUNS + 1];
-  __shared__ uint32_t s_work, s_warp[COUNT_THREADS / 32 + 1];
+  __shared__ uint32_t s_work, s_warp[COUNT_THREADS / 32 + 1], s_hist[HIST_CTA_BINS];
   __shared__ unsigned long long s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < HIST_CTA_BINS) s_hist[tid] = 0;
   unsigned long long *table = reinterpret_cast<unsigned long long *>(P.scratch) + (uint64_t)blockIdx.x * (2ull << P.scratch_log2);
   uint32_t next_work = 0;
   if (tid == 0) next_work = atomicAdd(P.next, 1u);
@@ -391,16 +418,20 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
     __syncthreads();
     uint64_t o = out0 + s_warp[warp] + (incl - mine);
     const ulonglong2 *tab2 = reinterpret_cast<const ulonglong2 *>(table);
-    for (uint64_t i = tid; i <= mask; i += COUNT_THREADS) {
+    for (uint64_t i = tid; i <= mask; i += COUNT_THREADS) {  // trip count is warp-uniform (mask + 1 is a multiple of 256)
       const ulonglong2 sl = __ldcg(tab2 + i);
-      if (sl.x == EMPTY_KEY) continue;
-      __stcs(P.out_keys + o, sl.x);
-      __stcs(P.out_counts + o, sl.y + 1);  // slots store occurrences - 1
-      ++o;
-      reinterpret_cast<ulonglong2 *>(table)[i] = make_ulonglong2(EMPTY_KEY, 0ull);
+      const bool used = sl.x != EMPTY_KEY;
+      if (used) {
+        __stcs(P.out_keys + o, sl.x);
+        __stcs(P.out_counts + o, sl.y + 1);  // slots store occurrences - 1
+        ++o;
+        reinterpret_cast<ulonglong2 *>(table)[i] = make_ulonglong2(EMPTY_KEY, 0ull);
+      }
+      if (P.hist) hist_note(used, sl.y + 1, s_hist, P, lane);
     }
     __syncthreads();  // table clean (same-CTA visibility) before the next partition's upserts
   }
+  if (P.hist) hist_flush(s_hist, P, tid);
 }
 
 
@@ -421,10 +452,11 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
   __shared__ uint32_t s_list_n;
   __shared__ uint64_t seg_begin[CONS_MAX_RUNS];
   __shared__ uint64_t seg_prefix[CONS_MAX_RUNS + 1];
-  __shared__ uint32_t s_work;
+  __shared__ uint32_t s_work, s_hist[HIST_CTA_BINS];
   __shared__ unsigned long long s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t SLOTS = SMEM_TABLE_SLOTS;
+  if (tid < HIST_CTA_BINS) s_hist[tid] = 0;
   for (uint32_t i = tid; i < SLOTS; i += SMEM_COUNT_THREADS) { skeys[i] = EMPTY_KEY; scnt[i] = 0; }
   uint32_t next_work = 0;
   if (tid == 0) { next_work = atomicAdd(P.next, 1u); s_list_n = 0; }
@@ -553,16 +585,24 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
     {
       const unsigned long long out0 = s_base;
       const uint32_t d = s_list_n;
-      for (uint32_t i = tid; i < d; i += SMEM_COUNT_THREADS) {
-        const uint32_t slot = slist[i];
-        __stcs(P.out_keys + out0 + i, (uint64_t)skeys[slot]);
-        __stcs(P.out_counts + out0 + i, (uint64_t)scnt[slot] + 1);  // slots store occurrences - 1
-        skeys[slot] = EMPTY_KEY; scnt[slot] = 0;
+      for (uint32_t i0 = 0; i0 < d; i0 += SMEM_COUNT_THREADS) {
+        const uint32_t i = i0 + tid;
+        const bool ok = i < d;
+        unsigned long long cnt = 0;
+        if (ok) {
+          const uint32_t slot = slist[i];
+          cnt = (unsigned long long)scnt[slot] + 1;  // slots store occurrences - 1
+          __stcs(P.out_keys + out0 + i, (uint64_t)skeys[slot]);
+          __stcs(P.out_counts + out0 + i, (uint64_t)cnt);
+          skeys[slot] = EMPTY_KEY; scnt[slot] = 0;
+        }
+        if (P.hist) hist_note(ok, cnt, s_hist, P, lane);
       }
     }
     __syncthreads();  // table clean before the next partition
     if (tid == 0) s_list_n = 0;
   }
+  if (P.hist) hist_flush(s_hist, P, tid);
 }
 
 cudaError_t launch_count_partitions_smem(const CountParams &P, cudaStream_t s) {
