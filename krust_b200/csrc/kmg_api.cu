@@ -25,7 +25,8 @@ thread_local std::string g_create_error;
 constexpr double LOAD_TARGET = 0.60;  // sizing goal when memory allows
 constexpr double LOAD_SOFT = 0.70;    // grow after a batch if exceeded and memory allows
 constexpr double LOAD_HARD = 0.90;    // never start a batch that could exceed this
-constexpr uint64_t DEFAULT_BATCH_BASES = 1ull << 30;  // per staging slot; every batch becomes one run of the partitioned pipeline
+constexpr uint64_t DEFAULT_BATCH_BASES = 1ull << 28;  // per staging slot; every batch becomes one run of the partitioned pipeline
+constexpr int N_STAGE = 4;                             // ASCII staging ring: copies run up to 3 chunks ahead of the kernels
 constexpr uint64_t MIN_TABLE_SLOTS = 1ull << 16;
 
 struct Staging {
@@ -77,10 +78,11 @@ struct kmg_ctx {
   uint64_t packed_words = 0;  // capacity in words (excluding lead-in)
 
   uint64_t batch_bases = DEFAULT_BATCH_BASES;
-  Staging st[2];
+  Staging st[N_STAGE];  // the pre-packed feed uses slots 0 and 1 only
   bool staging_ready = false, packed_feed_ready = false;
   uint64_t staging_cap = 0;
-  uint32_t next_slot = 0;
+  uint32_t next_slot = 0;    // pre-packed feed (0/1)
+  uint32_t next_ascii = 0;   // ASCII staging ring
 
   // partitioned pipeline (v2)
   enum Mode { MODE_UNDECIDED, MODE_DENSE, MODE_TABLE, MODE_PARTITIONED } mode = MODE_UNDECIDED;
@@ -88,6 +90,8 @@ struct kmg_ctx {
   std::vector<Run> runs;      // pending, not yet consolidated
   Run result;                 // consolidated (key, count) run
   bool has_result = false;
+  void *d_scan_tmp = nullptr;                // CUB scan scratch for n_parts items (n_parts is fixed once the mode is decided)
+  size_t scan_tmp_bytes = 0;
   // count-of-counts of `result`, produced by phase B itself (consolidate)
   unsigned long long *d_hist = nullptr;      // HIST_DENSE_BINS bins + overflow counter
   uint64_t *d_hist_ov = nullptr;             // HIST_OVERFLOW_CAP counts >= HIST_DENSE_BINS
@@ -380,7 +384,11 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   rp.fine_start = reinterpret_cast<const unsigned long long *>(r.d_seg_start);
   rp.fine_cursor = c->d_fine_cursor;
   e = launch_refine(rp, false, c->stream);
-  if (e == cudaSuccess) e = exclusive_sum_u64(r.d_seg_len, r.d_seg_start, P, c->stream);
+  if (e == cudaSuccess && !c->d_scan_tmp) {
+    e = exclusive_sum_u64(nullptr, nullptr, P, nullptr, &c->scan_tmp_bytes, c->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_scan_tmp, c->scan_tmp_bytes ? c->scan_tmp_bytes : 16);
+  }
+  if (e == cudaSuccess) e = exclusive_sum_u64(r.d_seg_len, r.d_seg_start, P, c->d_scan_tmp, &c->scan_tmp_bytes, c->stream);
   if (e != cudaSuccess) { cleanup(); free_run(c, r); return cuda_fail(c, e, "refine count"); }
   kmg_status s = alloc_or_consolidate(c, reinterpret_cast<void **>(&r.d_keys), n * 8, "fine keys");
   if (s == KMG_OK && d_ccounts) s = alloc_or_consolidate(c, reinterpret_cast<void **>(&r.d_counts), n * 8, "fine counts");
@@ -643,14 +651,13 @@ kmg_status count_device_chunk(kmg_ctx *c, const uint8_t *d_seq, const uint8_t *d
   return scan_packed(c, n_words_total, has_start);
 }
 
-kmg_status ensure_staging(kmg_ctx *c, bool need_pinned, uint64_t need_bytes) {
+kmg_status ensure_staging(kmg_ctx *c, bool need_pinned, bool need_qual, uint64_t need_bytes) {
   // staging slots are sized for the largest chunk seen so far (at most batch_bases), not for batch_bases up front
   const uint64_t want = std::min<uint64_t>(c->batch_bases, std::max<uint64_t>(need_bytes, 1u << 20)) + 64;
   if (want > c->staging_cap) {
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaStreamSynchronize(c->copy_stream));
-    for (int i = 0; i < 2; ++i) {
-      Staging &s = c->st[i];
+    for (auto &s : c->st) {
       cudaFree(s.d_seq); cudaFree(s.d_qual); s.d_seq = s.d_qual = nullptr;
       if (s.h_seq) cudaFreeHost(s.h_seq);
       if (s.h_qual) cudaFreeHost(s.h_qual);
@@ -659,20 +666,15 @@ kmg_status ensure_staging(kmg_ctx *c, bool need_pinned, uint64_t need_bytes) {
     }
     c->staging_cap = want;
   }
-  for (int i = 0; i < 2; ++i) {
-    Staging &s = c->st[i];
-    if (!s.d_seq) {
-      CU(c, cudaMalloc(&s.d_seq, c->staging_cap));
-      CU(c, cudaMalloc(&s.d_qual, c->staging_cap));
-    }
+  for (auto &s : c->st) {
+    if (!s.d_seq) CU(c, cudaMalloc(&s.d_seq, c->staging_cap));
+    if (need_qual && !s.d_qual) CU(c, cudaMalloc(&s.d_qual, c->staging_cap));
     if (!s.h2d_done) {
       CU(c, cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
       CU(c, cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
     }
-    if (need_pinned && !s.h_seq) {
-      CU(c, cudaHostAlloc(&s.h_seq, c->staging_cap, cudaHostAllocDefault));
-      CU(c, cudaHostAlloc(&s.h_qual, c->staging_cap, cudaHostAllocDefault));
-    }
+    if (need_pinned && !s.h_seq) CU(c, cudaHostAlloc(&s.h_seq, c->staging_cap, cudaHostAllocDefault));
+    if (need_pinned && need_qual && !s.h_qual) CU(c, cudaHostAlloc(&s.h_qual, c->staging_cap, cudaHostAllocDefault));
   }
   c->staging_ready = true;
   return KMG_OK;
@@ -762,7 +764,7 @@ KMG_EXPORT void kmg_destroy(kmg_ctx *c) {
   pool_release_idle(c);
   for (auto &kv : c->pool_live) cudaFree(kv.first);
   cudaFree(c->d_part); cudaFree(c->d_fine_cursor);
-  cudaFree(c->table.slots); cudaFree(c->dense); cudaFree(c->d_counters); cudaFree(c->d_stats); cudaFree(c->d_hist); cudaFree(c->d_hist_ov);
+  cudaFree(c->table.slots); cudaFree(c->dense); cudaFree(c->d_counters); cudaFree(c->d_stats); cudaFree(c->d_hist); cudaFree(c->d_hist_ov); cudaFree(c->d_scan_tmp);
   cudaFree(c->d_bases); cudaFree(c->d_valid); cudaFree(c->d_start);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   for (auto &s : c->st) {
@@ -888,7 +890,7 @@ KMG_EXPORT kmg_status kmg_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint
   const uint64_t begin = offsets[0], end = offsets[n_records];
   const bool use_q = c->cfg.has_min_quality && qual != nullptr;
   const bool src_pinned = is_pinned_host(seq + begin) && (!use_q || is_pinned_host(qual + begin));
-  kmg_status s = ensure_staging(c, !src_pinned, end - begin);
+  kmg_status s = ensure_staging(c, !src_pinned, use_q, end - begin);
   if (s != KMG_OK) return s;
   const uint64_t K1 = (uint64_t)c->k - 1;
   const uint64_t B = c->batch_bases;  // bytes per chunk including the k-1 overlap
@@ -929,11 +931,14 @@ KMG_EXPORT kmg_status kmg_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint
     st.h2d_pending = true;
     return KMG_OK;
   };
-  const uint32_t slot0 = c->next_slot;
-  if (!chunks.empty() && (s = stage_chunk(chunks[0], c->st[slot0])) != KMG_OK) return s;
+  // ring of N_STAGE slots: chunk i lives in slot (slot0 + i) % N_STAGE, and chunks i+1 .. i+N_STAGE-1 are already
+  // queued on the copy stream while chunk i is processed (slot reuse waits for the previous user's compute_done)
+  const uint32_t slot0 = c->next_ascii;
+  size_t staged = 0;
   for (size_t i = 0; i < chunks.size(); ++i) {
-    Staging &st = c->st[(slot0 + i) & 1];
-    if (i + 1 < chunks.size() && (s = stage_chunk(chunks[i + 1], c->st[(slot0 + i + 1) & 1])) != KMG_OK) return s;
+    for (; staged < chunks.size() && staged < i + N_STAGE; ++staged)
+      if ((s = stage_chunk(chunks[staged], c->st[(slot0 + staged) % N_STAGE])) != KMG_OK) return s;
+    Staging &st = c->st[(slot0 + i) % N_STAGE];
     const Chunk &ch = chunks[i];
     CU(c, cudaStreamWaitEvent(c->stream, st.h2d_done, 0));
     s = count_device_chunk(c, st.d_seq, use_q ? st.d_qual : nullptr, ch.nrec ? st.d_off : nullptr, ch.nrec, ch.pos, ch.len);
@@ -941,7 +946,7 @@ KMG_EXPORT kmg_status kmg_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint
     CU(c, cudaEventRecord(st.compute_done, c->stream));
     st.compute_pending = true;
   }
-  c->next_slot = (slot0 + (uint32_t)chunks.size()) & 1;
+  c->next_ascii = (slot0 + (uint32_t)chunks.size()) % N_STAGE;
   c->n_records += n_records; c->n_bases += end - begin;
   return KMG_OK;
 }
@@ -951,7 +956,8 @@ KMG_EXPORT kmg_status kmg_acquire_batch(kmg_ctx *c, kmg_batch *b) {
   CU(c, cudaSetDevice(c->device));
   const uint64_t words = round_up((c->batch_bases + 31) / 32, TILE_WORDS);
   if (!c->packed_feed_ready) {
-    for (auto &s : c->st) {
+    for (int i = 0; i < 2; ++i) {
+      Staging &s = c->st[i];
       CU(c, cudaHostAlloc(&s.hp_bases, words * 8, cudaHostAllocDefault));
       CU(c, cudaHostAlloc(&s.hp_valid, words * 4, cudaHostAllocDefault));
       CU(c, cudaHostAlloc(&s.hp_start, words * 4, cudaHostAllocDefault));

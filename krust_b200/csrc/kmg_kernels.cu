@@ -961,17 +961,11 @@ cudaError_t sort_pairs(uint64_t *d_keys, uint64_t *d_counts, uint64_t n, int key
 }
 
 
-// exclusive prefix sum of per-partition sizes (library scan, bookkeeping only)
-cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, cudaStream_t s) {
+// exclusive prefix sum of per-partition sizes (library scan, bookkeeping only); scratch comes from the caller
+cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, void *tmp, size_t *tmp_bytes, cudaStream_t s) {
+  if (!tmp) { *tmp_bytes = 0; return cub::DeviceScan::ExclusiveSum(nullptr, *tmp_bytes, d_in, d_out, n ? n : 1, s); }
   if (n == 0) return cudaSuccess;
-  void *tmp = nullptr;
-  size_t bytes = 0;
-  cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, bytes, d_in, d_out, n, s);
-  if (e == cudaSuccess) e = cudaMalloc(&tmp, bytes ? bytes : 1);
-  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, bytes, d_in, d_out, n, s);
-  cudaError_t e2 = cudaStreamSynchronize(s);
-  cudaFree(tmp);
-  return e != cudaSuccess ? e : e2;
+  return cub::DeviceScan::ExclusiveSum(tmp, *tmp_bytes, d_in, d_out, n, s);
 }
 
 }  // namespace kmg

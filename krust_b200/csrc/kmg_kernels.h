@@ -29,7 +29,7 @@ struct TableView {
 };
 
 // ---- partitioned pipeline (kmg_partition.cu) ----------------------------------------------------------
-constexpr int CONS_MAX_RUNS = 16;
+constexpr int CONS_MAX_RUNS = 32;  // one warp scans the segment table of a partition
 constexpr int MAX_PARTS = 8192;        // bins of ONE scatter level (shared-memory histogram)
 constexpr int REFINE_THREADS = 512;
 constexpr int REFINE_TILE = 8192;      // keys per level-2 tile (staged in shared memory: 64 KiB, 128 KiB with counts)
@@ -104,7 +104,8 @@ cudaError_t launch_refine(const RefineParams &P, bool scatter, cudaStream_t s);
 cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, cudaStream_t s);
 cudaError_t launch_count_partitions(const CountParams &P, unsigned grid, cudaStream_t s);
 cudaError_t launch_count_partitions_smem(const CountParams &P, cudaStream_t s);
-cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, cudaStream_t s);
+// tmp == nullptr: returns the scratch size needed for n items in *tmp_bytes.  Asynchronous on s.
+cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, void *tmp, size_t *tmp_bytes, cudaStream_t s);
 int num_sms();
 void set_debug(uint32_t v);  // ablation switches (tools/ablate.py)
 cudaError_t launch_table_init(HashTable t, cudaStream_t s);

@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
     // ---- upsert all entries of partition p
     constexpr int G = 4;
     uint32_t new_keys = 0;
+    uint32_t r = 0;  // run holding the thread's current entry: entries are visited in ascending order
 #pragma unroll 1
     for (uint64_t base = 0; base < n_p; base += (uint64_t)COUNT_THREADS * G) {
       uint64_t key[G], w[G], slot[G], cur[G];
@@ -331,7 +332,6 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
         const uint64_t idx = base + (uint64_t)j * COUNT_THREADS + tid;
         w[j] = 0; key[j] = EMPTY_KEY;
         if (idx < n_p) {
-          uint32_t r = 0;
           while (r + 1 < P.R && idx >= seg_prefix[r + 1]) ++r;
           const uint64_t src = seg_begin[r] + (idx - seg_prefix[r]);
           key[j] = __ldcs(P.runs[r].keys + src);
@@ -496,6 +496,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
     // 8 keys per thread are loaded up front (one exposed global-load latency per 4096 entries instead of two),
     // then upserted in two batches of 4 whose first probes are in flight together.
     constexpr int G = 8, H = 4;
+    uint32_t r = 0;  // run holding the thread's current entry: entries are visited in ascending order
 #pragma unroll 1
     for (uint64_t base = 0; base < n_p; base += (uint64_t)SMEM_COUNT_THREADS * G) {
       uint64_t key[G];
@@ -505,7 +506,6 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
         const uint64_t idx = base + (uint64_t)j * SMEM_COUNT_THREADS + tid;
         w[j] = 0; key[j] = EMPTY_KEY;
         if (idx < n_p) {
-          uint32_t r = 0;
           while (r + 1 < P.R && idx >= seg_prefix[r + 1]) ++r;
           const uint64_t src = seg_begin[r] + (idx - seg_prefix[r]);
           key[j] = __ldcs(P.runs[r].keys + src);

@@ -81,7 +81,7 @@ def test_chunked_feed_equals_single_shot(k):
     for bb in (4096, 10_000):
         gpu = gpu_count(k, recs, quals, 20, _lib.KMG_FLAG_FORCE_HASH, batch_bases=bb)
         assert_same(gpu, oracle)
-        # partitioned pipeline: every chunk becomes a run; > 15 runs force intermediate consolidations (result + runs merge)
+        # partitioned pipeline: every chunk becomes a run; > 31 runs force intermediate consolidations (result + runs merge)
         gpu = gpu_count(k, recs, quals, 20, PART, batch_bases=bb, parts_log2=5)
         assert_same(gpu, oracle)
         assert gpu[2]["path"] == 2 and gpu[2]["n_grows"] >= 1 and gpu[2]["n_windows"] == oracle[2]
