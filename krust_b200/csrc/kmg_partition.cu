@@ -529,46 +529,75 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
           }
         }
       }
+      // First probes of all G keys, H at a time in flight; whatever collides is left in `pend`.
+      uint32_t pend = 0, newm = 0;  // bit j: key j still to place / key j claimed a fresh slot
+      uint64_t fs_lo = 0, fs_hi = 0;  // slot of key j, 16 bits each (keys 0-3 / 4-7), meaningful for the keys in newm
 #pragma unroll
       for (int h0 = 0; h0 < G; h0 += H) {
         uint32_t sl[H];
         unsigned long long cur[H];
 #pragma unroll
-        for (int j = 0; j < H; ++j) { sl[j] = (uint32_t)mix64(key[h0 + j]) & mask; cur[j] = w[h0 + j] ? skeys[sl[j]] : 0ull; }  // H probes in flight
+        for (int j = 0; j < H; ++j) { sl[j] = (uint32_t)mix64(key[h0 + j]) & mask; cur[j] = w[h0 + j] ? skeys[sl[j]] : 0ull; }
 #pragma unroll
         for (int j = 0; j < H; ++j) if (w[h0 + j] && cur[j] == EMPTY_KEY) cur[j] = atomicCAS(&skeys[sl[j]], EMPTY_KEY, key[h0 + j]);
 #pragma unroll
         for (int j = 0; j < H; ++j) {
           const uint32_t wj = w[h0 + j];
-          bool is_new = false;
-          uint32_t fslot = 0;
-          if (wj) {
-            const uint64_t kj = key[h0 + j];
-            unsigned long long c2 = cur[j];
-            uint32_t s2 = sl[j];
-            for (uint32_t tries = 0;; ++tries) {  // linear probing in shared memory: a step is tens of cycles
-              if (c2 == EMPTY_KEY || c2 == kj) {
-                is_new = c2 == EMPTY_KEY;
-                fslot = s2;
-                const uint32_t add = wj - (is_new ? 1u : 0u);  // slots store occurrences - 1
-                if (add) { const uint32_t old = atomicAdd(&scnt[s2], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
-                break;
-              }
-              if (tries > mask) { atomicExch(P.error_flag, 1u); break; }
-              s2 = (s2 + 1) & mask;
-              c2 = skeys[s2];
-              if (c2 == EMPTY_KEY) c2 = atomicCAS(&skeys[s2], EMPTY_KEY, kj);
-            }
+          if (!wj) continue;
+          const bool is_new = cur[j] == EMPTY_KEY;
+          if (is_new || cur[j] == key[h0 + j]) {
+            const uint32_t add = wj - (is_new ? 1u : 0u);  // slots store occurrences - 1
+            if (add) { const uint32_t old = atomicAdd(&scnt[sl[j]], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
+            if (is_new) { newm |= 1u << (h0 + j); (h0 + j < 4 ? fs_lo : fs_hi) |= (uint64_t)sl[j] << (16 * ((h0 + j) & 3)); }
+          } else pend |= 1u << (h0 + j);
+        }
+      }
+      // Collisions: every lane works through ITS pending keys on its own (no warp-wide rendezvous per key, so the
+      // warp runs for the longest per-lane total, not for the sum of the per-key maxima).  Double hashing -- an odd
+      // stride from the high mix bits -- keeps the chains short; lookups only ever happen through this same sequence.
+      while (pend) {
+        const int j = __ffs(pend) - 1;
+        uint64_t kj = key[0];
+        uint32_t wj = w[0];
+#pragma unroll
+        for (int q = 1; q < G; ++q) if (j == q) { kj = key[q]; wj = w[q]; }
+        const uint64_t m = mix64(kj);
+        const uint32_t step = (uint32_t)(m >> 40) | 1u;
+        uint32_t s2 = (uint32_t)m & mask;
+        unsigned long long c2;
+        for (uint32_t tries = 0;; ++tries) {
+          s2 = (s2 + step) & mask;
+          c2 = skeys[s2];
+          if (c2 == EMPTY_KEY) c2 = atomicCAS(&skeys[s2], EMPTY_KEY, kj);
+          if (c2 == EMPTY_KEY || c2 == kj) break;
+          if (tries > mask) { atomicExch(P.error_flag, 1u); break; }  // table full: the host re-runs with the L2 variant
+        }
+        const bool is_new = c2 == EMPTY_KEY;
+        if (is_new || c2 == kj) {
+          const uint32_t add = wj - (is_new ? 1u : 0u);
+          if (add) { const uint32_t old = atomicAdd(&scnt[s2], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
+          if (is_new) {
+            newm |= 1u << j;
+            const uint64_t f = (uint64_t)s2 << (16 * (j & 3));
+            if (j < 4) fs_lo |= f; else fs_hi |= f;
           }
-          // remember which slots this partition claimed (warp-aggregated append): compaction then visits only those
-          const uint32_t nm = __ballot_sync(0xffffffffu, is_new);
-          if (nm) {
-            const int leader = __ffs(nm) - 1;
-            uint32_t lb = 0;
-            if (lane == leader) lb = atomicAdd(&s_list_n, (uint32_t)__popc(nm));
-            lb = __shfl_sync(0xffffffffu, lb, leader);
-            if (is_new) slist[lb + __popc(nm & ((1u << lane) - 1u))] = (uint16_t)fslot;
-          }
+        }
+        pend &= pend - 1;
+      }
+      // remember which slots this partition claimed -- ONE warp-aggregated append per batch; compaction visits only those
+      {
+        const uint32_t mine = (uint32_t)__popc(newm);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {  // warp-uniform
+          uint32_t lb = 0;
+          if (lane == 31) lb = atomicAdd(&s_list_n, total);
+          lb = __shfl_sync(0xffffffffu, lb, 31) + incl - mine;
+#pragma unroll
+          for (int q = 0; q < G; ++q)
+            if (newm >> q & 1u) slist[lb++] = (uint16_t)((q < 4 ? fs_lo : fs_hi) >> (16 * (q & 3)));
         }
       }
     }

@@ -34,8 +34,10 @@ torch.cuda.synchronize()
 print(f"H2D 1 GiB pinned: {(1 << 30) / (time.perf_counter() - t0) / 1e9:.1f} GB/s", flush=True)
 del d_tmp
 
+import os
+STREAM = int(os.environ.get("PROBE_STREAM", "0")) or None   # 1 = the legacy default stream (what torch hands out)
 for bb in [int(x) for x in (sys.argv[1:] or ["1073741824", "536870912", "268435456", "134217728"])]:
-    eng = kb.GpuKmerCounter(k, device=0, expected_distinct=int(exp * 1.03), batch_bases=bb)
+    eng = kb.GpuKmerCounter(k, device=0, expected_distinct=int(exp * 1.03), batch_bases=bb, stream=STREAM)
     best = None
     for it in range(4):
         eng.reset()
