@@ -90,6 +90,7 @@ struct kmg_ctx {
   std::vector<Run> runs;      // pending, not yet consolidated
   Run result;                 // consolidated (key, count) run
   bool has_result = false;
+  size_t total_mem = 0;                      // device memory size (cudaMemGetInfo is slow; asked once)
   void *d_scan_tmp = nullptr;                // CUB scan scratch for n_parts items (n_parts is fixed once the mode is decided)
   size_t scan_tmp_bytes = 0;
   // count-of-counts of `result`, produced by phase B itself (consolidate)
@@ -336,8 +337,8 @@ kmg_status add_run(kmg_ctx *c, Run &&r) {
   if (r.n == 0) { free_run(c, r); return KMG_OK; }
   c->pending_bytes += r.n * (r.d_counts ? 16 : 8);
   c->runs.push_back(std::move(r));
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
+  if (!c->total_mem) { size_t free_b = 0; cudaMemGetInfo(&free_b, &c->total_mem); }
+  const size_t total_b = c->total_mem;
   // consolidate early when the pending runs get numerous or large (keeps streaming inputs bounded in memory)
   if (c->runs.size() + (c->has_result ? 1 : 0) >= (size_t)CONS_MAX_RUNS - 1 || c->pending_bytes > (uint64_t)total_b * 35 / 100)
     return consolidate(c);
@@ -357,7 +358,11 @@ kmg_status alloc_or_consolidate(kmg_ctx *c, void **p, size_t bytes, const char *
 }
 
 // A2: coarse-partitioned keys (+counts) -> fine-partitioned run.  Takes ownership of the coarse buffers when `owns`.
-kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, const std::vector<uint64_t> &coarse_off, bool owns = true) {
+// `sync`: wait for the scatter before returning (needed when the input belongs to the caller).  Without it the coarse
+// buffers go back to the pool while the kernels are still queued, which is safe because every pool block is only ever
+// touched by work on c->stream (stream-ordered reuse).
+kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, const std::vector<uint64_t> &coarse_off, bool owns = true,
+                         bool sync = true) {
   const uint32_t P1 = c->n_coarse, P = c->n_parts;
   const uint64_t n = coarse_off[P1];
   Run r;
@@ -395,7 +400,7 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   if (s != KMG_OK) { cleanup(); free_run(c, r); return s; }
   rp.out_keys = r.d_keys; rp.out_counts = r.d_counts;
   e = launch_refine(rp, true, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess && sync) e = cudaStreamSynchronize(c->stream);
   cleanup();
   if (e != cudaSuccess) { free_run(c, r); return cuda_fail(c, e, "refine scatter"); }
   r.n = n;
@@ -430,7 +435,7 @@ kmg_status scan_to_run(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
     if (s != KMG_OK) return s;
     CU(c, cudaMemcpyAsync(d_start, off.data(), P1 * 8, cudaMemcpyHostToDevice, c->stream));
     CU(c, launch_scan_partition(in, P1, true, d_cnt, d_start, d_cur, d_ckeys, c->d_counters, c->stream));
-    s = refine_to_run(c, d_ckeys, nullptr, off);
+    s = refine_to_run(c, d_ckeys, nullptr, off, /*owns=*/true, /*sync=*/false);  // input is the context's own packed stream
     timer_end(c, tmr);
     if (s != KMG_OK) return s;
   }

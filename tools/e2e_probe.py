@@ -58,3 +58,30 @@ for bb in [int(x) for x in (sys.argv[1:] or ["1073741824", "536870912", "2684354
           f"  | scan_ms {bs.get('scan_ns', 0)/1e6:.1f} cons_ms {bs.get('consolidate_ns', 0)/1e6:.1f} kernel_ms {bs.get('kernel_ns', 0)/1e6:.1f}"
           f" grows {bs.get('n_grows')} -> {exp / best[0] / 1e9:.2f} G/s", flush=True)
     eng.close()
+
+if os.environ.get("PROBE_BENCHLIKE"):
+    # what bench.py does: device-resident steps first, then host-buffer steps on the SAME engine (pool holds the big blocks)
+    from krust_b200.dist import GpuShardEngine
+    d_seq = torch.empty(total + 64, dtype=torch.uint8, device=dev)[:total]
+    d_seq.copy_(h_seq)
+    d_off = torch.from_numpy(offsets_np.astype(np.int64)).to(dev)
+    engine = GpuShardEngine(k, dev, expected_distinct=int(exp * 1.03) + 1024)
+    for it in range(3):
+        engine.reset()
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        engine.count_local(d_seq, d_off)
+        engine.finalize(False)
+        torch.cuda.synchronize()
+        print(f"device step {it}: {(time.perf_counter() - t0) * 1e3:.1f} ms", flush=True)
+    for it in range(5):
+        t0 = time.perf_counter()
+        engine.reset()
+        t1 = time.perf_counter()
+        engine.counter.count_batch(h_np, None, offsets_np)
+        t2 = time.perf_counter()
+        engine.finalize(False)
+        t3 = time.perf_counter()
+        engine.histogram(1)
+        t4 = time.perf_counter()
+        free_b, total_b = torch.cuda.mem_get_info()
+        print(f"host step {it}: reset {(t1-t0)*1e3:.1f} count {(t2-t1)*1e3:.1f} finalize {(t3-t2)*1e3:.1f} hist {(t4-t3)*1e3:.1f} ms; free {free_b/2**30:.1f} GiB", flush=True)
