@@ -318,7 +318,9 @@ kmg_status decide_mode(kmg_ctx *c, uint64_t first_call_windows) {
     c->n_coarse = 1u << (lg / 2);
     c->n_sub = 1u << (lg - lg / 2);
   } else {
-    const uint64_t want = std::max<uint64_t>(4, (hint + TARGET_KEYS_PER_PART - 1) / TARGET_KEYS_PER_PART);
+    uint64_t target = TARGET_KEYS_PER_PART;
+    if (const char *t = getenv("KMG_TARGET_KEYS")) target = std::max<uint64_t>(256, strtoull(t, nullptr, 10));  // tuning experiments only
+    const uint64_t want = std::max<uint64_t>(4, (hint + target - 1) / target);
     uint64_t p1 = 1;
     while (p1 * p1 < want) ++p1;
     p1 = std::min<uint64_t>(p1, 2048);
@@ -498,7 +500,9 @@ kmg_status consolidate(kmg_ctx *c) {
   if (e != cudaSuccess) { pool_free(c, d_order); return cuda_fail(c, e, "consolidate setup"); }
   std::vector<uint32_t> order;
   order.reserve(P);
+  uint64_t max_total = 0;
   {
+    for (uint32_t p = 0; p < P; ++p) max_total = std::max<uint64_t>(max_total, totals[p]);
     const uint64_t heavy = 8 * std::max<uint64_t>(total / P, 1024);
     std::vector<uint32_t> big;
     for (uint32_t p = 0; p < P; ++p) if (totals[p] > heavy) big.push_back(p);
@@ -547,7 +551,9 @@ kmg_status consolidate(kmg_ctx *c) {
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_hist, 0, (HIST_DENSE_BINS + 1) * sizeof(unsigned long long), c->stream);
     if (e == cudaSuccess && slots) e = launch_table_init(HashTable{d_scratch, slots}, c->stream);
     const size_t tmr = timer_begin(c, 1);
-    if (e == cudaSuccess) e = use_smem ? launch_count_partitions_smem(prm, c->stream) : launch_count_partitions(prm, grid, c->stream);
+    bool weighted = max_total > 2ull * SMEM_COUNT_THREADS * 8;  // oversized partitions want the pre-aggregating variant
+    for (uint32_t r = 0; r < R; ++r) weighted |= in[r]->d_counts != nullptr;
+    if (e == cudaSuccess) e = use_smem ? launch_count_partitions_smem(prm, weighted, c->stream) : launch_count_partitions(prm, grid, c->stream);
     timer_end(c, tmr);
     unsigned long long h_sync[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 16, cudaMemcpyDeviceToHost, c->stream);

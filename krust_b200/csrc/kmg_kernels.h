@@ -103,7 +103,8 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
 cudaError_t launch_refine(const RefineParams &P, bool scatter, cudaStream_t s);
 cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, cudaStream_t s);
 cudaError_t launch_count_partitions(const CountParams &P, unsigned grid, cudaStream_t s);
-cudaError_t launch_count_partitions_smem(const CountParams &P, cudaStream_t s);
+// weighted: some input run carries counts, or a partition is large enough to want run-length pre-aggregation
+cudaError_t launch_count_partitions_smem(const CountParams &P, bool weighted, cudaStream_t s);
 // tmp == nullptr: returns the scratch size needed for n items in *tmp_bytes.  Asynchronous on s.
 cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, void *tmp, size_t *tmp_bytes, cudaStream_t s);
 int num_sms();

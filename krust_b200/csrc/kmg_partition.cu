@@ -436,30 +436,40 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
 
 
 // ---------------------------------------------------------------------------------------------------
-// phase B, primary variant: the partition's table lives in SHARED memory.  A probe step then costs tens
-// of cycles instead of an L2 round trip, which is what gated the L2-scratch variant above (its CTA-wide
-// time per partition was set by the longest probe chain).  Layout: SoA, 8192 x u64 keys + 8192 x u32
-// (occurrences - 1) = 96 KiB, so TWO 512-thread CTAs fit per SM and one CTA's latency bubbles (metadata,
-// key loads, output reservation) overlap with the other's work.  Output is compacted per warp (ballot +
-// popc) so that a warp writes one contiguous run.
-// If a partition holds more distinct keys than the table, or a count does not fit 32 bits, error_flag is
-// raised and the host re-runs phase B with the L2-scratch variant (u64 counts, larger tables).
+// phase B, primary variant: the partition's table lives in SHARED memory.  The kernel is instruction-issue
+// bound (profiles/), so everything here is about warp-instructions per key:
+//  * layout: SoA, 8192 x u64 keys + 8192 x u32 (occurrences - 1) + 8192 x u16 claimed-slot lists = 112 KiB, so
+//    TWO 512-thread CTAs fit per SM and one CTA's bubbles (metadata, key loads, output reservation) overlap
+//    with the other's work;
+//  * a key's home is a BUCKET of two adjacent slots read with one 16-byte load; all first probes of a batch
+//    of 8 keys per thread are issued together (4 at a time in flight);
+//  * the few keys whose bucket is taken are then finished lane by lane (no warp-wide rendezvous per key), walking
+//    further buckets with an odd stride taken from the high mix bits (double hashing: short chains);
+//  * every warp lists the slots IT claimed (ballot + popc, no atomics); compaction walks those lists, so it
+//    touches only occupied slots, writes coalesced output and leaves the table clean;
+//  * WEIGHTED = false (no input run carries counts, no oversized partition): no per-key weights in registers.
+// If a partition holds more distinct keys than the table, a warp claims more than its list holds, or a count does
+// not fit 32 bits, error_flag is raised and the host re-runs phase B with the L2-scratch variant.
 // ---------------------------------------------------------------------------------------------------
+template <bool WEIGHTED>
 __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_kernel(CountParams P) {
-  extern __shared__ __align__(16) unsigned long long skeys[];  // SMEM_TABLE_SLOTS keys, u32 counts, u16 occupied-slot list
-  uint32_t *scnt = reinterpret_cast<uint32_t *>(skeys + SMEM_TABLE_SLOTS);
-  uint16_t *slist = reinterpret_cast<uint16_t *>(scnt + SMEM_TABLE_SLOTS);  // slots claimed for this partition, in claim order
-  __shared__ uint32_t s_list_n;
+  extern __shared__ __align__(16) unsigned long long skeys[];
+  constexpr uint32_t SLOTS = SMEM_TABLE_SLOTS;
+  constexpr int NW = SMEM_COUNT_THREADS / 32;
+  constexpr uint32_t WLIST = SLOTS / NW;  // claimed-slot list entries per warp
+  uint32_t *scnt = reinterpret_cast<uint32_t *>(skeys + SLOTS);
+  uint16_t *slist = reinterpret_cast<uint16_t *>(scnt + SLOTS);
   __shared__ uint64_t seg_begin[CONS_MAX_RUNS];
   __shared__ uint64_t seg_prefix[CONS_MAX_RUNS + 1];
-  __shared__ uint32_t s_work, s_hist[HIST_CTA_BINS];
+  __shared__ uint32_t s_work, s_hist[HIST_CTA_BINS], s_wn[NW];
   __shared__ unsigned long long s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr uint32_t SLOTS = SMEM_TABLE_SLOTS;
+  uint16_t *wlist = slist + warp * WLIST;
   if (tid < HIST_CTA_BINS) s_hist[tid] = 0;
   for (uint32_t i = tid; i < SLOTS; i += SMEM_COUNT_THREADS) { skeys[i] = EMPTY_KEY; scnt[i] = 0; }
   uint32_t next_work = 0;
-  if (tid == 0) { next_work = atomicAdd(P.next, 1u); s_list_n = 0; }
+  if (tid == 0) next_work = atomicAdd(P.next, 1u);
+  if (tid < NW) s_wn[tid] = 0;
   __syncthreads();
 
   for (;;) {
@@ -489,88 +499,134 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
       __syncthreads();
       continue;
     }
-    uint32_t cap_log2 = 8;  // small partitions use a prefix of the table: less to compact
+    uint32_t cap_log2 = 8;  // small partitions use a prefix of the table
     while ((1u << cap_log2) < SLOTS && (1ull << cap_log2) * 5 < n_p * 8) ++cap_log2;
-    const uint32_t mask = (1u << cap_log2) - 1;
+    const uint32_t mask = (1u << cap_log2) - 1, bmask = mask & ~1u;
 
-    // 8 keys per thread are loaded up front (one exposed global-load latency per 4096 entries instead of two),
-    // then upserted in two batches of 4 whose first probes are in flight together.
     constexpr int G = 8, H = 4;
-    uint32_t r = 0;  // run holding the thread's current entry: entries are visited in ascending order
+    static_assert(G == 8, "slot bookkeeping below packs 8 x 16 bits");
+    // entry idx of the partition is kq[idx] while idx < hi (the pointers are biased by the run's first index)
+    uint32_t r = 0;
+    uint64_t hi = seg_prefix[1];
+    const uint64_t *kq = P.runs[0].keys + seg_begin[0];
+    const uint64_t *cq = (WEIGHTED && P.runs[0].counts) ? P.runs[0].counts + seg_begin[0] : nullptr;
 #pragma unroll 1
     for (uint64_t base = 0; base < n_p; base += (uint64_t)SMEM_COUNT_THREADS * G) {
       uint64_t key[G];
-      uint32_t w[G];
+      uint32_t w[WEIGHTED ? G : 1];
+      uint32_t live = 0;  // bit j: key j is a real entry with a non-zero weight
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         const uint64_t idx = base + (uint64_t)j * SMEM_COUNT_THREADS + tid;
-        w[j] = 0; key[j] = EMPTY_KEY;
+        key[j] = EMPTY_KEY;
+        if (WEIGHTED) w[j] = 0;
         if (idx < n_p) {
-          while (r + 1 < P.R && idx >= seg_prefix[r + 1]) ++r;
-          const uint64_t src = seg_begin[r] + (idx - seg_prefix[r]);
-          key[j] = __ldcs(P.runs[r].keys + src);
-          uint64_t w64 = 1;
-          if (P.runs[r].counts) w64 = __ldcs(P.runs[r].counts + src);
-          if (w64 > 0xffffffffull) { atomicExch(P.error_flag, 1u); w64 = 0; }  // needs the u64 (L2-scratch) variant
-          w[j] = (uint32_t)w64;
+          while (idx >= hi) {  // entries are visited in ascending order: runs only ever advance
+            ++r;
+            hi = seg_prefix[r + 1];
+            kq = P.runs[r].keys + seg_begin[r] - seg_prefix[r];
+            if (WEIGHTED) cq = P.runs[r].counts ? P.runs[r].counts + seg_begin[r] - seg_prefix[r] : nullptr;
+          }
+          key[j] = __ldcs(kq + idx);
+          live |= 1u << j;
+          if (WEIGHTED) {
+            uint64_t w64 = 1;
+            if (cq) w64 = __ldcs(cq + idx);
+            if (w64 > 0xffffffffull) { atomicExch(P.error_flag, 1u); w64 = 0; }  // needs the u64 (L2-scratch) variant
+            w[j] = (uint32_t)w64;
+            if (!w64) live &= ~(1u << j);
+          }
         }
       }
-      if (P.preagg && n_p > 2 * SMEM_COUNT_THREADS * G) {  // warp run-length pre-aggregation, only for oversized (= skewed) partitions
+      if (WEIGHTED && (P.preagg & 1u) && n_p > 2 * SMEM_COUNT_THREADS * G) {
+        // Warp run-length pre-aggregation, only for oversized (= skewed) partitions: the scatter passes keep the keys of
+        // consecutive windows close together, so homopolymer / tandem-repeat runs arrive as runs of equal keys in
+        // adjacent lanes.  The head lane of each run upserts once with the run length.
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-          const uint64_t kk = w[j] ? key[j] : EMPTY_KEY;
+          const uint64_t kk = (live >> j & 1u) ? key[j] : EMPTY_KEY;
           const uint64_t kp = __shfl_up_sync(0xffffffffu, kk, 1);
           const bool head = lane == 0 || kp != kk;
           const uint32_t heads = __ballot_sync(0xffffffffu, head);
           if (__all_sync(0xffffffffu, w[j] <= 1u)) {
             const uint32_t above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
             const uint32_t end = above ? (uint32_t)__ffs(above) - 1u : 32u;
-            if (w[j]) w[j] = head ? end - lane : 0u;
+            if (live >> j & 1u) { w[j] = head ? end - lane : 0u; if (!head) live &= ~(1u << j); }
           }
         }
       }
-      // First probes of all G keys, H at a time in flight; whatever collides is left in `pend`.
-      uint32_t pend = 0, newm = 0;  // bit j: key j still to place / key j claimed a fresh slot
+      // ---- two straight-line probe rounds, H keys in flight each: the home bucket (one 16-byte load), then -- for the
+      // keys that lost -- the next position of their sequence.  Both rounds run converged; only the ~2 % of keys that are
+      // still homeless afterwards enter the divergent loop below.
+      // Probe sequence of a key: bucket t = b0 + t * step2 (b0 from the mix, the odd stride from key bits), slots (t,0), (t,1).
+      uint32_t pend = 0, newm = 0;    // bit j: key j still to place / key j claimed a fresh slot
+      uint32_t odd = 0, adv = 0;      // pending key j lost slot (adv, odd) last: it continues at u = 2 * adv + odd + 1
       uint64_t fs_lo = 0, fs_hi = 0;  // slot of key j, 16 bits each (keys 0-3 / 4-7), meaningful for the keys in newm
 #pragma unroll
       for (int h0 = 0; h0 < G; h0 += H) {
         uint32_t sl[H];
-        unsigned long long cur[H];
 #pragma unroll
-        for (int j = 0; j < H; ++j) { sl[j] = (uint32_t)mix64(key[h0 + j]) & mask; cur[j] = w[h0 + j] ? skeys[sl[j]] : 0ull; }
+        for (int j = 0; j < H; ++j) sl[j] = (uint32_t)mix64(key[h0 + j]) & bmask;
 #pragma unroll
-        for (int j = 0; j < H; ++j) if (w[h0 + j] && cur[j] == EMPTY_KEY) cur[j] = atomicCAS(&skeys[sl[j]], EMPTY_KEY, key[h0 + j]);
+        for (int round = 0; round < 2; ++round) {
+          const uint32_t act = round ? pend : live;
+          ulonglong2 cur[H];
+          unsigned long long got[H];
 #pragma unroll
-        for (int j = 0; j < H; ++j) {
-          const uint32_t wj = w[h0 + j];
-          if (!wj) continue;
-          const bool is_new = cur[j] == EMPTY_KEY;
-          if (is_new || cur[j] == key[h0 + j]) {
-            const uint32_t add = wj - (is_new ? 1u : 0u);  // slots store occurrences - 1
-            if (add) { const uint32_t old = atomicAdd(&scnt[sl[j]], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
-            if (is_new) { newm |= 1u << (h0 + j); (h0 + j < 4 ? fs_lo : fs_hi) |= (uint64_t)sl[j] << (16 * ((h0 + j) & 3)); }
-          } else pend |= 1u << (h0 + j);
+          for (int j = 0; j < H; ++j) {
+            const int q = h0 + j;
+            if (round && (odd >> q & 1u)) sl[j] = ((sl[j] & ~1u) + ((((uint32_t)(key[q] >> 9)) | 1u) << 1)) & mask;  // both home slots lost: next bucket
+            else sl[j] &= ~1u;
+            cur[j] = make_ulonglong2(0ull, 0ull);
+            if (act >> q & 1u) cur[j] = *reinterpret_cast<const ulonglong2 *>(&skeys[sl[j]]);
+          }
+          const uint32_t was_odd = odd;
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            const int q = h0 + j;
+            const unsigned long long k = key[q];
+            got[j] = 0ull;
+            if (!(act >> q & 1u)) continue;
+            const bool x_known_taken = round && !(was_odd >> q & 1u);  // lost the race for the first home slot in round 0
+            if (x_known_taken || (cur[j].x != k && cur[j].x != EMPTY_KEY)) { sl[j] |= 1u; cur[j].x = cur[j].y; }
+            got[j] = cur[j].x;
+            if (cur[j].x == EMPTY_KEY) got[j] = atomicCAS(&skeys[sl[j]], EMPTY_KEY, k);
+          }
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            const int q = h0 + j;
+            if (!(act >> q & 1u)) continue;
+            const bool is_new = got[j] == EMPTY_KEY;
+            if (is_new || got[j] == key[q]) {
+              const uint32_t wj = WEIGHTED ? w[q] : 1u;
+              const uint32_t add = wj - (is_new ? 1u : 0u);  // slots store occurrences - 1
+              if (add) { const uint32_t old = atomicAdd(&scnt[sl[j]], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
+              if (is_new) { newm |= 1u << q; (q < 4 ? fs_lo : fs_hi) |= (uint64_t)sl[j] << (16 * (q & 3)); }
+              pend &= ~(1u << q);
+            } else {
+              pend |= 1u << q;
+              if (round) adv |= (was_odd >> q & 1u) << q;  // this round looked at the next bucket iff both home slots were lost before
+              odd = (odd & ~(1u << q)) | ((sl[j] & 1u) << q);
+            }
+          }
         }
       }
-      // Collisions: every lane works through ITS pending keys on its own (no warp-wide rendezvous per key, so the
-      // warp runs for the longest per-lane total, not for the sum of the per-key maxima).  Double hashing -- an odd
-      // stride from the high mix bits -- keeps the chains short; lookups only ever happen through this same sequence.
+      // ---- what is left: every lane works through ITS pending keys on its own, continuing behind the slot it lost
       while (pend) {
         const int j = __ffs(pend) - 1;
         uint64_t kj = key[0];
-        uint32_t wj = w[0];
+        uint32_t wj = WEIGHTED ? w[0] : 1u;
 #pragma unroll
-        for (int q = 1; q < G; ++q) if (j == q) { kj = key[q]; wj = w[q]; }
-        const uint64_t m = mix64(kj);
-        const uint32_t step = (uint32_t)(m >> 40) | 1u;
-        uint32_t s2 = (uint32_t)m & mask;
-        unsigned long long c2;
-        for (uint32_t tries = 0;; ++tries) {
-          s2 = (s2 + step) & mask;
+        for (int q = 1; q < G; ++q) if (j == q) { kj = key[q]; if (WEIGHTED) wj = w[q]; }
+        const uint32_t b0 = (uint32_t)mix64(kj) & bmask, step2 = (((uint32_t)(kj >> 9)) | 1u) << 1;
+        uint32_t s2 = 0;
+        unsigned long long c2 = 0;
+        for (uint32_t u = 2u * (adv >> j & 1u) + (odd >> j & 1u) + 1u;; ++u) {
+          s2 = ((b0 + (u >> 1) * step2) & mask) | (u & 1u);
           c2 = skeys[s2];
           if (c2 == EMPTY_KEY) c2 = atomicCAS(&skeys[s2], EMPTY_KEY, kj);
           if (c2 == EMPTY_KEY || c2 == kj) break;
-          if (tries > mask) { atomicExch(P.error_flag, 1u); break; }  // table full: the host re-runs with the L2 variant
+          if (u > mask + 4) { atomicExch(P.error_flag, 1u); break; }  // every slot visited: the host re-runs with the L2 variant
         }
         const bool is_new = c2 == EMPTY_KEY;
         if (is_new || c2 == kj) {
@@ -584,42 +640,44 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
         }
         pend &= pend - 1;
       }
-      // remember which slots this partition claimed -- ONE warp-aggregated append per batch; compaction visits only those
-      {
-        const uint32_t mine = (uint32_t)__popc(newm);
-        uint32_t incl = mine;
+      __syncwarp();  // reconverge here: otherwise the rest of the batch runs once per fragment of the warp
+      // ---- every lane appends the slots it claimed to its warp's list.  One same-address shared atomic per lane
+      // and batch hands out the positions; deliberately no warp collective here: this point follows divergent
+      // code, where a *_sync intrinsic costs a software convergence routine per call.
+      if (newm) {
+        uint32_t pos = atomicAdd(&s_wn[warp], (uint32_t)__popc(newm));
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {  // warp-uniform
-          uint32_t lb = 0;
-          if (lane == 31) lb = atomicAdd(&s_list_n, total);
-          lb = __shfl_sync(0xffffffffu, lb, 31) + incl - mine;
-#pragma unroll
-          for (int q = 0; q < G; ++q)
-            if (newm >> q & 1u) slist[lb++] = (uint16_t)((q < 4 ? fs_lo : fs_hi) >> (16 * (q & 3)));
-        }
+        for (int q = 0; q < G; ++q)
+          if (newm >> q & 1u) { if (pos < WLIST) wlist[pos] = (uint16_t)((q < 4 ? fs_lo : fs_hi) >> (16 * (q & 3))); ++pos; }
       }
     }
-    __syncthreads();  // all upserts done; s_list_n = number of distinct keys of this partition
-    // ---- compact: reserve the partition's output range with one global atomic, then walk the claimed-slot list:
-    // entry i goes to out[base + i] (perfectly coalesced) and its slot is handed back clean.
-    if (tid == 0) {
-      const uint32_t d = s_list_n;
-      const unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);
-      P.out_seg_start[p] = b; P.out_seg_len[p] = d;
-      s_base = b;
+    __syncthreads();  // all upserts done
+    uint32_t wn = s_wn[warp];  // slots this warp claimed for the partition
+    if (wn > WLIST) { if (lane == 0) atomicExch(P.error_flag, 1u); wn = WLIST; }  // list full: results are discarded, stay in bounds
+    // ---- compact: the partition gets one contiguous output range (one global atomic), each warp a sub-range of it
+    uint32_t pre;
+    {
+      const uint32_t v = lane < NW ? min(s_wn[lane], WLIST) : 0u;
+      uint32_t incl = v;
+#pragma unroll
+      for (int o = 1; o < NW; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+      const uint32_t d = __shfl_sync(0xffffffffu, incl, NW - 1);
+      pre = __shfl_sync(0xffffffffu, incl - v, warp);
+      if (tid == 0) {
+        const unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);
+        P.out_seg_start[p] = b; P.out_seg_len[p] = d;
+        s_base = b;
+      }
     }
     __syncthreads();
     {
-      const unsigned long long out0 = s_base;
-      const uint32_t d = s_list_n;
-      for (uint32_t i0 = 0; i0 < d; i0 += SMEM_COUNT_THREADS) {
-        const uint32_t i = i0 + tid;
-        const bool ok = i < d;
+      const unsigned long long out0 = s_base + pre;
+      for (uint32_t i0 = 0; i0 < wn; i0 += 32) {  // warp-uniform trip count
+        const uint32_t i = i0 + lane;
+        const bool ok = i < wn;
         unsigned long long cnt = 0;
         if (ok) {
-          const uint32_t slot = slist[i];
+          const uint32_t slot = wlist[i];
           cnt = (unsigned long long)scnt[slot] + 1;  // slots store occurrences - 1
           __stcs(P.out_keys + out0 + i, (uint64_t)skeys[slot]);
           __stcs(P.out_counts + out0 + i, (uint64_t)cnt);
@@ -628,20 +686,22 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
         if (P.hist) hist_note(ok, cnt, s_hist, P, lane);
       }
     }
-    __syncthreads();  // table clean before the next partition
-    if (tid == 0) s_list_n = 0;
+    __syncthreads();  // table clean before the next partition (and every warp has read the list counters)
+    if (tid < NW) s_wn[tid] = 0;  // ordered before the next partition's appends by the barrier after its metadata fetch
   }
   if (P.hist) hist_flush(s_hist, P, tid);
 }
 
-cudaError_t launch_count_partitions_smem(const CountParams &P, cudaStream_t s) {
+cudaError_t launch_count_partitions_smem(const CountParams &P, bool weighted, cudaStream_t s) {
   if (P.n_parts == 0) return cudaSuccess;
-  const size_t smem = (size_t)SMEM_TABLE_SLOTS * 14;  // u64 keys + u32 counts + u16 slot list
-  cudaError_t e = cudaFuncSetAttribute(count_partitions_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)SMEM_TABLE_SLOTS * 14;  // u64 keys + u32 counts + u16 slot lists
+  const unsigned grid = (unsigned)std::min<uint64_t>(P.n_parts, (uint64_t)num_sms() * 2);
+  cudaError_t e = weighted ? cudaFuncSetAttribute(count_partitions_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(count_partitions_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  const unsigned grid = (unsigned)std::min<uint64_t>(P.n_parts, (uint64_t)num_sms() * 2);
-  count_partitions_smem_kernel<<<grid, SMEM_COUNT_THREADS, smem, s>>>(P);
+  if (weighted) count_partitions_smem_kernel<true><<<grid, SMEM_COUNT_THREADS, smem, s>>>(P);
+  else count_partitions_smem_kernel<false><<<grid, SMEM_COUNT_THREADS, smem, s>>>(P);
   return cudaGetLastError();
 }
 
