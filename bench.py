@@ -250,7 +250,9 @@ def main():
         pipeline = {"phase_a_ms": a_ms, "phase_b_ms": b_ms, "phase_a_gbs": gpu_windows * 24.375 / (a_ms * 1e-3) / 1e9 if a_ms else 0.0,
                     "phase_b_gbs": gpu_windows * 24.0 / (b_ms * 1e-3) / 1e9 if b_ms else 0.0,
                     "whole_gbs": gpu_windows * B_ALG_HASH_NEW / ((a_ms + b_ms) * 1e-3) / 1e9 if a_ms + b_ms else 0.0}
-        if b_ms >= a_ms:
+        # dominant single KERNEL: phase B is one launch; phase A is five (ingest, partition_count, partition_scatter_staged,
+        # refine<count>, refine<scatter>), the largest of which takes ~40 % of phase A (profiles/r1_v5_launches.csv)
+        if b_ms >= 0.4 * a_ms:
             kern_ms, per_unit, kern_name = b_ms, 24.0, "count_partitions_smem_kernel (phase B: one CTA per hash partition, upsert into a shared-memory table, compact)"
         else:
             kern_ms, per_unit, kern_name = a_ms, 24.375, "phase A kernels (partition_count/scatter over the scan + refine count/scatter: two-level hash partitioning)"

@@ -5,7 +5,7 @@ import csv, subprocess, sys
 rep, kern = sys.argv[1], sys.argv[2]
 keys = float(sys.argv[3]) if len(sys.argv) > 3 else None
 N = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern, "--print-source", "cuda,sass"],
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", *(["--kernel-id", ":::" + kern[3:]] if kern.startswith("id:") else ["--kernel-name", "regex:" + kern]), "--print-source", "cuda,sass"],
                      capture_output=True, text=True).stdout
 fname, hdr, lines = "?", None, []
 for r in csv.reader(out.splitlines()):
