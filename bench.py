@@ -151,11 +151,33 @@ def run_reference(args, rank: int):
                        "k": args.k, "sample_bases": n},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The driver parses stdout as ONE JSON line: route everything libraries print there (e.g. NCCL's version banner)
+    to stderr and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
     args = parse_args()
+    claim_stdout()
     if os.environ.get("KMG_BENCH_DEBUG"):
         import faulthandler
         faulthandler.dump_traceback_later(int(os.environ["KMG_BENCH_DEBUG"]), repeat=True, file=sys.stderr)
@@ -342,7 +364,7 @@ def main():
                            "step": "table clear + ingest + scan/upsert (+ bucket, all-to-all, upsert for N>1) + finalize",
                            "parallelism": f"hash-shard x{world}" if world > 1 else "single GPU"},
                 "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     engine.close()
     if world > 1:
         dist.destroy_process_group()
