@@ -33,6 +33,9 @@ constexpr int CONS_MAX_RUNS = 32;  // one warp scans the segment table of a part
 constexpr int MAX_PARTS = 8192;        // bins of ONE scatter level (shared-memory histogram)
 constexpr int REFINE_THREADS = 512;
 constexpr int REFINE_TILE = 8192;      // keys per level-2 tile (staged in shared memory: 64 KiB, 128 KiB with counts)
+constexpr int REFINE_ROWS_THREADS = 1024;   // single-pass level-2 scatter: one CTA per SM
+constexpr int REFINE_ROWS_SLOTS = 16384;    // n_sub rows of 2^cap_log2 keys (128 KiB)
+constexpr int REFINE_ROWS_OVERFLOW = 512;   // keys whose row was full
 constexpr int COUNT_THREADS = 512;
 constexpr int COUNT_CTAS_PER_SM = 2;
 constexpr int SMEM_COUNT_THREADS = 512;    // phase B primary variant: table in shared memory, 2 CTAs/SM
@@ -50,7 +53,7 @@ struct RefineParams {
   const uint64_t *keys, *counts;          // coarse-partitioned input (counts may be nullptr)
   const uint64_t *coarse_start;           // n_coarse + 1
   const uint32_t *tile_prefix;            // n_coarse + 1: first global tile number of each coarse partition
-  uint32_t n_coarse, n_sub, n_tiles, pad;
+  uint32_t n_coarse, n_sub, n_tiles, cap_log2;  // cap_log2: row size of the single-pass scatter (set by launch_refine)
   unsigned long long *fine_counts;        // count pass
   const unsigned long long *fine_start;   // scatter pass: exclusive prefix of fine_counts
   unsigned long long *fine_cursor;        // scatter pass: zeroed

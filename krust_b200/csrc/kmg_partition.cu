@@ -111,111 +111,254 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
 // SCATTER == false: fine_counts[c*n_sub + s] += ...      SCATTER == true: fine_start[] is the exclusive
 // prefix of those counts and fine_cursor[] starts at zero.
 // ---------------------------------------------------------------------------------------------------
+// One tile, exact two-pass procedure: histogram -> (count: add to fine_counts | scatter: prefix, one global reservation
+// per sub-bin, rank the keys into `staging` in sub-bin order, coalesced copy-out).  hist[] is zero on entry and on exit.
+template <int THREADS, bool SCATTER>
+__device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, const uint64_t begin, const uint32_t m, const uint64_t f0,
+                                                     uint64_t *staging, uint64_t *staging_c, uint32_t *hist, uint32_t *s_off,
+                                                     uint32_t *g_base, uint32_t *s_scan) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int U = 8;  // keys in flight per thread
+  for (uint32_t i0 = 0; i0 < m; i0 += U * THREADS) {
+    uint64_t key[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const uint32_t i = i0 + j * THREADS + tid;
+      key[j] = i < m ? (SCATTER ? P.keys[begin + i] : __ldcs(P.keys + begin + i)) : EMPTY_KEY;
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) if (i0 + j * THREADS + tid < m) atomicAdd(hist + sub_of_mix(mix64(key[j]), P.n_sub), 1u);
+  }
+  __syncthreads();
+  if (!SCATTER) {
+    for (uint32_t s = tid; s < P.n_sub; s += THREADS) {
+      const uint32_t h = hist[s];
+      if (h) { atomicAdd(P.fine_counts + f0 + s, (unsigned long long)h); hist[s] = 0; }
+    }
+    return;
+  }
+  // exclusive prefix over the sub-bins (staging offsets) + one global reservation per sub-bin
+  const uint32_t per = (P.n_sub + THREADS - 1) / THREADS;
+  const uint32_t b0 = min((uint32_t)tid * per, P.n_sub), b1 = min(b0 + per, P.n_sub);
+  uint32_t mine = 0;
+  for (uint32_t s = b0; s < b1; ++s) mine += hist[s];
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v = lane < THREADS / 32 ? s_scan[lane] : 0, inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane < THREADS / 32) s_scan[lane] = inc - v;
+  }
+  __syncthreads();
+  uint32_t run = s_scan[warp] + (incl - mine);
+  for (uint32_t s = b0; s < b1; ++s) {
+    const uint32_t h = hist[s];
+    s_off[s] = run;
+    g_base[s] = h ? (uint32_t)(P.fine_start[f0 + s] + atomicAdd(P.fine_cursor + f0 + s, (unsigned long long)h)) : 0u;
+    hist[s] = run;  // becomes the staging cursor
+    run += h;
+  }
+  __syncthreads();
+  for (uint32_t i0 = 0; i0 < m; i0 += U * THREADS) {  // second read of the tile comes from L2
+    uint64_t key[U], cnt[U];
+    uint32_t sb[U], o[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const uint32_t i = i0 + j * THREADS + tid;
+      key[j] = i < m ? __ldcs(P.keys + begin + i) : EMPTY_KEY;  // last use of this tile
+      cnt[j] = (i < m && P.counts) ? __ldcs(P.counts + begin + i) : 1ull;
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) { sb[j] = sub_of_mix(mix64(key[j]), P.n_sub); o[j] = 0; if (i0 + j * THREADS + tid < m) o[j] = atomicAdd(hist + sb[j], 1u); }
+#pragma unroll
+    for (int j = 0; j < U; ++j)
+      if (i0 + j * THREADS + tid < m) { staging[o[j]] = key[j]; if (P.counts) staging_c[o[j]] = cnt[j]; }
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < m; i += THREADS) {  // coalesced copy-out; destination recomputed from the key
+    const uint64_t key = staging[i];
+    const uint32_t sbin = sub_of_mix(mix64(key), P.n_sub);
+    const uint64_t dst = (uint64_t)g_base[sbin] + (i - s_off[sbin]);
+    P.out_keys[dst] = key;
+    if (P.out_counts) P.out_counts[dst] = P.counts ? staging_c[i] : 1ull;
+  }
+  __syncthreads();
+  for (uint32_t s = tid; s < P.n_sub; s += THREADS) hist[s] = 0;
+}
+
+// which coarse partition owns tile g (largest c with tile_prefix[c] <= g), and the tile's key range
+__device__ __forceinline__ void refine_locate_tile(const RefineParams &P, uint32_t g, uint32_t *s_c, uint32_t &c, uint64_t &begin, uint32_t &m) {
+  if (threadIdx.x == 0) {
+    uint32_t lo = 0, hi = P.n_coarse;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.tile_prefix[mid] <= g) lo = mid; else hi = mid; }
+    *s_c = lo;
+  }
+  __syncthreads();
+  c = *s_c;
+  begin = P.coarse_start[c] + (uint64_t)(g - P.tile_prefix[c]) * REFINE_TILE;
+  const uint64_t end_c = P.coarse_start[c + 1];
+  m = (uint32_t)(end_c - begin < (uint64_t)REFINE_TILE ? end_c - begin : (uint64_t)REFINE_TILE);
+}
+
 template <bool SCATTER>
 __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) {
   extern __shared__ __align__(16) uint8_t rsm[];
-  // count pass: one histogram.  scatter pass: the tile's keys are ranked into a shared-memory staging buffer in
-  // sub-bin order and copied out by consecutive lanes (see partition_scatter_staged_kernel: scattered 8-byte
-  // stores, one L2 transaction each, were 60 % of the unstaged kernels).
+  // count pass: one histogram.  scatter pass (weighted keys, or KMG_REFINE=legacy): the tile's keys are ranked into a
+  // shared-memory staging buffer in sub-bin order and copied out by consecutive lanes (scattered 8-byte stores, one L2
+  // transaction each, were 60 % of the unstaged kernels).
   uint64_t *staging = reinterpret_cast<uint64_t *>(rsm);                                // SCATTER only: REFINE_TILE keys
   uint64_t *staging_c = staging + REFINE_TILE;                                          // SCATTER with counts only
   uint32_t *hist = reinterpret_cast<uint32_t *>(rsm + (SCATTER ? (size_t)REFINE_TILE * 8 * (P.counts ? 2 : 1) : 0));
   uint32_t *s_off = hist + P.n_sub, *g_base = s_off + P.n_sub;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   __shared__ uint32_t s_c, s_scan[REFINE_THREADS / 32 + 1];
   for (uint32_t s = tid; s < P.n_sub; s += REFINE_THREADS) hist[s] = 0;
   __syncthreads();
   for (uint32_t g = blockIdx.x; g < P.n_tiles; g += gridDim.x) {
-    if (tid == 0) {  // which coarse partition owns tile g: largest c with tile_prefix[c] <= g
-      uint32_t lo = 0, hi = P.n_coarse;
-      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.tile_prefix[mid] <= g) lo = mid; else hi = mid; }
-      s_c = lo;
-    }
-    __syncthreads();
-    const uint32_t c = s_c;
-    const uint64_t begin = P.coarse_start[c] + (uint64_t)(g - P.tile_prefix[c]) * REFINE_TILE;
-    const uint64_t end_c = P.coarse_start[c + 1];
-    const uint32_t m = (uint32_t)(end_c - begin < (uint64_t)REFINE_TILE ? end_c - begin : (uint64_t)REFINE_TILE);
-    constexpr int U = 8;  // keys in flight per thread
-    for (uint32_t i0 = 0; i0 < m; i0 += U * REFINE_THREADS) {
-      uint64_t key[U];
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const uint32_t i = i0 + j * REFINE_THREADS + tid;
-        key[j] = i < m ? (SCATTER ? P.keys[begin + i] : __ldcs(P.keys + begin + i)) : EMPTY_KEY;
-      }
-#pragma unroll
-      for (int j = 0; j < U; ++j) if (i0 + j * REFINE_THREADS + tid < m) atomicAdd(hist + sub_of_mix(mix64(key[j]), P.n_sub), 1u);
-    }
-    __syncthreads();
-    const uint64_t f0 = (uint64_t)c * P.n_sub;
-    if (!SCATTER) {
-      for (uint32_t s = tid; s < P.n_sub; s += REFINE_THREADS) {
-        const uint32_t h = hist[s];
-        if (h) { atomicAdd(P.fine_counts + f0 + s, (unsigned long long)h); hist[s] = 0; }
-      }
-    } else {
-      // exclusive prefix over the sub-bins (staging offsets) + one global reservation per sub-bin
-      const uint32_t per = (P.n_sub + REFINE_THREADS - 1) / REFINE_THREADS;
-      const uint32_t b0 = tid * per, b1 = b0 + per < P.n_sub ? b0 + per : P.n_sub;
-      uint32_t mine = 0;
-      for (uint32_t s = b0; s < b1; ++s) mine += hist[s];
-      uint32_t incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      if (lane == 31) s_scan[warp] = incl;
-      __syncthreads();
-      if (warp == 0) {
-        uint32_t v = lane < REFINE_THREADS / 32 ? s_scan[lane] : 0, inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-        if (lane < REFINE_THREADS / 32) s_scan[lane] = inc - v;
-      }
-      __syncthreads();
-      uint32_t run = s_scan[warp] + (incl - mine);
-      for (uint32_t s = b0; s < b1; ++s) {
-        const uint32_t h = hist[s];
-        s_off[s] = run;
-        g_base[s] = h ? (uint32_t)(P.fine_start[f0 + s] + atomicAdd(P.fine_cursor + f0 + s, (unsigned long long)h)) : 0u;
-        hist[s] = run;  // becomes the staging cursor
-        run += h;
-      }
-      __syncthreads();
-      for (uint32_t i0 = 0; i0 < m; i0 += U * REFINE_THREADS) {  // second read of the tile comes from L2
-        uint64_t key[U], cnt[U];
-        uint32_t sb[U], o[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const uint32_t i = i0 + j * REFINE_THREADS + tid;
-          key[j] = i < m ? __ldcs(P.keys + begin + i) : EMPTY_KEY;  // last use of this tile
-          cnt[j] = (i < m && P.counts) ? __ldcs(P.counts + begin + i) : 1ull;
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j) { sb[j] = sub_of_mix(mix64(key[j]), P.n_sub); o[j] = 0; if (i0 + j * REFINE_THREADS + tid < m) o[j] = atomicAdd(hist + sb[j], 1u); }
-#pragma unroll
-        for (int j = 0; j < U; ++j)
-          if (i0 + j * REFINE_THREADS + tid < m) { staging[o[j]] = key[j]; if (P.counts) staging_c[o[j]] = cnt[j]; }
-      }
-      __syncthreads();
-      for (uint32_t i = tid; i < m; i += REFINE_THREADS) {  // coalesced copy-out; destination recomputed from the key
-        const uint64_t key = staging[i];
-        const uint32_t sbin = sub_of_mix(mix64(key), P.n_sub);
-        const uint64_t dst = (uint64_t)g_base[sbin] + (i - s_off[sbin]);
-        P.out_keys[dst] = key;
-        if (P.out_counts) P.out_counts[dst] = P.counts ? staging_c[i] : 1ull;
-      }
-      __syncthreads();
-      for (uint32_t s = tid; s < P.n_sub; s += REFINE_THREADS) hist[s] = 0;
-    }
+    uint32_t c, m;
+    uint64_t begin;
+    refine_locate_tile(P, g, &s_c, c, begin, m);
+    refine_tile_two_pass<REFINE_THREADS, SCATTER>(P, begin, m, (uint64_t)c * P.n_sub, staging, staging_c, hist, s_off, g_base, s_scan);
     __syncthreads();
   }
 }
 
-cudaError_t launch_refine(const RefineParams &P, bool scatter, cudaStream_t s) {
-  if (P.n_tiles == 0) return cudaSuccess;
+// ---------------------------------------------------------------------------------------------------
+// level 2 scatter, single pass (unweighted keys -- the scan path): every sub-bin owns a ROW of 2^cap_log2 key slots in
+// shared memory.  A key is read once, hashed once, ranked inside its sub-bin by one shared atomic (with return) and
+// dropped into its row; the few keys whose row is full (sub-bin sizes are Poisson around 9/16 of the row) go to a
+// small overflow list together with their rank.  Then one global reservation per sub-bin and a copy-out in which
+// consecutive lanes write consecutive keys of a row.  Compared with histogram + prefix + re-read + re-hash this is
+// ~1/3 of the instructions per key (the two-pass kernel was issue bound, profiles/r1_v4_phaseA_lines.txt).
+// A tile whose overflow list does not suffice (heavily repeated keys) is redone with the exact two-pass procedure.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(RefineParams P) {
+  extern __shared__ __align__(16) uint8_t rsm[];
+  const uint32_t cl = P.cap_log2, cap = 1u << cl, n_slots = P.n_sub << cl;
+  uint64_t *rows = reinterpret_cast<uint64_t *>(rsm);  // REFINE_ROWS_SLOTS
+  uint64_t *ov_key = rows + REFINE_ROWS_SLOTS;         // REFINE_ROWS_OVERFLOW
+  uint32_t *ov_meta = reinterpret_cast<uint32_t *>(ov_key + REFINE_ROWS_OVERFLOW);
+  uint32_t *cnt = ov_meta + REFINE_ROWS_OVERFLOW, *s_off = cnt + P.n_sub, *g_base = s_off + P.n_sub;
+  __shared__ uint32_t s_c[2], s_ovn, s_scan[REFINE_ROWS_THREADS / 32 + 1];
+  const int tid = threadIdx.x;
+  constexpr int U = REFINE_TILE / REFINE_ROWS_THREADS;  // the whole tile is in registers: one exposed load latency per tile
+  static_assert(U * REFINE_ROWS_THREADS == REFINE_TILE, "tile must be a multiple of the CTA size");
+  // a CTA owns a CONTIGUOUS range of tiles, so consecutive tiles mostly share their coarse partition
+  const uint32_t per_cta = (P.n_tiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t g_begin = blockIdx.x * per_cta, g_end = min(g_begin + per_cta, P.n_tiles);
+  if (g_begin >= g_end) return;
+  uint32_t c_hint = 0;  // thread 0: coarse partition of the tile located last
+  auto locate = [&](uint32_t g, int slot) {  // thread 0 publishes the partition of tile g
+    if (tid == 0) {
+      if (P.tile_prefix[c_hint] > g || c_hint >= P.n_coarse) c_hint = 0;
+      if (P.tile_prefix[c_hint + 1] <= g) {  // not in the same or the next non-empty partition: binary search
+        uint32_t lo = c_hint, hi = P.n_coarse;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.tile_prefix[mid] <= g) lo = mid; else hi = mid; }
+        c_hint = lo;
+      }
+      s_c[slot] = c_hint;
+    }
+  };
+  auto tile_range = [&](uint32_t g, uint32_t c, uint64_t &begin, uint32_t &m) {
+    begin = P.coarse_start[c] + (uint64_t)(g - P.tile_prefix[c]) * REFINE_TILE;
+    const uint64_t end_c = P.coarse_start[c + 1];
+    m = (uint32_t)(end_c - begin < (uint64_t)REFINE_TILE ? end_c - begin : (uint64_t)REFINE_TILE);
+  };
+  for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
+  if (tid == 0) s_ovn = 0;
+  locate(g_begin, 0);
+  __syncthreads();
+  uint32_t c = s_c[0], m;
+  uint64_t begin;
+  tile_range(g_begin, c, begin, m);
+  uint64_t key[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m ? __ldcs(P.keys + begin + i) : EMPTY_KEY; }
+
+  for (uint32_t g = g_begin; g < g_end; ++g) {
+    const uint64_t f0 = (uint64_t)c * P.n_sub;
+    {  // ---- rank the tile's keys into the rows
+      uint32_t sb[U], r[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        sb[j] = sub_of_mix(mix64(key[j]), P.n_sub);
+        r[j] = 0;
+        if (j * REFINE_ROWS_THREADS + tid < m) r[j] = atomicAdd(cnt + sb[j], 1u);
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (j * REFINE_ROWS_THREADS + tid >= m) continue;
+        if (r[j] < cap) rows[(sb[j] << cl) + r[j]] = key[j];
+        else {
+          const uint32_t o = atomicAdd(&s_ovn, 1u);
+          if (o < REFINE_ROWS_OVERFLOW) { ov_key[o] = key[j]; ov_meta[o] = (sb[j] << 16) | r[j]; }  // r < REFINE_TILE <= 65536
+        }
+      }
+    }
+    const int nslot = (g - g_begin + 1) & 1;
+    if (g + 1 < g_end) locate(g + 1, nslot);
+    __syncthreads();
+    const uint32_t n_ov = s_ovn;
+    const bool exact = n_ov > REFINE_ROWS_OVERFLOW;  // block-uniform: skewed tile, take the exact route
+    if (exact) {
+      for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
+      __syncthreads();
+      refine_tile_two_pass<REFINE_ROWS_THREADS, true>(P, begin, m, f0, rows, nullptr, cnt, s_off, g_base, s_scan);
+    } else {
+      for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) {
+        const uint32_t h = cnt[s];
+        g_base[s] = h ? (uint32_t)(P.fine_start[f0 + s] + atomicAdd(P.fine_cursor + f0 + s, (unsigned long long)h)) : 0u;
+      }
+    }
+    // ---- the next tile's keys are requested now, so their latency hides behind this tile's copy-out
+    uint32_t c_next = c, m_next = 0;
+    uint64_t begin_next = 0;
+    if (g + 1 < g_end) {
+      c_next = s_c[nslot];
+      tile_range(g + 1, c_next, begin_next, m_next);
+#pragma unroll
+      for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m_next ? __ldcs(P.keys + begin_next + i) : EMPTY_KEY; }
+    }
+    __syncthreads();
+    if (!exact) {
+      for (uint32_t x = tid; x < n_slots; x += REFINE_ROWS_THREADS) {  // lanes walk along the rows: contiguous destinations
+        const uint32_t s = x >> cl, e = x & (cap - 1);
+        if (e < cnt[s]) P.out_keys[(uint64_t)g_base[s] + e] = rows[x];
+      }
+      for (uint32_t o = tid; o < n_ov; o += REFINE_ROWS_THREADS) {
+        const uint32_t meta = ov_meta[o];
+        P.out_keys[(uint64_t)g_base[meta >> 16] + (meta & 0xffffu)] = ov_key[o];
+      }
+      __syncthreads();
+      for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
+    }
+    if (tid == 0) s_ovn = 0;
+    __syncthreads();
+    c = c_next; m = m_next; begin = begin_next;
+  }
+}
+
+cudaError_t launch_refine(const RefineParams &P_in, bool scatter, cudaStream_t s) {
+  if (P_in.n_tiles == 0) return cudaSuccess;
+  RefineParams P = P_in;
+  cudaError_t e;
+  static const bool legacy = [] { const char *v = getenv("KMG_REFINE"); return v && v[0] == 'l'; }();  // ablation: KMG_REFINE=legacy
+  if (scatter && !P.counts && !P.out_counts && !legacy && P.n_sub <= REFINE_ROWS_SLOTS / 8) {
+    uint32_t cl = 3;
+    while ((P.n_sub << (cl + 1)) <= (uint32_t)REFINE_ROWS_SLOTS && cl < 15) ++cl;  // largest row that fits
+    P.cap_log2 = cl;
+    const size_t smem = (size_t)REFINE_ROWS_SLOTS * 8 + (size_t)REFINE_ROWS_OVERFLOW * 12 + 3 * (size_t)P.n_sub * sizeof(uint32_t);
+    if ((e = cudaFuncSetAttribute(refine_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    refine_rows_kernel<<<(unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms()), REFINE_ROWS_THREADS, smem, s>>>(P);
+    return cudaGetLastError();
+  }
   const size_t smem = scatter ? (size_t)REFINE_TILE * 8 * (P.counts ? 2 : 1) + 3 * (size_t)P.n_sub * sizeof(uint32_t) : (size_t)P.n_sub * sizeof(uint32_t);
   const unsigned grid = (unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms() * ((scatter && smem > 110 * 1024) ? 1 : 2));
-  cudaError_t e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (scatter) {
     if ((e = cudaFuncSetAttribute(refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
