@@ -563,6 +563,64 @@ struct StageEmit {
       if ((okg >> j) & 1u) staging[o[j]] = key[j];
   }
 };
+// One sub-tile (n_words words starting at w0), exact: histogram -> prefix + one global reservation per partition ->
+// rank pass into `staging` -> coalesced copy-out.  hist[] is zero on entry and on exit; ends with a barrier.
+template <int THREADS>
+__device__ __forceinline__ void stage_subtile_exact(const TileSmem *ts, int w0, int n_words, const ScanInput &in, bool has_start,
+                                                    uint32_t n_parts, const unsigned long long *part_start, unsigned long long *part_cursor,
+                                                    uint64_t *out, uint64_t *staging, uint32_t *hist, uint32_t *s_off, uint32_t *g_base,
+                                                    uint32_t *s_scan) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    PartCountEmit e{hist, n_parts};
+#pragma unroll 1
+    for (int w = tid; w < n_words; w += THREADS) scan_word<8>(ts, w0 + w, in.k, has_start, e);
+  }
+  __syncthreads();
+  // exclusive prefix over the partitions: thread t owns the contiguous chunk [t*per, (t+1)*per)
+  const uint32_t per = (n_parts + THREADS - 1) / THREADS;
+  const uint32_t b0 = min((uint32_t)tid * per, n_parts), b1 = min(b0 + per, n_parts);
+  uint32_t mine = 0;
+  for (uint32_t p = b0; p < b1; ++p) mine += hist[p];
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v = lane < THREADS / 32 ? s_scan[lane] : 0, inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane < THREADS / 32) s_scan[lane] = inc - v;
+    if (lane == 31) s_scan[THREADS / 32] = inc;  // keys in this sub-tile
+  }
+  __syncthreads();
+  uint32_t run = s_scan[warp] + (incl - mine);
+  for (uint32_t p = b0; p < b1; ++p) {
+    const uint32_t c = hist[p];
+    s_off[p] = run;
+    g_base[p] = c ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)c)) : 0u;
+    hist[p] = run;  // becomes the staging cursor
+    run += c;
+  }
+  const uint32_t n_sub = s_scan[THREADS / 32];
+  __syncthreads();
+  {
+    StageEmit e{hist, staging, n_parts};
+#pragma unroll 1
+    for (int w = tid; w < n_words; w += THREADS) scan_word<8>(ts, w0 + w, in.k, has_start, e);
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < n_sub; i += THREADS) {  // coalesced copy-out
+    const uint64_t key = staging[i];
+    const uint32_t p = part_of(key, n_parts);
+    __stcs(out + ((uint64_t)g_base[p] + (i - s_off[p])), key);
+  }
+  __syncthreads();
+  for (uint32_t p = tid; p < n_parts; p += THREADS) hist[p] = 0;
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(STAGE_THREADS, 1) partition_scatter_staged_kernel(ScanInput in, uint32_t n_parts,
                                                                                      const unsigned long long *part_start,
                                                                                      unsigned long long *part_cursor, uint64_t *out) {
@@ -574,7 +632,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) partition_scatter_staged_ker
   uint32_t *hist = reinterpret_cast<uint32_t *>(staging + STAGE_KEYS);  // histogram, then staging cursors
   uint32_t *s_off = hist + n_parts;                                     // staging offset of each partition
   uint32_t *g_base = s_off + n_parts;                                   // index in `out` of the partition's reservation
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const bool has_start = in.start != nullptr;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
   for (uint32_t p = tid; p < n_parts; p += STAGE_THREADS) hist[p] = 0;
@@ -587,56 +645,140 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) partition_scatter_staged_ker
     const uint64_t next = tile + gridDim.x;
     if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
     wait_stage(bars, stage, phase0, phase1);
+    for (int sub = 0; sub < TILE_WORDS / STAGE_SUB_WORDS; ++sub)
+      stage_subtile_exact<STAGE_THREADS>(&stages[stage], sub * STAGE_SUB_WORDS, STAGE_SUB_WORDS, in, has_start, n_parts, part_start,
+                                         part_cursor, out, staging, hist, s_off, g_base, s_scan);
+    stage ^= 1;
+  }
+}
+
+// pass 2, ROWS variant (default for up to 2048 partitions): ONE scan of the input.  Every partition owns a row of
+// 2^cl key slots in shared memory; a window's key is ranked inside its partition by one shared atomic (with return)
+// and dropped into the row, the few keys whose row is full (partition sizes per sub-tile are Poisson around 9/16 of
+// a row) go to a small overflow list with their rank.  Then one global reservation per partition and a copy-out
+// in which consecutive lanes write consecutive keys of a row.  The staged variant above scans and hashes every window
+// twice and was issue bound (4.4 warp-instructions per window, profiles/r1_v4_phaseA_lines.txt).
+// 1024 threads, one CTA per SM, sub-tiles of 256 words: a thread owns 8 consecutive windows of one word.
+// A sub-tile whose overflow list does not suffice (heavily repeated keys) is redone with the exact staged procedure.
+constexpr int ROWS_THREADS = 1024;
+constexpr int ROWS_SUB_WORDS = ROWS_THREADS / 4;   // 8192 windows per sub-tile
+constexpr int ROWS_SLOTS = 16384;                  // n_parts rows of 2^cl keys (128 KiB; also the staging buffer of the exact route)
+constexpr int ROWS_OVERFLOW = 512;
+struct RowsEmit {
+  uint32_t *cnt;
+  uint64_t *rows, *ov_key;
+  uint32_t *ov_meta, *ov_n;
+  uint32_t n_parts, cl, cap;
+  template <int G>
+  __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
+    uint32_t p[G], r[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) p[j] = part_of(key[j], n_parts);
+#pragma unroll
+    for (int j = 0; j < G; ++j) { r[j] = 0; if ((okg >> j) & 1u) r[j] = atomicAdd(cnt + p[j], 1u); }
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      if (!((okg >> j) & 1u)) continue;
+      if (r[j] < cap) rows[(p[j] << cl) + r[j]] = key[j];
+      else {
+        const uint32_t o = atomicAdd(ov_n, 1u);
+        if (o < (uint32_t)ROWS_OVERFLOW) { ov_key[o] = key[j]; ov_meta[o] = (p[j] << 16) | r[j]; }  // r < 8192, p < 2048
+      }
+    }
+  }
+};
+// the 8 windows ending at bases 8g .. 8g+7 of word i
+template <class Emit>
+__device__ __forceinline__ void scan_octet(const TileSmem *ts, int i, int g, int k, bool has_start, Emit &emit) {
+  const uint64_t prev = ts->bases[LEAD_BASE_WORDS + i - 1];
+  const uint64_t cur = ts->bases[LEAD_BASE_WORDS + i];
+  const uint32_t vprev = ts->valid[LEAD_MASK_WORDS + i - 1], vcur = ts->valid[LEAD_MASK_WORDS + i];
+  uint32_t sprev = 0, scur = 0;
+  if (has_start) { sprev = ts->start[LEAD_MASK_WORDS + i - 1]; scur = ts->start[LEAD_MASK_WORDS + i]; }
+  const uint32_t ok8 = (window_ok_mask(vprev, vcur, sprev, scur, k, has_start) >> (24 - 8 * g)) & 0xffu;  // window 8g+j at bit 7-j
+  if (ok8 == 0) return;
+  const uint64_t mask = kmer_mask(k);
+  const int rc_shift = 2 * (k - 1), e0 = 8 * g;
+  uint64_t fwd = (e0 ? ((prev << (2 * e0)) | (cur >> (64 - 2 * e0))) : prev) & mask;  // the k-mer ending just before base e0
+  uint64_t rc = revcomp(fwd, k);
+  uint64_t key[8];
+  uint32_t okg = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint64_t c = (cur >> (62 - 2 * (e0 + j))) & 3ull;
+    fwd = ((fwd << 2) | c) & mask;
+    rc = (rc >> 2) | ((3ull - c) << rc_shift);
+    key[j] = fwd < rc ? fwd : rc;
+    okg |= ((ok8 >> (7 - j)) & 1u) << j;
+  }
+  emit.template group<8>(key, okg);
+}
+__global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel(ScanInput in, uint32_t n_parts, uint32_t cl,
+                                                                                  const unsigned long long *part_start,
+                                                                                  unsigned long long *part_cursor, uint64_t *out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t s_scan[ROWS_THREADS / 32 + 1], s_ovn;
+  uint64_t *rows = reinterpret_cast<uint64_t *>(smem_raw + 2 * sizeof(TileSmem));
+  uint64_t *ov_key = rows + ROWS_SLOTS;
+  uint32_t *ov_meta = reinterpret_cast<uint32_t *>(ov_key + ROWS_OVERFLOW);
+  uint32_t *cnt = ov_meta + ROWS_OVERFLOW, *s_off = cnt + n_parts, *g_base = s_off + n_parts;
+  const uint32_t cap = 1u << cl, n_slots = n_parts << cl;
+  const int tid = threadIdx.x;
+  const bool has_start = in.start != nullptr;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); s_ovn = 0; }
+  for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
+  __syncthreads();
+  uint64_t tile = blockIdx.x;
+  int stage = 0;
+  uint32_t phase0 = 0, phase1 = 0;
+  if (tile < in.n_tiles && tid == 0) issue_tile(in, &stages[0], &bars[0], tile);
+  for (; tile < in.n_tiles; tile += gridDim.x) {
+    const uint64_t next = tile + gridDim.x;
+    if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
+    wait_stage(bars, stage, phase0, phase1);
     const TileSmem *ts = &stages[stage];
-    for (int sub = 0; sub < TILE_WORDS / STAGE_SUB_WORDS; ++sub) {
-      const int w0 = sub * STAGE_SUB_WORDS;
+    for (int sub = 0; sub < TILE_WORDS / ROWS_SUB_WORDS; ++sub) {
+      const int w0 = sub * ROWS_SUB_WORDS;
       {
-        PartCountEmit e{hist, n_parts};
-#pragma unroll 1
-        for (int r = 0; r < STAGE_SUB_WORDS / STAGE_THREADS; ++r) scan_word<8>(ts, w0 + r * STAGE_THREADS + tid, in.k, has_start, e);
+        RowsEmit e{cnt, rows, ov_key, ov_meta, &s_ovn, n_parts, cl, cap};
+        scan_octet(ts, w0 + (tid >> 2), tid & 3, in.k, has_start, e);
       }
       __syncthreads();
-      // exclusive prefix over the partitions: thread t owns the contiguous chunk [t*per, (t+1)*per)
-      const uint32_t per = (n_parts + STAGE_THREADS - 1) / STAGE_THREADS;
-      const uint32_t b0 = tid * per, b1 = b0 + per < n_parts ? b0 + per : n_parts;
-      uint32_t mine = 0;
-      for (uint32_t p = b0; p < b1; ++p) mine += hist[p];
-      uint32_t incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      if (lane == 31) s_scan[warp] = incl;
-      __syncthreads();
-      if (warp == 0) {
-        uint32_t v = lane < STAGE_THREADS / 32 ? s_scan[lane] : 0, inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-        if (lane < STAGE_THREADS / 32) s_scan[lane] = inc - v;
-        if (lane == 31) s_scan[STAGE_THREADS / 32] = inc;  // keys in this sub-tile
+      const uint32_t n_ov = s_ovn;
+      if (n_ov > (uint32_t)ROWS_OVERFLOW) {  // block-uniform: skewed sub-tile, take the exact route
+        for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
+        __syncthreads();
+        stage_subtile_exact<ROWS_THREADS>(ts, w0, ROWS_SUB_WORDS, in, has_start, n_parts, part_start, part_cursor, out, rows, cnt, s_off,
+                                          g_base, s_scan);
+      } else {
+        for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) {
+          const uint32_t h = cnt[p];
+          g_base[p] = h ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)h)) : 0u;
+        }
+        __syncthreads();
+        if (cap <= (uint32_t)ROWS_THREADS) {  // lanes walk along the rows (contiguous destinations); a thread keeps its column
+          const uint32_t e = tid & (cap - 1), p_step = ROWS_THREADS >> cl;
+          uint64_t *dst = out + e;
+          const uint64_t *src = rows + tid;
+#pragma unroll 4
+          for (uint32_t p = tid >> cl; p < n_parts; p += p_step, src += ROWS_THREADS)
+            if (e < cnt[p]) __stcs(dst + g_base[p], *src);
+        } else {
+          for (uint32_t x = tid; x < n_slots; x += ROWS_THREADS) {
+            const uint32_t p = x >> cl, e = x & (cap - 1);
+            if (e < cnt[p]) __stcs(out + (uint64_t)g_base[p] + e, rows[x]);
+          }
+        }
+        for (uint32_t o = tid; o < n_ov; o += ROWS_THREADS) {
+          const uint32_t meta = ov_meta[o];
+          __stcs(out + (uint64_t)g_base[meta >> 16] + (meta & 0xffffu), ov_key[o]);
+        }
+        __syncthreads();
+        for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
       }
-      __syncthreads();
-      uint32_t run = s_scan[warp] + (incl - mine);
-      for (uint32_t p = b0; p < b1; ++p) {
-        const uint32_t c = hist[p];
-        s_off[p] = run;
-        g_base[p] = c ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)c)) : 0u;
-        hist[p] = run;  // becomes the staging cursor
-        run += c;
-      }
-      const uint32_t n_sub = s_scan[STAGE_THREADS / 32];
-      __syncthreads();
-      {
-        StageEmit e{hist, staging, n_parts};
-#pragma unroll 1
-        for (int r = 0; r < STAGE_SUB_WORDS / STAGE_THREADS; ++r) scan_word<8>(ts, w0 + r * STAGE_THREADS + tid, in.k, has_start, e);
-      }
-      __syncthreads();
-      for (uint32_t i = tid; i < n_sub; i += STAGE_THREADS) {  // coalesced copy-out
-        const uint64_t key = staging[i];
-        const uint32_t p = part_of(key, n_parts);
-        __stcs(out + ((uint64_t)g_base[p] + (i - s_off[p])), key);
-      }
-      __syncthreads();
-      for (uint32_t p = tid; p < n_parts; p += STAGE_THREADS) hist[p] = 0;
+      if (tid == 0) s_ovn = 0;
       __syncthreads();
     }
     stage ^= 1;
@@ -862,7 +1004,14 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
   cudaError_t e;
   const size_t wsmem = 2 * sizeof(TileSmem) + (size_t)WSCATTER_WARPS * n_parts * sizeof(uint32_t);
   const size_t stsmem = 2 * sizeof(TileSmem) + (size_t)STAGE_KEYS * 8 + 3 * (size_t)n_parts * sizeof(uint32_t);
-  if (scatter && stsmem <= 220 * 1024 && !(getenv("KMG_SCATTER") && atoi(getenv("KMG_SCATTER")) != 0)) {  // staged variant (default)
+  const size_t rwsmem = 2 * sizeof(TileSmem) + (size_t)ROWS_SLOTS * 8 + (size_t)ROWS_OVERFLOW * 12 + 3 * (size_t)n_parts * sizeof(uint32_t);
+  if (scatter && n_parts <= (uint32_t)ROWS_SLOTS / 8 && !getenv("KMG_SCATTER")) {  // single-scan rows variant (default)
+    uint32_t cl = 3;
+    while ((n_parts << (cl + 1)) <= (uint32_t)ROWS_SLOTS && cl < 15) ++cl;  // largest row that fits
+    if ((e = set_smem(partition_scatter_rows_kernel, rwsmem)) != cudaSuccess) return e;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    partition_scatter_rows_kernel<<<(unsigned)std::min<uint64_t>(in.n_tiles, (uint64_t)num_sms()), ROWS_THREADS, rwsmem, s>>>(in, n_parts, cl, part_start, part_cursor, out);
+  } else if (scatter && stsmem <= 220 * 1024 && !(getenv("KMG_SCATTER") && atoi(getenv("KMG_SCATTER")) != 0)) {  // staged variant (KMG_SCATTER=0, or > 2048 partitions)
     if ((e = set_smem(partition_scatter_staged_kernel, stsmem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     partition_scatter_staged_kernel<<<(unsigned)std::min<uint64_t>(in.n_tiles, (uint64_t)num_sms()), STAGE_THREADS, stsmem, s>>>(in, n_parts, part_start, part_cursor, out);

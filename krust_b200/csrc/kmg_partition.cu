@@ -325,9 +325,18 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
     }
     __syncthreads();
     if (!exact) {
-      for (uint32_t x = tid; x < n_slots; x += REFINE_ROWS_THREADS) {  // lanes walk along the rows: contiguous destinations
-        const uint32_t s = x >> cl, e = x & (cap - 1);
-        if (e < cnt[s]) P.out_keys[(uint64_t)g_base[s] + e] = rows[x];
+      if (cap <= REFINE_ROWS_THREADS) {  // lanes walk along the rows (contiguous destinations); a thread keeps its column
+        const uint32_t e = tid & (cap - 1), s_step = REFINE_ROWS_THREADS >> cl;
+        uint64_t *dst = P.out_keys + e;
+        const uint64_t *src = rows + tid;
+#pragma unroll 4
+        for (uint32_t s2 = tid >> cl; s2 < P.n_sub; s2 += s_step, src += REFINE_ROWS_THREADS)
+          if (e < cnt[s2]) dst[g_base[s2]] = *src;
+      } else {
+        for (uint32_t x = tid; x < n_slots; x += REFINE_ROWS_THREADS) {
+          const uint32_t s2 = x >> cl, e = x & (cap - 1);
+          if (e < cnt[s2]) P.out_keys[(uint64_t)g_base[s2] + e] = rows[x];
+        }
       }
       for (uint32_t o = tid; o < n_ov; o += REFINE_ROWS_THREADS) {
         const uint32_t meta = ov_meta[o];
