@@ -3,6 +3,7 @@
 // The counting itself happens in the sm_100a kernels of kmg_kernels.cu.  There is no CPU fallback:
 // every entry point needs a CUDA device.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -90,6 +91,7 @@ struct kmg_ctx {
   std::vector<Run> runs;      // pending, not yet consolidated
   Run result;                 // consolidated (key, count) run
   bool has_result = false;
+  bool spec_fine_ok = !getenv("KMG_NO_SPECULATION");  // level-2 scatter without a count pass until a partition overflows its share
   size_t total_mem = 0;                      // device memory size (cudaMemGetInfo is slow; asked once)
   void *d_scan_tmp = nullptr;                // CUB scan scratch for n_parts items (n_parts is fixed once the mode is decided)
   size_t scan_tmp_bytes = 0;
@@ -387,6 +389,36 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   RefineParams rp{};
   rp.keys = d_ckeys; rp.counts = d_ccounts; rp.coarse_start = d_cstart; rp.tile_prefix = d_tprefix;
   rp.n_coarse = P1; rp.n_sub = c->n_sub; rp.n_tiles = (uint32_t)tiles;
+  // Speculative layout first: hash partitions are Poisson-sized, so every fine partition gets mean + 7 sigma + 16 slots
+  // and the count pass (a full read of the keys) is skipped.  Skewed input overflows a share: the kernel then raises a
+  // flag, and this chunk -- and, sticky, the rest of the job -- takes the exact count + prefix + scatter route below.
+  const double mu = (double)n / P;
+  const uint64_t cap_f = ((uint64_t)(mu + 7.0 * std::sqrt(mu) + 16.0) + 7) & ~7ull;
+  if (c->spec_fine_ok && mu >= 64.0 && cap_f * P < (1ull << 32) && refine_single_pass_available(c->n_sub, d_ccounts != nullptr)) {
+    kmg_status s = alloc_or_consolidate(c, reinterpret_cast<void **>(&r.d_keys), cap_f * P * 8, "fine keys");
+    if (s != KMG_OK) { cleanup(); free_run(c, r); return s; }
+    rp.fine_cap = cap_f;
+    rp.fine_cursor = reinterpret_cast<unsigned long long *>(r.d_seg_len);  // zeroed above; ends up as the partition sizes
+    rp.overflow_flag = reinterpret_cast<uint32_t *>(c->d_stats + 5);
+    rp.out_keys = r.d_keys;
+    uint32_t h_flag = 0;
+    e = cudaMemsetAsync(rp.overflow_flag, 0, 4, c->stream);
+    if (e == cudaSuccess) e = launch_fill_strided(r.d_seg_start, P, cap_f, c->stream);
+    if (e == cudaSuccess) e = launch_refine(rp, true, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, rp.overflow_flag, 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { cleanup(); free_run(c, r); return cuda_fail(c, e, "refine scatter (speculative layout)"); }
+    if (!h_flag) {
+      cleanup();
+      r.n = n;
+      return add_run(c, std::move(r));
+    }
+    c->spec_fine_ok = false;
+    pool_free(c, r.d_keys); r.d_keys = nullptr;
+    rp.fine_cap = 0; rp.overflow_flag = nullptr; rp.out_keys = nullptr;
+    e = cudaMemsetAsync(r.d_seg_len, 0, (size_t)P * 8, c->stream);
+    if (e != cudaSuccess) { cleanup(); free_run(c, r); return cuda_fail(c, e, "refine setup"); }
+  }
   rp.fine_counts = reinterpret_cast<unsigned long long *>(r.d_seg_len);
   rp.fine_start = reinterpret_cast<const unsigned long long *>(r.d_seg_start);
   rp.fine_cursor = c->d_fine_cursor;

@@ -58,6 +58,11 @@ struct RefineParams {
   const unsigned long long *fine_start;   // scatter pass: exclusive prefix of fine_counts
   unsigned long long *fine_cursor;        // scatter pass: zeroed
   uint64_t *out_keys, *out_counts;
+  // speculative layout (no count pass): fine partition f owns out[f * fine_cap, (f + 1) * fine_cap); fine_cursor[] then ends
+  // up as the partition sizes.  A reservation that does not fit raises *overflow_flag and writes nothing (the host redoes
+  // the chunk with exact counts).  fine_cap == 0: exact layout, fine_start[] is the prefix of the counted sizes.
+  uint64_t fine_cap;
+  uint32_t *overflow_flag;
 };
 struct CountParams {
   uint32_t n_parts, R, scratch_log2, preagg;
@@ -104,6 +109,8 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
                                unsigned long long *coarse_counts, const unsigned long long *coarse_start,
                                unsigned long long *coarse_cursor, uint64_t *out_keys, uint64_t *out_counts, cudaStream_t s);
 cudaError_t launch_refine(const RefineParams &P, bool scatter, cudaStream_t s);
+bool refine_single_pass_available(uint32_t n_sub, bool weighted);  // the rows kernel applies (it can run without a count pass)
+cudaError_t launch_fill_strided(uint64_t *d, uint64_t n, uint64_t stride, cudaStream_t s);  // d[i] = i * stride
 cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, cudaStream_t s);
 cudaError_t launch_count_partitions(const CountParams &P, unsigned grid, cudaStream_t s);
 // weighted: some input run carries counts, or a partition is large enough to want run-length pre-aggregation

@@ -111,6 +111,19 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
 // SCATTER == false: fine_counts[c*n_sub + s] += ...      SCATTER == true: fine_start[] is the exclusive
 // prefix of those counts and fine_cursor[] starts at zero.
 // ---------------------------------------------------------------------------------------------------
+// where sub-bin f of this tile lands in the output: exact layout = counted prefix + running cursor; speculative layout =
+// f * fine_cap + running cursor, refused (marker, nothing is written) when the partition's share is exhausted
+constexpr uint32_t NO_BASE = 0xffffffffu;
+__device__ __forceinline__ uint32_t refine_reserve(const RefineParams &P, uint64_t f, uint32_t h) {
+  if (!h) return 0u;
+  const unsigned long long off = atomicAdd(P.fine_cursor + f, (unsigned long long)h);
+  if (P.fine_cap) {
+    if (off + h > P.fine_cap) { atomicExch(P.overflow_flag, 1u); return NO_BASE; }
+    return (uint32_t)(f * P.fine_cap + off);
+  }
+  return (uint32_t)(P.fine_start[f] + off);
+}
+
 // One tile, exact two-pass procedure: histogram -> (count: add to fine_counts | scatter: prefix, one global reservation
 // per sub-bin, rank the keys into `staging` in sub-bin order, coalesced copy-out).  hist[] is zero on entry and on exit.
 template <int THREADS, bool SCATTER>
@@ -158,7 +171,7 @@ __device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, cons
   for (uint32_t s = b0; s < b1; ++s) {
     const uint32_t h = hist[s];
     s_off[s] = run;
-    g_base[s] = h ? (uint32_t)(P.fine_start[f0 + s] + atomicAdd(P.fine_cursor + f0 + s, (unsigned long long)h)) : 0u;
+    g_base[s] = refine_reserve(P, f0 + s, h);
     hist[s] = run;  // becomes the staging cursor
     run += h;
   }
@@ -182,6 +195,7 @@ __device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, cons
   for (uint32_t i = tid; i < m; i += THREADS) {  // coalesced copy-out; destination recomputed from the key
     const uint64_t key = staging[i];
     const uint32_t sbin = sub_of_mix(mix64(key), P.n_sub);
+    if (g_base[sbin] == NO_BASE) continue;
     const uint64_t dst = (uint64_t)g_base[sbin] + (i - s_off[sbin]);
     P.out_keys[dst] = key;
     if (P.out_counts) P.out_counts[dst] = P.counts ? staging_c[i] : 1ull;
@@ -311,7 +325,8 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
     } else {
       for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) {
         const uint32_t h = cnt[s];
-        g_base[s] = h ? (uint32_t)(P.fine_start[f0 + s] + atomicAdd(P.fine_cursor + f0 + s, (unsigned long long)h)) : 0u;
+        g_base[s] = refine_reserve(P, f0 + s, h);
+        if (g_base[s] == NO_BASE) cnt[s] = 0;  // refused: nothing of this sub-bin is written
       }
     }
     // ---- the next tile's keys are requested now, so their latency hides behind this tile's copy-out
@@ -340,7 +355,7 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
       }
       for (uint32_t o = tid; o < n_ov; o += REFINE_ROWS_THREADS) {
         const uint32_t meta = ov_meta[o];
-        P.out_keys[(uint64_t)g_base[meta >> 16] + (meta & 0xffffu)] = ov_key[o];
+        if (g_base[meta >> 16] != NO_BASE) P.out_keys[(uint64_t)g_base[meta >> 16] + (meta & 0xffffu)] = ov_key[o];
       }
       __syncthreads();
       for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
@@ -351,12 +366,27 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
   }
 }
 
+static bool refine_legacy() {
+  static const bool legacy = [] { const char *v = getenv("KMG_REFINE"); return v && v[0] == 'l'; }();  // ablation: KMG_REFINE=legacy
+  return legacy;
+}
+bool refine_single_pass_available(uint32_t n_sub, bool weighted) { return !weighted && !refine_legacy() && n_sub <= REFINE_ROWS_SLOTS / 8; }
+
+__global__ void fill_strided_kernel(uint64_t *d, uint64_t n, uint64_t stride) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) d[i] = i * stride;
+}
+cudaError_t launch_fill_strided(uint64_t *d, uint64_t n, uint64_t stride, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  fill_strided_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)num_sms() * 8), 256, 0, s>>>(d, n, stride);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_refine(const RefineParams &P_in, bool scatter, cudaStream_t s) {
   if (P_in.n_tiles == 0) return cudaSuccess;
   RefineParams P = P_in;
   cudaError_t e;
-  static const bool legacy = [] { const char *v = getenv("KMG_REFINE"); return v && v[0] == 'l'; }();  // ablation: KMG_REFINE=legacy
-  if (scatter && !P.counts && !P.out_counts && !legacy && P.n_sub <= REFINE_ROWS_SLOTS / 8) {
+  if (scatter && refine_single_pass_available(P.n_sub, P.counts || P.out_counts)) {
     uint32_t cl = 3;
     while ((P.n_sub << (cl + 1)) <= (uint32_t)REFINE_ROWS_SLOTS && cl < 15) ++cl;  // largest row that fits
     P.cap_log2 = cl;
