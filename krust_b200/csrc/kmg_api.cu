@@ -91,6 +91,7 @@ struct kmg_ctx {
   std::vector<Run> runs;      // pending, not yet consolidated
   Run result;                 // consolidated (key, count) run
   bool has_result = false;
+  bool spec_coarse_ok = !getenv("KMG_NO_SPECULATION");  // same for the level-1 scatter
   bool spec_fine_ok = !getenv("KMG_NO_SPECULATION");  // level-2 scatter without a count pass until a partition overflows its share
   size_t total_mem = 0;                      // device memory size (cudaMemGetInfo is slow; asked once)
   void *d_scan_tmp = nullptr;                // CUB scan scratch for n_parts items (n_parts is fixed once the mode is decided)
@@ -365,19 +366,26 @@ kmg_status alloc_or_consolidate(kmg_ctx *c, void **p, size_t bytes, const char *
 // `sync`: wait for the scatter before returning (needed when the input belongs to the caller).  Without it the coarse
 // buffers go back to the pool while the kernels are still queued, which is safe because every pool block is only ever
 // touched by work on c->stream (stream-ordered reuse).
+// coarse_len == nullptr: coarse partition p is [coarse_off[p], coarse_off[p + 1]); otherwise [coarse_off[p], coarse_off[p] + len[p]).
 kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, const std::vector<uint64_t> &coarse_off, bool owns = true,
-                         bool sync = true) {
+                         bool sync = true, const std::vector<uint64_t> *coarse_len = nullptr) {
   const uint32_t P1 = c->n_coarse, P = c->n_parts;
-  const uint64_t n = coarse_off[P1];
+  auto len_of = [&](uint32_t p) { return coarse_len ? (*coarse_len)[p] : coarse_off[p + 1] - coarse_off[p]; };
+  uint64_t n = 0;
+  for (uint32_t p = 0; p < P1; ++p) n += len_of(p);
   Run r;
-  uint64_t *d_cstart = nullptr;
+  uint64_t *d_cstart = nullptr, *d_clen = nullptr;
   uint32_t *d_tprefix = nullptr;
-  auto cleanup = [&]() { if (owns) { pool_free(c, d_ckeys); pool_free(c, d_ccounts); } pool_free(c, d_cstart); pool_free(c, d_tprefix); };
+  auto cleanup = [&]() { if (owns) { pool_free(c, d_ckeys); pool_free(c, d_ccounts); } pool_free(c, d_cstart); pool_free(c, d_clen); pool_free(c, d_tprefix); };
   std::vector<uint32_t> tprefix(P1 + 1, 0);
   uint64_t tiles = 0;
-  for (uint32_t p = 0; p < P1; ++p) { tprefix[p] = (uint32_t)tiles; tiles += (coarse_off[p + 1] - coarse_off[p] + REFINE_TILE - 1) / REFINE_TILE; }
+  for (uint32_t p = 0; p < P1; ++p) { tprefix[p] = (uint32_t)tiles; tiles += (len_of(p) + REFINE_TILE - 1) / REFINE_TILE; }
   tprefix[P1] = (uint32_t)tiles;
   cudaError_t e = pool_alloc(c, &d_cstart, (P1 + 1) * 8);
+  if (e == cudaSuccess && coarse_len) {
+    e = pool_alloc(c, &d_clen, (size_t)P1 * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_clen, coarse_len->data(), (size_t)P1 * 8, cudaMemcpyHostToDevice, c->stream);
+  }
   if (e == cudaSuccess) e = pool_alloc(c, &d_tprefix, (P1 + 1) * 4);
   if (e == cudaSuccess) e = pool_alloc(c, &r.d_seg_start, (size_t)P * 8);
   if (e == cudaSuccess) e = pool_alloc(c, &r.d_seg_len, (size_t)P * 8);
@@ -387,7 +395,7 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_fine_cursor, 0, (size_t)P * 8, c->stream);
   if (e != cudaSuccess) { cleanup(); free_run(c, r); return cuda_fail(c, e, "refine setup"); }
   RefineParams rp{};
-  rp.keys = d_ckeys; rp.counts = d_ccounts; rp.coarse_start = d_cstart; rp.tile_prefix = d_tprefix;
+  rp.keys = d_ckeys; rp.counts = d_ccounts; rp.coarse_start = d_cstart; rp.coarse_len = d_clen; rp.tile_prefix = d_tprefix;
   rp.n_coarse = P1; rp.n_sub = c->n_sub; rp.n_tiles = (uint32_t)tiles;
   // Speculative layout first: hash partitions are Poisson-sized, so every fine partition gets mean + 7 sigma + 16 slots
   // and the count pass (a full read of the keys) is skipped.  Skewed input overflows a share: the kernel then raises a
@@ -456,6 +464,44 @@ kmg_status scan_to_run(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
     in.k = c->k;
     const size_t tmr = timer_begin(c, 0);
     CU(c, cudaMemsetAsync(c->d_part, 0, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
+    // Speculative layout first (no count pass): hash bins are Poisson-sized, so every coarse bin gets an equal share of
+    // (windows of this launch) / P1 + 7 sigma + 1024 slots.  A bin that outgrows its share (heavily repeated k-mers) raises
+    // a flag; this launch -- and, sticky, the rest of the job -- then takes the exact count + prefix + scatter route.
+    {
+      const uint64_t n_ub = in.n_tiles * (uint64_t)TILE_WORDS * 32;
+      const double mu = (double)n_ub / P1;
+      const uint64_t cap_c = ((uint64_t)(mu + 7.0 * std::sqrt(mu) + 1024.0) + 15) & ~15ull;
+      if (c->spec_coarse_ok && cap_c * P1 < (1ull << 32) && scan_scatter_supports_cap(P1)) {
+        uint64_t *d_ckeys = nullptr;
+        kmg_status s = alloc_or_consolidate(c, reinterpret_cast<void **>(&d_ckeys), cap_c * P1 * 8, "coarse keys");
+        if (s != KMG_OK) return s;
+        std::vector<uint64_t> off(P1 + 1, 0), lens(P1, 0);
+        for (uint32_t p = 0; p <= P1; ++p) off[p] = (uint64_t)p * cap_c;
+        ScanInput sin = in;
+        sin.part_cap = cap_c;
+        sin.overflow_flag = reinterpret_cast<uint32_t *>(c->d_stats + 5);
+        uint32_t h_flag = 0;
+        cudaError_t e = cudaMemsetAsync(sin.overflow_flag, 0, 4, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_start, off.data(), P1 * 8, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = launch_scan_partition(sin, P1, true, d_cnt, d_start, d_cur, d_ckeys, c->d_counters, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(lens.data(), d_cur, P1 * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, sin.overflow_flag, 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { pool_free(c, d_ckeys); return cuda_fail(c, e, "coarse scatter (speculative layout)"); }
+        if (!h_flag) {
+          uint64_t n = 0;
+          for (uint32_t p = 0; p < P1; ++p) n += lens[p];
+          if (n == 0) { pool_free(c, d_ckeys); timer_end(c, tmr); continue; }
+          s = refine_to_run(c, d_ckeys, nullptr, off, /*owns=*/true, /*sync=*/false, &lens);
+          timer_end(c, tmr);
+          if (s != KMG_OK) return s;
+          continue;
+        }
+        c->spec_coarse_ok = false;
+        pool_free(c, d_ckeys);
+        CU(c, cudaMemsetAsync(c->d_part, 0, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
+      }
+    }
     CU(c, launch_scan_partition(in, P1, false, d_cnt, d_start, d_cur, nullptr, c->d_counters, c->stream));
     std::vector<unsigned long long> counts(P1);
     CU(c, cudaMemcpyAsync(counts.data(), d_cnt, P1 * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -563,6 +563,16 @@ struct StageEmit {
       if ((okg >> j) & 1u) staging[o[j]] = key[j];
   }
 };
+// where partition p's share of this sub-tile lands in `out` (see ScanInput::part_cap)
+constexpr uint32_t NO_BASE = 0xffffffffu;
+__device__ __forceinline__ uint32_t part_reserve(const ScanInput &in, const unsigned long long *part_start, unsigned long long *part_cursor,
+                                                 uint32_t p, uint32_t h) {
+  if (!h) return 0u;
+  const unsigned long long off = atomicAdd(part_cursor + p, (unsigned long long)h);
+  if (in.part_cap && off + h > in.part_cap) { atomicExch(in.overflow_flag, 1u); return NO_BASE; }
+  return (uint32_t)(part_start[p] + off);
+}
+
 // One sub-tile (n_words words starting at w0), exact: histogram -> prefix + one global reservation per partition ->
 // rank pass into `staging` -> coalesced copy-out.  hist[] is zero on entry and on exit; ends with a barrier.
 template <int THREADS>
@@ -599,7 +609,7 @@ __device__ __forceinline__ void stage_subtile_exact(const TileSmem *ts, int w0, 
   for (uint32_t p = b0; p < b1; ++p) {
     const uint32_t c = hist[p];
     s_off[p] = run;
-    g_base[p] = c ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)c)) : 0u;
+    g_base[p] = part_reserve(in, part_start, part_cursor, p, c);
     hist[p] = run;  // becomes the staging cursor
     run += c;
   }
@@ -614,7 +624,7 @@ __device__ __forceinline__ void stage_subtile_exact(const TileSmem *ts, int w0, 
   for (uint32_t i = tid; i < n_sub; i += THREADS) {  // coalesced copy-out
     const uint64_t key = staging[i];
     const uint32_t p = part_of(key, n_parts);
-    __stcs(out + ((uint64_t)g_base[p] + (i - s_off[p])), key);
+    if (g_base[p] != NO_BASE) __stcs(out + ((uint64_t)g_base[p] + (i - s_off[p])), key);
   }
   __syncthreads();
   for (uint32_t p = tid; p < n_parts; p += THREADS) hist[p] = 0;
@@ -755,7 +765,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
       } else {
         for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) {
           const uint32_t h = cnt[p];
-          g_base[p] = h ? (uint32_t)(part_start[p] + atomicAdd(part_cursor + p, (unsigned long long)h)) : 0u;
+          g_base[p] = part_reserve(in, part_start, part_cursor, p, h);
+          if (g_base[p] == NO_BASE) cnt[p] = 0;  // refused: nothing of this partition is written
         }
         __syncthreads();
         if (cap <= (uint32_t)ROWS_THREADS) {  // lanes walk along the rows (contiguous destinations); a thread keeps its column
@@ -773,7 +784,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
         }
         for (uint32_t o = tid; o < n_ov; o += ROWS_THREADS) {
           const uint32_t meta = ov_meta[o];
-          __stcs(out + (uint64_t)g_base[meta >> 16] + (meta & 0xffffu), ov_key[o]);
+          if (g_base[meta >> 16] != NO_BASE) __stcs(out + (uint64_t)g_base[meta >> 16] + (meta & 0xffffu), ov_key[o]);
         }
         __syncthreads();
         for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
@@ -993,6 +1004,12 @@ cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, un
     kern<<<grid, SCAN_THREADS, smem, s>>>(in, none, dense, counters, flags);
   }
   return cudaGetLastError();
+}
+
+bool scan_scatter_supports_cap(uint32_t n_parts) {  // the rows / staged kernels honour ScanInput::part_cap
+  const size_t stsmem = 2 * sizeof(TileSmem) + (size_t)STAGE_KEYS * 8 + 3 * (size_t)n_parts * sizeof(uint32_t);
+  const char *v = getenv("KMG_SCATTER");
+  return (!v || atoi(v) == 0) && (n_parts <= (uint32_t)ROWS_SLOTS / 8 || stsmem <= 220 * 1024);
 }
 
 cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool scatter, unsigned long long *part_counts,

@@ -12,6 +12,10 @@ struct ScanInput {
   const uint32_t *start;  // nullptr: single record / no boundaries inside the stream
   uint64_t n_tiles;
   int k;
+  // speculative scatter (no count pass): partition p owns out[p * part_cap, (p + 1) * part_cap); a reservation that does not
+  // fit raises *overflow_flag and writes nothing.  part_cap == 0: exact layout from the counted prefix.
+  uint64_t part_cap = 0;
+  uint32_t *overflow_flag = nullptr;
 };
 
 struct HashTable {
@@ -52,6 +56,7 @@ struct ConsRun {
 struct RefineParams {
   const uint64_t *keys, *counts;          // coarse-partitioned input (counts may be nullptr)
   const uint64_t *coarse_start;           // n_coarse + 1
+  const uint64_t *coarse_len;             // nullptr: partition c ends where c + 1 starts (exact layout)
   const uint32_t *tile_prefix;            // n_coarse + 1: first global tile number of each coarse partition
   uint32_t n_coarse, n_sub, n_tiles, cap_log2;  // cap_log2: row size of the single-pass scatter (set by launch_refine)
   unsigned long long *fine_counts;        // count pass
@@ -105,6 +110,7 @@ cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, un
 cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool scatter, unsigned long long *part_counts,
                                   const unsigned long long *part_start, unsigned long long *part_cursor, uint64_t *out,
                                   unsigned long long *counters, cudaStream_t s);
+bool scan_scatter_supports_cap(uint32_t n_parts);
 cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n, uint32_t n_coarse, bool scatter,
                                unsigned long long *coarse_counts, const unsigned long long *coarse_start,
                                unsigned long long *coarse_cursor, uint64_t *out_keys, uint64_t *out_counts, cudaStream_t s);

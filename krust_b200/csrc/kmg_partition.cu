@@ -214,7 +214,7 @@ __device__ __forceinline__ void refine_locate_tile(const RefineParams &P, uint32
   __syncthreads();
   c = *s_c;
   begin = P.coarse_start[c] + (uint64_t)(g - P.tile_prefix[c]) * REFINE_TILE;
-  const uint64_t end_c = P.coarse_start[c + 1];
+  const uint64_t end_c = P.coarse_len ? P.coarse_start[c] + P.coarse_len[c] : P.coarse_start[c + 1];
   m = (uint32_t)(end_c - begin < (uint64_t)REFINE_TILE ? end_c - begin : (uint64_t)REFINE_TILE);
 }
 
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
   };
   auto tile_range = [&](uint32_t g, uint32_t c, uint64_t &begin, uint32_t &m) {
     begin = P.coarse_start[c] + (uint64_t)(g - P.tile_prefix[c]) * REFINE_TILE;
-    const uint64_t end_c = P.coarse_start[c + 1];
+    const uint64_t end_c = P.coarse_len ? P.coarse_start[c] + P.coarse_len[c] : P.coarse_start[c + 1];
     m = (uint32_t)(end_c - begin < (uint64_t)REFINE_TILE ? end_c - begin : (uint64_t)REFINE_TILE);
   };
   for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
