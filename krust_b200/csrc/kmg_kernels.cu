@@ -678,7 +678,7 @@ struct RowsEmit {
   uint32_t *cnt;
   uint64_t *rows, *ov_key;
   uint32_t *ov_meta, *ov_n;
-  uint32_t n_parts, cl, cap;
+  uint32_t n_parts, cap;
   template <int G>
   __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
     uint32_t p[G], r[G];
@@ -689,7 +689,7 @@ struct RowsEmit {
 #pragma unroll
     for (int j = 0; j < G; ++j) {
       if (!((okg >> j) & 1u)) continue;
-      if (r[j] < cap) rows[(p[j] << cl) + r[j]] = key[j];
+      if (r[j] < cap) rows[p[j] * cap + r[j]] = key[j];
       else {
         const uint32_t o = atomicAdd(ov_n, 1u);
         if (o < (uint32_t)ROWS_OVERFLOW) { ov_key[o] = key[j]; ov_meta[o] = (p[j] << 16) | r[j]; }  // r < 8192, p < 2048
@@ -723,7 +723,7 @@ __device__ __forceinline__ void scan_octet(const TileSmem *ts, int i, int g, int
   }
   emit.template group<8>(key, okg);
 }
-__global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel(ScanInput in, uint32_t n_parts, uint32_t cl,
+__global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel(ScanInput in, uint32_t n_parts, uint32_t cap, uint32_t magic,
                                                                                   const unsigned long long *part_start,
                                                                                   unsigned long long *part_cursor, uint64_t *out) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
   uint64_t *ov_key = rows + ROWS_SLOTS;
   uint32_t *ov_meta = reinterpret_cast<uint32_t *>(ov_key + ROWS_OVERFLOW);
   uint32_t *cnt = ov_meta + ROWS_OVERFLOW, *s_off = cnt + n_parts, *g_base = s_off + n_parts;
-  const uint32_t cap = 1u << cl, n_slots = n_parts << cl;
+  const uint32_t n_slots = n_parts * cap;  // x / cap == __umulhi(x, magic) for x < 2^16
   const int tid = threadIdx.x;
   const bool has_start = in.start != nullptr;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); s_ovn = 0; }
@@ -752,7 +752,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
     for (int sub = 0; sub < TILE_WORDS / ROWS_SUB_WORDS; ++sub) {
       const int w0 = sub * ROWS_SUB_WORDS;
       {
-        RowsEmit e{cnt, rows, ov_key, ov_meta, &s_ovn, n_parts, cl, cap};
+        RowsEmit e{cnt, rows, ov_key, ov_meta, &s_ovn, n_parts, cap};
         scan_octet(ts, w0 + (tid >> 2), tid & 3, in.k, has_start, e);
       }
       __syncthreads();
@@ -769,18 +769,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
           if (g_base[p] == NO_BASE) cnt[p] = 0;  // refused: nothing of this partition is written
         }
         __syncthreads();
-        if (cap <= (uint32_t)ROWS_THREADS) {  // lanes walk along the rows (contiguous destinations); a thread keeps its column
-          const uint32_t e = tid & (cap - 1), p_step = ROWS_THREADS >> cl;
-          uint64_t *dst = out + e;
-          const uint64_t *src = rows + tid;
 #pragma unroll 4
-          for (uint32_t p = tid >> cl; p < n_parts; p += p_step, src += ROWS_THREADS)
-            if (e < cnt[p]) __stcs(dst + g_base[p], *src);
-        } else {
-          for (uint32_t x = tid; x < n_slots; x += ROWS_THREADS) {
-            const uint32_t p = x >> cl, e = x & (cap - 1);
-            if (e < cnt[p]) __stcs(out + (uint64_t)g_base[p] + e, rows[x]);
-          }
+        for (uint32_t x = tid; x < n_slots; x += ROWS_THREADS) {  // lanes walk along the rows: contiguous destinations
+          const uint32_t p = __umulhi(x, magic), e = x - p * cap;
+          if (e < cnt[p]) __stcs(out + (uint64_t)g_base[p] + e, rows[x]);
         }
         for (uint32_t o = tid; o < n_ov; o += ROWS_THREADS) {
           const uint32_t meta = ov_meta[o];
@@ -1023,11 +1015,11 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
   const size_t stsmem = 2 * sizeof(TileSmem) + (size_t)STAGE_KEYS * 8 + 3 * (size_t)n_parts * sizeof(uint32_t);
   const size_t rwsmem = 2 * sizeof(TileSmem) + (size_t)ROWS_SLOTS * 8 + (size_t)ROWS_OVERFLOW * 12 + 3 * (size_t)n_parts * sizeof(uint32_t);
   if (scatter && n_parts <= (uint32_t)ROWS_SLOTS / 8 && !getenv("KMG_SCATTER")) {  // single-scan rows variant (default)
-    uint32_t cl = 3;
-    while ((n_parts << (cl + 1)) <= (uint32_t)ROWS_SLOTS && cl < 15) ++cl;  // largest row that fits
+    const uint32_t cap = std::min<uint32_t>((uint32_t)ROWS_SLOTS / n_parts, ROWS_SUB_WORDS * 32);  // mean fill 8192 / (n_parts * cap) ~ 0.5
+    const uint32_t magic = (uint32_t)(((1ull << 32) + cap - 1) / cap);
     if ((e = set_smem(partition_scatter_rows_kernel, rwsmem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    partition_scatter_rows_kernel<<<(unsigned)std::min<uint64_t>(in.n_tiles, (uint64_t)num_sms()), ROWS_THREADS, rwsmem, s>>>(in, n_parts, cl, part_start, part_cursor, out);
+    partition_scatter_rows_kernel<<<(unsigned)std::min<uint64_t>(in.n_tiles, (uint64_t)num_sms()), ROWS_THREADS, rwsmem, s>>>(in, n_parts, cap, magic, part_start, part_cursor, out);
   } else if (scatter && stsmem <= 220 * 1024 && !(getenv("KMG_SCATTER") && atoi(getenv("KMG_SCATTER")) != 0)) {  // staged variant (KMG_SCATTER=0, or > 2048 partitions)
     if ((e = set_smem(partition_scatter_staged_kernel, stsmem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -58,7 +58,8 @@ struct RefineParams {
   const uint64_t *coarse_start;           // n_coarse + 1
   const uint64_t *coarse_len;             // nullptr: partition c ends where c + 1 starts (exact layout)
   const uint32_t *tile_prefix;            // n_coarse + 1: first global tile number of each coarse partition
-  uint32_t n_coarse, n_sub, n_tiles, cap_log2;  // cap_log2: row size of the single-pass scatter (set by launch_refine)
+  uint32_t n_coarse, n_sub, n_tiles, row_cap;   // row_cap / row_magic: row size of the single-pass scatter (set by launch_refine)
+  uint32_t row_magic, pad;
   unsigned long long *fine_counts;        // count pass
   const unsigned long long *fine_start;   // scatter pass: exclusive prefix of fine_counts
   unsigned long long *fine_cursor;        // scatter pass: zeroed

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(RefineParams P) {
   extern __shared__ __align__(16) uint8_t rsm[];
-  const uint32_t cl = P.cap_log2, cap = 1u << cl, n_slots = P.n_sub << cl;
+  const uint32_t cap = P.row_cap, n_slots = P.n_sub * cap, magic = P.row_magic;  // x / cap == __umulhi(x, magic) for x < 2^16
   uint64_t *rows = reinterpret_cast<uint64_t *>(rsm);  // REFINE_ROWS_SLOTS
   uint64_t *ov_key = rows + REFINE_ROWS_SLOTS;         // REFINE_ROWS_OVERFLOW
   uint32_t *ov_meta = reinterpret_cast<uint32_t *>(ov_key + REFINE_ROWS_OVERFLOW);
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         if (j * REFINE_ROWS_THREADS + tid >= m) continue;
-        if (r[j] < cap) rows[(sb[j] << cl) + r[j]] = key[j];
+        if (r[j] < cap) rows[sb[j] * cap + r[j]] = key[j];
         else {
           const uint32_t o = atomicAdd(&s_ovn, 1u);
           if (o < REFINE_ROWS_OVERFLOW) { ov_key[o] = key[j]; ov_meta[o] = (sb[j] << 16) | r[j]; }  // r < REFINE_TILE <= 65536
@@ -340,18 +340,10 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
     }
     __syncthreads();
     if (!exact) {
-      if (cap <= REFINE_ROWS_THREADS) {  // lanes walk along the rows (contiguous destinations); a thread keeps its column
-        const uint32_t e = tid & (cap - 1), s_step = REFINE_ROWS_THREADS >> cl;
-        uint64_t *dst = P.out_keys + e;
-        const uint64_t *src = rows + tid;
 #pragma unroll 4
-        for (uint32_t s2 = tid >> cl; s2 < P.n_sub; s2 += s_step, src += REFINE_ROWS_THREADS)
-          if (e < cnt[s2]) dst[g_base[s2]] = *src;
-      } else {
-        for (uint32_t x = tid; x < n_slots; x += REFINE_ROWS_THREADS) {
-          const uint32_t s2 = x >> cl, e = x & (cap - 1);
-          if (e < cnt[s2]) P.out_keys[(uint64_t)g_base[s2] + e] = rows[x];
-        }
+      for (uint32_t x = tid; x < n_slots; x += REFINE_ROWS_THREADS) {  // lanes walk along the rows: contiguous destinations
+        const uint32_t s2 = __umulhi(x, magic), e = x - s2 * cap;
+        if (e < cnt[s2]) P.out_keys[(uint64_t)g_base[s2] + e] = rows[x];
       }
       for (uint32_t o = tid; o < n_ov; o += REFINE_ROWS_THREADS) {
         const uint32_t meta = ov_meta[o];
@@ -387,9 +379,8 @@ cudaError_t launch_refine(const RefineParams &P_in, bool scatter, cudaStream_t s
   RefineParams P = P_in;
   cudaError_t e;
   if (scatter && refine_single_pass_available(P.n_sub, P.counts || P.out_counts)) {
-    uint32_t cl = 3;
-    while ((P.n_sub << (cl + 1)) <= (uint32_t)REFINE_ROWS_SLOTS && cl < 15) ++cl;  // largest row that fits
-    P.cap_log2 = cl;
+    P.row_cap = std::min<uint32_t>((uint32_t)REFINE_ROWS_SLOTS / P.n_sub, REFINE_TILE);  // mean fill 8192 / (n_sub * cap) ~ 0.5
+    P.row_magic = (uint32_t)(((1ull << 32) + P.row_cap - 1) / P.row_cap);
     const size_t smem = (size_t)REFINE_ROWS_SLOTS * 8 + (size_t)REFINE_ROWS_OVERFLOW * 12 + 3 * (size_t)P.n_sub * sizeof(uint32_t);
     if ((e = cudaFuncSetAttribute(refine_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
