@@ -979,7 +979,9 @@ KMG_EXPORT kmg_status kmg_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint
   const uint64_t begin = offsets[0], end = offsets[n_records];
   const bool use_q = c->cfg.has_min_quality && qual != nullptr;
   const bool src_pinned = is_pinned_host(seq + begin) && (!use_q || is_pinned_host(qual + begin));
-  kmg_status s = ensure_staging(c, !src_pinned, use_q, end - begin);
+  kmg_status s = decide_mode(c, end - begin);  // plan for the whole call, not for its first staging chunk
+  if (s != KMG_OK) return s;
+  s = ensure_staging(c, !src_pinned, use_q, end - begin);
   if (s != KMG_OK) return s;
   const uint64_t K1 = (uint64_t)c->k - 1;
   const uint64_t B = c->batch_bases;  // bytes per chunk including the k-1 overlap
