@@ -50,7 +50,8 @@ struct Staging {
 // partition p of a run is entries [seg_start[p], seg_start[p] + seg_len[p]).
 struct Run {
   uint64_t *d_keys = nullptr, *d_counts = nullptr, *d_seg_start = nullptr, *d_seg_len = nullptr;
-  uint64_t n = 0;
+  uint64_t n = 0;        // entries (a consolidated run may hold skipped filler entries, see count_partitions_smem_kernel)
+  uint64_t n_valid = 0;  // consolidated runs: distinct keys
 };
 
 struct kmg_ctx {
@@ -613,40 +614,52 @@ kmg_status consolidate(kmg_ctx *c) {
   unsigned long long n_out = 0;
   // attempt 0: shared-memory tables (primary).  If a partition holds more distinct keys than such a table
   // (inputs much larger than the partition plan), fall back to L2-resident scratch tables of growing size.
+  // The shared-memory kernel counts partitions that outgrew the plan in several passes (split_log2, from the average
+  // partition size); if a partition still overflows its table the split is refined twice before the L2-scratch variant
+  // takes over.
+  uint32_t split_log2 = 0;
+  while (split_log2 < 8 && (3600ull << split_log2) * 5 / 4 < total / std::max<uint32_t>(P, 1)) ++split_log2;
+  unsigned long long n_valid = 0;
+  int smem_attempts = 0;
   for (int attempt = 0;; ++attempt) {
-    const bool use_smem = attempt == 0;
+    const bool use_smem = smem_attempts < 3 && split_log2 <= 8;
     uint64_t *d_scratch = nullptr;
-    unsigned long long *d_sync = nullptr;  // [0] out_cursor, [1] next (u32) | error (u32)
+    unsigned long long *d_sync = nullptr;  // [0] out_cursor, [1] next (u32) | error (u32), [2] distinct keys
     const uint64_t slots = use_smem ? 0 : (uint64_t)grid << c->scratch_log2;
-    e = pool_alloc(c, &d_sync, 16);
+    prm.split_log2 = split_log2;
+    e = pool_alloc(c, &d_sync, 24);
     if (e == cudaSuccess && slots) e = pool_alloc(c, &d_scratch, slots * 16);
     if (e != cudaSuccess) { pool_free(c, d_scratch); pool_free(c, d_sync); st = cuda_fail(c, e, "cudaMalloc(count scratch)"); break; }
     prm.scratch = d_scratch; prm.scratch_log2 = c->scratch_log2;
     prm.out_cursor = d_sync;
+    prm.out_distinct = d_sync + 2;
     prm.next = reinterpret_cast<uint32_t *>(d_sync + 1);
     prm.error_flag = reinterpret_cast<uint32_t *>(d_sync + 1) + 1;
-    e = cudaMemsetAsync(d_sync, 0, 16, c->stream);
+    e = cudaMemsetAsync(d_sync, 0, 24, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_hist, 0, (HIST_DENSE_BINS + 1) * sizeof(unsigned long long), c->stream);
     if (e == cudaSuccess && slots) e = launch_table_init(HashTable{d_scratch, slots}, c->stream);
     const size_t tmr = timer_begin(c, 1);
-    bool weighted = max_total > 2ull * SMEM_COUNT_THREADS * 8;  // oversized partitions want the pre-aggregating variant
+    bool weighted = max_total > ((2ull * SMEM_COUNT_THREADS * 8) << split_log2);  // partitions oversized beyond the split want the pre-aggregating variant
     for (uint32_t r = 0; r < R; ++r) weighted |= in[r]->d_counts != nullptr;
     if (e == cudaSuccess) e = use_smem ? launch_count_partitions_smem(prm, weighted, c->stream) : launch_count_partitions(prm, grid, c->stream);
     timer_end(c, tmr);
-    unsigned long long h_sync[2] = {0, 0};
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 16, cudaMemcpyDeviceToHost, c->stream);
+    unsigned long long h_sync[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 24, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     pool_free(c, d_scratch); pool_free(c, d_sync);
     if (e != cudaSuccess) { st = cuda_fail(c, e, "count_partitions"); break; }
-    n_out = h_sync[0];
+    n_out = h_sync[0]; n_valid = h_sync[2];
     if (!(h_sync[1] >> 32)) break;  // no overflow
-    if (attempt >= 12 || c->scratch_log2 >= 30) { st = fail(c, KMG_ERR_TABLE_FULL, "partition table overflow could not be resolved"); break; }
-    if (!use_smem) ++c->scratch_log2;  // retry with larger tables
-    else c->scratch_log2 = std::max<uint32_t>(c->scratch_log2, 14);
+    if (attempt >= 16 || c->scratch_log2 >= 30) { st = fail(c, KMG_ERR_TABLE_FULL, "partition table overflow could not be resolved"); break; }
+    if (use_smem) {  // finer split first (weights beyond 32 bits are not cured by it: the L2 variant follows after three tries)
+      ++smem_attempts;
+      split_log2 += 2;
+      c->scratch_log2 = std::max<uint32_t>(c->scratch_log2, 14);
+    } else ++c->scratch_log2;  // retry with larger tables
   }
   pool_free(c, d_order);
   if (st != KMG_OK) { free_run(c, out); return st; }
-  out.n = n_out;
+  out.n = n_out; out.n_valid = n_valid;
   if (c->has_result) free_run(c, c->result);
   for (auto &r : c->runs) free_run(c, r);
   c->runs.clear();
@@ -686,7 +699,7 @@ bool fetch_fused_hist(kmg_ctx *c) {
   uint64_t others = ov_n, sum = 0, mx = 0;
   for (uint64_t b = 2; b < (uint64_t)HIST_DENSE_BINS; ++b) if (c->h_bins[b]) { others += c->h_bins[b]; sum += b * c->h_bins[b]; mx = b; }
   c->h_bins[0] = 0;
-  c->h_bins[1] = c->result.n - others;  // counts of 1 are not recorded by the kernel
+  c->h_bins[1] = c->result.n_valid - others;  // counts of 1 are not recorded by the kernel
   sum += c->h_bins[1];
   if (c->h_bins[1] && mx < 1) mx = 1;
   for (uint64_t v : c->h_ov) sum += v;
@@ -1202,7 +1215,7 @@ KMG_EXPORT kmg_status kmg_finalize(kmg_ctx *c, kmg_summary *out) {
   if (!out) return KMG_OK;
   memset(out, 0, sizeof *out);
   unsigned long long h[3];
-  if (fetch_fused_hist(c)) { h[0] = c->result.n; h[1] = c->fused_max; h[2] = c->fused_sum; }
+  if (fetch_fused_hist(c)) { h[0] = c->result.n_valid; h[1] = c->fused_max; h[2] = c->fused_sum; }
   else {
     CU(c, launch_table_stats(view_of(c), 1, c->d_stats, c->stream));
     CU(c, cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));

@@ -840,7 +840,7 @@ __global__ void rehash_kernel(HashTable from, HashTable to, unsigned long long *
 
 // A "view" unifies both table kinds for the read-side kernels: entry i is (key, count); empty if count == 0.
 __device__ __forceinline__ bool view_get(const TableView &v, uint64_t i, uint64_t &key, uint64_t &count) {
-  if (v.pair_keys) { key = v.pair_keys[i]; count = v.pair_counts[i]; return true; }
+  if (v.pair_keys) { key = v.pair_keys[i]; count = v.pair_counts[i]; return count != 0; }  // count 0: filler entry of a multi-pass partition
   if (v.dense) { key = i; count = v.dense[i]; return count != 0; }
   ulonglong2 s = reinterpret_cast<const ulonglong2 *>(v.slots)[i];
   key = s.x; count = s.y + 1;  // slots store occurrences - 1

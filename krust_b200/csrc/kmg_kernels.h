@@ -72,11 +72,13 @@ struct RefineParams {
 };
 struct CountParams {
   uint32_t n_parts, R, scratch_log2, preagg;
+  uint32_t split_log2, pad0;         // shared-memory kernel: partitions larger than a table are counted in up to 2^split_log2 passes
   ConsRun runs[CONS_MAX_RUNS];
   const uint32_t *order;             // partitions in processing order (largest first)
   uint64_t *scratch;                 // gridDim.x private tables of 2^scratch_log2 (key, count-1) slots, clean
   uint64_t *out_keys, *out_counts;
-  unsigned long long *out_cursor;    // zeroed; ends up = number of distinct keys
+  unsigned long long *out_cursor;    // zeroed; ends up = entries of the output run (distinct keys + skipped filler entries)
+  unsigned long long *out_distinct;  // zeroed; ends up = number of distinct keys
   uint64_t *out_seg_start, *out_seg_len;  // n_parts each: where partition p landed in the output
   uint32_t *next, *error_flag;       // zeroed
   // count-of-counts of the OUTPUT, built while compacting (zeroed by the host; nullptr = skip):

@@ -569,6 +569,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
       for (int w2 = 0; w2 < COUNT_THREADS / 32; ++w2) d += s_warp[w2];
       const unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);  // the partition's contiguous output range
       P.out_seg_start[p] = b; P.out_seg_len[p] = d;
+      if (d) atomicAdd(P.out_distinct, (unsigned long long)d);
       s_base = b;
     }
     __syncthreads();
@@ -636,6 +637,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
   __shared__ uint64_t seg_prefix[CONS_MAX_RUNS + 1];
   __shared__ uint32_t s_work, s_hist[HIST_CTA_BINS], s_wn[NW];
   __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_run;  // entries of the current partition already written (multi-pass partitions)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint16_t *wlist = slist + warp * WLIST;
   if (tid < HIST_CTA_BINS) s_hist[tid] = 0;
@@ -675,9 +677,21 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
     uint32_t cap_log2 = 8;  // small partitions use a prefix of the table
     while ((1u << cap_log2) < SLOTS && (1ull << cap_log2) * 5 < n_p * 8) ++cap_log2;
     const uint32_t mask = (1u << cap_log2) - 1, bmask = mask & ~1u;
+    // A partition with more entries than one table comfortably holds (the input outgrew the partition plan) is counted in
+    // m passes: pass q takes the keys whose spare mix bits equal q, so every pass sees ~1/m of the distinct keys.  Its
+    // output range is then reserved up front for all n_p entries; what stays unused is filled with (EMPTY, 0) entries
+    // that every reader skips.  m is capped by the launch-wide P.split_log2 (set from the AVERAGE partition size): a
+    // partition that is large only because a few keys are hot does not need more passes than its neighbours.
+    uint32_t m_log2 = 0;
+    while (m_log2 < P.split_log2 && ((uint64_t)(SLOTS / 2) << m_log2) < n_p) ++m_log2;
+    const uint32_t n_pass = 1u << m_log2;
+    if (n_pass > 1 && tid == 0) { s_base = atomicAdd(P.out_cursor, (unsigned long long)n_p); s_run = 0; }
 
     constexpr int G = 8, H = 4;
     static_assert(G == 8, "slot bookkeeping below packs 8 x 16 bits");
+#pragma unroll 1
+    for (uint32_t pass = 0; pass < n_pass; ++pass) {
+    if (pass) __syncthreads();  // the previous pass's list counters are reset
     // entry idx of the partition is kq[idx] while idx < hi (the pointers are biased by the run's first index)
     uint32_t r = 0;
     uint64_t hi = seg_prefix[1];
@@ -700,8 +714,8 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
             kq = P.runs[r].keys + seg_begin[r] - seg_prefix[r];
             if (WEIGHTED) cq = P.runs[r].counts ? P.runs[r].counts + seg_begin[r] - seg_prefix[r] : nullptr;
           }
-          key[j] = __ldcs(kq + idx);
-          live |= 1u << j;
+          key[j] = n_pass > 1 ? __ldg(kq + idx) : __ldcs(kq + idx);  // multi-pass: the entries are read again, keep them in L2
+          if (n_pass == 1 || (((uint32_t)mix64(key[j]) >> 13) & (n_pass - 1)) == pass) live |= 1u << j;
           if (WEIGHTED) {
             uint64_t w64 = 1;
             if (cq) w64 = __ldcs(cq + idx);
@@ -828,7 +842,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
     uint32_t wn = s_wn[warp];  // slots this warp claimed for the partition
     if (wn > WLIST) { if (lane == 0) atomicExch(P.error_flag, 1u); wn = WLIST; }  // list full: results are discarded, stay in bounds
     // ---- compact: the partition gets one contiguous output range (one global atomic), each warp a sub-range of it
-    uint32_t pre;
+    uint32_t pre, pass_d;
     {
       const uint32_t v = lane < NW ? min(s_wn[lane], WLIST) : 0u;
       uint32_t incl = v;
@@ -836,15 +850,17 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
       for (int o = 1; o < NW; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
       const uint32_t d = __shfl_sync(0xffffffffu, incl, NW - 1);
       pre = __shfl_sync(0xffffffffu, incl - v, warp);
-      if (tid == 0) {
+      if (n_pass == 1 && tid == 0) {
         const unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);
         P.out_seg_start[p] = b; P.out_seg_len[p] = d;
-        s_base = b;
+        s_base = b; s_run = 0;
+        if (d) atomicAdd(P.out_distinct, (unsigned long long)d);
       }
+      pass_d = d;
     }
     __syncthreads();
     {
-      const unsigned long long out0 = s_base + pre;
+      const unsigned long long out0 = s_base + s_run + pre;
       for (uint32_t i0 = 0; i0 < wn; i0 += 32) {  // warp-uniform trip count
         const uint32_t i = i0 + lane;
         const bool ok = i < wn;
@@ -859,8 +875,23 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
         if (P.hist) hist_note(ok, cnt, s_hist, P, lane);
       }
     }
-    __syncthreads();  // table clean before the next partition (and every warp has read the list counters)
-    if (tid < NW) s_wn[tid] = 0;  // ordered before the next partition's appends by the barrier after its metadata fetch
+    __syncthreads();  // table clean before the next pass / partition (and every warp has read the list counters)
+    if (tid < NW) s_wn[tid] = 0;  // ordered before the next appends by the barrier that opens the next pass / follows the metadata fetch
+    if (tid == 0) s_run += pass_d;
+    }  // pass
+    if (n_pass > 1) {
+      __syncthreads();
+      const uint32_t done = s_run;  // <= n_p: every entry contributes at most one distinct key
+      for (uint64_t i = done + tid; i < n_p; i += SMEM_COUNT_THREADS) {  // unused tail of the reservation: entries every reader skips
+        __stcs(P.out_keys + s_base + i, (uint64_t)EMPTY_KEY);
+        __stcs(P.out_counts + s_base + i, (uint64_t)0);
+      }
+      if (tid == 0) {
+        P.out_seg_start[p] = s_base; P.out_seg_len[p] = done;
+        if (done) atomicAdd(P.out_distinct, (unsigned long long)done);
+      }
+      __syncthreads();  // s_base / s_run are rewritten by the next partition
+    }
   }
   if (P.hist) hist_flush(s_hist, P, tid);
 }

@@ -380,3 +380,24 @@ def test_partitioned_fallbacks_large_weights_and_overfull_partitions():
             s = c.finalize()
             assert_same(c.export(1, True), (uk, uc))
             assert s["n_windows"] == int(uc.sum()) and s["max_count"] == int(uc.max())
+
+
+def test_input_outgrows_the_partition_plan():
+    """The plan is made from the first call; when far more data follows, partitions hold many times what one shared-memory
+    table takes.  Phase B must then count them in several passes (and still be exact), not fall off a cliff."""
+    rng = np.random.default_rng(2024)
+    k = 23
+    small = [bytes(rng.choice(list(b"ACGT"), size=30_000).tolist())]
+    big = [bytes(rng.choice(list(b"ACGT"), size=600_000).tolist()) for _ in range(4)]
+    big.append(b"ACGTTGCAAT" * 40_000)  # plus a block of hot keys
+    oracle = orc.count_records(k, small + big, mode="rolling")
+    with kb.GpuKmerCounter(k, flags=PART) as c:   # ~9 partitions planned for 30 K windows, 2.8 M windows arrive
+        for recs in (small, big):
+            c.count_records(recs)
+        s = c.finalize()
+        keys, counts = c.export(1, True)
+        assert s["path"] == 2
+        assert_same((keys, counts, s), oracle)
+        hv, hf = c.histogram(2)
+        ov, of = orc.histogram(oracle[1], 2)
+        assert (hv == ov).all() and (hf == of).all()
