@@ -95,8 +95,10 @@ struct kmg_ctx {
   bool spec_coarse_ok = !getenv("KMG_NO_SPECULATION");  // same for the level-1 scatter
   bool spec_fine_ok = !getenv("KMG_NO_SPECULATION");  // level-2 scatter without a count pass until a partition overflows its share
   size_t total_mem = 0;                      // device memory size (cudaMemGetInfo is slow; asked once)
-  void *d_scan_tmp = nullptr;                // CUB scan scratch for n_parts items (n_parts is fixed once the mode is decided)
+  void *d_scan_tmp = nullptr;                // CUB scan scratch for scan_tmp_items items
   size_t scan_tmp_bytes = 0;
+  uint64_t scan_tmp_items = 0, fine_cursor_items = 0;
+  bool in_resplit = false;
   // count-of-counts of `result`, produced by phase B itself (consolidate)
   unsigned long long *d_hist = nullptr;      // HIST_DENSE_BINS bins + overflow counter
   uint64_t *d_hist_ov = nullptr;             // HIST_OVERFLOW_CAP counts >= HIST_DENSE_BINS
@@ -334,6 +336,7 @@ kmg_status decide_mode(kmg_ctx *c, uint64_t first_call_windows) {
   c->n_parts = c->n_coarse * c->n_sub;
   CU(c, cudaMalloc(&c->d_part, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long)));
   CU(c, cudaMalloc(&c->d_fine_cursor, (size_t)c->n_parts * sizeof(unsigned long long)));
+  c->fine_cursor_items = c->n_parts;
   return KMG_OK;
 }
 
@@ -356,6 +359,7 @@ kmg_status alloc_or_consolidate(kmg_ctx *c, void **p, size_t bytes, const char *
   cudaError_t e = pool_alloc(c, p, bytes ? bytes : 1);
   if (e == cudaSuccess) return KMG_OK;
   cudaGetLastError();
+  if (c->in_resplit) return fail(c, KMG_ERR_OOM, std::string("cudaMalloc(") + what + ") failed while re-splitting the runs");
   kmg_status s = consolidate(c);
   if (s != KMG_OK) return s;
   e = pool_alloc(c, p, bytes ? bytes : 1);
@@ -368,9 +372,14 @@ kmg_status alloc_or_consolidate(kmg_ctx *c, void **p, size_t bytes, const char *
 // buffers go back to the pool while the kernels are still queued, which is safe because every pool block is only ever
 // touched by work on c->stream (stream-ordered reuse).
 // coarse_len == nullptr: coarse partition p is [coarse_off[p], coarse_off[p + 1]); otherwise [coarse_off[p], coarse_off[p] + len[p]).
+// `split` != nullptr: the input is a fine-partitioned run (split->n_in partitions) that is re-split split->m ways; the new run is
+// returned in *split->out instead of being added to the pending runs.
+struct SplitPlan { uint32_t n_in, m, sub_old; Run *out; };
 kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, const std::vector<uint64_t> &coarse_off, bool owns = true,
-                         bool sync = true, const std::vector<uint64_t> *coarse_len = nullptr) {
-  const uint32_t P1 = c->n_coarse, P = c->n_parts;
+                         bool sync = true, const std::vector<uint64_t> *coarse_len = nullptr, const SplitPlan *split = nullptr) {
+  const uint32_t P1 = split ? split->n_in : c->n_coarse;
+  const uint32_t n_sub = split ? split->m : c->n_sub;
+  const uint32_t P = split ? split->n_in * split->m : c->n_parts;
   auto len_of = [&](uint32_t p) { return coarse_len ? (*coarse_len)[p] : coarse_off[p + 1] - coarse_off[p]; };
   uint64_t n = 0;
   for (uint32_t p = 0; p < P1; ++p) n += len_of(p);
@@ -382,7 +391,14 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   uint64_t tiles = 0;
   for (uint32_t p = 0; p < P1; ++p) { tprefix[p] = (uint32_t)tiles; tiles += (len_of(p) + REFINE_TILE - 1) / REFINE_TILE; }
   tprefix[P1] = (uint32_t)tiles;
-  cudaError_t e = pool_alloc(c, &d_cstart, (P1 + 1) * 8);
+  cudaError_t e = cudaSuccess;
+  if (c->fine_cursor_items < P) {  // the partition count grew (re-split)
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_fine_cursor); c->d_fine_cursor = nullptr; c->fine_cursor_items = 0;
+    CU(c, cudaMalloc(&c->d_fine_cursor, (size_t)P * sizeof(unsigned long long)));
+    c->fine_cursor_items = P;
+  }
+  e = pool_alloc(c, &d_cstart, (P1 + 1) * 8);
   if (e == cudaSuccess && coarse_len) {
     e = pool_alloc(c, &d_clen, (size_t)P1 * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_clen, coarse_len->data(), (size_t)P1 * 8, cudaMemcpyHostToDevice, c->stream);
@@ -397,13 +413,14 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   if (e != cudaSuccess) { cleanup(); free_run(c, r); return cuda_fail(c, e, "refine setup"); }
   RefineParams rp{};
   rp.keys = d_ckeys; rp.counts = d_ccounts; rp.coarse_start = d_cstart; rp.coarse_len = d_clen; rp.tile_prefix = d_tprefix;
-  rp.n_coarse = P1; rp.n_sub = c->n_sub; rp.n_tiles = (uint32_t)tiles;
+  rp.n_coarse = P1; rp.n_sub = n_sub; rp.n_tiles = (uint32_t)tiles;
+  if (split) { rp.sub_total = split->sub_old * split->m; rp.sub_old = split->sub_old; }
   // Speculative layout first: hash partitions are Poisson-sized, so every fine partition gets mean + 7 sigma + 16 slots
   // and the count pass (a full read of the keys) is skipped.  Skewed input overflows a share: the kernel then raises a
   // flag, and this chunk -- and, sticky, the rest of the job -- takes the exact count + prefix + scatter route below.
   const double mu = (double)n / P;
   const uint64_t cap_f = ((uint64_t)(mu + 7.0 * std::sqrt(mu) + 16.0) + 7) & ~7ull;
-  if (c->spec_fine_ok && mu >= 64.0 && cap_f * P < (1ull << 32) && refine_single_pass_available(c->n_sub, d_ccounts != nullptr)) {
+  if (c->spec_fine_ok && mu >= 64.0 && cap_f * P < (1ull << 32) && refine_single_pass_available(n_sub, d_ccounts != nullptr)) {
     kmg_status s = alloc_or_consolidate(c, reinterpret_cast<void **>(&r.d_keys), cap_f * P * 8, "fine keys");
     if (s != KMG_OK) { cleanup(); free_run(c, r); return s; }
     rp.fine_cap = cap_f;
@@ -420,6 +437,7 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
     if (!h_flag) {
       cleanup();
       r.n = n;
+      if (split) { *split->out = std::move(r); return KMG_OK; }
       return add_run(c, std::move(r));
     }
     c->spec_fine_ok = false;
@@ -432,10 +450,13 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   rp.fine_start = reinterpret_cast<const unsigned long long *>(r.d_seg_start);
   rp.fine_cursor = c->d_fine_cursor;
   e = launch_refine(rp, false, c->stream);
-  if (e == cudaSuccess && !c->d_scan_tmp) {
+  if (e == cudaSuccess && (!c->d_scan_tmp || c->scan_tmp_items < P)) {
+    cudaFree(c->d_scan_tmp); c->d_scan_tmp = nullptr;
     e = exclusive_sum_u64(nullptr, nullptr, P, nullptr, &c->scan_tmp_bytes, c->stream);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_scan_tmp, c->scan_tmp_bytes ? c->scan_tmp_bytes : 16);
+    c->scan_tmp_items = P;
   }
+
   if (e == cudaSuccess) e = exclusive_sum_u64(r.d_seg_len, r.d_seg_start, P, c->d_scan_tmp, &c->scan_tmp_bytes, c->stream);
   if (e != cudaSuccess) { cleanup(); free_run(c, r); return cuda_fail(c, e, "refine count"); }
   kmg_status s = alloc_or_consolidate(c, reinterpret_cast<void **>(&r.d_keys), n * 8, "fine keys");
@@ -447,6 +468,7 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   cleanup();
   if (e != cudaSuccess) { free_run(c, r); return cuda_fail(c, e, "refine scatter"); }
   r.n = n;
+  if (split) { *split->out = std::move(r); return KMG_OK; }
   return add_run(c, std::move(r));
 }
 
@@ -551,9 +573,50 @@ kmg_status keys_to_run(kmg_ctx *c, const uint64_t *d_keys, const uint64_t *d_cou
   return KMG_OK;
 }
 
+// The input outgrew the partition plan: split every fine partition of every run m ways (one streaming pass per run; the
+// sub-bin function nests, so partition p becomes partitions p*m .. p*m + m-1).  Afterwards n_sub and n_parts are m times larger.
+kmg_status resplit_runs(kmg_ctx *c, uint32_t m) {
+  const uint32_t P_old = c->n_parts;
+  std::vector<Run *> all;
+  if (c->has_result && c->result.n) all.push_back(&c->result);
+  for (auto &r : c->runs) all.push_back(&r);
+  for (auto *r : all) if (r->n >= (1ull << 32) - 1) return KMG_OK;  // refine launches index with 32 bits: leave it to the multi-pass kernel
+  c->in_resplit = true;
+  kmg_status st = KMG_OK;
+  std::vector<uint64_t> off(P_old + 1), lens(P_old);
+  for (auto *r : all) {
+    cudaError_t e = cudaMemcpyAsync(off.data(), r->d_seg_start, (size_t)P_old * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lens.data(), r->d_seg_len, (size_t)P_old * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { st = cuda_fail(c, e, "re-split (segment table)"); break; }
+    off[P_old] = P_old ? off[P_old - 1] + lens[P_old - 1] : 0;
+    Run nr;
+    SplitPlan sp{P_old, m, c->n_sub, &nr};
+    st = refine_to_run(c, r->d_keys, r->d_counts, off, /*owns=*/false, /*sync=*/true, &lens, &sp);
+    if (st != KMG_OK) break;
+    nr.n_valid = r->n_valid;
+    free_run(c, *r);
+    *r = std::move(nr);
+  }
+  c->in_resplit = false;
+  if (st != KMG_OK) return st;  // NOTE: runs already re-split and runs not yet re-split must not be mixed -- the caller gives up
+  c->n_sub *= m;
+  c->n_parts = P_old * m;
+  return KMG_OK;
+}
+
 // phase B: merge the consolidated result (if any) and all pending runs into a new consolidated run
 kmg_status consolidate(kmg_ctx *c) {
   if (c->runs.empty()) return KMG_OK;
+  {  // partitions several times larger than planned: refine the plan before counting
+    uint64_t entries = c->has_result ? c->result.n_valid : 0;
+    for (auto &r : c->runs) entries += r.n;
+    const uint64_t avg = entries / std::max<uint32_t>(c->n_parts, 1);
+    if (avg > 2 * TARGET_KEYS_PER_PART && c->n_sub * 2 <= 2048 && !c->cfg.parts_log2) {  // an explicit partition count is respected
+      const uint32_t m = (uint32_t)std::min<uint64_t>((avg + TARGET_KEYS_PER_PART - 1) / TARGET_KEYS_PER_PART, 2048 / c->n_sub);
+      if (m >= 2) { kmg_status rs = resplit_runs(c, m); if (rs != KMG_OK) return rs; }
+    }
+  }
   std::vector<Run *> in;
   if (c->has_result && c->result.n) in.push_back(&c->result);
   for (auto &r : c->runs) in.push_back(&r);

@@ -60,6 +60,10 @@ struct RefineParams {
   const uint32_t *tile_prefix;            // n_coarse + 1: first global tile number of each coarse partition
   uint32_t n_coarse, n_sub, n_tiles, row_cap;   // row_cap / row_magic: row size of the single-pass scatter (set by launch_refine)
   uint32_t row_magic, pad;
+  // bin of a key inside input partition c: sub_of_mix(mix, sub_total) - (c % sub_old) * n_sub.  Plain refinement of coarse bins:
+  // sub_total = n_sub, sub_old = 1.  Re-splitting a fine-partitioned run m ways (the sub-bin function nests: floor(x * P2 * m) / m ==
+  // floor(x * P2)): n_sub = m, sub_old = old sub-bins per coarse bin, sub_total = sub_old * m.
+  uint32_t sub_total, sub_old;
   unsigned long long *fine_counts;        // count pass
   const unsigned long long *fine_start;   // scatter pass: exclusive prefix of fine_counts
   unsigned long long *fine_cursor;        // scatter pass: zeroed

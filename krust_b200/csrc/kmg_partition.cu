@@ -127,7 +127,7 @@ __device__ __forceinline__ uint32_t refine_reserve(const RefineParams &P, uint64
 // One tile, exact two-pass procedure: histogram -> (count: add to fine_counts | scatter: prefix, one global reservation
 // per sub-bin, rank the keys into `staging` in sub-bin order, coalesced copy-out).  hist[] is zero on entry and on exit.
 template <int THREADS, bool SCATTER>
-__device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, const uint64_t begin, const uint32_t m, const uint64_t f0,
+__device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, const uint64_t begin, const uint32_t m, const uint64_t f0, const uint32_t sub_base,
                                                      uint64_t *staging, uint64_t *staging_c, uint32_t *hist, uint32_t *s_off,
                                                      uint32_t *g_base, uint32_t *s_scan) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -140,7 +140,7 @@ __device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, cons
       key[j] = i < m ? (SCATTER ? P.keys[begin + i] : __ldcs(P.keys + begin + i)) : EMPTY_KEY;
     }
 #pragma unroll
-    for (int j = 0; j < U; ++j) if (i0 + j * THREADS + tid < m) atomicAdd(hist + sub_of_mix(mix64(key[j]), P.n_sub), 1u);
+    for (int j = 0; j < U; ++j) if (i0 + j * THREADS + tid < m) atomicAdd(hist + (sub_of_mix(mix64(key[j]), P.sub_total) - sub_base), 1u);
   }
   __syncthreads();
   if (!SCATTER) {
@@ -186,7 +186,7 @@ __device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, cons
       cnt[j] = (i < m && P.counts) ? __ldcs(P.counts + begin + i) : 1ull;
     }
 #pragma unroll
-    for (int j = 0; j < U; ++j) { sb[j] = sub_of_mix(mix64(key[j]), P.n_sub); o[j] = 0; if (i0 + j * THREADS + tid < m) o[j] = atomicAdd(hist + sb[j], 1u); }
+    for (int j = 0; j < U; ++j) { sb[j] = sub_of_mix(mix64(key[j]), P.sub_total) - sub_base; o[j] = 0; if (i0 + j * THREADS + tid < m) o[j] = atomicAdd(hist + sb[j], 1u); }
 #pragma unroll
     for (int j = 0; j < U; ++j)
       if (i0 + j * THREADS + tid < m) { staging[o[j]] = key[j]; if (P.counts) staging_c[o[j]] = cnt[j]; }
@@ -194,7 +194,7 @@ __device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, cons
   __syncthreads();
   for (uint32_t i = tid; i < m; i += THREADS) {  // coalesced copy-out; destination recomputed from the key
     const uint64_t key = staging[i];
-    const uint32_t sbin = sub_of_mix(mix64(key), P.n_sub);
+    const uint32_t sbin = sub_of_mix(mix64(key), P.sub_total) - sub_base;
     if (g_base[sbin] == NO_BASE) continue;
     const uint64_t dst = (uint64_t)g_base[sbin] + (i - s_off[sbin]);
     P.out_keys[dst] = key;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
     uint32_t c, m;
     uint64_t begin;
     refine_locate_tile(P, g, &s_c, c, begin, m);
-    refine_tile_two_pass<REFINE_THREADS, SCATTER>(P, begin, m, (uint64_t)c * P.n_sub, staging, staging_c, hist, s_off, g_base, s_scan);
+    refine_tile_two_pass<REFINE_THREADS, SCATTER>(P, begin, m, (uint64_t)c * P.n_sub, (c % P.sub_old) * P.n_sub, staging, staging_c, hist, s_off, g_base, s_scan);
     __syncthreads();
   }
 }
@@ -295,11 +295,12 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
 
   for (uint32_t g = g_begin; g < g_end; ++g) {
     const uint64_t f0 = (uint64_t)c * P.n_sub;
+    const uint32_t sub_base = (c % P.sub_old) * P.n_sub;
     {  // ---- rank the tile's keys into the rows
       uint32_t sb[U], r[U];
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        sb[j] = sub_of_mix(mix64(key[j]), P.n_sub);
+        sb[j] = sub_of_mix(mix64(key[j]), P.sub_total) - sub_base;
         r[j] = 0;
         if (j * REFINE_ROWS_THREADS + tid < m) r[j] = atomicAdd(cnt + sb[j], 1u);
       }
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
     if (exact) {
       for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
       __syncthreads();
-      refine_tile_two_pass<REFINE_ROWS_THREADS, true>(P, begin, m, f0, rows, nullptr, cnt, s_off, g_base, s_scan);
+      refine_tile_two_pass<REFINE_ROWS_THREADS, true>(P, begin, m, f0, sub_base, rows, nullptr, cnt, s_off, g_base, s_scan);
     } else {
       for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) {
         const uint32_t h = cnt[s];
@@ -377,6 +378,7 @@ cudaError_t launch_fill_strided(uint64_t *d, uint64_t n, uint64_t stride, cudaSt
 cudaError_t launch_refine(const RefineParams &P_in, bool scatter, cudaStream_t s) {
   if (P_in.n_tiles == 0) return cudaSuccess;
   RefineParams P = P_in;
+  if (!P.sub_total) { P.sub_total = P.n_sub; P.sub_old = 1; }  // plain refinement of coarse bins
   cudaError_t e;
   if (scatter && refine_single_pass_available(P.n_sub, P.counts || P.out_counts)) {
     P.row_cap = std::min<uint32_t>((uint32_t)REFINE_ROWS_SLOTS / P.n_sub, REFINE_TILE);  // mean fill 8192 / (n_sub * cap) ~ 0.5

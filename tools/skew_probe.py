@@ -62,6 +62,21 @@ if "--stream" in sys.argv:
         print(f"streamed in {len(rec)} calls, no hint: {dt * 1e3:8.1f} ms  {s2['n_windows'] / dt / 1e9:6.2f} G k-mers/s  distinct {s2['n_distinct']} "
               f"consolidations {s2['n_grows']} | phase A {s2['scan_ns'] / 1e6:.1f} ms, phase B {s2['consolidate_ns'] / 1e6:.1f} ms", flush=True)
         assert s2["n_distinct"] == s["n_distinct"] and s2["n_windows"] == s["n_windows"]
+if "--stream-part" in sys.argv:
+    # 128 calls on the partitioned path: with and without a size hint (31 runs pending -> LSM-style consolidation)
+    from krust_b200 import _lib
+    cuts = np.linspace(0, n, 129).astype(np.int64)
+    for hint in (n, 0):
+        with kb.GpuKmerCounter(k, flags=_lib.KMG_FLAG_FORCE_PARTITIONED, expected_distinct=hint) as c:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                a2 = max(0, a - (k - 1)) if a else 0   # callers of a chunked feed overlap by k-1 themselves; here: separate records
+                c.count_batch(h_np[a:b], None, np.array([0, b - a], dtype=np.uint64))
+            s3 = c.finalize(True)
+            dt = time.perf_counter() - t0
+            print(f"128 calls, partitioned, hint {hint:>10}: {dt * 1e3:8.1f} ms  {s3['n_windows'] / dt / 1e9:6.2f} G k-mers/s  distinct {s3['n_distinct']} "
+                  f"consolidations {s3['n_grows']} | phase A {s3['scan_ns'] / 1e6:.1f} ms, phase B {s3['consolidate_ns'] / 1e6:.1f} ms", flush=True)
 if "--no-oracle" in sys.argv:
     sys.exit(0)
 t0 = time.perf_counter()
