@@ -614,7 +614,14 @@ kmg_status consolidate(kmg_ctx *c) {
     const uint64_t avg = entries / std::max<uint32_t>(c->n_parts, 1);
     if (avg > 2 * TARGET_KEYS_PER_PART && c->n_sub * 2 <= 2048 && !c->cfg.parts_log2) {  // an explicit partition count is respected
       const uint32_t m = (uint32_t)std::min<uint64_t>((avg + TARGET_KEYS_PER_PART - 1) / TARGET_KEYS_PER_PART, 2048 / c->n_sub);
-      if (m >= 2) { kmg_status rs = resplit_runs(c, m); if (rs != KMG_OK) return rs; }
+      // Re-splitting costs one tile (~3.5 us of one SM) per input partition or per 8192 entries of every run plus a streaming
+      // pass; counting in m passes instead costs ~7 ps per entry and extra pass, again at every later consolidation.  Many small
+      // runs over a slightly outgrown plan are cheaper in passes, one big run over a badly outgrown plan is cheaper re-split.
+      double resplit_ns = (double)entries * 0.006, passes_ns = (double)entries * (m - 1) * 0.007 * 2.0;
+      auto tiles_of = [&](const Run &r) { return (double)std::max<uint64_t>(c->n_parts, r.n / REFINE_TILE); };
+      if (c->has_result && c->result.n) resplit_ns += tiles_of(c->result) * 3500.0 / num_sms();
+      for (auto &r : c->runs) resplit_ns += tiles_of(r) * 3500.0 / num_sms();
+      if (m >= 2 && resplit_ns < passes_ns) { kmg_status rs = resplit_runs(c, m); if (rs != KMG_OK) return rs; }
     }
   }
   std::vector<Run *> in;
@@ -773,10 +780,42 @@ bool fetch_fused_hist(kmg_ctx *c) {
 }
 
 // Run the counting scan over a packed stream of n_words_total words (already in d_bases/d_valid/d_start).
+// A context that started small sits on the single HBM table (random atomics: fine while it fits L2, ~6x slower than the
+// partitioned pipeline beyond).  Once the table plus the incoming batch pass MIGRATE_KEYS it is emptied into a weighted run
+// and the context continues on the partitioned path, planned for 16x what it has seen (over-partitioning is cheap at this size;
+// re-splitting / multi-pass counting covers streams that grow further).
+constexpr uint64_t MIGRATE_KEYS = 1ull << 26;
+kmg_status migrate_to_partitioned(kmg_ctx *c, uint64_t incoming) {
+  kmg_status s = read_counters(c);
+  if (s != KMG_OK) return s;
+  const uint64_t n = c->h_counters[CTR_DISTINCT];
+  uint64_t *dk = nullptr, *dc = nullptr;
+  if (n) {
+    cudaError_t e = pool_alloc(c, &dk, n * 8);
+    if (e == cudaSuccess) e = pool_alloc(c, &dc, n * 8);
+    if (e == cudaSuccess) e = launch_compact(view_of(c), 1, dk, dc, n, c->d_stats + 3, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { pool_free(c, dk); pool_free(c, dc); return cuda_fail(c, e, "migrate to the partitioned path"); }
+  }
+  cudaFree(c->table.slots);
+  c->table = HashTable{nullptr, 0};
+  c->mode = kmg_ctx::MODE_UNDECIDED;
+  c->cfg.flags |= KMG_FLAG_FORCE_PARTITIONED;
+  s = decide_mode(c, std::max<uint64_t>(c->cfg.expected_distinct, 16 * (n + incoming)));
+  if (s == KMG_OK && n) s = keys_to_run(c, dk, dc, n);
+  pool_free(c, dk); pool_free(c, dc);
+  c->n_grows++;
+  return s;
+}
+
 kmg_status scan_packed(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
   const uint64_t n_tiles = n_words_total / TILE_WORDS;
   kmg_status ms = decide_mode(c, n_words_total * 32);
   if (ms != KMG_OK) return ms;
+  if (c->mode == kmg_ctx::MODE_TABLE && !(c->cfg.flags & KMG_FLAG_FORCE_HASH) && c->distinct_ub + n_words_total * 32 > MIGRATE_KEYS) {
+    ms = migrate_to_partitioned(c, n_words_total * 32);
+    if (ms != KMG_OK) return ms;
+  }
   if (c->mode == kmg_ctx::MODE_PARTITIONED) return scan_to_run(c, n_words_total, has_start);
   uint64_t tile0 = 0;
   const size_t tmr = timer_begin(c);

@@ -401,3 +401,33 @@ def test_input_outgrows_the_partition_plan():
         hv, hf = c.histogram(2)
         ov, of = orc.histogram(oracle[1], 2)
         assert (hv == ov).all() and (hf == of).all()
+
+
+def test_small_start_migrates_from_the_table_to_the_partitioned_path():
+    """A context whose first call is small starts on the single hash table; when the stream keeps growing it must move
+    its contents to the partitioned pipeline (weighted run) without losing or double counting anything."""
+    rng = np.random.default_rng(77)
+    k = 25
+    parts = [np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=30_000_000, dtype=np.uint8)] for _ in range(3)]
+    parts[2][:5_000_000] = parts[0][:5_000_000]  # shared sequence: counts of 2 across the migration boundary
+    with kb.GpuKmerCounter(k) as c:
+        for p in parts:
+            c.count_batch(p, None, np.array([0, len(p)], dtype=np.uint64))
+        s = c.finalize()
+        got = c.export(1, True)
+        hist = c.histogram(1)
+    assert s["path"] == 2 and s["n_windows"] == 3 * (30_000_000 - k + 1)
+    seq = np.concatenate(parts)
+    off = np.array([0, 30_000_000, 60_000_000, 90_000_000], dtype=np.uint64)
+    with kb.GpuKmerCounter(k, flags=PART) as c:
+        c.count_batch(seq, None, off)
+        s2 = c.finalize()
+        want = c.export(1, True)
+        hist2 = c.histogram(1)
+    assert s2["n_distinct"] == s["n_distinct"] and s2["max_count"] == s["max_count"]
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+    assert (hist[0] == hist2[0]).all() and (hist[1] == hist2[1]).all()
+    # and an oracle check on a slice of the key space: the 5 Mbp shared block alone
+    ok, oc, _ = orc.count_batch(k, parts[0][:200_000], None, np.array([0, 200_000], dtype=np.uint64))
+    idx = np.searchsorted(got[0], ok)
+    assert (got[0][idx] == ok).all() and (got[1][idx] >= 2 * oc).all()

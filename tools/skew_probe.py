@@ -55,8 +55,12 @@ if "--stream" in sys.argv:
     with kb.GpuKmerCounter(k) as c:
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        per_call = []
         for a, b in rec:
+            t1 = time.perf_counter()
             c.count_batch(h_np[a:b], None, np.array([0, b - a], dtype=np.uint64))
+            per_call.append((time.perf_counter() - t1) * 1e3)
+        print("per-call ms:", " ".join(f"{x:.1f}" for x in per_call), flush=True)
         s2 = c.finalize(True)
         dt = time.perf_counter() - t0
         print(f"streamed in {len(rec)} calls, no hint: {dt * 1e3:8.1f} ms  {s2['n_windows'] / dt / 1e9:6.2f} G k-mers/s  distinct {s2['n_distinct']} "
