@@ -51,7 +51,7 @@ enum {
   KMG_FLAG_FORCE_HASH = 1u,         /* use the single open-addressing HBM table (never the 4^k array / partitions) */
   KMG_FLAG_FORCE_DIRECT = 2u,       /* use the direct-indexed 4^k array (k <= 14 only) */
   KMG_FLAG_NO_PREAGG = 4u,          /* disable duplicate pre-aggregation (for A/B measurements) */
-  KMG_FLAG_FORCE_PARTITIONED = 8u   /* use the partitioned pipeline (hash partitions counted in L2-resident tables) */
+  KMG_FLAG_FORCE_PARTITIONED = 8u   /* use the partitioned pipeline (hash partitions counted in shared-memory tables) */
 };
 
 /* Replaces: KmerLength::new (src/kmer.rs:100) + the Option<u8> min_quality argument of
@@ -65,8 +65,11 @@ typedef struct kmg_config {
   uint8_t min_quality;        /* Phred; a base passes iff qual_byte >= saturating_add(min_quality, 33) (src/run.rs:538) */
   uint8_t parts_log2;         /* partitioned pipeline: log2(#partitions), 0 = choose from the input size (max 20) */
   uint8_t reserved[5];
-  uint64_t expected_distinct; /* capacity hint (distinct canonical k-mers); 0 = start small and grow */
-  uint64_t batch_bases;       /* capacity of each pinned staging buffer in bases; 0 = default */
+  uint64_t expected_distinct; /* capacity hint (distinct canonical k-mers, or simply the number of bases to come); 0 = plan from
+                                 the first call and adapt: the hash table migrates to the partitioned pipeline past 2^26 keys,
+                                 an outgrown partition plan is re-split.  A good hint avoids that extra work. */
+  uint64_t batch_bases;       /* bases per staging chunk of kmg_count_ascii (4 chunks in flight) and capacity of a pre-packed
+                                 batch; 0 = default (2^28) */
   void *stream;               /* cudaStream_t to run on; NULL = library-owned stream (pass cudaStreamLegacy, 0x1, to
                                  share the legacy default stream with e.g. a torch process) */
 } kmg_config;
@@ -83,11 +86,11 @@ typedef struct kmg_summary {
   uint64_t max_count;
   uint64_t table_capacity;  /* slots (hash path) or 4^k (direct path) */
   uint32_t path;            /* 0 = hash table, 1 = direct-indexed array, 2 = partitioned pipeline */
-  uint32_t n_grows;         /* number of rehash/grow events (path 0) or consolidation passes (path 2) */
+  uint32_t n_grows;         /* number of rehash/grow events (path 0; + 1 for a migration to path 2) or consolidation passes (path 2) */
   uint64_t kernel_ns;       /* device time spent in the counting kernels (CUDA events on the launching stream) */
   uint64_t h2d_bytes;
   uint64_t scan_ns;         /* of kernel_ns: tile scan (+ upsert on paths 0/1, + partition scatter on path 2) */
-  uint64_t consolidate_ns;  /* of kernel_ns: path 2 phase B (L2-resident partition tables) */
+  uint64_t consolidate_ns;  /* of kernel_ns: path 2 phase B (one CTA per hash partition, table in shared memory) */
 } kmg_summary;
 
 /* One pinned, library-owned staging buffer for the pre-packed feed (the Rust reader packs
