@@ -376,7 +376,8 @@ kmg_status alloc_or_consolidate(kmg_ctx *c, void **p, size_t bytes, const char *
 // returned in *split->out instead of being added to the pending runs.
 struct SplitPlan { uint32_t n_in, m, sub_old; Run *out; };
 kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, const std::vector<uint64_t> &coarse_off, bool owns = true,
-                         bool sync = true, const std::vector<uint64_t> *coarse_len = nullptr, const SplitPlan *split = nullptr) {
+                         bool sync = true, const std::vector<uint64_t> *coarse_len = nullptr, const SplitPlan *split = nullptr,
+                         bool in_keys = false) {  // in_keys: the input holds plain keys, not mixes (blocks adopted from another rank)
   const uint32_t P1 = split ? split->n_in : c->n_coarse;
   const uint32_t n_sub = split ? split->m : c->n_sub;
   const uint32_t P = split ? split->n_in * split->m : c->n_parts;
@@ -415,6 +416,7 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   rp.keys = d_ckeys; rp.counts = d_ccounts; rp.coarse_start = d_cstart; rp.coarse_len = d_clen; rp.tile_prefix = d_tprefix;
   rp.n_coarse = P1; rp.n_sub = n_sub; rp.n_tiles = (uint32_t)tiles;
   if (split) { rp.sub_total = split->sub_old * split->m; rp.sub_old = split->sub_old; }
+  rp.in_keys = in_keys ? 1u : 0u;
   // Speculative layout first: hash partitions are Poisson-sized, so every fine partition gets mean + 7 sigma + 16 slots
   // and the count pass (a full read of the keys) is skipped.  Skewed input overflows a share: the kernel then raises a
   // flag, and this chunk -- and, sticky, the rest of the job -- takes the exact count + prefix + scatter route below.
@@ -506,7 +508,7 @@ kmg_status scan_to_run(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
         uint32_t h_flag = 0;
         cudaError_t e = cudaMemsetAsync(sin.overflow_flag, 0, 4, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_start, off.data(), P1 * 8, cudaMemcpyHostToDevice, c->stream);
-        if (e == cudaSuccess) e = launch_scan_partition(sin, P1, true, d_cnt, d_start, d_cur, d_ckeys, c->d_counters, c->stream);
+        if (e == cudaSuccess) e = launch_scan_partition(sin, P1, true, d_cnt, d_start, d_cur, d_ckeys, c->d_counters, c->stream, /*mixed=*/true);
         if (e == cudaSuccess) e = cudaMemcpyAsync(lens.data(), d_cur, P1 * 8, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, sin.overflow_flag, 4, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -537,7 +539,7 @@ kmg_status scan_to_run(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
     kmg_status s = alloc_or_consolidate(c, reinterpret_cast<void **>(&d_ckeys), n * 8, "coarse keys");
     if (s != KMG_OK) return s;
     CU(c, cudaMemcpyAsync(d_start, off.data(), P1 * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(c, launch_scan_partition(in, P1, true, d_cnt, d_start, d_cur, d_ckeys, c->d_counters, c->stream));
+    CU(c, launch_scan_partition(in, P1, true, d_cnt, d_start, d_cur, d_ckeys, c->d_counters, c->stream, /*mixed=*/true));
     s = refine_to_run(c, d_ckeys, nullptr, off, /*owns=*/true, /*sync=*/false);  // input is the context's own packed stream
     timer_end(c, tmr);
     if (s != KMG_OK) return s;
@@ -707,7 +709,7 @@ kmg_status consolidate(kmg_ctx *c) {
     prm.error_flag = reinterpret_cast<uint32_t *>(d_sync + 1) + 1;
     e = cudaMemsetAsync(d_sync, 0, 24, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_hist, 0, (HIST_DENSE_BINS + 1) * sizeof(unsigned long long), c->stream);
-    if (e == cudaSuccess && slots) e = launch_table_init(HashTable{d_scratch, slots}, c->stream);
+    if (e == cudaSuccess && slots) e = launch_table_init(HashTable{d_scratch, slots}, c->stream, EMPTY_MIX);
     const size_t tmr = timer_begin(c, 1);
     bool weighted = max_total > ((2ull * SMEM_COUNT_THREADS * 8) << split_log2);  // partitions oversized beyond the split want the pre-aggregating variant
     for (uint32_t r = 0; r < R; ++r) weighted |= in[r]->d_counts != nullptr;
@@ -1256,7 +1258,7 @@ KMG_EXPORT kmg_status kmg_adopt_coarse_device(kmg_ctx *c, const uint64_t *d_keys
   if (!d_keys) return fail(c, KMG_ERR_INVALID_ARG, "d_keys is NULL");
   CU(c, cudaSetDevice(c->device));
   const size_t tmr = timer_begin(c, 0);
-  kmg_status s = refine_to_run(c, const_cast<uint64_t *>(d_keys), nullptr, off, /*owns=*/false);  // synchronises before returning
+  kmg_status s = refine_to_run(c, const_cast<uint64_t *>(d_keys), nullptr, off, /*owns=*/false, /*sync=*/true, nullptr, nullptr, /*in_keys=*/true);
   timer_end(c, tmr);
   return s;
 }

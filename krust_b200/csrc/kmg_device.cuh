@@ -32,6 +32,18 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 
+// inverse of mix64 (every step of the finaliser is a bijection: x ^= x >> 33 is an involution, the multipliers are odd)
+__host__ __device__ __forceinline__ uint64_t unmix64(uint64_t x) {
+  x ^= x >> 33; x *= 0x9cb4b2f8129337dbull;  // inverse of 0xc4ceb9fe1a85ec53 mod 2^64
+  x ^= x >> 33; x *= 0x4f74430c22a54005ull;  // inverse of 0xff51afd7ed558ccd mod 2^64
+  x ^= x >> 33;
+  return x;
+}
+// The partitioned pipeline carries MIXED keys (v = mix64(key)) through its runs: every stage needs hash bits, none needs the
+// key itself, and the mix is a bijection, so equality of mixes is equality of keys; the key is recovered with unmix64 when
+// a result leaves the table (export / compaction).  EMPTY_MIX = mix64(EMPTY_KEY) can therefore never be a stored value.
+constexpr uint64_t EMPTY_MIX = 0x64b5720b4b825f21ull;
+
 // Multiply-shift range reduction of a 32-bit hash to [0, n).  On the device this MUST be the __umulhi
 // intrinsic: nvcc 12.9 miscompiled the equivalent 64-bit expression when it indexed a shared-memory
 // atomic (the IMAD.HI term vanished and every key landed in bin 0; tools/test_partkeys.cu).

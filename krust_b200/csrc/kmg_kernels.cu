@@ -547,6 +547,9 @@ __global__ void __launch_bounds__(WSCATTER_THREADS) partition_scatter_warp_kerne
 constexpr int STAGE_THREADS = 512;
 constexpr int STAGE_SUB_WORDS = 512;                 // 16384 windows per sub-tile
 constexpr int STAGE_KEYS = STAGE_SUB_WORDS * 32;     // staging capacity (128 KiB)
+// MIXED: what is staged / written is mix64(key) (the partitioned pipeline's internal streams, kmg_device.cuh); otherwise the key
+// itself (kmg_extract_keys_device hands keys to the caller).
+template <bool MIXED>
 struct StageEmit {
   uint32_t *cursor;   // smem: next staging slot of each partition
   uint64_t *staging;  // smem
@@ -554,13 +557,14 @@ struct StageEmit {
   template <int G>
   __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
     uint32_t p[G], o[G];
+    uint64_t v[G];
 #pragma unroll
-    for (int j = 0; j < G; ++j) p[j] = part_of(key[j], n_parts);
+    for (int j = 0; j < G; ++j) { const uint64_t m = mix64(key[j]); p[j] = coarse_of_mix(m, n_parts); v[j] = MIXED ? m : key[j]; }
 #pragma unroll
     for (int j = 0; j < G; ++j) { o[j] = 0; if ((okg >> j) & 1u) o[j] = atomicAdd(cursor + p[j], 1u); }
 #pragma unroll
     for (int j = 0; j < G; ++j)
-      if ((okg >> j) & 1u) staging[o[j]] = key[j];
+      if ((okg >> j) & 1u) staging[o[j]] = v[j];
   }
 };
 // where partition p's share of this sub-tile lands in `out` (see ScanInput::part_cap)
@@ -575,7 +579,7 @@ __device__ __forceinline__ uint32_t part_reserve(const ScanInput &in, const unsi
 
 // One sub-tile (n_words words starting at w0), exact: histogram -> prefix + one global reservation per partition ->
 // rank pass into `staging` -> coalesced copy-out.  hist[] is zero on entry and on exit; ends with a barrier.
-template <int THREADS>
+template <int THREADS, bool MIXED>
 __device__ __forceinline__ void stage_subtile_exact(const TileSmem *ts, int w0, int n_words, const ScanInput &in, bool has_start,
                                                     uint32_t n_parts, const unsigned long long *part_start, unsigned long long *part_cursor,
                                                     uint64_t *out, uint64_t *staging, uint32_t *hist, uint32_t *s_off, uint32_t *g_base,
@@ -616,14 +620,14 @@ __device__ __forceinline__ void stage_subtile_exact(const TileSmem *ts, int w0, 
   const uint32_t n_sub = s_scan[THREADS / 32];
   __syncthreads();
   {
-    StageEmit e{hist, staging, n_parts};
+    StageEmit<MIXED> e{hist, staging, n_parts};
 #pragma unroll 1
     for (int w = tid; w < n_words; w += THREADS) scan_word<8>(ts, w0 + w, in.k, has_start, e);
   }
   __syncthreads();
   for (uint32_t i = tid; i < n_sub; i += THREADS) {  // coalesced copy-out
     const uint64_t key = staging[i];
-    const uint32_t p = part_of(key, n_parts);
+    const uint32_t p = MIXED ? coarse_of_mix(key, n_parts) : part_of(key, n_parts);
     if (g_base[p] != NO_BASE) __stcs(out + ((uint64_t)g_base[p] + (i - s_off[p])), key);
   }
   __syncthreads();
@@ -631,6 +635,7 @@ __device__ __forceinline__ void stage_subtile_exact(const TileSmem *ts, int w0, 
   __syncthreads();
 }
 
+template <bool MIXED>
 __global__ void __launch_bounds__(STAGE_THREADS, 1) partition_scatter_staged_kernel(ScanInput in, uint32_t n_parts,
                                                                                      const unsigned long long *part_start,
                                                                                      unsigned long long *part_cursor, uint64_t *out) {
@@ -656,7 +661,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) partition_scatter_staged_ker
     if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
     wait_stage(bars, stage, phase0, phase1);
     for (int sub = 0; sub < TILE_WORDS / STAGE_SUB_WORDS; ++sub)
-      stage_subtile_exact<STAGE_THREADS>(&stages[stage], sub * STAGE_SUB_WORDS, STAGE_SUB_WORDS, in, has_start, n_parts, part_start,
+      stage_subtile_exact<STAGE_THREADS, MIXED>(&stages[stage], sub * STAGE_SUB_WORDS, STAGE_SUB_WORDS, in, has_start, n_parts, part_start,
                                          part_cursor, out, staging, hist, s_off, g_base, s_scan);
     stage ^= 1;
   }
@@ -674,6 +679,7 @@ constexpr int ROWS_THREADS = 1024;
 constexpr int ROWS_SUB_WORDS = ROWS_THREADS / 4;   // 8192 windows per sub-tile
 constexpr int ROWS_SLOTS = 16384;                  // n_parts rows of 2^cl keys (128 KiB; also the staging buffer of the exact route)
 constexpr int ROWS_OVERFLOW = 512;
+template <bool MIXED>
 struct RowsEmit {
   uint32_t *cnt;
   uint64_t *rows, *ov_key;
@@ -682,17 +688,18 @@ struct RowsEmit {
   template <int G>
   __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
     uint32_t p[G], r[G];
+    uint64_t v[G];
 #pragma unroll
-    for (int j = 0; j < G; ++j) p[j] = part_of(key[j], n_parts);
+    for (int j = 0; j < G; ++j) { const uint64_t m = mix64(key[j]); p[j] = coarse_of_mix(m, n_parts); v[j] = MIXED ? m : key[j]; }
 #pragma unroll
     for (int j = 0; j < G; ++j) { r[j] = 0; if ((okg >> j) & 1u) r[j] = atomicAdd(cnt + p[j], 1u); }
 #pragma unroll
     for (int j = 0; j < G; ++j) {
       if (!((okg >> j) & 1u)) continue;
-      if (r[j] < cap) rows[p[j] * cap + r[j]] = key[j];
+      if (r[j] < cap) rows[p[j] * cap + r[j]] = v[j];
       else {
         const uint32_t o = atomicAdd(ov_n, 1u);
-        if (o < (uint32_t)ROWS_OVERFLOW) { ov_key[o] = key[j]; ov_meta[o] = (p[j] << 16) | r[j]; }  // r < 8192, p < 2048
+        if (o < (uint32_t)ROWS_OVERFLOW) { ov_key[o] = v[j]; ov_meta[o] = (p[j] << 16) | r[j]; }  // r < 8192, p < 2048
       }
     }
   }
@@ -723,6 +730,7 @@ __device__ __forceinline__ void scan_octet(const TileSmem *ts, int i, int g, int
   }
   emit.template group<8>(key, okg);
 }
+template <bool MIXED>
 __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel(ScanInput in, uint32_t n_parts, uint32_t cap, uint32_t magic,
                                                                                   const unsigned long long *part_start,
                                                                                   unsigned long long *part_cursor, uint64_t *out) {
@@ -752,7 +760,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
     for (int sub = 0; sub < TILE_WORDS / ROWS_SUB_WORDS; ++sub) {
       const int w0 = sub * ROWS_SUB_WORDS;
       {
-        RowsEmit e{cnt, rows, ov_key, ov_meta, &s_ovn, n_parts, cap};
+        RowsEmit<MIXED> e{cnt, rows, ov_key, ov_meta, &s_ovn, n_parts, cap};
         scan_octet(ts, w0 + (tid >> 2), tid & 3, in.k, has_start, e);
       }
       __syncthreads();
@@ -760,7 +768,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
       if (n_ov > (uint32_t)ROWS_OVERFLOW) {  // block-uniform: skewed sub-tile, take the exact route
         for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
         __syncthreads();
-        stage_subtile_exact<ROWS_THREADS>(ts, w0, ROWS_SUB_WORDS, in, has_start, n_parts, part_start, part_cursor, out, rows, cnt, s_off,
+        stage_subtile_exact<ROWS_THREADS, MIXED>(ts, w0, ROWS_SUB_WORDS, in, has_start, n_parts, part_start, part_cursor, out, rows, cnt, s_off,
                                           g_base, s_scan);
       } else {
         for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) {
@@ -791,10 +799,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
 // =================================================================================================
 // Table maintenance, weighted inserts, compaction (K5), histogram (K6)
 // =================================================================================================
-__global__ void table_init_kernel(uint64_t *slots, uint64_t cap) {
+__global__ void table_init_kernel(uint64_t *slots, uint64_t cap, uint64_t empty) {
   ulonglong2 *p = reinterpret_cast<ulonglong2 *>(slots);
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
-    p[i] = make_ulonglong2(EMPTY_KEY, 0ull);
+    p[i] = make_ulonglong2(empty, 0ull);
 }
 
 __global__ void insert_keys_kernel(HashTable t, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ counts,
@@ -840,7 +848,7 @@ __global__ void rehash_kernel(HashTable from, HashTable to, unsigned long long *
 
 // A "view" unifies both table kinds for the read-side kernels: entry i is (key, count); empty if count == 0.
 __device__ __forceinline__ bool view_get(const TableView &v, uint64_t i, uint64_t &key, uint64_t &count) {
-  if (v.pair_keys) { key = v.pair_keys[i]; count = v.pair_counts[i]; return count != 0; }  // count 0: filler entry of a multi-pass partition
+  if (v.pair_keys) { key = unmix64(v.pair_keys[i]); count = v.pair_counts[i]; return count != 0; }  // runs hold mixed keys; count 0: filler entry of a multi-pass partition
   if (v.dense) { key = i; count = v.dense[i]; return count != 0; }
   ulonglong2 s = reinterpret_cast<const ulonglong2 *>(v.slots)[i];
   key = s.x; count = s.y + 1;  // slots store occurrences - 1
@@ -1006,7 +1014,7 @@ bool scan_scatter_supports_cap(uint32_t n_parts) {  // the rows / staged kernels
 
 cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool scatter, unsigned long long *part_counts,
                                   const unsigned long long *part_start, unsigned long long *part_cursor, uint64_t *out,
-                                  unsigned long long *counters, cudaStream_t s) {
+                                  unsigned long long *counters, cudaStream_t s, bool mixed) {
   if (in.n_tiles == 0) return cudaSuccess;
   const size_t smem = 2 * sizeof(TileSmem) + (size_t)n_parts * sizeof(uint32_t);
   const uint64_t max_ctas = (uint64_t)num_sms() * (smem > 100 * 1024 ? 1 : smem > 72 * 1024 ? 2 : SCAN_CTAS_PER_SM);
@@ -1017,13 +1025,19 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
   if (scatter && n_parts <= (uint32_t)ROWS_SLOTS / 8 && !getenv("KMG_SCATTER")) {  // single-scan rows variant (default)
     const uint32_t cap = std::min<uint32_t>((uint32_t)ROWS_SLOTS / n_parts, ROWS_SUB_WORDS * 32);  // mean fill 8192 / (n_parts * cap) ~ 0.5
     const uint32_t magic = (uint32_t)(((1ull << 32) + cap - 1) / cap);
-    if ((e = set_smem(partition_scatter_rows_kernel, rwsmem)) != cudaSuccess) return e;
+    const unsigned grid = (unsigned)std::min<uint64_t>(in.n_tiles, (uint64_t)num_sms());
+    if ((e = mixed ? set_smem(partition_scatter_rows_kernel<true>, rwsmem) : set_smem(partition_scatter_rows_kernel<false>, rwsmem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    partition_scatter_rows_kernel<<<(unsigned)std::min<uint64_t>(in.n_tiles, (uint64_t)num_sms()), ROWS_THREADS, rwsmem, s>>>(in, n_parts, cap, magic, part_start, part_cursor, out);
+    if (mixed) partition_scatter_rows_kernel<true><<<grid, ROWS_THREADS, rwsmem, s>>>(in, n_parts, cap, magic, part_start, part_cursor, out);
+    else partition_scatter_rows_kernel<false><<<grid, ROWS_THREADS, rwsmem, s>>>(in, n_parts, cap, magic, part_start, part_cursor, out);
   } else if (scatter && stsmem <= 220 * 1024 && !(getenv("KMG_SCATTER") && atoi(getenv("KMG_SCATTER")) != 0)) {  // staged variant (KMG_SCATTER=0, or > 2048 partitions)
-    if ((e = set_smem(partition_scatter_staged_kernel, stsmem)) != cudaSuccess) return e;
+    const unsigned grid = (unsigned)std::min<uint64_t>(in.n_tiles, (uint64_t)num_sms());
+    if ((e = mixed ? set_smem(partition_scatter_staged_kernel<true>, stsmem) : set_smem(partition_scatter_staged_kernel<false>, stsmem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    partition_scatter_staged_kernel<<<(unsigned)std::min<uint64_t>(in.n_tiles, (uint64_t)num_sms()), STAGE_THREADS, stsmem, s>>>(in, n_parts, part_start, part_cursor, out);
+    if (mixed) partition_scatter_staged_kernel<true><<<grid, STAGE_THREADS, stsmem, s>>>(in, n_parts, part_start, part_cursor, out);
+    else partition_scatter_staged_kernel<false><<<grid, STAGE_THREADS, stsmem, s>>>(in, n_parts, part_start, part_cursor, out);
+  } else if (scatter && mixed) {
+    return cudaErrorInvalidValue;  // > 8192-ish partitions with mixed output: no kernel variant (the plan never asks for it)
   } else if (scatter && wsmem <= 110 * 1024 && !(getenv("KMG_SCATTER") && atoi(getenv("KMG_SCATTER")) == 2)) {  // warp-multisplit variant: >= 2 CTAs/SM
     if ((e = set_smem(partition_scatter_warp_kernel, wsmem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1042,9 +1056,9 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
   return cudaGetLastError();
 }
 
-cudaError_t launch_table_init(HashTable t, cudaStream_t s) {
+cudaError_t launch_table_init(HashTable t, cudaStream_t s, uint64_t empty) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  table_init_kernel<<<grid_for(t.cap, 256, 8), 256, 0, s>>>(t.slots, t.cap);
+  table_init_kernel<<<grid_for(t.cap, 256, 8), 256, 0, s>>>(t.slots, t.cap, empty);
   return cudaGetLastError();
 }
 cudaError_t launch_insert_keys(HashTable t, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n,

@@ -64,6 +64,7 @@ struct RefineParams {
   // sub_total = n_sub, sub_old = 1.  Re-splitting a fine-partitioned run m ways (the sub-bin function nests: floor(x * P2 * m) / m ==
   // floor(x * P2)): n_sub = m, sub_old = old sub-bins per coarse bin, sub_total = sub_old * m.
   uint32_t sub_total, sub_old;
+  uint32_t in_keys, pad1;                 // 1: the input holds plain keys (adopted from another rank) -- mix on load; the output is always mixed
   unsigned long long *fine_counts;        // count pass
   const unsigned long long *fine_start;   // scatter pass: exclusive prefix of fine_counts
   unsigned long long *fine_cursor;        // scatter pass: zeroed
@@ -116,7 +117,7 @@ cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, un
 // out[part_start[p] + ...]; part_cursor[] (zeroed) hands out ranges inside each partition.
 cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool scatter, unsigned long long *part_counts,
                                   const unsigned long long *part_start, unsigned long long *part_cursor, uint64_t *out,
-                                  unsigned long long *counters, cudaStream_t s);
+                                  unsigned long long *counters, cudaStream_t s, bool mixed = false);  // mixed: write mix64(key)
 bool scan_scatter_supports_cap(uint32_t n_parts);
 cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n, uint32_t n_coarse, bool scatter,
                                unsigned long long *coarse_counts, const unsigned long long *coarse_start,
@@ -132,7 +133,7 @@ cudaError_t launch_count_partitions_smem(const CountParams &P, bool weighted, cu
 cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, void *tmp, size_t *tmp_bytes, cudaStream_t s);
 int num_sms();
 void set_debug(uint32_t v);  // ablation switches (tools/ablate.py)
-cudaError_t launch_table_init(HashTable t, cudaStream_t s);
+cudaError_t launch_table_init(HashTable t, cudaStream_t s, uint64_t empty = ~0ull);  // empty: EMPTY_KEY, or EMPTY_MIX for phase B scratch
 cudaError_t launch_insert_keys(HashTable t, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n,
                                unsigned long long *counters, cudaStream_t s);
 cudaError_t launch_insert_keys_dense(unsigned long long *dense, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n,

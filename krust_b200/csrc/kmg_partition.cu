@@ -66,11 +66,11 @@ __global__ void __launch_bounds__(256) keys_coarse_kernel(const uint64_t *__rest
           cnt[j] = (i < m && counts) ? counts[t0 + i] : 1ull;
         }
 #pragma unroll
-        for (int j = 0; j < U; ++j) { p[j] = coarse_of_mix(mix64(key[j]), n_coarse); o[j] = 0; if (i0 + j * 256 + threadIdx.x < m) o[j] = atomicAdd(hist + p[j], 1u); }
+        for (int j = 0; j < U; ++j) { key[j] = mix64(key[j]); p[j] = coarse_of_mix(key[j], n_coarse); o[j] = 0; if (i0 + j * 256 + threadIdx.x < m) o[j] = atomicAdd(hist + p[j], 1u); }
 #pragma unroll
         for (int j = 0; j < U; ++j)
           if (i0 + j * 256 + threadIdx.x < m) {
-            out_keys[o[j]] = key[j];
+            out_keys[o[j]] = key[j];  // the runs carry MIXED keys (kmg_device.cuh)
             if (out_counts) out_counts[o[j]] = cnt[j];
           }
       }
@@ -140,7 +140,7 @@ __device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, cons
       key[j] = i < m ? (SCATTER ? P.keys[begin + i] : __ldcs(P.keys + begin + i)) : EMPTY_KEY;
     }
 #pragma unroll
-    for (int j = 0; j < U; ++j) if (i0 + j * THREADS + tid < m) atomicAdd(hist + (sub_of_mix(mix64(key[j]), P.sub_total) - sub_base), 1u);
+    for (int j = 0; j < U; ++j) if (i0 + j * THREADS + tid < m) atomicAdd(hist + (sub_of_mix(P.in_keys ? mix64(key[j]) : key[j], P.sub_total) - sub_base), 1u);
   }
   __syncthreads();
   if (!SCATTER) {
@@ -186,7 +186,7 @@ __device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, cons
       cnt[j] = (i < m && P.counts) ? __ldcs(P.counts + begin + i) : 1ull;
     }
 #pragma unroll
-    for (int j = 0; j < U; ++j) { sb[j] = sub_of_mix(mix64(key[j]), P.sub_total) - sub_base; o[j] = 0; if (i0 + j * THREADS + tid < m) o[j] = atomicAdd(hist + sb[j], 1u); }
+    for (int j = 0; j < U; ++j) { if (P.in_keys) key[j] = mix64(key[j]); sb[j] = sub_of_mix(key[j], P.sub_total) - sub_base; o[j] = 0; if (i0 + j * THREADS + tid < m) o[j] = atomicAdd(hist + sb[j], 1u); }
 #pragma unroll
     for (int j = 0; j < U; ++j)
       if (i0 + j * THREADS + tid < m) { staging[o[j]] = key[j]; if (P.counts) staging_c[o[j]] = cnt[j]; }
@@ -194,7 +194,7 @@ __device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, cons
   __syncthreads();
   for (uint32_t i = tid; i < m; i += THREADS) {  // coalesced copy-out; destination recomputed from the key
     const uint64_t key = staging[i];
-    const uint32_t sbin = sub_of_mix(mix64(key), P.sub_total) - sub_base;
+    const uint32_t sbin = sub_of_mix(key, P.sub_total) - sub_base;  // staged values are mixed keys
     if (g_base[sbin] == NO_BASE) continue;
     const uint64_t dst = (uint64_t)g_base[sbin] + (i - s_off[sbin]);
     P.out_keys[dst] = key;
@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
       uint32_t sb[U], r[U];
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        sb[j] = sub_of_mix(mix64(key[j]), P.sub_total) - sub_base;
+        if (P.in_keys) key[j] = mix64(key[j]);
+        sb[j] = sub_of_mix(key[j], P.sub_total) - sub_base;
         r[j] = 0;
         if (j * REFINE_ROWS_THREADS + tid < m) r[j] = atomicAdd(cnt + sb[j], 1u);
       }
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         const uint64_t idx = base + (uint64_t)j * COUNT_THREADS + tid;
-        w[j] = 0; key[j] = EMPTY_KEY;
+        w[j] = 0; key[j] = EMPTY_MIX;
         if (idx < n_p) {
           while (r + 1 < P.R && idx >= seg_prefix[r + 1]) ++r;
           const uint64_t src = seg_begin[r] + (idx - seg_prefix[r]);
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
         // of each run upserts once with the run length; this bounds same-address atomic bursts on skewed inputs.
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-          const uint64_t kk = w[j] ? key[j] : EMPTY_KEY;
+          const uint64_t kk = w[j] ? key[j] : EMPTY_MIX;
           const uint64_t kp = __shfl_up_sync(0xffffffffu, kk, 1);
           const bool head = lane == 0 || kp != kk;
           const uint32_t heads = __ballot_sync(0xffffffffu, head);
@@ -533,14 +534,14 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
       uint32_t pend = 0;
 #pragma unroll
       for (int j = 0; j < G; ++j) {  // first probes of all G keys in flight together
-        slot[j] = mix64(key[j]) & mask;  // lowest mix bits; coarse / sub-bin used the top bits of each half
+        slot[j] = key[j] & mask;  // the stored values ARE the mixes: lowest bits here, coarse / sub-bin used the top bits of each half
         cur[j] = 0;
-        if (w[j]) cur[j] = atomicCAS(table + 2 * slot[j], EMPTY_KEY, key[j]);
+        if (w[j]) cur[j] = atomicCAS(table + 2 * slot[j], EMPTY_MIX, key[j]);
       }
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         if (!w[j]) continue;
-        if (cur[j] == EMPTY_KEY) { ++new_keys; if (w[j] > 1) atomicAdd(table + 2 * slot[j] + 1, (unsigned long long)(w[j] - 1)); }
+        if (cur[j] == EMPTY_MIX) { ++new_keys; if (w[j] > 1) atomicAdd(table + 2 * slot[j] + 1, (unsigned long long)(w[j] - 1)); }
         else if (cur[j] == key[j]) atomicAdd(table + 2 * slot[j] + 1, (unsigned long long)w[j]);
         else pend |= 1u << j;
       }
@@ -552,11 +553,11 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
           if (pend >> j & 1u) { slot[j] = (slot[j] + 1) & mask; cur[j] = *reinterpret_cast<volatile unsigned long long *>(table + 2 * slot[j]); }
 #pragma unroll
         for (int j = 0; j < G; ++j)
-          if ((pend >> j & 1u) && cur[j] == EMPTY_KEY) cur[j] = atomicCAS(table + 2 * slot[j], EMPTY_KEY, key[j]);
+          if ((pend >> j & 1u) && cur[j] == EMPTY_MIX) cur[j] = atomicCAS(table + 2 * slot[j], EMPTY_MIX, key[j]);
 #pragma unroll
         for (int j = 0; j < G; ++j) {
           if (!(pend >> j & 1u)) continue;
-          if (cur[j] == EMPTY_KEY) { ++new_keys; if (w[j] > 1) atomicAdd(table + 2 * slot[j] + 1, (unsigned long long)(w[j] - 1)); pend &= ~(1u << j); }
+          if (cur[j] == EMPTY_MIX) { ++new_keys; if (w[j] > 1) atomicAdd(table + 2 * slot[j] + 1, (unsigned long long)(w[j] - 1)); pend &= ~(1u << j); }
           else if (cur[j] == key[j]) { atomicAdd(table + 2 * slot[j] + 1, (unsigned long long)w[j]); pend &= ~(1u << j); }
         }
       }
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
     // ---- compact the table into the output run and clean it
     const unsigned long long out0 = s_base;
     uint32_t mine = 0;
-    for (uint64_t i = tid; i <= mask; i += COUNT_THREADS) mine += __ldcg(table + 2 * i) != EMPTY_KEY;
+    for (uint64_t i = tid; i <= mask; i += COUNT_THREADS) mine += __ldcg(table + 2 * i) != EMPTY_MIX;
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -596,12 +597,12 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
     const ulonglong2 *tab2 = reinterpret_cast<const ulonglong2 *>(table);
     for (uint64_t i = tid; i <= mask; i += COUNT_THREADS) {  // trip count is warp-uniform (mask + 1 is a multiple of 256)
       const ulonglong2 sl = __ldcg(tab2 + i);
-      const bool used = sl.x != EMPTY_KEY;
+      const bool used = sl.x != EMPTY_MIX;
       if (used) {
         __stcs(P.out_keys + o, sl.x);
         __stcs(P.out_counts + o, sl.y + 1);  // slots store occurrences - 1
         ++o;
-        reinterpret_cast<ulonglong2 *>(table)[i] = make_ulonglong2(EMPTY_KEY, 0ull);
+        reinterpret_cast<ulonglong2 *>(table)[i] = make_ulonglong2(EMPTY_MIX, 0ull);
       }
       if (P.hist) hist_note(used, sl.y + 1, s_hist, P, lane);
     }
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint16_t *wlist = slist + warp * WLIST;
   if (tid < HIST_CTA_BINS) s_hist[tid] = 0;
-  for (uint32_t i = tid; i < SLOTS; i += SMEM_COUNT_THREADS) { skeys[i] = EMPTY_KEY; scnt[i] = 0; }
+  for (uint32_t i = tid; i < SLOTS; i += SMEM_COUNT_THREADS) { skeys[i] = EMPTY_MIX; scnt[i] = 0; }
   uint32_t next_work = 0;
   if (tid == 0) next_work = atomicAdd(P.next, 1u);
   if (tid < NW) s_wn[tid] = 0;
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         const uint64_t idx = base + (uint64_t)j * SMEM_COUNT_THREADS + tid;
-        key[j] = EMPTY_KEY;
+        key[j] = EMPTY_MIX;
         if (WEIGHTED) w[j] = 0;
         if (idx < n_p) {
           while (idx >= hi) {  // entries are visited in ascending order: runs only ever advance
@@ -717,7 +718,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
             if (WEIGHTED) cq = P.runs[r].counts ? P.runs[r].counts + seg_begin[r] - seg_prefix[r] : nullptr;
           }
           key[j] = n_pass > 1 ? __ldg(kq + idx) : __ldcs(kq + idx);  // multi-pass: the entries are read again, keep them in L2
-          if (n_pass == 1 || (((uint32_t)mix64(key[j]) >> 13) & (n_pass - 1)) == pass) live |= 1u << j;
+          if (n_pass == 1 || (((uint32_t)key[j] >> 13) & (n_pass - 1)) == pass) live |= 1u << j;
           if (WEIGHTED) {
             uint64_t w64 = 1;
             if (cq) w64 = __ldcs(cq + idx);
@@ -733,7 +734,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
         // adjacent lanes.  The head lane of each run upserts once with the run length.
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-          const uint64_t kk = (live >> j & 1u) ? key[j] : EMPTY_KEY;
+          const uint64_t kk = (live >> j & 1u) ? key[j] : EMPTY_MIX;
           const uint64_t kp = __shfl_up_sync(0xffffffffu, kk, 1);
           const bool head = lane == 0 || kp != kk;
           const uint32_t heads = __ballot_sync(0xffffffffu, head);
@@ -747,7 +748,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
       // ---- two straight-line probe rounds, H keys in flight each: the home bucket (one 16-byte load), then -- for the
       // keys that lost -- the next position of their sequence.  Both rounds run converged; only the ~2 % of keys that are
       // still homeless afterwards enter the divergent loop below.
-      // Probe sequence of a key: bucket t = b0 + t * step2 (b0 from the mix, the odd stride from key bits), slots (t,0), (t,1).
+      // Probe sequence of a (mixed) key: bucket t = b0 + t * step2 (b0 = its lowest bits, the odd stride from bits 40+), slots (t,0), (t,1).
       uint32_t pend = 0, newm = 0;    // bit j: key j still to place / key j claimed a fresh slot
       uint32_t odd = 0, adv = 0;      // pending key j lost slot (adv, odd) last: it continues at u = 2 * adv + odd + 1
       uint64_t fs_lo = 0, fs_hi = 0;  // slot of key j, 16 bits each (keys 0-3 / 4-7), meaningful for the keys in newm
@@ -755,7 +756,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
       for (int h0 = 0; h0 < G; h0 += H) {
         uint32_t sl[H];
 #pragma unroll
-        for (int j = 0; j < H; ++j) sl[j] = (uint32_t)mix64(key[h0 + j]) & bmask;
+        for (int j = 0; j < H; ++j) sl[j] = (uint32_t)key[h0 + j] & bmask;
 #pragma unroll
         for (int round = 0; round < 2; ++round) {
           const uint32_t act = round ? pend : live;
@@ -764,7 +765,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
 #pragma unroll
           for (int j = 0; j < H; ++j) {
             const int q = h0 + j;
-            if (round && (odd >> q & 1u)) sl[j] = ((sl[j] & ~1u) + ((((uint32_t)(key[q] >> 9)) | 1u) << 1)) & mask;  // both home slots lost: next bucket
+            if (round && (odd >> q & 1u)) sl[j] = ((sl[j] & ~1u) + ((((uint32_t)(key[q] >> 40)) | 1u) << 1)) & mask;  // both home slots lost: next bucket
             else sl[j] &= ~1u;
             cur[j] = make_ulonglong2(0ull, 0ull);
             if (act >> q & 1u) cur[j] = *reinterpret_cast<const ulonglong2 *>(&skeys[sl[j]]);
@@ -777,15 +778,15 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
             got[j] = 0ull;
             if (!(act >> q & 1u)) continue;
             const bool x_known_taken = round && !(was_odd >> q & 1u);  // lost the race for the first home slot in round 0
-            if (x_known_taken || (cur[j].x != k && cur[j].x != EMPTY_KEY)) { sl[j] |= 1u; cur[j].x = cur[j].y; }
+            if (x_known_taken || (cur[j].x != k && cur[j].x != EMPTY_MIX)) { sl[j] |= 1u; cur[j].x = cur[j].y; }
             got[j] = cur[j].x;
-            if (cur[j].x == EMPTY_KEY) got[j] = atomicCAS(&skeys[sl[j]], EMPTY_KEY, k);
+            if (cur[j].x == EMPTY_MIX) got[j] = atomicCAS(&skeys[sl[j]], EMPTY_MIX, k);
           }
 #pragma unroll
           for (int j = 0; j < H; ++j) {
             const int q = h0 + j;
             if (!(act >> q & 1u)) continue;
-            const bool is_new = got[j] == EMPTY_KEY;
+            const bool is_new = got[j] == EMPTY_MIX;
             if (is_new || got[j] == key[q]) {
               const uint32_t wj = WEIGHTED ? w[q] : 1u;
               const uint32_t add = wj - (is_new ? 1u : 0u);  // slots store occurrences - 1
@@ -807,17 +808,17 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
         uint32_t wj = WEIGHTED ? w[0] : 1u;
 #pragma unroll
         for (int q = 1; q < G; ++q) if (j == q) { kj = key[q]; if (WEIGHTED) wj = w[q]; }
-        const uint32_t b0 = (uint32_t)mix64(kj) & bmask, step2 = (((uint32_t)(kj >> 9)) | 1u) << 1;
+        const uint32_t b0 = (uint32_t)kj & bmask, step2 = (((uint32_t)(kj >> 40)) | 1u) << 1;
         uint32_t s2 = 0;
         unsigned long long c2 = 0;
         for (uint32_t u = 2u * (adv >> j & 1u) + (odd >> j & 1u) + 1u;; ++u) {
           s2 = ((b0 + (u >> 1) * step2) & mask) | (u & 1u);
           c2 = skeys[s2];
-          if (c2 == EMPTY_KEY) c2 = atomicCAS(&skeys[s2], EMPTY_KEY, kj);
-          if (c2 == EMPTY_KEY || c2 == kj) break;
+          if (c2 == EMPTY_MIX) c2 = atomicCAS(&skeys[s2], EMPTY_MIX, kj);
+          if (c2 == EMPTY_MIX || c2 == kj) break;
           if (u > mask + 4) { atomicExch(P.error_flag, 1u); break; }  // every slot visited: the host re-runs with the L2 variant
         }
-        const bool is_new = c2 == EMPTY_KEY;
+        const bool is_new = c2 == EMPTY_MIX;
         if (is_new || c2 == kj) {
           const uint32_t add = wj - (is_new ? 1u : 0u);
           if (add) { const uint32_t old = atomicAdd(&scnt[s2], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
@@ -872,7 +873,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
           cnt = (unsigned long long)scnt[slot] + 1;  // slots store occurrences - 1
           __stcs(P.out_keys + out0 + i, (uint64_t)skeys[slot]);
           __stcs(P.out_counts + out0 + i, (uint64_t)cnt);
-          skeys[slot] = EMPTY_KEY; scnt[slot] = 0;
+          skeys[slot] = EMPTY_MIX; scnt[slot] = 0;
         }
         if (P.hist) hist_note(ok, cnt, s_hist, P, lane);
       }
@@ -885,7 +886,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
       __syncthreads();
       const uint32_t done = s_run;  // <= n_p: every entry contributes at most one distinct key
       for (uint64_t i = done + tid; i < n_p; i += SMEM_COUNT_THREADS) {  // unused tail of the reservation: entries every reader skips
-        __stcs(P.out_keys + s_base + i, (uint64_t)EMPTY_KEY);
+        __stcs(P.out_keys + s_base + i, (uint64_t)EMPTY_MIX);
         __stcs(P.out_counts + s_base + i, (uint64_t)0);
       }
       if (tid == 0) {
