@@ -112,21 +112,27 @@ class GpuShardEngine:
 class ShardedKmerCounter:
     """Drives one engine per rank through scan -> bucket -> all-to-all -> local upsert."""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, engine, group=None, n_chunks: int = 0):
         self.engine = engine
         self.group = group
+        self.n_chunks = n_chunks   # 0 = 1: one exchange per call.  Measured on 2 x B200 (C4): 5 pieces 71 ms/step vs 62.5 ms for
+                                   # one -- the per-piece host round trips cost more than the overlap wins at this size
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.sent_keys = 0
         self.recv_keys = 0
         self._p1 = None
 
-    def count(self, seq, offsets=None, qual=None, expected_keys_per_rank: int = 0):
+    def count(self, seq, offsets=None, qual=None, expected_keys_per_rank: int = 0, n_chunks: Optional[int] = None):
         """`seq` is THIS rank's slice (see slice_for_rank); offsets/qual are relative to it.
 
         Every rank buckets its keys straight into world x P1 global coarse hash bins (P1 = the engines' common
         coarse-partition count); bins [r*P1, (r+1)*P1) belong to rank r, so ONE all-to-all moves contiguous
-        ranges and the owner adopts each received block as already coarse-partitioned input."""
+        ranges and the owner adopts each received block as already coarse-partitioned input.
+
+        With `n_chunks` > 1 the slice is processed in pieces (k-1 bases of overlap, every window counted by exactly
+        one piece) so that the key exchange of piece j runs on NCCL's stream while the engine refines piece j-1 and
+        scans piece j+1 (off by default, see __init__)."""
         if self.world == 1:
             self.engine.count_local(seq, offsets, qual)
             return
@@ -139,23 +145,58 @@ class ShardedKmerCounter:
             self._p1 = int(t.item())
             if self._p1 != mine:
                 raise RuntimeError(f"ranks disagree on the partition plan ({mine} vs {self._p1}); pass the same expected_keys_per_rank")
-        p1, world = self._p1, self.world
-        keys, bin_counts = self.engine.extract(seq, world * p1, offsets, qual)
-        dev = keys.device
-        send_m = torch.as_tensor(bin_counts.astype(np.int64), device=dev)       # [world * p1], owner-major
-        recv_m = torch.empty_like(send_m)
-        dist.all_to_all_single(recv_m, send_m, group=self.group)                # row s = what source s holds for my bins
-        recv_m = recv_m.cpu().numpy().reshape(world, p1)
-        send_split = bin_counts.reshape(world, p1).sum(axis=1).astype(np.int64).tolist()
-        recv_split = recv_m.sum(axis=1).astype(np.int64).tolist()
-        recv = torch.empty(int(sum(recv_split)), dtype=torch.int64, device=dev)
-        dist.all_to_all_single(recv, keys, output_split_sizes=recv_split, input_split_sizes=send_split, group=self.group)
-        self.sent_keys += int(sum(send_split)) - send_split[self.rank]
-        self.recv_keys += int(sum(recv_split)) - recv_split[self.rank]
-        o = 0
-        for src in range(world):
-            self.engine.adopt(recv[o:o + recv_split[src]], recv_m[src].astype(np.uint64))
-            o += recv_split[src]
+        p1, world, k = self._p1, self.world, int(self.engine.k)
+        n = int(seq.numel())
+        # every rank must run the same number of exchanges: agree on the largest slice's choice
+        if n_chunks is None:
+            n_chunks = self.n_chunks if self.n_chunks else 1
+        dev0 = getattr(self.engine, "device", torch.device("cpu"))
+        t = torch.tensor([int(n_chunks)], dtype=torch.int64, device=dev0)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        n_chunks = int(t.item())
+        cuts = [((n * j) // n_chunks) & ~15 for j in range(n_chunks)] + [n]   # 16-byte aligned piece starts
+        off_host = None if offsets is None else offsets.detach().cpu().numpy().astype(np.int64)
+
+        def finish(p):
+            work, recv, recv_split, recv_m, _keep = p
+            if work is not None:
+                work.wait()
+            o = 0
+            for src in range(world):
+                self.engine.adopt(recv[o:o + recv_split[src]], recv_m[src].astype(np.uint64))
+                o += recv_split[src]
+
+        pending = None
+        for j in range(n_chunks):
+            a = cuts[j]
+            b = n if j + 1 == n_chunks else min(n, cuts[j + 1] + k - 1)
+            if b <= a:
+                sub_seq, sub_qual, sub_off = seq[:0], (None if qual is None else qual[:0]), None
+            else:
+                sub_seq = seq[a:b]
+                sub_qual = None if qual is None else qual[a:b]
+                sub_off = None
+                if off_host is not None:
+                    inside = off_host[(off_host > a) & (off_host < b)] - a
+                    sub_off = torch.from_numpy(np.concatenate([[0], inside, [b - a]]).astype(np.int64)).to(seq.device)
+            keys, bin_counts = self.engine.extract(sub_seq, world * p1, sub_off, sub_qual)
+            dev = keys.device
+            send_m = torch.as_tensor(bin_counts.astype(np.int64), device=dev)       # [world * p1], owner-major
+            recv_m = torch.empty_like(send_m)
+            dist.all_to_all_single(recv_m, send_m, group=self.group)                # row s = what source s holds for my bins
+            recv_m = recv_m.cpu().numpy().reshape(world, p1)
+            send_split = bin_counts.reshape(world, p1).sum(axis=1).astype(np.int64).tolist()
+            recv_split = recv_m.sum(axis=1).astype(np.int64).tolist()
+            recv = torch.empty(int(sum(recv_split)), dtype=torch.int64, device=dev)
+            work = dist.all_to_all_single(recv, keys, output_split_sizes=recv_split, input_split_sizes=send_split, group=self.group,
+                                          async_op=True)
+            self.sent_keys += int(sum(send_split)) - send_split[self.rank]
+            self.recv_keys += int(sum(recv_split)) - recv_split[self.rank]
+            if pending is not None:
+                finish(pending)          # refine piece j-1 while piece j is on the wire
+            pending = (work, recv, recv_split, recv_m, keys)
+        if pending is not None:
+            finish(pending)
 
     def finalize(self) -> dict:
         """Global summary: sums over shards (shards are disjoint), max of max_count."""

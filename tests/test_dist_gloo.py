@@ -95,7 +95,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, k, q, data_path, out_dir):
+def _worker(rank, world, port, k, q, data_path, out_dir, n_chunks=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -107,7 +107,7 @@ def _worker(rank, world, port, k, q, data_path, out_dir):
         off = torch.tensor([0] + inside + [b - a], dtype=torch.int64)
         seq = torch.from_numpy(seq_np[a:b].copy())
         qual = None if qual_np is None else torch.from_numpy(qual_np[a:b].copy())
-        sc = ShardedKmerCounter(OracleShardEngine(k, q))
+        sc = ShardedKmerCounter(OracleShardEngine(k, q), n_chunks=n_chunks)
         sc.count(seq, off, qual)
         summary = sc.finalize()
         keys, counts = sc.export_gathered(1)
@@ -121,8 +121,8 @@ def _worker(rank, world, port, k, q, data_path, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,k,q", [(2, 21, None), (2, 5, 20), (3, 31, 10)])
-def test_sharded_count_equals_single_process(tmp_path, world, k, q):
+@pytest.mark.parametrize("world,k,q,n_chunks", [(2, 21, None, 0), (2, 5, 20, 0), (3, 31, 10, 0), (2, 21, 15, 3), (3, 7, None, 5)])
+def test_sharded_count_equals_single_process(tmp_path, world, k, q, n_chunks):
     rng = np.random.default_rng(world * 100 + k)
     recs, quals = [], []
     for _ in range(40):
@@ -135,7 +135,7 @@ def test_sharded_count_equals_single_process(tmp_path, world, k, q):
     data = tmp_path / "data.pkl"
     with open(data, "wb") as f:
         pickle.dump((seq, qual, offsets), f)
-    mp.spawn(_worker, args=(world, _free_port(), k, q, str(data), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), k, q, str(data), str(tmp_path), n_chunks), nprocs=world, join=True)
     okeys, ocounts, windows = orc.count_batch(k, seq, qual, offsets, q, mode="literal")
     ov, of = orc.histogram(ocounts, 2)
     sent = recv = 0
