@@ -431,3 +431,47 @@ def test_small_start_migrates_from_the_table_to_the_partitioned_path():
     ok, oc, _ = orc.count_batch(k, parts[0][:200_000], None, np.array([0, 200_000], dtype=np.uint64))
     idx = np.searchsorted(got[0], ok)
     assert (got[0][idx] == ok).all() and (got[1][idx] >= 2 * oc).all()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_exchange_shapes_on_one_device(world):
+    """The bucket counts of the N-GPU exchange (world x P1 global coarse bins: ~1300, ~1850 and > 2048, which takes the
+    staged scatter kernel instead of the rows kernel) exercised on ONE device: extract into world x P1 bins, then every
+    'rank' adopts its P1 bins from every source and the union of the shard tables must equal the oracle count."""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(40 + world)
+    k = 21
+    host = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), p=[.248, .248, .248, .248, .008], size=3_000_000).astype(np.uint8)
+    offsets_np = np.array([0, 1_200_000, len(host)], dtype=np.uint64)
+    oracle = orc.count_batch(k, host, None, offsets_np, mode="rolling")
+    seq = torch.from_numpy(host).to(dev)
+    offsets = torch.from_numpy(offsets_np.astype(np.int64)).to(dev)
+    p1 = {2: 657, 4: 464, 8: 328}[world]   # what the plan gives for C4 split over `world` ranks
+    shards = []
+    for r in range(world):
+        c = kb.GpuKmerCounter(k, flags=PART, expected_distinct=p1 * p1 * 3600)
+        assert c.partition_plan(p1 * p1 * 3600)[0] == p1
+        shards.append(c)
+    try:
+        out = torch.empty(len(host), dtype=torch.int64, device=dev)
+        counts = shards[0].extract_keys_device(seq.data_ptr(), len(host), world * p1, out.data_ptr(), len(host),
+                                               d_offsets=offsets.data_ptr(), n_records=2)
+        assert int(counts.sum()) == oracle[2]
+        bounds = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        got_k, got_c = [], []
+        for r in range(world):
+            lo, hi = bounds[r * p1], bounds[(r + 1) * p1]
+            block = out[lo:hi]
+            if hi > lo:
+                shards[r].adopt_coarse_device(block.data_ptr(), counts[r * p1:(r + 1) * p1].astype(np.uint64), int(hi - lo))
+            shards[r].finalize()
+            kk, cc = shards[r].export(1, True)
+            assert all(kb.owner_of(int(x), world) == r for x in kk[:200])
+            got_k.append(kk); got_c.append(cc)
+        allk = np.concatenate(got_k); allc = np.concatenate(got_c)
+        order = np.argsort(allk, kind="stable")
+        assert_same((allk[order], allc[order]), oracle)
+    finally:
+        for c in shards:
+            c.close()
