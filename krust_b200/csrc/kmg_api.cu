@@ -1282,7 +1282,7 @@ KMG_EXPORT kmg_status kmg_extract_keys_device(kmg_ctx *c, const uint8_t *d_seq, 
   if (has_start) CU(c, launch_start_bits(d_offsets, n_records, 0, n_bytes, n_words_total, c->d_start, c->stream));
   if (n_bytes >= (1ull << 32)) return fail(c, KMG_ERR_INVALID_ARG, "kmg_extract_keys_device handles < 2^32 bytes per call");
   unsigned long long *d_pc = nullptr;
-  CU(c, cudaMalloc(&d_pc, 3 * (size_t)n_shards * 8 + 64));
+  CU(c, pool_alloc(c, &d_pc, 3 * (size_t)n_shards * 8 + 64));  // pooled: a cudaMalloc / cudaFree pair per call synchronises the device
   unsigned long long *d_cur = d_pc + n_shards;
   unsigned long long *d_ps = d_cur + n_shards;
   unsigned long long *d_ctr = d_ps + n_shards;  // scratch counters (windows of this call only)
@@ -1292,15 +1292,15 @@ KMG_EXPORT kmg_status kmg_extract_keys_device(kmg_ctx *c, const uint8_t *d_seq, 
   std::vector<unsigned long long> h(n_shards);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), d_pc, n_shards * 8, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  if (e != cudaSuccess) { cudaFree(d_pc); return cuda_fail(c, e, "partition count pass"); }
+  if (e != cudaSuccess) { pool_free(c, d_pc); return cuda_fail(c, e, "partition count pass"); }
   uint64_t total = 0;
   std::vector<unsigned long long> prefix(n_shards);
   for (uint32_t i = 0; i < n_shards; ++i) { prefix[i] = total; total += h[i]; shard_counts_out[i] = h[i]; }
-  if (total > cap || (total && !d_keys_out)) { cudaFree(d_pc); return fail(c, KMG_ERR_CAPACITY, "d_keys_out too small: need " + std::to_string(total)); }
+  if (total > cap || (total && !d_keys_out)) { pool_free(c, d_pc); return fail(c, KMG_ERR_CAPACITY, "d_keys_out too small: need " + std::to_string(total)); }
   e = cudaMemcpyAsync(d_ps, prefix.data(), n_shards * 8, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = launch_scan_partition(in, n_shards, true, d_pc, d_ps, d_cur, d_keys_out, d_ctr, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFree(d_pc);
+  pool_free(c, d_pc);
   if (e != cudaSuccess) return cuda_fail(c, e, "partition scatter pass");
   c->n_records += n_records; c->n_bases += n_bytes;
   return KMG_OK;
