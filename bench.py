@@ -232,9 +232,16 @@ def main():
         return float(t.item())
 
     def step_device():
+        t_dbg = time.perf_counter()
         engine.reset()
+        if os.environ.get("KMG_DIST_TIMING") and rank == 0:
+            torch.cuda.synchronize(dev); print(f"[dist timing] reset: {(time.perf_counter() - t_dbg) * 1e3:.2f} ms", file=sys.stderr, flush=True); t_dbg = time.perf_counter()
         sharded.count(d_seq, off_arg, expected_keys_per_rank=exp_windows // world + 1024)
+        if os.environ.get("KMG_DIST_TIMING") and rank == 0:
+            t_dbg = time.perf_counter()
         engine.finalize(False)
+        if os.environ.get("KMG_DIST_TIMING") and rank == 0:
+            torch.cuda.synchronize(dev); print(f"[dist timing] finalize: {(time.perf_counter() - t_dbg) * 1e3:.2f} ms", file=sys.stderr, flush=True)
 
     # ---- device-resident timing: W warm-up, then exactly K steps between barriers, CUDA events, max over ranks
     for _ in range(args.warmup):

@@ -18,9 +18,14 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
 
+import os
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+_TIMING = bool(os.environ.get("KMG_DIST_TIMING"))
 
 
 def slice_for_rank(total: int, world: int, rank: int, k: int) -> Tuple[int, int]:
@@ -166,7 +171,15 @@ class ShardedKmerCounter:
                 self.engine.adopt(recv[o:o + recv_split[src]], recv_m[src].astype(np.uint64))
                 o += recv_split[src]
 
+        def lap(tag, t0):
+            if _TIMING and self.rank == 0:
+                if seq.is_cuda:
+                    torch.cuda.synchronize(seq.device)
+                print(f"[dist timing] {tag}: {(time.perf_counter() - t0) * 1e3:.2f} ms", flush=True)
+            return time.perf_counter()
+
         pending = None
+        t0 = time.perf_counter()
         for j in range(n_chunks):
             a = cuts[j]
             b = n if j + 1 == n_chunks else min(n, cuts[j + 1] + k - 1)
@@ -180,6 +193,7 @@ class ShardedKmerCounter:
                     inside = off_host[(off_host > a) & (off_host < b)] - a
                     sub_off = torch.from_numpy(np.concatenate([[0], inside, [b - a]]).astype(np.int64)).to(seq.device)
             keys, bin_counts = self.engine.extract(sub_seq, world * p1, sub_off, sub_qual)
+            t0 = lap("extract", t0)
             dev = keys.device
             send_m = torch.as_tensor(bin_counts.astype(np.int64), device=dev)       # [world * p1], owner-major
             recv_m = torch.empty_like(send_m)
@@ -188,15 +202,20 @@ class ShardedKmerCounter:
             send_split = bin_counts.reshape(world, p1).sum(axis=1).astype(np.int64).tolist()
             recv_split = recv_m.sum(axis=1).astype(np.int64).tolist()
             recv = torch.empty(int(sum(recv_split)), dtype=torch.int64, device=dev)
+            t0 = lap("count exchange", t0)
             work = dist.all_to_all_single(recv, keys, output_split_sizes=recv_split, input_split_sizes=send_split, group=self.group,
                                           async_op=True)
             self.sent_keys += int(sum(send_split)) - send_split[self.rank]
             self.recv_keys += int(sum(recv_split)) - recv_split[self.rank]
+            if _TIMING:
+                work.wait()
+                t0 = lap("key exchange", t0)
             if pending is not None:
                 finish(pending)          # refine piece j-1 while piece j is on the wire
             pending = (work, recv, recv_split, recv_m, keys)
         if pending is not None:
             finish(pending)
+            t0 = lap("adopt", t0)
 
     def finalize(self) -> dict:
         """Global summary: sums over shards (shards are disjoint), max of max_count."""
