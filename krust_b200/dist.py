@@ -120,8 +120,9 @@ class ShardedKmerCounter:
     def __init__(self, engine, group=None, n_chunks: int = 0):
         self.engine = engine
         self.group = group
-        self.n_chunks = n_chunks   # 0 = 1: one exchange per call.  Measured on 2 x B200 (C4): 5 pieces 71 ms/step vs 62.5 ms for
-                                   # one -- the per-piece host round trips cost more than the overlap wins at this size
+        self.n_chunks = n_chunks   # 0 = automatic: two pieces for slices of >= 2^30 bases, else one.  Measured on 2 x B200 (C4,
+                                   # 1.55 G bases per rank): 1 piece 63.3 ms/step, 2 pieces 59.8, 3 pieces 68.5, 5 pieces 71 -- every
+                                   # piece costs a few host round trips, which soon outweigh the overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.sent_keys = 0
@@ -137,7 +138,7 @@ class ShardedKmerCounter:
 
         With `n_chunks` > 1 the slice is processed in pieces (k-1 bases of overlap, every window counted by exactly
         one piece) so that the key exchange of piece j runs on NCCL's stream while the engine refines piece j-1 and
-        scans piece j+1 (off by default, see __init__)."""
+        scans piece j+1 (see __init__ for the default)."""
         if self.world == 1:
             self.engine.count_local(seq, offsets, qual)
             return
@@ -154,7 +155,7 @@ class ShardedKmerCounter:
         n = int(seq.numel())
         # every rank must run the same number of exchanges: agree on the largest slice's choice
         if n_chunks is None:
-            n_chunks = self.n_chunks if self.n_chunks else 1
+            n_chunks = self.n_chunks if self.n_chunks else int(os.environ.get("KMG_DIST_CHUNKS", "2" if n >= (1 << 30) else "1"))
         dev0 = getattr(self.engine, "device", torch.device("cpu"))
         t = torch.tensor([int(n_chunks)], dtype=torch.int64, device=dev0)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
