@@ -638,30 +638,33 @@ kmg_status consolidate(kmg_ctx *c) {
   prm.n_parts = P; prm.R = R; prm.preagg = !(c->cfg.flags & KMG_FLAG_NO_PREAGG);
   for (uint32_t r = 0; r < R; ++r) prm.runs[r] = ConsRun{in[r]->d_keys, in[r]->d_counts, in[r]->d_seg_start, in[r]->d_seg_len};
 
-  // processing order: partitions with many entries first (a partition is counted by ONE CTA)
+  // processing order: partitions with many entries first (a partition is counted by ONE CTA).  Only when some partition is
+  // heavy (> 8x the average) is the per-partition table fetched and sorted; otherwise partitions are taken as they come.
   unsigned long long *d_totals = nullptr;
   uint32_t *d_order = nullptr;
-  std::vector<unsigned long long> totals(P);
+  unsigned long long h_max = 0;
   cudaError_t e = pool_alloc(c, &d_totals, (size_t)P * 8);
-  if (e == cudaSuccess) e = pool_alloc(c, &d_order, (size_t)P * 4);
-  if (e == cudaSuccess) e = launch_sum_lens(prm, d_totals, c->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(totals.data(), d_totals, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = launch_sum_lens(prm, d_totals, c->d_stats + 6, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_max, c->d_stats + 6, 8, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  pool_free(c, d_totals);
-  if (e != cudaSuccess) { pool_free(c, d_order); return cuda_fail(c, e, "consolidate setup"); }
-  std::vector<uint32_t> order;
-  order.reserve(P);
-  uint64_t max_total = 0;
-  {
-    for (uint32_t p = 0; p < P; ++p) max_total = std::max<uint64_t>(max_total, totals[p]);
-    const uint64_t heavy = 8 * std::max<uint64_t>(total / P, 1024);
-    std::vector<uint32_t> big;
+  if (e != cudaSuccess) { pool_free(c, d_totals); return cuda_fail(c, e, "consolidate setup"); }
+  const uint64_t max_total = h_max;
+  const uint64_t heavy = 8 * std::max<uint64_t>(total / P, 1024);
+  if (max_total > heavy) {
+    std::vector<unsigned long long> totals(P);
+    e = pool_alloc(c, &d_order, (size_t)P * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(totals.data(), d_totals, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { pool_free(c, d_totals); pool_free(c, d_order); return cuda_fail(c, e, "consolidate setup"); }
+    std::vector<uint32_t> order, big;
+    order.reserve(P);
     for (uint32_t p = 0; p < P; ++p) if (totals[p] > heavy) big.push_back(p);
     std::sort(big.begin(), big.end(), [&](uint32_t a, uint32_t b) { return totals[a] > totals[b]; });
     order = big;
     for (uint32_t p = 0; p < P; ++p) if (totals[p] <= heavy) order.push_back(p);
+    e = cudaMemcpy(d_order, order.data(), (size_t)P * 4, cudaMemcpyHostToDevice);  // synchronous: `order` dies with this scope
   }
-  e = cudaMemcpyAsync(d_order, order.data(), (size_t)P * 4, cudaMemcpyHostToDevice, c->stream);
+  pool_free(c, d_totals);
   prm.order = d_order;
 
   Run out;

@@ -79,7 +79,7 @@ struct CountParams {
   uint32_t n_parts, R, scratch_log2, preagg;
   uint32_t split_log2, pad0;         // shared-memory kernel: partitions larger than a table are counted in up to 2^split_log2 passes
   ConsRun runs[CONS_MAX_RUNS];
-  const uint32_t *order;             // partitions in processing order (largest first)
+  const uint32_t *order;             // partitions in processing order (largest first); nullptr = 0, 1, 2, ...
   uint64_t *scratch;                 // gridDim.x private tables of 2^scratch_log2 (key, count-1) slots, clean
   uint64_t *out_keys, *out_counts;
   unsigned long long *out_cursor;    // zeroed; ends up = entries of the output run (distinct keys + skipped filler entries)
@@ -125,7 +125,7 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
 cudaError_t launch_refine(const RefineParams &P, bool scatter, cudaStream_t s);
 bool refine_single_pass_available(uint32_t n_sub, bool weighted);  // the rows kernel applies (it can run without a count pass)
 cudaError_t launch_fill_strided(uint64_t *d, uint64_t n, uint64_t stride, cudaStream_t s);  // d[i] = i * stride
-cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, cudaStream_t s);
+cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, unsigned long long *d_max, cudaStream_t s);
 cudaError_t launch_count_partitions(const CountParams &P, unsigned grid, cudaStream_t s);
 // weighted: some input run carries counts, or a partition is large enough to want run-length pre-aggregation
 cudaError_t launch_count_partitions_smem(const CountParams &P, bool weighted, cudaStream_t s);

@@ -404,16 +404,25 @@ cudaError_t launch_refine(const RefineParams &P_in, bool scatter, cudaStream_t s
 }
 
 // per-partition totals over all input runs (for load-balanced ordering on the host)
-__global__ void sum_lens_kernel(CountParams P, unsigned long long *totals) {
+__global__ void sum_lens_kernel(CountParams P, unsigned long long *totals, unsigned long long *max_total) {
+  unsigned long long mx = 0;
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n_parts; p += gridDim.x * blockDim.x) {
     unsigned long long t = 0;
     for (uint32_t r = 0; r < P.R; ++r) t += P.runs[r].seg_len[p];
     totals[p] = t;
+    mx = t > mx ? t : mx;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, mx, o); mx = v > mx ? v : mx; }
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_total, mx);
 }
-cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, cudaStream_t s) {
+// d_max (zeroed by this call) receives the largest per-partition total: the host only fetches the whole table when some
+// partition is heavy enough to need the largest-first processing order
+cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, unsigned long long *d_max, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  sum_lens_kernel<<<(unsigned)std::min<uint64_t>((P.n_parts + 255) / 256, (uint64_t)num_sms() * 8), 256, 0, s>>>(P, d_totals);
+  sum_lens_kernel<<<(unsigned)std::min<uint64_t>((P.n_parts + 255) / 256, (uint64_t)num_sms() * 8), 256, 0, s>>>(P, d_totals, d_max);
   return cudaGetLastError();
 }
 
@@ -470,7 +479,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
       if (lane == 0) { w = next_work; if (w < P.n_parts) next_work = atomicAdd(P.next, 1u); }
       w = __shfl_sync(0xffffffffu, w, 0);
       if (w < P.n_parts) {
-        const uint32_t p = P.order[w];
+        const uint32_t p = P.order ? P.order[w] : w;
         uint64_t b = 0, len = 0;
         if (lane < (int)P.R) { b = P.runs[lane].seg_start[p]; len = P.runs[lane].seg_len[p]; }
         uint64_t incl = len;
@@ -484,7 +493,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
     __syncthreads();
     const uint32_t work = s_work;
     if (work >= P.n_parts) break;
-    const uint32_t p = P.order[work];
+    const uint32_t p = P.order ? P.order[work] : work;
     const uint64_t n_p = seg_prefix[P.R];
     if (n_p == 0) {  // block-uniform
       if (tid == 0) { P.out_seg_start[p] = 0; P.out_seg_len[p] = 0; }
@@ -656,7 +665,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
       if (lane == 0) { w = next_work; if (w < P.n_parts) next_work = atomicAdd(P.next, 1u); }
       w = __shfl_sync(0xffffffffu, w, 0);
       if (w < P.n_parts) {
-        const uint32_t p = P.order[w];
+        const uint32_t p = P.order ? P.order[w] : w;
         uint64_t b = 0, len = 0;
         if (lane < (int)P.R) { b = P.runs[lane].seg_start[p]; len = P.runs[lane].seg_len[p]; }
         uint64_t incl = len;
@@ -670,7 +679,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
     __syncthreads();
     const uint32_t work = s_work;
     if (work >= P.n_parts) break;
-    const uint32_t p = P.order[work];
+    const uint32_t p = P.order ? P.order[work] : work;
     const uint64_t n_p = seg_prefix[P.R];
     if (n_p == 0) {
       if (tid == 0) { P.out_seg_start[p] = 0; P.out_seg_len[p] = 0; }
