@@ -1,4 +1,5 @@
-"""Ablation timing of the A1 scatter kernel: KMG_DEBUG=bits python tools/ablate.py  (results are WRONG with bits set)."""
+"""Ablation timing of the legacy warp-scatter A1 kernel (select it with KMG_SCATTER=1): KMG_DEBUG=bits python tools/ablate.py
+(results are WRONG with bits set).  The default rows kernel has no ablation switches."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
