@@ -169,3 +169,36 @@ def test_owner_of_is_a_partition():
         assert all(0 <= o < n for o in owners)
         if n > 1:
             assert len(set(owners)) == n
+
+
+def test_mixed_key_constants_are_consistent():
+    """The partitioned pipeline stores mix64(key) in its runs and un-mixes on export: the constants in kmg_device.cuh must be
+    modular inverses of each other, EMPTY_MIX must be mix64(EMPTY_KEY), and the host-visible owner function must agree with a
+    Python restatement of the mix."""
+    import re
+    import pathlib
+    import random
+    import krust_b200 as kb
+    src = (pathlib.Path(__file__).resolve().parents[1] / "krust_b200" / "csrc" / "kmg_device.cuh").read_text()
+    M = (1 << 64) - 1
+    muls = [int(x, 16) for x in re.findall(r"x \*= (0x[0-9a-fA-F]+)ull", src)]
+    assert len(muls) == 4, muls                      # two in mix64, two in unmix64
+    m1, m2, i2, i1 = muls
+    assert (m1 * i1) & M == 1 and (m2 * i2) & M == 1
+    empty_mix = int(re.search(r"EMPTY_MIX = (0x[0-9a-fA-F]+)ull", src).group(1), 16)
+
+    def mix(x):
+        x ^= x >> 33; x = (x * m1) & M; x ^= x >> 33; x = (x * m2) & M; x ^= x >> 33
+        return x
+
+    def unmix(x):
+        x ^= x >> 33; x = (x * i2) & M; x ^= x >> 33; x = (x * i1) & M; x ^= x >> 33
+        return x
+
+    assert mix(M) == empty_mix
+    rnd = random.Random(5)
+    for _ in range(2000):
+        key = rnd.getrandbits(64)
+        assert unmix(mix(key)) == key
+        n = rnd.choice([2, 3, 8, 657, 928, 4096])
+        assert kb.owner_of(key, n) == ((mix(key) >> 32) * n) >> 32
