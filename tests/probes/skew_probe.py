@@ -7,7 +7,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repository root: python tests/probes/skew_probe.py 1e9 --no-oracle
 import krust_b200 as kb  # noqa: E402
 from oracle import oracle as orc  # noqa: E402  (checker only)
 
