@@ -1,7 +1,9 @@
-// C-ABI layer of libkmerust_gpu (include/kmerust_gpu.h): context, memory management, pinned
-// double-buffered staging, capacity planning / growth of the HBM table, result export.
-// The counting itself happens in the sm_100a kernels of kmg_kernels.cu.  There is no CPU fallback:
-// every entry point needs a CUDA device.
+// C-ABI layer of libkmerust_gpu (include/kmerust_gpu.h): context, device memory pool, the staging ring of the
+// host feed, the choice between the three counting paths (direct 4^k array, one HBM table, partitioned pipeline) and
+// its adaptation to a growing input (table growth, migration to the partitioned path, speculative layouts with
+// exact fallback, re-split / multi-pass when the partition plan is outgrown), consolidation of the runs, result export.
+// The counting itself happens in the sm_100a kernels of kmg_kernels.cu / kmg_partition.cu.  There is no CPU
+// fallback: every entry point needs a CUDA device.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

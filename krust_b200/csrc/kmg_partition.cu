@@ -3,16 +3,19 @@
 // Why partition at all: an upsert into one big HBM-resident table is bounded by ~20 G random atomics/s
 // on a B200 and moves 144 B of DRAM traffic per k-mer (profiles/r1_summary.md), while HBM streams at
 // 6.5 TB/s.  So the keys are radix-partitioned by hash with streaming writes until a partition is so
-// small (~4.4 K keys) that ONE CTA can count it in a private 128 KiB scratch table that never leaves
-// L2, compact it into the output and move on -- no cross-CTA dependencies, no grid barriers, HBM sees
-// only streams.
+// small (~3.5 K keys) that ONE CTA can count it in a SHARED-MEMORY table, compact it into the output and
+// move on -- no cross-CTA dependencies, no grid barriers, HBM sees only streams.
 //
-//   A1  scan -> canonical keys -> P1 coarse partitions           (partition_count/scatter_kernel)
-//   A2  coarse partition -> P2 sub-bins each (P = P1*P2 fine)    (refine_kernel<false/true>, here)
-//   B   one CTA per fine partition: upsert, compact, clean       (count_partitions_kernel, here)
+//   A1  scan -> mixed canonical keys -> P1 coarse bins            (partition_scatter_rows_kernel, kmg_kernels.cu)
+//   A2  coarse bin -> P2 sub-bins each (P = P1*P2 fine)           (refine_rows_kernel; refine_kernel<> = exact route)
+//   B   one CTA per fine partition: upsert, compact, histogram   (count_partitions_smem_kernel; count_partitions_kernel
+//                                                                  = L2-scratch fallback)
 //
-// Two levels because a scatter needs long runs per (tile, bin) to write whole sectors: with ~850 bins per
-// level a 16-32 K-key tile yields 20-40 key runs, while a single level with 700 K bins would not.
+// The streams between the stages hold MIXED keys v = mix64(key) (kmg_device.cuh): coarse bin = top bits of v's high
+// half, sub-bin = top bits of its low half, table slot = its lowest bits.  Both scatter levels write into speculative
+// fixed shares per bin (mean + 7 sigma), so neither needs a count pass; overflow -> exact route (kmg_api.cu).
+// Two levels because a scatter needs runs per (tile, bin) long enough to write whole sectors: with ~900 bins per
+// level an 8 K-key tile yields ~9-key runs, while a single level with 860 K bins would not.
 //
 // Replaces the DashMap upsert + iteration of src/run.rs:565-582 for large inputs; results are the same
 // multiset of (canonical key, count) pairs.
