@@ -169,6 +169,13 @@ kmg_status kmg_export_counts(kmg_ctx *ctx, uint64_t min_count, int sorted, uint6
 kmg_status kmg_export_counts_device(kmg_ctx *ctx, uint64_t min_count, int sorted, uint64_t *d_keys,
                                     uint64_t *d_counts, uint64_t cap, uint64_t *n_out);
 
+/* The same result in pieces: shard s of n_shards holds the entries with key % n_shards == s (n_shards <= 1: everything).  For
+ * tables larger than the caller's memory -- the 3.1 Gbp configuration's HashMap<u64,u64> is 50 GB -- and for sampled checks. */
+kmg_status kmg_export_shard(kmg_ctx *ctx, uint64_t min_count, int sorted, uint64_t n_shards, uint64_t shard, uint64_t *keys,
+                            uint64_t *counts, uint64_t cap, uint64_t *n_out);
+kmg_status kmg_export_shard_device(kmg_ctx *ctx, uint64_t min_count, int sorted, uint64_t n_shards, uint64_t shard,
+                                   uint64_t *d_keys, uint64_t *d_counts, uint64_t cap, uint64_t *n_out);
+
 /* Replaces compute_histogram_packed after the min-count filter (src/histogram.rs:110-116,
  * src/run.rs:471-481): ascending (count, number of distinct k-mers with that count). */
 kmg_status kmg_histogram(kmg_ctx *ctx, uint64_t min_count, uint64_t *count_vals, uint64_t *freqs,
@@ -177,6 +184,13 @@ kmg_status kmg_histogram(kmg_ctx *ctx, uint64_t min_count, uint64_t *count_vals,
 /* Replaces counts_to_packed + KmerIndex::new + save_index (src/main.rs:155-202, :284-299,
  * src/index.rs:156-196, :222-279).  Writes ALL k-mers (the index is never min-count filtered). */
 kmg_status kmg_save_kmix(kmg_ctx *ctx, const char *path);
+/* The same index written from several shards (one context per GPU, hash-sharded table): kmg_kmix_begin creates the file; every
+ * shard writes its records at record_offset (= records of the shards before it; sizes from kmg_finalize) and reports their
+ * number and CRC-32; kmg_kmix_finish writes the header (n = sum over shards) and the CRC of the whole file combined from the
+ * shard CRCs (the format allows any record order, src/index.rs:7-23).  Paths ending in .gz are refused (no compression here). */
+kmg_status kmg_kmix_begin(const char *path);
+kmg_status kmg_save_kmix_shard(kmg_ctx *ctx, const char *path, uint64_t record_offset, uint64_t *n_records_out, uint32_t *crc_out);
+kmg_status kmg_kmix_finish(const char *path, uint32_t k, const uint64_t *shard_records, const uint32_t *shard_crcs, uint32_t n_shards);
 
 /* Replaces ProgressTracker::snapshot (src/progress.rs). */
 kmg_status kmg_progress(const kmg_ctx *ctx, uint64_t *records, uint64_t *bases);
@@ -187,6 +201,12 @@ uint64_t kmg_kernel_launches(void);
 /* Test/bench helper: fill d_out[n] with the deterministic synthetic base stream
  * (same generator as oracle/kmer_oracle.c orc_synth_uniform). */
 kmg_status kmg_synth_uniform_device(kmg_ctx *ctx, uint64_t seed, uint64_t first_base, uint64_t n, uint8_t *d_out);
+
+/* Test/bench helper: n_reads synthetic 150 bp reads laid back to back (d_seq, and d_qual unless NULL: n_reads * 150 bytes
+ * each); profile 3 = the R20M shape of config C3 (N bases, Phred qualities), 5 = the R200M shape of config C5 (10 % satellite
+ * reads).  Same generator as oracle/kmer_oracle.c orc_synth_reads. */
+kmg_status kmg_synth_reads_device(kmg_ctx *ctx, uint64_t seed, uint32_t profile, uint64_t first_read, uint64_t n_reads,
+                                  uint8_t *d_seq, uint8_t *d_qual);
 
 /* Host utility (no CUDA): FASTA/FASTQ record splitter for hosts without the Rust reader layer; stands
  * in for bio::io::{fasta,fastq}::Reader as used by src/reader.rs:91,96,176,181.  seq_out (and

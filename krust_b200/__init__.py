@@ -8,7 +8,7 @@ from .api import (BuilderError, GpuError, GpuKmerCounter, InvalidIndexError, Kme
                   KmerLength, KmerLengthError, OutputFormat, SequenceFormat, SequenceParseError, compute_histogram,
                   compute_histogram_packed, count_kmers, count_kmers_from_sequences, count_kmers_sequential,
                   count_kmers_streaming, count_kmers_streaming_packed, count_kmers_with_format,
-                  count_kmers_with_quality, histogram_stats, load_index, owner_of, parse_fastx, read_records,
+                  count_kmers_with_quality, histogram_stats, kmix_begin, kmix_finish, load_index, owner_of, parse_fastx, read_records,
                   save_index, unpack_many, unpack_to_string, write_counts)
 
 __version__ = "0.1.0"

@@ -54,11 +54,17 @@ SIGNATURES = {
     "kmg_finalize": (i32, [vp, C.POINTER(KmgSummary)]),
     "kmg_export_counts": (i32, [vp, u64, i32, vp, vp, u64, C.POINTER(u64)]),
     "kmg_export_counts_device": (i32, [vp, u64, i32, vp, vp, u64, C.POINTER(u64)]),
+    "kmg_export_shard": (i32, [vp, u64, i32, u64, u64, vp, vp, u64, C.POINTER(u64)]),
+    "kmg_export_shard_device": (i32, [vp, u64, i32, u64, u64, vp, vp, u64, C.POINTER(u64)]),
     "kmg_histogram": (i32, [vp, u64, vp, vp, u64, C.POINTER(u64)]),
     "kmg_save_kmix": (i32, [vp, C.c_char_p]),
+    "kmg_kmix_begin": (i32, [C.c_char_p]),
+    "kmg_save_kmix_shard": (i32, [vp, C.c_char_p, u64, C.POINTER(u64), C.POINTER(u32)]),
+    "kmg_kmix_finish": (i32, [C.c_char_p, u32, vp, vp, u32]),
     "kmg_progress": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
     "kmg_kernel_launches": (u64, []),
     "kmg_synth_uniform_device": (i32, [vp, u64, u64, u64, vp]),
+    "kmg_synth_reads_device": (i32, [vp, u64, u32, u64, u64, vp, vp]),
     "kmg_parse_fastx": (i32, [vp, u64, i32, vp, vp, vp, u64, C.POINTER(u64), C.c_char_p, C.c_size_t]),
 }
 

@@ -283,6 +283,9 @@ class GpuKmerCounter:
     def synth_uniform_device(self, seed: int, first_base: int, n: int, d_out: int):
         _check(self._L.kmg_synth_uniform_device(self._ctx, seed, first_base, n, d_out), self._ctx)
 
+    def synth_reads_device(self, seed: int, profile: int, first_read: int, n_reads: int, d_seq: int, d_qual: int = 0):
+        _check(self._L.kmg_synth_reads_device(self._ctx, seed, profile, first_read, n_reads, d_seq, d_qual or None), self._ctx)
+
     # -- results
     def finalize(self, want_summary: bool = True) -> Optional[dict]:
         if not want_summary:
@@ -300,6 +303,17 @@ class GpuKmerCounter:
         if n.value:
             _check(self._L.kmg_export_counts(self._ctx, min_count, int(sorted), keys.ctypes.data, counts.ctypes.data,
                                              n.value, C.byref(n)), self._ctx)
+        return keys, counts
+
+    def export_shard(self, n_shards: int, shard: int, min_count: int = 1, sorted: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+        """The entries with key % n_shards == shard (kmg_export_shard): the result in pieces that fit the host."""
+        n = C.c_uint64(0)
+        _check(self._L.kmg_export_shard(self._ctx, min_count, int(sorted), n_shards, shard, None, None, 0, C.byref(n)), self._ctx)
+        keys = np.empty(n.value, dtype=np.uint64)
+        counts = np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            _check(self._L.kmg_export_shard(self._ctx, min_count, int(sorted), n_shards, shard, keys.ctypes.data,
+                                            counts.ctypes.data, n.value, C.byref(n)), self._ctx)
         return keys, counts
 
     def export_device(self, d_keys: int, d_counts: int, cap: int, min_count: int = 1, sorted: bool = False) -> int:
@@ -321,10 +335,30 @@ class GpuKmerCounter:
     def save_kmix(self, path):
         _check(self._L.kmg_save_kmix(self._ctx, os.fspath(path).encode()), self._ctx)
 
+    def save_kmix_shard(self, path, record_offset: int) -> Tuple[int, int]:
+        """Write this shard's records into its byte range of `path`; returns (records, crc32 of those bytes)."""
+        n, crc = C.c_uint64(0), C.c_uint32(0)
+        _check(self._L.kmg_save_kmix_shard(self._ctx, os.fspath(path).encode(), int(record_offset), C.byref(n), C.byref(crc)), self._ctx)
+        return n.value, crc.value
+
     def progress(self) -> Tuple[int, int]:
         r, b = C.c_uint64(0), C.c_uint64(0)
         _check(self._L.kmg_progress(self._ctx, C.byref(r), C.byref(b)), self._ctx)
         return r.value, b.value
+
+
+def kmix_begin(path):
+    st = _lib.load().kmg_kmix_begin(os.fspath(path).encode())
+    if st != _lib.KMG_OK:
+        raise KmeRustError(f"failed to write index to '{os.fspath(path)}'")
+
+
+def kmix_finish(path, k: int, shard_records: Sequence[int], shard_crcs: Sequence[int]):
+    rec = np.asarray(list(shard_records), dtype=np.uint64)
+    crc = np.asarray(list(shard_crcs), dtype=np.uint32)
+    st = _lib.load().kmg_kmix_finish(os.fspath(path).encode(), int(k), rec.ctypes.data, crc.ctypes.data, len(rec))
+    if st != _lib.KMG_OK:
+        raise KmeRustError(f"failed to write index to '{os.fspath(path)}'")
 
 
 def owner_of(key: int, n_shards: int) -> int:

@@ -101,6 +101,7 @@ struct kmg_ctx {
   size_t scan_tmp_bytes = 0;
   uint64_t scan_tmp_items = 0, fine_cursor_items = 0;
   bool in_resplit = false;
+  int building_run = 0;  // > 0 while refine_to_run derives a run from the current plan: a nested consolidate must not re-split
   // count-of-counts of `result`, produced by phase B itself (consolidate)
   unsigned long long *d_hist = nullptr;      // HIST_DENSE_BINS bins + overflow counter
   uint64_t *d_hist_ov = nullptr;             // HIST_OVERFLOW_CAP counts >= HIST_DENSE_BINS
@@ -380,6 +381,12 @@ struct SplitPlan { uint32_t n_in, m, sub_old; Run *out; };
 kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, const std::vector<uint64_t> &coarse_off, bool owns = true,
                          bool sync = true, const std::vector<uint64_t> *coarse_len = nullptr, const SplitPlan *split = nullptr,
                          bool in_keys = false) {  // in_keys: the input holds plain keys, not mixes (blocks adopted from another rank)
+  struct BuildGuard {
+    kmg_ctx *c;
+    explicit BuildGuard(kmg_ctx *c_) : c(c_) { ++c->building_run; }
+    void release() { if (c) { --c->building_run; c = nullptr; } }
+    ~BuildGuard() { release(); }
+  } guard(c);
   const uint32_t P1 = split ? split->n_in : c->n_coarse;
   const uint32_t n_sub = split ? split->m : c->n_sub;
   const uint32_t P = split ? split->n_in * split->m : c->n_parts;
@@ -442,6 +449,7 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
       cleanup();
       r.n = n;
       if (split) { *split->out = std::move(r); return KMG_OK; }
+      guard.release();  // the run is complete: a consolidation triggered by add_run may re-split it with the others
       return add_run(c, std::move(r));
     }
     c->spec_fine_ok = false;
@@ -473,6 +481,7 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   if (e != cudaSuccess) { free_run(c, r); return cuda_fail(c, e, "refine scatter"); }
   r.n = n;
   if (split) { *split->out = std::move(r); return KMG_OK; }
+  guard.release();
   return add_run(c, std::move(r));
 }
 
@@ -616,7 +625,9 @@ kmg_status consolidate(kmg_ctx *c) {
     uint64_t entries = c->has_result ? c->result.n_valid : 0;
     for (auto &r : c->runs) entries += r.n;
     const uint64_t avg = entries / std::max<uint32_t>(c->n_parts, 1);
-    if (avg > 2 * TARGET_KEYS_PER_PART && c->n_sub * 2 <= 2048 && !c->cfg.parts_log2) {  // an explicit partition count is respected
+    // (not while refine_to_run is building a run from the current plan -- its allocations may land here -- : the run would be
+    // finished with the old partition count and sub-bin function; partitions are counted in passes instead)
+    if (avg > 2 * TARGET_KEYS_PER_PART && c->n_sub * 2 <= 2048 && !c->cfg.parts_log2 && !c->building_run) {  // an explicit partition count is respected
       const uint32_t m = (uint32_t)std::min<uint64_t>((avg + TARGET_KEYS_PER_PART - 1) / TARGET_KEYS_PER_PART, 2048 / c->n_sub);
       // Re-splitting costs one tile (~3.5 us of one SM) per input partition or per 8192 entries of every run plus a streaming
       // pass; counting in m passes instead costs ~7 ps per entry and extra pass, again at every later consolidation.  Many small
@@ -1161,6 +1172,9 @@ KMG_EXPORT kmg_status kmg_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint
   }
   c->next_ascii = (slot0 + (uint32_t)chunks.size()) % N_STAGE;
   c->n_records += n_records; c->n_bases += end - begin;
+  if (src_pinned)  // the copies read the CALLER's buffer: it must be reusable when this call returns
+    for (auto &st : c->st)
+      if (st.h2d_pending) { CU(c, cudaEventSynchronize(st.h2d_done)); st.h2d_pending = false; }
   return KMG_OK;
 }
 
@@ -1344,47 +1358,52 @@ KMG_EXPORT kmg_status kmg_finalize(kmg_ctx *c, kmg_summary *out) {
 }
 
 namespace {
-kmg_status count_filtered(kmg_ctx *c, uint64_t min_count, uint64_t *n) {
+kmg_status count_filtered(kmg_ctx *c, uint64_t min_count, uint64_t *n, uint64_t shard_mod = 0, uint64_t shard_rem = 0) {
   CU(c, cudaStreamSynchronize(c->copy_stream));
   if (c->mode == kmg_ctx::MODE_PARTITIONED) { kmg_status s = consolidate(c); if (s != KMG_OK) return s; }
-  if (fetch_fused_hist(c)) {
+  if (shard_mod <= 1 && fetch_fused_hist(c)) {
     uint64_t m = 0;
     for (uint64_t b = std::max<uint64_t>(min_count, 1); b < (uint64_t)HIST_DENSE_BINS; ++b) m += c->h_bins[b];
     m += c->h_ov.end() - std::lower_bound(c->h_ov.begin(), c->h_ov.end(), min_count);
     *n = m;
     return KMG_OK;
   }
-  CU(c, launch_table_stats(view_of(c), min_count, c->d_stats, c->stream));
+  TableView v = view_of(c);
+  v.shard_mod = shard_mod; v.shard_rem = shard_rem;
+  CU(c, launch_table_stats(v, min_count, c->d_stats, c->stream));
   unsigned long long h[3];
   CU(c, cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   *n = h[0];
   return KMG_OK;
 }
-}  // namespace
 
-KMG_EXPORT kmg_status kmg_export_counts_device(kmg_ctx *c, uint64_t min_count, int sorted, uint64_t *d_keys, uint64_t *d_counts,
-                                               uint64_t cap, uint64_t *n_out) {
+kmg_status export_device(kmg_ctx *c, uint64_t min_count, int sorted, uint64_t shard_mod, uint64_t shard_rem, uint64_t *d_keys,
+                         uint64_t *d_counts, uint64_t cap, uint64_t *n_out) {
   if (!c || !n_out) return KMG_ERR_INVALID_ARG;
+  if (shard_mod > 1 && shard_rem >= shard_mod) return fail(c, KMG_ERR_INVALID_ARG, "shard must be < n_shards");
   CU(c, cudaSetDevice(c->device));
   uint64_t n = 0;
-  kmg_status s = count_filtered(c, min_count, &n);
+  kmg_status s = count_filtered(c, min_count, &n, shard_mod, shard_rem);
   if (s != KMG_OK) return s;
   *n_out = n;
   if (!d_keys || !d_counts) return KMG_OK;
   if (cap < n) return fail(c, KMG_ERR_CAPACITY, "output arrays hold " + std::to_string(cap) + " entries, need " + std::to_string(n));
-  CU(c, launch_compact(view_of(c), min_count, d_keys, d_counts, cap, c->d_stats + 3, c->stream));
+  TableView v = view_of(c);
+  v.shard_mod = shard_mod; v.shard_rem = shard_rem;
+  CU(c, launch_compact(v, min_count, d_keys, d_counts, cap, c->d_stats + 3, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   if (sorted) CU(c, sort_pairs(d_keys, d_counts, n, 2 * c->k, c->stream));
   return KMG_OK;
 }
 
-KMG_EXPORT kmg_status kmg_export_counts(kmg_ctx *c, uint64_t min_count, int sorted, uint64_t *keys, uint64_t *counts, uint64_t cap,
-                                        uint64_t *n_out) {
+kmg_status export_host(kmg_ctx *c, uint64_t min_count, int sorted, uint64_t shard_mod, uint64_t shard_rem, uint64_t *keys,
+                       uint64_t *counts, uint64_t cap, uint64_t *n_out) {
   if (!c || !n_out) return KMG_ERR_INVALID_ARG;
+  if (shard_mod > 1 && shard_rem >= shard_mod) return fail(c, KMG_ERR_INVALID_ARG, "shard must be < n_shards");
   CU(c, cudaSetDevice(c->device));
   uint64_t n = 0;
-  kmg_status s = count_filtered(c, min_count, &n);
+  kmg_status s = count_filtered(c, min_count, &n, shard_mod, shard_rem);
   if (s != KMG_OK) return s;
   *n_out = n;
   if (!keys || !counts) return KMG_OK;
@@ -1395,7 +1414,7 @@ KMG_EXPORT kmg_status kmg_export_counts(kmg_ctx *c, uint64_t min_count, int sort
   cudaError_t e = pool_alloc(c, &dc, n * 8);
   if (e != cudaSuccess) { pool_free(c, dk); return cuda_fail(c, e, "cudaMalloc(export)"); }
   uint64_t n2 = 0;
-  s = kmg_export_counts_device(c, min_count, sorted, dk, dc, n, &n2);
+  s = export_device(c, min_count, sorted, shard_mod, shard_rem, dk, dc, n, &n2);
   if (s == KMG_OK) {
     e = cudaMemcpyAsync(keys, dk, n * 8, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(counts, dc, n * 8, cudaMemcpyDeviceToHost, c->stream);
@@ -1404,6 +1423,27 @@ KMG_EXPORT kmg_status kmg_export_counts(kmg_ctx *c, uint64_t min_count, int sort
   }
   pool_free(c, dk); pool_free(c, dc);
   return s;
+}
+}  // namespace
+
+KMG_EXPORT kmg_status kmg_export_counts_device(kmg_ctx *c, uint64_t min_count, int sorted, uint64_t *d_keys, uint64_t *d_counts,
+                                               uint64_t cap, uint64_t *n_out) {
+  return export_device(c, min_count, sorted, 0, 0, d_keys, d_counts, cap, n_out);
+}
+
+KMG_EXPORT kmg_status kmg_export_counts(kmg_ctx *c, uint64_t min_count, int sorted, uint64_t *keys, uint64_t *counts, uint64_t cap,
+                                        uint64_t *n_out) {
+  return export_host(c, min_count, sorted, 0, 0, keys, counts, cap, n_out);
+}
+
+KMG_EXPORT kmg_status kmg_export_shard(kmg_ctx *c, uint64_t min_count, int sorted, uint64_t n_shards, uint64_t shard, uint64_t *keys,
+                                       uint64_t *counts, uint64_t cap, uint64_t *n_out) {
+  return export_host(c, min_count, sorted, n_shards, shard, keys, counts, cap, n_out);
+}
+
+KMG_EXPORT kmg_status kmg_export_shard_device(kmg_ctx *c, uint64_t min_count, int sorted, uint64_t n_shards, uint64_t shard,
+                                              uint64_t *d_keys, uint64_t *d_counts, uint64_t cap, uint64_t *n_out) {
+  return export_device(c, min_count, sorted, n_shards, shard, d_keys, d_counts, cap, n_out);
 }
 
 KMG_EXPORT kmg_status kmg_histogram(kmg_ctx *c, uint64_t min_count, uint64_t *count_vals, uint64_t *freqs, uint64_t cap, uint64_t *n_out) {
@@ -1473,48 +1513,164 @@ KMG_EXPORT kmg_status kmg_histogram(kmg_ctx *c, uint64_t min_count, uint64_t *co
   return KMG_OK;
 }
 
+namespace {
+// CRC-32 of a concatenation from the parts' CRCs (zlib's crc32_combine idea: advance crc1 over len2 zero bytes with
+// GF(2) matrix squaring, then xor crc2) -- lets every GPU shard checksum its own records (src/index.rs:434-456 streams one CRC).
+uint32_t gf2_times(const uint32_t *mat, uint32_t vec) {
+  uint32_t sum = 0;
+  for (; vec; vec >>= 1, ++mat) if (vec & 1) sum ^= *mat;
+  return sum;
+}
+void gf2_square(uint32_t *sq, const uint32_t *mat) { for (int n = 0; n < 32; ++n) sq[n] = gf2_times(mat, mat[n]); }
+uint32_t crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) {
+  if (len2 == 0) return crc1;
+  uint32_t even[32], odd[32];
+  odd[0] = 0xEDB88320u;  // operator for one zero bit
+  for (uint32_t n = 1, row = 1; n < 32; ++n, row <<= 1) odd[n] = row;
+  gf2_square(even, odd);  // two zero bits
+  gf2_square(odd, even);  // four zero bits
+  do {
+    gf2_square(even, odd);
+    if (len2 & 1) crc1 = gf2_times(even, crc1);
+    len2 >>= 1;
+    if (!len2) break;
+    gf2_square(odd, even);
+    if (len2 & 1) crc1 = gf2_times(odd, crc1);
+    len2 >>= 1;
+  } while (len2);
+  return crc1 ^ crc2;
+}
+
+// Stream all (key, count) records of the context to `f` in ascending key order WITHOUT a second copy of the table: the
+// key space is cut into ranges of at most ~2^25 entries (from a histogram over the top key bits), each range is compacted,
+// sorted and written on its own.  *crc is the finished CRC-32 of the bytes written here (standard init / xor-out).
+kmg_status write_kmix_records(kmg_ctx *c, FILE *f, uint32_t *crc_out, uint64_t *n_out) {
+  uint64_t n = 0;
+  kmg_status s = count_filtered(c, 0, &n);
+  if (s != KMG_OK) return s;
+  *n_out = n;
+  const Crc32 &T = crc_tables();
+  uint32_t crc = ~0u;
+  if (n) {
+    const int shift = 2 * c->k > 12 ? 2 * c->k - 12 : 0;
+    unsigned long long *d_b = nullptr;
+    CU(c, pool_alloc(c, &d_b, KEY_BUCKETS * 8));
+    std::vector<unsigned long long> hb(KEY_BUCKETS);
+    cudaError_t e = launch_key_buckets(view_of(c), shift, d_b, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hb.data(), d_b, KEY_BUCKETS * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    pool_free(c, d_b);
+    if (e != cudaSuccess) return cuda_fail(c, e, "kmix key histogram");
+    uint64_t piece_cap = std::min<uint64_t>(n, 1ull << 25);
+    for (auto v : hb) piece_cap = std::max<uint64_t>(piece_cap, v);
+    uint64_t *dk = nullptr, *dc = nullptr;
+    CU(c, pool_alloc(c, &dk, piece_cap * 8));
+    e = pool_alloc(c, &dc, piece_cap * 8);
+    if (e != cudaSuccess) { pool_free(c, dk); return cuda_fail(c, e, "cudaMalloc(kmix piece)"); }
+    const uint64_t CH = 1ull << 20;
+    std::vector<uint64_t> hk(CH), hc(CH), pairs(2 * CH);
+    bool ok = true;
+    uint64_t written = 0;
+    for (int b0 = 0; ok && b0 < KEY_BUCKETS;) {
+      uint64_t m = hb[b0];
+      int b1 = b0 + 1;
+      while (b1 < KEY_BUCKETS && m + hb[b1] <= piece_cap) m += hb[b1++];
+      if (m) {
+        TableView v = view_of(c);
+        v.range_lo = (uint64_t)b0 << shift;
+        v.range_hi = b1 == KEY_BUCKETS ? ~0ull : ((uint64_t)b1 << shift) - 1;
+        e = launch_compact(v, 0, dk, dc, piece_cap, c->d_stats + 3, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = sort_pairs(dk, dc, m, 2 * c->k, c->stream);
+        for (uint64_t i = 0; e == cudaSuccess && ok && i < m; i += CH) {
+          const uint64_t mm = std::min(CH, m - i);
+          e = cudaMemcpy(hk.data(), dk + i, mm * 8, cudaMemcpyDeviceToHost);
+          if (e == cudaSuccess) e = cudaMemcpy(hc.data(), dc + i, mm * 8, cudaMemcpyDeviceToHost);
+          if (e != cudaSuccess) break;
+          for (uint64_t j = 0; j < mm; ++j) { pairs[2 * j] = hk[j]; pairs[2 * j + 1] = hc[j]; }  // x86-64 / aarch64: little endian
+          ok = fwrite(pairs.data(), 16, mm, f) == mm;
+          crc = T.update(crc, reinterpret_cast<const uint8_t *>(pairs.data()), mm * 16);
+        }
+        if (e != cudaSuccess) { pool_free(c, dk); pool_free(c, dc); return cuda_fail(c, e, "kmix piece"); }
+        written += m;
+      }
+      b0 = b1;
+    }
+    pool_free(c, dk); pool_free(c, dc);
+    if (!ok) return fail(c, KMG_ERR_IO, "short write to the index file");
+    if (written != n) return fail(c, KMG_ERR_STATE, "kmix writer: pieces do not add up to the table");
+  }
+  *crc_out = ~crc;
+  return KMG_OK;
+}
+
+bool has_gz_suffix(const char *path) { const size_t l = strlen(path); return l >= 3 && strcmp(path + l - 3, ".gz") == 0; }
+}  // namespace
+
 KMG_EXPORT kmg_status kmg_save_kmix(kmg_ctx *c, const char *path) {
   if (!c || !path) return KMG_ERR_INVALID_ARG;
+  // src/index.rs:159-168 gzips when the path ends in .gz; this writer does not compress -- refuse rather than write raw bytes
+  // under a .gz name (the reference's load_index would reject that file)
+  if (has_gz_suffix(path)) return fail(c, KMG_ERR_INVALID_ARG, "kmg_save_kmix writes uncompressed .kmix files; gzip on the host side for a .gz path");
   CU(c, cudaSetDevice(c->device));
   uint64_t n = 0;
   kmg_status s = count_filtered(c, 0, &n);
   if (s != KMG_OK) return s;
-  uint64_t *dk = nullptr, *dc = nullptr;
-  if (n) {
-    CU(c, pool_alloc(c, &dk, n * 8));
-    cudaError_t e = pool_alloc(c, &dc, n * 8);
-    if (e != cudaSuccess) { pool_free(c, dk); return cuda_fail(c, e, "cudaMalloc(kmix)"); }
-    uint64_t n2 = 0;
-    s = kmg_export_counts_device(c, 0, /*sorted=*/1, dk, dc, n, &n2);  // sorted => byte-reproducible files
-    if (s == KMG_ERR_OOM || s == KMG_ERR_CUDA) { cudaGetLastError(); s = kmg_export_counts_device(c, 0, 0, dk, dc, n, &n2); }
-    if (s != KMG_OK) { pool_free(c, dk); pool_free(c, dc); return s; }
-  }
   FILE *f = fopen(path, "wb");
-  if (!f) { pool_free(c, dk); pool_free(c, dc); return fail(c, KMG_ERR_IO, std::string("cannot open ") + path + " for writing"); }
+  if (!f) return fail(c, KMG_ERR_IO, std::string("cannot open ") + path + " for writing");
   const Crc32 &T = crc_tables();
-  uint32_t crc = ~0u;
   uint8_t hdr[14] = {'K', 'M', 'I', 'X', 1, (uint8_t)c->k};
   for (int b = 0; b < 8; ++b) hdr[6 + b] = (uint8_t)(n >> (8 * b));
   bool ok = fwrite(hdr, 1, 14, f) == 14;
-  crc = T.update(crc, hdr, 14);
-  const uint64_t CH = 1ull << 20;
-  std::vector<uint64_t> hk(CH), hc(CH), pairs(2 * CH);
-  for (uint64_t i = 0; ok && i < n; i += CH) {
-    const uint64_t m = std::min(CH, n - i);
-    cudaError_t e = cudaMemcpy(hk.data(), dk + i, m * 8, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(hc.data(), dc + i, m * 8, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { fclose(f); pool_free(c, dk); pool_free(c, dc); return cuda_fail(c, e, "D2H kmix"); }
-    for (uint64_t j = 0; j < m; ++j) { pairs[2 * j] = hk[j]; pairs[2 * j + 1] = hc[j]; }  // x86-64/aarch64: little endian
-    ok = fwrite(pairs.data(), 16, m, f) == m;
-    crc = T.update(crc, reinterpret_cast<const uint8_t *>(pairs.data()), m * 16);
-  }
-  crc = ~crc;
+  uint32_t crc = ~T.update(~0u, hdr, 14), body_crc = 0;
+  uint64_t n2 = 0;
+  s = write_kmix_records(c, f, &body_crc, &n2);
+  if (s != KMG_OK) { fclose(f); return s; }
+  crc = crc32_combine(crc, body_crc, n2 * 16);
   uint8_t tail[4] = {(uint8_t)crc, (uint8_t)(crc >> 8), (uint8_t)(crc >> 16), (uint8_t)(crc >> 24)};
-  ok = ok && fwrite(tail, 1, 4, f) == 4;
+  ok = ok && n2 == n && fwrite(tail, 1, 4, f) == 4;
   ok = (fclose(f) == 0) && ok;
-  pool_free(c, dk); pool_free(c, dc);
   if (!ok) return fail(c, KMG_ERR_IO, std::string("short write to ") + path);
   return KMG_OK;
+}
+
+// .kmix from several shards (one context per GPU / process; src/index.rs:222-279 writes header, n records in arbitrary order,
+// CRC).  Every shard writes its records into ITS byte range of the same file -- record_offset = number of records of the shards
+// before it -- and reports their count and CRC; kmg_kmix_finish then writes the header (n = sum) and the trailing CRC combined
+// from the shards' CRCs.  The file must exist (kmg_kmix_begin creates / truncates it).
+KMG_EXPORT kmg_status kmg_kmix_begin(const char *path) {
+  if (!path || has_gz_suffix(path)) return KMG_ERR_INVALID_ARG;
+  FILE *f = fopen(path, "wb");
+  if (!f) return KMG_ERR_IO;
+  return fclose(f) == 0 ? KMG_OK : KMG_ERR_IO;
+}
+KMG_EXPORT kmg_status kmg_save_kmix_shard(kmg_ctx *c, const char *path, uint64_t record_offset, uint64_t *n_records_out, uint32_t *crc_out) {
+  if (!c || !path || !n_records_out || !crc_out) return KMG_ERR_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  FILE *f = fopen(path, "r+b");
+  if (!f) return fail(c, KMG_ERR_IO, std::string("cannot open ") + path + " (call kmg_kmix_begin first)");
+  if (fseeko(f, (off_t)(14 + 16 * record_offset), SEEK_SET) != 0) { fclose(f); return fail(c, KMG_ERR_IO, "seek failed"); }
+  kmg_status s = write_kmix_records(c, f, crc_out, n_records_out);
+  const bool ok = fclose(f) == 0;
+  if (s != KMG_OK) return s;
+  return ok ? KMG_OK : fail(c, KMG_ERR_IO, std::string("short write to ") + path);
+}
+KMG_EXPORT kmg_status kmg_kmix_finish(const char *path, uint32_t k, const uint64_t *shard_records, const uint32_t *shard_crcs, uint32_t n_shards) {
+  if (!path || k < 1 || k > 32 || (n_shards && (!shard_records || !shard_crcs))) return KMG_ERR_INVALID_ARG;
+  uint64_t n = 0;
+  for (uint32_t i = 0; i < n_shards; ++i) n += shard_records[i];
+  FILE *f = fopen(path, "r+b");
+  if (!f) return KMG_ERR_IO;
+  const Crc32 &T = crc_tables();
+  uint8_t hdr[14] = {'K', 'M', 'I', 'X', 1, (uint8_t)k};
+  for (int b = 0; b < 8; ++b) hdr[6 + b] = (uint8_t)(n >> (8 * b));
+  uint32_t crc = ~T.update(~0u, hdr, 14);
+  for (uint32_t i = 0; i < n_shards; ++i) crc = crc32_combine(crc, shard_crcs[i], shard_records[i] * 16);
+  uint8_t tail[4] = {(uint8_t)crc, (uint8_t)(crc >> 8), (uint8_t)(crc >> 16), (uint8_t)(crc >> 24)};
+  bool ok = fseeko(f, 0, SEEK_SET) == 0 && fwrite(hdr, 1, 14, f) == 14;
+  ok = ok && fseeko(f, (off_t)(14 + 16 * n), SEEK_SET) == 0 && fwrite(tail, 1, 4, f) == 4;
+  ok = (fclose(f) == 0) && ok;
+  return ok ? KMG_OK : KMG_ERR_IO;
 }
 
 KMG_EXPORT kmg_status kmg_progress(const kmg_ctx *c, uint64_t *records, uint64_t *bases) {
@@ -1530,6 +1686,17 @@ KMG_EXPORT kmg_status kmg_synth_uniform_device(kmg_ctx *c, uint64_t seed, uint64
   if (!c) return KMG_ERR_INVALID_ARG;
   CU(c, cudaSetDevice(c->device));
   if (n) CU(c, launch_synth_uniform(seed, first_base, n, d_out, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_synth_reads_device(kmg_ctx *c, uint64_t seed, uint32_t profile, uint64_t first_read, uint64_t n_reads,
+                                             uint8_t *d_seq, uint8_t *d_qual) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  if (profile != 3 && profile != 5) return fail(c, KMG_ERR_INVALID_ARG, "profile must be 3 (R20M shape) or 5 (R200M shape)");
+  if (n_reads && !d_seq) return fail(c, KMG_ERR_INVALID_ARG, "d_seq is NULL");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, launch_synth_reads(seed, profile, first_read, n_reads, d_seq, d_qual, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return KMG_OK;
 }

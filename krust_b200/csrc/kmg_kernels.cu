@@ -103,6 +103,51 @@ __global__ void synth_uniform_kernel(uint64_t seed, uint64_t first_base, uint64_
   }
 }
 
+// Synthetic READS (test / bench helper, SURVEY.md 8d: R20M for C3, R200M for C5).  Same counter-based specification as
+// oracle/kmer_oracle.c orc_synth_reads (written from the spec in that file's comment, not shared code): one thread per base.
+__device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ uint32_t synth_genome_code(uint64_t g) {
+  return (uint32_t)(splitmix64_dev(42ull * 0x9E3779B97F4A7C15ull + (g >> 5)) >> (62 - 2 * (g & 31))) & 3u;
+}
+__global__ void synth_reads_kernel(uint64_t seed, uint32_t profile, uint64_t first_read, uint64_t n_reads, uint8_t *__restrict__ seq,
+                                   uint8_t *__restrict__ qual) {
+  constexpr uint32_t L = 150;
+  constexpr uint64_t GOLD = 0x9E3779B97F4A7C15ull, GENOME = 100000000ull;
+  const uint64_t n = n_reads * L;
+  for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t rr = x / L, r = first_read + rr;
+    const uint32_t i = (uint32_t)(x - rr * L);
+    const uint64_t a = splitmix64_dev(seed * GOLD + 2 * r), b = splitmix64_dev(seed * GOLD + 2 * r + 1);
+    const uint64_t h = splitmix64_dev((seed ^ 0xABCDEFull) * GOLD + 256 * r + i);
+    uint32_t code;
+    if (profile == 5 && ((b >> 1) % 10) == 0) {  // satellite read
+      const uint32_t u = (uint32_t)((b >> 8) % 64), ulen = u == 0 ? 1u : u == 1 ? 2u : 3u + u % 29u;
+      const uint32_t j = ((uint32_t)((b >> 16) % ulen) + i) % ulen;
+      code = u == 0 ? 0u : u == 1 ? (j & 1u) : (uint32_t)(splitmix64_dev(0x5A7E111Eull + u) >> (62 - 2 * j)) & 3u;
+    } else {
+      const uint64_t start = ((a >> 32) * (GENOME - L + 1)) >> 32;
+      code = (b & 1) ? 3u - synth_genome_code(start + (L - 1 - i)) : synth_genome_code(start + i);
+    }
+    if ((h & 0xFFFF) < (profile == 3 ? 655u : 328u)) code = (code + 1u + (uint32_t)((h >> 16) & 0xFF) % 3u) & 3u;
+    uint8_t base = "ACGT"[code], q = 'I';
+    if (profile == 3) {
+      const uint32_t npos = (uint32_t)((b >> 16) % (L - 9));
+      if (((h >> 24) & 0xFFFF) < 328u || (((b >> 1) % 100) == 0 && i >= npos && i < npos + 10)) base = 'N';
+      const uint32_t uq = (uint32_t)((h >> 40) & 0xFFFF);
+      const bool late = i >= L - 30;
+      const uint32_t t0 = late ? 3932u : 1311u, t1 = late ? 19661u : 6554u, t2 = late ? 32768u : 19661u;
+      q = (uint8_t)(33 + (uq < t0 ? 2 : uq < t1 ? 11 : uq < t2 ? 25 : 37));
+    }
+    seq[x] = base;
+    if (qual) qual[x] = q;
+  }
+}
+
 // =================================================================================================
 // Tile pipeline: double-buffered TMA bulk copies of the packed stream into shared memory.
 // =================================================================================================
@@ -862,7 +907,7 @@ __global__ void table_stats_kernel(TableView v, uint64_t min_count, unsigned lon
     uint64_t key, c;
     if (view_get(v, i, key, c)) {
       sum += c;
-      if (c >= min_count) ++n;
+      if (c >= min_count && v.keeps(key)) ++n;
       mx = c > mx ? c : mx;
     }
   }
@@ -884,7 +929,7 @@ __global__ void compact_kernel(TableView v, uint64_t min_count, uint64_t *__rest
   const uint64_t n_round = (v.n + 31) & ~31ull;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round; i += stride) {
     uint64_t key = 0, c = 0;
-    bool take = i < v.n && view_get(v, i, key, c) && c >= min_count;
+    bool take = i < v.n && view_get(v, i, key, c) && c >= min_count && v.keeps(key);
     const uint32_t ballot = __ballot_sync(0xffffffffu, take);
     if (ballot == 0) continue;
     const int lane = threadIdx.x & 31;
@@ -896,6 +941,20 @@ __global__ void compact_kernel(TableView v, uint64_t min_count, uint64_t *__rest
       if (o < cap_out) { keys_out[o] = key; counts_out[o] = c; }
     }
   }
+}
+
+// entries per key bucket (top bits of the 2k-bit key): lets the .kmix writer cut the key space into pieces of bounded size
+__global__ void __launch_bounds__(256) key_buckets_kernel(TableView v, int shift, unsigned long long *buckets) {
+  __shared__ uint32_t sh[KEY_BUCKETS];
+  for (int b = threadIdx.x; b < KEY_BUCKETS; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < v.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t key, c;
+    if (view_get(v, i, key, c)) atomicAdd(&sh[(uint32_t)(key >> shift) & (KEY_BUCKETS - 1)], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < KEY_BUCKETS; b += blockDim.x)
+    if (sh[b]) atomicAdd(buckets + b, (unsigned long long)sh[b]);
 }
 
 // K6: count-of-counts.  Counts below HIST_DENSE_BINS go to dense bins (the first HIST_SMEM_BINS of them
@@ -963,6 +1022,14 @@ cudaError_t launch_start_bits(const uint64_t *d_offsets, uint64_t n_records, uin
 cudaError_t launch_synth_uniform(uint64_t seed, uint64_t first_base, uint64_t n, uint8_t *d_out, cudaStream_t s) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   synth_uniform_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(seed, first_base, n, d_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_synth_reads(uint64_t seed, uint32_t profile, uint64_t first_read, uint64_t n_reads, uint8_t *d_seq, uint8_t *d_qual,
+                               cudaStream_t s) {
+  if (n_reads == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  synth_reads_kernel<<<grid_for(n_reads * 150, 256, 8), 256, 0, s>>>(seed, profile, first_read, n_reads, d_seq, d_qual);
   return cudaGetLastError();
 }
 
@@ -1095,6 +1162,13 @@ cudaError_t launch_compact(const TableView &v, uint64_t min_count, uint64_t *d_k
   if (v.n == 0) return cudaSuccess;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   compact_kernel<<<grid_for(v.n, 256, 8), 256, 0, s>>>(v, min_count, d_keys, d_counts, cap_out, d_cursor);
+  return cudaGetLastError();
+}
+cudaError_t launch_key_buckets(const TableView &v, int shift, unsigned long long *d_bucket_counts, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(d_bucket_counts, 0, KEY_BUCKETS * sizeof(unsigned long long), s);
+  if (e != cudaSuccess || v.n == 0) return e;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  key_buckets_kernel<<<grid_for(v.n, 256, 4), 256, 0, s>>>(v, shift, d_bucket_counts);
   return cudaGetLastError();
 }
 cudaError_t launch_histogram(const TableView &v, uint64_t min_count, unsigned long long *d_bins, uint64_t *d_overflow,

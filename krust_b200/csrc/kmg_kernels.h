@@ -30,7 +30,13 @@ struct TableView {
   const uint64_t *pair_keys;         // partitioned path: consolidated run, SoA
   const uint64_t *pair_counts;
   uint64_t n;                        // slots, 4^k or number of pairs
+  uint64_t shard_mod = 0, shard_rem = 0;  // stats (entry count) / compaction only: keep keys with key % shard_mod == shard_rem (<= 1: all)
+  uint64_t range_lo = 0, range_hi = ~0ull;  // ... and range_lo <= key <= range_hi
+  __host__ __device__ bool keeps(uint64_t key) const {
+    return (shard_mod <= 1 || key % shard_mod == shard_rem) && key >= range_lo && key <= range_hi;
+  }
 };
+constexpr int KEY_BUCKETS = 4096;  // kmg_save_kmix sizes its sorted pieces from a histogram over the top 12 bits of the 2k-bit keys
 
 // ---- partitioned pipeline (kmg_partition.cu) ----------------------------------------------------------
 constexpr int CONS_MAX_RUNS = 32;  // one warp scans the segment table of a partition
@@ -110,6 +116,8 @@ cudaError_t launch_ingest(const uint8_t *d_seq, const uint8_t *d_qual, uint64_t 
 cudaError_t launch_start_bits(const uint64_t *d_offsets, uint64_t n_records, uint64_t base_offset, uint64_t n_bytes,
                               uint64_t n_words_total, uint32_t *d_start, cudaStream_t s);
 cudaError_t launch_synth_uniform(uint64_t seed, uint64_t first_base, uint64_t n, uint8_t *d_out, cudaStream_t s);
+cudaError_t launch_synth_reads(uint64_t seed, uint32_t profile, uint64_t first_read, uint64_t n_reads, uint8_t *d_seq, uint8_t *d_qual,
+                               cudaStream_t s);
 cudaError_t launch_scan_hash(const ScanInput &in, HashTable t, unsigned long long *counters, uint32_t flags, cudaStream_t s);
 cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, unsigned long long *counters, uint32_t flags,
                               cudaStream_t s);
@@ -144,6 +152,8 @@ cudaError_t launch_compact(const TableView &v, uint64_t min_count, uint64_t *d_k
                            unsigned long long *d_cursor, cudaStream_t s);
 cudaError_t launch_histogram(const TableView &v, uint64_t min_count, unsigned long long *d_bins, uint64_t *d_overflow,
                              uint64_t overflow_cap, unsigned long long *d_overflow_n, cudaStream_t s);
+// bucket_counts[key >> shift] += 1 for every entry (KEY_BUCKETS bins, zeroed by this call)
+cudaError_t launch_key_buckets(const TableView &v, int shift, unsigned long long *d_bucket_counts, cudaStream_t s);
 uint64_t kernel_launches();  // number of kernels of this library launched so far (process-wide)
 cudaError_t sort_pairs(uint64_t *d_keys, uint64_t *d_counts, uint64_t n, int key_bits, cudaStream_t s);
 

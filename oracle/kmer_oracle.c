@@ -627,3 +627,205 @@ ORC_API void orc_synth_uniform(uint64_t seed, uint64_t first_base, uint64_t n, u
     out[i] = T[(w >> (62 - 2 * (g & 31))) & 3];
   }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic READ generator (R20M for config C3, R200M for config C5), counter-based
+ * like orc_synth_uniform so that the device generator of the product library
+ * (kmg_synth_reads_device) can produce the identical bytes without shipping files; a test
+ * compares the two.  Specification (all arithmetic on u64, GOLD = 0x9E3779B97F4A7C15):
+ *   source genome = orc_synth_uniform(seed 42), SYN_GENOME bases; every read has SYN_READ_LEN bases.
+ *   read r:  a = splitmix64(seed*GOLD + 2r), b = splitmix64(seed*GOLD + 2r + 1)
+ *            start  = ((a >> 32) * (SYN_GENOME - SYN_READ_LEN + 1)) >> 32,  strand = b & 1
+ *     profile 3 (R20M): 1 % of the reads ((b >> 1) % 100 == 0) carry a 10-base N run at (b >> 16) % 141
+ *     profile 5 (R200M): 10 % of the reads ((b >> 1) % 10 == 0) come from a satellite set instead of the
+ *            genome: unit u = (b >> 8) % 64 (u = 0: "A", u = 1: "AC", else 3 + u % 29 bases drawn from
+ *            splitmix64(0x5A7E111E + u), 2 bits per base from the top), phase (b >> 16) % unit length
+ *   base i:  h = splitmix64((seed ^ 0xABCDEF)*GOLD + 256r + i)
+ *            code = genome (forward, or reverse complement when strand = 1) or satellite unit base
+ *            substitution when (h & 0xFFFF) < S (profile 3: 655 = 1 %, profile 5: 328 = 0.5 %):
+ *                code = (code + 1 + ((h >> 16) & 0xFF) % 3) & 3
+ *            profile 3: 'N' when ((h >> 24) & 0xFFFF) < 328 (0.5 %) or inside the read's N run
+ *            profile 3 quality: u = (h >> 40) & 0xFFFF, classes Phred {2, 11, 25, 37} with cumulative
+ *                thresholds {1311, 6554, 19661} (2 %, 8 %, 20 %, 70 %); in the last 30 cycles the two
+ *                lowest classes are 3x likelier: {3932, 19661, 32768} (6 %, 24 %, 20 %, 50 %)
+ *            profile 5: quality 'I' (no filter applies)
+ * ---------------------------------------------------------------------------------------- */
+#define SYN_GOLD 0x9E3779B97F4A7C15ULL
+#define SYN_GENOME 100000000ULL
+#define SYN_READ_LEN 150u
+
+static inline unsigned syn_genome_code(uint64_t g) {
+  uint64_t w = splitmix64(42ULL * SYN_GOLD + (g >> 5));
+  return (unsigned)((w >> (62 - 2 * (g & 31))) & 3);
+}
+static inline unsigned syn_unit_len(unsigned u) { return u == 0 ? 1u : u == 1 ? 2u : 3u + u % 29u; }
+static inline unsigned syn_unit_code(unsigned u, unsigned j) {
+  if (u == 0) return 0;
+  if (u == 1) return j & 1u;  /* A, C */
+  uint64_t w = splitmix64(0x5A7E111EULL + u);
+  return (unsigned)((w >> (62 - 2 * j)) & 3);
+}
+
+ORC_API void orc_synth_reads(uint64_t seed, uint32_t profile, uint64_t first_read, uint64_t n_reads,
+                             uint8_t *seq_out, uint8_t *qual_out) {
+  static const uint8_t T[4] = {'A', 'C', 'G', 'T'};
+  const unsigned L = SYN_READ_LEN;
+  for (uint64_t rr = 0; rr < n_reads; rr++) {
+    const uint64_t r = first_read + rr;
+    const uint64_t a = splitmix64(seed * SYN_GOLD + 2 * r), b = splitmix64(seed * SYN_GOLD + 2 * r + 1);
+    const uint64_t start = ((a >> 32) * (SYN_GENOME - L + 1)) >> 32;
+    const unsigned strand = (unsigned)(b & 1);
+    const int sat = profile == 5 && ((b >> 1) % 10) == 0;
+    const unsigned u = (unsigned)((b >> 8) % 64), ulen = syn_unit_len(u), phase = (unsigned)((b >> 16) % ulen);
+    const int nrun = profile == 3 && ((b >> 1) % 100) == 0;
+    const unsigned npos = (unsigned)((b >> 16) % (L - 9));
+    const unsigned sub_thr = profile == 3 ? 655u : 328u;
+    for (unsigned i = 0; i < L; i++) {
+      const uint64_t h = splitmix64((seed ^ 0xABCDEFULL) * SYN_GOLD + 256 * r + i);
+      unsigned code;
+      if (sat) code = syn_unit_code(u, (phase + i) % ulen);
+      else code = strand ? 3u - syn_genome_code(start + (L - 1 - i)) : syn_genome_code(start + i);
+      if ((h & 0xFFFF) < sub_thr) code = (code + 1 + (unsigned)((h >> 16) & 0xFF) % 3u) & 3u;
+      uint8_t base = T[code], q = 'I';
+      if (profile == 3) {
+        if (((h >> 24) & 0xFFFF) < 328u || (nrun && i >= npos && i < npos + 10)) base = 'N';
+        const unsigned uq = (unsigned)((h >> 40) & 0xFFFF);
+        const int late = i >= L - 30;
+        const unsigned t0 = late ? 3932u : 1311u, t1 = late ? 19661u : 6554u, t2 = late ? 32768u : 19661u;
+        q = (uint8_t)(33 + (uq < t0 ? 2 : uq < t1 ? 11 : uq < t2 ? 25 : 37));
+      }
+      seq_out[rr * L + i] = base;
+      if (qual_out) qual_out[rr * L + i] = q;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-threaded form of oracle #2 for inputs of BASELINE size (1e8 .. 3e9 windows): worker threads scan
+ * disjoint groups of records with the rolling predicate / canonical min of orc_add_rolling (same semantics,
+ * run.rs:526-571), optionally keep only the keys with key % filter_mod == filter_rem (a design-independent
+ * sample of the key space, used to check the 3.1 Gbp configuration shard-wise), then the keys are bucketed by
+ * their top byte and every bucket is sorted + run-length encoded by a thread.  Output arrays are malloc'ed
+ * here and released with orc_free.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t k; int has_q; uint8_t min_quality;
+  const uint8_t *seq, *qual; const uint64_t *offsets; uint64_t n_records, grain;
+  uint64_t filter_mod, filter_rem;
+  volatile uint64_t next;
+  uint64_t windows;
+  uint64_t **bufs; uint64_t *lens; /* per thread */
+} orc_mt;
+typedef struct { orc_mt *M; uint32_t tid; } orc_mt_arg;
+
+static void *orc_mt_scan(void *argp) {
+  orc_mt_arg *A = (orc_mt_arg *)argp;
+  orc_mt *M = A->M;
+  const uint64_t k = M->k, mask = k == 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
+  const uint8_t thr = sat_add_u8(M->min_quality, 33);
+  uint64_t *buf = NULL, n = 0, cap = 0, windows = 0;
+  for (;;) {
+    const uint64_t r0 = __atomic_fetch_add(&M->next, M->grain, __ATOMIC_RELAXED);
+    if (r0 >= M->n_records) break;
+    const uint64_t r1 = r0 + M->grain < M->n_records ? r0 + M->grain : M->n_records;
+    for (uint64_t r = r0; r < r1; r++) {
+      const uint8_t *s = M->seq + M->offsets[r];
+      const uint8_t *q = M->qual ? M->qual + M->offsets[r] : NULL;
+      const uint64_t len = M->offsets[r + 1] - M->offsets[r];
+      const int have_thr = M->has_q && q != NULL;
+      uint64_t fwd = 0, rc = 0, run = 0;
+      for (uint64_t e = 0; e < len; e++) {
+        const int code = orc_code(s[e]);
+        if (code < 0 || (have_thr && q[e] < thr)) { run = 0; fwd = 0; rc = 0; continue; }
+        fwd = ((fwd << 2) | (uint64_t)code) & mask;
+        rc = (rc >> 2) | ((uint64_t)(3 - code) << (2 * (k - 1)));
+        if (++run >= k) {
+          const uint64_t key = fwd < rc ? fwd : rc;
+          windows++;
+          if (M->filter_mod && key % M->filter_mod != M->filter_rem) continue;
+          if (n == cap) { cap = cap ? cap * 2 : (1u << 16); buf = (uint64_t *)realloc(buf, cap * 8); }
+          buf[n++] = key;
+        }
+      }
+    }
+  }
+  M->bufs[A->tid] = buf; M->lens[A->tid] = n;
+  __atomic_fetch_add(&M->windows, windows, __ATOMIC_RELAXED);
+  return NULL;
+}
+
+typedef struct {
+  uint64_t *keys; const uint64_t *bstart; volatile uint64_t next; uint64_t *out_n; /* per bucket: distinct */
+  uint64_t *counts;                                                                /* RLE written in place: keys[], counts[] */
+} orc_bs;
+static void *orc_bucket_sort(void *argp) {
+  orc_bs *B = (orc_bs *)argp;
+  for (;;) {
+    const uint64_t b = __atomic_fetch_add(&B->next, 1, __ATOMIC_RELAXED);
+    if (b >= 256) break;
+    uint64_t *a = B->keys + B->bstart[b];
+    const uint64_t n = B->bstart[b + 1] - B->bstart[b];
+    uint64_t *c = B->counts + B->bstart[b];
+    radix_sort_u64(a, n);
+    uint64_t d = 0;
+    for (uint64_t i = 0; i < n;) {
+      uint64_t j = i;
+      while (j < n && a[j] == a[i]) j++;
+      a[d] = a[i]; c[d] = j - i; d++;
+      i = j;
+    }
+    B->out_n[b] = d;
+  }
+  return NULL;
+}
+
+ORC_API void orc_free(void *p) { free(p); }
+
+/* Returns the number of distinct (kept) keys; *keys_out / *counts_out ascending by key; *windows_out counts
+ * ALL counted windows (before the key filter). */
+ORC_API uint64_t orc_count_batch_mt(uint32_t k, int has_min_quality, uint8_t min_quality, const uint8_t *seq,
+                                    const uint8_t *qual, const uint64_t *offsets, uint64_t n_records,
+                                    uint32_t n_threads, uint64_t filter_mod, uint64_t filter_rem,
+                                    uint64_t **keys_out, uint64_t **counts_out, uint64_t *windows_out) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  orc_mt M; memset(&M, 0, sizeof M);
+  M.k = k; M.has_q = has_min_quality; M.min_quality = min_quality;
+  M.seq = seq; M.qual = qual; M.offsets = offsets; M.n_records = n_records;
+  M.grain = n_records > 4096ull * n_threads ? 1024 : 1;
+  M.filter_mod = filter_mod; M.filter_rem = filter_rem;
+  M.bufs = (uint64_t **)calloc(n_threads, sizeof(uint64_t *));
+  M.lens = (uint64_t *)calloc(n_threads, 8);
+  pthread_t *th = (pthread_t *)malloc(n_threads * sizeof *th);
+  orc_mt_arg *args = (orc_mt_arg *)malloc(n_threads * sizeof *args);
+  for (uint32_t t = 0; t < n_threads; t++) { args[t].M = &M; args[t].tid = t; pthread_create(&th[t], NULL, orc_mt_scan, &args[t]); }
+  for (uint32_t t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  uint64_t total = 0;
+  for (uint32_t t = 0; t < n_threads; t++) total += M.lens[t];
+  /* bucket by the top byte of the 2k-bit key (for 2k < 8: by the whole key) */
+  const int sh = 2 * (int)k > 8 ? 2 * (int)k - 8 : 0;
+  uint64_t bstart[257]; memset(bstart, 0, sizeof bstart);
+  for (uint32_t t = 0; t < n_threads; t++)
+    for (uint64_t i = 0; i < M.lens[t]; i++) bstart[((M.bufs[t][i] >> sh) & 255) + 1]++;
+  for (int b = 0; b < 256; b++) bstart[b + 1] += bstart[b];
+  uint64_t *keys = (uint64_t *)malloc((total + 1) * 8), *counts = (uint64_t *)malloc((total + 1) * 8);
+  uint64_t cur[256];
+  for (int b = 0; b < 256; b++) cur[b] = bstart[b];
+  for (uint32_t t = 0; t < n_threads; t++) {
+    for (uint64_t i = 0; i < M.lens[t]; i++) { const uint64_t key = M.bufs[t][i]; keys[cur[(key >> sh) & 255]++] = key; }
+    free(M.bufs[t]);
+  }
+  uint64_t out_n[256];
+  orc_bs B; B.keys = keys; B.bstart = bstart; B.next = 0; B.out_n = out_n; B.counts = counts;
+  for (uint32_t t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, orc_bucket_sort, &B);
+  for (uint32_t t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  uint64_t d = 0;
+  for (int b = 0; b < 256; b++) {  /* close the gaps between the buckets' run-length encoded prefixes */
+    if (d != bstart[b]) { memmove(keys + d, keys + bstart[b], out_n[b] * 8); memmove(counts + d, counts + bstart[b], out_n[b] * 8); }
+    d += out_n[b];
+  }
+  free(M.bufs); free(M.lens); free(th); free(args);
+  *keys_out = keys; *counts_out = counts;
+  if (windows_out) *windows_out = M.windows;
+  return d;
+}

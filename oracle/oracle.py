@@ -66,6 +66,12 @@ def lib():
         L.orc_reference_path_count.restype = C.c_uint64
         L.orc_synth_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_synth_uniform.restype = None
+        L.orc_synth_reads.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.orc_synth_reads.restype = None
+        L.orc_free.argtypes = [C.c_void_p]; L.orc_free.restype = None
+        L.orc_count_batch_mt.argtypes = [C.c_uint32, C.c_int, C.c_uint8, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p]
+        L.orc_count_batch_mt.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -244,3 +250,33 @@ def synth_uniform(seed: int, first_base: int, n: int) -> np.ndarray:
     out = np.empty(n, dtype=np.uint8)
     lib().orc_synth_uniform(seed, first_base, n, _ptr(out))
     return out
+
+
+READ_LEN = 150  # SYN_READ_LEN of the read generator
+
+
+def synth_reads(seed: int, profile: int, first_read: int, n_reads: int, want_qual: bool = True):
+    """Synthetic reads of SURVEY.md 8d (profile 3 = R20M shape for C3, 5 = R200M shape for C5), laid back to back.
+    Returns (seq u8[n*150], qual u8[n*150] | None, offsets u64[n+1])."""
+    seq = np.empty(n_reads * READ_LEN, dtype=np.uint8)
+    qual = np.empty(n_reads * READ_LEN, dtype=np.uint8) if want_qual else None
+    lib().orc_synth_reads(seed, profile, first_read, n_reads, _ptr(seq), _ptr(qual))
+    return seq, qual, np.arange(0, (n_reads + 1) * READ_LEN, READ_LEN, dtype=np.uint64)
+
+
+def count_batch_mt(k: int, seq: np.ndarray, qual: Optional[np.ndarray], offsets: np.ndarray,
+                   min_quality: Optional[int] = None, threads: int = 0, filter_mod: int = 0, filter_rem: int = 0):
+    """Multi-threaded rolling oracle for BASELINE-sized inputs; optional key-space sample key % filter_mod == filter_rem.
+    Returns (keys, counts, windows) with keys ascending; `windows` counts all windows (before the filter)."""
+    threads = threads or (os.cpu_count() or 1)
+    seq = np.ascontiguousarray(seq, dtype=np.uint8); offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    if qual is not None:
+        qual = np.ascontiguousarray(qual, dtype=np.uint8)
+    kp, cp, w = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    L = lib()
+    n = L.orc_count_batch_mt(k, int(min_quality is not None), int(min_quality or 0), _ptr(seq), _ptr(qual), _ptr(offsets),
+                             len(offsets) - 1, threads, filter_mod, filter_rem, C.byref(kp), C.byref(cp), C.byref(w))
+    keys = np.ctypeslib.as_array(C.cast(kp, u64p), shape=(max(n, 1),))[:n].copy()
+    counts = np.ctypeslib.as_array(C.cast(cp, u64p), shape=(max(n, 1),))[:n].copy()
+    L.orc_free(kp); L.orc_free(cp)
+    return keys, counts, int(w.value)

@@ -320,10 +320,11 @@ def test_extract_and_insert_equal_direct_count():
 
 
 @pytest.mark.parametrize("k,flags", [(21, 0), (21, _lib.KMG_FLAG_FORCE_HASH), (12, 0), (5, 0)])
-def test_full_size_properties_100mbp(k, flags):
-    """BASELINE configs 1-2 at full size (100 Mbp, 100 records): properties that need no oracle --
-    sum of counts == windows, reverse-complement invariance of the whole table, linearity (counting the
-    genome twice doubles every count), histogram consistency."""
+def test_full_size_100mbp_oracle_and_properties(k, flags):
+    """BASELINE configs C1 (k=21) and C2 (k=12, k=5) at full size (G100: 100 Mbp, 100 records, seed 42): the sorted
+    (key, count) list and the histogram text against the multi-threaded rolling oracle, plus size-independent properties --
+    sum of counts == windows, reverse-complement invariance of the whole table, linearity (counting the genome twice
+    doubles every count), histogram consistency."""
     import torch
     dev = torch.device("cuda:0")
     n, n_rec = 100_000_000, 100
@@ -340,6 +341,15 @@ def test_full_size_properties_100mbp(k, flags):
         hv, hf = c.histogram(1)
         assert int(hf.sum()) == s["n_distinct"] and int((hv * hf).sum()) == s["n_windows"]
         assert (np.diff(hv.astype(np.int64)) > 0).all()
+        # the oracle on the same bytes (generated on the host by the oracle's own generator)
+        host = orc.synth_uniform(42, 0, n)
+        okeys, ocounts, owin = orc.count_batch_mt(k, host, None, np.arange(0, n + 1, n // n_rec, dtype=np.uint64))
+        del host
+        assert owin == s["n_windows"] and s["n_distinct"] == len(okeys)
+        assert_same((keys, counts), (okeys, ocounts))
+        ov, of = orc.histogram(ocounts, 1)
+        assert b"".join(b"%d\t%d\n" % (int(a), int(b)) for a, b in zip(hv, hf)) == b"".join(b"%d\t%d\n" % (int(a), int(b)) for a, b in zip(ov, of))
+        del okeys, ocounts
         # linearity
         c.count_device(buf.data_ptr(), n, d_offsets=offsets.data_ptr(), n_records=n_rec)
         c.finalize()

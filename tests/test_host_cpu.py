@@ -202,3 +202,28 @@ def test_mixed_key_constants_are_consistent():
         assert unmix(mix(key)) == key
         n = rnd.choice([2, 3, 8, 657, 928, 4096])
         assert kb.owner_of(key, n) == ((mix(key) >> 32) * n) >> 32
+
+
+def test_sharded_kmix_crc_combination_on_host(tmp_path):
+    """kmg_kmix_begin / kmg_kmix_finish are host-only: records written by 'shards' at their offsets, per-shard CRC-32s combined
+    into the file CRC (src/index.rs:222-279 format; zlib's crc32 as the independent CRC)."""
+    import zlib
+    rng = np.random.default_rng(3)
+    for sizes in ([5, 0, 11], [1], [0, 0], [4096, 1, 70000]):
+        p = tmp_path / "s.kmix"
+        kb.kmix_begin(p)
+        keys = rng.integers(0, 4**21, size=sum(sizes), dtype=np.uint64)
+        counts = rng.integers(1, 1000, size=sum(sizes), dtype=np.uint64)
+        crcs, off = [], 0
+        with open(p, "r+b") as f:
+            for n in sizes:
+                body = np.stack([keys[off:off + n], counts[off:off + n]], axis=1).astype("<u8").tobytes()
+                f.seek(14 + 16 * off); f.write(body)
+                crcs.append(zlib.crc32(body) & 0xFFFFFFFF)
+                off += n
+        kb.kmix_finish(p, 21, sizes, crcs)
+        blob = p.read_bytes()
+        assert blob == orc.kmix_encode(21, keys, counts)
+        assert kb.load_index(p).k().get() == 21
+    with pytest.raises(kb.KmeRustError):
+        kb.kmix_begin(tmp_path / "x.kmix.gz")

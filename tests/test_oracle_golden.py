@@ -202,3 +202,41 @@ def test_synth_uniform_is_counter_based():
     a = orc.synth_uniform(42, 0, 1000)
     b = orc.synth_uniform(42, 500, 500)
     assert (a[500:] == b).all() and set(a.tolist()) <= set(b"ACGT")
+
+
+def test_multithreaded_oracle_equals_literal_and_rolling():
+    """orc_count_batch_mt (used for the BASELINE-sized comparisons) against oracle #1 and #2, incl. the key-space filter."""
+    for k in (1, 2, 5, 12, 21, 31, 32):
+        seq, qual, off = orc.synth_reads(43, 3, 7, 1500)
+        lit = orc.count_batch(k, seq, qual, off, 20, mode="literal")
+        rol = orc.count_batch(k, seq, qual, off, 20, mode="rolling")
+        for threads in (1, 3):
+            mt = orc.count_batch_mt(k, seq, qual, off, 20, threads=threads)
+            assert (mt[0] == lit[0]).all() and (mt[1] == lit[1]).all() and mt[2] == lit[2] == rol[2]
+        flt = orc.count_batch_mt(k, seq, qual, off, 20, threads=2, filter_mod=5, filter_rem=2)
+        m = lit[0] % np.uint64(5) == 2
+        assert (flt[0] == lit[0][m]).all() and (flt[1] == lit[1][m]).all() and flt[2] == lit[2]
+    # empty input, records shorter than k
+    e = orc.count_batch_mt(21, np.zeros(0, dtype=np.uint8), None, np.zeros(1, dtype=np.uint64))
+    assert len(e[0]) == 0 and e[2] == 0
+    e = orc.count_batch_mt(21, np.frombuffer(b"ACGTACGT", dtype=np.uint8), None, np.array([0, 4, 8], dtype=np.uint64))
+    assert len(e[0]) == 0 and e[2] == 0
+
+
+def test_synthetic_read_generator_matches_committed_fixture(golden_dir):
+    import hashlib
+    import json
+    fx = json.load(open(os.path.join(golden_dir, "synth_reads.json")))
+    for name, f in fx.items():
+        seq, qual, off = orc.synth_reads(f["seed"], f["profile"], f["first_read"], f["reads"])
+        assert seq[:150].tobytes().decode() == f["read0"] and qual[:150].tobytes().decode() == f["qual0"], name
+        assert hashlib.sha256(seq.tobytes()).hexdigest() == f["sha256_seq"], name
+        assert hashlib.sha256(qual.tobytes()).hexdigest() == f["sha256_qual"], name
+        assert len(off) == f["reads"] + 1 and int(off[-1]) == len(seq)
+    # shape of the R20M / R200M specifications
+    seq, qual, _ = orc.synth_reads(43, 3, 0, 20000)
+    assert 0.004 < (seq == ord("N")).mean() < 0.008
+    q = qual.reshape(-1, 150)
+    assert 0.08 < (q[:, :120] < 53).mean() < 0.12 and 0.27 < (q[:, 120:] < 53).mean() < 0.33
+    seq5, qual5, _ = orc.synth_reads(45, 5, 0, 20000)
+    assert (qual5 == ord("I")).all() and (seq5 != ord("N")).all()
