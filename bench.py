@@ -1,13 +1,13 @@
 #!/usr/bin/env python
-"""Headline benchmark: canonical k-mers counted per second on the 3.1 Gbp k=21 workload
-(BASELINE.json configs[3], "C4"), hash-sharded across N B200s.
+"""Benchmark of the canonical k-mer counting path on the five BASELINE.json configurations.
 
-    python bench.py --gpus N --steps K --warmup W            # our CUDA path
-    python bench.py --impl reference --gpus N ...            # the reference's CPU algorithm (oracle port)
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path, headline config C4 (k=21, 3.1 Gbp)
+    python bench.py --config C1|C2|C3|C4|C5 ...              # the other configurations (single GPU unless stated)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU algorithm (oracle port), same config
 
-A "step" is one complete counting job: clear the table, scan the synthetic genome (ASCII already in
-HBM for `value`; pinned HOST memory for `e2e`), bucket/exchange/upsert (N>1), table final.
-Prints ONE JSON line on rank 0.  See DESIGN.md section "Measurement" for every field.
+A "step" is one complete counting job: clear the table, ingest + scan the synthetic input (ASCII already in HBM for
+`value`; pinned HOST memory for `e2e`), exchange for N>1, table final, the configuration's device-side result.
+Prints ONE JSON line on rank 0.  DESIGN.md section "Measurement" explains every field.
 """
 from __future__ import annotations
 
@@ -26,8 +26,22 @@ if ROOT not in sys.path:
 
 METRIC = "canonical k-mers counted/sec"
 UNIT = "kmers/s"
-SEED = 44                       # G3100
-B_ALG_HASH_NEW = 0.375 + 32.0   # algorithmic bytes per counted k-mer, every key new
+READ_LEN = 150
+ATOMIC_CEILING = 20.4e9   # measured random u64 atomics/s on an HBM-resident table (profiles/microbench_r1.jsonl, 8-64 GB tables)
+
+# name -> workload (generators, seeds, algorithmic bytes per counted k-mer)
+CONFIGS = {
+    "C1": dict(k=21, gen="uniform", seed=42, bases=100_000_000, records=100, alg=32.375, result="export",
+               what="k=21 canonical k-mer counting, 100 Mbp uniform-random FASTA (G100: 100 records x 1 Mbp), --format tsv"),
+    "C2": dict(k=12, gen="uniform", seed=42, bases=100_000_000, records=100, alg=16.375, result="histogram", also_k=5, also_alg=0.375,
+               what="k=12 (and k=5) direct-indexed 4^k array on the same 100 Mbp FASTA, --format histogram"),
+    "C3": dict(k=31, gen="reads", profile=3, seed=43, reads=20_000_000, min_quality=20, min_count=2, alg=24.5, result="export",
+               what="k=31, 20 M x 150 bp FASTQ-shaped reads with N bases, -Q 20, --min-count 2"),
+    "C4": dict(k=21, gen="uniform", seed=44, bases=3_100_000_000, records=31, alg=32.375, result="histogram",
+               what="k=21 canonical k-mer counting, 3.1 Gbp uniform-random FASTA (31 records x 100 Mbp), hash-sharded across N GPUs"),
+    "C5": dict(k=21, gen="reads", profile=5, seed=45, reads=200_000_000, alg=24.4, result="histogram+kmix",
+               what="k=21, 200 M x 150 bp skewed reads (~30 Gbp, 10 % satellite / poly-A), --format histogram + .kmix from GPU shards"),
+}
 
 
 def parse_args():
@@ -36,12 +50,15 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--k", type=int, default=21)
-    ap.add_argument("--bases", type=float, default=3.1e9, help="total bases of the synthetic genome")
-    ap.add_argument("--records", type=int, default=31)
-    ap.add_argument("--cpu-sample-bases", type=float, default=32e6)
+    ap.add_argument("--config", default="C4", choices=sorted(CONFIGS))
+    ap.add_argument("--k", type=int, default=0, help="override the configuration's k")
+    ap.add_argument("--bases", type=float, default=0, help="override the genome size (uniform generators)")
+    ap.add_argument("--reads", type=float, default=0, help="override the number of reads (read generators)")
+    ap.add_argument("--records", type=int, default=0)
+    ap.add_argument("--cpu-sample-bases", type=float, default=0, help="bases of the CPU sample (0 = largest that fits the time budget, <= 310 Mbp)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kmix", default="", help="C5: also time kmg_save_kmix(_shard) into this path (needs ~16 B x distinct of disk)")
     ap.add_argument("--flags", type=int, default=0)
     return ap.parse_args()
 
@@ -101,54 +118,81 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_slice(total: int, records: int, world: int, rank: int, k: int):
-    """Global stream = `records` equal records back to back.  Returns this rank's byte range and the record-start
-    offsets inside it (relative), per krust_b200.dist.slice_for_rank."""
-    import numpy as np
-    from krust_b200.dist import slice_for_rank
-    a, b = slice_for_rank(total, world, rank, k)
-    rec_len = total // records
-    starts = [r * rec_len for r in range(records)]
-    inside = [s - a for s in starts if a < s < b]
-    offsets = np.array([0] + inside + [b - a], dtype=np.uint64)
-    return a, b, offsets
+def resolve(args) -> dict:
+    cfg = dict(CONFIGS[args.config])
+    cfg["name"] = args.config
+    if args.k:
+        cfg["k"] = args.k
+    if args.bases and cfg["gen"] == "uniform":
+        cfg["bases"] = int(args.bases)
+    if args.reads and cfg["gen"] == "reads":
+        cfg["reads"] = int(args.reads)
+    if args.records and cfg["gen"] == "uniform":
+        cfg["records"] = args.records
+    if cfg["gen"] == "reads":
+        cfg["bases"] = cfg["reads"] * READ_LEN
+        cfg["records"] = cfg["reads"]
+    return cfg
 
 
-def expected_windows(total: int, records: int, k: int) -> int:
+def expected_windows_uniform(total: int, records: int, k: int) -> int:
     rec_len = total // records
     last = total - rec_len * (records - 1)
     return (records - 1) * max(0, rec_len - k + 1) + max(0, last - k + 1)
 
 
-def run_reference(args, rank: int):
-    """The reference's own CPU algorithm (oracle port: the Rust crate cannot be built here) on a bounded
-    sample of the same workload, all host threads."""
-    if rank != 0:
-        return
+# --------------------------------------------------------------------------------------------- reference arm
+def cpu_sample(cfg, sample_bases: int):
+    """A bounded sample of the configuration's own generator for the CPU arm: (seq, qual, offsets, description)."""
     import numpy as np
     from oracle import oracle as orc
+    if cfg["gen"] == "uniform":
+        rec = max(1, cfg["records"])
+        rec_len = max(cfg["k"], sample_bases // rec)
+        n = rec_len * rec
+        seq = orc.synth_uniform(cfg["seed"], 0, n)
+        return seq, None, np.arange(0, n + 1, rec_len, dtype=np.uint64), f"{rec} records x {rec_len} bp uniform ACGT (seed {cfg['seed']})"
+    n_reads = max(1, sample_bases // READ_LEN)
+    seq, qual, off = orc.synth_reads(cfg["seed"], cfg["profile"], 0, n_reads, want_qual=cfg.get("min_quality") is not None)
+    return seq, qual, off, f"{n_reads} reads x {READ_LEN} bp of the profile-{cfg['profile']} read generator (seed {cfg['seed']})"
+
+
+def run_reference(args, rank: int):
+    """The reference's own CPU algorithm (oracle port: the Rust crate cannot be built here) on a bounded sample of the same
+    workload, all host threads.  Sample per step: the largest prefix (<= 310 Mbp, what the packed map of a 62 GB host holds)
+    such that W/8 + K steps stay within ~3 minutes at the rate measured during warm-up."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    cfg = resolve(args)
     cores = os.cpu_count() or 1
-    n = int(args.cpu_sample_bases)
-    rec = max(1, args.records)
-    rec_len = n // rec
-    n = rec_len * rec
-    seq = orc.synth_uniform(SEED, 0, n)
-    offsets = np.arange(0, n + 1, rec_len, dtype=np.uint64)
-    for _ in range(args.warmup):
-        orc.reference_path_count(args.k, seq[: n // 8], None, (offsets // 8).astype(np.uint64), threads=cores)
+    k, q = cfg["k"], cfg.get("min_quality")
+    probe = cpu_sample(cfg, 16_000_000)
+    t0 = time.perf_counter()
+    orc.reference_path_count(k, probe[0], probe[1], probe[2], min_quality=q, threads=cores)
+    rate = float(probe[2][-1]) / max(time.perf_counter() - t0, 1e-3)   # bases/s, small-map regime (optimistic)
+    if args.cpu_sample_bases:
+        n = int(args.cpu_sample_bases)
+    else:
+        n = int(min(310e6, max(32e6, 0.6 * 180.0 * rate / max(1, args.steps))))
+    n = min(n, cfg["bases"])
+    seq, qual, offsets, what = cpu_sample(cfg, n)
+    for _ in range(max(0, args.warmup - 1)):
+        m = max(1, (len(offsets) - 1) // 8)
+        orc.reference_path_count(k, seq[: int(offsets[m])], None if qual is None else qual[: int(offsets[m])], offsets[: m + 1], min_quality=q, threads=cores)
     t0 = time.perf_counter()
     windows = 0
     for _ in range(args.steps):
-        w, _d = orc.reference_path_count(args.k, seq, None, offsets, threads=cores)
+        w, _d = orc.reference_path_count(k, seq, qual, offsets, min_quality=q, threads=cores)
         windows += w
     dt = time.perf_counter() - t0
     value = windows / dt
-    sample = f"{rec} records x {rec_len} bp uniform ACGT (seed {SEED}), k={args.k}, per step; restated reference CPU path (oracle/kmer_oracle.c orc_reference_path_count)"
+    sample = f"{what}, k={k}, per step; restated reference CPU path (oracle/kmer_oracle.c orc_reference_path_count)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "C4: k=21 canonical k-mer counting, 3.1 Gbp uniform-random FASTA (31 x 100 Mbp), bounded CPU sample",
-                       "k": args.k, "sample_bases": n},
+            "config": {"workload": f"{cfg['name']}: {cfg['what']}; bounded CPU sample", "k": k, "sample_bases": int(offsets[-1]),
+                       "full_bases": cfg["bases"]},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -175,6 +219,7 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+# --------------------------------------------------------------------------------------------- our arm
 def main():
     args = parse_args()
     claim_stdout()
@@ -192,9 +237,9 @@ def main():
     import torch
     import torch.distributed as dist
 
-    import krust_b200 as kb
+    import krust_b200 as kb  # noqa: F401
     from krust_b200 import _lib
-    from krust_b200.dist import GpuShardEngine, ShardedKmerCounter
+    from krust_b200.dist import GpuShardEngine, ShardedKmerCounter, slice_for_rank
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: krust_b200 has no CPU fallback")
@@ -204,20 +249,42 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.load()
+    cfg = resolve(args)
+    k = cfg["k"]
+    reads = cfg["gen"] == "reads"
+    min_q = cfg.get("min_quality")
+    min_count = cfg.get("min_count", 1)
 
-    k = args.k
-    total = int(args.bases)
-    a, b, offsets_np = workload_slice(total, args.records, world, rank, k)
-    n_local = b - a
-    exp_windows = expected_windows(total, args.records, k)
-
-    # ---- synthetic input, generated on the device (same counter-based generator as the oracle)
+    # ---- this rank's slice of the synthetic input, generated on the device (same counter-based generators as the oracle)
+    if reads:
+        r0, r1 = cfg["reads"] * rank // world, cfg["reads"] * (rank + 1) // world
+        n_local = (r1 - r0) * READ_LEN
+        n_rec_local = r1 - r0
+    else:
+        a, b = slice_for_rank(cfg["bases"], world, rank, k)
+        n_local = b - a
+        rec_len = cfg["bases"] // cfg["records"]
+        inside = [s - a for s in (r * rec_len for r in range(cfg["records"])) if a < s < b]
+        offsets_np = np.array([0] + inside + [n_local], dtype=np.uint64)
+        n_rec_local = len(offsets_np) - 1
+        exp_windows = expected_windows_uniform(cfg["bases"], cfg["records"], k)
     d_seq = torch.empty(n_local + 64, dtype=torch.uint8, device=dev)[:n_local]
-    d_off = torch.from_numpy(offsets_np.astype(np.int64)).to(dev)
-    engine = GpuShardEngine(k, dev, expected_distinct=int(exp_windows / world * 1.03) + 1024, flags=args.flags)
-    engine.counter.synth_uniform_device(SEED, a, n_local, d_seq.data_ptr())
+    d_qual = torch.empty(n_local + 64, dtype=torch.uint8, device=dev)[:n_local] if (reads and min_q is not None) else None
+    hint = int(cfg["bases"] / world * 1.03) + 1024 if (not reads or min_q is None) else 0   # quality-filtered: planned from the data
+    CH_READS = 1 << 24   # reads per device call (2.5 GB of ASCII): every call leaves a run; large jobs consolidate while streaming
+    bb = 0
+    if world > 1:   # sharded: one fused scatter + exchange round moves <= batch_bases bases per rank (identical on every rank)
+        per_rank = (cfg["bases"] + world - 1) // world + k
+        rounds = max(1, round(per_rank / 3.0e8)) if not reads else max(1, -(-per_rank // (CH_READS * READ_LEN)))
+        bb = ((per_rank + rounds - 1) // rounds + k + 31) // 32 * 32
+    engine = GpuShardEngine(k, dev, min_quality=min_q, expected_distinct=hint, flags=args.flags, batch_bases=bb)
+    if reads:
+        engine.counter.synth_reads_device(cfg["seed"], cfg["profile"], r0, n_rec_local, d_seq.data_ptr(), d_qual.data_ptr() if d_qual is not None else 0)
+        d_off = torch.arange(0, (min(CH_READS, n_rec_local) + 1) * READ_LEN, READ_LEN, dtype=torch.int64, device=dev)
+    else:
+        engine.counter.synth_uniform_device(cfg["seed"], a, n_local, d_seq.data_ptr())
+        d_off = torch.from_numpy(offsets_np.astype(np.int64)).to(dev)
     sharded = ShardedKmerCounter(engine)
-    off_arg = d_off if len(offsets_np) > 2 else None
 
     def barrier():
         if world > 1:
@@ -231,17 +298,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def step_device():
-        t_dbg = time.perf_counter()
-        engine.reset()
-        if os.environ.get("KMG_DIST_TIMING") and rank == 0:
-            torch.cuda.synchronize(dev); print(f"[dist timing] reset: {(time.perf_counter() - t_dbg) * 1e3:.2f} ms", file=sys.stderr, flush=True); t_dbg = time.perf_counter()
-        sharded.count(d_seq, off_arg, expected_keys_per_rank=exp_windows // world + 1024)
-        if os.environ.get("KMG_DIST_TIMING") and rank == 0:
-            t_dbg = time.perf_counter()
+    def feed_device():
+        if not reads:
+            sharded.count(d_seq, d_off if n_rec_local > 1 else None, expected_keys_per_rank=exp_windows // world + 1024)
+            return
+        for c0 in range(0, n_rec_local, CH_READS):
+            c1 = min(n_rec_local, c0 + CH_READS)
+            sl = slice(c0 * READ_LEN, c1 * READ_LEN)
+            sharded.count(d_seq[sl], d_off[: c1 - c0 + 1], None if d_qual is None else d_qual[sl],
+                          expected_keys_per_rank=cfg["bases"] // world)
+
+    def device_result():
+        """the configuration's result, device side: table final (+ the count-of-counts for the histogram outputs)"""
         engine.finalize(False)
-        if os.environ.get("KMG_DIST_TIMING") and rank == 0:
-            torch.cuda.synchronize(dev); print(f"[dist timing] finalize: {(time.perf_counter() - t_dbg) * 1e3:.2f} ms", file=sys.stderr, flush=True)
+        if "histogram" in cfg["result"]:
+            return sharded.histogram(min_count)
+        return None
+
+    def step_device():
+        engine.reset()
+        feed_device()
+        return device_result()
 
     # ---- device-resident timing: W warm-up, then exactly K steps between barriers, CUDA events, max over ranks
     for _ in range(args.warmup):
@@ -262,37 +339,47 @@ def main():
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_per_step = ms_total / args.steps
     summary = sharded.finalize()   # global sums over shards
-    if summary["n_windows"] != exp_windows:
+    if reads:
+        exp_windows = summary["n_windows"]        # reads: no closed form (N bases, quality filter); parity is checked in tests/
+        if min_q is None and exp_windows != cfg["reads"] * (READ_LEN - k + 1):
+            raise SystemExit(f"PARITY FAILURE: counted {exp_windows} windows, expected {cfg['reads'] * (READ_LEN - k + 1)}")
+    elif summary["n_windows"] != exp_windows:
         raise SystemExit(f"PARITY FAILURE: counted {summary['n_windows']} windows, expected {exp_windows}")
     local = summary.get("local", summary)
     value = exp_windows / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel, timed live with CUDA events on its launching stream
+    # ---- roofline.  frac_job: the design-independent algorithmic bytes of SURVEY.md 8(d) over the whole step;
+    # frac / achieved: the dominant kernel alone with ITS algorithmic bytes, timed live with CUDA events on its stream
     peak, peak_src = peaks()
-    pipeline = None
     gpu_windows = exp_windows / world   # per-GPU share (strong scaling)
+    input_bytes = 0.375 * cfg["bases"] / world
+    new_frac = summary["n_distinct"] / max(1, exp_windows)
+    if local["path"] == 1:
+        alg_job = gpu_windows * (16.0 if k > 6 else 0.0) + input_bytes
+    else:
+        alg_job = gpu_windows * 24.0 + 8.0 * summary["n_distinct"] / world + input_bytes
+    pipeline = None
     if local["path"] == 2:
-        # partitioned pipeline: phase A (A1 scan + coarse scatter, A2 refine) and phase B (count_partitions kernel); reset()
-        # clears the timers, so these are the last step's kernels on rank 0.  Algorithmic bytes per k-mer: A1 = 0.375 in + 8 out,
-        # A2 = 8 in + 8 out, B = 8 in + 16 out; design-independent figure for the whole job: 32.375.
+        # partitioned pipeline: phase A (ingest, A1 partition_scatter_rows, A2 refine_rows) and phase B (count_partitions_smem); reset()
+        # clears the timers, so these are the last step's kernels on this rank.  Per k-mer: A1 = 0.375 in + 8 out, A2 = 8 in + 8 out,
+        # B = 8 in + 16 out per DISTINCT key.
         a_ms, b_ms = local["scan_ns"] / 1e6, local["consolidate_ns"] / 1e6
-        pipeline = {"phase_a_ms": a_ms, "phase_b_ms": b_ms, "phase_a_gbs": gpu_windows * 24.375 / (a_ms * 1e-3) / 1e9 if a_ms else 0.0,
-                    "phase_b_gbs": gpu_windows * 24.0 / (b_ms * 1e-3) / 1e9 if b_ms else 0.0,
-                    "whole_gbs": gpu_windows * B_ALG_HASH_NEW / ((a_ms + b_ms) * 1e-3) / 1e9 if a_ms + b_ms else 0.0}
-        # dominant single KERNEL: phase B is one launch; phase A is five (ingest, partition_count, partition_scatter_staged,
-        # refine<count>, refine<scatter>), the largest of which takes ~40 % of phase A (profiles/r1_v5_launches.csv)
+        b_bytes = gpu_windows * 8.0 + 16.0 * summary["n_distinct"] / world
+        pipeline = {"phase_a_ms": a_ms, "phase_b_ms": b_ms,
+                    "phase_a_gbs": (gpu_windows * 24.0 + input_bytes) / (a_ms * 1e-3) / 1e9 if a_ms else 0.0,
+                    "phase_b_gbs": b_bytes / (b_ms * 1e-3) / 1e9 if b_ms else 0.0,
+                    "consolidations": local["n_grows"]}
         if b_ms >= 0.4 * a_ms:
-            kern_ms, per_unit, kern_name = b_ms, 24.0, "count_partitions_smem_kernel (phase B: one CTA per hash partition, upsert into a shared-memory table, compact)"
+            kern_ms, alg_bytes, kern_name = b_ms, b_bytes, "count_partitions_smem_kernel (phase B: one CTA per hash partition, upsert into a shared-memory table, compact)"
         else:
-            kern_ms, per_unit, kern_name = a_ms, 24.375, "phase A kernels (partition_count/scatter over the scan + refine count/scatter: two-level hash partitioning)"
-        alg_bytes = gpu_windows * per_unit
+            kern_ms, alg_bytes, kern_name = a_ms, gpu_windows * 24.0 + input_bytes, "phase A kernels (ingest + partition_scatter_rows + refine_rows: two-level hash partitioning)"
     else:
         kern_ms = local["kernel_ns"] / 1e6          # scan_count_kernel of the last step (reset() clears the timer)
-        alg_bytes = gpu_windows * B_ALG_HASH_NEW
-        kern_name = "scan_count_kernel (tile scan + upsert into one HBM-resident table / direct-indexed array)"
-        per_unit = B_ALG_HASH_NEW
+        alg_bytes = alg_job
+        kern_name = ("scan_count_kernel<DENSE> (tile scan + direct-indexed 4^k array: shared-memory privatised for k <= 6, L2 atomics above)"
+                     if local["path"] == 1 else "scan_count_kernel<HASH> (tile scan + upsert into one HBM-resident table)")
     # DRAM traffic of the dominant kernel: bytes per k-mer from the committed `ncu --set full` capture (taken on a 5e8-base
-    # slice of the same workload: the full job would make ncu save/restore ~100 GB per pass), scaled to this launch
+    # slice of C4: the full job would make ncu save/restore ~100 GB per pass), scaled to this launch -- not measured in this run
     traffic = None
     try:
         tpk = json.load(open(os.path.join(ROOT, "profiles", "traffic_per_kmer.json")))
@@ -302,30 +389,94 @@ def main():
     except Exception:
         traffic = None
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    job_gbs = alg_job / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": kern_name, "kernel_ms": kern_ms, "alg_bytes_per_kmer": per_unit, "peak_source": peak_src,
+                "traffic_source": "scaled from the committed ncu --set full capture of a 5e8-base C4 slice (profiles/traffic_per_kmer.json)" if traffic else None,
+                "kernel": kern_name, "kernel_ms": kern_ms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "frac_job": job_gbs / peak, "job_gbs": job_gbs, "alg_bytes_per_kmer_job": alg_job / max(1.0, gpu_windows),
+                "survey_alg_bytes_per_kmer": cfg["alg"], "new_key_fraction": new_frac,
+                "atomic_ceiling_frac": value / world / ATOMIC_CEILING,
+                "atomic_ceiling": "20.4 G random u64 atomics/s on an HBM-resident table (profiles/microbench_r1.jsonl): what ONE open-addressing "
+                                  "HBM table could reach at best; > 1 means the partitioned design beats that ceiling",
                 "pipeline": pipeline}
 
-    # ---- end to end: HOST (pinned) ASCII in, histogram + summary out, through the public C-ABI call
+    # ---- C2 also names k=5: one more device-resident measurement on the same input (shared-memory privatised counters)
+    also = None
+    if cfg.get("also_k") and world == 1:
+        k2 = cfg["also_k"]
+        with kb.GpuKmerCounter(k2, device=dev.index) as c2:
+            def step2():
+                c2.reset()
+                c2.count_device(d_seq.data_ptr(), n_local, d_offsets=d_off.data_ptr(), n_records=n_rec_local)
+                c2.finalize(False)
+                return c2.histogram(1)
+            for _ in range(args.warmup):
+                step2()
+            torch.cuda.synchronize(dev)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(dev))
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                hv2, hf2 = step2()
+            torch.cuda.synchronize(dev)
+            ms2 = (time.perf_counter() - t0) * 1e3 / args.steps
+            s2 = c2.finalize()
+            w2 = expected_windows_uniform(cfg["bases"], cfg["records"], k2)
+            if s2["n_windows"] != w2 or int((hv2 * hf2).sum()) != w2:
+                raise SystemExit("PARITY FAILURE in the k=5 leg")
+            km = s2["kernel_ns"] / 1e6
+            also = {"k": k2, "value": w2 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "kernel_ms": km, "path": s2["path"],
+                    "input_gbs": 0.375 * cfg["bases"] / (km * 1e-3) / 1e9 if km else None,
+                    "frac": 0.375 * cfg["bases"] / (km * 1e-3) / 1e9 / peak if km else None,
+                    "note": "k=5: 512 canonical keys, counters privatised per CTA in shared memory; bound by shared-memory atomic issue, "
+                            "algorithmic bytes = packed input only (0.375 B/k-mer)"}
+
+    # ---- end to end: HOST (pinned) ASCII in, the configuration's result on the HOST, through the public C-ABI calls
     e2e = None
     if not args.no_e2e:
-        h_seq = torch.empty(n_local, dtype=torch.uint8, pin_memory=True)
-        h_seq.copy_(d_seq)
+        import psutil
+        need = n_local * (2 if d_qual is not None else 1)
+        avail = psutil.virtual_memory().available
+        frac_e2e = 1.0
+        n_e2e_rec, n_e2e = n_rec_local, n_local
+        if need > 0.6 * avail:   # C5 at full size wants 30 GB of pinned memory: take the largest prefix the host can pin
+            frac_e2e = 0.6 * avail / need
+            n_e2e_rec = max(1, int(n_rec_local * frac_e2e))
+            n_e2e = n_e2e_rec * READ_LEN if reads else int(n_local * frac_e2e)
+        h_seq = torch.empty(n_e2e, dtype=torch.uint8, pin_memory=True)
+        h_seq.copy_(d_seq[:n_e2e])
+        h_qual = None
+        if d_qual is not None:
+            h_qual = torch.empty(n_e2e, dtype=torch.uint8, pin_memory=True)
+            h_qual.copy_(d_qual[:n_e2e])
         torch.cuda.synchronize(dev)
         h_np = h_seq.numpy()
+        hq_np = h_qual.numpy() if h_qual is not None else None
+        if reads:
+            off_e2e = np.arange(0, (n_e2e_rec + 1) * READ_LEN, READ_LEN, dtype=np.uint64)
+        elif frac_e2e < 1.0:
+            off_e2e = np.append(offsets_np[offsets_np < n_e2e], np.uint64(n_e2e)).astype(np.uint64)
+        else:
+            off_e2e = offsets_np
         d2h_bytes = 0
+        e2e_windows = 0
 
         def step_e2e():
-            nonlocal d2h_bytes
+            nonlocal d2h_bytes, e2e_windows
             engine.reset()
             if world == 1:
-                engine.counter.count_batch(h_np, None, offsets_np)     # kmg_count_ascii: chunked H2D overlapped with the kernels
+                engine.counter.count_batch(h_np, hq_np, off_e2e)     # kmg_count_ascii: chunked H2D overlapped with the kernels
             else:
-                d_tmp = h_seq.to(dev, non_blocking=True)
-                sharded.count(d_tmp, off_arg, expected_keys_per_rank=exp_windows // world + 1024)
+                sharded.count_host(h_np, off_e2e, hq_np, expected_keys_per_rank=cfg["bases"] // world + 1024)
             engine.finalize(False)
-            vals, freqs = sharded.histogram(1)                          # D2H of the result
+            if cfg["result"] == "export":                            # what count_kmers_streaming_packed returns: the (filtered) map
+                keys, counts = engine.counter.export(min_count, sorted=False)
+                d2h_bytes = keys.nbytes + counts.nbytes
+                e2e_windows = -1
+                return keys, counts
+            vals, freqs = sharded.histogram(min_count)               # D2H of the count-of-counts
             d2h_bytes = (vals.nbytes + freqs.nbytes) + 65536 * 8
+            e2e_windows = int((vals * freqs).sum())
             return vals, freqs
 
         for _ in range(max(2, args.warmup // 2)):   # the first host-fed step sizes the staging ring and the pool
@@ -333,44 +484,63 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            vals, freqs = step_e2e()
+            res = step_e2e()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
-        if int((vals * freqs).sum()) != exp_windows:
+        s_e2e = sharded.finalize()
+        if frac_e2e == 1.0 and s_e2e["n_windows"] != exp_windows:
             raise SystemExit("PARITY FAILURE in the end-to-end path")
-        e2e = {"value": exp_windows / (dt / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(n_local + offsets_np.nbytes),
+        e2e = {"value": s_e2e["n_windows"] / (dt / args.steps), "unit": UNIT,
+               "h2d_bytes_per_step": int(n_e2e * (2 if hq_np is not None else 1) + off_e2e.nbytes),
                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": dt / args.steps * 1e3,
-               "result": "count-of-counts histogram + summary to host; table stays in HBM"}
-        del h_seq
+               "result": ("filtered (key, count) arrays on the host (min_count %d): %d entries" % (min_count, len(res[0]))) if cfg["result"] == "export"
+                         else "count-of-counts histogram + summary to host; table stays in HBM",
+               "input_fraction": frac_e2e}
+        del h_seq, h_qual
 
-    # ---- CPU baseline on the box's host cores (rank 0, N=1 only; bounded sample)
+    # ---- C5: the .kmix index written from the GPU shard(s) (timed once, outside the steps: it is disk-bound)
+    kmix = None
+    if args.kmix and "kmix" in cfg["result"]:
+        engine.reset(); feed_device(); engine.finalize(False)
+        t0 = time.perf_counter()
+        info = sharded.save_kmix(args.kmix)
+        barrier()
+        kmix = {"seconds": max_over_ranks(time.perf_counter() - t0), "records": info["records"], "bytes": 18 + 16 * info["records"], "path": args.kmix}
+
+    # ---- CPU baseline on the box's host cores (rank 0, N=1 only; bounded sample of the same generator)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         cores = os.cpu_count() or 1
-        rec_len = int(args.cpu_sample_bases) // args.records
-        n = rec_len * args.records
-        seq = orc.synth_uniform(SEED, 0, n)
-        offs = np.arange(0, n + 1, rec_len, dtype=np.uint64)
+        n = int(args.cpu_sample_bases) if args.cpu_sample_bases else int(min(310e6, cfg["bases"]))
+        seq, qual, offs, what = cpu_sample(cfg, n)
         t0 = time.perf_counter()
-        w, _d = orc.reference_path_count(k, seq, None, offs, threads=cores)
+        w, _d = orc.reference_path_count(k, seq, qual, offs, min_quality=min_q, threads=cores)
         dt = time.perf_counter() - t0
         cpu = {"value": w / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.records} records x {rec_len} bp of the same generator (seed {SEED}), k={k}; restated reference CPU path, {dt:.1f} s"}
+               "sample": f"{what}, k={k}: the largest prefix whose packed map fits a 62 GB host (<= 310 Mbp); restated reference CPU path, {dt:.1f} s"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
                 "data": "synthetic",
-                "config": {"workload": "C4: k=21 canonical k-mer counting, 3.1 Gbp uniform-random FASTA (31 records x 100 Mbp), "
-                                       "hash-sharded across N GPUs",
-                           "k": k, "bases": total, "records": args.records, "windows": exp_windows,
-                           "distinct": summary["n_distinct"], "path": {0: "hbm-table", 1: "direct-4^k", 2: "partitioned"}[local["path"]],
+                "config": {"workload": f"{cfg['name']}: {cfg['what']}",
+                           "k": k, "bases": cfg["bases"], "records": cfg["records"], "windows": exp_windows,
+                           "distinct": summary["n_distinct"], "max_count": summary["max_count"],
+                           "min_quality": min_q, "min_count": min_count,
+                           "path": {0: "hbm-table", 1: "direct-4^k", 2: "partitioned"}[local["path"]],
                            "table_slots_or_partitions_per_gpu": local["table_capacity"],
-                           "l2_policy": "inputs and table are far larger than L2 (no flush needed)",
-                           "step": "table clear + ingest + scan/upsert (+ bucket, all-to-all, upsert for N>1) + finalize",
+                           "l2_policy": "inputs and tables are far larger than L2 (no flush needed)" if cfg["bases"] > 5e8 else
+                                        "input (>= 100 MB ASCII + packed streams) exceeds the 126 MB L2 between steps; the k=12 counter array (134 MB) does too",
+                           "step": "table clear + ingest + scan/upsert (+ fused bucket/exchange over NVLink for N>1) + finalize + device-side result",
                            "parallelism": f"hash-shard x{world}" if world > 1 else "single GPU"},
                 "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+        if also:
+            line["also"] = also
+        if kmix:
+            line["kmix"] = kmix
+        if world > 1:
+            line["exchange"] = sharded.stats()
         emit(line)
     engine.close()
     if world > 1:

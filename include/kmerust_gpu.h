@@ -158,6 +158,33 @@ uint32_t kmg_owner_of(uint64_t canonical_key, uint32_t n_shards);
 kmg_status kmg_partition_plan(kmg_ctx *ctx, uint64_t expected_keys, uint32_t *n_coarse, uint32_t *n_sub);
 kmg_status kmg_adopt_coarse_device(kmg_ctx *ctx, const uint64_t *d_keys, const uint64_t *bin_counts, uint32_t n_bins, uint64_t n);
 
+/* ---- hash-sharded counting across the GPUs of one box ------------------------------------------------------
+ * One context per GPU -- one process per device (torchrun, a Rust host that forks per GPU) or one thread per device -- joined
+ * into a group.  The table shards by k-mer hash; the exchange is fused into the scan: the scatter kernel of every rank writes
+ * each hash bin straight into its owner's receive buffer through P2P-mapped memory (NVLink stores), the owner refines and
+ * counts what arrived.  Only sizes, flags and results cross on the host, through a POSIX shared-memory segment named after
+ * `group` (created by rank 0, unlinked once everybody is attached) -- no NCCL inside the library.  All kmg_shard_* calls are
+ * COLLECTIVE: every rank makes the same sequence of them (a rank without input passes n_bytes / n_records = 0); a rank that
+ * fails marks the group aborted, so its peers return KMG_ERR_STATE instead of waiting.  world == 1 degenerates to the plain
+ * single-GPU calls.  Local feeds (kmg_count_ascii, kmg_insert_keys_device ...) are refused on a grouped context.
+ *   kmg_shard_join: before the first feed; identical k / batch_bases / expected_keys_total (keys of the WHOLE job; 0 = the
+ *   config's expected_distinct) on every rank.  One round moves at most batch_bases bases per rank.
+ * Replaces the single shared DashMap of src/run.rs:489-583 by `world` disjoint tables. */
+kmg_status kmg_shard_join(kmg_ctx *ctx, uint32_t world, uint32_t rank, const char *group, uint64_t expected_keys_total);
+kmg_status kmg_shard_leave(kmg_ctx *ctx);
+/* THIS rank's slice of the records; layouts as kmg_count_ascii_device / kmg_count_ascii. */
+kmg_status kmg_shard_count_ascii_device(kmg_ctx *ctx, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_offsets,
+                                        uint64_t n_records, uint64_t n_bytes);
+kmg_status kmg_shard_count_ascii(kmg_ctx *ctx, const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets, uint64_t n_records);
+/* kmg_finalize + the summary of the WHOLE table (sums over the shards; kernel timings stay this rank's). */
+kmg_status kmg_shard_finalize(kmg_ctx *ctx, kmg_summary *summary);
+/* kmg_histogram merged over the shards (element-wise sum); the size query does the merge, the second call copies it out. */
+kmg_status kmg_shard_histogram(kmg_ctx *ctx, uint64_t min_count, uint64_t *count_vals, uint64_t *freqs, uint64_t cap, uint64_t *n_out);
+/* ONE .kmix from all shards: rank 0 writes header and combined CRC, every rank its own records (src/index.rs:222-279). */
+kmg_status kmg_shard_save_kmix(kmg_ctx *ctx, const char *path, uint64_t *n_records_out);
+/* Diagnostics: keys written to other ranks, keys received, rounds, rounds that took the exact (count + prefix) route. */
+kmg_status kmg_shard_stats(const kmg_ctx *ctx, uint64_t *sent_keys, uint64_t *recv_keys, uint64_t *rounds, uint64_t *exact_rounds);
+
 /* Waits for all queued work; replaces into_hashmap()'s barrier role (src/run.rs:573-582). */
 kmg_status kmg_finalize(kmg_ctx *ctx, kmg_summary *summary);
 

@@ -51,6 +51,14 @@ SIGNATURES = {
     "kmg_owner_of": (u32, [u64, u32]),
     "kmg_partition_plan": (i32, [vp, u64, C.POINTER(u32), C.POINTER(u32)]),
     "kmg_adopt_coarse_device": (i32, [vp, vp, vp, u32, u64]),
+    "kmg_shard_join": (i32, [vp, u32, u32, C.c_char_p, u64]),
+    "kmg_shard_leave": (i32, [vp]),
+    "kmg_shard_count_ascii_device": (i32, [vp, vp, vp, vp, u64, u64]),
+    "kmg_shard_count_ascii": (i32, [vp, vp, vp, vp, u64]),
+    "kmg_shard_finalize": (i32, [vp, C.POINTER(KmgSummary)]),
+    "kmg_shard_histogram": (i32, [vp, u64, vp, vp, u64, C.POINTER(u64)]),
+    "kmg_shard_save_kmix": (i32, [vp, C.c_char_p, C.POINTER(u64)]),
+    "kmg_shard_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
     "kmg_finalize": (i32, [vp, C.POINTER(KmgSummary)]),
     "kmg_export_counts": (i32, [vp, u64, i32, vp, vp, u64, C.POINTER(u64)]),
     "kmg_export_counts_device": (i32, [vp, u64, i32, vp, vp, u64, C.POINTER(u64)]),

@@ -283,6 +283,48 @@ class GpuKmerCounter:
     def synth_uniform_device(self, seed: int, first_base: int, n: int, d_out: int):
         _check(self._L.kmg_synth_uniform_device(self._ctx, seed, first_base, n, d_out), self._ctx)
 
+    # -- hash-sharded group of contexts, one per GPU (collective calls; see include/kmerust_gpu.h)
+    def shard_join(self, world: int, rank: int, group: str, expected_keys_total: int = 0):
+        _check(self._L.kmg_shard_join(self._ctx, world, rank, group.encode(), int(expected_keys_total)), self._ctx)
+
+    def shard_leave(self):
+        _check(self._L.kmg_shard_leave(self._ctx), self._ctx)
+
+    def shard_count_device(self, d_seq: int, n_bytes: int, d_qual: int = 0, d_offsets: int = 0, n_records: int = 1):
+        _check(self._L.kmg_shard_count_ascii_device(self._ctx, d_seq or None, d_qual or None, d_offsets or None, n_records, n_bytes), self._ctx)
+
+    def shard_count_batch(self, seq: np.ndarray, qual: Optional[np.ndarray], offsets: np.ndarray):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_rec = max(0, len(offsets) - 1)
+        assert seq.dtype == np.uint8 and seq.flags.c_contiguous
+        _check(self._L.kmg_shard_count_ascii(self._ctx, seq.ctypes.data if len(seq) else None,
+                                             qual.ctypes.data if qual is not None and len(qual) else None,
+                                             offsets.ctypes.data if n_rec else None, n_rec), self._ctx)
+
+    def shard_finalize(self) -> dict:
+        s = KmgSummary()
+        _check(self._L.kmg_shard_finalize(self._ctx, C.byref(s)), self._ctx)
+        return {f: getattr(s, f) for f, _ in KmgSummary._fields_}
+
+    def shard_histogram(self, min_count: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+        n = C.c_uint64(0)
+        _check(self._L.kmg_shard_histogram(self._ctx, min_count, None, None, 0, C.byref(n)), self._ctx)
+        vals = np.empty(n.value, dtype=np.uint64)
+        freqs = np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            _check(self._L.kmg_shard_histogram(self._ctx, min_count, vals.ctypes.data, freqs.ctypes.data, n.value, C.byref(n)), self._ctx)
+        return vals, freqs
+
+    def shard_save_kmix(self, path) -> int:
+        n = C.c_uint64(0)
+        _check(self._L.kmg_shard_save_kmix(self._ctx, os.fspath(path).encode(), C.byref(n)), self._ctx)
+        return n.value
+
+    def shard_stats(self) -> dict:
+        a, b, r, x = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(self._L.kmg_shard_stats(self._ctx, C.byref(a), C.byref(b), C.byref(r), C.byref(x)), self._ctx)
+        return {"sent_keys": a.value, "recv_keys": b.value, "rounds": r.value, "exact_rounds": x.value}
+
     def synth_reads_device(self, seed: int, profile: int, first_read: int, n_reads: int, d_seq: int, d_qual: int = 0):
         _check(self._L.kmg_synth_reads_device(self._ctx, seed, profile, first_read, n_reads, d_seq, d_qual or None), self._ctx)
 

@@ -4,6 +4,13 @@
 // exact fallback, re-split / multi-pass when the partition plan is outgrown), consolidation of the runs, result export.
 // The counting itself happens in the sm_100a kernels of kmg_kernels.cu / kmg_partition.cu.  There is no CPU
 // fallback: every entry point needs a CUDA device.
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -101,6 +108,15 @@ struct kmg_ctx {
   size_t scan_tmp_bytes = 0;
   uint64_t scan_tmp_items = 0, fine_cursor_items = 0;
   bool in_resplit = false;
+  struct ShardShm *shm = nullptr;     // sharded mode (kmg_shard_join): the group's shared segment
+  uint32_t sh_world = 1, sh_rank = 0;
+  uint64_t *sh_recv = nullptr;        // this rank's coarse receive buffer (peers write into it over NVLink)
+  uint64_t sh_recv_entries = 0;
+  uint64_t *sh_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // every rank's receive buffer as seen from here
+  bool sh_peer_ipc[8] = {false, false, false, false, false, false, false, false};
+  uint64_t sh_sent = 0, sh_recv_keys = 0, sh_rounds = 0, sh_exact_rounds = 0;
+  std::vector<uint64_t> sh_hist_vals, sh_hist_freqs;  // merged histogram of the last kmg_shard_histogram
+  double plan_scale = 1.0;  // kmg_count_ascii with a quality filter: (bases of the whole call) / (bases of its first chunk)
   int building_run = 0;  // > 0 while refine_to_run derives a run from the current plan: a nested consolidate must not re-split
   // count-of-counts of `result`, produced by phase B itself (consolidate)
   unsigned long long *d_hist = nullptr;      // HIST_DENSE_BINS bins + overflow counter
@@ -128,6 +144,8 @@ struct kmg_ctx {
 };
 
 namespace {
+
+void shard_release(kmg_ctx *c);  // defined with the shard group code below
 
 kmg_status fail(kmg_ctx *ctx, kmg_status s, const std::string &msg) {
   if (ctx) ctx->err = msg; else g_create_error = msg;
@@ -306,12 +324,21 @@ void timers_collect(kmg_ctx *c) {
 // =================================================================================================
 constexpr uint64_t TARGET_KEYS_PER_PART = 3600;  // <= 4096 with 8 sigma to spare: one upsert round per partition; load ~0.44
 
+// n_coarse / n_sub are set: allocate the partitioned pipeline's bookkeeping
+kmg_status init_partitioned(kmg_ctx *c) {
+  c->n_parts = c->n_coarse * c->n_sub;
+  CU(c, cudaMalloc(&c->d_part, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long)));
+  CU(c, cudaMalloc(&c->d_fine_cursor, (size_t)c->n_parts * sizeof(unsigned long long)));
+  c->fine_cursor_items = c->n_parts;
+  return KMG_OK;
+}
+
 // Decide how this context counts.  Called at the first feeding call, when the input size is known.
 kmg_status decide_mode(kmg_ctx *c, uint64_t first_call_windows) {
   if (c->mode != kmg_ctx::MODE_UNDECIDED) return KMG_OK;
   if (c->use_dense) { c->mode = kmg_ctx::MODE_DENSE; return KMG_OK; }
   const uint32_t f = c->cfg.flags;
-  const uint64_t hint = std::max<uint64_t>(c->cfg.expected_distinct, first_call_windows);
+  const uint64_t hint = c->cfg.expected_distinct ? c->cfg.expected_distinct : first_call_windows;  // an explicit hint is taken at its word
   const bool part = (f & KMG_FLAG_FORCE_PARTITIONED) || (!(f & KMG_FLAG_FORCE_HASH) && hint >= (1ull << 25));
   if (!part) {
     c->mode = kmg_ctx::MODE_TABLE;
@@ -336,11 +363,7 @@ kmg_status decide_mode(kmg_ctx *c, uint64_t first_call_windows) {
     c->n_coarse = (uint32_t)p1;
     c->n_sub = (uint32_t)std::min<uint64_t>((want + p1 - 1) / p1, 2048);
   }
-  c->n_parts = c->n_coarse * c->n_sub;
-  CU(c, cudaMalloc(&c->d_part, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long)));
-  CU(c, cudaMalloc(&c->d_fine_cursor, (size_t)c->n_parts * sizeof(unsigned long long)));
-  c->fine_cursor_items = c->n_parts;
-  return KMG_OK;
+  return init_partitioned(c);
 }
 
 kmg_status consolidate(kmg_ctx *c);
@@ -380,14 +403,15 @@ kmg_status alloc_or_consolidate(kmg_ctx *c, void **p, size_t bytes, const char *
 struct SplitPlan { uint32_t n_in, m, sub_old; Run *out; };
 kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, const std::vector<uint64_t> &coarse_off, bool owns = true,
                          bool sync = true, const std::vector<uint64_t> *coarse_len = nullptr, const SplitPlan *split = nullptr,
-                         bool in_keys = false) {  // in_keys: the input holds plain keys, not mixes (blocks adopted from another rank)
+                         bool in_keys = false,    // in_keys: the input holds plain keys, not mixes (blocks adopted from another rank)
+                         uint32_t in_group = 1) { // in_group g: coarse bin b arrives as the g input partitions b*g .. b*g+g-1 (sharded scatter: one per source)
   struct BuildGuard {
     kmg_ctx *c;
     explicit BuildGuard(kmg_ctx *c_) : c(c_) { ++c->building_run; }
     void release() { if (c) { --c->building_run; c = nullptr; } }
     ~BuildGuard() { release(); }
   } guard(c);
-  const uint32_t P1 = split ? split->n_in : c->n_coarse;
+  const uint32_t P1 = split ? split->n_in : c->n_coarse * in_group;  // input partitions
   const uint32_t n_sub = split ? split->m : c->n_sub;
   const uint32_t P = split ? split->n_in * split->m : c->n_parts;
   auto len_of = [&](uint32_t p) { return coarse_len ? (*coarse_len)[p] : coarse_off[p + 1] - coarse_off[p]; };
@@ -426,6 +450,7 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   rp.n_coarse = P1; rp.n_sub = n_sub; rp.n_tiles = (uint32_t)tiles;
   if (split) { rp.sub_total = split->sub_old * split->m; rp.sub_old = split->sub_old; }
   rp.in_keys = in_keys ? 1u : 0u;
+  rp.in_group = in_group;
   // Speculative layout first: hash partitions are Poisson-sized, so every fine partition gets mean + 7 sigma + 16 slots
   // and the count pass (a full read of the keys) is skipped.  Skewed input overflows a share: the kernel then raises a
   // flag, and this chunk -- and, sticky, the rest of the job -- takes the exact count + prefix + scatter route below.
@@ -819,7 +844,8 @@ kmg_status migrate_to_partitioned(kmg_ctx *c, uint64_t incoming) {
   c->table = HashTable{nullptr, 0};
   c->mode = kmg_ctx::MODE_UNDECIDED;
   c->cfg.flags |= KMG_FLAG_FORCE_PARTITIONED;
-  s = decide_mode(c, std::max<uint64_t>(c->cfg.expected_distinct, 16 * (n + incoming)));
+  c->cfg.expected_distinct = std::max<uint64_t>(c->cfg.expected_distinct, 16 * (n + incoming));  // the hint was too small (or absent)
+  s = decide_mode(c, c->cfg.expected_distinct);
   if (s == KMG_OK && n) s = keys_to_run(c, dk, dc, n);
   pool_free(c, dk); pool_free(c, dc);
   c->n_grows++;
@@ -828,10 +854,24 @@ kmg_status migrate_to_partitioned(kmg_ctx *c, uint64_t incoming) {
 
 kmg_status scan_packed(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
   const uint64_t n_tiles = n_words_total / TILE_WORDS;
-  kmg_status ms = decide_mode(c, n_words_total * 32);
+  uint64_t incoming = n_words_total * 32;  // upper bound of the keys this stream adds
+  bool incoming_exact = false;
+  if (!c->use_dense && c->cfg.has_min_quality && c->mode != kmg_ctx::MODE_PARTITIONED) {
+    // a quality filter can remove almost every window (config C3 keeps ~3 %): plan the table / the partitions from the
+    // countable windows (masks only, 0.25 B/base), not from the bases
+    unsigned long long h_ok = 0;
+    CU(c, launch_count_windows(c->d_valid, has_start ? c->d_start : nullptr, n_words_total, c->k, c->d_stats + 7, c->stream));
+    CU(c, cudaMemcpyAsync(&h_ok, c->d_stats + 7, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    incoming = h_ok; incoming_exact = true;
+  }
+  uint64_t plan_windows = incoming;
+  if (incoming_exact && c->plan_scale > 1.0) plan_windows = (uint64_t)((double)incoming * c->plan_scale * 1.25) + 1024;  // first chunk of a longer call
+  c->plan_scale = 1.0;
+  kmg_status ms = decide_mode(c, plan_windows);
   if (ms != KMG_OK) return ms;
-  if (c->mode == kmg_ctx::MODE_TABLE && !(c->cfg.flags & KMG_FLAG_FORCE_HASH) && c->distinct_ub + n_words_total * 32 > MIGRATE_KEYS) {
-    ms = migrate_to_partitioned(c, n_words_total * 32);
+  if (c->mode == kmg_ctx::MODE_TABLE && !(c->cfg.flags & KMG_FLAG_FORCE_HASH) && c->distinct_ub + incoming > MIGRATE_KEYS) {
+    ms = migrate_to_partitioned(c, incoming);
     if (ms != KMG_OK) return ms;
   }
   if (c->mode == kmg_ctx::MODE_PARTITIONED) return scan_to_run(c, n_words_total, has_start);
@@ -839,6 +879,7 @@ kmg_status scan_packed(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
   const size_t tmr = timer_begin(c);
   while (tile0 < n_tiles) {
     uint64_t want = (n_tiles - tile0) * TILE_WORDS * 32, granted = 0;
+    if (incoming_exact && tile0 == 0) want = std::max<uint64_t>(incoming, 1);  // the whole stream adds exactly this many keys
     kmg_status s = reserve_capacity(c, want, &granted);
     if (s != KMG_OK) return s;
     uint64_t tiles = granted >= want ? n_tiles - tile0 : granted / ((uint64_t)TILE_WORDS * 32);
@@ -981,6 +1022,7 @@ KMG_EXPORT void kmg_destroy(kmg_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   timers_collect(c);
+  if (c->shm || c->sh_recv) shard_release(c);
   for (auto &r : c->runs) free_run(c, r);
   if (c->has_result) free_run(c, c->result);
   pool_release_idle(c);
@@ -1089,6 +1131,7 @@ KMG_EXPORT kmg_status kmg_reset(kmg_ctx *c) {
 KMG_EXPORT kmg_status kmg_count_ascii_device(kmg_ctx *c, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_offsets,
                                              uint64_t n_records, uint64_t n_bytes) {
   if (!c) return KMG_ERR_INVALID_ARG;
+  if (c->shm) return fail(c, KMG_ERR_STATE, "context belongs to a shard group: feed it with kmg_shard_count_ascii(_device)");
   if (n_bytes && !d_seq) return fail(c, KMG_ERR_INVALID_ARG, "d_seq is NULL");
   if (((uintptr_t)d_seq & 15) || ((uintptr_t)d_qual & 15)) return fail(c, KMG_ERR_INVALID_ARG, "d_seq / d_qual must be 16-byte aligned");
   CU(c, cudaSetDevice(c->device));
@@ -1101,6 +1144,7 @@ KMG_EXPORT kmg_status kmg_count_ascii_device(kmg_ctx *c, const uint8_t *d_seq, c
 
 KMG_EXPORT kmg_status kmg_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets, uint64_t n_records) {
   if (!c) return KMG_ERR_INVALID_ARG;
+  if (c->shm) return fail(c, KMG_ERR_STATE, "context belongs to a shard group: feed it with kmg_shard_count_ascii(_device)");
   if (n_records == 0) return KMG_OK;
   if (!offsets || !seq) {
     if (offsets && offsets[n_records] == offsets[0]) { c->n_records += n_records; return KMG_OK; }
@@ -1112,7 +1156,10 @@ KMG_EXPORT kmg_status kmg_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint
   const uint64_t begin = offsets[0], end = offsets[n_records];
   const bool use_q = c->cfg.has_min_quality && qual != nullptr;
   const bool src_pinned = is_pinned_host(seq + begin) && (!use_q || is_pinned_host(qual + begin));
-  kmg_status s = decide_mode(c, end - begin);  // plan for the whole call, not for its first staging chunk
+  kmg_status s = KMG_OK;
+  if (use_q && !c->cfg.expected_distinct && c->mode == kmg_ctx::MODE_UNDECIDED && !c->use_dense)
+    c->plan_scale = (double)(end - begin) / (double)std::min<uint64_t>(end - begin, c->batch_bases);  // decided after the first chunk's ingest (scan_packed)
+  else s = decide_mode(c, end - begin);  // plan for the whole call, not for its first staging chunk
   if (s != KMG_OK) return s;
   s = ensure_staging(c, !src_pinned, use_q, end - begin);
   if (s != KMG_OK) return s;
@@ -1206,6 +1253,7 @@ KMG_EXPORT kmg_status kmg_acquire_batch(kmg_ctx *c, kmg_batch *b) {
 
 KMG_EXPORT kmg_status kmg_submit_batch(kmg_ctx *c, const kmg_batch *b) {
   if (!c || !b) return KMG_ERR_INVALID_ARG;
+  if (c->shm) return fail(c, KMG_ERR_STATE, "context belongs to a shard group: feed it with kmg_shard_count_ascii(_device)");
   if (b->slot > 1 || !c->packed_feed_ready || b->bases2bit != c->st[b->slot].hp_bases)
     return fail(c, KMG_ERR_STATE, "batch was not obtained from kmg_acquire_batch");
   if (b->n_bases > b->capacity_bases) return fail(c, KMG_ERR_INVALID_ARG, "n_bases exceeds the batch capacity");
@@ -1231,6 +1279,7 @@ KMG_EXPORT kmg_status kmg_submit_batch(kmg_ctx *c, const kmg_batch *b) {
 
 KMG_EXPORT kmg_status kmg_insert_keys_device(kmg_ctx *c, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n) {
   if (!c) return KMG_ERR_INVALID_ARG;
+  if (c->shm) return fail(c, KMG_ERR_STATE, "context belongs to a shard group: feed it with kmg_shard_count_ascii(_device)");
   if (n == 0) return KMG_OK;
   if (!d_keys) return fail(c, KMG_ERR_INVALID_ARG, "d_keys is NULL");
   CU(c, cudaSetDevice(c->device));
@@ -1267,6 +1316,7 @@ KMG_EXPORT kmg_status kmg_partition_plan(kmg_ctx *c, uint64_t expected_keys, uin
 
 KMG_EXPORT kmg_status kmg_adopt_coarse_device(kmg_ctx *c, const uint64_t *d_keys, const uint64_t *bin_counts, uint32_t n_bins, uint64_t n) {
   if (!c || !bin_counts) return KMG_ERR_INVALID_ARG;
+  if (c->shm) return fail(c, KMG_ERR_STATE, "context belongs to a shard group: feed it with kmg_shard_count_ascii(_device)");
   if (c->mode != kmg_ctx::MODE_PARTITIONED) return fail(c, KMG_ERR_STATE, "call kmg_partition_plan first");
   if (n_bins != c->n_coarse) return fail(c, KMG_ERR_INVALID_ARG, "n_bins must equal the context's coarse partition count");
   if (n >= (1ull << 32)) return fail(c, KMG_ERR_INVALID_ARG, "at most 2^32-1 keys per call");
@@ -1322,6 +1372,434 @@ KMG_EXPORT kmg_status kmg_extract_keys_device(kmg_ctx *c, const uint8_t *d_seq, 
   pool_free(c, d_pc);
   if (e != cudaSuccess) return cuda_fail(c, e, "partition scatter pass");
   c->n_records += n_records; c->n_bases += n_bytes;
+  return KMG_OK;
+}
+
+
+// =================================================================================================
+// Sharded (multi-GPU) counting: one context per GPU -- processes (torchrun, a Rust host with one process per device) or
+// threads of one process -- joined into a group on ONE box.  The count table shards by hash: global coarse bin
+// g = coarse_of_mix(mix, world * P1) belongs to rank g / P1.  The exchange is FUSED into the scatter kernel: A1's copy-out
+// writes every bin straight into its owner's coarse receive buffer through P2P-mapped pointers (NVLink stores), region
+// (local bin c, source s) of the owner's buffer; the owner then refines + counts what arrived (A2, B) like local input.
+// Only metadata crosses between the ranks on the host: a POSIX shared-memory segment carries the region sizes, flags,
+// summaries, histograms and a sense-reversing barrier.  No NCCL, no staging copies, no count pass on the fast path.
+// =================================================================================================
+constexpr uint32_t SHARD_MAX_WORLD = 8;
+constexpr uint32_t SHARD_MAX_BINS = 2048;        // world * P1 (the single-scan rows kernel's limit)
+constexpr uint32_t SHARD_HIST_MAX = 2 * 65536;   // (value, frequency) pairs a rank can post
+constexpr uint32_t SHARD_MAGIC = 0x4b4d4753u;
+constexpr double SHARD_TIMEOUT_S = 120.0;
+
+struct ShardRankSlot {
+  int32_t pid, device;
+  cudaIpcMemHandle_t handle;
+  uint64_t raw_ptr, recv_entries;
+  uint64_t round_bytes, round_flag;
+  uint64_t summary[8];
+  uint64_t hist_n;
+};
+struct ShardShm {
+  uint32_t ready, world;
+  uint32_t bar_count, bar_gen, abort, spec_disabled;
+  ShardRankSlot ranks[SHARD_MAX_WORLD];
+  uint64_t lens[SHARD_MAX_WORLD][SHARD_MAX_BINS];      // [source rank][global bin]: keys source s holds for bin g this round
+  uint64_t hist[SHARD_MAX_WORLD][2 * SHARD_HIST_MAX];  // a rank's (value, frequency) pairs
+};
+
+namespace {
+
+double now_s() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
+
+kmg_status shard_fail(kmg_ctx *c, kmg_status st, const std::string &msg) {
+  if (c->shm) __atomic_store_n(&c->shm->abort, 1u, __ATOMIC_RELEASE);  // peers waiting in a barrier give up instead of hanging
+  return fail(c, st, msg);
+}
+
+// sense-reversing barrier over the group's shared segment (processes or threads)
+kmg_status shard_barrier(kmg_ctx *c) {
+  ShardShm *S = c->shm;
+  const uint32_t gen = __atomic_load_n(&S->bar_gen, __ATOMIC_ACQUIRE);
+  if (__atomic_add_fetch(&S->bar_count, 1u, __ATOMIC_ACQ_REL) == S->world) {
+    __atomic_store_n(&S->bar_count, 0u, __ATOMIC_RELAXED);
+    __atomic_add_fetch(&S->bar_gen, 1u, __ATOMIC_RELEASE);
+    return KMG_OK;
+  }
+  const double t0 = now_s();
+  for (uint32_t spins = 0;; ++spins) {
+    if (__atomic_load_n(&S->bar_gen, __ATOMIC_ACQUIRE) != gen) return KMG_OK;
+    if (__atomic_load_n(&S->abort, __ATOMIC_ACQUIRE)) return fail(c, KMG_ERR_STATE, "a peer rank of the shard group failed");
+    if (spins > 2000) {
+      sched_yield();
+      if ((spins & 1023) == 0 && now_s() - t0 > SHARD_TIMEOUT_S) return shard_fail(c, KMG_ERR_STATE, "shard group barrier timed out (a peer did not make the matching call)");
+    }
+  }
+}
+#define SB(c) do { kmg_status _s = shard_barrier(c); if (_s != KMG_OK) return _s; } while (0)
+#define SCU(c, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cuda_fail(c, _e, #call); return shard_fail(c, _e == cudaErrorMemoryAllocation ? KMG_ERR_OOM : KMG_ERR_CUDA, c->err); } } while (0)
+
+void shard_release(kmg_ctx *c) {
+  for (uint32_t r = 0; r < SHARD_MAX_WORLD; ++r) {
+    if (c->sh_peer[r] && c->sh_peer_ipc[r]) cudaIpcCloseMemHandle(c->sh_peer[r]);
+    c->sh_peer[r] = nullptr; c->sh_peer_ipc[r] = false;
+  }
+  if (c->sh_recv) { cudaFree(c->sh_recv); c->sh_recv = nullptr; }
+  if (c->shm) { munmap(c->shm, sizeof(ShardShm)); c->shm = nullptr; }
+  c->sh_world = 1; c->sh_rank = 0;
+}
+
+// one round of the fused scatter + exchange over the context's packed stream (n_words_total may be 0: a rank that has run out
+// of input still takes part), then A2 over what this rank received
+kmg_status shard_scan_round(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
+  ShardShm *S = c->shm;
+  const uint32_t W = c->sh_world, me = c->sh_rank, P1 = c->n_coarse, G = W * P1;
+  unsigned long long *d_cnt = c->d_part, *d_start = c->d_part + MAX_PARTS, *d_cur = c->d_part + 2 * MAX_PARTS;
+  // 1. this rank's receive buffer is free again (the previous round's A2 has read it) and the round's size is known to all
+  SCU(c, cudaStreamSynchronize(c->stream));
+  S->ranks[me].round_bytes = n_words_total * 32;
+  S->ranks[me].round_flag = 0;
+  SB(c);
+  uint64_t max_w = 0;
+  for (uint32_t r = 0; r < W; ++r) max_w = std::max<uint64_t>(max_w, S->ranks[r].round_bytes);
+  if (max_w == 0) { SB(c); return KMG_OK; }
+  if (max_w >= (1ull << 32)) return shard_fail(c, KMG_ERR_INVALID_ARG, "a sharded round handles < 2^32 bases per rank (lower batch_bases)");
+  ScanInput in;
+  in.bases = c->d_bases; in.valid = c->d_valid; in.start = has_start ? c->d_start : nullptr;
+  in.n_tiles = n_words_total / TILE_WORDS; in.k = c->k;
+  in.n_peers = W; in.peer_magic = (uint32_t)(((1ull << 32) + P1 - 1) / P1);
+  for (uint32_t r = 0; r < W; ++r) in.peer_out[r] = c->sh_peer[r];
+  std::vector<uint64_t> h_start(G), h_len(G);
+  const size_t tmr = timer_begin(c, 0);
+  c->sh_rounds++;
+  bool done = false;
+  // 2. speculative layout: region (local bin cl, source s) of every owner's buffer holds cap entries, no sizes needed up front
+  const double mu = (double)max_w / G;
+  const uint64_t cap = ((uint64_t)(mu + 7.0 * std::sqrt(mu) + 64.0) + 15) & ~15ull;
+  if (!__atomic_load_n(&S->spec_disabled, __ATOMIC_ACQUIRE) && cap * G <= c->sh_recv_entries && scan_scatter_supports_cap(G)) {
+    for (uint32_t r = 0; r < W; ++r)
+      for (uint32_t cl = 0; cl < P1; ++cl) h_start[r * P1 + cl] = ((uint64_t)cl * W + me) * cap;
+    ScanInput sin = in;
+    sin.part_cap = cap;
+    sin.overflow_flag = reinterpret_cast<uint32_t *>(c->d_stats + 5);
+    uint32_t h_flag = 0;
+    SCU(c, cudaMemsetAsync(c->d_part, 0, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
+    SCU(c, cudaMemsetAsync(sin.overflow_flag, 0, 4, c->stream));
+    SCU(c, cudaMemcpyAsync(d_start, h_start.data(), G * 8, cudaMemcpyHostToDevice, c->stream));
+    if (in.n_tiles) SCU(c, launch_scan_partition(sin, G, true, d_cnt, d_start, d_cur, c->sh_recv, c->d_counters, c->stream, /*mixed=*/true));
+    SCU(c, cudaMemcpyAsync(h_len.data(), d_cur, G * 8, cudaMemcpyDeviceToHost, c->stream));
+    SCU(c, cudaMemcpyAsync(&h_flag, sin.overflow_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    SCU(c, cudaStreamSynchronize(c->stream));  // the P2P stores of this rank have landed
+    memcpy(S->lens[me], h_len.data(), G * 8);
+    S->ranks[me].round_flag = h_flag;
+    SB(c);
+    bool any = false;
+    for (uint32_t r = 0; r < W; ++r) any |= S->ranks[r].round_flag != 0;
+    if (!any) {
+      std::vector<uint64_t> off((size_t)P1 * W + 1), lens((size_t)P1 * W);
+      uint64_t n_in = 0;
+      for (uint32_t cl = 0; cl < P1; ++cl)
+        for (uint32_t s2 = 0; s2 < W; ++s2) {
+          const size_t j = (size_t)cl * W + s2;
+          off[j] = j * cap; lens[j] = S->lens[s2][me * P1 + cl]; n_in += lens[j];
+        }
+      off[(size_t)P1 * W] = (uint64_t)P1 * W * cap;
+      for (uint32_t g = 0; g < G; ++g) if (g / P1 != me) c->sh_sent += h_len[g];
+      c->sh_recv_keys += n_in;
+      SB(c);  // everybody has read the size matrix: the next round may overwrite it
+      if (n_in) {
+        kmg_status st = refine_to_run(c, c->sh_recv, nullptr, off, /*owns=*/false, /*sync=*/true, &lens, nullptr, false, W);
+        if (st != KMG_OK) return shard_fail(c, st, c->err);
+      }
+      done = true;
+    } else {
+      __atomic_store_n(&S->spec_disabled, 1u, __ATOMIC_RELEASE);  // sticky for the whole group: skewed input
+      SB(c);
+    }
+  }
+  // 3. exact route: count pass, sizes through the shared segment, exact region offsets, scatter
+  if (!done) {
+    c->sh_exact_rounds++;
+    SCU(c, cudaMemsetAsync(c->d_part, 0, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
+    if (in.n_tiles) {
+      ScanInput cin = in; cin.n_peers = 0;
+      SCU(c, launch_scan_partition(cin, G, false, d_cnt, d_start, d_cur, nullptr, c->d_counters, c->stream));
+    }
+    SCU(c, cudaMemcpyAsync(h_len.data(), d_cnt, G * 8, cudaMemcpyDeviceToHost, c->stream));
+    SCU(c, cudaStreamSynchronize(c->stream));
+    memcpy(S->lens[me], h_len.data(), G * 8);
+    SB(c);
+    std::vector<uint64_t> off((size_t)P1 * W + 1);
+    uint64_t worst = 0;
+    for (uint32_t r = 0; r < W; ++r) {  // every rank derives every owner's layout from the same matrix
+      uint64_t run = 0;
+      for (uint32_t cl = 0; cl < P1; ++cl)
+        for (uint32_t s2 = 0; s2 < W; ++s2) {
+          if (s2 == me) h_start[r * P1 + cl] = run;
+          if (r == me) off[(size_t)cl * W + s2] = run;
+          run += S->lens[s2][r * P1 + cl];
+        }
+      if (r == me) off[(size_t)P1 * W] = run;
+      worst = std::max(worst, run);
+    }
+    const uint64_t n_in = off[(size_t)P1 * W];
+    for (uint32_t g = 0; g < G; ++g) if (g / P1 != me) c->sh_sent += h_len[g];
+    c->sh_recv_keys += n_in;
+    SB(c);  // the size matrix has been read by everyone
+    if (worst > c->sh_recv_entries)  // the same verdict on every rank
+      return fail(c, KMG_ERR_CAPACITY, "a shard would receive " + std::to_string(worst) + " keys in one round but its receive buffer holds " +
+                                           std::to_string(c->sh_recv_entries) + " (lower batch_bases or raise it at kmg_create for a larger buffer)");
+    SCU(c, cudaMemsetAsync(d_cur, 0, (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
+    SCU(c, cudaMemcpyAsync(d_start, h_start.data(), G * 8, cudaMemcpyHostToDevice, c->stream));
+    if (in.n_tiles) SCU(c, launch_scan_partition(in, G, true, d_cnt, d_start, d_cur, c->sh_recv, c->d_counters, c->stream, /*mixed=*/true));
+    SCU(c, cudaStreamSynchronize(c->stream));
+    SB(c);  // all scatters have landed
+    if (n_in) {
+      kmg_status st = refine_to_run(c, c->sh_recv, nullptr, off, /*owns=*/false, /*sync=*/true, nullptr, nullptr, false, W);
+      if (st != KMG_OK) return shard_fail(c, st, c->err);
+    }
+  }
+  timer_end(c, tmr);
+  return KMG_OK;
+}
+
+}  // namespace
+
+KMG_EXPORT kmg_status kmg_shard_join(kmg_ctx *c, uint32_t world, uint32_t rank, const char *group, uint64_t expected_keys_total) {
+  if (!c || !group || !*group) return KMG_ERR_INVALID_ARG;
+  if (world < 1 || world > SHARD_MAX_WORLD || rank >= world) return fail(c, KMG_ERR_INVALID_ARG, "world must be 1..=8 and rank < world");
+  if (c->shm || c->sh_world > 1) return fail(c, KMG_ERR_STATE, "context already belongs to a shard group");
+  if (c->mode != kmg_ctx::MODE_UNDECIDED) return fail(c, KMG_ERR_STATE, "kmg_shard_join must come before the first feeding call");
+  if (world == 1) return KMG_OK;  // a group of one is the plain single-GPU path
+  if (c->cfg.flags & (KMG_FLAG_FORCE_HASH | KMG_FLAG_FORCE_DIRECT)) return fail(c, KMG_ERR_INVALID_ARG, "the sharded path is the partitioned pipeline: FORCE_HASH / FORCE_DIRECT do not apply");
+  CU(c, cudaSetDevice(c->device));
+  // ---- partition plan: every rank derives the same one from the same arguments
+  if (c->use_dense) { cudaFree(c->dense); c->dense = nullptr; c->dense_n = 0; c->use_dense = false; }
+  c->cfg.flags |= KMG_FLAG_FORCE_PARTITIONED;
+  c->mode = kmg_ctx::MODE_PARTITIONED;
+  {
+    const uint64_t per_rank = std::max<uint64_t>(expected_keys_total ? expected_keys_total : c->cfg.expected_distinct, 1) / world + 1;
+    const uint64_t want = std::max<uint64_t>(4, (per_rank + TARGET_KEYS_PER_PART - 1) / TARGET_KEYS_PER_PART);
+    uint64_t p1 = 1;
+    while (p1 * p1 < want) ++p1;
+    p1 = std::min<uint64_t>(p1, 1024 / world);  // world * P1 <= 1024 global bins: >= 8-key (64-byte) runs per bin and sub-tile in the NVLink copy-out
+    c->n_coarse = (uint32_t)std::max<uint64_t>(p1, 1);
+    c->n_sub = (uint32_t)std::min<uint64_t>((want + c->n_coarse - 1) / c->n_coarse, 2048);
+    kmg_status st = init_partitioned(c);
+    if (st != KMG_OK) return st;
+  }
+  // ---- receive buffer: one round moves at most batch_bases windows per source; 25 % headroom for uneven owners
+  const uint64_t G = (uint64_t)world * c->n_coarse;
+  const double mu = (double)c->batch_bases / (double)G;
+  c->sh_recv_entries = std::min<uint64_t>((uint64_t)((double)c->batch_bases * 1.25) + G * (uint64_t)(7.0 * std::sqrt(mu) + 80.0), (1ull << 32) - 1);
+  CU(c, cudaMalloc(&c->sh_recv, c->sh_recv_entries * 8));
+  // ---- shared segment: rank 0 creates, the others attach
+  const std::string name = std::string("/kmg-") + group;
+  int fd = -1;
+  const double t0 = now_s();
+  if (rank == 0) {
+    shm_unlink(name.c_str());
+    fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)sizeof(ShardShm)) != 0) { if (fd >= 0) close(fd); shard_release(c); return fail(c, KMG_ERR_IO, "cannot create the shard group's shared segment " + name); }
+  } else {
+    while ((fd = shm_open(name.c_str(), O_RDWR, 0600)) < 0) {
+      if (now_s() - t0 > SHARD_TIMEOUT_S) { shard_release(c); return fail(c, KMG_ERR_STATE, "shard group " + name + " did not appear (rank 0 missing?)"); }
+      usleep(1000);
+    }
+    struct stat sb;
+    while (fstat(fd, &sb) == 0 && (size_t)sb.st_size < sizeof(ShardShm)) {
+      if (now_s() - t0 > SHARD_TIMEOUT_S) { close(fd); shard_release(c); return fail(c, KMG_ERR_STATE, "shard group segment was never sized"); }
+      usleep(1000);
+    }
+  }
+  void *mem = mmap(nullptr, sizeof(ShardShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (mem == MAP_FAILED) { shard_release(c); return fail(c, KMG_ERR_IO, "cannot map the shard group's shared segment"); }
+  c->shm = static_cast<ShardShm *>(mem);
+  c->sh_world = world; c->sh_rank = rank;
+  ShardShm *S = c->shm;
+  if (rank == 0) {  // ftruncate zero-filled the segment
+    S->world = world;
+    __atomic_store_n(&S->ready, SHARD_MAGIC, __ATOMIC_RELEASE);
+  } else {
+    while (__atomic_load_n(&S->ready, __ATOMIC_ACQUIRE) != SHARD_MAGIC) {
+      if (now_s() - t0 > SHARD_TIMEOUT_S) { shard_release(c); return fail(c, KMG_ERR_STATE, "shard group segment was never initialised"); }
+      usleep(200);
+    }
+    if (S->world != world) { shard_release(c); return fail(c, KMG_ERR_INVALID_ARG, "ranks disagree on the world size"); }
+  }
+  ShardRankSlot &mine = S->ranks[rank];
+  mine.pid = (int32_t)getpid(); mine.device = c->device;
+  mine.raw_ptr = (uint64_t)(uintptr_t)c->sh_recv; mine.recv_entries = c->sh_recv_entries;
+  mine.summary[0] = c->n_coarse; mine.summary[1] = c->n_sub; mine.summary[2] = (uint64_t)c->k;
+  cudaError_t e = cudaIpcGetMemHandle(&mine.handle, c->sh_recv);
+  if (e != cudaSuccess) { cudaGetLastError(); memset(&mine.handle, 0, sizeof mine.handle); }  // same-process groups do not need it
+  kmg_status st = shard_barrier(c);
+  if (st != KMG_OK) { shard_release(c); return st; }
+  std::string why;
+  for (uint32_t r = 0; r < world && why.empty(); ++r) {
+    const ShardRankSlot &o = S->ranks[r];
+    if (o.summary[0] != c->n_coarse || o.summary[1] != c->n_sub || o.summary[2] != (uint64_t)c->k || o.recv_entries != c->sh_recv_entries) {
+      why = "ranks disagree on k / the partition plan / batch_bases (pass identical arguments on every rank)";
+    } else if (r == rank) {
+      c->sh_peer[r] = c->sh_recv;
+    } else if (o.pid == mine.pid) {  // threads of one process: plain pointers (+ peer access between different devices)
+      if (o.device != c->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, c->device, o.device);
+        if (!can) { why = "no peer access between devices " + std::to_string(c->device) + " and " + std::to_string(o.device); break; }
+        cudaError_t pe = cudaDeviceEnablePeerAccess(o.device, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) why = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe);
+        cudaGetLastError();
+      }
+      c->sh_peer[r] = reinterpret_cast<uint64_t *>((uintptr_t)o.raw_ptr);
+    } else {
+      void *pp = nullptr;
+      cudaError_t pe = cudaIpcOpenMemHandle(&pp, o.handle, cudaIpcMemLazyEnablePeerAccess);
+      if (pe != cudaSuccess) { cudaGetLastError(); why = std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(pe); }
+      else { c->sh_peer[r] = static_cast<uint64_t *>(pp); c->sh_peer_ipc[r] = true; }
+    }
+  }
+  if (!why.empty()) __atomic_store_n(&S->abort, 1u, __ATOMIC_RELEASE);
+  st = shard_barrier(c);  // every rank has opened its peers (or the group is aborted)
+  if (rank == 0) shm_unlink(name.c_str());  // the mapping lives on; no name is left behind
+  if (!why.empty() || st != KMG_OK) { shard_release(c); c->mode = kmg_ctx::MODE_PARTITIONED; return why.empty() ? st : fail(c, KMG_ERR_CUDA, why); }
+  return KMG_OK;
+}
+
+KMG_EXPORT kmg_status kmg_shard_leave(kmg_ctx *c) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  if (!c->shm) return KMG_OK;
+  CU(c, cudaSetDevice(c->device));
+  cudaStreamSynchronize(c->stream);
+  shard_barrier(c);  // nobody may still be writing into a buffer that is about to be unmapped / freed
+  shard_release(c);
+  return KMG_OK;
+}
+
+// Collective: every rank of the group calls it the same number of times (a rank without input passes n_bytes = 0).
+// Input: THIS rank's slice of the records (device pointers), layout as kmg_count_ascii_device.
+KMG_EXPORT kmg_status kmg_shard_count_ascii_device(kmg_ctx *c, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_offsets,
+                                                   uint64_t n_records, uint64_t n_bytes) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  if (!c->shm) return kmg_count_ascii_device(c, d_seq, d_qual, d_offsets, n_records, n_bytes);
+  if (n_bytes && !d_seq) return shard_fail(c, KMG_ERR_INVALID_ARG, "d_seq is NULL");
+  if (((uintptr_t)d_seq & 15) || ((uintptr_t)d_qual & 15)) return shard_fail(c, KMG_ERR_INVALID_ARG, "d_seq / d_qual must be 16-byte aligned");
+  CU(c, cudaSetDevice(c->device));
+  // rounds of at most batch_bases bases (k-1 overlap, records may span rounds); the ranks agree on the number of rounds
+  // (round starts stay 16-byte aligned for the ingest kernel's vector loads: step is rounded down, a round covers step + k-1 bases)
+  const uint64_t K1 = (uint64_t)c->k - 1, B = c->batch_bases, step = (B - K1) & ~15ull;
+  if (step == 0) return shard_fail(c, KMG_ERR_INVALID_ARG, "batch_bases is too small for sharded rounds");
+  uint64_t my_rounds = 0;
+  for (uint64_t pos = 0; pos < n_bytes; pos += step) { if (pos && n_bytes - pos <= K1) break; ++my_rounds; }
+  ShardShm *S = c->shm;
+  S->ranks[c->sh_rank].summary[7] = my_rounds;
+  SB(c);
+  uint64_t rounds = 0;
+  for (uint32_t r = 0; r < c->sh_world; ++r) rounds = std::max<uint64_t>(rounds, S->ranks[r].summary[7]);
+  SB(c);
+  const bool use_q = c->cfg.has_min_quality && d_qual != nullptr;
+  const uint32_t thr = std::min<uint32_t>(255u, (uint32_t)c->cfg.min_quality + 33u);
+  for (uint64_t i = 0; i < rounds; ++i) {
+    const uint64_t pos = i * step;
+    uint64_t len = 0;
+    if (i < my_rounds) len = std::min<uint64_t>(step + K1, n_bytes - pos);
+    uint64_t n_words_total = 0;
+    bool has_start = false;
+    if (len) {
+      n_words_total = round_up((len + 31) / 32, TILE_WORDS);
+      kmg_status st = ensure_packed(c, n_words_total);
+      if (st != KMG_OK) return shard_fail(c, st, c->err);
+      SCU(c, launch_ingest(d_seq + pos, use_q ? d_qual + pos : nullptr, len, thr, n_words_total, c->d_bases, c->d_valid, c->stream));
+      has_start = d_offsets != nullptr && n_records > 1;
+      if (has_start) SCU(c, launch_start_bits(d_offsets, n_records, pos, len, n_words_total, c->d_start, c->stream));
+    }
+    kmg_status st = shard_scan_round(c, n_words_total, has_start);
+    if (st != KMG_OK) return st;
+  }
+  c->n_records += n_records; c->n_bases += n_bytes;
+  return KMG_OK;
+}
+
+// The same with HOST pointers (this rank's slice): staged through the context's pinned ring like kmg_count_ascii.
+KMG_EXPORT kmg_status kmg_shard_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets, uint64_t n_records) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  if (!c->shm) return kmg_count_ascii(c, seq, qual, offsets, n_records);
+  if (n_records && (!offsets || !seq)) return shard_fail(c, KMG_ERR_INVALID_ARG, "seq / offsets must not be NULL");
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t begin = n_records ? offsets[0] : 0, end = n_records ? offsets[n_records] : 0;
+  const bool use_q = c->cfg.has_min_quality && qual != nullptr;
+  const bool src_pinned = end > begin && is_pinned_host(seq + begin) && (!use_q || is_pinned_host(qual + begin));
+  kmg_status s = ensure_staging(c, !src_pinned, use_q, std::max<uint64_t>(end - begin, 1));
+  if (s != KMG_OK) return shard_fail(c, s, c->err);
+  const uint64_t K1 = (uint64_t)c->k - 1, B = c->batch_bases, step = B - K1;
+  struct Chunk { uint64_t pos, len, r_lo, nrec; };
+  std::vector<Chunk> chunks;
+  {
+    uint64_t r_lo = 0;
+    for (uint64_t pos = begin; pos < end; pos += step) {
+      const uint64_t len = std::min<uint64_t>(B, end - pos);
+      if (pos != begin && len <= K1) break;
+      while (r_lo < n_records && offsets[r_lo] <= pos) ++r_lo;
+      uint64_t r_hi = r_lo;
+      while (r_hi < n_records && offsets[r_hi] < pos + len) ++r_hi;
+      chunks.push_back(Chunk{pos, len, r_lo, r_hi - r_lo});
+    }
+  }
+  ShardShm *S = c->shm;
+  S->ranks[c->sh_rank].summary[7] = chunks.size();
+  SB(c);
+  uint64_t rounds = 0;
+  for (uint32_t r = 0; r < c->sh_world; ++r) rounds = std::max<uint64_t>(rounds, S->ranks[r].summary[7]);
+  SB(c);
+  auto stage_chunk = [&](const Chunk &ch, Staging &st) -> kmg_status {
+    if (st.h2d_pending) { CU(c, cudaEventSynchronize(st.h2d_done)); st.h2d_pending = false; }
+    if (st.compute_pending) { CU(c, cudaStreamWaitEvent(c->copy_stream, st.compute_done, 0)); }
+    kmg_status es = ensure_offsets(c, st, ch.nrec);
+    if (es != KMG_OK) return es;
+    const uint8_t *src_seq = seq + ch.pos, *src_qual = use_q ? qual + ch.pos : nullptr;
+    if (!src_pinned) {
+      memcpy(st.h_seq, src_seq, ch.len); src_seq = st.h_seq;
+      if (use_q) { memcpy(st.h_qual, src_qual, ch.len); src_qual = st.h_qual; }
+    }
+    CU(c, cudaMemcpyAsync(st.d_seq, src_seq, ch.len, cudaMemcpyHostToDevice, c->copy_stream));
+    if (use_q) CU(c, cudaMemcpyAsync(st.d_qual, src_qual, ch.len, cudaMemcpyHostToDevice, c->copy_stream));
+    if (ch.nrec) {
+      memcpy(st.h_off, offsets + ch.r_lo, ch.nrec * 8);
+      CU(c, cudaMemcpyAsync(st.d_off, st.h_off, ch.nrec * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    c->h2d_bytes += ch.len * (use_q ? 2 : 1) + ch.nrec * 8;
+    CU(c, cudaEventRecord(st.h2d_done, c->copy_stream));
+    st.h2d_pending = true;
+    return KMG_OK;
+  };
+  const uint32_t thr = std::min<uint32_t>(255u, (uint32_t)c->cfg.min_quality + 33u);
+  const uint32_t slot0 = c->next_ascii;
+  size_t staged = 0;
+  for (uint64_t i = 0; i < rounds; ++i) {
+    uint64_t n_words_total = 0;
+    bool has_start = false;
+    if (i < chunks.size()) {
+      for (; staged < chunks.size() && staged < i + N_STAGE; ++staged)
+        if ((s = stage_chunk(chunks[staged], c->st[(slot0 + staged) % N_STAGE])) != KMG_OK) return shard_fail(c, s, c->err);
+      Staging &st = c->st[(slot0 + i) % N_STAGE];
+      const Chunk &ch = chunks[i];
+      SCU(c, cudaStreamWaitEvent(c->stream, st.h2d_done, 0));
+      n_words_total = round_up((ch.len + 31) / 32, TILE_WORDS);
+      if ((s = ensure_packed(c, n_words_total)) != KMG_OK) return shard_fail(c, s, c->err);
+      SCU(c, launch_ingest(st.d_seq, use_q ? st.d_qual : nullptr, ch.len, thr, n_words_total, c->d_bases, c->d_valid, c->stream));
+      has_start = ch.nrec > 0;
+      if (has_start) SCU(c, launch_start_bits(st.d_off, ch.nrec, ch.pos, ch.len, n_words_total, c->d_start, c->stream));
+      SCU(c, cudaEventRecord(st.compute_done, c->stream));  // the staging slot is free once ingest has packed it
+      st.compute_pending = true;
+    }
+    s = shard_scan_round(c, n_words_total, has_start);
+    if (s != KMG_OK) return s;
+  }
+  c->next_ascii = (slot0 + (uint32_t)chunks.size()) % N_STAGE;
+  c->n_records += n_records; c->n_bases += end - begin;
+  if (src_pinned)
+    for (auto &st : c->st)
+      if (st.h2d_pending) { CU(c, cudaEventSynchronize(st.h2d_done)); st.h2d_pending = false; }
   return KMG_OK;
 }
 
@@ -1671,6 +2149,125 @@ KMG_EXPORT kmg_status kmg_kmix_finish(const char *path, uint32_t k, const uint64
   ok = ok && fseeko(f, (off_t)(14 + 16 * n), SEEK_SET) == 0 && fwrite(tail, 1, 4, f) == 4;
   ok = (fclose(f) == 0) && ok;
   return ok ? KMG_OK : KMG_ERR_IO;
+}
+
+
+// ---- results of a shard group (collective calls: every rank makes the same sequence of them) ---------------------------
+// Global summary: sums over the (disjoint) shards, maximum of max_count; the timing fields stay this rank's own.
+KMG_EXPORT kmg_status kmg_shard_finalize(kmg_ctx *c, kmg_summary *out) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  kmg_summary loc;
+  kmg_status s = kmg_finalize(c, &loc);
+  if (!c->shm) { if (out) *out = loc; return s; }
+  if (s != KMG_OK) return shard_fail(c, s, c->err);
+  ShardShm *S = c->shm;
+  uint64_t *m = S->ranks[c->sh_rank].summary;
+  m[0] = loc.n_windows; m[1] = loc.n_distinct; m[2] = loc.n_records; m[3] = loc.n_bases; m[4] = loc.max_count;
+  SB(c);
+  if (out) {
+    *out = loc;
+    out->n_windows = out->n_distinct = out->n_records = out->n_bases = out->max_count = 0;
+    for (uint32_t r = 0; r < c->sh_world; ++r) {
+      const uint64_t *o = S->ranks[r].summary;
+      out->n_windows += o[0]; out->n_distinct += o[1]; out->n_records += o[2]; out->n_bases += o[3];
+      out->max_count = std::max<uint64_t>(out->max_count, o[4]);
+    }
+  }
+  SB(c);
+  return KMG_OK;
+}
+
+// Count-of-counts over all shards: the element-wise sum of the shard histograms (a k-mer lives in exactly one shard).
+// Replaces compute_histogram_packed (src/histogram.rs:110-116) for the sharded table.  Two-call protocol like kmg_histogram;
+// the size query does the merge (collective), the call with arrays returns that merged result.
+KMG_EXPORT kmg_status kmg_shard_histogram(kmg_ctx *c, uint64_t min_count, uint64_t *count_vals, uint64_t *freqs, uint64_t cap, uint64_t *n_out) {
+  if (!c || !n_out) return KMG_ERR_INVALID_ARG;
+  if (!c->shm) return kmg_histogram(c, min_count, count_vals, freqs, cap, n_out);
+  if (!count_vals || !freqs) {
+    uint64_t n = 0;
+    kmg_status s = kmg_histogram(c, min_count, nullptr, nullptr, 0, &n);
+    if (s != KMG_OK) return shard_fail(c, s, c->err);
+    if (n > SHARD_HIST_MAX) return shard_fail(c, KMG_ERR_CAPACITY, "shard histogram has too many distinct count values");
+    ShardShm *S = c->shm;
+    uint64_t *mine = S->hist[c->sh_rank];
+    if (n && (s = kmg_histogram(c, min_count, mine, mine + SHARD_HIST_MAX, n, &n)) != KMG_OK) return shard_fail(c, s, c->err);
+    S->ranks[c->sh_rank].hist_n = n;
+    SB(c);
+    std::vector<std::pair<uint64_t, uint64_t>> all;
+    for (uint32_t r = 0; r < c->sh_world; ++r)
+      for (uint64_t i = 0; i < S->ranks[r].hist_n; ++i) all.emplace_back(S->hist[r][i], S->hist[r][SHARD_HIST_MAX + i]);
+    SB(c);
+    std::sort(all.begin(), all.end());
+    c->sh_hist_vals.clear(); c->sh_hist_freqs.clear();
+    for (size_t i = 0; i < all.size();) {
+      uint64_t f = 0;
+      size_t j = i;
+      for (; j < all.size() && all[j].first == all[i].first; ++j) f += all[j].second;
+      c->sh_hist_vals.push_back(all[i].first); c->sh_hist_freqs.push_back(f);
+      i = j;
+    }
+    *n_out = c->sh_hist_vals.size();
+    return KMG_OK;
+  }
+  const uint64_t n = c->sh_hist_vals.size();
+  *n_out = n;
+  if (cap < n) return fail(c, KMG_ERR_CAPACITY, "histogram arrays hold " + std::to_string(cap) + " bins, need " + std::to_string(n));
+  if (n) { memcpy(count_vals, c->sh_hist_vals.data(), n * 8); memcpy(freqs, c->sh_hist_freqs.data(), n * 8); }
+  return KMG_OK;
+}
+
+// ONE .kmix index from all shards of the group (src/index.rs:222-279; records in shard order, each shard ascending): rank 0
+// creates the file, every rank writes its records into its own byte range, rank 0 writes the header (n = sum) and the CRC of
+// the whole file combined from the shards' CRCs.  *n_records_out: records of the whole index.
+KMG_EXPORT kmg_status kmg_shard_save_kmix(kmg_ctx *c, const char *path, uint64_t *n_records_out) {
+  if (!c || !path) return KMG_ERR_INVALID_ARG;
+  if (!c->shm) {
+    kmg_status s = kmg_save_kmix(c, path);
+    if (s == KMG_OK && n_records_out) { uint64_t n = 0; s = count_filtered(c, 0, &n); *n_records_out = n; }
+    return s;
+  }
+  if (has_gz_suffix(path)) return shard_fail(c, KMG_ERR_INVALID_ARG, "kmg_shard_save_kmix writes uncompressed .kmix files");
+  CU(c, cudaSetDevice(c->device));
+  ShardShm *S = c->shm;
+  uint64_t n = 0;
+  kmg_status s = count_filtered(c, 0, &n);
+  if (s != KMG_OK) return shard_fail(c, s, c->err);
+  uint64_t *m = S->ranks[c->sh_rank].summary;
+  m[5] = n;
+  if (c->sh_rank == 0 && kmg_kmix_begin(path) != KMG_OK) return shard_fail(c, KMG_ERR_IO, std::string("cannot create ") + path);
+  SB(c);
+  uint64_t before = 0;
+  for (uint32_t r = 0; r < c->sh_rank; ++r) before += S->ranks[r].summary[5];
+  uint64_t n2 = 0;
+  uint32_t crc = 0;
+  s = kmg_save_kmix_shard(c, path, before, &n2, &crc);
+  if (s != KMG_OK) return shard_fail(c, s, c->err);
+  if (n2 != n) return shard_fail(c, KMG_ERR_STATE, "shard index writer wrote an unexpected number of records");
+  m[6] = crc;
+  SB(c);
+  uint64_t total = 0;
+  for (uint32_t r = 0; r < c->sh_world; ++r) total += S->ranks[r].summary[5];
+  kmg_status fs = KMG_OK;
+  if (c->sh_rank == 0) {
+    uint64_t recs[SHARD_MAX_WORLD];
+    uint32_t crcs[SHARD_MAX_WORLD];
+    for (uint32_t r = 0; r < c->sh_world; ++r) { recs[r] = S->ranks[r].summary[5]; crcs[r] = (uint32_t)S->ranks[r].summary[6]; }
+    fs = kmg_kmix_finish(path, (uint32_t)c->k, recs, crcs, c->sh_world);
+    if (fs != KMG_OK) return shard_fail(c, fs, std::string("cannot finish ") + path);
+  }
+  SB(c);
+  if (n_records_out) *n_records_out = total;
+  return KMG_OK;
+}
+
+// Diagnostics of the exchange: keys this rank wrote into other ranks' buffers, keys it received, rounds, exact-route rounds.
+KMG_EXPORT kmg_status kmg_shard_stats(const kmg_ctx *c, uint64_t *sent_keys, uint64_t *recv_keys, uint64_t *rounds, uint64_t *exact_rounds) {
+  if (!c) return KMG_ERR_INVALID_ARG;
+  if (sent_keys) *sent_keys = c->sh_sent;
+  if (recv_keys) *recv_keys = c->sh_recv_keys;
+  if (rounds) *rounds = c->sh_rounds;
+  if (exact_rounds) *exact_rounds = c->sh_exact_rounds;
+  return KMG_OK;
 }
 
 KMG_EXPORT kmg_status kmg_progress(const kmg_ctx *c, uint64_t *records, uint64_t *bases) {

@@ -368,6 +368,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_count_kernel(ScanInput in, 
   }
 }
 
+// number of countable windows of a packed stream (masks only): lets the host plan the table / partition count for inputs
+// whose quality filter removes most windows (config C3 keeps ~3 % of them) before any key is produced
+__global__ void __launch_bounds__(256) count_windows_kernel(const uint32_t *__restrict__ valid, const uint32_t *__restrict__ start,
+                                                            uint64_t n_words, int k, unsigned long long *out) {
+  uint64_t n = 0;
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t vprev = valid[LEAD_MASK_WORDS + w - 1], vcur = valid[LEAD_MASK_WORDS + w];
+    uint32_t sprev = 0, scur = 0;
+    if (start) { sprev = start[LEAD_MASK_WORDS + w - 1]; scur = start[LEAD_MASK_WORDS + w]; }
+    n += __popc(window_ok_mask(vprev, vcur, sprev, scur, k, start != nullptr));
+  }
+  n = warp_sum(n);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, (unsigned long long)n);
+}
+
 // ---- K4: owner / partition bucketing ------------------------------------------------------------------
 struct PartCountEmit {
   uint32_t *hist;
@@ -622,6 +637,11 @@ __device__ __forceinline__ uint32_t part_reserve(const ScanInput &in, const unsi
   return (uint32_t)(part_start[p] + off);
 }
 
+// destination array of partition p (see ScanInput::peer_out)
+__device__ __forceinline__ uint64_t *out_of(const ScanInput &in, uint64_t *out, uint32_t p) {
+  return in.n_peers ? in.peer_out[__umulhi(p, in.peer_magic)] : out;
+}
+
 // One sub-tile (n_words words starting at w0), exact: histogram -> prefix + one global reservation per partition ->
 // rank pass into `staging` -> coalesced copy-out.  hist[] is zero on entry and on exit; ends with a barrier.
 template <int THREADS, bool MIXED>
@@ -673,7 +693,7 @@ __device__ __forceinline__ void stage_subtile_exact(const TileSmem *ts, int w0, 
   for (uint32_t i = tid; i < n_sub; i += THREADS) {  // coalesced copy-out
     const uint64_t key = staging[i];
     const uint32_t p = MIXED ? coarse_of_mix(key, n_parts) : part_of(key, n_parts);
-    if (g_base[p] != NO_BASE) __stcs(out + ((uint64_t)g_base[p] + (i - s_off[p])), key);
+    if (g_base[p] != NO_BASE) __stcs(out_of(in, out, p) + ((uint64_t)g_base[p] + (i - s_off[p])), key);
   }
   __syncthreads();
   for (uint32_t p = tid; p < n_parts; p += THREADS) hist[p] = 0;
@@ -825,11 +845,11 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
 #pragma unroll 4
         for (uint32_t x = tid; x < n_slots; x += ROWS_THREADS) {  // lanes walk along the rows: contiguous destinations
           const uint32_t p = __umulhi(x, magic), e = x - p * cap;
-          if (e < cnt[p]) __stcs(out + (uint64_t)g_base[p] + e, rows[x]);
+          if (e < cnt[p]) __stcs(out_of(in, out, p) + (uint64_t)g_base[p] + e, rows[x]);
         }
         for (uint32_t o = tid; o < n_ov; o += ROWS_THREADS) {
           const uint32_t meta = ov_meta[o];
-          if (g_base[meta >> 16] != NO_BASE) __stcs(out + (uint64_t)g_base[meta >> 16] + (meta & 0xffffu), ov_key[o]);
+          if (g_base[meta >> 16] != NO_BASE) __stcs(out_of(in, out, meta >> 16) + (uint64_t)g_base[meta >> 16] + (meta & 0xffffu), ov_key[o]);
         }
         __syncthreads();
         for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
@@ -1022,6 +1042,15 @@ cudaError_t launch_start_bits(const uint64_t *d_offsets, uint64_t n_records, uin
 cudaError_t launch_synth_uniform(uint64_t seed, uint64_t first_base, uint64_t n, uint8_t *d_out, cudaStream_t s) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   synth_uniform_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(seed, first_base, n, d_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_count_windows(const uint32_t *d_valid, const uint32_t *d_start, uint64_t n_words, int k, unsigned long long *d_out,
+                                 cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), s);
+  if (e != cudaSuccess || n_words == 0) return e;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  count_windows_kernel<<<grid_for(n_words, 256, 8), 256, 0, s>>>(d_valid, d_start, n_words, k, d_out);
   return cudaGetLastError();
 }
 

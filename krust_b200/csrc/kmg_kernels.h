@@ -16,6 +16,11 @@ struct ScanInput {
   // fit raises *overflow_flag and writes nothing.  part_cap == 0: exact layout from the counted prefix.
   uint64_t part_cap = 0;
   uint32_t *overflow_flag = nullptr;
+  // sharded (multi-GPU) scatter: bin p belongs to owner p / peer_bins and is written straight into THAT GPU's coarse receive
+  // buffer peer_out[owner] over NVLink (P2P-mapped pointers; the own rank's entry is a local pointer).  part_start[] then holds
+  // indices into the owner's buffer.  n_peers == 0: everything goes to the kernel's `out` argument.
+  uint64_t *peer_out[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint32_t n_peers = 0, peer_magic = 0;  // owner = __umulhi(p, peer_magic) == p / peer_bins for p < 2^16
 };
 
 struct HashTable {
@@ -70,7 +75,8 @@ struct RefineParams {
   // sub_total = n_sub, sub_old = 1.  Re-splitting a fine-partitioned run m ways (the sub-bin function nests: floor(x * P2 * m) / m ==
   // floor(x * P2)): n_sub = m, sub_old = old sub-bins per coarse bin, sub_total = sub_old * m.
   uint32_t sub_total, sub_old;
-  uint32_t in_keys, pad1;                 // 1: the input holds plain keys (adopted from another rank) -- mix on load; the output is always mixed
+  uint32_t in_keys, in_group;             // in_keys 1: the input holds plain keys (adopted from another rank) -- mix on load; the output is always mixed
+                                          // in_group g > 1: input partitions c*g .. c*g+g-1 are g pieces of coarse bin c (one per source rank of the sharded scatter)
   unsigned long long *fine_counts;        // count pass
   const unsigned long long *fine_start;   // scatter pass: exclusive prefix of fine_counts
   unsigned long long *fine_cursor;        // scatter pass: zeroed
@@ -118,6 +124,8 @@ cudaError_t launch_start_bits(const uint64_t *d_offsets, uint64_t n_records, uin
 cudaError_t launch_synth_uniform(uint64_t seed, uint64_t first_base, uint64_t n, uint8_t *d_out, cudaStream_t s);
 cudaError_t launch_synth_reads(uint64_t seed, uint32_t profile, uint64_t first_read, uint64_t n_reads, uint8_t *d_seq, uint8_t *d_qual,
                                cudaStream_t s);
+cudaError_t launch_count_windows(const uint32_t *d_valid, const uint32_t *d_start, uint64_t n_words, int k, unsigned long long *d_out,
+                                 cudaStream_t s);
 cudaError_t launch_scan_hash(const ScanInput &in, HashTable t, unsigned long long *counters, uint32_t flags, cudaStream_t s);
 cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, unsigned long long *counters, uint32_t flags,
                               cudaStream_t s);

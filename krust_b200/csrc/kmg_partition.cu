@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
     uint32_t c, m;
     uint64_t begin;
     refine_locate_tile(P, g, &s_c, c, begin, m);
-    refine_tile_two_pass<REFINE_THREADS, SCATTER>(P, begin, m, (uint64_t)c * P.n_sub, (c % P.sub_old) * P.n_sub, staging, staging_c, hist, s_off, g_base, s_scan);
+    const uint32_t cb = c / P.in_group;  // coarse bin of input partition c
+    refine_tile_two_pass<REFINE_THREADS, SCATTER>(P, begin, m, (uint64_t)cb * P.n_sub, (cb % P.sub_old) * P.n_sub, staging, staging_c, hist, s_off, g_base, s_scan);
     __syncthreads();
   }
 }
@@ -297,8 +298,9 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
   for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m ? __ldcs(P.keys + begin + i) : EMPTY_KEY; }
 
   for (uint32_t g = g_begin; g < g_end; ++g) {
-    const uint64_t f0 = (uint64_t)c * P.n_sub;
-    const uint32_t sub_base = (c % P.sub_old) * P.n_sub;
+    const uint32_t cb = c / P.in_group;  // coarse bin of input partition c
+    const uint64_t f0 = (uint64_t)cb * P.n_sub;
+    const uint32_t sub_base = (cb % P.sub_old) * P.n_sub;
     {  // ---- rank the tile's keys into the rows
       uint32_t sb[U], r[U];
 #pragma unroll
@@ -383,6 +385,7 @@ cudaError_t launch_refine(const RefineParams &P_in, bool scatter, cudaStream_t s
   if (P_in.n_tiles == 0) return cudaSuccess;
   RefineParams P = P_in;
   if (!P.sub_total) { P.sub_total = P.n_sub; P.sub_old = 1; }  // plain refinement of coarse bins
+  if (!P.in_group) P.in_group = 1;
   cudaError_t e;
   if (scatter && refine_single_pass_available(P.n_sub, P.counts || P.out_counts)) {
     P.row_cap = std::min<uint32_t>((uint32_t)REFINE_ROWS_SLOTS / P.n_sub, REFINE_TILE);  // mean fill 8192 / (n_sub * cap) ~ 0.5

@@ -1,18 +1,16 @@
-"""Hash-sharded multi-GPU counting: one process per GPU, torch.distributed for the plumbing.
+"""Hash-sharded multi-GPU counting: one process per GPU, torch.distributed for launch / rendezvous.
 
-The count table shards by k-mer hash: owner = kmg_owner_of(canonical key, world).
-Every rank scans its slice of the input, buckets the canonical keys by owner
-(kmg_extract_keys_device), exchanges the buckets with ONE all-to-all (NCCL over NVLink on GPUs,
-gloo in the CPU tests), and upserts what it receives into its local shard
-(kmg_insert_keys_device).  Shards are disjoint, so the global result is the concatenation of the
-shards; the histogram is the element-wise sum of the shard histograms.
+The count table shards by k-mer hash.  With the CUDA engine the exchange is FUSED into the scan
+(`kmg_shard_*` in include/kmerust_gpu.h): every rank's scatter kernel writes each hash bin straight into its owner's receive
+buffer over NVLink (P2P-mapped memory), the owner refines and counts what arrived; sizes, flags, summaries and histograms
+cross through a shared-memory segment inside the library.  torch.distributed only names the group and times the run.
 
-The reference has no distributed mode; this replaces the single shared DashMap of
-src/run.rs:489-583 by `world` disjoint tables.
+A generic path (bucket -> all_to_all_single -> adopt) remains for engines without the fused calls: it is what the CPU tests
+drive with the gloo backend and a stand-in engine (tests/test_dist_gloo.py), and it can be forced on GPUs with
+KMG_DIST_FUSED=0 for A/B measurements (NCCL all-to-all of raw keys: the round-1 design).
 
-The engine behind a rank is duck-typed (`extract`, `insert`, `finalize`, `export`, `histogram`) so
-that the exchange logic can be exercised on CPU with gloo (tests/test_dist_gloo.py) while the
-product engine (`GpuShardEngine`) runs the CUDA kernels.
+The reference has no distributed mode; this replaces the single shared DashMap of src/run.rs:489-583 by `world`
+disjoint tables.
 """
 from __future__ import annotations
 
@@ -52,8 +50,10 @@ def merge_histograms(parts: List[Tuple[np.ndarray, np.ndarray]]) -> Tuple[np.nda
 class GpuShardEngine:
     """One rank's CUDA engine: thin adapter from torch tensors to the raw-pointer C ABI."""
 
+    fused = True   # offers the kmg_shard_* calls (scatter kernel writes into the owners' buffers over NVLink)
+
     def __init__(self, k: int, device: torch.device, min_quality: Optional[int] = None, expected_distinct: int = 0,
-                 flags: int = 0):
+                 flags: int = 0, batch_bases: int = 0):
         from .api import GpuKmerCounter
         self.device = device
         torch.cuda.set_device(device)
@@ -66,8 +66,19 @@ class GpuShardEngine:
             from ._lib import KMG_FLAG_FORCE_PARTITIONED
             flags |= KMG_FLAG_FORCE_PARTITIONED  # the exchange moves hash-partitioned keys, whatever k is
         self.counter = GpuKmerCounter(k, min_quality=min_quality, expected_distinct=expected_distinct, flags=flags,
-                                      device=device.index, stream=handle)
+                                      device=device.index, stream=handle, batch_bases=batch_bases)
         self.k = k
+        self.batch_bases = batch_bases
+        self.joined = False
+
+    def join(self, world: int, rank: int, group: str, expected_keys_total: int):
+        self.counter.shard_join(world, rank, group, expected_keys_total)
+        self.joined = True
+
+    def count_fused(self, seq: torch.Tensor, offsets: Optional[torch.Tensor] = None, qual: Optional[torch.Tensor] = None):
+        n_rec = 1 if offsets is None else offsets.numel() - 1
+        self.counter.shard_count_device(seq.data_ptr() if seq.numel() else 0, seq.numel(), qual.data_ptr() if qual is not None and qual.numel() else 0,
+                                        offsets.data_ptr() if offsets is not None else 0, n_rec)
 
     def count_local(self, seq: torch.Tensor, offsets: Optional[torch.Tensor] = None, qual: Optional[torch.Tensor] = None):
         n_rec = 1 if offsets is None else offsets.numel() - 1
@@ -111,6 +122,12 @@ class GpuShardEngine:
         self.counter.reset()
 
     def close(self):
+        if self.joined:
+            try:
+                self.counter.shard_leave()
+            except Exception:
+                pass
+            self.joined = False
         self.counter.close()
 
 
@@ -128,6 +145,16 @@ class ShardedKmerCounter:
         self.sent_keys = 0
         self.recv_keys = 0
         self._p1 = None
+        self.fused = bool(getattr(engine, "fused", False)) and os.environ.get("KMG_DIST_FUSED", "1") != "0" and self.world > 1
+
+    def _join(self, expected_keys_total: int):
+        """All ranks join ONE shard group with identical arguments (name from rank 0, size hint = the largest proposal)."""
+        dev0 = getattr(self.engine, "device", torch.device("cpu"))
+        t = torch.tensor([int(expected_keys_total)], dtype=torch.int64, device=dev0)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        name = [f"{os.getpid()}-{time.time_ns() & 0xffffffffff:x}" if self.rank == 0 else None]
+        dist.broadcast_object_list(name, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        self.engine.join(self.world, self.rank, name[0], int(t.item()))
 
     def count(self, seq, offsets=None, qual=None, expected_keys_per_rank: int = 0, n_chunks: Optional[int] = None):
         """`seq` is THIS rank's slice (see slice_for_rank); offsets/qual are relative to it.
@@ -141,6 +168,11 @@ class ShardedKmerCounter:
         scans piece j+1 (see __init__ for the default)."""
         if self.world == 1:
             self.engine.count_local(seq, offsets, qual)
+            return
+        if self.fused:
+            if not self.engine.joined:
+                self._join(max(int(expected_keys_per_rank), int(seq.numel()), 1) * self.world)
+            self.engine.count_fused(seq, offsets, qual)   # rounds of batch_bases; the ranks agree on their number inside
             return
         if self._p1 is None:
             # all ranks must agree on P1: take the plan of the rank expecting the most keys
@@ -218,8 +250,28 @@ class ShardedKmerCounter:
             finish(pending)
             t0 = lap("adopt", t0)
 
+    def count_host(self, seq: np.ndarray, offsets: np.ndarray, qual: Optional[np.ndarray] = None, expected_keys_per_rank: int = 0):
+        """THIS rank's slice in HOST memory (pinned arrays are DMA'd directly): kmg_shard_count_ascii stages it through the
+        context's pinned ring, chunk by chunk, every chunk one fused scatter + exchange round."""
+        if self.world == 1:
+            self.engine.counter.count_batch(seq, qual, offsets)
+        elif self.fused:
+            if not self.engine.joined:
+                self._join(max(int(expected_keys_per_rank), len(seq), 1) * self.world)
+            self.engine.counter.shard_count_batch(seq, qual, offsets)
+        else:
+            dev = self.engine.device
+            self.count(torch.from_numpy(seq).to(dev, non_blocking=True), torch.from_numpy(np.asarray(offsets).astype(np.int64)).to(dev),
+                       None if qual is None else torch.from_numpy(qual).to(dev, non_blocking=True), expected_keys_per_rank=expected_keys_per_rank)
+
     def finalize(self) -> dict:
         """Global summary: sums over shards (shards are disjoint), max of max_count."""
+        if self.fused and self.engine.joined:
+            out = self.engine.counter.shard_finalize()      # kmg_shard_finalize: merged inside the library
+            out["local"] = self.engine.finalize(True)
+            st = self.engine.counter.shard_stats()
+            self.sent_keys, self.recv_keys = st["sent_keys"], st["recv_keys"]
+            return out
         s = self.engine.finalize(True)
         if self.world == 1:
             return s
@@ -236,6 +288,8 @@ class ShardedKmerCounter:
 
     def histogram(self, min_count: int = 1):
         """Count-of-counts over all shards (every rank gets the merged result)."""
+        if self.fused and self.engine.joined:
+            return self.engine.counter.shard_histogram(min_count)
         vals, freqs = self.engine.histogram(min_count)
         if self.world == 1:
             return vals, freqs
@@ -253,3 +307,31 @@ class ShardedKmerCounter:
         k = np.concatenate([p[0] for p in parts]); c = np.concatenate([p[1] for p in parts])
         order = np.argsort(k, kind="stable")
         return k[order], c[order]
+
+    def save_kmix(self, path) -> dict:
+        """ONE .kmix index from all shards (rank 0 writes header + combined CRC, every rank its own records)."""
+        if self.world == 1 or (self.fused and self.engine.joined):
+            n = self.engine.counter.shard_save_kmix(path)
+            return {"records": int(n)}
+        # generic path: the same protocol driven from here (kmg_kmix_begin / kmg_save_kmix_shard / kmg_kmix_finish)
+        from .api import kmix_begin, kmix_finish
+        s = self.engine.finalize(True)
+        sizes: List = [None] * self.world
+        dist.all_gather_object(sizes, int(s["n_distinct"]), group=self.group)
+        if self.rank == 0:
+            kmix_begin(path)
+        dist.barrier(group=self.group)
+        n, crc = self.engine.counter.save_kmix_shard(path, sum(sizes[: self.rank]))
+        parts: List = [None] * self.world
+        dist.all_gather_object(parts, (int(n), int(crc)), group=self.group)
+        if self.rank == 0:
+            kmix_finish(path, int(self.engine.k), [p[0] for p in parts], [p[1] for p in parts])
+        dist.barrier(group=self.group)
+        return {"records": int(sum(p[0] for p in parts))}
+
+    def stats(self) -> dict:
+        out = {"path": "fused scatter+exchange (P2P stores into the owners' buffers)" if self.fused else "bucket + NCCL all_to_all_single + adopt",
+               "sent_keys": int(self.sent_keys), "recv_keys": int(self.recv_keys)}
+        if self.fused and getattr(self.engine, "joined", False):
+            out.update(self.engine.counter.shard_stats())
+        return out

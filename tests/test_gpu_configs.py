@@ -46,11 +46,13 @@ def test_c3_shape_reads_q20_min_count_2(flags):
     n_reads, k = 2_000_000, 31
     seq, qual, offsets = orc.synth_reads(43, 3, 0, n_reads)
     okeys, ocounts, owin = orc.count_batch_mt(k, seq, qual, offsets, 20)
-    with kb.GpuKmerCounter(k, min_quality=20, flags=flags, expected_distinct=len(okeys)) as c:
+    with kb.GpuKmerCounter(k, min_quality=20, flags=flags) as c:   # no size hint: planned from the countable windows of the data
         c.count_batch(seq, qual, offsets)
         s = c.finalize()
         assert s["n_windows"] == owin and s["n_distinct"] == len(okeys) and s["n_records"] == n_reads
-        assert s["path"] == (2 if flags else 0)
+        assert s["path"] == (2 if flags else 0)   # ~6 M windows survive -Q 20: a small job for the single table unless forced
+        if flags:
+            assert s["table_capacity"] <= 4 * (owin // 3600 + 4)   # partitions planned for what survives, not for 300 M bases
         for m in (2, 1):
             gk, gc = c.export(m, True)
             fk, fc = orc.filter_min_count(okeys, ocounts, m)
@@ -109,7 +111,7 @@ def test_kmix_from_two_shards_on_one_device(tmp_path):
     import torch
     dev = torch.device("cuda:0")
     k = 21
-    seq, _, offsets = orc.synth_reads(45, 5, 0, 300_000, False)
+    seq, _, offsets = orc.synth_reads(45, 5, 0, 40_000, False)
     okeys, ocounts, _ = orc.count_batch_mt(k, seq, None, offsets)
     owner = np.array([kb.owner_of(int(x), 2) for x in okeys[:2000]])
     assert 0 < owner.sum() < 2000
