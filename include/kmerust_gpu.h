@@ -160,9 +160,10 @@ kmg_status kmg_adopt_coarse_device(kmg_ctx *ctx, const uint64_t *d_keys, const u
 
 /* ---- hash-sharded counting across the GPUs of one box ------------------------------------------------------
  * One context per GPU -- one process per device (torchrun, a Rust host that forks per GPU) or one thread per device -- joined
- * into a group.  The table shards by k-mer hash; the exchange is fused into the scan: the scatter kernel of every rank writes
- * each hash bin straight into its owner's receive buffer through P2P-mapped memory (NVLink stores), the owner refines and
- * counts what arrived.  Only sizes, flags and results cross on the host, through a POSIX shared-memory segment named after
+ * into a group.  The table shards by k-mer hash; every rank scatters its keys by (owner, hash bin) into its own send buffer,
+ * and the exchange is fused into the owner's refine kernel, whose tile loads read the owner's bins straight out of all ranks'
+ * send buffers through P2P-mapped memory (NVLink loads): no key is copied, it crosses NVLink on its way into the kernel that
+ * partitions it further.  Only sizes, flags and results cross on the host, through a POSIX shared-memory segment named after
  * `group` (created by rank 0, unlinked once everybody is attached) -- no NCCL inside the library.  All kmg_shard_* calls are
  * COLLECTIVE: every rank makes the same sequence of them (a rank without input passes n_bytes / n_records = 0); a rank that
  * fails marks the group aborted, so its peers return KMG_ERR_STATE instead of waiting.  world == 1 degenerates to the plain

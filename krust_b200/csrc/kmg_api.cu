@@ -110,9 +110,9 @@ struct kmg_ctx {
   bool in_resplit = false;
   struct ShardShm *shm = nullptr;     // sharded mode (kmg_shard_join): the group's shared segment
   uint32_t sh_world = 1, sh_rank = 0;
-  uint64_t *sh_recv = nullptr;        // this rank's coarse receive buffer (peers write into it over NVLink)
+  uint64_t *sh_recv = nullptr;        // this rank's SEND buffer: two halves of sh_recv_entries keys (owners pull their regions over NVLink)
   uint64_t sh_recv_entries = 0;
-  uint64_t *sh_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // every rank's receive buffer as seen from here
+  uint64_t *sh_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // every rank's send buffer as seen from here
   bool sh_peer_ipc[8] = {false, false, false, false, false, false, false, false};
   uint64_t sh_sent = 0, sh_recv_keys = 0, sh_rounds = 0, sh_exact_rounds = 0;
   std::vector<uint64_t> sh_hist_vals, sh_hist_freqs;  // merged histogram of the last kmg_shard_histogram
@@ -404,7 +404,8 @@ struct SplitPlan { uint32_t n_in, m, sub_old; Run *out; };
 kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, const std::vector<uint64_t> &coarse_off, bool owns = true,
                          bool sync = true, const std::vector<uint64_t> *coarse_len = nullptr, const SplitPlan *split = nullptr,
                          bool in_keys = false,    // in_keys: the input holds plain keys, not mixes (blocks adopted from another rank)
-                         uint32_t in_group = 1) { // in_group g: coarse bin b arrives as the g input partitions b*g .. b*g+g-1 (sharded scatter: one per source)
+                         uint32_t in_group = 1,   // in_group g: coarse bin b arrives as the g input partitions b*g .. b*g+g-1 (sharded: one per source rank)
+                         const uint64_t *const *src = nullptr) {  // src[s]: input partition p is read from src[p % in_group] (other ranks' send buffers)
   struct BuildGuard {
     kmg_ctx *c;
     explicit BuildGuard(kmg_ctx *c_) : c(c_) { ++c->building_run; }
@@ -451,6 +452,7 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   if (split) { rp.sub_total = split->sub_old * split->m; rp.sub_old = split->sub_old; }
   rp.in_keys = in_keys ? 1u : 0u;
   rp.in_group = in_group;
+  if (src) { rp.n_src = in_group; for (uint32_t i = 0; i < in_group && i < 8; ++i) rp.src[i] = src[i]; }
   // Speculative layout first: hash partitions are Poisson-sized, so every fine partition gets mean + 7 sigma + 16 slots
   // and the count pass (a full read of the keys) is skipped.  Skewed input overflows a share: the kernel then raises a
   // flag, and this chunk -- and, sticky, the rest of the job -- takes the exact count + prefix + scatter route below.
@@ -1379,11 +1381,15 @@ KMG_EXPORT kmg_status kmg_extract_keys_device(kmg_ctx *c, const uint8_t *d_seq, 
 // =================================================================================================
 // Sharded (multi-GPU) counting: one context per GPU -- processes (torchrun, a Rust host with one process per device) or
 // threads of one process -- joined into a group on ONE box.  The count table shards by hash: global coarse bin
-// g = coarse_of_mix(mix, world * P1) belongs to rank g / P1.  The exchange is FUSED into the scatter kernel: A1's copy-out
-// writes every bin straight into its owner's coarse receive buffer through P2P-mapped pointers (NVLink stores), region
-// (local bin c, source s) of the owner's buffer; the owner then refines + counts what arrived (A2, B) like local input.
-// Only metadata crosses between the ranks on the host: a POSIX shared-memory segment carries the region sizes, flags,
-// summaries, histograms and a sense-reversing barrier.  No NCCL, no staging copies, no count pass on the fast path.
+// g = coarse_of_mix(mix, world * P1) belongs to rank g / P1.  Every rank scatters its keys into its own send buffer, one
+// region per global bin; the exchange is FUSED into the owner's refine kernel (A2), whose tile loads read the owner's regions
+// straight out of all ranks' send buffers through P2P-mapped pointers (NVLink loads, prefetched a tile ahead), so no key is
+// ever copied: it crosses NVLink once, on its way into the kernel that partitions it further.  Only metadata crosses between
+// the ranks on the host: a POSIX shared-memory segment carries the region sizes, flags, summaries, histograms and a
+// sense-reversing barrier.  No NCCL, no staging copies, no count pass on the fast path.
+// (Measured alternative, round 2: the scatter kernel writing into the owners' buffers with P2P STORES.  A sub-tile yields only
+// ~8 keys per bin, and 64-byte NVLink writes cost more than they move: 4.45 ms per 310 M-base round against 2.05 ms for the
+// local scatter; fewer bins made the stores longer but the owner's refine slower -- profiles/r2_summary.md.)
 // =================================================================================================
 constexpr uint32_t SHARD_MAX_WORLD = 8;
 constexpr uint32_t SHARD_MAX_BINS = 2048;        // world * P1 (the single-scan rows kernel's limit)
@@ -1448,36 +1454,43 @@ void shard_release(kmg_ctx *c) {
   c->sh_world = 1; c->sh_rank = 0;
 }
 
-// one round of the fused scatter + exchange over the context's packed stream (n_words_total may be 0: a rank that has run out
-// of input still takes part), then A2 over what this rank received
+// One round of the sharded pipeline over the context's packed stream (n_words_total may be 0: a rank that has run out of
+// input still takes part).  A1 scatters this rank's keys into ITS OWN send buffer, one region per global bin (owner-major);
+// after the barrier every owner runs A2 straight over the regions that belong to it in ALL ranks' send buffers -- the tile
+// loads of the refine kernel are P2P loads, i.e. the NVLink transfer happens inside A2, tile by tile, prefetched one tile ahead.
+// Send buffers are double buffered: round i+1 scatters into the other half while slower owners may still be pulling round i.
 kmg_status shard_scan_round(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
   ShardShm *S = c->shm;
   const uint32_t W = c->sh_world, me = c->sh_rank, P1 = c->n_coarse, G = W * P1;
   unsigned long long *d_cnt = c->d_part, *d_start = c->d_part + MAX_PARTS, *d_cur = c->d_part + 2 * MAX_PARTS;
-  // 1. this rank's receive buffer is free again (the previous round's A2 has read it) and the round's size is known to all
-  SCU(c, cudaStreamSynchronize(c->stream));
+  static const bool trace = getenv("KMG_SHARD_TIMING") != nullptr;  // per-round wall times (every phase ends in a sync anyway)
+  const double tr0 = now_s();
+  // 1. the round's size is known to all (and everybody has finished the round before the previous one: see the buffers' reuse)
   S->ranks[me].round_bytes = n_words_total * 32;
   S->ranks[me].round_flag = 0;
   SB(c);
   uint64_t max_w = 0;
   for (uint32_t r = 0; r < W; ++r) max_w = std::max<uint64_t>(max_w, S->ranks[r].round_bytes);
-  if (max_w == 0) { SB(c); return KMG_OK; }
-  if (max_w >= (1ull << 32)) return shard_fail(c, KMG_ERR_INVALID_ARG, "a sharded round handles < 2^32 bases per rank (lower batch_bases)");
+  if (max_w == 0) return KMG_OK;
+  if (max_w >= (1ull << 32) || max_w > c->sh_recv_entries) return shard_fail(c, KMG_ERR_INVALID_ARG, "a sharded round handles at most batch_bases (< 2^32) bases per rank");
+  const uint64_t parity = c->sh_rounds & 1;
+  c->sh_rounds++;
+  uint64_t *send = c->sh_recv + parity * c->sh_recv_entries;
+  const uint64_t *src[SHARD_MAX_WORLD];
+  for (uint32_t r = 0; r < W; ++r) src[r] = c->sh_peer[r] + parity * c->sh_recv_entries;
   ScanInput in;
   in.bases = c->d_bases; in.valid = c->d_valid; in.start = has_start ? c->d_start : nullptr;
   in.n_tiles = n_words_total / TILE_WORDS; in.k = c->k;
-  in.n_peers = W; in.peer_magic = (uint32_t)(((1ull << 32) + P1 - 1) / P1);
-  for (uint32_t r = 0; r < W; ++r) in.peer_out[r] = c->sh_peer[r];
   std::vector<uint64_t> h_start(G), h_len(G);
   const size_t tmr = timer_begin(c, 0);
-  c->sh_rounds++;
   bool done = false;
-  // 2. speculative layout: region (local bin cl, source s) of every owner's buffer holds cap entries, no sizes needed up front
+  double tr1 = tr0, tr2 = tr0;
+  // 2. speculative layout: every global bin owns cap slots of the send buffer (cap from the largest rank's round, so that owners
+  //    know where to read without being told); no count pass
   const double mu = (double)max_w / G;
   const uint64_t cap = ((uint64_t)(mu + 7.0 * std::sqrt(mu) + 64.0) + 15) & ~15ull;
   if (!__atomic_load_n(&S->spec_disabled, __ATOMIC_ACQUIRE) && cap * G <= c->sh_recv_entries && scan_scatter_supports_cap(G)) {
-    for (uint32_t r = 0; r < W; ++r)
-      for (uint32_t cl = 0; cl < P1; ++cl) h_start[r * P1 + cl] = ((uint64_t)cl * W + me) * cap;
+    for (uint32_t g = 0; g < G; ++g) h_start[g] = (uint64_t)g * cap;
     ScanInput sin = in;
     sin.part_cap = cap;
     sin.overflow_flag = reinterpret_cast<uint32_t *>(c->d_stats + 5);
@@ -1485,13 +1498,15 @@ kmg_status shard_scan_round(kmg_ctx *c, uint64_t n_words_total, bool has_start) 
     SCU(c, cudaMemsetAsync(c->d_part, 0, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
     SCU(c, cudaMemsetAsync(sin.overflow_flag, 0, 4, c->stream));
     SCU(c, cudaMemcpyAsync(d_start, h_start.data(), G * 8, cudaMemcpyHostToDevice, c->stream));
-    if (in.n_tiles) SCU(c, launch_scan_partition(sin, G, true, d_cnt, d_start, d_cur, c->sh_recv, c->d_counters, c->stream, /*mixed=*/true));
+    if (in.n_tiles) SCU(c, launch_scan_partition(sin, G, true, d_cnt, d_start, d_cur, send, c->d_counters, c->stream, /*mixed=*/true));
     SCU(c, cudaMemcpyAsync(h_len.data(), d_cur, G * 8, cudaMemcpyDeviceToHost, c->stream));
     SCU(c, cudaMemcpyAsync(&h_flag, sin.overflow_flag, 4, cudaMemcpyDeviceToHost, c->stream));
-    SCU(c, cudaStreamSynchronize(c->stream));  // the P2P stores of this rank have landed
+    SCU(c, cudaStreamSynchronize(c->stream));
+    tr1 = now_s();
     memcpy(S->lens[me], h_len.data(), G * 8);
     S->ranks[me].round_flag = h_flag;
-    SB(c);
+    SB(c);  // every rank's regions are complete in its send buffer
+    tr2 = now_s();
     bool any = false;
     for (uint32_t r = 0; r < W; ++r) any |= S->ranks[r].round_flag != 0;
     if (!any) {
@@ -1500,65 +1515,60 @@ kmg_status shard_scan_round(kmg_ctx *c, uint64_t n_words_total, bool has_start) 
       for (uint32_t cl = 0; cl < P1; ++cl)
         for (uint32_t s2 = 0; s2 < W; ++s2) {
           const size_t j = (size_t)cl * W + s2;
-          off[j] = j * cap; lens[j] = S->lens[s2][me * P1 + cl]; n_in += lens[j];
+          off[j] = (uint64_t)(me * P1 + cl) * cap; lens[j] = S->lens[s2][me * P1 + cl]; n_in += lens[j];
         }
-      off[(size_t)P1 * W] = (uint64_t)P1 * W * cap;
+      off[(size_t)P1 * W] = 0;  // unused: lengths are explicit
       for (uint32_t g = 0; g < G; ++g) if (g / P1 != me) c->sh_sent += h_len[g];
       c->sh_recv_keys += n_in;
-      SB(c);  // everybody has read the size matrix: the next round may overwrite it
       if (n_in) {
-        kmg_status st = refine_to_run(c, c->sh_recv, nullptr, off, /*owns=*/false, /*sync=*/true, &lens, nullptr, false, W);
+        kmg_status st = refine_to_run(c, nullptr, nullptr, off, /*owns=*/false, /*sync=*/true, &lens, nullptr, false, W, src);
         if (st != KMG_OK) return shard_fail(c, st, c->err);
       }
       done = true;
     } else {
       __atomic_store_n(&S->spec_disabled, 1u, __ATOMIC_RELEASE);  // sticky for the whole group: skewed input
-      SB(c);
     }
   }
-  // 3. exact route: count pass, sizes through the shared segment, exact region offsets, scatter
+  // 3. exact route (skewed input): count pass, exact prefix inside the own send buffer, scatter; owners derive every source's
+  //    region offsets from the size matrix in the shared segment
   if (!done) {
     c->sh_exact_rounds++;
     SCU(c, cudaMemsetAsync(c->d_part, 0, 3 * (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
-    if (in.n_tiles) {
-      ScanInput cin = in; cin.n_peers = 0;
-      SCU(c, launch_scan_partition(cin, G, false, d_cnt, d_start, d_cur, nullptr, c->d_counters, c->stream));
-    }
+    if (in.n_tiles) SCU(c, launch_scan_partition(in, G, false, d_cnt, d_start, d_cur, nullptr, c->d_counters, c->stream));
     SCU(c, cudaMemcpyAsync(h_len.data(), d_cnt, G * 8, cudaMemcpyDeviceToHost, c->stream));
     SCU(c, cudaStreamSynchronize(c->stream));
+    uint64_t run = 0;
+    for (uint32_t g = 0; g < G; ++g) { h_start[g] = run; run += h_len[g]; }
+    if (run > c->sh_recv_entries) return shard_fail(c, KMG_ERR_STATE, "send buffer smaller than a round (internal sizing error)");
+    SCU(c, cudaMemcpyAsync(d_start, h_start.data(), G * 8, cudaMemcpyHostToDevice, c->stream));
+    if (in.n_tiles) SCU(c, launch_scan_partition(in, G, true, d_cnt, d_start, d_cur, send, c->d_counters, c->stream, /*mixed=*/true));
+    SCU(c, cudaStreamSynchronize(c->stream));
+    tr1 = now_s();
     memcpy(S->lens[me], h_len.data(), G * 8);
     SB(c);
-    std::vector<uint64_t> off((size_t)P1 * W + 1);
-    uint64_t worst = 0;
-    for (uint32_t r = 0; r < W; ++r) {  // every rank derives every owner's layout from the same matrix
-      uint64_t run = 0;
-      for (uint32_t cl = 0; cl < P1; ++cl)
-        for (uint32_t s2 = 0; s2 < W; ++s2) {
-          if (s2 == me) h_start[r * P1 + cl] = run;
-          if (r == me) off[(size_t)cl * W + s2] = run;
-          run += S->lens[s2][r * P1 + cl];
-        }
-      if (r == me) off[(size_t)P1 * W] = run;
-      worst = std::max(worst, run);
+    tr2 = now_s();
+    std::vector<uint64_t> off((size_t)P1 * W + 1), lens((size_t)P1 * W);
+    uint64_t n_in = 0;
+    for (uint32_t s2 = 0; s2 < W; ++s2) {
+      uint64_t pre = 0;
+      for (uint32_t g = 0; g < G; ++g) {
+        if (g / P1 == me) { const size_t j = (size_t)(g - me * P1) * W + s2; off[j] = pre; lens[j] = S->lens[s2][g]; n_in += lens[j]; }
+        pre += S->lens[s2][g];
+      }
     }
-    const uint64_t n_in = off[(size_t)P1 * W];
+    off[(size_t)P1 * W] = 0;
     for (uint32_t g = 0; g < G; ++g) if (g / P1 != me) c->sh_sent += h_len[g];
     c->sh_recv_keys += n_in;
-    SB(c);  // the size matrix has been read by everyone
-    if (worst > c->sh_recv_entries)  // the same verdict on every rank
-      return fail(c, KMG_ERR_CAPACITY, "a shard would receive " + std::to_string(worst) + " keys in one round but its receive buffer holds " +
-                                           std::to_string(c->sh_recv_entries) + " (lower batch_bases or raise it at kmg_create for a larger buffer)");
-    SCU(c, cudaMemsetAsync(d_cur, 0, (size_t)MAX_PARTS * sizeof(unsigned long long), c->stream));
-    SCU(c, cudaMemcpyAsync(d_start, h_start.data(), G * 8, cudaMemcpyHostToDevice, c->stream));
-    if (in.n_tiles) SCU(c, launch_scan_partition(in, G, true, d_cnt, d_start, d_cur, c->sh_recv, c->d_counters, c->stream, /*mixed=*/true));
-    SCU(c, cudaStreamSynchronize(c->stream));
-    SB(c);  // all scatters have landed
     if (n_in) {
-      kmg_status st = refine_to_run(c, c->sh_recv, nullptr, off, /*owns=*/false, /*sync=*/true, nullptr, nullptr, false, W);
+      kmg_status st = refine_to_run(c, nullptr, nullptr, off, /*owns=*/false, /*sync=*/true, &lens, nullptr, false, W, src);
       if (st != KMG_OK) return shard_fail(c, st, c->err);
     }
   }
   timer_end(c, tmr);
+  if (trace && me == 0)
+    fprintf(stderr, "[shard round %llu] bases %llu  scatter %.2f ms  wait-for-peers %.2f ms  pull+refine %.2f ms  (G=%u, %s)\n",
+            (unsigned long long)c->sh_rounds, (unsigned long long)(n_words_total * 32), (tr1 - tr0) * 1e3, (tr2 - tr1) * 1e3, (now_s() - tr2) * 1e3,
+            G, done ? "speculative" : "exact");
   return KMG_OK;
 }
 
@@ -1581,17 +1591,21 @@ KMG_EXPORT kmg_status kmg_shard_join(kmg_ctx *c, uint32_t world, uint32_t rank, 
     const uint64_t want = std::max<uint64_t>(4, (per_rank + TARGET_KEYS_PER_PART - 1) / TARGET_KEYS_PER_PART);
     uint64_t p1 = 1;
     while (p1 * p1 < want) ++p1;
-    p1 = std::min<uint64_t>(p1, 1024 / world);  // world * P1 <= 1024 global bins: >= 8-key (64-byte) runs per bin and sub-tile in the NVLink copy-out
+    uint64_t g_max = SHARD_MAX_BINS;  // world * P1 global bins in one scatter (the single-scan rows kernel's limit)
+    if (const char *e = getenv("KMG_SHARD_BINS")) g_max = std::min<uint64_t>(std::max<uint64_t>(strtoull(e, nullptr, 10), world), SHARD_MAX_BINS);
+    p1 = std::min<uint64_t>(p1, g_max / world);
     c->n_coarse = (uint32_t)std::max<uint64_t>(p1, 1);
     c->n_sub = (uint32_t)std::min<uint64_t>((want + c->n_coarse - 1) / c->n_coarse, 2048);
     kmg_status st = init_partitioned(c);
     if (st != KMG_OK) return st;
   }
-  // ---- receive buffer: one round moves at most batch_bases windows per source; 25 % headroom for uneven owners
+  // ---- send buffer (double buffered, one allocation so that one IPC handle covers both halves): a round scatters at most
+  // batch_bases keys into it; the speculative layout needs mean + 7 sigma + 64 slots per global bin
   const uint64_t G = (uint64_t)world * c->n_coarse;
-  const double mu = (double)c->batch_bases / (double)G;
-  c->sh_recv_entries = std::min<uint64_t>((uint64_t)((double)c->batch_bases * 1.25) + G * (uint64_t)(7.0 * std::sqrt(mu) + 80.0), (1ull << 32) - 1);
-  CU(c, cudaMalloc(&c->sh_recv, c->sh_recv_entries * 8));
+  const uint64_t round_max = round_up(c->batch_bases, (uint64_t)TILE_WORDS * 32);  // rounds are padded to whole tiles
+  const double mu = (double)round_max / (double)G;
+  c->sh_recv_entries = std::min<uint64_t>(round_max + G * (uint64_t)(7.0 * std::sqrt(mu) + 96.0), (1ull << 32) - 1);
+  CU(c, cudaMalloc(&c->sh_recv, 2 * c->sh_recv_entries * 8));
   // ---- shared segment: rank 0 creates, the others attach
   const std::string name = std::string("/kmg-") + group;
   int fd = -1;

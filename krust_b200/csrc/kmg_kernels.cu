@@ -637,11 +637,6 @@ __device__ __forceinline__ uint32_t part_reserve(const ScanInput &in, const unsi
   return (uint32_t)(part_start[p] + off);
 }
 
-// destination array of partition p (see ScanInput::peer_out)
-__device__ __forceinline__ uint64_t *out_of(const ScanInput &in, uint64_t *out, uint32_t p) {
-  return in.n_peers ? in.peer_out[__umulhi(p, in.peer_magic)] : out;
-}
-
 // One sub-tile (n_words words starting at w0), exact: histogram -> prefix + one global reservation per partition ->
 // rank pass into `staging` -> coalesced copy-out.  hist[] is zero on entry and on exit; ends with a barrier.
 template <int THREADS, bool MIXED>
@@ -693,7 +688,7 @@ __device__ __forceinline__ void stage_subtile_exact(const TileSmem *ts, int w0, 
   for (uint32_t i = tid; i < n_sub; i += THREADS) {  // coalesced copy-out
     const uint64_t key = staging[i];
     const uint32_t p = MIXED ? coarse_of_mix(key, n_parts) : part_of(key, n_parts);
-    if (g_base[p] != NO_BASE) __stcs(out_of(in, out, p) + ((uint64_t)g_base[p] + (i - s_off[p])), key);
+    if (g_base[p] != NO_BASE) __stcs(out + ((uint64_t)g_base[p] + (i - s_off[p])), key);
   }
   __syncthreads();
   for (uint32_t p = tid; p < n_parts; p += THREADS) hist[p] = 0;
@@ -845,11 +840,11 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
 #pragma unroll 4
         for (uint32_t x = tid; x < n_slots; x += ROWS_THREADS) {  // lanes walk along the rows: contiguous destinations
           const uint32_t p = __umulhi(x, magic), e = x - p * cap;
-          if (e < cnt[p]) __stcs(out_of(in, out, p) + (uint64_t)g_base[p] + e, rows[x]);
+          if (e < cnt[p]) __stcs(out + (uint64_t)g_base[p] + e, rows[x]);
         }
         for (uint32_t o = tid; o < n_ov; o += ROWS_THREADS) {
           const uint32_t meta = ov_meta[o];
-          if (g_base[meta >> 16] != NO_BASE) __stcs(out_of(in, out, meta >> 16) + (uint64_t)g_base[meta >> 16] + (meta & 0xffffu), ov_key[o]);
+          if (g_base[meta >> 16] != NO_BASE) __stcs(out + (uint64_t)g_base[meta >> 16] + (meta & 0xffffu), ov_key[o]);
         }
         __syncthreads();
         for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;

@@ -16,11 +16,6 @@ struct ScanInput {
   // fit raises *overflow_flag and writes nothing.  part_cap == 0: exact layout from the counted prefix.
   uint64_t part_cap = 0;
   uint32_t *overflow_flag = nullptr;
-  // sharded (multi-GPU) scatter: bin p belongs to owner p / peer_bins and is written straight into THAT GPU's coarse receive
-  // buffer peer_out[owner] over NVLink (P2P-mapped pointers; the own rank's entry is a local pointer).  part_start[] then holds
-  // indices into the owner's buffer.  n_peers == 0: everything goes to the kernel's `out` argument.
-  uint64_t *peer_out[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  uint32_t n_peers = 0, peer_magic = 0;  // owner = __umulhi(p, peer_magic) == p / peer_bins for p < 2^16
 };
 
 struct HashTable {
@@ -75,6 +70,10 @@ struct RefineParams {
   // sub_total = n_sub, sub_old = 1.  Re-splitting a fine-partitioned run m ways (the sub-bin function nests: floor(x * P2 * m) / m ==
   // floor(x * P2)): n_sub = m, sub_old = old sub-bins per coarse bin, sub_total = sub_old * m.
   uint32_t sub_total, sub_old;
+  // sharded pull: input partition c is read from src[c % in_group] (the send buffer of source rank c % in_group, P2P-mapped:
+  // the tile loads below are the NVLink transfer); n_src == 0: everything comes from `keys`
+  const uint64_t *src[8];
+  uint32_t n_src, pad2;
   uint32_t in_keys, in_group;             // in_keys 1: the input holds plain keys (adopted from another rank) -- mix on load; the output is always mixed
                                           // in_group g > 1: input partitions c*g .. c*g+g-1 are g pieces of coarse bin c (one per source rank of the sharded scatter)
   unsigned long long *fine_counts;        // count pass

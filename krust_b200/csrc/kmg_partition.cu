@@ -127,10 +127,15 @@ __device__ __forceinline__ uint32_t refine_reserve(const RefineParams &P, uint64
   return (uint32_t)(P.fine_start[f] + off);
 }
 
+// where input partition c's keys live (RefineParams::src)
+__device__ __forceinline__ const uint64_t *refine_keys_of(const RefineParams &P, uint32_t c) {
+  return P.n_src ? P.src[c % P.in_group] : P.keys;
+}
+
 // One tile, exact two-pass procedure: histogram -> (count: add to fine_counts | scatter: prefix, one global reservation
 // per sub-bin, rank the keys into `staging` in sub-bin order, coalesced copy-out).  hist[] is zero on entry and on exit.
 template <int THREADS, bool SCATTER>
-__device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, const uint64_t begin, const uint32_t m, const uint64_t f0, const uint32_t sub_base,
+__device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, const uint64_t *__restrict__ kbase, const uint64_t begin, const uint32_t m, const uint64_t f0, const uint32_t sub_base,
                                                      uint64_t *staging, uint64_t *staging_c, uint32_t *hist, uint32_t *s_off,
                                                      uint32_t *g_base, uint32_t *s_scan) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -140,7 +145,7 @@ __device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, cons
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       const uint32_t i = i0 + j * THREADS + tid;
-      key[j] = i < m ? (SCATTER ? P.keys[begin + i] : __ldcs(P.keys + begin + i)) : EMPTY_KEY;
+      key[j] = i < m ? (SCATTER ? kbase[begin + i] : __ldcs(kbase + begin + i)) : EMPTY_KEY;
     }
 #pragma unroll
     for (int j = 0; j < U; ++j) if (i0 + j * THREADS + tid < m) atomicAdd(hist + (sub_of_mix(P.in_keys ? mix64(key[j]) : key[j], P.sub_total) - sub_base), 1u);
@@ -185,7 +190,7 @@ __device__ __forceinline__ void refine_tile_two_pass(const RefineParams &P, cons
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       const uint32_t i = i0 + j * THREADS + tid;
-      key[j] = i < m ? __ldcs(P.keys + begin + i) : EMPTY_KEY;  // last use of this tile
+      key[j] = i < m ? __ldcs(kbase + begin + i) : EMPTY_KEY;  // last use of this tile
       cnt[j] = (i < m && P.counts) ? __ldcs(P.counts + begin + i) : 1ull;
     }
 #pragma unroll
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams P) 
     uint64_t begin;
     refine_locate_tile(P, g, &s_c, c, begin, m);
     const uint32_t cb = c / P.in_group;  // coarse bin of input partition c
-    refine_tile_two_pass<REFINE_THREADS, SCATTER>(P, begin, m, (uint64_t)cb * P.n_sub, (cb % P.sub_old) * P.n_sub, staging, staging_c, hist, s_off, g_base, s_scan);
+    refine_tile_two_pass<REFINE_THREADS, SCATTER>(P, refine_keys_of(P, c), begin, m, (uint64_t)cb * P.n_sub, (cb % P.sub_old) * P.n_sub, staging, staging_c, hist, s_off, g_base, s_scan);
     __syncthreads();
   }
 }
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
   tile_range(g_begin, c, begin, m);
   uint64_t key[U];
 #pragma unroll
-  for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m ? __ldcs(P.keys + begin + i) : EMPTY_KEY; }
+  for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m ? __ldcs(refine_keys_of(P, c) + begin + i) : EMPTY_KEY; }
 
   for (uint32_t g = g_begin; g < g_end; ++g) {
     const uint32_t cb = c / P.in_group;  // coarse bin of input partition c
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
     if (exact) {
       for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
       __syncthreads();
-      refine_tile_two_pass<REFINE_ROWS_THREADS, true>(P, begin, m, f0, sub_base, rows, nullptr, cnt, s_off, g_base, s_scan);
+      refine_tile_two_pass<REFINE_ROWS_THREADS, true>(P, refine_keys_of(P, c), begin, m, f0, sub_base, rows, nullptr, cnt, s_off, g_base, s_scan);
     } else {
       for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) {
         const uint32_t h = cnt[s];
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
       c_next = s_c[nslot];
       tile_range(g + 1, c_next, begin_next, m_next);
 #pragma unroll
-      for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m_next ? __ldcs(P.keys + begin_next + i) : EMPTY_KEY; }
+      for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m_next ? __ldcs(refine_keys_of(P, c_next) + begin_next + i) : EMPTY_KEY; }
     }
     __syncthreads();
     if (!exact) {

@@ -1,9 +1,10 @@
 """Hash-sharded multi-GPU counting: one process per GPU, torch.distributed for launch / rendezvous.
 
-The count table shards by k-mer hash.  With the CUDA engine the exchange is FUSED into the scan
-(`kmg_shard_*` in include/kmerust_gpu.h): every rank's scatter kernel writes each hash bin straight into its owner's receive
-buffer over NVLink (P2P-mapped memory), the owner refines and counts what arrived; sizes, flags, summaries and histograms
-cross through a shared-memory segment inside the library.  torch.distributed only names the group and times the run.
+The count table shards by k-mer hash.  With the CUDA engine the exchange is FUSED into the pipeline
+(`kmg_shard_*` in include/kmerust_gpu.h): every rank scatters its keys by (owner, hash bin) into its own send buffer and the
+owner's refine kernel pulls its bins out of all ranks' buffers over NVLink (P2P-mapped memory) while it partitions them
+further; sizes, flags, summaries and histograms cross through a shared-memory segment inside the library.
+torch.distributed only names the group and times the run.
 
 A generic path (bucket -> all_to_all_single -> adopt) remains for engines without the fused calls: it is what the CPU tests
 drive with the gloo backend and a stand-in engine (tests/test_dist_gloo.py), and it can be forced on GPUs with
@@ -50,7 +51,7 @@ def merge_histograms(parts: List[Tuple[np.ndarray, np.ndarray]]) -> Tuple[np.nda
 class GpuShardEngine:
     """One rank's CUDA engine: thin adapter from torch tensors to the raw-pointer C ABI."""
 
-    fused = True   # offers the kmg_shard_* calls (scatter kernel writes into the owners' buffers over NVLink)
+    fused = True   # offers the kmg_shard_* calls (the owners' refine kernels pull their bins over NVLink)
 
     def __init__(self, k: int, device: torch.device, min_quality: Optional[int] = None, expected_distinct: int = 0,
                  flags: int = 0, batch_bases: int = 0):
@@ -330,7 +331,7 @@ class ShardedKmerCounter:
         return {"records": int(sum(p[0] for p in parts))}
 
     def stats(self) -> dict:
-        out = {"path": "fused scatter+exchange (P2P stores into the owners' buffers)" if self.fused else "bucket + NCCL all_to_all_single + adopt",
+        out = {"path": "fused exchange (owners' refine kernels pull their bins from all ranks' send buffers over NVLink)" if self.fused else "bucket + NCCL all_to_all_single + adopt",
                "sent_keys": int(self.sent_keys), "recv_keys": int(self.recv_keys)}
         if self.fused and getattr(self.engine, "joined", False):
             out.update(self.engine.counter.shard_stats())
