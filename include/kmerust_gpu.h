@@ -209,6 +209,17 @@ kmg_status kmg_export_shard_device(kmg_ctx *ctx, uint64_t min_count, int sorted,
 kmg_status kmg_histogram(kmg_ctx *ctx, uint64_t min_count, uint64_t *count_vals, uint64_t *freqs,
                          uint64_t cap, uint64_t *n_out);
 
+/* Replaces the fasta / tsv text emitters of output_counts and count_to_writer (src/run.rs:452-470, src/builder.rs:399-442) and
+ * unpack_to_string (src/kmer.rs:431-456): entries with count >= min_count (0 behaves as 1) in ascending k-mer order -- the
+ * reference prints HashMap iteration order, parity is defined on the sorted text -- formatted on the device
+ * (tsv "{kmer}\t{count}\n", fasta ">{count}\n{kmer}\n") and delivered to `sink` in chunks of at most 64 MiB; a non-zero
+ * return from the sink aborts with KMG_ERR_IO.  kmg_write_text writes the same bytes to a file ("-" = stdout). */
+enum { KMG_TEXT_FASTA = 0, KMG_TEXT_TSV = 1 };
+typedef int (*kmg_text_sink)(void *user, const uint8_t *bytes, size_t n);
+kmg_status kmg_emit_text(kmg_ctx *ctx, uint64_t min_count, int format, kmg_text_sink sink, void *user, uint64_t *n_records_out,
+                         uint64_t *n_bytes_out);
+kmg_status kmg_write_text(kmg_ctx *ctx, uint64_t min_count, int format, const char *path, uint64_t *n_records_out, uint64_t *n_bytes_out);
+
 /* Replaces counts_to_packed + KmerIndex::new + save_index (src/main.rs:155-202, :284-299,
  * src/index.rs:156-196, :222-279).  Writes ALL k-mers (the index is never min-count filtered). */
 kmg_status kmg_save_kmix(kmg_ctx *ctx, const char *path);

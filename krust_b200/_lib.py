@@ -12,6 +12,8 @@ KMG_ABI_VERSION = 1
 KMG_OK, KMG_ERR_INVALID_K, KMG_ERR_INVALID_ARG, KMG_ERR_CUDA, KMG_ERR_OOM, KMG_ERR_TABLE_FULL, KMG_ERR_STATE, \
     KMG_ERR_IO, KMG_ERR_ABI, KMG_ERR_CAPACITY, KMG_ERR_PARSE = range(11)
 KMG_FLAG_FORCE_HASH, KMG_FLAG_FORCE_DIRECT, KMG_FLAG_NO_PREAGG, KMG_FLAG_FORCE_PARTITIONED = 1, 2, 4, 8
+KMG_TEXT_FASTA, KMG_TEXT_TSV = 0, 1
+TEXT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t)
 
 
 class KmgConfig(C.Structure):
@@ -66,6 +68,8 @@ SIGNATURES = {
     "kmg_export_shard_device": (i32, [vp, u64, i32, u64, u64, vp, vp, u64, C.POINTER(u64)]),
     "kmg_histogram": (i32, [vp, u64, vp, vp, u64, C.POINTER(u64)]),
     "kmg_save_kmix": (i32, [vp, C.c_char_p]),
+    "kmg_emit_text": (i32, [vp, u64, i32, vp, vp, C.POINTER(u64), C.POINTER(u64)]),
+    "kmg_write_text": (i32, [vp, u64, i32, C.c_char_p, C.POINTER(u64), C.POINTER(u64)]),
     "kmg_kmix_begin": (i32, [C.c_char_p]),
     "kmg_save_kmix_shard": (i32, [vp, C.c_char_p, u64, C.POINTER(u64), C.POINTER(u32)]),
     "kmg_kmix_finish": (i32, [C.c_char_p, u32, vp, vp, u32]),

@@ -374,6 +374,29 @@ class GpuKmerCounter:
                    self._ctx)
         return vals, freqs
 
+    def emit_text(self, writer: IO[bytes], fmt: str = "tsv", min_count: int = 1) -> Tuple[int, int]:
+        """kmg_emit_text: sorted fasta / tsv lines formatted on the device, written to `writer` chunk by chunk.
+        Returns (records, bytes)."""
+        code = {"fasta": _lib.KMG_TEXT_FASTA, "tsv": _lib.KMG_TEXT_TSV}[fmt]
+
+        def sink(_user, ptr, n):
+            try:
+                writer.write(C.string_at(ptr, n))
+                return 0
+            except Exception:  # noqa: BLE001 -- reported through the status code
+                return 1
+
+        cb = _lib.TEXT_SINK(sink)
+        n_rec, n_bytes = C.c_uint64(0), C.c_uint64(0)
+        _check(self._L.kmg_emit_text(self._ctx, min_count, code, cb, None, C.byref(n_rec), C.byref(n_bytes)), self._ctx)
+        return n_rec.value, n_bytes.value
+
+    def write_text(self, path, fmt: str = "tsv", min_count: int = 1) -> Tuple[int, int]:
+        code = {"fasta": _lib.KMG_TEXT_FASTA, "tsv": _lib.KMG_TEXT_TSV}[fmt]
+        n_rec, n_bytes = C.c_uint64(0), C.c_uint64(0)
+        _check(self._L.kmg_write_text(self._ctx, min_count, code, os.fspath(path).encode(), C.byref(n_rec), C.byref(n_bytes)), self._ctx)
+        return n_rec.value, n_bytes.value
+
     def save_kmix(self, path):
         _check(self._L.kmg_save_kmix(self._ctx, os.fspath(path).encode()), self._ctx)
 
@@ -584,9 +607,21 @@ class KmerCounter:
         return _stringify(keys, counts, self._need_k().get())
 
     def count_to_writer(self, path, writer: IO[bytes]):
-        """src/builder.rs:399-442."""
-        keys, counts = self.count_packed(path)
-        write_counts(writer, keys, counts, self._need_k().get(), self._format)
+        """src/builder.rs:399-442.  fasta / tsv lines are formatted on the GPU (kmg_emit_text), sorted by k-mer; histogram comes
+        from kmg_histogram; json (host formatting, SURVEY.md out of scope) goes through write_counts."""
+        k = self._need_k()
+        seq, qual, offsets = read_records(path, self._input_format)
+        with GpuKmerCounter(k, min_quality=self._min_quality) as c:
+            c.count_batch(seq, qual, offsets)
+            c.finalize(False)
+            if self._format in (OutputFormat.FASTA, OutputFormat.TSV):
+                c.emit_text(writer, self._format, self._min_count)
+            elif self._format == OutputFormat.HISTOGRAM:
+                vals, freqs = c.histogram(self._min_count)
+                writer.write(b"".join(b"%d\t%d\n" % (int(v), int(f)) for v, f in zip(vals, freqs)))
+            else:
+                keys, counts = c.export(self._min_count, sorted=True)
+                write_counts(writer, keys, counts, k.get(), self._format)
 
     def run(self, path):
         """src/builder.rs:366-375 -- to stdout."""

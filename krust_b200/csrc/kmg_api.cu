@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -116,6 +117,7 @@ struct kmg_ctx {
   bool sh_peer_ipc[8] = {false, false, false, false, false, false, false, false};
   uint64_t sh_sent = 0, sh_recv_keys = 0, sh_rounds = 0, sh_exact_rounds = 0;
   std::vector<uint64_t> sh_hist_vals, sh_hist_freqs;  // merged histogram of the last kmg_shard_histogram
+  double dedup_ratio = 1.0;  // distinct keys per raw entry seen by the last consolidation (sizes the next consolidated run)
   double plan_scale = 1.0;  // kmg_count_ascii with a quality filter: (bases of the whole call) / (bases of its first chunk)
   int building_run = 0;  // > 0 while refine_to_run derives a run from the current plan: a nested consolidate must not re-split
   // count-of-counts of `result`, produced by phase B itself (consolidate)
@@ -366,7 +368,7 @@ kmg_status decide_mode(kmg_ctx *c, uint64_t first_call_windows) {
   return init_partitioned(c);
 }
 
-kmg_status consolidate(kmg_ctx *c);
+kmg_status consolidate(kmg_ctx *c, bool recompact = false);
 
 kmg_status add_run(kmg_ctx *c, Run &&r) {
   if (r.n == 0) { free_run(c, r); return KMG_OK; }
@@ -375,7 +377,7 @@ kmg_status add_run(kmg_ctx *c, Run &&r) {
   if (!c->total_mem) { size_t free_b = 0; cudaMemGetInfo(&free_b, &c->total_mem); }
   const size_t total_b = c->total_mem;
   // consolidate early when the pending runs get numerous or large (keeps streaming inputs bounded in memory)
-  if (c->runs.size() + (c->has_result ? 1 : 0) >= (size_t)CONS_MAX_RUNS - 1 || c->pending_bytes > (uint64_t)total_b * 35 / 100)
+  if (c->runs.size() + (c->has_result ? 1 : 0) >= (size_t)CONS_MAX_RUNS - 1 || c->pending_bytes > (uint64_t)total_b * 20 / 100)
     return consolidate(c);
   return KMG_OK;
 }
@@ -646,8 +648,10 @@ kmg_status resplit_runs(kmg_ctx *c, uint32_t m) {
 }
 
 // phase B: merge the consolidated result (if any) and all pending runs into a new consolidated run
-kmg_status consolidate(kmg_ctx *c) {
-  if (c->runs.empty()) return KMG_OK;
+// recompact: rewrite the consolidated result alone (its entries are mostly skipped fillers after a direct-emit launch on
+// duplicate-rich input) with the compacting kernel
+kmg_status consolidate(kmg_ctx *c, bool recompact) {
+  if (c->runs.empty() && !(recompact && c->has_result && c->result.n)) return KMG_OK;
   {  // partitions several times larger than planned: refine the plan before counting
     uint64_t entries = c->has_result ? c->result.n_valid : 0;
     for (auto &r : c->runs) entries += r.n;
@@ -707,14 +711,46 @@ kmg_status consolidate(kmg_ctx *c) {
   pool_free(c, d_totals);
   prm.order = d_order;
 
+  // The output run holds one entry per DISTINCT key.  `total` (one per input entry) is always enough, but read sets repeat every
+  // k-mer many times (C5: 26 G windows, 2.4 G distinct) and a run sized for the input would not fit next to the inputs.  So the
+  // run is sized from the dedup ratio the previous consolidation observed (1.0 at first), and a launch that runs out of space
+  // (nospace flag, nothing written past the capacity) is repeated with whatever memory allows.
   Run out;
-  if (e == cudaSuccess) e = pool_alloc(c, &out.d_keys, std::max<uint64_t>(total, 1) * 8);
-  if (e == cudaSuccess) e = pool_alloc(c, &out.d_counts, std::max<uint64_t>(total, 1) * 8);
+  uint64_t raw_entries = 0;
+  for (auto *r : in) if (!r->d_counts) raw_entries += r->n;
+  // Direct emit (count_partitions_smem_kernel<false, true>): only unweighted runs of keys that are mostly distinct (a genome, not a
+  // deep read set), partitions within the plan.  Its output holds one entry per input entry.
+  static const bool no_direct = getenv("KMG_NO_DIRECT") != nullptr;  // ablation
+  bool direct = !no_direct && !recompact && raw_entries == total && c->dedup_ratio >= 0.5 && max_total <= 0xffffu &&
+                total / std::max<uint32_t>(P, 1) <= SMEM_TABLE_SLOTS / 2 && !(c->cfg.flags & KMG_FLAG_NO_PREAGG);
+  uint64_t out_cap = std::max<uint64_t>(total, 1);
+  if (recompact) out_cap = std::min<uint64_t>(out_cap, c->result.n_valid + (1ull << 20));
+  else if (total > (1ull << 28) && !direct) {
+    const uint64_t est = (total - raw_entries) + (uint64_t)((double)raw_entries * std::min(1.0, c->dedup_ratio * 1.25 + 0.02)) + (1ull << 24);
+    out_cap = std::min(out_cap, est);
+  }
+  auto alloc_out = [&](uint64_t cap) -> cudaError_t {
+    cudaError_t ae = pool_alloc(c, &out.d_keys, cap * 8);
+    if (ae == cudaSuccess) ae = pool_alloc(c, &out.d_counts, cap * 8);
+    if (ae != cudaSuccess) { pool_free(c, out.d_keys); pool_free(c, out.d_counts); out.d_keys = out.d_counts = nullptr; cudaGetLastError(); }
+    return ae;
+  };
+  if (e == cudaSuccess) {
+    e = alloc_out(out_cap);
+    if (e != cudaSuccess && out_cap > (1ull << 26)) {  // not even the estimate fits: take what is there
+      size_t free_b = 0, total_b = 0;
+      pool_release_idle(c);
+      cudaMemGetInfo(&free_b, &total_b);
+      const uint64_t room = free_b > (3ull << 30) ? (free_b - (2ull << 30)) / 16 : 0;
+      if (room >= (1ull << 26)) { out_cap = std::min(out_cap, room); e = alloc_out(out_cap); }
+    }
+  }
   if (e == cudaSuccess) e = pool_alloc(c, &out.d_seg_start, (size_t)P * 8);
   if (e == cudaSuccess) e = pool_alloc(c, &out.d_seg_len, (size_t)P * 8);
   if (e != cudaSuccess) { pool_free(c, d_order); free_run(c, out); return cuda_fail(c, e, "cudaMalloc(consolidated run)"); }
   prm.out_keys = out.d_keys; prm.out_counts = out.d_counts;
   prm.out_seg_start = out.d_seg_start; prm.out_seg_len = out.d_seg_len;
+  prm.out_cap = out_cap;
 
   if (!c->d_hist) {
     e = cudaMalloc(&c->d_hist, (HIST_DENSE_BINS + 1) * sizeof(unsigned long long));
@@ -739,10 +775,10 @@ kmg_status consolidate(kmg_ctx *c) {
   for (int attempt = 0;; ++attempt) {
     const bool use_smem = smem_attempts < 3 && split_log2 <= 8;
     uint64_t *d_scratch = nullptr;
-    unsigned long long *d_sync = nullptr;  // [0] out_cursor, [1] next (u32) | error (u32), [2] distinct keys
+    unsigned long long *d_sync = nullptr;  // [0] out_cursor, [1] next (u32) | error (u32), [2] distinct keys, [3] no-space flag (u32)
     const uint64_t slots = use_smem ? 0 : (uint64_t)grid << c->scratch_log2;
     prm.split_log2 = split_log2;
-    e = pool_alloc(c, &d_sync, 24);
+    e = pool_alloc(c, &d_sync, 32);
     if (e == cudaSuccess && slots) e = pool_alloc(c, &d_scratch, slots * 16);
     if (e != cudaSuccess) { pool_free(c, d_scratch); pool_free(c, d_sync); st = cuda_fail(c, e, "cudaMalloc(count scratch)"); break; }
     prm.scratch = d_scratch; prm.scratch_log2 = c->scratch_log2;
@@ -750,21 +786,37 @@ kmg_status consolidate(kmg_ctx *c) {
     prm.out_distinct = d_sync + 2;
     prm.next = reinterpret_cast<uint32_t *>(d_sync + 1);
     prm.error_flag = reinterpret_cast<uint32_t *>(d_sync + 1) + 1;
-    e = cudaMemsetAsync(d_sync, 0, 24, c->stream);
+    prm.nospace_flag = reinterpret_cast<uint32_t *>(d_sync + 3);
+    e = cudaMemsetAsync(d_sync, 0, 32, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_hist, 0, (HIST_DENSE_BINS + 1) * sizeof(unsigned long long), c->stream);
     if (e == cudaSuccess && slots) e = launch_table_init(HashTable{d_scratch, slots}, c->stream, EMPTY_MIX);
     const size_t tmr = timer_begin(c, 1);
     bool weighted = max_total > ((2ull * SMEM_COUNT_THREADS * 8) << split_log2);  // partitions oversized beyond the split want the pre-aggregating variant
     for (uint32_t r = 0; r < R; ++r) weighted |= in[r]->d_counts != nullptr;
-    if (e == cudaSuccess) e = use_smem ? launch_count_partitions_smem(prm, weighted, c->stream) : launch_count_partitions(prm, grid, c->stream);
+    if (weighted || split_log2 || !use_smem) direct = false;
+    if (e == cudaSuccess) e = use_smem ? launch_count_partitions_smem(prm, weighted, direct, c->stream) : launch_count_partitions(prm, grid, c->stream);
     timer_end(c, tmr);
-    unsigned long long h_sync[3] = {0, 0, 0};
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 24, cudaMemcpyDeviceToHost, c->stream);
+    unsigned long long h_sync[4] = {0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 32, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     pool_free(c, d_scratch); pool_free(c, d_sync);
     if (e != cudaSuccess) { st = cuda_fail(c, e, "count_partitions"); break; }
+    if ((uint32_t)h_sync[3] && !(h_sync[1] >> 32)) {  // the run was too small for the distinct keys: enlarge it and repeat
+      const uint64_t need = std::min<uint64_t>(total, h_sync[0] + (1ull << 20));  // out_cursor kept counting: the exact demand (plus filler entries)
+      if (out_cap >= total || attempt >= 16) { st = fail(c, KMG_ERR_OOM, "the consolidated run does not fit in device memory"); break; }
+      pool_free(c, out.d_keys); pool_free(c, out.d_counts); out.d_keys = out.d_counts = nullptr;
+      out_cap = need;
+      if (alloc_out(out_cap) != cudaSuccess) {
+        pool_release_idle(c);
+        if (alloc_out(out_cap) != cudaSuccess) { st = fail(c, KMG_ERR_OOM, "the consolidated run (" + std::to_string(need) + " entries) does not fit in device memory"); break; }
+      }
+      prm.out_keys = out.d_keys; prm.out_counts = out.d_counts; prm.out_cap = out_cap;
+      c->dedup_ratio = 1.0;
+      continue;
+    }
     n_out = h_sync[0]; n_valid = h_sync[2];
     if (!(h_sync[1] >> 32)) break;  // no overflow
+    if (direct) { direct = false; continue; }  // a partition beyond the direct variant's limits: the compacting variant takes the launch
     if (attempt >= 16 || c->scratch_log2 >= 30) { st = fail(c, KMG_ERR_TABLE_FULL, "partition table overflow could not be resolved"); break; }
     if (use_smem) {  // finer split first (weights beyond 32 bits are not cured by it: the L2 variant follows after three tries)
       ++smem_attempts;
@@ -775,6 +827,10 @@ kmg_status consolidate(kmg_ctx *c) {
   pool_free(c, d_order);
   if (st != KMG_OK) { free_run(c, out); return st; }
   out.n = n_out; out.n_valid = n_valid;
+  if (raw_entries > (1ull << 24)) {  // distinct keys the raw runs added per raw entry (an upper estimate: keys already in the result count as new)
+    const uint64_t before = total - raw_entries;
+    c->dedup_ratio = std::min(1.0, (double)(n_valid > before / 2 ? n_valid - before / 2 : 0) / (double)raw_entries);
+  }
   if (c->has_result) free_run(c, c->result);
   for (auto &r : c->runs) free_run(c, r);
   c->runs.clear();
@@ -794,6 +850,13 @@ kmg_status consolidate(kmg_ctx *c) {
   c->has_result = true;
   c->fused_valid = true;
   c->n_consolidations++;
+  if (direct && c->result.n > (1ull << 20) && c->result.n_valid < c->result.n / 2) {
+    // duplicate-rich input went through the direct variant (nothing was known about it yet): most entries are fillers.
+    // Rewrite the run compactly once; dedup_ratio now steers later consolidations to the compacting variant.
+    kmg_status rs = consolidate(c, /*recompact=*/true);
+    if (rs != KMG_OK) return rs;
+    c->n_consolidations--;
+  }
   return KMG_OK;
 }
 
@@ -1119,7 +1182,7 @@ KMG_EXPORT kmg_status kmg_reset(kmg_ctx *c) {
     for (auto &r : c->runs) free_run(c, r);
     c->runs.clear();
     if (c->has_result) free_run(c, c->result);
-    c->has_result = false; c->pending_bytes = 0; c->n_consolidations = 0;
+    c->has_result = false; c->pending_bytes = 0; c->n_consolidations = 0; c->dedup_ratio = 1.0;
     c->fused_valid = c->fused_cached = false;
   }
   CU(c, cudaMemsetAsync(c->d_counters, 0, CTR_N * sizeof(unsigned long long), c->stream));
@@ -2033,66 +2096,132 @@ uint32_t crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) {
   return crc1 ^ crc2;
 }
 
-// Stream all (key, count) records of the context to `f` in ascending key order WITHOUT a second copy of the table: the
-// key space is cut into ranges of at most ~2^25 entries (from a histogram over the top key bits), each range is compacted,
-// sorted and written on its own.  *crc is the finished CRC-32 of the bytes written here (standard init / xor-out).
+// CRC-32 of a large buffer on all host cores: the parts' CRCs are combined (a single core manages ~2 GB/s, an index is tens of GB)
+uint32_t crc32_parallel(const uint8_t *p, size_t n) {
+  const Crc32 &T = crc_tables();
+  unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+  if (n < (8u << 20) || nt == 1) return ~T.update(~0u, p, n);
+  const size_t per = (n + nt - 1) / nt;
+  std::vector<uint32_t> part(nt, 0);
+  std::vector<size_t> len(nt, 0);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t) {
+    const size_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+    len[t] = hi - lo;
+    th.emplace_back([&, t, lo, hi] { part[t] = ~T.update(~0u, p + lo, hi - lo); });
+  }
+  for (auto &x : th) x.join();
+  uint32_t crc = part[0];
+  for (unsigned t = 1; t < nt; ++t) crc = crc32_combine(crc, part[t], len[t]);
+  return crc;
+}
+
+// Walk the table in ascending key order WITHOUT a second copy of it: the key space is cut into ranges of at most ~piece_target
+// entries (from a histogram over the top key bits); each range is compacted (count >= min_count), sorted, and handed to
+// fn(d_keys, d_counts, m).  The pieces concatenate to the sorted result.
+template <class F>
+kmg_status for_each_sorted_piece(kmg_ctx *c, uint64_t min_count, uint64_t piece_target, F &&fn) {
+  uint64_t n_all = 0;
+  kmg_status s = count_filtered(c, 0, &n_all);
+  if (s != KMG_OK || n_all == 0) return s;
+  const int shift = 2 * c->k > 12 ? 2 * c->k - 12 : 0;
+  unsigned long long *d_b = nullptr;
+  CU(c, pool_alloc(c, &d_b, KEY_BUCKETS * 8));
+  std::vector<unsigned long long> hb(KEY_BUCKETS);
+  cudaError_t e = launch_key_buckets(view_of(c), shift, d_b, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hb.data(), d_b, KEY_BUCKETS * 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  pool_free(c, d_b);
+  if (e != cudaSuccess) return cuda_fail(c, e, "key histogram");
+  uint64_t piece_cap = std::min<uint64_t>(n_all, piece_target);
+  for (auto v : hb) piece_cap = std::max<uint64_t>(piece_cap, v);
+  uint64_t *dk = nullptr, *dc = nullptr;
+  CU(c, pool_alloc(c, &dk, piece_cap * 8));
+  e = pool_alloc(c, &dc, piece_cap * 8);
+  if (e != cudaSuccess) { pool_free(c, dk); return cuda_fail(c, e, "cudaMalloc(sorted piece)"); }
+  for (int b0 = 0; s == KMG_OK && b0 < KEY_BUCKETS;) {
+    uint64_t ub = hb[b0];
+    int b1 = b0 + 1;
+    while (b1 < KEY_BUCKETS && ub + hb[b1] <= piece_cap) ub += hb[b1++];
+    if (ub) {
+      TableView v = view_of(c);
+      v.range_lo = (uint64_t)b0 << shift;
+      v.range_hi = b1 == KEY_BUCKETS ? ~0ull : ((uint64_t)b1 << shift) - 1;
+      unsigned long long m = 0;
+      e = launch_compact(v, min_count, dk, dc, piece_cap, c->d_stats + 3, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&m, c->d_stats + 3, 8, cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      if (e == cudaSuccess && m > piece_cap) { s = fail(c, KMG_ERR_STATE, "sorted piece larger than its key histogram"); break; }
+      if (e == cudaSuccess && m) e = sort_pairs(dk, dc, m, 2 * c->k, c->stream);
+      if (e != cudaSuccess) { s = cuda_fail(c, e, "sorted piece"); break; }
+      if (m) s = fn(dk, dc, (uint64_t)m);
+    }
+    b0 = b1;
+  }
+  pool_free(c, dk); pool_free(c, dc);
+  return s;
+}
+
+// Device bytes -> sink through two pinned staging buffers (the copy of chunk i+1 overlaps the sink of chunk i).
+struct HostStager {
+  kmg_ctx *c;
+  uint8_t *h[2] = {nullptr, nullptr};
+  size_t cap = 0;
+  explicit HostStager(kmg_ctx *c_, size_t cap_) : c(c_), cap(cap_) {}
+  ~HostStager() { for (auto *p : h) if (p) cudaFreeHost(p); }
+  template <class Sink>
+  kmg_status drain(const uint8_t *d_src, size_t n, Sink &&sink) {
+    for (int i = 0; i < 2; ++i)
+      if (!h[i] && cudaHostAlloc(&h[i], cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(c, KMG_ERR_OOM, "pinned staging buffer"); }
+    size_t issued = 0;
+    int slot = 0;
+    size_t len_prev = 0;
+    if (n) { len_prev = std::min(cap, n); CU(c, cudaMemcpyAsync(h[0], d_src, len_prev, cudaMemcpyDeviceToHost, c->stream)); issued = len_prev; }
+    while (len_prev) {
+      CU(c, cudaStreamSynchronize(c->stream));
+      const size_t len_next = std::min(cap, n - issued);
+      if (len_next) { CU(c, cudaMemcpyAsync(h[slot ^ 1], d_src + issued, len_next, cudaMemcpyDeviceToHost, c->stream)); issued += len_next; }
+      kmg_status s = sink(h[slot], len_prev);
+      if (s != KMG_OK) { cudaStreamSynchronize(c->stream); return s; }
+      slot ^= 1; len_prev = len_next;
+    }
+    return KMG_OK;
+  }
+};
+
+// Stream all (key, count) records of the context to `f` in ascending key order (16-byte records interleaved on the device).
+// *crc_out is the finished CRC-32 of the bytes written here (standard init / xor-out).
 kmg_status write_kmix_records(kmg_ctx *c, FILE *f, uint32_t *crc_out, uint64_t *n_out) {
   uint64_t n = 0;
   kmg_status s = count_filtered(c, 0, &n);
   if (s != KMG_OK) return s;
   *n_out = n;
-  const Crc32 &T = crc_tables();
-  uint32_t crc = ~0u;
-  if (n) {
-    const int shift = 2 * c->k > 12 ? 2 * c->k - 12 : 0;
-    unsigned long long *d_b = nullptr;
-    CU(c, pool_alloc(c, &d_b, KEY_BUCKETS * 8));
-    std::vector<unsigned long long> hb(KEY_BUCKETS);
-    cudaError_t e = launch_key_buckets(view_of(c), shift, d_b, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(hb.data(), d_b, KEY_BUCKETS * 8, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    pool_free(c, d_b);
-    if (e != cudaSuccess) return cuda_fail(c, e, "kmix key histogram");
-    uint64_t piece_cap = std::min<uint64_t>(n, 1ull << 25);
-    for (auto v : hb) piece_cap = std::max<uint64_t>(piece_cap, v);
-    uint64_t *dk = nullptr, *dc = nullptr;
-    CU(c, pool_alloc(c, &dk, piece_cap * 8));
-    e = pool_alloc(c, &dc, piece_cap * 8);
-    if (e != cudaSuccess) { pool_free(c, dk); return cuda_fail(c, e, "cudaMalloc(kmix piece)"); }
-    const uint64_t CH = 1ull << 20;
-    std::vector<uint64_t> hk(CH), hc(CH), pairs(2 * CH);
-    bool ok = true;
-    uint64_t written = 0;
-    for (int b0 = 0; ok && b0 < KEY_BUCKETS;) {
-      uint64_t m = hb[b0];
-      int b1 = b0 + 1;
-      while (b1 < KEY_BUCKETS && m + hb[b1] <= piece_cap) m += hb[b1++];
-      if (m) {
-        TableView v = view_of(c);
-        v.range_lo = (uint64_t)b0 << shift;
-        v.range_hi = b1 == KEY_BUCKETS ? ~0ull : ((uint64_t)b1 << shift) - 1;
-        e = launch_compact(v, 0, dk, dc, piece_cap, c->d_stats + 3, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e == cudaSuccess) e = sort_pairs(dk, dc, m, 2 * c->k, c->stream);
-        for (uint64_t i = 0; e == cudaSuccess && ok && i < m; i += CH) {
-          const uint64_t mm = std::min(CH, m - i);
-          e = cudaMemcpy(hk.data(), dk + i, mm * 8, cudaMemcpyDeviceToHost);
-          if (e == cudaSuccess) e = cudaMemcpy(hc.data(), dc + i, mm * 8, cudaMemcpyDeviceToHost);
-          if (e != cudaSuccess) break;
-          for (uint64_t j = 0; j < mm; ++j) { pairs[2 * j] = hk[j]; pairs[2 * j + 1] = hc[j]; }  // x86-64 / aarch64: little endian
-          ok = fwrite(pairs.data(), 16, mm, f) == mm;
-          crc = T.update(crc, reinterpret_cast<const uint8_t *>(pairs.data()), mm * 16);
-        }
-        if (e != cudaSuccess) { pool_free(c, dk); pool_free(c, dc); return cuda_fail(c, e, "kmix piece"); }
-        written += m;
-      }
-      b0 = b1;
+  uint32_t crc = 0;  // CRC of the empty string
+  uint64_t written = 0;
+  bool first = true;
+  HostStager stage(c, 64u << 20);
+  void *d_pairs = nullptr;
+  uint64_t pairs_cap = 0;
+  s = for_each_sorted_piece(c, 0, 1ull << 25, [&](const uint64_t *dk, const uint64_t *dc, uint64_t m) -> kmg_status {
+    if (m > pairs_cap) {
+      pool_free(c, d_pairs); d_pairs = nullptr;
+      pairs_cap = std::max<uint64_t>(m, std::min<uint64_t>(n, 1ull << 25));
+      CU(c, pool_alloc(c, &d_pairs, pairs_cap * 16));
     }
-    pool_free(c, dk); pool_free(c, dc);
-    if (!ok) return fail(c, KMG_ERR_IO, "short write to the index file");
-    if (written != n) return fail(c, KMG_ERR_STATE, "kmix writer: pieces do not add up to the table");
-  }
-  *crc_out = ~crc;
+    CU(c, launch_interleave_pairs(dk, dc, m, d_pairs, c->stream));
+    written += m;
+    return stage.drain(static_cast<const uint8_t *>(d_pairs), m * 16, [&](const uint8_t *p, size_t len) -> kmg_status {
+      if (fwrite(p, 1, len, f) != len) return fail(c, KMG_ERR_IO, "short write to the index file");
+      const uint32_t part = crc32_parallel(p, len);
+      crc = first ? part : crc32_combine(crc, part, len);
+      first = false;
+      return KMG_OK;
+    });
+  });
+  pool_free(c, d_pairs);
+  if (s != KMG_OK) return s;
+  if (written != n) return fail(c, KMG_ERR_STATE, "kmix writer: pieces do not add up to the table");
+  *crc_out = crc;
   return KMG_OK;
 }
 
@@ -2282,6 +2411,66 @@ KMG_EXPORT kmg_status kmg_shard_stats(const kmg_ctx *c, uint64_t *sent_keys, uin
   if (rounds) *rounds = c->sh_rounds;
   if (exact_rounds) *exact_rounds = c->sh_exact_rounds;
   return KMG_OK;
+}
+
+
+// Text emitters of output_counts / count_to_writer (src/run.rs:452-470, src/builder.rs:399-442) for --format tsv and fasta:
+// records with count >= min_count in ascending k-mer order (the reference prints HashMap order; parity is on the sorted text),
+// formatted ON THE DEVICE (2-bit unpack + decimal count), delivered to `sink` in chunks of at most 64 MiB.
+KMG_EXPORT kmg_status kmg_emit_text(kmg_ctx *c, uint64_t min_count, int format, kmg_text_sink sink, void *user, uint64_t *n_records_out,
+                                    uint64_t *n_bytes_out) {
+  if (!c || !sink) return KMG_ERR_INVALID_ARG;
+  if (format != KMG_TEXT_FASTA && format != KMG_TEXT_TSV) return fail(c, KMG_ERR_INVALID_ARG, "format must be KMG_TEXT_FASTA or KMG_TEXT_TSV");
+  CU(c, cudaSetDevice(c->device));
+  if (min_count == 0) min_count = 1;
+  const int fasta = format == KMG_TEXT_FASTA;
+  uint64_t records = 0, bytes = 0;
+  HostStager stage(c, 64u << 20);
+  uint64_t *d_off = nullptr;
+  uint8_t *d_text = nullptr;
+  uint64_t off_cap = 0, text_cap = 0;
+  kmg_status s = for_each_sorted_piece(c, min_count, 1ull << 24, [&](const uint64_t *dk, const uint64_t *dc, uint64_t m) -> kmg_status {
+    if (m + 1 > off_cap) { pool_free(c, d_off); d_off = nullptr; off_cap = std::max<uint64_t>(m + 1, 1ull << 20); CU(c, pool_alloc(c, &d_off, off_cap * 8)); }
+    CU(c, launch_text_len(dc, m, c->k, fasta, d_off, c->stream));
+    CU(c, cudaMemsetAsync(d_off + m, 0, 8, c->stream));
+    if (!c->d_scan_tmp || c->scan_tmp_items < m + 1) {
+      CU(c, cudaStreamSynchronize(c->stream));
+      cudaFree(c->d_scan_tmp); c->d_scan_tmp = nullptr;
+      CU(c, exclusive_sum_u64(nullptr, nullptr, m + 1, nullptr, &c->scan_tmp_bytes, c->stream));
+      CU(c, cudaMalloc(&c->d_scan_tmp, c->scan_tmp_bytes ? c->scan_tmp_bytes : 16));
+      c->scan_tmp_items = m + 1;
+    }
+    CU(c, exclusive_sum_u64(d_off, d_off, m + 1, c->d_scan_tmp, &c->scan_tmp_bytes, c->stream));  // entry m = bytes of the piece
+    uint64_t total = 0;
+    CU(c, cudaMemcpyAsync(&total, d_off + m, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (total > text_cap) { pool_free(c, d_text); d_text = nullptr; text_cap = total + total / 8; CU(c, pool_alloc(c, &d_text, text_cap)); }
+    CU(c, launch_text_write(dk, dc, d_off, m, c->k, fasta, d_text, c->stream));
+    records += m; bytes += total;
+    return stage.drain(d_text, total, [&](const uint8_t *p, size_t len) -> kmg_status {
+      return sink(user, p, len) == 0 ? KMG_OK : fail(c, KMG_ERR_IO, "the text sink reported an error");
+    });
+  });
+  pool_free(c, d_off); pool_free(c, d_text);
+  if (n_records_out) *n_records_out = records;
+  if (n_bytes_out) *n_bytes_out = bytes;
+  return s;
+}
+
+namespace {
+int file_sink(void *user, const uint8_t *p, size_t n) { return fwrite(p, 1, n, static_cast<FILE *>(user)) == n ? 0 : 1; }
+}  // namespace
+
+// The same into a file ("-" = stdout): what `kmerust <k> <path> --format tsv|fasta --min-count m > file` produces, sorted.
+KMG_EXPORT kmg_status kmg_write_text(kmg_ctx *c, uint64_t min_count, int format, const char *path, uint64_t *n_records_out, uint64_t *n_bytes_out) {
+  if (!c || !path) return KMG_ERR_INVALID_ARG;
+  const bool to_stdout = strcmp(path, "-") == 0;
+  FILE *f = to_stdout ? stdout : fopen(path, "wb");
+  if (!f) return fail(c, KMG_ERR_IO, std::string("cannot open ") + path + " for writing");
+  kmg_status s = kmg_emit_text(c, min_count, format, file_sink, f, n_records_out, n_bytes_out);
+  const bool ok = to_stdout ? fflush(f) == 0 : fclose(f) == 0;
+  if (s == KMG_OK && !ok) return fail(c, KMG_ERR_IO, std::string("short write to ") + path);
+  return s;
 }
 
 KMG_EXPORT kmg_status kmg_progress(const kmg_ctx *c, uint64_t *records, uint64_t *bases) {

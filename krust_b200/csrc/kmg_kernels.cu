@@ -738,7 +738,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) partition_scatter_staged_ker
 constexpr int ROWS_THREADS = 1024;
 constexpr int ROWS_SUB_WORDS = ROWS_THREADS / 4;   // 8192 windows per sub-tile
 constexpr int ROWS_SLOTS = 16384;                  // n_parts rows of 2^cl keys (128 KiB; also the staging buffer of the exact route)
-constexpr int ROWS_OVERFLOW = 512;
+constexpr int ROWS_OVERFLOW = 1536;   // keys whose row was full (repeat-rich reads put ~200 per sub-tile there; beyond it the sub-tile takes the exact route)
 template <bool MIXED>
 struct RowsEmit {
   uint32_t *cnt;
@@ -972,6 +972,38 @@ __global__ void __launch_bounds__(256) key_buckets_kernel(TableView v, int shift
     if (sh[b]) atomicAdd(buckets + b, (unsigned long long)sh[b]);
 }
 
+// ---- output formatting on the device (replaces the per-k-mer writeln! of src/run.rs:452-470 / src/builder.rs:406-429 and
+// unpack_to_string, src/kmer.rs:431-456): record i of a sorted piece becomes "{kmer}\t{count}\n" (tsv) or ">{count}\n{kmer}\n" (fasta)
+__device__ __forceinline__ uint32_t dec_digits(uint64_t v) {
+  uint32_t d = 1;
+  while (v >= 10) { v /= 10; ++d; }
+  return d;
+}
+__global__ void text_len_kernel(const uint64_t *__restrict__ counts, uint64_t n, int k, int fasta, uint64_t *__restrict__ lens) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    lens[i] = (uint64_t)k + dec_digits(counts[i]) + (fasta ? 3u : 2u);
+}
+__global__ void text_write_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ counts, const uint64_t *__restrict__ offs,
+                                  uint64_t n, int k, int fasta, uint8_t *__restrict__ out) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = keys[i];
+    uint64_t cnt = counts[i];
+    uint8_t *p = out + offs[i];
+    const uint32_t nd = dec_digits(cnt);
+    uint8_t *num = fasta ? p + 1 : p + k + 1;       // where the decimal count goes
+    uint8_t *mer = fasta ? p + 1 + nd + 1 : p;      // where the k-mer goes
+    if (fasta) { p[0] = '>'; p[1 + nd] = '\n'; p[1 + nd + 1 + k] = '\n'; }
+    else { p[k] = '\t'; p[k + 1 + nd] = '\n'; }
+    for (int d = (int)nd - 1; d >= 0; --d) { num[d] = (uint8_t)('0' + cnt % 10); cnt /= 10; }
+    for (int j = 0; j < k; ++j) mer[j] = "ACGT"[(key >> (2 * (k - 1 - j))) & 3];  // base j = (bits >> 2(k-1-j)) & 3 (src/kmer.rs:431-440)
+  }
+}
+// (key, count) SoA -> the 16-byte little-endian records of the .kmix DATA section (src/index.rs:7-23)
+__global__ void interleave_pairs_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ counts, uint64_t n, ulonglong2 *__restrict__ out) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = make_ulonglong2(keys[i], counts[i]);
+}
+
 // K6: count-of-counts.  Counts below HIST_DENSE_BINS go to dense bins (the first HIST_SMEM_BINS of them
 // privatised in shared memory); larger counts are appended to an overflow list (at most
 // total_windows / HIST_DENSE_BINS entries can ever land there).
@@ -1193,6 +1225,25 @@ cudaError_t launch_key_buckets(const TableView &v, int shift, unsigned long long
   if (e != cudaSuccess || v.n == 0) return e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   key_buckets_kernel<<<grid_for(v.n, 256, 4), 256, 0, s>>>(v, shift, d_bucket_counts);
+  return cudaGetLastError();
+}
+cudaError_t launch_text_len(const uint64_t *d_counts, uint64_t n, int k, int fasta, uint64_t *d_lens, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  text_len_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(d_counts, n, k, fasta, d_lens);
+  return cudaGetLastError();
+}
+cudaError_t launch_text_write(const uint64_t *d_keys, const uint64_t *d_counts, const uint64_t *d_offs, uint64_t n, int k, int fasta, uint8_t *d_out,
+                              cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  text_write_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(d_keys, d_counts, d_offs, n, k, fasta, d_out);
+  return cudaGetLastError();
+}
+cudaError_t launch_interleave_pairs(const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n, void *d_out, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  interleave_pairs_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(d_keys, d_counts, n, static_cast<ulonglong2 *>(d_out));
   return cudaGetLastError();
 }
 cudaError_t launch_histogram(const TableView &v, uint64_t min_count, unsigned long long *d_bins, uint64_t *d_overflow,

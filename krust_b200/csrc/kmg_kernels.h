@@ -45,7 +45,7 @@ constexpr int REFINE_THREADS = 512;
 constexpr int REFINE_TILE = 8192;      // keys per level-2 tile (staged in shared memory: 64 KiB, 128 KiB with counts)
 constexpr int REFINE_ROWS_THREADS = 1024;   // single-pass level-2 scatter: one CTA per SM
 constexpr int REFINE_ROWS_SLOTS = 16384;    // n_sub rows of 2^cap_log2 keys (128 KiB)
-constexpr int REFINE_ROWS_OVERFLOW = 512;   // keys whose row was full
+constexpr int REFINE_ROWS_OVERFLOW = 4096;  // keys whose row was full (a coarse bin holding a hot key puts hundreds per tile there)
 constexpr int COUNT_THREADS = 512;
 constexpr int COUNT_CTAS_PER_SM = 2;
 constexpr int SMEM_COUNT_THREADS = 512;    // phase B primary variant: table in shared memory, 2 CTAs/SM
@@ -97,6 +97,11 @@ struct CountParams {
   unsigned long long *out_distinct;  // zeroed; ends up = number of distinct keys
   uint64_t *out_seg_start, *out_seg_len;  // n_parts each: where partition p landed in the output
   uint32_t *next, *error_flag;       // zeroed
+  // the output run holds out_cap entries (the host sizes it from the expected number of DISTINCT keys, not from the input
+  // entries: read sets repeat every k-mer many times); a partition whose reservation does not fit writes nothing and raises
+  // *nospace_flag -- the host then retries with a larger run
+  unsigned long long out_cap;
+  uint32_t *nospace_flag;            // zeroed
   // count-of-counts of the OUTPUT, built while compacting (zeroed by the host; nullptr = skip):
   // hist[c] for 2 <= c < HIST_DENSE_BINS, hist[HIST_DENSE_BINS] = number of overflow entries;
   // counts >= HIST_DENSE_BINS are appended to hist_overflow.  hist[1] is implied (distinct - the rest).
@@ -143,7 +148,9 @@ cudaError_t launch_fill_strided(uint64_t *d, uint64_t n, uint64_t stride, cudaSt
 cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, unsigned long long *d_max, cudaStream_t s);
 cudaError_t launch_count_partitions(const CountParams &P, unsigned grid, cudaStream_t s);
 // weighted: some input run carries counts, or a partition is large enough to want run-length pre-aggregation
-cudaError_t launch_count_partitions_smem(const CountParams &P, bool weighted, cudaStream_t s);
+// direct: unweighted, mostly distinct keys -- new keys go straight to the output, no compaction pass (the output then holds one
+// entry per INPUT entry, the duplicates' as skipped fillers)
+cudaError_t launch_count_partitions_smem(const CountParams &P, bool weighted, bool direct, cudaStream_t s);
 // tmp == nullptr: returns the scratch size needed for n items in *tmp_bytes.  Asynchronous on s.
 cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, void *tmp, size_t *tmp_bytes, cudaStream_t s);
 int num_sms();
@@ -161,6 +168,11 @@ cudaError_t launch_histogram(const TableView &v, uint64_t min_count, unsigned lo
                              uint64_t overflow_cap, unsigned long long *d_overflow_n, cudaStream_t s);
 // bucket_counts[key >> shift] += 1 for every entry (KEY_BUCKETS bins, zeroed by this call)
 cudaError_t launch_key_buckets(const TableView &v, int shift, unsigned long long *d_bucket_counts, cudaStream_t s);
+// text emitters / index records of a sorted piece (formatting happens on the device)
+cudaError_t launch_text_len(const uint64_t *d_counts, uint64_t n, int k, int fasta, uint64_t *d_lens, cudaStream_t s);
+cudaError_t launch_text_write(const uint64_t *d_keys, const uint64_t *d_counts, const uint64_t *d_offs, uint64_t n, int k, int fasta, uint8_t *d_out,
+                              cudaStream_t s);
+cudaError_t launch_interleave_pairs(const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n, void *d_out, cudaStream_t s);
 uint64_t kernel_launches();  // number of kernels of this library launched so far (process-wide)
 cudaError_t sort_pairs(uint64_t *d_keys, uint64_t *d_counts, uint64_t n, int key_bits, cudaStream_t s);
 

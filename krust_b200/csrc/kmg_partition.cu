@@ -117,6 +117,7 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
 // where sub-bin f of this tile lands in the output: exact layout = counted prefix + running cursor; speculative layout =
 // f * fine_cap + running cursor, refused (marker, nothing is written) when the partition's share is exhausted
 constexpr uint32_t NO_BASE = 0xffffffffu;
+constexpr unsigned long long NO_SPACE = ~0ull;  // phase B: the partition's output reservation did not fit the run (CountParams::out_cap)
 __device__ __forceinline__ uint32_t refine_reserve(const RefineParams &P, uint64_t f, uint32_t h) {
   if (!h) return 0u;
   const unsigned long long off = atomicAdd(P.fine_cursor + f, (unsigned long long)h);
@@ -590,7 +591,8 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
     if (tid == 0) {
       uint32_t d = 0;
       for (int w2 = 0; w2 < COUNT_THREADS / 32; ++w2) d += s_warp[w2];
-      const unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);  // the partition's contiguous output range
+      unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);  // the partition's contiguous output range
+      if (b + d > P.out_cap) { atomicExch(P.nospace_flag, 1u); b = NO_SPACE; }
       P.out_seg_start[p] = b; P.out_seg_len[p] = d;
       if (d) atomicAdd(P.out_distinct, (unsigned long long)d);
       s_base = b;
@@ -599,6 +601,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
 
     // ---- compact the table into the output run and clean it
     const unsigned long long out0 = s_base;
+    const bool fits = out0 != NO_SPACE;
     uint32_t mine = 0;
     for (uint64_t i = tid; i <= mask; i += COUNT_THREADS) mine += __ldcg(table + 2 * i) != EMPTY_MIX;
     uint32_t incl = mine;
@@ -619,8 +622,10 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
       const ulonglong2 sl = __ldcg(tab2 + i);
       const bool used = sl.x != EMPTY_MIX;
       if (used) {
-        __stcs(P.out_keys + o, sl.x);
-        __stcs(P.out_counts + o, sl.y + 1);  // slots store occurrences - 1
+        if (fits) {
+          __stcs(P.out_keys + o, sl.x);
+          __stcs(P.out_counts + o, sl.y + 1);  // slots store occurrences - 1
+        }
         ++o;
         reinterpret_cast<ulonglong2 *>(table)[i] = make_ulonglong2(EMPTY_MIX, 0ull);
       }
@@ -648,19 +653,28 @@ __global__ void __launch_bounds__(COUNT_THREADS, COUNT_CTAS_PER_SM) count_partit
 // If a partition holds more distinct keys than the table, a warp claims more than its list holds, or a count does
 // not fit 32 bits, error_flag is raised and the host re-runs phase B with the L2-scratch variant.
 // ---------------------------------------------------------------------------------------------------
-template <bool WEIGHTED>
+//  * DIRECT (unweighted runs of mostly distinct keys, e.g. a genome: no oversized partitions): no compaction pass at all.  The
+//    partition's output range is reserved for all its entries when its segment table is fetched; a key that claims a fresh slot
+//    is written to the output right away with count 1 -- positions from ballots taken in the converged code after the two probe
+//    rounds, so consecutive lanes write consecutive entries -- and remembers its output index in the slot (u16, where the other
+//    variant keeps its slot lists).  Duplicates only bump the slot's counter; after the partition a sweep over the table patches
+//    the few entries whose counter is non-zero, feeds the count-of-counts, and cleans the slots.  The unused tail of the
+//    reservation (one entry per duplicate) is filled with (EMPTY, 0) entries that every reader skips.
+template <bool WEIGHTED, bool DIRECT = false>
 __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_kernel(CountParams P) {
+  static_assert(!(WEIGHTED && DIRECT), "the direct variant counts unweighted keys");
   extern __shared__ __align__(16) unsigned long long skeys[];
   constexpr uint32_t SLOTS = SMEM_TABLE_SLOTS;
   constexpr int NW = SMEM_COUNT_THREADS / 32;
   constexpr uint32_t WLIST = SLOTS / NW;  // claimed-slot list entries per warp
   uint32_t *scnt = reinterpret_cast<uint32_t *>(skeys + SLOTS);
-  uint16_t *slist = reinterpret_cast<uint16_t *>(scnt + SLOTS);
+  uint16_t *slist = reinterpret_cast<uint16_t *>(scnt + SLOTS);  // DIRECT: sidx[slot] = output index of the slot's key
   __shared__ uint64_t seg_begin[CONS_MAX_RUNS];
   __shared__ uint64_t seg_prefix[CONS_MAX_RUNS + 1];
   __shared__ uint32_t s_work, s_hist[HIST_CTA_BINS], s_wn[NW];
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_run;  // entries of the current partition already written (multi-pass partitions)
+  __shared__ uint32_t s_emit; // DIRECT: entries of the current partition written so far
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint16_t *wlist = slist + warp * WLIST;
   if (tid < HIST_CTA_BINS) s_hist[tid] = 0;
@@ -683,7 +697,14 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint64_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         if (lane < (int)P.R) { seg_begin[lane] = b; seg_prefix[lane] = incl - len; }
-        if (lane == (int)P.R - 1) seg_prefix[P.R] = incl;
+        if (lane == (int)P.R - 1) {
+          seg_prefix[P.R] = incl;
+          if (DIRECT) {  // the output range for ALL entries of the partition, reserved while the others still wait at the barrier
+            unsigned long long ob = 0;
+            if (incl) { ob = atomicAdd(P.out_cursor, (unsigned long long)incl); if (ob + incl > P.out_cap) { atomicExch(P.nospace_flag, 1u); ob = NO_SPACE; } }
+            s_base = ob; s_emit = 0;
+          }
+        }
       }
       if (lane == 0) s_work = w;
     }
@@ -700,15 +721,24 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
     uint32_t cap_log2 = 8;  // small partitions use a prefix of the table
     while ((1u << cap_log2) < SLOTS && (1ull << cap_log2) * 5 < n_p * 8) ++cap_log2;
     const uint32_t mask = (1u << cap_log2) - 1, bmask = mask & ~1u;
+    if (DIRECT && n_p > 0xffffu) {  // block-uniform: output indices are 16 bits; such a partition needs the multi-pass variant
+      if (tid == 0) { atomicExch(P.error_flag, 1u); P.out_seg_start[p] = 0; P.out_seg_len[p] = 0; }
+      __syncthreads();
+      continue;
+    }
     // A partition with more entries than one table comfortably holds (the input outgrew the partition plan) is counted in
     // m passes: pass q takes the keys whose spare mix bits equal q, so every pass sees ~1/m of the distinct keys.  Its
     // output range is then reserved up front for all n_p entries; what stays unused is filled with (EMPTY, 0) entries
     // that every reader skips.  m is capped by the launch-wide P.split_log2 (set from the AVERAGE partition size): a
     // partition that is large only because a few keys are hot does not need more passes than its neighbours.
     uint32_t m_log2 = 0;
-    while (m_log2 < P.split_log2 && ((uint64_t)(SLOTS / 2) << m_log2) < n_p) ++m_log2;
+    while (!DIRECT && m_log2 < P.split_log2 && ((uint64_t)(SLOTS / 2) << m_log2) < n_p) ++m_log2;
     const uint32_t n_pass = 1u << m_log2;
-    if (n_pass > 1 && tid == 0) { s_base = atomicAdd(P.out_cursor, (unsigned long long)n_p); s_run = 0; }
+    if (n_pass > 1 && tid == 0) {
+      unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)n_p);
+      if (b + n_p > P.out_cap) { atomicExch(P.nospace_flag, 1u); b = NO_SPACE; }
+      s_base = b; s_run = 0;
+    }
 
     constexpr int G = 8, H = 4;
     static_assert(G == 8, "slot bookkeeping below packs 8 x 16 bits");
@@ -821,6 +851,27 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
           }
         }
       }
+      if (DIRECT) {
+        // ---- the keys that claimed a slot in the two rounds go to the output now: key q of all lanes forms one run, lanes in
+        // order, so a warp store covers consecutive entries.  Still converged code: the ballots are plain votes.
+        uint32_t bal[G], tot = 0;
+#pragma unroll
+        for (int q = 0; q < G; ++q) { bal[q] = __ballot_sync(0xffffffffu, newm >> q & 1u); tot += __popc(bal[q]); }
+        uint32_t wb = 0;
+        if (lane == 0 && tot) wb = atomicAdd(&s_emit, tot);
+        wb = __shfl_sync(0xffffffffu, wb, 0);
+        const uint32_t lt = (1u << lane) - 1u;
+        const bool fits = s_base != NO_SPACE;
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+          if (newm >> q & 1u) {
+            const uint32_t oi = wb + __popc(bal[q] & lt);
+            slist[(uint32_t)((q < 4 ? fs_lo : fs_hi) >> (16 * (q & 3))) & 0xffffu] = (uint16_t)oi;
+            if (fits) { __stcs(P.out_keys + s_base + oi, (uint64_t)key[q]); __stcs(P.out_counts + s_base + oi, (uint64_t)1); }
+          }
+          wb += __popc(bal[q]);
+        }
+      }
       // ---- what is left: every lane works through ITS pending keys on its own, continuing behind the slot it lost
       while (pend) {
         const int j = __ffs(pend) - 1;
@@ -843,14 +894,21 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
           const uint32_t add = wj - (is_new ? 1u : 0u);
           if (add) { const uint32_t old = atomicAdd(&scnt[s2], add); if (old > 0xffffffffu - add) atomicExch(P.error_flag, 1u); }
           if (is_new) {
-            newm |= 1u << j;
-            const uint64_t f = (uint64_t)s2 << (16 * (j & 3));
-            if (j < 4) fs_lo |= f; else fs_hi |= f;
+            if (DIRECT) {  // rare (~2 % of the keys): one shared atomic hands out the output index
+              const uint32_t oi = atomicAdd(&s_emit, 1u);
+              slist[s2] = (uint16_t)oi;
+              if (s_base != NO_SPACE) { __stcs(P.out_keys + s_base + oi, (uint64_t)kj); __stcs(P.out_counts + s_base + oi, (uint64_t)1); }
+            } else {
+              newm |= 1u << j;
+              const uint64_t f = (uint64_t)s2 << (16 * (j & 3));
+              if (j < 4) fs_lo |= f; else fs_hi |= f;
+            }
           }
         }
         pend &= pend - 1;
       }
       __syncwarp();  // reconverge here: otherwise the rest of the batch runs once per fragment of the warp
+      if (DIRECT) continue;  // everything of this batch has been written
       // ---- every lane appends the slots it claimed to its warp's list.  One same-address shared atomic per lane
       // and batch hands out the positions; deliberately no warp collective here: this point follows divergent
       // code, where a *_sync intrinsic costs a software convergence routine per call.
@@ -862,6 +920,40 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
       }
     }
     __syncthreads();  // all upserts done
+    if (DIRECT) {
+      const uint32_t d = s_emit;  // distinct keys of the partition, all of them already in the output with count 1
+      const bool fits = s_base != NO_SPACE;
+      // sweep the table: patch the entries of the keys that were seen again, note their counts, clean the slots
+      for (uint32_t i = 2 * tid; i <= mask; i += 2 * SMEM_COUNT_THREADS) {
+        const uint2 c2 = *reinterpret_cast<const uint2 *>(&scnt[i]);
+        if (c2.x | c2.y) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t cc = h ? c2.y : c2.x;
+            if (!cc) continue;
+            const unsigned long long cnt = (unsigned long long)cc + 1;  // slots store occurrences - 1
+            if (fits) __stcs(P.out_counts + s_base + slist[i + h], (uint64_t)cnt);
+            if (P.hist) {
+              if (cnt < (unsigned long long)HIST_CTA_BINS) atomicAdd(&s_hist[cnt], 1u);
+              else if (cnt < (unsigned long long)HIST_DENSE_BINS) atomicAdd(P.hist + cnt, 1ull);
+              else { const unsigned long long o = atomicAdd(P.hist + HIST_DENSE_BINS, 1ull); if (o < P.hist_overflow_cap) P.hist_overflow[o] = cnt; }
+            }
+          }
+          *reinterpret_cast<uint2 *>(&scnt[i]) = make_uint2(0u, 0u);
+        }
+        *reinterpret_cast<ulonglong2 *>(&skeys[i]) = make_ulonglong2(EMPTY_MIX, EMPTY_MIX);
+      }
+      for (uint64_t i = d + tid; i < n_p && fits; i += SMEM_COUNT_THREADS) {  // one unused entry per duplicate: readers skip them
+        __stcs(P.out_keys + s_base + i, (uint64_t)EMPTY_MIX);
+        __stcs(P.out_counts + s_base + i, (uint64_t)0);
+      }
+      if (tid == 0) {
+        P.out_seg_start[p] = fits ? s_base : 0; P.out_seg_len[p] = d;
+        if (d) atomicAdd(P.out_distinct, (unsigned long long)d);
+      }
+      __syncthreads();  // table clean, s_base / s_emit free for the next partition
+      continue;
+    }
     uint32_t wn = s_wn[warp];  // slots this warp claimed for the partition
     if (wn > WLIST) { if (lane == 0) atomicExch(P.error_flag, 1u); wn = WLIST; }  // list full: results are discarded, stay in bounds
     // ---- compact: the partition gets one contiguous output range (one global atomic), each warp a sub-range of it
@@ -874,7 +966,8 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
       const uint32_t d = __shfl_sync(0xffffffffu, incl, NW - 1);
       pre = __shfl_sync(0xffffffffu, incl - v, warp);
       if (n_pass == 1 && tid == 0) {
-        const unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);
+        unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);
+        if (b + d > P.out_cap) { atomicExch(P.nospace_flag, 1u); b = NO_SPACE; }
         P.out_seg_start[p] = b; P.out_seg_len[p] = d;
         s_base = b; s_run = 0;
         if (d) atomicAdd(P.out_distinct, (unsigned long long)d);
@@ -883,6 +976,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
     }
     __syncthreads();
     {
+      const bool fits = s_base != NO_SPACE;  // otherwise the table is only cleaned (the host retries with a larger run)
       const unsigned long long out0 = s_base + s_run + pre;
       for (uint32_t i0 = 0; i0 < wn; i0 += 32) {  // warp-uniform trip count
         const uint32_t i = i0 + lane;
@@ -891,8 +985,10 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
         if (ok) {
           const uint32_t slot = wlist[i];
           cnt = (unsigned long long)scnt[slot] + 1;  // slots store occurrences - 1
-          __stcs(P.out_keys + out0 + i, (uint64_t)skeys[slot]);
-          __stcs(P.out_counts + out0 + i, (uint64_t)cnt);
+          if (fits) {
+            __stcs(P.out_keys + out0 + i, (uint64_t)skeys[slot]);
+            __stcs(P.out_counts + out0 + i, (uint64_t)cnt);
+          }
           skeys[slot] = EMPTY_MIX; scnt[slot] = 0;
         }
         if (P.hist) hist_note(ok, cnt, s_hist, P, lane);
@@ -905,7 +1001,7 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
     if (n_pass > 1) {
       __syncthreads();
       const uint32_t done = s_run;  // <= n_p: every entry contributes at most one distinct key
-      for (uint64_t i = done + tid; i < n_p; i += SMEM_COUNT_THREADS) {  // unused tail of the reservation: entries every reader skips
+      for (uint64_t i = done + tid; i < n_p && s_base != NO_SPACE; i += SMEM_COUNT_THREADS) {  // unused tail of the reservation: entries every reader skips
         __stcs(P.out_keys + s_base + i, (uint64_t)EMPTY_MIX);
         __stcs(P.out_counts + s_base + i, (uint64_t)0);
       }
@@ -919,16 +1015,16 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
   if (P.hist) hist_flush(s_hist, P, tid);
 }
 
-cudaError_t launch_count_partitions_smem(const CountParams &P, bool weighted, cudaStream_t s) {
+cudaError_t launch_count_partitions_smem(const CountParams &P, bool weighted, bool direct, cudaStream_t s) {
   if (P.n_parts == 0) return cudaSuccess;
-  const size_t smem = (size_t)SMEM_TABLE_SLOTS * 14;  // u64 keys + u32 counts + u16 slot lists
+  const size_t smem = (size_t)SMEM_TABLE_SLOTS * 14;  // u64 keys + u32 counts + u16 slot lists / output indices
   const unsigned grid = (unsigned)std::min<uint64_t>(P.n_parts, (uint64_t)num_sms() * 2);
-  cudaError_t e = weighted ? cudaFuncSetAttribute(count_partitions_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(count_partitions_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (weighted && direct) return cudaErrorInvalidValue;
+  auto kern = weighted ? count_partitions_smem_kernel<true, false> : direct ? count_partitions_smem_kernel<false, true> : count_partitions_smem_kernel<false, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (weighted) count_partitions_smem_kernel<true><<<grid, SMEM_COUNT_THREADS, smem, s>>>(P);
-  else count_partitions_smem_kernel<false><<<grid, SMEM_COUNT_THREADS, smem, s>>>(P);
+  kern<<<grid, SMEM_COUNT_THREADS, smem, s>>>(P);
   return cudaGetLastError();
 }
 

@@ -186,3 +186,67 @@ def test_c4_full_size_sampled_against_oracle():
             exp1 = float(hf[hv == 1][0]) / 1009
             got1 = float((oc_ == 1).sum())
             assert abs(got1 - exp1) < 6 * exp1 ** 0.5 + 10
+
+
+def _oracle_text(keys, counts, k, fmt) -> bytes:
+    names = kb.unpack_many(keys, k).tolist()
+    if fmt == "tsv":
+        return b"".join(b"%s\t%d\n" % (s, int(c)) for s, c in zip(names, counts.tolist()))
+    return b"".join(b">%d\n%s\n" % (int(c), s) for s, c in zip(names, counts.tolist()))
+
+
+def test_device_text_emitters_small_cases(tmp_path):
+    """kmg_emit_text / kmg_write_text: fasta and tsv lines formatted on the device equal the reference's line formats
+    (src/run.rs:452-470) over the sorted oracle table -- all k, multi-digit counts, min-count, every engine path."""
+    import io
+    rng = np.random.default_rng(9)
+    recs = [b"A" * 5000, b"AC" * 700, b"ACGTTGCA" * 150] + [bytes(rng.choice(list(b"ACGTN"), size=int(rng.integers(0, 900))).tolist()) for _ in range(60)]
+    for k, flags in ((1, 0), (3, 0), (12, 0), (21, 0), (21, PART), (32, _lib.KMG_FLAG_FORCE_HASH), (31, PART)):
+        okeys, ocounts, _ = orc.count_records(k, recs, mode="rolling")
+        with kb.GpuKmerCounter(k, flags=flags, parts_log2=3 if flags == PART else 0) as c:
+            c.count_records(recs)
+            c.finalize(False)
+            for fmt in ("tsv", "fasta"):
+                for m in (0, 1, 2, 50):
+                    out = io.BytesIO()
+                    n_rec, n_bytes = c.emit_text(out, fmt, m)
+                    fk, fc = orc.filter_min_count(okeys, ocounts, max(m, 1))
+                    want = _oracle_text(fk, fc, k, fmt)
+                    assert out.getvalue() == want and n_rec == len(fk) and n_bytes == len(want)
+            p = tmp_path / "o.tsv"
+            assert c.write_text(p, "tsv", 1)[0] == len(okeys) and p.read_bytes() == _oracle_text(okeys, ocounts, k, "tsv")
+    # the reference's own exact-value line tests: soft_masked.fa k=3 -> "AAA\t2" (tests/integration_tests.rs:263-281)
+    out = io.BytesIO()
+    kb.KmerCounter.new().k(3).format("tsv").count_to_writer(os.path.join(os.path.dirname(__file__), "golden", "fixtures", "soft_masked.fa"), out)
+    assert out.getvalue() == b"AAA\t2\n"
+    out = io.BytesIO()
+    kb.KmerCounter.new().k(3).format("fasta").count_to_writer(os.path.join(os.path.dirname(__file__), "golden", "fixtures", "soft_masked.fa"), out)
+    assert out.getvalue() == b">2\nAAA\n"
+
+
+def test_c1_tsv_text_100mbp_equals_sorted_oracle_text(tmp_path):
+    """C1 end to end at its named size: kmerust 21 on the 100 Mbp genome, --format tsv.  The 2.4 GB of text produced on the device
+    equal the sorted oracle table formatted line by line (parity definition (iv): the reference's output order is random)."""
+    import torch
+    dev = torch.device("cuda:0")
+    n, n_rec, k = 100_000_000, 100, 21
+    host = orc.synth_uniform(42, 0, n)
+    offs = np.arange(0, n + 1, n // n_rec, dtype=np.uint64)
+    okeys, ocounts, _ = orc.count_batch_mt(k, host, None, offs)
+    assert int(ocounts.max()) < 10   # one-digit counts: every tsv line is k + 3 bytes, the oracle text can be built as a matrix
+    p = tmp_path / "c1.tsv"
+    with kb.GpuKmerCounter(k, expected_distinct=n) as c:
+        c.count_batch(host, None, offs)
+        c.finalize(False)
+        n_out, n_bytes = c.write_text(p, "tsv", 1)
+    assert n_out == len(okeys) and n_bytes == len(okeys) * (k + 3) == os.path.getsize(p)
+    got = np.memmap(p, dtype=np.uint8, mode="r").reshape(-1, k + 3)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    shifts = (np.arange(k - 1, -1, -1, dtype=np.uint64) * np.uint64(2))
+    step = 4_000_000
+    for i in range(0, len(okeys), step):
+        kk = okeys[i:i + step]
+        want = np.empty((len(kk), k + 3), dtype=np.uint8)
+        want[:, :k] = lut[((kk[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)]
+        want[:, k] = ord("\t"); want[:, k + 1] = ocounts[i:i + step].astype(np.uint8) + ord("0"); want[:, k + 2] = ord("\n")
+        assert (got[i:i + step] == want).all()
