@@ -130,6 +130,14 @@ kmg_status kmg_reset(kmg_ctx *ctx);
 kmg_status kmg_count_ascii(kmg_ctx *ctx, const uint8_t *seq, const uint8_t *qual,
                            const uint64_t *offsets, uint64_t n_records);
 
+/* Replaces reader::read / read_with_quality + the counting call for a whole FASTA / FASTQ FILE IMAGE in host memory (an mmap of
+ * the file, src/mmap.rs:33-71; src/reader.rs:82-247 materialises every record on the host first): the raw bytes are copied to
+ * the device in chunks cut at line / record boundaries and parsed THERE (line classification, trim_end of every sequence and
+ * quality line, record starts), then ingested and scanned as usual.  Well-formed single- or multi-line FASTA and 4-line FASTQ
+ * (\n or \r\n); multi-line FASTQ or a line longer than batch_bases gives KMG_ERR_PARSE -- fall back to kmg_parse_fastx +
+ * kmg_count_ascii after kmg_reset.  *n_records_out: records (header lines) seen. */
+kmg_status kmg_count_fastx(kmg_ctx *ctx, const uint8_t *buf, uint64_t len, int is_fastq, uint64_t *n_records_out);
+
 /* Pre-packed, zero-copy feed for the Rust reader layer (src/reader.rs, src/streaming.rs, src/mmap.rs). */
 kmg_status kmg_acquire_batch(kmg_ctx *ctx, kmg_batch *batch);
 kmg_status kmg_submit_batch(kmg_ctx *ctx, const kmg_batch *batch);

@@ -233,6 +233,15 @@ class GpuKmerCounter:
                                        qual.ctypes.data if qual is not None and len(qual) else None,
                                        offsets.ctypes.data, n_rec), self._ctx)
 
+    def count_fastx(self, data, is_fastq: bool) -> int:
+        """kmg_count_fastx: a whole FASTA / FASTQ file image (bytes, bytearray, numpy u8 or mmap) parsed on the device.
+        Returns the number of records."""
+        arr = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+        assert arr.dtype == np.uint8 and arr.flags.c_contiguous
+        n = C.c_uint64(0)
+        _check(self._L.kmg_count_fastx(self._ctx, arr.ctypes.data if len(arr) else None, len(arr), int(is_fastq), C.byref(n)), self._ctx)
+        return n.value
+
     def count_records(self, records: Iterable[bytes], quals: Optional[Iterable[bytes]] = None):
         records = [bytes(r) for r in records]
         offsets = np.zeros(len(records) + 1, dtype=np.uint64)
@@ -440,10 +449,39 @@ def count_kmers_from_sequences(sequences: Iterable[bytes], k: KmerLength) -> Dic
     return dict(zip(keys.tolist(), counts.tolist()))
 
 
-def _count_path_packed(path, k, fmt=SequenceFormat.AUTO, min_quality: Optional[int] = None, min_count: int = 1):
-    seq, qual, offsets = read_records(path, fmt)
-    with GpuKmerCounter(k, min_quality=min_quality) as c:
+def _read_file_image(path, fmt: str):
+    """(bytes of the decompressed file, is_fastq)."""
+    p = os.fspath(path)
+    if p == "-":
+        return sys.stdin.buffer.read(), SequenceFormat.resolve(fmt, None) == SequenceFormat.FASTQ
+    try:
+        with open(p, "rb") as f:
+            data = f.read()
+    except OSError as e:
+        raise KmeRustError(f"failed to read sequences from '{p}': {e}") from e
+    if p.lower().endswith(".gz"):
+        try:
+            data = gzip.decompress(data)
+        except (OSError, EOFError, zlib.error) as e:
+            raise KmeRustError(f"failed to read sequences from '{p}': {e}") from e
+    return data, SequenceFormat.resolve(fmt, p) == SequenceFormat.FASTQ
+
+
+def _feed_file(c: "GpuKmerCounter", path, fmt: str):
+    """File -> counter: records are found on the device (kmg_count_fastx); inputs the device parser refuses (multi-line FASTQ,
+    broken records) go through the host splitter, which reports the reference's parse errors."""
+    data, is_fastq = _read_file_image(path, fmt)
+    try:
+        c.count_fastx(data, is_fastq)
+    except SequenceParseError:
+        c.reset()
+        seq, qual, offsets = parse_fastx(data, is_fastq)
         c.count_batch(seq, qual, offsets)
+
+
+def _count_path_packed(path, k, fmt=SequenceFormat.AUTO, min_quality: Optional[int] = None, min_count: int = 1):
+    with GpuKmerCounter(k, min_quality=min_quality) as c:
+        _feed_file(c, path, fmt)
         c.finalize(False)
         return c.export(min_count, sorted=True)
 

@@ -1290,6 +1290,182 @@ KMG_EXPORT kmg_status kmg_count_ascii(kmg_ctx *c, const uint8_t *seq, const uint
   return KMG_OK;
 }
 
+
+// FASTA / FASTQ file image (HOST bytes, e.g. an mmap'ed file: src/mmap.rs:33-71) -> counts, with the records found ON THE DEVICE:
+// the raw bytes go over PCIe in chunks cut at line (FASTA) / record (FASTQ) boundaries, a few small kernels classify the lines,
+// compact sequence (+ quality) bytes, mark the record starts, and the usual ingest + scan follow.  Replaces reader::read /
+// read_with_quality (src/reader.rs:82-247: whole file -> Vec<Record> -> Vec<SequenceWithQuality>, two host copies) for
+// well-formed input; multi-line FASTQ, or a line longer than a chunk, is refused with KMG_ERR_PARSE -- nothing has been
+// counted then only if it happens in the first chunk, so callers fall back to kmg_parse_fastx + kmg_count_ascii after kmg_reset.
+KMG_EXPORT kmg_status kmg_count_fastx(kmg_ctx *c, const uint8_t *buf, uint64_t len, int is_fastq, uint64_t *n_records_out) {
+  if (!c || (len && !buf)) return KMG_ERR_INVALID_ARG;
+  if (c->shm) return fail(c, KMG_ERR_STATE, "context belongs to a shard group: feed it with kmg_shard_count_ascii(_device)");
+  if (n_records_out) *n_records_out = 0;
+  if (len == 0) return KMG_OK;
+  const uint8_t marker = is_fastq ? '@' : '>';
+  if (buf[0] != marker) return fail(c, KMG_ERR_PARSE, is_fastq ? "FASTQ record does not start with '@' (record 0)" : "FASTA record does not start with '>' (record 0)");
+  CU(c, cudaSetDevice(c->device));
+  const bool use_q = is_fastq && c->cfg.has_min_quality;
+  const uint64_t K1 = (uint64_t)c->k - 1;
+  const uint64_t CB = std::min<uint64_t>(c->batch_bases, 1ull << 30);
+  // ---- chunk plan: cuts at line starts (FASTA) / record starts (FASTQ)
+  struct Chunk { uint64_t pos, len; };
+  std::vector<Chunk> chunks;
+  for (uint64_t pos = 0; pos < len;) {
+    uint64_t end = std::min(len, pos + CB);
+    if (end < len) {
+      const void *nl = memrchr(buf + pos, '\n', (size_t)(end - pos));
+      if (!nl) return fail(c, KMG_ERR_PARSE, "a line is longer than a staging chunk (raise batch_bases or use the host splitter)");
+      end = (uint64_t)((const uint8_t *)nl - buf) + 1;
+      if (is_fastq) {  // step back line by line to a line that opens a record: '@' first, and the line after next begins with '+'
+        uint64_t cut = end;
+        bool found = false;
+        for (int tries = 0; tries < 64 && cut > pos; ++tries) {
+          if (buf[cut] == '@') {
+            const void *l1 = memchr(buf + cut, '\n', (size_t)(len - cut));
+            const void *l2 = l1 ? memchr((const uint8_t *)l1 + 1, '\n', (size_t)(buf + len - ((const uint8_t *)l1 + 1))) : nullptr;
+            if (l2 && (const uint8_t *)l2 + 1 < buf + len && ((const uint8_t *)l2)[1] == '+') { found = true; break; }
+          }
+          const void *prev = cut >= 2 ? memrchr(buf + pos, '\n', (size_t)(cut - 1 - pos)) : nullptr;  // start of the previous line
+          if (!prev) break;
+          cut = (uint64_t)((const uint8_t *)prev - buf) + 1;
+        }
+        if (!found || cut <= pos) return fail(c, KMG_ERR_PARSE, "no FASTQ record boundary found near a chunk end (multi-line FASTQ? use the host splitter)");
+        end = cut;
+      }
+    }
+    chunks.push_back(Chunk{pos, end - pos});
+    pos = end;
+  }
+  uint64_t max_len = 0;
+  for (auto &ch : chunks) max_len = std::max(max_len, ch.len);
+  if (max_len >= (1ull << 32)) return fail(c, KMG_ERR_INVALID_ARG, "staging chunks must stay below 4 GiB");
+  // ---- plan the table / partitions for the whole file
+  kmg_status s = KMG_OK;
+  if (use_q && !c->cfg.expected_distinct && c->mode == kmg_ctx::MODE_UNDECIDED && !c->use_dense) c->plan_scale = (double)len / (double)chunks[0].len;
+  else s = decide_mode(c, is_fastq ? len / 2 : len);
+  if (s != KMG_OK) return s;
+  const bool src_pinned = is_pinned_host(buf);
+  s = ensure_staging(c, !src_pinned, false, max_len);
+  if (s != KMG_OK) return s;
+  // ---- parse buffers (pooled)
+  uint8_t *d_kind = nullptr, *d_keep = nullptr, *d_seq = nullptr, *d_qual = nullptr, *d_mark = nullptr, *d_carry = nullptr;
+  uint32_t *d_lineno = nullptr, *d_pos_s = nullptr, *d_pos_q = nullptr, *d_misc = nullptr, *h_tot = nullptr;
+  void *d_tmp = nullptr;
+  const size_t tmp_bytes = fastx_scan_tmp_bytes(max_len);
+  auto release = [&]() {
+    pool_free(c, d_kind); pool_free(c, d_keep); pool_free(c, d_seq); pool_free(c, d_qual); pool_free(c, d_mark); pool_free(c, d_carry);
+    pool_free(c, d_lineno); pool_free(c, d_pos_s); pool_free(c, d_pos_q); pool_free(c, d_misc); pool_free(c, d_tmp);
+    if (h_tot) cudaFreeHost(h_tot);
+  };
+  cudaError_t e = pool_alloc(c, &d_kind, max_len);
+  if (e == cudaSuccess) e = pool_alloc(c, &d_keep, max_len);
+  if (e == cudaSuccess) e = pool_alloc(c, &d_pos_s, max_len * 4);
+  if (e == cudaSuccess && is_fastq) e = pool_alloc(c, &d_lineno, max_len * 4);
+  if (e == cudaSuccess && is_fastq) e = pool_alloc(c, &d_pos_q, max_len * 4);
+  if (e == cudaSuccess) e = pool_alloc(c, &d_seq, max_len + K1 + 64);
+  if (e == cudaSuccess && use_q) e = pool_alloc(c, &d_qual, max_len + K1 + 64);
+  if (e == cudaSuccess) e = pool_alloc(c, &d_mark, max_len + K1 + 64);
+  if (e == cudaSuccess) e = pool_alloc(c, &d_carry, 2 * 64);
+  if (e == cudaSuccess) e = pool_alloc(c, &d_misc, 64);   // [0..1] n_records (u64), [2..3] totals, [4] error word
+  if (e == cudaSuccess) e = pool_alloc(c, &d_tmp, tmp_bytes);
+  if (e == cudaSuccess) e = cudaHostAlloc(&h_tot, 16, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_misc, 0, 64, c->stream);
+  if (e != cudaSuccess) { release(); return cuda_fail(c, e, "cudaMalloc(fastx parse buffers)"); }
+  unsigned long long *d_nrec = reinterpret_cast<unsigned long long *>(d_misc);
+  uint32_t *d_err = d_misc + 4;
+  const uint32_t thr = std::min<uint32_t>(255u, (uint32_t)c->cfg.min_quality + 33u);
+  auto stage_chunk = [&](const Chunk &ch, Staging &st) -> kmg_status {
+    if (st.h2d_pending) { CU(c, cudaEventSynchronize(st.h2d_done)); st.h2d_pending = false; }
+    if (st.compute_pending) { CU(c, cudaStreamWaitEvent(c->copy_stream, st.compute_done, 0)); }
+    const uint8_t *src = buf + ch.pos;
+    if (!src_pinned) { memcpy(st.h_seq, src, ch.len); src = st.h_seq; }
+    CU(c, cudaMemcpyAsync(st.d_seq, src, ch.len, cudaMemcpyHostToDevice, c->copy_stream));
+    c->h2d_bytes += ch.len;
+    CU(c, cudaEventRecord(st.h2d_done, c->copy_stream));
+    st.h2d_pending = true;
+    return KMG_OK;
+  };
+  const uint32_t slot0 = c->next_ascii;
+  size_t staged = 0;
+  uint64_t prev_n = 0, bases = 0;
+  auto body = [&]() -> kmg_status {
+    for (size_t i = 0; i < chunks.size(); ++i) {
+      for (; staged < chunks.size() && staged < i + N_STAGE; ++staged) {
+        kmg_status ss = stage_chunk(chunks[staged], c->st[(slot0 + staged) % N_STAGE]);
+        if (ss != KMG_OK) return ss;
+      }
+      Staging &st = c->st[(slot0 + i) % N_STAGE];
+      const Chunk &ch = chunks[i];
+      CU(c, cudaStreamWaitEvent(c->stream, st.h2d_done, 0));
+      // a FASTA chunk that does not open with a header continues the previous chunk's last record: its last k-1 bases (and their
+      // record marks) are put in front, so that the windows spanning the cut are counted -- and none twice (k-1 bases hold no window)
+      const uint64_t carry = (!is_fastq && i > 0 && buf[ch.pos] != '>') ? std::min<uint64_t>(K1, prev_n) : 0;
+      CU(c, cudaMemsetAsync(d_mark, 0, ch.len + K1 + 64, c->stream));
+      CU(c, cudaMemsetAsync(d_err, 0, 4, c->stream));
+      if (carry) {
+        CU(c, cudaMemcpyAsync(d_seq, d_carry + (K1 - carry), carry, cudaMemcpyDeviceToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(d_mark, d_carry + 64 + (K1 - carry), carry, cudaMemcpyDeviceToDevice, c->stream));
+      }
+      CU(c, launch_fastx_parse(st.d_seq, ch.len, is_fastq, d_kind, d_keep, d_lineno, d_pos_s, d_pos_q, d_tmp, tmp_bytes, carry, d_seq, d_qual, d_mark,
+                               d_nrec, d_err, h_tot, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
+      const uint32_t total_s = h_tot[0], total_q = h_tot[1], err = h_tot[2];
+      if (err & 1u) return fail(c, KMG_ERR_PARSE, "FASTQ record does not start with '@' (multi-line FASTQ is not handled by the device parser)");
+      if (err & 2u) return fail(c, KMG_ERR_PARSE, "FASTQ record without a '+' separator line where one is expected");
+      if (is_fastq && total_s != total_q) return fail(c, KMG_ERR_PARSE, "sequence and quality lengths differ");
+      // a record whose header closed the previous chunk starts with this chunk's first base (the scatter below may raise the flag anew)
+      if (!is_fastq && total_s) CU(c, launch_fastx_apply_pending(d_err + 1, d_mark + carry, c->stream));
+      CU(c, launch_fastx_scatter(st.d_seq, ch.len, is_fastq, d_kind, d_lineno, d_keep, d_pos_s, d_pos_q, carry, total_s, d_seq, use_q ? d_qual : nullptr,
+                                 d_mark, d_nrec, d_err, c->stream));
+      CU(c, cudaEventRecord(st.compute_done, c->stream));  // the raw chunk has been consumed
+      st.compute_pending = true;
+      const uint64_t n = carry + total_s;
+      bases += total_s;
+      if (n) {
+        const uint64_t n_words_total = round_up((n + 31) / 32, TILE_WORDS);
+        kmg_status ps = ensure_packed(c, n_words_total);
+        if (ps != KMG_OK) return ps;
+        CU(c, launch_ingest(d_seq, use_q ? d_qual : nullptr, n, thr, n_words_total, c->d_bases, c->d_valid, c->stream));
+        CU(c, launch_marks_to_bits(d_mark, n, n_words_total, c->d_start, c->stream));
+        if (!is_fastq) {  // keep the tail for the next chunk
+          const uint64_t t = std::min<uint64_t>(K1, n);
+          if (t) {
+            CU(c, cudaMemcpyAsync(d_carry + (K1 - t), d_seq + (n - t), t, cudaMemcpyDeviceToDevice, c->stream));
+            CU(c, cudaMemcpyAsync(d_carry + 64 + (K1 - t), d_mark + (n - t), t, cudaMemcpyDeviceToDevice, c->stream));
+          }
+        }
+        ps = scan_packed(c, n_words_total, true);
+        if (ps != KMG_OK) return ps;
+        if (is_fastq && use_q) {  // a quality mismatch inside a record shows up at the next record start (checked in the scatter)
+          uint32_t e2 = 0;
+          CU(c, cudaMemcpyAsync(&e2, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
+          CU(c, cudaStreamSynchronize(c->stream));
+          if (e2 & 8u) return fail(c, KMG_ERR_PARSE, "sequence and quality lengths differ");
+        }
+      }
+      prev_n = n;
+    }
+    return KMG_OK;
+  };
+  s = body();
+  unsigned long long n_rec = 0;
+  if (s == KMG_OK) {
+    e = cudaMemcpyAsync(&n_rec, d_nrec, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) s = cuda_fail(c, e, "fastx record count");
+  } else {
+    cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
+  }
+  c->next_ascii = (slot0 + (uint32_t)chunks.size()) % N_STAGE;
+  for (auto &st : c->st) if (st.h2d_pending && src_pinned) { cudaEventSynchronize(st.h2d_done); st.h2d_pending = false; }
+  release();
+  if (s != KMG_OK) return s;
+  c->n_records += n_rec; c->n_bases += bases;
+  if (n_records_out) *n_records_out = n_rec;
+  return KMG_OK;
+}
+
 KMG_EXPORT kmg_status kmg_acquire_batch(kmg_ctx *c, kmg_batch *b) {
   if (!c || !b) return KMG_ERR_INVALID_ARG;
   CU(c, cudaSetDevice(c->device));

@@ -15,6 +15,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "kmg_device.cuh"
 
@@ -972,6 +973,97 @@ __global__ void __launch_bounds__(256) key_buckets_kernel(TableView v, int shift
     if (sh[b]) atomicAdd(buckets + b, (unsigned long long)sh[b]);
 }
 
+// =================================================================================================
+// FASTA / FASTQ parsing on the device (replaces the record iteration of bio::io::{fasta,fastq}::Reader as used by
+// src/reader.rs:82-247 for well-formed files): raw file bytes -> compacted sequence (+ quality) bytes + record-start marks.
+// A chunk always starts at a line start (FASTQ: at a record).  Line kinds: FASTA 0 = sequence, 1 = header ('>' first);
+// FASTQ = line number mod 4 (0 header '@', 1 sequence, 2 '+', 3 quality; multi-line FASTQ is left to the host splitter).
+// Every sequence / quality line is trim_end()-ed like the reference's parser does (trailing blanks, \r, \n).
+// =================================================================================================
+__device__ __forceinline__ bool fx_is_ws(uint8_t b) { return b == ' ' || (b >= 9 && b <= 13); }
+// seed of the line-kind scan: the kind at a line start, "inherit" (0xff) elsewhere; FASTQ: newline flags for the line counter
+__global__ void fx_seed_kernel(const uint8_t *__restrict__ buf, uint64_t n, int is_fastq, uint8_t *__restrict__ seed) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (is_fastq) seed[i] = buf[i] == '\n';
+    else seed[i] = (i == 0 || buf[i - 1] == '\n') ? (buf[i] == '>' ? 1 : 0) : 0xff;
+  }
+}
+struct FxBit0 { __host__ __device__ __forceinline__ uint32_t operator()(uint8_t k) const { return k == 1; } };
+struct FxBit1 { __host__ __device__ __forceinline__ uint32_t operator()(uint8_t k) const { return k == 2; } };
+struct FxInherit {  // scan operator: the kind of the most recent line start
+  __host__ __device__ __forceinline__ uint8_t operator()(uint8_t a, uint8_t b) const { return b == 0xff ? a : b; }
+};
+// keep flags: byte i belongs to the compacted sequence (bit 0) / quality (bit 1) stream.
+// err bits: 1 header line without its marker, 2 '+' line missing, 4 first line of a FASTA chunk that opens the file is no header
+__global__ void fx_keep_kernel(const uint8_t *__restrict__ buf, uint64_t n, int is_fastq, const uint8_t *__restrict__ kind8,
+                               const uint32_t *__restrict__ lineno, uint8_t *__restrict__ keep, uint32_t *err) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t b = buf[i];
+    const uint32_t kind = is_fastq ? (lineno[i] & 3u) : kind8[i];
+    const bool line_start = i == 0 || buf[i - 1] == '\n';
+    if (line_start) {
+      if (is_fastq && kind == 0 && b != '@') atomicOr(err, 1u);
+      if (is_fastq && kind == 2 && b != '+') atomicOr(err, 2u);
+    }
+    uint8_t k = 0;
+    const bool payload = is_fastq ? (kind == 1 || kind == 3) : kind == 0;
+    if (payload && b != '\n') {
+      bool trailing = false;
+      if (fx_is_ws(b)) {  // trim_end: blanks that run up to the end of the line are dropped, interior ones stay (and count as invalid bases)
+        uint64_t j = i + 1;
+        while (j < n && buf[j] != '\n' && fx_is_ws(buf[j])) ++j;
+        trailing = j == n || buf[j] == '\n';
+      }
+      if (!trailing) k = (is_fastq && kind == 3) ? 2 : 1;
+    }
+    keep[i] = k;
+  }
+}
+// positions: pos_s[i] / pos_q[i] = kept sequence / quality bytes before i (exclusive prefix sums of the keep bits, by CUB)
+__global__ void fx_scatter_kernel(const uint8_t *__restrict__ buf, uint64_t n, int is_fastq, const uint8_t *__restrict__ kind8,
+                                  const uint32_t *__restrict__ lineno, const uint8_t *__restrict__ keep, const uint32_t *__restrict__ pos_s,
+                                  const uint32_t *__restrict__ pos_q, uint64_t carry, uint64_t total_s, uint8_t *__restrict__ out_seq,
+                                  uint8_t *__restrict__ out_qual, uint8_t *__restrict__ out_mark, unsigned long long *n_records, uint32_t *err) {
+  unsigned long long recs = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t k = keep[i];
+    if (k == 1) out_seq[carry + pos_s[i]] = buf[i];
+    else if (k == 2 && out_qual) out_qual[carry + pos_q[i]] = buf[i];
+    if (i == 0 || buf[i - 1] == '\n') {  // a header line opens a record: its first base is the next kept sequence byte
+      const uint32_t kind = is_fastq ? (lineno[i] & 3u) : kind8[i];
+      if (kind == (is_fastq ? 0u : 1u)) {
+        ++recs;
+        if (pos_s[i] < total_s) out_mark[carry + pos_s[i]] = 1;
+        else atomicOr(err + 1, 1u);  // the record's first base lies in the NEXT chunk: remembered in the word behind the error word
+        if (is_fastq && pos_s[i] != pos_q[i]) atomicOr(err, 8u);  // an earlier record's quality length differs from its sequence length
+      }
+    }
+  }
+  recs = warp_sum(recs);
+  if ((threadIdx.x & 31) == 0 && recs) atomicAdd(n_records, recs);
+}
+// a record that opened at the very end of the previous chunk starts with this chunk's first new base
+__global__ void fx_apply_pending_kernel(uint32_t *pending, uint8_t *mark_at_first_new_base) {
+  if (*pending) { *mark_at_first_new_base = 1; *pending = 0; }
+}
+__global__ void fx_totals_kernel(const uint8_t *keep, const uint32_t *pos_s, const uint32_t *pos_q, uint64_t n, int is_fastq, uint32_t *totals) {
+  totals[0] = pos_s[n - 1] + (keep[n - 1] == 1);
+  totals[1] = is_fastq ? pos_q[n - 1] + (keep[n - 1] == 2) : 0u;
+}
+// record-start marks (one byte per base) -> the start bit stream of the packed layout (bit 31 - j%32 of word j/32)
+__global__ void fx_marks_to_bits_kernel(const uint8_t *__restrict__ mark, uint64_t n_bases, uint64_t n_words_total, uint32_t *__restrict__ start_out) {
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words_total; w += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t bits = 0;
+    const uint64_t b0 = w * 32;
+    if (b0 < n_bases) {
+      const uint64_t m = n_bases - b0 < 32 ? n_bases - b0 : 32;
+      for (uint64_t j = 0; j < m; ++j) bits |= (uint32_t)(mark[b0 + j] != 0) << (31 - j);
+      if (w == 0) bits &= 0x7fffffffu;  // position 0 has no predecessor
+    }
+    start_out[LEAD_MASK_WORDS + w] = bits;
+  }
+}
+
 // ---- output formatting on the device (replaces the per-k-mer writeln! of src/run.rs:452-470 / src/builder.rs:406-429 and
 // unpack_to_string, src/kmer.rs:431-456): record i of a sorted piece becomes "{kmer}\t{count}\n" (tsv) or ">{count}\n{kmer}\n" (fasta)
 __device__ __forceinline__ uint32_t dec_digits(uint64_t v) {
@@ -1227,6 +1319,63 @@ cudaError_t launch_key_buckets(const TableView &v, int shift, unsigned long long
   key_buckets_kernel<<<grid_for(v.n, 256, 4), 256, 0, s>>>(v, shift, d_bucket_counts);
   return cudaGetLastError();
 }
+// One parse pass over n raw bytes (device).  tmp layout is managed by the caller: seed/kind (n bytes), keep (n bytes), lineno / pos_s / pos_q
+// (n u32 each), scan scratch.  Totals (kept sequence / quality bytes) come back through d_totals[2] (u32), records are ADDED to *d_n_records.
+cudaError_t launch_fastx_parse(const uint8_t *d_buf, uint64_t n, int is_fastq, uint8_t *d_kind, uint8_t *d_keep, uint32_t *d_lineno, uint32_t *d_pos_s,
+                               uint32_t *d_pos_q, void *d_scan_tmp, size_t scan_tmp_bytes, uint64_t carry, uint8_t *d_out_seq, uint8_t *d_out_qual,
+                               uint8_t *d_out_mark, unsigned long long *d_n_records, uint32_t *d_err, uint32_t *h_totals_pinned, cudaStream_t s) {
+  if (n == 0) { h_totals_pinned[0] = h_totals_pinned[1] = 0; return cudaSuccess; }
+  const unsigned grid = grid_for(n, 256, 8);
+  cudaError_t e;
+  g_launches.fetch_add(4, std::memory_order_relaxed);
+  fx_seed_kernel<<<grid, 256, 0, s>>>(d_buf, n, is_fastq, d_kind);
+  size_t tb = scan_tmp_bytes;
+  if (is_fastq) e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, tb, d_kind, d_lineno, (int64_t)n, s);           // newlines before i = line number
+  else e = cub::DeviceScan::InclusiveScan(d_scan_tmp, tb, d_kind, d_kind, FxInherit(), (int64_t)n, s);         // kind of the current line
+  if (e != cudaSuccess) return e;
+  fx_keep_kernel<<<grid, 256, 0, s>>>(d_buf, n, is_fastq, d_kind, d_lineno, d_keep, d_err);
+  // exclusive prefix sums of the two keep bits (transform iterators would save a pass; these streams are tiny next to the PCIe copy)
+  tb = scan_tmp_bytes;
+  e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, tb, thrust::make_transform_iterator(d_keep, FxBit0()), d_pos_s, (int64_t)n, s);
+  if (e != cudaSuccess) return e;
+  if (is_fastq) {
+    tb = scan_tmp_bytes;
+    e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, tb, thrust::make_transform_iterator(d_keep, FxBit1()), d_pos_q, (int64_t)n, s);
+    if (e != cudaSuccess) return e;
+  }
+  // totals[0..1] = kept sequence / quality bytes (last prefix + last flag); totals[2] is the error word: one 16-byte D2H for the caller
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  fx_totals_kernel<<<1, 1, 0, s>>>(d_keep, d_pos_s, d_pos_q, n, is_fastq, d_err - 2);
+  e = cudaMemcpyAsync(h_totals_pinned, d_err - 2, 16, cudaMemcpyDeviceToHost, s);
+  return e;
+}
+size_t fastx_scan_tmp_bytes(uint64_t n) {
+  size_t a = 0, b = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, a, (const uint8_t *)nullptr, (uint32_t *)nullptr, (int64_t)n);
+  cub::DeviceScan::InclusiveScan(nullptr, b, (uint8_t *)nullptr, (uint8_t *)nullptr, FxInherit(), (int64_t)n);
+  return std::max(a, b) + 256;
+}
+cudaError_t launch_fastx_scatter(const uint8_t *d_buf, uint64_t n, int is_fastq, const uint8_t *d_kind, const uint32_t *d_lineno, const uint8_t *d_keep,
+                                 const uint32_t *d_pos_s, const uint32_t *d_pos_q, uint64_t carry, uint64_t total_s, uint8_t *d_out_seq, uint8_t *d_out_qual,
+                                 uint8_t *d_out_mark, unsigned long long *d_n_records, uint32_t *d_err, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  fx_scatter_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(d_buf, n, is_fastq, d_kind, d_lineno, d_keep, d_pos_s, d_pos_q, carry, total_s, d_out_seq, d_out_qual,
+                                                        d_out_mark, d_n_records, d_err);
+  return cudaGetLastError();
+}
+cudaError_t launch_fastx_apply_pending(uint32_t *d_pending, uint8_t *d_mark_first_new, cudaStream_t s) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  fx_apply_pending_kernel<<<1, 1, 0, s>>>(d_pending, d_mark_first_new);
+  return cudaGetLastError();
+}
+cudaError_t launch_marks_to_bits(const uint8_t *d_mark, uint64_t n_bases, uint64_t n_words_total, uint32_t *d_start, cudaStream_t s) {
+  if (n_words_total == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  fx_marks_to_bits_kernel<<<grid_for(n_words_total, 256, 8), 256, 0, s>>>(d_mark, n_bases, n_words_total, d_start);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_text_len(const uint64_t *d_counts, uint64_t n, int k, int fasta, uint64_t *d_lens, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -130,7 +130,7 @@ __device__ __forceinline__ uint32_t refine_reserve(const RefineParams &P, uint64
 
 // where input partition c's keys live (RefineParams::src)
 __device__ __forceinline__ const uint64_t *refine_keys_of(const RefineParams &P, uint32_t c) {
-  return P.n_src ? P.src[c % P.in_group] : P.keys;
+  return P.n_src ? P.src[c % P.in_group] : P.keys;  // once per tile, never per key
 }
 
 // One tile, exact two-pass procedure: histogram -> (count: add to fine_counts | scatter: prefix, one global reservation
@@ -300,11 +300,14 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
   uint64_t begin;
   tile_range(g_begin, c, begin, m);
   uint64_t key[U];
+  {
+    const uint64_t *kb = refine_keys_of(P, c) + begin;
 #pragma unroll
-  for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m ? __ldcs(refine_keys_of(P, c) + begin + i) : EMPTY_KEY; }
+    for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m ? __ldcs(kb + i) : EMPTY_KEY; }
+  }
 
   for (uint32_t g = g_begin; g < g_end; ++g) {
-    const uint32_t cb = c / P.in_group;  // coarse bin of input partition c
+    const uint32_t cb = P.in_group > 1 ? c / P.in_group : c;  // coarse bin of input partition c
     const uint64_t f0 = (uint64_t)cb * P.n_sub;
     const uint32_t sub_base = (cb % P.sub_old) * P.n_sub;
     {  // ---- rank the tile's keys into the rows
@@ -348,8 +351,9 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
     if (g + 1 < g_end) {
       c_next = s_c[nslot];
       tile_range(g + 1, c_next, begin_next, m_next);
+      const uint64_t *kb = refine_keys_of(P, c_next) + begin_next;
 #pragma unroll
-      for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m_next ? __ldcs(refine_keys_of(P, c_next) + begin_next + i) : EMPTY_KEY; }
+      for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m_next ? __ldcs(kb + i) : EMPTY_KEY; }
     }
     __syncthreads();
     if (!exact) {
