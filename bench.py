@@ -460,6 +460,11 @@ def main():
             off_e2e = offsets_np
         d2h_bytes = 0
         e2e_windows = 0
+        pin_k = pin_c = None
+        if cfg["result"] == "export":   # the (filtered) map lands in pinned host arrays: what the FFI wrapper would hand to HashMap::from_iter
+            cap_out = int(summary["n_distinct"] * (frac_e2e if frac_e2e < 1.0 else 1.0)) + 1024
+            pin_k = torch.empty(cap_out, dtype=torch.int64, pin_memory=True)
+            pin_c = torch.empty(cap_out, dtype=torch.int64, pin_memory=True)
 
         def step_e2e():
             nonlocal d2h_bytes, e2e_windows
@@ -470,10 +475,10 @@ def main():
                 sharded.count_host(h_np, off_e2e, hq_np, expected_keys_per_rank=cfg["bases"] // world + 1024)
             engine.finalize(False)
             if cfg["result"] == "export":                            # what count_kmers_streaming_packed returns: the (filtered) map
-                keys, counts = engine.counter.export(min_count, sorted=False)
-                d2h_bytes = keys.nbytes + counts.nbytes
+                n_out = engine.counter.export_into(pin_k.numpy().view(np.uint64), pin_c.numpy().view(np.uint64), min_count, sorted=False)
+                d2h_bytes = 16 * n_out
                 e2e_windows = -1
-                return keys, counts
+                return pin_k.numpy()[:n_out], pin_c.numpy()[:n_out]
             vals, freqs = sharded.histogram(min_count)               # D2H of the count-of-counts
             d2h_bytes = (vals.nbytes + freqs.nbytes) + 65536 * 8
             e2e_windows = int((vals * freqs).sum())
@@ -497,6 +502,67 @@ def main():
                          else "count-of-counts histogram + summary to host; table stays in HBM",
                "input_fraction": frac_e2e}
         del h_seq, h_qual
+    else:
+        pin_k = pin_c = None
+
+    # ---- from FILE BYTES: an in-RAM FASTA / FASTQ image of the workload (80-column FASTA lines; 4-line FASTQ), records found
+    # on the device by kmg_count_fastx.  Timed like e2e: raw bytes in pinned host memory -> result on the host.
+    e2e_file = None
+    if not args.no_e2e and world == 1 and cfg["bases"] <= 4_000_000_000:
+        host_seq = d_seq.cpu().numpy()
+        if reads:
+            n_r = n_rec_local
+            img_t = torch.empty(n_r * 316, dtype=torch.uint8, pin_memory=True)
+            img = img_t.numpy().reshape(n_r, 316)
+            idx = np.arange(n_r, dtype=np.int64)
+            img[:, 0] = ord("@"); img[:, 1] = ord("r")
+            for j in range(9):
+                img[:, 2 + j] = ((idx // 10 ** (8 - j)) % 10 + 48).astype(np.uint8)
+            img[:, 11] = 10
+            img[:, 12:162] = host_seq.reshape(n_r, READ_LEN)
+            img[:, 162] = 10; img[:, 163] = ord("+"); img[:, 164] = 10
+            img[:, 165:315] = d_qual.cpu().numpy().reshape(n_r, READ_LEN) if d_qual is not None else ord("I")
+            img[:, 315] = 10
+            image = img_t.numpy()
+        else:
+            rec_len = cfg["bases"] // cfg["records"]
+            assert rec_len % 80 == 0 and rec_len * cfg["records"] == cfg["bases"]
+            hdrs = [b">chr%d\n" % r for r in range(cfg["records"])]
+            per = rec_len + rec_len // 80
+            img_t = torch.empty(sum(len(h) for h in hdrs) + per * cfg["records"], dtype=torch.uint8, pin_memory=True)
+            image = img_t.numpy()
+            o = 0
+            for r, h in enumerate(hdrs):
+                image[o:o + len(h)] = np.frombuffer(h, dtype=np.uint8); o += len(h)
+                body = image[o:o + per].reshape(-1, 81)
+                body[:, :80] = host_seq[r * rec_len:(r + 1) * rec_len].reshape(-1, 80)
+                body[:, 80] = 10
+                o += per
+        del host_seq
+
+        def step_file():
+            engine.reset()
+            engine.counter.count_fastx(image, reads)
+            engine.finalize(False)
+            if cfg["result"] == "export" and pin_k is not None:
+                return engine.counter.export_into(pin_k.numpy().view(np.uint64), pin_c.numpy().view(np.uint64), min_count, sorted=False)
+            return sharded.histogram(min_count)
+
+        for _ in range(2):
+            step_file()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_file()
+        dt = (time.perf_counter() - t0) / args.steps
+        s_f = sharded.finalize()
+        if s_f["n_windows"] != exp_windows or s_f["n_records"] != cfg["records"]:
+            raise SystemExit("PARITY FAILURE in the file-image path")
+        e2e_file = {"value": exp_windows / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "file_bytes": int(image.nbytes),
+                    "file_gbs": image.nbytes / dt / 1e9,
+                    "format": "4-line FASTQ image, 316 B per read" if reads else "FASTA image, 80-column lines",
+                    "parser": "kmg_count_fastx: raw bytes over PCIe, records found on the device"}
+        del image, img_t
 
     # ---- C5: the .kmix index written from the GPU shard(s) (timed once, outside the steps: it is disk-bound)
     kmix = None
@@ -535,6 +601,8 @@ def main():
                            "step": "table clear + ingest + scan/upsert (+ fused bucket/exchange over NVLink for N>1) + finalize + device-side result",
                            "parallelism": f"hash-shard x{world}" if world > 1 else "single GPU"},
                 "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+        if e2e_file:
+            line["e2e_file"] = e2e_file
         if also:
             line["also"] = also
         if kmix:

@@ -118,6 +118,8 @@ const char *kmg_last_error(const kmg_ctx *ctx);
 /* Replaces KmerMap::new / StreamingKmerCounter::new (src/run.rs:494-498, src/streaming.rs:838-843). */
 kmg_status kmg_create(const kmg_config *cfg, kmg_ctx **out);
 void kmg_destroy(kmg_ctx *ctx);
+/* The context's k (KmerIndex::k, src/index.rs:95; what kmg_index_open read from the file header). */
+uint32_t kmg_ctx_k(const kmg_ctx *ctx);
 /* Forget all counts but keep the allocations (benchmark steps, repeated use). */
 kmg_status kmg_reset(kmg_ctx *ctx);
 
@@ -238,6 +240,17 @@ kmg_status kmg_save_kmix(kmg_ctx *ctx, const char *path);
 kmg_status kmg_kmix_begin(const char *path);
 kmg_status kmg_save_kmix_shard(kmg_ctx *ctx, const char *path, uint64_t record_offset, uint64_t *n_records_out, uint32_t *crc_out);
 kmg_status kmg_kmix_finish(const char *path, uint32_t k, const uint64_t *shard_records, const uint32_t *shard_crcs, uint32_t n_shards);
+
+/* Batched look-ups (replaces KmerIndex::get, src/index.rs:127-131, and the canonicalisation the `query` subcommand does first,
+ * src/main.rs:254-266).  HOST arrays.  kmg_query_keys: canonical packed keys -> counts (0 = absent).  kmg_query_ascii: n k-mers
+ * of k ASCII bytes each, any case, canonicalised on the device; a k-mer with a byte outside ACGTacgt counts 0 and is reported in
+ * *n_invalid_out.  A context of a shard group answers for the keys it owns (0 for the others: sum the ranks' answers). */
+kmg_status kmg_query_keys(kmg_ctx *ctx, const uint64_t *keys, uint64_t n, uint64_t *counts_out);
+kmg_status kmg_query_ascii(kmg_ctx *ctx, const uint8_t *kmers, uint64_t n, uint64_t *counts_out, uint64_t *n_invalid_out);
+/* Replaces load_index / read_index (src/index.rs:199-216, :282-401): opens an uncompressed .kmix file as a ready-to-query
+ * context on `device` (-1 = current).  Same checks in the same order: size >= 18, magic, CRC-32, version, k, data size == n * 16.
+ * KMG_ERR_IO = cannot read, KMG_ERR_PARSE = invalid index (message: kmg_last_error(NULL)). */
+kmg_status kmg_index_open(const char *path, int32_t device, kmg_ctx **out);
 
 /* Replaces ProgressTracker::snapshot (src/progress.rs). */
 kmg_status kmg_progress(const kmg_ctx *ctx, uint64_t *records, uint64_t *bases);

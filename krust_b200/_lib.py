@@ -43,6 +43,7 @@ SIGNATURES = {
     "kmg_last_error": (C.c_char_p, [vp]),
     "kmg_create": (i32, [C.POINTER(KmgConfig), C.POINTER(vp)]),
     "kmg_destroy": (None, [vp]),
+    "kmg_ctx_k": (u32, [vp]),
     "kmg_reset": (i32, [vp]),
     "kmg_count_ascii": (i32, [vp, vp, vp, vp, u64]),
     "kmg_count_fastx": (i32, [vp, vp, u64, i32, C.POINTER(u64)]),
@@ -74,6 +75,9 @@ SIGNATURES = {
     "kmg_kmix_begin": (i32, [C.c_char_p]),
     "kmg_save_kmix_shard": (i32, [vp, C.c_char_p, u64, C.POINTER(u64), C.POINTER(u32)]),
     "kmg_kmix_finish": (i32, [C.c_char_p, u32, vp, vp, u32]),
+    "kmg_query_keys": (i32, [vp, vp, u64, vp]),
+    "kmg_query_ascii": (i32, [vp, vp, u64, vp, C.POINTER(u64)]),
+    "kmg_index_open": (i32, [C.c_char_p, C.c_int32, C.POINTER(vp)]),
     "kmg_progress": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
     "kmg_kernel_launches": (u64, []),
     "kmg_synth_uniform_device": (i32, [vp, u64, u64, u64, vp]),

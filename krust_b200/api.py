@@ -356,6 +356,15 @@ class GpuKmerCounter:
                                              n.value, C.byref(n)), self._ctx)
         return keys, counts
 
+    def export_into(self, keys: np.ndarray, counts: np.ndarray, min_count: int = 1, sorted: bool = False) -> int:
+        """kmg_export_counts into caller-owned arrays (e.g. numpy views of pinned memory: the D2H copy then runs at PCIe speed).
+        Returns the number of entries written; raises when the arrays are too small."""
+        assert keys.dtype == np.uint64 and counts.dtype == np.uint64 and keys.flags.c_contiguous and counts.flags.c_contiguous
+        n = C.c_uint64(0)
+        _check(self._L.kmg_export_counts(self._ctx, min_count, int(sorted), keys.ctypes.data, counts.ctypes.data,
+                                         min(len(keys), len(counts)), C.byref(n)), self._ctx)
+        return n.value
+
     def export_shard(self, n_shards: int, shard: int, min_count: int = 1, sorted: bool = True) -> Tuple[np.ndarray, np.ndarray]:
         """The entries with key % n_shards == shard (kmg_export_shard): the result in pieces that fit the host."""
         n = C.c_uint64(0)
@@ -405,6 +414,47 @@ class GpuKmerCounter:
         n_rec, n_bytes = C.c_uint64(0), C.c_uint64(0)
         _check(self._L.kmg_write_text(self._ctx, min_count, code, os.fspath(path).encode(), C.byref(n_rec), C.byref(n_bytes)), self._ctx)
         return n_rec.value, n_bytes.value
+
+    def query_keys(self, keys: np.ndarray) -> np.ndarray:
+        """Counts of canonical packed keys (0 = absent), looked up on the device (kmg_query_keys)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.zeros(len(keys), dtype=np.uint64)
+        if len(keys):
+            _check(self._L.kmg_query_keys(self._ctx, keys.ctypes.data, len(keys), out.ctypes.data), self._ctx)
+        return out
+
+    def query_kmers(self, kmers: Sequence[bytes]) -> Tuple[np.ndarray, int]:
+        """Counts of k-mer strings (any case; canonicalised on the device like the `query` subcommand does on the host).
+        Returns (counts, number of invalid k-mers)."""
+        blob = b"".join(bytes(x) for x in kmers)
+        if len(blob) != len(kmers) * self.k:
+            raise KmeRustError(f"every query k-mer must have length {self.k}")
+        arr = np.frombuffer(blob, dtype=np.uint8)
+        out = np.zeros(len(kmers), dtype=np.uint64)
+        bad = C.c_uint64(0)
+        if len(kmers):
+            _check(self._L.kmg_query_ascii(self._ctx, arr.ctypes.data, len(kmers), out.ctypes.data, C.byref(bad)), self._ctx)
+        return out, bad.value
+
+    @classmethod
+    def open_index(cls, path, device: int = -1) -> "GpuKmerCounter":
+        """kmg_index_open: a .kmix file as a ready-to-query counter on the device (src/index.rs:199-216, :282-401)."""
+        L = _lib.load()
+        ctx = C.c_void_p()
+        st = L.kmg_index_open(os.fspath(path).encode(), device, C.byref(ctx))
+        if st != _lib.KMG_OK:
+            msg = (L.kmg_last_error(None) or b"").decode() or L.kmg_status_string(st).decode()
+            if st == _lib.KMG_ERR_PARSE:
+                raise InvalidIndexError(msg)
+            if st == _lib.KMG_ERR_IO:
+                raise KmeRustError(msg)
+            raise GpuError(st, msg)
+        self = cls.__new__(cls)
+        self._L, self._ctx = L, ctx
+        self.k = 0
+        s = self.finalize()
+        self.k = int(L.kmg_ctx_k(ctx))
+        return self
 
     def save_kmix(self, path):
         _check(self._L.kmg_save_kmix(self._ctx, os.fspath(path).encode()), self._ctx)

@@ -1059,6 +1059,7 @@ const Crc32 &crc_tables() { static Crc32 c; return c; }
 
 // =================================================================================================
 KMG_EXPORT uint32_t kmg_abi_version(void) { return KMG_ABI_VERSION; }
+KMG_EXPORT uint32_t kmg_ctx_k(const kmg_ctx *c) { return c ? (uint32_t)c->k : 0u; }
 
 KMG_EXPORT const char *kmg_status_string(kmg_status s) {
   switch (s) {
@@ -2647,6 +2648,138 @@ KMG_EXPORT kmg_status kmg_write_text(kmg_ctx *c, uint64_t min_count, int format,
   const bool ok = to_stdout ? fflush(f) == 0 : fclose(f) == 0;
   if (s == KMG_OK && !ok) return fail(c, KMG_ERR_IO, std::string("short write to ") + path);
   return s;
+}
+
+
+// ---- index queries and loading (src/index.rs:127-131 KmerIndex::get, :199-216 load_index, :282-401 read_index; the consumer is
+// the `query` subcommand, src/main.rs:233-281) --------------------------------------------------------------------------------
+namespace {
+kmg_status query_device_keys(kmg_ctx *c, const uint64_t *d_keys, uint64_t n, uint64_t *counts_out) {
+  CU(c, cudaStreamSynchronize(c->copy_stream));
+  if (c->mode == kmg_ctx::MODE_PARTITIONED) { kmg_status s = consolidate(c); if (s != KMG_OK) return s; }
+  uint64_t *d_counts = nullptr;
+  CU(c, pool_alloc(c, &d_counts, std::max<uint64_t>(n, 1) * 8));
+  const bool part = c->mode == kmg_ctx::MODE_PARTITIONED;
+  TableView v = view_of(c);
+  cudaError_t e = cudaSuccess;
+  if (part && !c->has_result) e = cudaMemsetAsync(d_counts, 0, n * 8, c->stream);  // nothing counted yet
+  else e = launch_query(v, c->table, part ? c->result.d_seg_start : nullptr, part ? c->result.d_seg_len : nullptr, std::max<uint32_t>(c->n_coarse, 1),
+                        std::max<uint32_t>(c->n_sub, 1), c->shm ? c->sh_world : 1, c->shm ? c->sh_rank : 0, d_keys, n, d_counts, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(counts_out, d_counts, n * 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  pool_free(c, d_counts);
+  if (e != cudaSuccess) return cuda_fail(c, e, "query");
+  return KMG_OK;
+}
+}  // namespace
+
+// counts_out[i] = count of the canonical packed key keys[i] (0 when absent).  HOST arrays.
+KMG_EXPORT kmg_status kmg_query_keys(kmg_ctx *c, const uint64_t *keys, uint64_t n, uint64_t *counts_out) {
+  if (!c || (n && (!keys || !counts_out))) return KMG_ERR_INVALID_ARG;
+  if (n == 0) return KMG_OK;
+  CU(c, cudaSetDevice(c->device));
+  uint64_t *d_keys = nullptr;
+  CU(c, pool_alloc(c, &d_keys, n * 8));
+  cudaError_t e = cudaMemcpyAsync(d_keys, keys, n * 8, cudaMemcpyHostToDevice, c->stream);
+  kmg_status s = e == cudaSuccess ? query_device_keys(c, d_keys, n, counts_out) : cuda_fail(c, e, "H2D query keys");
+  pool_free(c, d_keys);
+  return s;
+}
+
+// n k-mers as ASCII, k bytes each, back to back, any case: canonicalised on the device (upper-case, pack, min(fwd, rc) -- what the
+// query subcommand does on the host) and looked up.  A k-mer with a byte outside ACGTacgt counts 0 and sets *n_invalid_out.
+KMG_EXPORT kmg_status kmg_query_ascii(kmg_ctx *c, const uint8_t *kmers, uint64_t n, uint64_t *counts_out, uint64_t *n_invalid_out) {
+  if (!c || (n && (!kmers || !counts_out))) return KMG_ERR_INVALID_ARG;
+  if (n_invalid_out) *n_invalid_out = 0;
+  if (n == 0) return KMG_OK;
+  CU(c, cudaSetDevice(c->device));
+  uint8_t *d_kmers = nullptr;
+  uint64_t *d_keys = nullptr;
+  CU(c, pool_alloc(c, &d_kmers, n * (uint64_t)c->k));
+  cudaError_t e = pool_alloc(c, &d_keys, n * 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_kmers, kmers, n * (uint64_t)c->k, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = launch_query_pack(d_kmers, n, c->k, d_keys, c->stream);
+  kmg_status s = e == cudaSuccess ? query_device_keys(c, d_keys, n, counts_out) : cuda_fail(c, e, "query (pack)");
+  if (s == KMG_OK && n_invalid_out) {
+    std::vector<uint64_t> hk(n);
+    e = cudaMemcpy(hk.data(), d_keys, n * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) s = cuda_fail(c, e, "query (invalid k-mers)");
+    else for (uint64_t x : hk) *n_invalid_out += x == EMPTY_KEY;
+  }
+  pool_free(c, d_kmers); pool_free(c, d_keys);
+  return s;
+}
+
+// Open a .kmix index as a ready-to-query context on `device`: the checks of read_index in the reference's order (size >= 18,
+// magic, CRC, version, k, n * 16 == data size; src/index.rs:282-401), then the records are streamed to the device and
+// upserted.  Errors: KMG_ERR_IO (cannot read) / KMG_ERR_PARSE (invalid index; message via kmg_last_error(NULL)).
+KMG_EXPORT kmg_status kmg_index_open(const char *path, int32_t device, kmg_ctx **out) {
+  if (!path || !out) return KMG_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (has_gz_suffix(path)) return fail(nullptr, KMG_ERR_INVALID_ARG, "kmg_index_open reads uncompressed .kmix files; gunzip on the host side");
+  FILE *f = fopen(path, "rb");
+  if (!f) return fail(nullptr, KMG_ERR_IO, std::string("failed to read index from '") + path + "'");
+  struct Closer { FILE *f; ~Closer() { if (f) fclose(f); } } closer{f};
+  if (fseeko(f, 0, SEEK_END) != 0) return fail(nullptr, KMG_ERR_IO, "seek failed");
+  const uint64_t size = (uint64_t)ftello(f);
+  rewind(f);
+  if (size < 18) return fail(nullptr, KMG_ERR_PARSE, "file too small");
+  uint8_t hdr[14];
+  if (fread(hdr, 1, 14, f) != 14) return fail(nullptr, KMG_ERR_IO, "short read");
+  if (memcmp(hdr, "KMIX", 4) != 0) return fail(nullptr, KMG_ERR_PARSE, "invalid magic bytes (not a kmerust index file)");
+  // CRC over everything before the last four bytes, streamed (the reference buffers the whole file)
+  const Crc32 &T = crc_tables();
+  uint32_t crc = ~T.update(~0u, hdr, 14);
+  const uint64_t body = size - 18;
+  std::vector<uint8_t> buf((size_t)std::min<uint64_t>(std::max<uint64_t>(body, 16), 256ull << 20));
+  for (uint64_t done = 0; done < body;) {
+    const size_t m = (size_t)std::min<uint64_t>(buf.size(), body - done);
+    if (fread(buf.data(), 1, m, f) != m) return fail(nullptr, KMG_ERR_IO, "short read");
+    crc = crc32_combine(crc, crc32_parallel(buf.data(), m), m);
+    done += m;
+  }
+  uint8_t tail[4];
+  if (fread(tail, 1, 4, f) != 4) return fail(nullptr, KMG_ERR_IO, "short read");
+  const uint32_t stored = (uint32_t)tail[0] | (uint32_t)tail[1] << 8 | (uint32_t)tail[2] << 16 | (uint32_t)tail[3] << 24;
+  if (stored != crc) { char m[96]; snprintf(m, sizeof m, "checksum mismatch (expected %#x, got %#x)", stored, crc); return fail(nullptr, KMG_ERR_PARSE, m); }
+  if (hdr[4] != 1) return fail(nullptr, KMG_ERR_PARSE, "unsupported version " + std::to_string(hdr[4]));
+  const uint32_t k = hdr[5];
+  if (k < 1 || k > 32) return fail(nullptr, KMG_ERR_PARSE, "invalid k-mer length: k-mer length " + std::to_string(k) + " is out of range (must be 1-32)");
+  uint64_t n = 0;
+  for (int b = 0; b < 8; ++b) n |= (uint64_t)hdr[6 + b] << (8 * b);
+  if (body != n * 16) return fail(nullptr, KMG_ERR_PARSE, "data size mismatch (expected " + std::to_string(n * 16) + " bytes, got " + std::to_string(body) + " bytes)");
+  kmg_config cfg{};
+  cfg.abi_version = KMG_ABI_VERSION; cfg.k = k; cfg.device = device; cfg.expected_distinct = std::max<uint64_t>(n, 1);
+  kmg_ctx *c = nullptr;
+  kmg_status s = kmg_create(&cfg, &c);
+  if (s != KMG_OK) return s;
+  auto bail = [&](kmg_status st) { g_create_error = c->err; kmg_destroy(c); return st; };
+  if (n) {
+    if (fseeko(f, 14, SEEK_SET) != 0) return bail(fail(c, KMG_ERR_IO, "seek failed"));
+    const uint64_t CH = std::min<uint64_t>(n, 1ull << 24);  // records per piece (256 MiB)
+    void *d_pairs = nullptr;
+    uint64_t *dk = nullptr, *dc = nullptr;
+    cudaError_t e = pool_alloc(c, &d_pairs, CH * 16);
+    if (e == cudaSuccess) e = pool_alloc(c, &dk, CH * 8);
+    if (e == cudaSuccess) e = pool_alloc(c, &dc, CH * 8);
+    if (e != cudaSuccess) return bail(cuda_fail(c, e, "cudaMalloc(index load)"));
+    buf.resize((size_t)(CH * 16));
+    for (uint64_t done = 0; done < n && s == KMG_OK;) {
+      const uint64_t m = std::min<uint64_t>(CH, n - done);
+      if (fread(buf.data(), 16, m, f) != m) { s = fail(c, KMG_ERR_IO, "short read"); break; }
+      e = cudaMemcpyAsync(d_pairs, buf.data(), m * 16, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) e = launch_deinterleave_pairs(d_pairs, m, dk, dc, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) { s = cuda_fail(c, e, "index load"); break; }
+      s = kmg_insert_keys_device(c, dk, dc, m);
+      done += m;
+    }
+    pool_free(c, d_pairs); pool_free(c, dk); pool_free(c, dc);
+    if (s == KMG_OK) s = kmg_finalize(c, nullptr);
+    if (s != KMG_OK) return bail(s);
+  }
+  *out = c;
+  return KMG_OK;
 }
 
 KMG_EXPORT kmg_status kmg_progress(const kmg_ctx *c, uint64_t *records, uint64_t *bases) {

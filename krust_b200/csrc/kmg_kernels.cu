@@ -1064,6 +1064,68 @@ __global__ void fx_marks_to_bits_kernel(const uint8_t *__restrict__ mark, uint64
   }
 }
 
+// =================================================================================================
+// Index queries (replaces KmerIndex::get, src/index.rs:127-131, and the canonicalisation the `query` subcommand does first,
+// src/main.rs:254-266): batched look-ups against whichever table the context holds.
+// =================================================================================================
+// ASCII k-mers (n x k bytes, any case) -> canonical packed keys; ~0 for a k-mer with a non-ACGT byte (never a canonical key)
+__global__ void query_pack_kernel(const uint8_t *__restrict__ kmers, uint64_t n, int k, uint64_t *__restrict__ keys) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t *p = kmers + i * (uint64_t)k;
+    uint64_t fwd = 0;
+    bool ok = true;
+    for (int j = 0; j < k; ++j) {
+      const uint8_t b = p[j] & 0xDF;
+      ok &= b == 'A' || b == 'C' || b == 'G' || b == 'T';
+      fwd = (fwd << 2) | (uint64_t)(((p[j] >> 1) ^ (p[j] >> 2)) & 3u);
+    }
+    const uint64_t rc = revcomp(fwd & kmer_mask(k), k);
+    fwd &= kmer_mask(k);
+    keys[i] = ok ? (fwd < rc ? fwd : rc) : EMPTY_KEY;
+  }
+}
+// one warp per query: hash table -> probe sequence; dense array -> direct; partitioned run -> the lanes sweep the key's partition
+__global__ void __launch_bounds__(256) query_kernel(TableView v, HashTable t, const uint64_t *__restrict__ seg_start, const uint64_t *__restrict__ seg_len,
+                                                    uint32_t n_coarse, uint32_t n_sub, uint32_t shard_world, uint32_t shard_rank,
+                                                    const uint64_t *__restrict__ keys, uint64_t n, uint64_t *__restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t i = warp0; i < n; i += n_warps) {
+    const uint64_t key = keys[i];
+    uint64_t found = 0;
+    if (key == EMPTY_KEY) { if (lane == 0) counts[i] = 0; continue; }
+    if (v.dense) {
+      if (lane == 0) found = key < v.n ? v.dense[key] : 0;
+    } else if (v.pair_keys) {
+      const uint64_t m = mix64(key);
+      uint32_t g = coarse_of_mix(m, n_coarse * shard_world);
+      if (g / n_coarse == shard_rank) {  // a sharded table answers for its own keys only
+        const uint64_t p = (uint64_t)(g - shard_rank * n_coarse) * n_sub + sub_of_mix(m, n_sub);
+        const uint64_t b = seg_start[p], e = b + seg_len[p];
+        for (uint64_t j = b + lane; j < e; j += 32)
+          if (v.pair_keys[j] == m) found = v.pair_counts[j];
+      }
+    } else if (t.slots && lane == 0) {
+      uint64_t slot = slot_of(key, t.cap);
+      for (uint64_t probe = 0; probe < t.cap; ++probe) {
+        const ulonglong2 sl = reinterpret_cast<const ulonglong2 *>(t.slots)[slot];
+        if (sl.x == key) { found = sl.y + 1; break; }
+        if (sl.x == EMPTY_KEY) break;
+        slot = slot + 1 == t.cap ? 0 : slot + 1;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) found |= __shfl_xor_sync(0xffffffffu, found, o);  // at most one lane holds a non-zero count
+    if (lane == 0) counts[i] = found;
+  }
+}
+__global__ void deinterleave_pairs_kernel(const ulonglong2 *__restrict__ in, uint64_t n, uint64_t *__restrict__ keys, uint64_t *__restrict__ counts) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const ulonglong2 r = in[i];
+    keys[i] = r.x; counts[i] = r.y;
+  }
+}
+
 // ---- output formatting on the device (replaces the per-k-mer writeln! of src/run.rs:452-470 / src/builder.rs:406-429 and
 // unpack_to_string, src/kmer.rs:431-456): record i of a sorted piece becomes "{kmer}\t{count}\n" (tsv) or ">{count}\n{kmer}\n" (fasta)
 __device__ __forceinline__ uint32_t dec_digits(uint64_t v) {
@@ -1376,6 +1438,25 @@ cudaError_t launch_marks_to_bits(const uint8_t *d_mark, uint64_t n_bases, uint64
   return cudaGetLastError();
 }
 
+cudaError_t launch_query_pack(const uint8_t *d_kmers, uint64_t n, int k, uint64_t *d_keys, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  query_pack_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(d_kmers, n, k, d_keys);
+  return cudaGetLastError();
+}
+cudaError_t launch_query(const TableView &v, HashTable t, const uint64_t *d_seg_start, const uint64_t *d_seg_len, uint32_t n_coarse, uint32_t n_sub,
+                         uint32_t shard_world, uint32_t shard_rank, const uint64_t *d_keys, uint64_t n, uint64_t *d_counts, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  query_kernel<<<grid_for(n * 32, 256, 8), 256, 0, s>>>(v, t, d_seg_start, d_seg_len, n_coarse, n_sub, shard_world, shard_rank, d_keys, n, d_counts);
+  return cudaGetLastError();
+}
+cudaError_t launch_deinterleave_pairs(const void *d_in, uint64_t n, uint64_t *d_keys, uint64_t *d_counts, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  deinterleave_pairs_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(static_cast<const ulonglong2 *>(d_in), n, d_keys, d_counts);
+  return cudaGetLastError();
+}
 cudaError_t launch_text_len(const uint64_t *d_counts, uint64_t n, int k, int fasta, uint64_t *d_lens, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   g_launches.fetch_add(1, std::memory_order_relaxed);

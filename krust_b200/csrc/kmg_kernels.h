@@ -178,6 +178,11 @@ cudaError_t launch_fastx_scatter(const uint8_t *d_buf, uint64_t n, int is_fastq,
                                  uint8_t *d_out_mark, unsigned long long *d_n_records, uint32_t *d_err, cudaStream_t s);
 cudaError_t launch_fastx_apply_pending(uint32_t *d_pending, uint8_t *d_mark_first_new, cudaStream_t s);
 cudaError_t launch_marks_to_bits(const uint8_t *d_mark, uint64_t n_bases, uint64_t n_words_total, uint32_t *d_start, cudaStream_t s);
+// index queries / loading
+cudaError_t launch_query_pack(const uint8_t *d_kmers, uint64_t n, int k, uint64_t *d_keys, cudaStream_t s);
+cudaError_t launch_query(const TableView &v, HashTable t, const uint64_t *d_seg_start, const uint64_t *d_seg_len, uint32_t n_coarse, uint32_t n_sub,
+                         uint32_t shard_world, uint32_t shard_rank, const uint64_t *d_keys, uint64_t n, uint64_t *d_counts, cudaStream_t s);
+cudaError_t launch_deinterleave_pairs(const void *d_in, uint64_t n, uint64_t *d_keys, uint64_t *d_counts, cudaStream_t s);
 // text emitters / index records of a sorted piece (formatting happens on the device)
 cudaError_t launch_text_len(const uint64_t *d_counts, uint64_t n, int k, int fasta, uint64_t *d_lens, cudaStream_t s);
 cudaError_t launch_text_write(const uint64_t *d_keys, const uint64_t *d_counts, const uint64_t *d_offs, uint64_t n, int k, int fasta, uint8_t *d_out,

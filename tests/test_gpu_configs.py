@@ -250,3 +250,46 @@ def test_c1_tsv_text_100mbp_equals_sorted_oracle_text(tmp_path):
         want[:, :k] = lut[((kk[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)]
         want[:, k] = ord("\t"); want[:, k + 1] = ocounts[i:i + step].astype(np.uint8) + ord("0"); want[:, k + 2] = ord("\n")
         assert (got[i:i + step] == want).all()
+
+
+def test_index_round_trip_and_batched_queries_on_the_device(tmp_path):
+    """save -> kmg_index_open -> kmg_query_*: the `query` subcommand's semantics (src/main.rs:233-281: upper-case, canonicalise,
+    look up; absent -> 0) batched on the device, for every table kind; index round trips like src/index.rs:510-524."""
+    rng = np.random.default_rng(3)
+    recs = [bytes(rng.choice(list(b"ACGTN"), p=[.245, .245, .245, .245, .02], size=int(rng.integers(50, 4000))).tolist()) for _ in range(200)]
+    recs.append(b"A" * 3000)
+    for k, flags in ((1, 0), (5, 0), (16, _lib.KMG_FLAG_FORCE_HASH), (21, PART), (32, PART), (21, 0)):
+        okeys, ocounts, _ = orc.count_records(k, recs, mode="rolling")
+        table = dict(zip(okeys.tolist(), ocounts.tolist()))
+        p = tmp_path / f"q{k}.kmix"
+        # queries: present keys, absent keys, k-mer strings in both orientations and cases, an invalid one
+        absent = np.array([x for x in rng.integers(0, 4 ** k, size=300, dtype=np.uint64).tolist() if x not in table][:100] or [0], dtype=np.uint64)
+        qk = np.concatenate([okeys[:: max(1, len(okeys) // 500)], absent])
+        want = np.array([table.get(int(x), 0) for x in qk], dtype=np.uint64)
+        strs = [kb.unpack_to_string(int(x), k).encode() for x in okeys[:50]]
+        comp = bytes.maketrans(b"ACGT", b"TGCA")
+        strs += [s.translate(comp)[::-1].lower() for s in strs[:25]] + [b"N" * k]
+        want_s = [table[int(x)] for x in okeys[:50]] + [table[int(x)] for x in okeys[:25]] + [0]
+        with kb.GpuKmerCounter(k, flags=flags, parts_log2=6 if flags == PART else 0) as c:
+            c.count_records(recs)
+            c.finalize(False)
+            assert (c.query_keys(qk) == want).all()
+            got_s, bad = c.query_kmers(strs)
+            assert got_s.tolist() == want_s and bad == 1
+            c.save_kmix(p)
+        with kb.GpuKmerCounter.open_index(p) as idx:
+            assert idx.k == k
+            s = idx.finalize()
+            assert s["n_distinct"] == len(okeys) and s["n_windows"] == int(ocounts.sum())
+            assert (idx.query_keys(qk) == want).all()
+            got_s, bad = idx.query_kmers(strs)
+            assert got_s.tolist() == want_s and bad == 1
+            gk, gc = idx.export(1, True)
+            assert (gk == okeys).all() and (gc == ocounts).all()
+            p2 = tmp_path / "again.kmix"
+            idx.save_kmix(p2)
+        assert p2.read_bytes() == p.read_bytes() == orc.kmix_encode(k, okeys, ocounts)
+    empty = tmp_path / "empty.kmix"
+    empty.write_bytes(orc.kmix_encode(7, np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint64)))
+    with kb.GpuKmerCounter.open_index(empty) as idx:
+        assert idx.k == 7 and idx.query_keys(np.array([5], dtype=np.uint64)).tolist() == [0]

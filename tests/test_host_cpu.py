@@ -227,3 +227,49 @@ def test_sharded_kmix_crc_combination_on_host(tmp_path):
         assert kb.load_index(p).k().get() == 21
     with pytest.raises(kb.KmeRustError):
         kb.kmix_begin(tmp_path / "x.kmix.gz")
+
+
+def test_index_open_rejects_invalid_files_like_the_reference(tmp_path):
+    """kmg_index_open validates before it touches CUDA: the checks and their order are read_index's
+    (src/index.rs:282-401; reference tests src/index.rs:527-573: too small, bad magic, flipped byte)."""
+    good = orc.kmix_encode(5, np.array([1, 7, 300], dtype=np.uint64), np.array([2, 9, 1], dtype=np.uint64))
+    cases = {"small": (good[:10], "file too small"), "magic": (b"XMIX" + good[4:], "invalid magic"),
+             "flip": (good[:20] + bytes([good[20] ^ 1]) + good[21:], "checksum mismatch"),
+             "trunc": (good[:-20] + good[-4:], "checksum mismatch")}
+    import struct, zlib
+    def with_crc(body):
+        return body + struct.pack("<I", zlib.crc32(body) & 0xFFFFFFFF)
+    cases["version"] = (with_crc(good[:4] + b"\x02" + good[5:-4]), "unsupported version 2")
+    cases["k"] = (with_crc(good[:5] + b"\x28" + good[6:-4]), "invalid k-mer length")
+    cases["size"] = (with_crc(good[:6] + struct.pack("<Q", 9) + good[14:-4]), "data size mismatch")
+    for name, (blob, msg) in cases.items():
+        p = tmp_path / f"{name}.kmix"
+        p.write_bytes(blob)
+        with pytest.raises(kb.InvalidIndexError) as e:
+            kb.GpuKmerCounter.open_index(p)
+        assert msg in str(e.value), (name, str(e.value))
+        with pytest.raises(Exception):
+            kb.load_index(p)            # the host-side reader rejects the same files
+    with pytest.raises(kb.KmeRustError):
+        kb.GpuKmerCounter.open_index(tmp_path / "missing.kmix")
+
+
+def test_rust_sys_bindings_are_generated_from_the_header():
+    """bindings/rust/kmerust-gpu-sys/src/lib.rs cannot be compiled here (no Rust toolchain): it is GENERATED from
+    include/kmerust_gpu.h by tools/gen_rust_sys.py, and this test fails when the committed file and the header drift."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(ROOT, "tools", "gen_rust_sys.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    committed = open(gen.OUT).read()
+    assert committed == gen.render(), "run `python tools/gen_rust_sys.py` after changing include/kmerust_gpu.h"
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "kmerust_gpu.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(kmg_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(re.findall(r"pub fn (kmg_\w+)", committed))
+    # every sys function the safe wrapper calls exists
+    wrapper = open(os.path.join(ROOT, "bindings", "rust", "kmerust-gpu", "src", "lib.rs")).read()
+    assert set(re.findall(r"sys::(kmg_[a-z0-9_]+)\(", wrapper)) <= declared
+    # field-for-field agreement of the three #[repr(C)] structs with the ctypes mirror
+    for name, st in (("kmg_config", _lib.KmgConfig), ("kmg_summary", _lib.KmgSummary), ("kmg_batch", _lib.KmgBatch)):
+        body = re.search(r"pub struct %s \{(.*?)\}" % name, committed, flags=re.S).group(1)
+        assert re.findall(r"pub (\w+):", body) == [f for f, _ in st._fields_]
