@@ -117,6 +117,9 @@ struct kmg_ctx {
   bool sh_peer_ipc[8] = {false, false, false, false, false, false, false, false};
   uint64_t sh_sent = 0, sh_recv_keys = 0, sh_rounds = 0, sh_exact_rounds = 0;
   std::vector<uint64_t> sh_hist_vals, sh_hist_freqs;  // merged histogram of the last kmg_shard_histogram
+  int feed_kind = 0;        // partitioned path: 1 = runs binned by this context's own coarse function, 2 = blocks adopted from a sender
+                            // that binned by (owner, bin) -- the two bin functions differ, so one context takes only one kind
+  bool poisoned = false;    // a re-split failed half way: runs with different partitionings coexist; only kmg_reset / kmg_destroy are safe
   double dedup_ratio = 1.0;  // distinct keys per raw entry seen by the last consolidation (sizes the next consolidated run)
   double plan_scale = 1.0;  // kmg_count_ascii with a quality filter: (bases of the whole call) / (bases of its first chunk)
   int building_run = 0;  // > 0 while refine_to_run derives a run from the current plan: a nested consolidate must not re-split
@@ -516,6 +519,9 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
 
 // A1 over the packed stream: coarse count pass, exact offsets, coarse scatter; then A2.
 kmg_status scan_to_run(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
+  if (c->poisoned) return fail(c, KMG_ERR_STATE, "context is inconsistent after a failed re-split: kmg_reset it");
+  if (c->feed_kind == 2) return fail(c, KMG_ERR_STATE, "context holds blocks adopted from a sender (kmg_adopt_coarse_device): it cannot also scan input itself");
+  c->feed_kind = 1;
   const uint64_t n_tiles = n_words_total / TILE_WORDS;
   const uint64_t max_tiles = ((1ull << 32) - 1) / ((uint64_t)TILE_WORDS * 32);  // < 2^32 windows per launch
   const uint32_t P1 = c->n_coarse;
@@ -589,6 +595,9 @@ kmg_status scan_to_run(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
 
 // weighted keys (device) -> one run (the receive side of the multi-GPU exchange)
 kmg_status keys_to_run(kmg_ctx *c, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n) {
+  if (c->poisoned) return fail(c, KMG_ERR_STATE, "context is inconsistent after a failed re-split: kmg_reset it");
+  if (c->feed_kind == 2) return fail(c, KMG_ERR_STATE, "context holds blocks adopted from a sender (kmg_adopt_coarse_device): it cannot also take plain keys");
+  c->feed_kind = 1;
   const uint32_t P1 = c->n_coarse;
   unsigned long long *d_cnt = c->d_part, *d_start = c->d_part + MAX_PARTS, *d_cur = c->d_part + 2 * MAX_PARTS;
   const uint64_t max_n = (1ull << 32) - 1;
@@ -641,7 +650,10 @@ kmg_status resplit_runs(kmg_ctx *c, uint32_t m) {
     *r = std::move(nr);
   }
   c->in_resplit = false;
-  if (st != KMG_OK) return st;  // NOTE: runs already re-split and runs not yet re-split must not be mixed -- the caller gives up
+  if (st != KMG_OK) {  // runs already re-split and runs not yet re-split coexist now: refuse everything but a reset
+    c->poisoned = true;
+    return fail(c, st, c->err + " (while re-splitting the runs: the context must be reset)");
+  }
   c->n_sub *= m;
   c->n_parts = P_old * m;
   return KMG_OK;
@@ -1184,6 +1196,7 @@ KMG_EXPORT kmg_status kmg_reset(kmg_ctx *c) {
     c->runs.clear();
     if (c->has_result) free_run(c, c->result);
     c->has_result = false; c->pending_bytes = 0; c->n_consolidations = 0; c->dedup_ratio = 1.0;
+    c->feed_kind = 0; c->poisoned = false;
     c->fused_valid = c->fused_cached = false;
   }
   CU(c, cudaMemsetAsync(c->d_counters, 0, CTR_N * sizeof(unsigned long long), c->stream));
@@ -1567,6 +1580,9 @@ KMG_EXPORT kmg_status kmg_adopt_coarse_device(kmg_ctx *c, const uint64_t *d_keys
   if (off[n_bins] != n) return fail(c, KMG_ERR_INVALID_ARG, "bin_counts do not add up to n");
   if (n == 0) return KMG_OK;
   if (!d_keys) return fail(c, KMG_ERR_INVALID_ARG, "d_keys is NULL");
+  if (c->poisoned) return fail(c, KMG_ERR_STATE, "context is inconsistent after a failed re-split: kmg_reset it");
+  if (c->feed_kind == 1) return fail(c, KMG_ERR_STATE, "context already holds runs binned by its own coarse function: adopted blocks (binned by owner and bin) cannot be mixed in");
+  c->feed_kind = 2;
   CU(c, cudaSetDevice(c->device));
   const size_t tmr = timer_begin(c, 0);
   kmg_status s = refine_to_run(c, const_cast<uint64_t *>(d_keys), nullptr, off, /*owns=*/false, /*sync=*/true, nullptr, nullptr, /*in_keys=*/true);

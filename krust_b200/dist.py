@@ -179,11 +179,11 @@ class ShardedKmerCounter:
             # all ranks must agree on P1: take the plan of the rank expecting the most keys
             mine = self.engine.plan(max(int(expected_keys_per_rank), int(seq.numel()), 1))
             dev0 = getattr(self.engine, "device", torch.device("cpu"))
-            t = torch.tensor([mine], dtype=torch.int64, device=dev0)
+            t = torch.tensor([mine, -mine], dtype=torch.int64, device=dev0)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            self._p1 = int(t.item())
-            if self._p1 != mine:
-                raise RuntimeError(f"ranks disagree on the partition plan ({mine} vs {self._p1}); pass the same expected_keys_per_rank")
+            self._p1 = int(t[0].item())
+            if self._p1 != -int(t[1].item()):   # EVERY rank sees the disagreement and raises: nobody is left waiting in a collective
+                raise RuntimeError(f"ranks disagree on the partition plan ({-int(t[1].item())}..{self._p1} coarse bins); pass the same expected_keys_per_rank")
         p1, world, k = self._p1, self.world, int(self.engine.k)
         n = int(seq.numel())
         # every rank must run the same number of exchanges: agree on the largest slice's choice

@@ -11,6 +11,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <optional>
 #include <sstream>
 #include <stdexcept>
@@ -228,7 +229,33 @@ class GpuKmerCounter {
     for (uint64_t i = 0; i < n; ++i) h[v[i]] = f[i];
     return h;
   }
-  void save_kmix(const std::string &path) { check(kmg_save_kmix(ctx_, path.c_str())); }
+  // A whole FASTA / FASTQ file image: records are found on the device (kmg_count_fastx).  false: the device parser refused the
+  // input (multi-line FASTQ ...) and the counter was reset -- feed it through read_with_quality() + count() instead.
+  bool count_file_image(const uint8_t *bytes, uint64_t len, bool is_fastq) {
+    uint64_t n = 0;
+    const kmg_status s = kmg_count_fastx(ctx_, bytes, len, is_fastq, &n);
+    if (s == KMG_ERR_PARSE) { check(kmg_reset(ctx_)); return false; }
+    check(s);
+    return true;
+  }
+  // fasta / tsv lines formatted on the device, sorted by k-mer (kmg_write_text; "-" = stdout)
+  uint64_t write_text(const std::string &path, OutputFormat fmt, uint64_t min_count) {
+    uint64_t recs = 0, bytes = 0;
+    check(kmg_write_text(ctx_, min_count, fmt == OutputFormat::Tsv ? KMG_TEXT_TSV : KMG_TEXT_FASTA, path.c_str(), &recs, &bytes));
+    return recs;
+  }
+  std::vector<uint64_t> query(const std::vector<std::string> &kmers, uint64_t *n_invalid = nullptr) {
+    std::string blob;
+    for (auto &q : kmers) blob += q;
+    std::vector<uint64_t> out(kmers.size());
+    uint64_t bad = 0;
+    if (!kmers.empty()) check(kmg_query_ascii(ctx_, reinterpret_cast<const uint8_t *>(blob.data()), kmers.size(), out.data(), &bad));
+    if (n_invalid) *n_invalid = bad;
+    return out;
+  }
+  // adopt a context opened by kmg_index_open
+  GpuKmerCounter(kmg_ctx *ctx, KmerLength k) : ctx_(ctx), k_(k) {}
+  void save_kmix(const std::string &path);  // defined after save_index (a .gz path goes through the host writer)
   Progress progress() const { Progress p{}; kmg_progress(ctx_, &p.sequences_processed, &p.bases_processed); return p; }
 };
 
@@ -362,7 +389,7 @@ inline void save_index(const KmerIndex &idx, const std::string &path) {
   std::vector<std::pair<uint64_t, uint64_t>> items(idx.counts().begin(), idx.counts().end());
   std::sort(items.begin(), items.end());
   for (auto &kv : items) { put_le(body, kv.first, 8); put_le(body, kv.second, 8); }
-  put_le(body, crc32(0L, reinterpret_cast<const Bytef *>(body.data()), (uInt)body.size()), 4);
+  put_le(body, crc32_z(0L, reinterpret_cast<const Bytef *>(body.data()), body.size()), 4);  // crc32_z: size_t length (indexes pass 4 GiB)
   if (ends_with(path, ".gz")) {
     gzFile g = gzopen(path.c_str(), "wb");
     if (!g || gzwrite(g, body.data(), (unsigned)body.size()) != (int)body.size()) { if (g) gzclose(g); throw IndexIoError("failed to write index to '" + path + "'"); }
@@ -380,7 +407,7 @@ inline KmerIndex load_index(const std::string &path) {
   if (d.size() < 18) throw InvalidIndexError("invalid index file '" + path + "': file too small");
   if (memcmp(d.data(), "KMIX", 4) != 0) throw InvalidIndexError("invalid index file '" + path + "': invalid magic bytes (not a kmerust index file)");
   const uint32_t stored = (uint32_t)get_le(d.data() + d.size() - 4, 4);
-  const uint32_t computed = (uint32_t)crc32(0L, d.data(), (uInt)(d.size() - 4));
+  const uint32_t computed = (uint32_t)crc32_z(0L, d.data(), d.size() - 4);
   if (stored != computed) {
     char buf[128];
     snprintf(buf, sizeof buf, "checksum mismatch (expected %#x, got %#x)", stored, computed);
@@ -393,6 +420,25 @@ inline KmerIndex load_index(const std::string &path) {
   PackedCounts m; m.reserve(n);
   for (uint64_t i = 0; i < n; ++i) m[get_le(d.data() + 14 + 16 * i, 8)] = get_le(d.data() + 22 + 16 * i, 8);
   return KmerIndex(KmerLength::create(d[5]), std::move(m));
+}
+
+// src/index.rs:156-196: the index straight from the device table; a path ending in .gz is gzip-wrapped like the reference does
+// (kmg_save_kmix itself refuses .gz names rather than writing raw bytes under them)
+inline void GpuKmerCounter::save_kmix(const std::string &path) {
+  if (!ends_with(path, ".gz")) { check(kmg_save_kmix(ctx_, path.c_str())); return; }
+  std::vector<uint64_t> keys, counts;
+  export_counts(0, false, keys, counts);
+  save_index(KmerIndex(k_, to_map(keys, counts)), path);
+}
+
+// src/index.rs:199-216 into device memory: a ready-to-query counter (kmg_index_open; .gz indexes go through load_index)
+inline std::unique_ptr<GpuKmerCounter> open_index_on_device(const std::string &path) {
+  kmg_ctx *ctx = nullptr;
+  const kmg_status s = kmg_index_open(path.c_str(), -1, &ctx);
+  if (s == KMG_ERR_PARSE) throw InvalidIndexError("invalid index file '" + path + "': " + kmg_last_error(nullptr));
+  if (s == KMG_ERR_IO) throw IndexIoError(kmg_last_error(nullptr));
+  if (s != KMG_OK) throw GpuError(s, kmg_last_error(nullptr));
+  return std::unique_ptr<GpuKmerCounter>(new GpuKmerCounter(ctx, KmerLength::create(kmg_ctx_k(ctx))));
 }
 
 }  // namespace kmerust

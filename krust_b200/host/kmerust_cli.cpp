@@ -19,14 +19,25 @@ static void die(const std::string &head, const std::string &msg) {
 static int run_query(int argc, char **argv) {
   if (argc != 4) { fprintf(stderr, "usage: %s query <index> <kmer>\n", argv[0]); return 2; }
   try {
-    KmerIndex idx = load_index(argv[2]);
     std::string kmer = argv[3];
-    for (auto &c : kmer) c = (char)toupper((unsigned char)c);
-    if (kmer.size() != idx.k().get())
-      die("Query error:", "k-mer length mismatch: query has " + std::to_string(kmer.size()) + " bases, index has k=" + std::to_string(idx.k().get()));
-    uint64_t packed;
-    try { packed = canonical_packed(kmer); } catch (const InvalidBaseError &e) { die("Invalid k-mer:", e.what()); return 1; }
-    printf("%llu\n", (unsigned long long)idx.get(packed).value_or(0));
+    const std::string ipath = argv[2];
+    if (ipath.size() >= 3 && ipath.compare(ipath.size() - 3, 3, ".gz") == 0) {  // gzip-wrapped index: host reader
+      KmerIndex idx = load_index(ipath);
+      for (auto &c : kmer) c = (char)toupper((unsigned char)c);
+      if (kmer.size() != idx.k().get())
+        die("Query error:", "k-mer length mismatch: query has " + std::to_string(kmer.size()) + " bases, index has k=" + std::to_string(idx.k().get()));
+      uint64_t packed;
+      try { packed = canonical_packed(kmer); } catch (const InvalidBaseError &e) { die("Invalid k-mer:", e.what()); return 1; }
+      printf("%llu\n", (unsigned long long)idx.get(packed).value_or(0));
+      return 0;
+    }
+    auto idx = open_index_on_device(ipath);  // records go to HBM, the look-up (canonicalisation included) runs there
+    if (kmer.size() != idx->k().get())
+      die("Query error:", "k-mer length mismatch: query has " + std::to_string(kmer.size()) + " bases, index has k=" + std::to_string(idx->k().get()));
+    uint64_t bad = 0;
+    const std::vector<uint64_t> got = idx->query({kmer}, &bad);
+    if (bad) { try { canonical_packed(kmer); } catch (const InvalidBaseError &e) { die("Invalid k-mer:", e.what()); } return 1; }
+    printf("%llu\n", (unsigned long long)got[0]);
   } catch (const KmeRustError &e) {
     die("Failed to load index:", e.what());
   }
@@ -97,7 +108,12 @@ int main(int argc, char **argv) {
   try {
     const KmerLength kl = KmerLength::create(k);
     GpuKmerCounter counter(kl, min_quality);
-    counter.count(read_with_quality(path, resolved));
+    bool fed = false;
+    if (path != "-") {  // file image -> device parser; refused inputs (multi-line FASTQ ...) take the host splitter below
+      const std::vector<uint8_t> image = slurp(path);
+      fed = counter.count_file_image(image.data(), image.size(), resolved == SequenceFormat::Fastq);
+    }
+    if (!fed) counter.count(read_with_quality(path, resolved));
     kmg_summary s = counter.finalize();
     if (!save.empty()) {  // the index holds ALL k-mers; --min-count only filters stdout (src/main.rs:155-212)
       try { counter.save_kmix(save); } catch (const KmeRustError &e) { die("Failed to save index:", e.what()); }
@@ -106,6 +122,9 @@ int main(int argc, char **argv) {
     std::ios::sync_with_stdio(false);
     if (format == OutputFormat::Histogram) {
       for (auto &kv : counter.histogram(min_count)) std::cout << kv.first << '\t' << kv.second << '\n';
+    } else if (format == OutputFormat::Fasta || format == OutputFormat::Tsv) {
+      std::cout.flush();
+      counter.write_text("-", format, min_count);  // lines are formatted on the device
     } else {
       std::vector<uint64_t> keys, counts;
       counter.export_counts(min_count, true, keys, counts);
