@@ -933,7 +933,7 @@ kmg_status scan_packed(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
   const uint64_t n_tiles = n_words_total / TILE_WORDS;
   uint64_t incoming = n_words_total * 32;  // upper bound of the keys this stream adds
   bool incoming_exact = false;
-  if (!c->use_dense && c->cfg.has_min_quality && c->mode != kmg_ctx::MODE_PARTITIONED) {
+  if (!c->use_dense && c->cfg.has_min_quality) {
     // a quality filter can remove almost every window (config C3 keeps ~3 %): plan the table / the partitions from the
     // countable windows (masks only, 0.25 B/base), not from the bases
     unsigned long long h_ok = 0;
@@ -951,7 +951,38 @@ kmg_status scan_packed(kmg_ctx *c, uint64_t n_words_total, bool has_start) {
     ms = migrate_to_partitioned(c, incoming);
     if (ms != KMG_OK) return ms;
   }
-  if (c->mode == kmg_ctx::MODE_PARTITIONED) return scan_to_run(c, n_words_total, has_start);
+  if (c->mode == kmg_ctx::MODE_PARTITIONED) {
+    static const bool no_sparse = getenv("KMG_NO_SPARSE") != nullptr;  // ablation
+    if (incoming_exact && !no_sparse && !c->shm && incoming * 8 < n_words_total * 32 && incoming < (1ull << 32) - 1) {
+      // sparse route: fewer than one window in eight survives the quality filter -- scan + compact the surviving keys, then partition
+      // those (the scatter kernels would pay their per-sub-tile work for every tile of the input)
+      if (incoming == 0) return KMG_OK;
+      uint64_t *d_keys = nullptr;
+      kmg_status st = alloc_or_consolidate(c, reinterpret_cast<void **>(&d_keys), incoming * 8, "sparse keys");
+      if (st != KMG_OK) return st;
+      const size_t tmr = timer_begin(c, 0);
+      unsigned long long h_n = 0;
+      cudaError_t e = cudaMemsetAsync(c->d_stats + 7, 0, 8, c->stream);
+      for (uint64_t tile0 = 0; e == cudaSuccess && tile0 < n_tiles;) {
+        const uint64_t tiles = std::min<uint64_t>(n_tiles - tile0, ((1ull << 32) - 1) / ((uint64_t)TILE_WORDS * 32));
+        ScanInput in;
+        in.bases = c->d_bases + tile0 * TILE_WORDS; in.valid = c->d_valid + tile0 * TILE_WORDS;
+        in.start = has_start ? c->d_start + tile0 * TILE_WORDS : nullptr;
+        in.n_tiles = tiles; in.k = c->k;
+        e = launch_scan_emit_keys(in, d_keys, c->d_stats + 7, c->stream);
+        tile0 += tiles;
+      }
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&h_n, c->d_stats + 7, 8, cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      timer_end(c, tmr);
+      if (e != cudaSuccess) { pool_free(c, d_keys); return cuda_fail(c, e, "sparse scan"); }
+      if (h_n != incoming) { pool_free(c, d_keys); return fail(c, KMG_ERR_STATE, "sparse scan: emitted keys differ from the counted windows"); }
+      st = keys_to_run(c, d_keys, nullptr, incoming);
+      pool_free(c, d_keys);
+      return st;
+    }
+    return scan_to_run(c, n_words_total, has_start);
+  }
   uint64_t tile0 = 0;
   const size_t tmr = timer_begin(c);
   while (tile0 < n_tiles) {

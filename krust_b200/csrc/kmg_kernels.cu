@@ -449,6 +449,62 @@ __device__ __forceinline__ void wait_stage(uint64_t *bars, int stage, uint32_t &
   if (stage == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
 }
 
+// ---- sparse inputs: scan + compact.  When a quality filter leaves only a few per cent of the windows (config C3: 2.5 %), the
+// partition scatter would still pay its per-sub-tile machinery for every tile.  This kernel only scans -- a word without a
+// countable window costs a mask test -- and appends the canonical keys of the survivors to a dense array: staged per sub-tile of
+// 8192 windows in shared memory (so the buffer can never overflow), one global reservation and a coalesced copy per sub-tile
+// that has keys at all.  The keys then take the ordinary keys -> run path (kmg_api.cu keys_to_run).
+constexpr int EMITK_SUB_WORDS = SCAN_THREADS;        // one word per thread and sub-tile
+constexpr int EMITK_CAP = EMITK_SUB_WORDS * 32;      // 8192 staged keys (64 KiB)
+struct KeyAppendEmit {
+  uint64_t *kbuf;  // smem staging
+  uint32_t *s_n;   // smem: keys staged so far in this sub-tile
+  template <int G>
+  __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
+    uint32_t pos = atomicAdd(s_n, (uint32_t)__popc(okg));
+#pragma unroll
+    for (int j = 0; j < G; ++j) if ((okg >> j) & 1u) kbuf[pos++] = key[j];
+  }
+};
+__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_emit_keys_kernel(ScanInput in, uint64_t *__restrict__ out, unsigned long long *cursor) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
+  uint64_t *kbuf = reinterpret_cast<uint64_t *>(smem_raw + 2 * sizeof(TileSmem));
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t s_n;
+  __shared__ unsigned long long s_gbase;
+  const int tid = threadIdx.x;
+  const bool has_start = in.start != nullptr;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); s_n = 0; }
+  __syncthreads();
+  uint64_t tile = blockIdx.x;
+  int stage = 0;
+  uint32_t phase0 = 0, phase1 = 0;
+  if (tile < in.n_tiles && tid == 0) issue_tile(in, &stages[0], &bars[0], tile);
+  for (; tile < in.n_tiles; tile += gridDim.x) {
+    const uint64_t next = tile + gridDim.x;
+    if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
+    wait_stage(bars, stage, phase0, phase1);
+    for (int sub = 0; sub < TILE_WORDS / EMITK_SUB_WORDS; ++sub) {
+      KeyAppendEmit e{kbuf, &s_n};
+      scan_word<8>(&stages[stage], sub * EMITK_SUB_WORDS + tid, in.k, has_start, e);
+      __syncthreads();
+      const uint32_t n = s_n;  // block-uniform
+      if (n) {
+        if (tid == 0) s_gbase = atomicAdd(cursor, (unsigned long long)n);
+        __syncthreads();
+        const unsigned long long g = s_gbase;
+        for (uint32_t i = tid; i < n; i += SCAN_THREADS) out[g + i] = kbuf[i];
+        __syncthreads();
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+      }
+    }
+    __syncthreads();  // everyone is done with this stage before it is refilled
+    stage ^= 1;
+  }
+}
+
 // pass 1 (count_pass_kernel): per-partition totals of the whole launch into part_counts[].
 __global__ void __launch_bounds__(SCAN_THREADS) partition_count_kernel(ScanInput in, uint32_t n_parts,
                                                                        unsigned long long *part_counts,
@@ -1248,6 +1304,18 @@ cudaError_t launch_synth_reads(uint64_t seed, uint32_t profile, uint64_t first_r
 template <class K>
 static cudaError_t set_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// canonical keys of all countable windows, appended to d_out from *d_cursor on (d_cursor is NOT reset here)
+cudaError_t launch_scan_emit_keys(const ScanInput &in, uint64_t *d_out, unsigned long long *d_cursor, cudaStream_t s) {
+  if (in.n_tiles == 0) return cudaSuccess;
+  const size_t smem = 2 * sizeof(TileSmem) + (size_t)EMITK_CAP * 8;
+  cudaError_t e = set_smem(scan_emit_keys_kernel, smem);
+  if (e != cudaSuccess) return e;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const unsigned grid = (unsigned)std::min<uint64_t>(in.n_tiles, (uint64_t)num_sms() * 2);
+  scan_emit_keys_kernel<<<grid, SCAN_THREADS, smem, s>>>(in, d_out, d_cursor);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_scan_hash(const ScanInput &in, HashTable t, unsigned long long *counters, uint32_t flags, cudaStream_t s) {

@@ -130,6 +130,7 @@ cudaError_t launch_synth_reads(uint64_t seed, uint32_t profile, uint64_t first_r
                                cudaStream_t s);
 cudaError_t launch_count_windows(const uint32_t *d_valid, const uint32_t *d_start, uint64_t n_words, int k, unsigned long long *d_out,
                                  cudaStream_t s);
+cudaError_t launch_scan_emit_keys(const ScanInput &in, uint64_t *d_out, unsigned long long *d_cursor, cudaStream_t s);
 cudaError_t launch_scan_hash(const ScanInput &in, HashTable t, unsigned long long *counters, uint32_t flags, cudaStream_t s);
 cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, unsigned long long *counters, uint32_t flags,
                               cudaStream_t s);
