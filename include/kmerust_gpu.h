@@ -107,7 +107,7 @@ typedef struct kmg_batch {
   uint64_t capacity_bases;
   uint64_t n_bases;    /* filled by the producer */
   uint64_t n_records;  /* filled by the producer (progress accounting only) */
-  uint32_t slot;       /* which of the double buffers this is (library-private) */
+  uint32_t slot;       /* which slot of the ring this is (library-private) */
 } kmg_batch;
 
 uint32_t kmg_abi_version(void);
@@ -140,7 +140,10 @@ kmg_status kmg_count_ascii(kmg_ctx *ctx, const uint8_t *seq, const uint8_t *qual
  * kmg_count_ascii after kmg_reset.  *n_records_out: records (header lines) seen. */
 kmg_status kmg_count_fastx(kmg_ctx *ctx, const uint8_t *buf, uint64_t len, int is_fastq, uint64_t *n_records_out);
 
-/* Pre-packed, zero-copy feed for the Rust reader layer (src/reader.rs, src/streaming.rs, src/mmap.rs). */
+/* Pre-packed, zero-copy feed for the Rust reader layer (src/reader.rs, src/streaming.rs, src/mmap.rs): a ring of four pinned
+ * batches (zeroed when handed out), each with its own device buffers.  kmg_submit_batch queues the batch's H2D copy on the copy
+ * stream at once and scans the batch submitted before it, so copies overlap the kernels while the producer fills the next
+ * batch; the last batch is scanned by kmg_finalize (or whichever call reads the table next). */
 kmg_status kmg_acquire_batch(kmg_ctx *ctx, kmg_batch *batch);
 kmg_status kmg_submit_batch(kmg_ctx *ctx, const kmg_batch *batch);
 

@@ -51,6 +51,9 @@ struct Staging {
   // pre-packed feed (kmg_acquire_batch)
   uint64_t *hp_bases = nullptr;
   uint32_t *hp_valid = nullptr, *hp_start = nullptr;
+  uint64_t *dp_bases = nullptr;                      // the slot's packed stream on the device (with the zero lead-in words)
+  uint32_t *dp_valid = nullptr, *dp_start = nullptr;
+  uint64_t hp_used_words = 0;                        // words the last producer may have written
 };
 
 }  // namespace
@@ -90,10 +93,12 @@ struct kmg_ctx {
   uint64_t packed_words = 0;  // capacity in words (excluding lead-in)
 
   uint64_t batch_bases = DEFAULT_BATCH_BASES;
-  Staging st[N_STAGE];  // the pre-packed feed uses slots 0 and 1 only
+  Staging st[N_STAGE];
   bool staging_ready = false, packed_feed_ready = false;
   uint64_t staging_cap = 0;
-  uint32_t next_slot = 0;    // pre-packed feed (0/1)
+  uint32_t next_slot = 0;    // pre-packed feed: next ring slot to hand out
+  int pending_slot = -1;     // pre-packed feed: batch whose copy is queued but which has not been scanned yet
+  uint64_t pending_words = 0, dp_words = 0;
   uint32_t next_ascii = 0;   // ASCII staging ring
 
   // partitioned pipeline (v2)
@@ -151,6 +156,7 @@ struct kmg_ctx {
 namespace {
 
 void shard_release(kmg_ctx *c);  // defined with the shard group code below
+kmg_status scan_pending_batch(kmg_ctx *c);  // pre-packed feed: scan the batch whose copy is in flight (defined with kmg_submit_batch)
 
 kmg_status fail(kmg_ctx *ctx, kmg_status s, const std::string &msg) {
   if (ctx) ctx->err = msg; else g_create_error = msg;
@@ -1148,6 +1154,7 @@ KMG_EXPORT void kmg_destroy(kmg_ctx *c) {
     if (s.hp_valid) cudaFreeHost(s.hp_valid);
     if (s.hp_start) cudaFreeHost(s.hp_start);
     cudaFree(s.d_seq); cudaFree(s.d_qual); cudaFree(s.d_off);
+    cudaFree(s.dp_bases); cudaFree(s.dp_valid); cudaFree(s.dp_start);
     if (s.h2d_done) cudaEventDestroy(s.h2d_done);
     if (s.compute_done) cudaEventDestroy(s.compute_done);
   }
@@ -1219,6 +1226,7 @@ KMG_EXPORT kmg_status kmg_reset(kmg_ctx *c) {
   if (!c) return KMG_ERR_INVALID_ARG;
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaStreamSynchronize(c->copy_stream));
+  c->pending_slot = -1;  // a submitted but unscanned pre-packed batch is forgotten with everything else
   if (c->use_dense) CU(c, cudaMemsetAsync(c->dense, 0, c->dense_n * 8, c->stream));
   else if (c->mode == kmg_ctx::MODE_TABLE) CU(c, launch_table_init(c->table, c->stream));
   else if (c->mode == kmg_ctx::MODE_PARTITIONED) {
@@ -1511,56 +1519,95 @@ KMG_EXPORT kmg_status kmg_count_fastx(kmg_ctx *c, const uint8_t *buf, uint64_t l
   return KMG_OK;
 }
 
+// ---- pre-packed, zero-copy feed (the Rust reader layer packs 2-bit words + masks straight into pinned memory) ------------------
+// N_STAGE pinned slots, each with its own packed device buffers.  kmg_submit_batch queues the slot's H2D copy on the copy stream
+// at once and then scans the batch submitted BEFORE it, so the copy of batch i overlaps the kernels of batch i-1 while the
+// producer fills batch i+1; the last batch is scanned by whichever call needs the table next (finalize, export, ...).
+namespace {
+kmg_status scan_pending_batch(kmg_ctx *c) {
+  if (c->pending_slot < 0) return KMG_OK;
+  Staging &s = c->st[c->pending_slot];
+  const uint64_t n_words_total = c->pending_words;
+  c->pending_slot = -1;
+  CU(c, cudaStreamWaitEvent(c->stream, s.h2d_done, 0));
+  // the scan reads the context's packed stream: point it at this slot's buffers for the duration of the call
+  uint64_t *sb = c->d_bases; uint32_t *sv = c->d_valid, *ss = c->d_start; const uint64_t sw = c->packed_words;
+  c->d_bases = s.dp_bases; c->d_valid = s.dp_valid; c->d_start = s.dp_start; c->packed_words = c->dp_words;
+  const kmg_status st = scan_packed(c, n_words_total, true);
+  c->d_bases = sb; c->d_valid = sv; c->d_start = ss; c->packed_words = sw;
+  if (st != KMG_OK) return st;
+  CU(c, cudaEventRecord(s.compute_done, c->stream));
+  s.compute_pending = true;
+  return KMG_OK;
+}
+}  // namespace
+
 KMG_EXPORT kmg_status kmg_acquire_batch(kmg_ctx *c, kmg_batch *b) {
   if (!c || !b) return KMG_ERR_INVALID_ARG;
   CU(c, cudaSetDevice(c->device));
   const uint64_t words = round_up((c->batch_bases + 31) / 32, TILE_WORDS);
   if (!c->packed_feed_ready) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < N_STAGE; ++i) {
       Staging &s = c->st[i];
       CU(c, cudaHostAlloc(&s.hp_bases, words * 8, cudaHostAllocDefault));
       CU(c, cudaHostAlloc(&s.hp_valid, words * 4, cudaHostAllocDefault));
       CU(c, cudaHostAlloc(&s.hp_start, words * 4, cudaHostAllocDefault));
+      memset(s.hp_bases, 0, words * 8); memset(s.hp_valid, 0, words * 4); memset(s.hp_start, 0, words * 4);
+      CU(c, cudaMalloc(&s.dp_bases, (LEAD_BASE_WORDS + words) * 8));
+      CU(c, cudaMalloc(&s.dp_valid, (LEAD_MASK_WORDS + words) * 4));
+      CU(c, cudaMalloc(&s.dp_start, (LEAD_MASK_WORDS + words) * 4));
+      CU(c, cudaMemsetAsync(s.dp_bases, 0, LEAD_BASE_WORDS * 8, c->stream));
+      CU(c, cudaMemsetAsync(s.dp_valid, 0, LEAD_MASK_WORDS * 4, c->stream));
+      CU(c, cudaMemsetAsync(s.dp_start, 0, LEAD_MASK_WORDS * 4, c->stream));
       if (!s.h2d_done) {
         CU(c, cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
       }
     }
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->dp_words = words;
     c->packed_feed_ready = true;
   }
+  if ((int)c->next_slot == c->pending_slot) {  // the ring is full: the oldest submitted batch must be scanned before its slot is handed out again
+    kmg_status st = scan_pending_batch(c);
+    if (st != KMG_OK) return st;
+  }
   Staging &s = c->st[c->next_slot];
-  if (s.h2d_pending) { CU(c, cudaEventSynchronize(s.h2d_done)); s.h2d_pending = false; }
-  memset(s.hp_bases, 0, words * 8); memset(s.hp_valid, 0, words * 4); memset(s.hp_start, 0, words * 4);
+  if (s.h2d_pending) { CU(c, cudaEventSynchronize(s.h2d_done)); s.h2d_pending = false; }  // the pinned words have left the host
+  if (s.hp_used_words) {  // hand out zeroed words (producers OR their bits in): only what the previous user touched
+    memset(s.hp_bases, 0, s.hp_used_words * 8); memset(s.hp_valid, 0, s.hp_used_words * 4); memset(s.hp_start, 0, s.hp_used_words * 4);
+    s.hp_used_words = 0;
+  }
   b->bases2bit = s.hp_bases; b->valid_bits = s.hp_valid; b->start_bits = s.hp_start;
   b->capacity_bases = c->batch_bases; b->n_bases = 0; b->n_records = 0; b->slot = c->next_slot;
-  c->next_slot ^= 1;
+  c->next_slot = (c->next_slot + 1) % N_STAGE;
   return KMG_OK;
 }
 
 KMG_EXPORT kmg_status kmg_submit_batch(kmg_ctx *c, const kmg_batch *b) {
   if (!c || !b) return KMG_ERR_INVALID_ARG;
   if (c->shm) return fail(c, KMG_ERR_STATE, "context belongs to a shard group: feed it with kmg_shard_count_ascii(_device)");
-  if (b->slot > 1 || !c->packed_feed_ready || b->bases2bit != c->st[b->slot].hp_bases)
+  if (b->slot >= (uint32_t)N_STAGE || !c->packed_feed_ready || b->bases2bit != c->st[b->slot].hp_bases)
     return fail(c, KMG_ERR_STATE, "batch was not obtained from kmg_acquire_batch");
   if (b->n_bases > b->capacity_bases) return fail(c, KMG_ERR_INVALID_ARG, "n_bases exceeds the batch capacity");
   if (b->n_bases == 0) return KMG_OK;
   CU(c, cudaSetDevice(c->device));
   Staging &s = c->st[b->slot];
   const uint64_t n_words = (b->n_bases + 31) / 32, n_words_total = round_up(n_words, TILE_WORDS);
-  kmg_status st = ensure_packed(c, n_words_total);
-  if (st != KMG_OK) return st;
-  // single compute stream: the packed device buffers are reused by every batch, so the copy is ordered behind
-  // the previous scan; the pinned buffer is free again once h2d_done fires.
-  CU(c, cudaMemcpyAsync(c->d_bases + LEAD_BASE_WORDS, s.hp_bases, n_words_total * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaMemcpyAsync(c->d_valid + LEAD_MASK_WORDS, s.hp_valid, n_words_total * 4, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaMemcpyAsync(c->d_start + LEAD_MASK_WORDS, s.hp_start, n_words_total * 4, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaEventRecord(s.h2d_done, c->stream));
+  s.hp_used_words = n_words_total;
+  // the copy goes out now, on the copy stream, as soon as the slot's device buffers are free (its previous scan has finished)
+  if (s.compute_pending) { CU(c, cudaStreamWaitEvent(c->copy_stream, s.compute_done, 0)); s.compute_pending = false; }
+  CU(c, cudaMemcpyAsync(s.dp_bases + LEAD_BASE_WORDS, s.hp_bases, n_words_total * 8, cudaMemcpyHostToDevice, c->copy_stream));
+  CU(c, cudaMemcpyAsync(s.dp_valid + LEAD_MASK_WORDS, s.hp_valid, n_words_total * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  CU(c, cudaMemcpyAsync(s.dp_start + LEAD_MASK_WORDS, s.hp_start, n_words_total * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  CU(c, cudaEventRecord(s.h2d_done, c->copy_stream));
   s.h2d_pending = true;
   c->h2d_bytes += n_words_total * 16;
-  st = scan_packed(c, n_words_total, true);
-  if (st != KMG_OK) return st;
   c->n_records += b->n_records; c->n_bases += b->n_bases;
-  return KMG_OK;
+  // ... and while it travels, the batch submitted before this one is scanned
+  kmg_status st = scan_pending_batch(c);
+  c->pending_slot = (int)b->slot; c->pending_words = n_words_total;
+  return st;
 }
 
 KMG_EXPORT kmg_status kmg_insert_keys_device(kmg_ctx *c, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n) {
@@ -2107,6 +2154,7 @@ KMG_EXPORT kmg_status kmg_shard_count_ascii(kmg_ctx *c, const uint8_t *seq, cons
 KMG_EXPORT kmg_status kmg_finalize(kmg_ctx *c, kmg_summary *out) {
   if (!c) return KMG_ERR_INVALID_ARG;
   CU(c, cudaSetDevice(c->device));
+  { kmg_status _fs = scan_pending_batch(c); if (_fs != KMG_OK) return _fs; }
   CU(c, cudaStreamSynchronize(c->copy_stream));
   kmg_status s = read_counters(c);
   if (s != KMG_OK) return s;
@@ -2138,6 +2186,7 @@ KMG_EXPORT kmg_status kmg_finalize(kmg_ctx *c, kmg_summary *out) {
 
 namespace {
 kmg_status count_filtered(kmg_ctx *c, uint64_t min_count, uint64_t *n, uint64_t shard_mod = 0, uint64_t shard_rem = 0) {
+  { kmg_status _fs = scan_pending_batch(c); if (_fs != KMG_OK) return _fs; }
   CU(c, cudaStreamSynchronize(c->copy_stream));
   if (c->mode == kmg_ctx::MODE_PARTITIONED) { kmg_status s = consolidate(c); if (s != KMG_OK) return s; }
   if (shard_mod <= 1 && fetch_fused_hist(c)) {
@@ -2228,6 +2277,7 @@ KMG_EXPORT kmg_status kmg_export_shard_device(kmg_ctx *c, uint64_t min_count, in
 KMG_EXPORT kmg_status kmg_histogram(kmg_ctx *c, uint64_t min_count, uint64_t *count_vals, uint64_t *freqs, uint64_t cap, uint64_t *n_out) {
   if (!c || !n_out) return KMG_ERR_INVALID_ARG;
   CU(c, cudaSetDevice(c->device));
+  { kmg_status _fs = scan_pending_batch(c); if (_fs != KMG_OK) return _fs; }
   CU(c, cudaStreamSynchronize(c->copy_stream));
   kmg_status s = read_counters(c);
   if (s != KMG_OK) return s;
@@ -2702,6 +2752,7 @@ KMG_EXPORT kmg_status kmg_write_text(kmg_ctx *c, uint64_t min_count, int format,
 // the `query` subcommand, src/main.rs:233-281) --------------------------------------------------------------------------------
 namespace {
 kmg_status query_device_keys(kmg_ctx *c, const uint64_t *d_keys, uint64_t n, uint64_t *counts_out) {
+  { kmg_status _fs = scan_pending_batch(c); if (_fs != KMG_OK) return _fs; }
   CU(c, cudaStreamSynchronize(c->copy_stream));
   if (c->mode == kmg_ctx::MODE_PARTITIONED) { kmg_status s = consolidate(c); if (s != KMG_OK) return s; }
   uint64_t *d_counts = nullptr;

@@ -230,35 +230,41 @@ def test_reference_named_entry_points(golden_dir, tmp_path):
 
 
 def test_prepacked_batch_feed():
-    """kmg_acquire_batch / kmg_submit_batch: the Rust reader's zero-copy path (2-bit words + valid/start bits)."""
+    """kmg_acquire_batch / kmg_submit_batch: the Rust reader's zero-copy path (2-bit words + valid/start bits), a ring of four
+    pinned batches whose copies overlap the previous batch's scan.  Ten batches (the ring wraps twice), every engine path."""
     rng = np.random.default_rng(31)
-    recs = [bytes(rng.choice(list(b"ACGTN"), p=[.24, .24, .24, .24, .04], size=int(rng.integers(1, 900))).tolist()) for _ in range(50)]
-    k = 17
-    oracle = orc.count_records(k, recs, mode="rolling")
+    recs = [bytes(rng.choice(list(b"ACGTN"), p=[.24, .24, .24, .24, .04], size=int(rng.integers(1, 900))).tolist()) for _ in range(500)]
     code = np.full(256, 255, dtype=np.uint8)
     for ch, v in zip(b"ACGTacgt", [0, 1, 2, 3, 0, 1, 2, 3]):
         code[ch] = v
-    with kb.GpuKmerCounter(k, batch_bases=65536, flags=_lib.KMG_FLAG_FORCE_HASH) as c:
-        b = c.acquire_batch()
-        words = (b.capacity_bases + 31) // 32
-        bases = np.ctypeslib.as_array(b.bases2bit, shape=(words,))
-        valid = np.ctypeslib.as_array(b.valid_bits, shape=(words,))
-        start = np.ctypeslib.as_array(b.start_bits, shape=(words,))
-        pos = 0
-        for r in recs:
-            start[pos // 32] |= np.uint32(1 << (31 - pos % 32))
-            for ch in r:
-                cd = code[ch]
-                if cd != 255:
-                    bases[pos // 32] |= np.uint64(int(cd) << (62 - 2 * (pos % 32)))
-                    valid[pos // 32] |= np.uint32(1 << (31 - pos % 32))
-                pos += 1
-        b.n_bases = pos
-        b.n_records = len(recs)
-        c.submit_batch(b)
-        s = c.finalize()
-        assert_same(c.export(1, True), oracle)
-        assert s["n_windows"] == oracle[2] and s["n_records"] == len(recs)
+    for k, flags, pl in ((17, _lib.KMG_FLAG_FORCE_HASH, 0), (21, PART, 5), (12, 0, 0), (31, 0, 0)):
+        oracle = orc.count_records(k, recs, mode="rolling")
+        with kb.GpuKmerCounter(k, batch_bases=32768, flags=flags, parts_log2=pl) as c:
+            per = len(recs) // 10
+            for bi in range(10):
+                b = c.acquire_batch()
+                words = (b.capacity_bases + 31) // 32
+                bases = np.ctypeslib.as_array(b.bases2bit, shape=(words,))
+                valid = np.ctypeslib.as_array(b.valid_bits, shape=(words,))
+                start = np.ctypeslib.as_array(b.start_bits, shape=(words,))
+                assert not bases.any() and not valid.any() and not start.any()     # handed out zeroed
+                pos = 0
+                chunk = recs[bi * per:(bi + 1) * per] if bi < 9 else recs[9 * per:]
+                for r in chunk:
+                    start[pos // 32] |= np.uint32(1 << (31 - pos % 32))
+                    for ch in r:
+                        cd = code[ch]
+                        if cd != 255:
+                            bases[pos // 32] |= np.uint64(int(cd) << (62 - 2 * (pos % 32)))
+                            valid[pos // 32] |= np.uint32(1 << (31 - pos % 32))
+                        pos += 1
+                assert pos <= b.capacity_bases
+                b.n_bases = pos
+                b.n_records = len(chunk)
+                c.submit_batch(b)
+            s = c.finalize()
+            assert_same(c.export(1, True), oracle)
+            assert s["n_windows"] == oracle[2] and s["n_records"] == len(recs)
 
 
 def test_device_resident_path_and_synthetic_generator():
