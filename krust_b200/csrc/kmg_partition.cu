@@ -836,6 +836,21 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
             got[j] = cur[j].x;
             if (cur[j].x == EMPTY_MIX) got[j] = atomicCAS(&skeys[sl[j]], EMPTY_MIX, k);
           }
+          if (round == 0) {
+            // second chance inside the home bucket: the whole partition is inserted concurrently, so most conflicts are lost RACES for
+            // the first slot -- the loser takes the second slot right away instead of waiting for round 1, which then already looks
+            // at the next bucket; only keys that lose three slots reach the divergent loop below
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+              const int q = h0 + j;
+              const unsigned long long k = key[q];
+              if ((act >> q & 1u) && !(sl[j] & 1u) && got[j] != EMPTY_MIX && got[j] != k) {
+                sl[j] |= 1u;
+                got[j] = cur[j].y;  // as loaded with the bucket; re-checked by the CAS when it looked empty
+                if (cur[j].y == EMPTY_MIX) got[j] = atomicCAS(&skeys[sl[j]], EMPTY_MIX, k);
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < H; ++j) {
             const int q = h0 + j;
