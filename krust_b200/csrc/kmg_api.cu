@@ -139,6 +139,7 @@ struct kmg_ctx {
   unsigned long long *d_part = nullptr;  // 3 * MAX_PARTS scratch: coarse counts, starts, cursors
   unsigned long long *d_fine_cursor = nullptr;  // n_parts
   uint32_t n_consolidations = 0;
+  uint64_t sieve_redo = 0;  // partitions the sieve variant of phase B handed to the compacting variant (diagnostic)
 
   // device-memory pool for the partitioned pipeline's large, short-lived buffers: cudaMalloc/cudaFree of tens
   // of GB cost ~10 ms each and a counting job needs a dozen of them, so freed blocks are kept for reuse
@@ -741,9 +742,16 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
   static const bool no_direct = getenv("KMG_NO_DIRECT") != nullptr;  // ablation
   bool direct = !no_direct && !recompact && raw_entries == total && c->dedup_ratio >= 0.5 && max_total <= 0xffffu &&
                 total / std::max<uint32_t>(P, 1) <= SMEM_TABLE_SLOTS / 2 && !(c->cfg.flags & KMG_FLAG_NO_PREAGG);
+  // Sieve variant (count_partitions_sieve_kernel): same precondition; it leaves the partitions it cannot take (too many repeated keys,
+  // more than one batch of entries) to the compacting variant, so no bound on the largest partition is needed.
+  static const bool no_sieve = getenv("KMG_NO_SIEVE") != nullptr;  // ablation
+  bool sieve = !no_sieve && !recompact && raw_entries == total && c->dedup_ratio >= 0.5 &&
+               total / std::max<uint32_t>(P, 1) <= SIEVE_MAX_ENTRIES * 15 / 16 && !(c->cfg.flags & KMG_FLAG_NO_PREAGG);
+  uint32_t *d_redo = nullptr;
+  if (sieve && pool_alloc(c, &d_redo, (size_t)P * 4) != cudaSuccess) { cudaGetLastError(); sieve = false; }
   uint64_t out_cap = std::max<uint64_t>(total, 1);
   if (recompact) out_cap = std::min<uint64_t>(out_cap, c->result.n_valid + (1ull << 20));
-  else if (total > (1ull << 28) && !direct) {
+  else if (total > (1ull << 28) && !direct && !sieve) {
     const uint64_t est = (total - raw_entries) + (uint64_t)((double)raw_entries * std::min(1.0, c->dedup_ratio * 1.25 + 0.02)) + (1ull << 24);
     out_cap = std::min(out_cap, est);
   }
@@ -765,7 +773,7 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
   }
   if (e == cudaSuccess) e = pool_alloc(c, &out.d_seg_start, (size_t)P * 8);
   if (e == cudaSuccess) e = pool_alloc(c, &out.d_seg_len, (size_t)P * 8);
-  if (e != cudaSuccess) { pool_free(c, d_order); free_run(c, out); return cuda_fail(c, e, "cudaMalloc(consolidated run)"); }
+  if (e != cudaSuccess) { pool_free(c, d_order); pool_free(c, d_redo); free_run(c, out); return cuda_fail(c, e, "cudaMalloc(consolidated run)"); }
   prm.out_keys = out.d_keys; prm.out_counts = out.d_counts;
   prm.out_seg_start = out.d_seg_start; prm.out_seg_len = out.d_seg_len;
   prm.out_cap = out_cap;
@@ -773,7 +781,7 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
   if (!c->d_hist) {
     e = cudaMalloc(&c->d_hist, (HIST_DENSE_BINS + 1) * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_hist_ov, HIST_OVERFLOW_CAP * 8);
-    if (e != cudaSuccess) { pool_free(c, d_order); free_run(c, out); return cuda_fail(c, e, "cudaMalloc(histogram)"); }
+    if (e != cudaSuccess) { pool_free(c, d_order); pool_free(c, d_redo); free_run(c, out); return cuda_fail(c, e, "cudaMalloc(histogram)"); }
   }
   prm.hist = c->d_hist; prm.hist_overflow = c->d_hist_ov; prm.hist_overflow_cap = HIST_OVERFLOW_CAP;
   c->fused_valid = c->fused_cached = false;
@@ -811,12 +819,35 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
     const size_t tmr = timer_begin(c, 1);
     bool weighted = max_total > ((2ull * SMEM_COUNT_THREADS * 8) << split_log2);  // partitions oversized beyond the split want the pre-aggregating variant
     for (uint32_t r = 0; r < R; ++r) weighted |= in[r]->d_counts != nullptr;
-    if (weighted || split_log2 || !use_smem) direct = false;
-    if (e == cudaSuccess) e = use_smem ? launch_count_partitions_smem(prm, weighted, direct, c->stream) : launch_count_partitions(prm, grid, c->stream);
-    timer_end(c, tmr);
+    if (weighted || split_log2 || !use_smem) direct = sieve = false;
     unsigned long long h_sync[4] = {0, 0, 0, 0};
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 32, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (sieve) {
+      prm.redo_list = d_redo; prm.redo_count = reinterpret_cast<uint32_t *>(d_sync + 3) + 1;
+      if (e == cudaSuccess) e = launch_count_partitions_sieve(prm, c->stream);
+      timer_end(c, tmr);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 32, cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      const uint32_t n_redo = (uint32_t)(h_sync[3] >> 32);
+      if (e == cudaSuccess && n_redo && !(uint32_t)h_sync[3]) {
+        // the partitions the sieve left alone: compacting variant, continuing the same output cursor, distinct count and histogram
+        CountParams redo = prm;
+        redo.order = d_redo; redo.n_parts = n_redo; redo.redo_list = nullptr; redo.redo_count = nullptr;
+        e = cudaMemsetAsync(prm.next, 0, 4, c->stream);
+        const size_t tmr2 = timer_begin(c, 1);
+        if (e == cudaSuccess) e = launch_count_partitions_smem(redo, false, false, c->stream);
+        timer_end(c, tmr2);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 32, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        c->sieve_redo += n_redo;
+      }
+      static const bool dbg_sieve = getenv("KMG_DEBUG_SIEVE") != nullptr;
+      if (dbg_sieve) fprintf(stderr, "[kmg] sieve: %u partitions, %u left to the compacting variant, %llu entries, %llu distinct\n", P, n_redo, (unsigned long long)h_sync[0], (unsigned long long)h_sync[2]);
+    } else {
+      if (e == cudaSuccess) e = use_smem ? launch_count_partitions_smem(prm, weighted, direct, c->stream) : launch_count_partitions(prm, grid, c->stream);
+      timer_end(c, tmr);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 32, cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    }
     pool_free(c, d_scratch); pool_free(c, d_sync);
     if (e != cudaSuccess) { st = cuda_fail(c, e, "count_partitions"); break; }
     if ((uint32_t)h_sync[3] && !(h_sync[1] >> 32)) {  // the run was too small for the distinct keys: enlarge it and repeat
@@ -834,6 +865,7 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
     }
     n_out = h_sync[0]; n_valid = h_sync[2];
     if (!(h_sync[1] >> 32)) break;  // no overflow
+    if (sieve) { sieve = false; continue; }    // a left-over partition was beyond the compacting variant too: the whole launch is repeated without the sieve
     if (direct) { direct = false; continue; }  // a partition beyond the direct variant's limits: the compacting variant takes the launch
     if (attempt >= 16 || c->scratch_log2 >= 30) { st = fail(c, KMG_ERR_TABLE_FULL, "partition table overflow could not be resolved"); break; }
     if (use_smem) {  // finer split first (weights beyond 32 bits are not cured by it: the L2 variant follows after three tries)
@@ -842,7 +874,7 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
       c->scratch_log2 = std::max<uint32_t>(c->scratch_log2, 14);
     } else ++c->scratch_log2;  // retry with larger tables
   }
-  pool_free(c, d_order);
+  pool_free(c, d_order); pool_free(c, d_redo);
   if (st != KMG_OK) { free_run(c, out); return st; }
   out.n = n_out; out.n_valid = n_valid;
   if (raw_entries > (1ull << 24)) {  // distinct keys the raw runs added per raw entry (an upper estimate: keys already in the result count as new)
@@ -868,7 +900,7 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
   c->has_result = true;
   c->fused_valid = true;
   c->n_consolidations++;
-  if (direct && c->result.n > (1ull << 20) && c->result.n_valid < c->result.n / 2) {
+  if ((direct || sieve) && c->result.n > (1ull << 20) && c->result.n_valid < c->result.n / 2) {
     // duplicate-rich input went through the direct variant (nothing was known about it yet): most entries are fillers.
     // Rewrite the run compactly once; dedup_ratio now steers later consolidations to the compacting variant.
     kmg_status rs = consolidate(c, /*recompact=*/true);

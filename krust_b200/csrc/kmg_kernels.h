@@ -108,6 +108,9 @@ struct CountParams {
   unsigned long long *hist;
   uint64_t *hist_overflow;
   uint64_t hist_overflow_cap;
+  // sieve variant only: partitions it hands to the compacting variant (more repeated keys than its side table holds, or more
+  // entries than one batch), appended as partition numbers
+  uint32_t *redo_list, *redo_count;  // redo_count zeroed
 };
 
 enum { CTR_WINDOWS = 0, CTR_DISTINCT = 1, CTR_FULL = 2, CTR_SCRATCH = 3, CTR_N = 8 };
@@ -152,6 +155,10 @@ cudaError_t launch_count_partitions(const CountParams &P, unsigned grid, cudaStr
 // direct: unweighted, mostly distinct keys -- new keys go straight to the output, no compaction pass (the output then holds one
 // entry per INPUT entry, the duplicates' as skipped fillers)
 cudaError_t launch_count_partitions_smem(const CountParams &P, bool weighted, bool direct, cudaStream_t s);
+// sieve: unweighted, mostly distinct keys -- a bitmap finds the few keys that MAY repeat, only those enter a (small) table; every
+// other key is copied to the output in place.  Partitions it cannot take are listed in P.redo_list for the variants above.
+constexpr uint32_t SIEVE_MAX_ENTRIES = 4096;  // entries of one partition the sieve variant takes (one batch)
+cudaError_t launch_count_partitions_sieve(const CountParams &P, cudaStream_t s);
 // tmp == nullptr: returns the scratch size needed for n items in *tmp_bytes.  Asynchronous on s.
 cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, void *tmp, size_t *tmp_bytes, cudaStream_t s);
 int num_sms();
