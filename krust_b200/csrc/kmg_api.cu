@@ -65,6 +65,7 @@ struct Run {
   uint64_t *d_keys = nullptr, *d_counts = nullptr, *d_seg_start = nullptr, *d_seg_len = nullptr;
   uint64_t n = 0;        // entries (a consolidated run may hold skipped filler entries, see count_partitions_smem_kernel)
   uint64_t n_valid = 0;  // consolidated runs: distinct keys
+  bool padded = false;   // speculative layout: segments start on 16-byte boundaries and an EMPTY_MIX entry follows every segment of odd length
 };
 
 struct kmg_ctx {
@@ -487,6 +488,7 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
     if (!h_flag) {
       cleanup();
       r.n = n;
+      if (!(cap_f & 1ull) && launch_pad_segments(r.d_keys, r.d_seg_start, r.d_seg_len, P, c->stream) == cudaSuccess) r.padded = true;
       if (split) { *split->out = std::move(r); return KMG_OK; }
       guard.release();  // the run is complete: a consolidation triggered by add_run may re-split it with the others
       return add_run(c, std::move(r));
@@ -748,8 +750,13 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
   bool sieve = !no_sieve && !recompact && raw_entries == total && c->dedup_ratio >= 0.5 &&
                total / std::max<uint32_t>(P, 1) <= SIEVE_MAX_ENTRIES * 15 / 16 && !(c->cfg.flags & KMG_FLAG_NO_PREAGG);
   uint32_t *d_redo = nullptr;
-  if (sieve && pool_alloc(c, &d_redo, (size_t)P * 4) != cudaSuccess) { cudaGetLastError(); sieve = false; }
-  uint64_t out_cap = std::max<uint64_t>(total, 1);
+  unsigned long long *d_redo_base = nullptr;
+  if (sieve && (pool_alloc(c, &d_redo, (size_t)P * 8) != cudaSuccess || pool_alloc(c, &d_redo_base, (size_t)P * 8) != cudaSuccess)) {  // d_redo: partition numbers, then range lengths
+    cudaGetLastError(); pool_free(c, d_redo); pool_free(c, d_redo_base); d_redo = nullptr; d_redo_base = nullptr; sieve = false;
+  }
+  bool sieve_padded = sieve && getenv("KMG_NO_SIEVE_TMA") == nullptr;
+  for (auto *r : in) sieve_padded = sieve_padded && r->padded;
+  uint64_t out_cap = std::max<uint64_t>(total, 1) + (sieve_padded ? (uint64_t)P * R : 0);  // padded segments: up to one filler entry per partition and run
   if (recompact) out_cap = std::min<uint64_t>(out_cap, c->result.n_valid + (1ull << 20));
   else if (total > (1ull << 28) && !direct && !sieve) {
     const uint64_t est = (total - raw_entries) + (uint64_t)((double)raw_entries * std::min(1.0, c->dedup_ratio * 1.25 + 0.02)) + (1ull << 24);
@@ -773,7 +780,7 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
   }
   if (e == cudaSuccess) e = pool_alloc(c, &out.d_seg_start, (size_t)P * 8);
   if (e == cudaSuccess) e = pool_alloc(c, &out.d_seg_len, (size_t)P * 8);
-  if (e != cudaSuccess) { pool_free(c, d_order); pool_free(c, d_redo); free_run(c, out); return cuda_fail(c, e, "cudaMalloc(consolidated run)"); }
+  if (e != cudaSuccess) { pool_free(c, d_order); pool_free(c, d_redo); pool_free(c, d_redo_base); free_run(c, out); return cuda_fail(c, e, "cudaMalloc(consolidated run)"); }
   prm.out_keys = out.d_keys; prm.out_counts = out.d_counts;
   prm.out_seg_start = out.d_seg_start; prm.out_seg_len = out.d_seg_len;
   prm.out_cap = out_cap;
@@ -781,7 +788,7 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
   if (!c->d_hist) {
     e = cudaMalloc(&c->d_hist, (HIST_DENSE_BINS + 1) * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_hist_ov, HIST_OVERFLOW_CAP * 8);
-    if (e != cudaSuccess) { pool_free(c, d_order); pool_free(c, d_redo); free_run(c, out); return cuda_fail(c, e, "cudaMalloc(histogram)"); }
+    if (e != cudaSuccess) { pool_free(c, d_order); pool_free(c, d_redo); pool_free(c, d_redo_base); free_run(c, out); return cuda_fail(c, e, "cudaMalloc(histogram)"); }
   }
   prm.hist = c->d_hist; prm.hist_overflow = c->d_hist_ov; prm.hist_overflow_cap = HIST_OVERFLOW_CAP;
   c->fused_valid = c->fused_cached = false;
@@ -823,15 +830,25 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
     unsigned long long h_sync[4] = {0, 0, 0, 0};
     if (sieve) {
       prm.redo_list = d_redo; prm.redo_count = reinterpret_cast<uint32_t *>(d_sync + 3) + 1;
-      if (e == cudaSuccess) e = launch_count_partitions_sieve(prm, c->stream);
+      prm.redo_len = d_redo + P; prm.redo_base = d_redo_base;
+      if (e == cudaSuccess) e = launch_count_partitions_sieve(prm, sieve_padded, c->stream);
       timer_end(c, tmr);
       if (e == cudaSuccess) e = cudaMemcpyAsync(h_sync, d_sync, 32, cudaMemcpyDeviceToHost, c->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
       const uint32_t n_redo = (uint32_t)(h_sync[3] >> 32);
-      if (e == cudaSuccess && n_redo && !(uint32_t)h_sync[3]) {
+      if (e == cudaSuccess && (n_redo > sieve_redo_limit_host(P) || (uint32_t)h_sync[3])) {
+        // duplicate-rich input (the reserved ranges of the partitions handed back are lost as fillers, the padded variant stops early):
+        // the launch is repeated without the sieve
+        pool_free(c, d_scratch); pool_free(c, d_sync);
+        sieve = sieve_padded = direct = false;
+        c->dedup_ratio = std::min(c->dedup_ratio, 0.49);
+        continue;
+      }
+      if (e == cudaSuccess && n_redo) {
         // the partitions the sieve left alone: compacting variant, continuing the same output cursor, distinct count and histogram
         CountParams redo = prm;
         redo.order = d_redo; redo.n_parts = n_redo; redo.redo_list = nullptr; redo.redo_count = nullptr;
+        redo.pre_base = d_redo_base; redo.pre_len = d_redo + P; redo.redo_base = nullptr; redo.redo_len = nullptr;
         e = cudaMemsetAsync(prm.next, 0, 4, c->stream);
         const size_t tmr2 = timer_begin(c, 1);
         if (e == cudaSuccess) e = launch_count_partitions_smem(redo, false, false, c->stream);
@@ -874,7 +891,7 @@ kmg_status consolidate(kmg_ctx *c, bool recompact) {
       c->scratch_log2 = std::max<uint32_t>(c->scratch_log2, 14);
     } else ++c->scratch_log2;  // retry with larger tables
   }
-  pool_free(c, d_order); pool_free(c, d_redo);
+  pool_free(c, d_order); pool_free(c, d_redo); pool_free(c, d_redo_base);
   if (st != KMG_OK) { free_run(c, out); return st; }
   out.n = n_out; out.n_valid = n_valid;
   if (raw_entries > (1ull << 24)) {  // distinct keys the raw runs added per raw entry (an upper estimate: keys already in the result count as new)

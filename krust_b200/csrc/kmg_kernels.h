@@ -111,6 +111,13 @@ struct CountParams {
   // sieve variant only: partitions it hands to the compacting variant (more repeated keys than its side table holds, or more
   // entries than one batch), appended as partition numbers
   uint32_t *redo_list, *redo_count;  // redo_count zeroed
+  // ... together with the output range a partition had already reserved (redo_base[i] = ~0: none).  The launch that takes the list
+  // over passes them back as pre_base / pre_len (indexed like `order`): such a partition is written into its range, the unused
+  // tail filled with skipped entries.
+  unsigned long long *redo_base;
+  uint32_t *redo_len;
+  const unsigned long long *pre_base;
+  const uint32_t *pre_len;
 };
 
 enum { CTR_WINDOWS = 0, CTR_DISTINCT = 1, CTR_FULL = 2, CTR_SCRATCH = 3, CTR_N = 8 };
@@ -158,7 +165,11 @@ cudaError_t launch_count_partitions_smem(const CountParams &P, bool weighted, bo
 // sieve: unweighted, mostly distinct keys -- a bitmap finds the few keys that MAY repeat, only those enter a (small) table; every
 // other key is copied to the output in place.  Partitions it cannot take are listed in P.redo_list for the variants above.
 constexpr uint32_t SIEVE_MAX_ENTRIES = 4096;  // entries of one partition the sieve variant takes (one batch)
-cudaError_t launch_count_partitions_sieve(const CountParams &P, cudaStream_t s);
+// padded: every input run has 16-byte aligned segments padded to an even length (launch_pad_segments) -- the copies then go
+// through the TMA unit and the output segments are the padded inputs
+cudaError_t launch_count_partitions_sieve(const CountParams &P, bool padded, cudaStream_t s);
+uint32_t sieve_redo_limit_host(uint32_t n_parts);  // more partitions handed back than this: the padded variant stopped early, repeat the launch without the sieve
+cudaError_t launch_pad_segments(uint64_t *keys, const uint64_t *seg_start, const uint64_t *seg_len, uint32_t n_parts, cudaStream_t s);
 // tmp == nullptr: returns the scratch size needed for n items in *tmp_bytes.  Asynchronous on s.
 cudaError_t exclusive_sum_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t n, void *tmp, size_t *tmp_bytes, cudaStream_t s);
 int num_sms();

@@ -985,8 +985,11 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
       const uint32_t d = __shfl_sync(0xffffffffu, incl, NW - 1);
       pre = __shfl_sync(0xffffffffu, incl - v, warp);
       if (n_pass == 1 && tid == 0) {
-        unsigned long long b = atomicAdd(P.out_cursor, (unsigned long long)d);
-        if (b + d > P.out_cap) { atomicExch(P.nospace_flag, 1u); b = NO_SPACE; }
+        unsigned long long b = P.pre_base ? P.pre_base[work] : NO_SPACE;  // a range the sieve variant had reserved (it holds >= n_p >= d entries)
+        if (b == NO_SPACE) {
+          b = atomicAdd(P.out_cursor, (unsigned long long)d);
+          if (b + d > P.out_cap) { atomicExch(P.nospace_flag, 1u); b = NO_SPACE; }
+        }
         P.out_seg_start[p] = b; P.out_seg_len[p] = d;
         s_base = b; s_run = 0;
         if (d) atomicAdd(P.out_distinct, (unsigned long long)d);
@@ -1012,6 +1015,10 @@ __global__ void __launch_bounds__(SMEM_COUNT_THREADS, 2) count_partitions_smem_k
         }
         if (P.hist) hist_note(ok, cnt, s_hist, P, lane);
       }
+    }
+    if (n_pass == 1 && P.pre_base && P.pre_base[work] != NO_SPACE) {  // the rest of the pre-reserved range: entries every reader skips
+      const unsigned long long b = P.pre_base[work];
+      for (uint32_t i = pass_d + tid; i < P.pre_len[work]; i += SMEM_COUNT_THREADS) { __stcs(P.out_keys + b + i, (uint64_t)EMPTY_MIX); __stcs(P.out_counts + b + i, (uint64_t)0); }
     }
     __syncthreads();  // table clean before the next pass / partition (and every warp has read the list counters)
     if (tid < NW) s_wn[tid] = 0;  // ordered before the next appends by the barrier that opens the next pass / follows the metadata fetch
@@ -1054,30 +1061,31 @@ constexpr uint32_t SV_L_MAX = 2048;                       // entries L may hold 
 constexpr int SV_THREADS = 512, SV_G = 8;
 static_assert(SV_THREADS * SV_G == (int)SIEVE_MAX_ENTRIES, "one batch per partition");
 
-__device__ __noinline__ void sieve_insert(unsigned long long *Lkey, uint16_t *Lused, uint32_t *n_used, uint32_t *fail, unsigned long long k) {
+__device__ __noinline__ void sieve_insert(unsigned long long *Lkey, uint16_t *Lused, uint32_t *n_used, uint32_t *fail, unsigned long long k,
+                                          uint32_t slot_mask = SV_L_SLOTS - 1, uint32_t max_used = SV_L_MAX) {
   if (*reinterpret_cast<volatile uint32_t *>(fail)) return;  // bounds the entries: every thread has at most one insertion past this test
-  uint32_t s = (uint32_t)(k >> 32) & (SV_L_SLOTS - 1);
-  for (uint32_t t = 0; t < SV_L_SLOTS; ++t) {
+  uint32_t s = (uint32_t)(k >> 32) & slot_mask;
+  for (uint32_t t = 0; t <= slot_mask; ++t) {
     unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&Lkey[s]);
     if (cur == EMPTY_MIX) cur = atomicCAS(&Lkey[s], EMPTY_MIX, k);
     if (cur == k) return;
     if (cur == EMPTY_MIX) {
       const uint32_t i = atomicAdd(n_used, 1u);
-      if (i < SV_L_MAX) Lused[i] = (uint16_t)s; else atomicExch(fail, 1u);
+      if (i < max_used) Lused[i] = (uint16_t)s; else atomicExch(fail, 1u);
       return;
     }
-    s = (s + 1) & (SV_L_SLOTS - 1);
+    s = (s + 1) & slot_mask;
   }
   atomicExch(fail, 1u);
 }
 // slot of k in L, or SV_L_SLOTS when it is not there (L is read-only by now)
-__device__ __noinline__ uint32_t sieve_find(const unsigned long long *Lkey, unsigned long long k) {
-  uint32_t s = (uint32_t)(k >> 32) & (SV_L_SLOTS - 1);
-  for (uint32_t t = 0; t < SV_L_SLOTS; ++t) {
+__device__ __noinline__ uint32_t sieve_find(const unsigned long long *Lkey, unsigned long long k, uint32_t slot_mask = SV_L_SLOTS - 1) {
+  uint32_t s = (uint32_t)(k >> 32) & slot_mask;
+  for (uint32_t t = 0; t <= slot_mask; ++t) {
     const unsigned long long cur = Lkey[s];
     if (cur == k) return s;
     if (cur == EMPTY_MIX) break;
-    s = (s + 1) & (SV_L_SLOTS - 1);
+    s = (s + 1) & slot_mask;
   }
   return SV_L_SLOTS;
 }
@@ -1150,7 +1158,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2) count_partitions_sieve_kernel(C
     if (n_p == 0) {
       if (tid == 0) { P.out_seg_start[p] = 0; P.out_seg_len[p] = 0; }
     } else if (n_p > (uint64_t)SIEVE_MAX_ENTRIES) {  // block-uniform
-      if (tid == 0) P.redo_list[atomicAdd(P.redo_count, 1u)] = p;
+      if (tid == 0) { const uint32_t ri = atomicAdd(P.redo_count, 1u); P.redo_list[ri] = p; P.redo_base[ri] = NO_SPACE; P.redo_len[ri] = 0; }
     } else {
       // ---- load the partition (one batch: G keys per thread, entry idx = j * SV_THREADS + tid)
       unsigned long long key[G];
@@ -1198,7 +1206,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2) count_partitions_sieve_kernel(C
       if (fail) {
         for (uint32_t i = tid; i < SV_L_SLOTS; i += SV_THREADS) { Lkey[i] = EMPTY_MIX; Lcnt[i] = 0; }
         __syncthreads();  // every thread has read s_fail / s_nL
-        if (tid == 0) { P.redo_list[atomicAdd(P.redo_count, 1u)] = p; s_nL = 0; s_fail = 0; }
+        if (tid == 0) { const uint32_t ri = atomicAdd(P.redo_count, 1u); P.redo_list[ri] = p; P.redo_base[ri] = NO_SPACE; P.redo_len[ri] = 0; s_nL = 0; s_fail = 0; }
       } else {
         counted = true;
         if (tid == 0) {
@@ -1271,9 +1279,319 @@ __global__ void __launch_bounds__(SV_THREADS, 2) count_partitions_sieve_kernel(C
   if (P.hist) hist_flush(s_hist, P, tid);
 }
 
-cudaError_t launch_count_partitions_sieve(const CountParams &P, cudaStream_t s) {
+// ---------------------------------------------------------------------------------------------------
+// The sieve with the key copies handed to the TMA unit (runs whose segments start on 16-byte boundaries and are padded to an even
+// number of entries with EMPTY_MIX: the speculative layouts, see launch_pad_segments).  ncu on the plain sieve: 3.9 warp-instr per key,
+// a third of them in the one-lane-active detours of the suspects, and half of all warp time at block barriers.  So here
+//   * the partition's keys arrive by 1-D bulk loads (one per input run) in one of two key stages, requested half a partition ahead,
+//     and leave by ONE bulk store of the stage (fillers and repeats are patched in the stage); counts go out as plain coalesced
+//     8-byte stores of 1 / 0 while the keys are read, and are patched afterwards where a key repeats;
+//   * nothing divergent happens in the two passes over the keys: pass 1 is the bit-map test-and-set (a suspect only sets a bit in a
+//     4096-bit filter indexed like the map), pass 2 tests that filter and queues the indices of the keys it flags -- the suspects,
+//     the earlier keys they met in the bit map, a few chance hits;
+//   * the queue (~100 of ~3600 entries) is then resolved by as many threads in parallel in a small table of stage indices
+//     (32-bit CAS; the key of a slot is read from the stage): first claimant = the entry that stays, the others become fillers;
+//   * two 512-thread CTAs per SM, so one CTA's barriers overlap the other's work; output ranges are reserved when the segment
+//     table is fetched (two partitions ahead), so no global atomic sits on the critical path.
+// The output segment is the padded input: entries (EMPTY, 0) are fillers every reader skips.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SVT_THREADS = 512, SVT_G = 8, SVT_NS = 2, SVT_META = 3;
+__host__ __device__ __forceinline__ uint32_t sieve_redo_limit_impl(uint32_t n_parts) { return n_parts / 8 + 64; }
+__device__ __forceinline__ uint32_t sieve_redo_limit(uint32_t n_parts) { return sieve_redo_limit_impl(n_parts); }
+constexpr uint32_t SVT_CAP = SIEVE_MAX_ENTRIES;  // entries per key stage
+constexpr uint32_t SVT_L_SLOTS = 1024, SVT_L_MAX = 704, SVT_Q = 2048, SVT_BLOOM_WORDS = 128;
+static_assert(SVT_THREADS * SVT_G == (int)SVT_CAP, "one batch per partition");
+constexpr size_t SVT_SMEM = (size_t)SVT_CAP * 8 * SVT_NS + (size_t)SV_BM_WORDS * 4 + (size_t)SVT_L_SLOTS * 8 + (size_t)SVT_Q * 2;
+
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <bool ONE_RUN>
+__global__ void __launch_bounds__(SVT_THREADS, 2) count_partitions_sieve_tma_kernel(CountParams P) {
+  extern __shared__ __align__(128) unsigned char svt_raw[];
+  constexpr int G = SVT_G, T = SVT_THREADS, NS = SVT_NS, NM = SVT_META;
+  unsigned long long *stage = reinterpret_cast<unsigned long long *>(svt_raw);  // [NS][SVT_CAP] keys
+  uint32_t *bm = reinterpret_cast<uint32_t *>(stage + (size_t)NS * SVT_CAP);    // bit map
+  uint32_t *Lslot = bm + SV_BM_WORDS;                                           // stage index + 1 of the entry that owns the slot, 0 = free
+  uint32_t *Lcnt = Lslot + SVT_L_SLOTS;                                         // further occurrences of that entry's key
+  uint16_t *Q = reinterpret_cast<uint16_t *>(Lcnt + SVT_L_SLOTS);               // stage indices of the flagged entries
+  __shared__ __align__(8) uint64_t bar[NS];
+  __shared__ uint64_t m_src[NM][CONS_MAX_RUNS];  // run r's segment of the partition (global address)
+  __shared__ uint32_t m_len[NM][CONS_MAX_RUNS];  // its padded length in entries
+  __shared__ uint32_t m_npad[NM], m_np[NM], m_work[NM], m_state[NM];  // state: 0 empty, 1 staged, 2 left to the compacting variant
+  __shared__ unsigned long long m_base[NM];
+  __shared__ uint32_t s_hist[HIST_CTA_BINS], s_bloom[SVT_BLOOM_WORDS];
+  __shared__ uint32_t s_nq, s_nL, s_fail, s_holes;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t R = P.R;
+
+  auto fetch = [&](uint32_t w, uint64_t &b, uint64_t &len) {
+    b = 0; len = 0;
+    if (w < P.n_parts && lane < (int)R) {
+      const uint32_t p = P.order ? P.order[w] : w;
+      b = P.runs[lane].seg_start[p]; len = P.runs[lane].seg_len[p];
+    }
+  };
+  // warp 0: work item w (lane r holds run r's segment) -> metadata slot sl.  The output range is reserved here, but the atomic's
+  // result is only looked at one iteration later (settle): its latency must not sit in this single-warp section.
+  unsigned long long pend_ob = 0;  // lane 0
+  uint32_t pend_npad = 0;
+  int pend_slot = -1;
+  auto settle = [&]() {  // lane 0
+    if (pend_slot < 0) return;
+    unsigned long long ob = pend_ob;
+    if (ob + pend_npad > P.out_cap) { atomicExch(P.nospace_flag, 1u); ob = NO_SPACE; }
+    m_base[pend_slot] = ob;
+    pend_slot = -1;
+  };
+  auto publish = [&](int sl, uint32_t w, uint64_t b, uint64_t len) {
+    const bool big = __any_sync(0xffffffffu, len > (uint64_t)SVT_CAP);
+    const uint32_t l32 = big ? 0u : (uint32_t)len, pl = (l32 + 1u) & ~1u;
+    uint32_t incl = pl, np = l32;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
+    const uint32_t npad = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t state = w >= P.n_parts ? 0u : (big || npad > SVT_CAP) ? 2u : npad ? 1u : 0u;
+    if (lane < (int)R) { m_src[sl][lane] = reinterpret_cast<uint64_t>(P.runs[lane].keys + b); m_len[sl][lane] = pl; }
+    if (lane == 0) {
+      if (state == 1u) { pend_ob = atomicAdd(P.out_cursor, (unsigned long long)npad); pend_npad = npad; pend_slot = sl; }
+      m_npad[sl] = npad; m_np[sl] = np; m_work[sl] = w; m_state[sl] = state;
+    }
+    __syncwarp();
+  };
+  // thread 0: bulk loads of the partition in metadata slot sl into key stage ks
+  auto issue = [&](int sl, int ks) {
+    if (m_state[sl] != 1u) return;
+    mbar_expect_tx(&bar[ks], m_npad[sl] * 8u);
+    uint32_t off = 0;
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint32_t pl = m_len[sl][r];
+      if (pl) tma_load_1d(stage + (size_t)ks * SVT_CAP + off, reinterpret_cast<const void *>(m_src[sl][r]), pl * 8u, &bar[ks]);
+      off += pl;
+    }
+  };
+
+  if (tid < HIST_CTA_BINS) s_hist[tid] = 0;
+  if (tid < (int)SVT_BLOOM_WORDS) s_bloom[tid] = 0;
+  for (uint32_t i = tid; i < SVT_L_SLOTS; i += T) { Lslot[i] = 0; Lcnt[i] = 0; }
+  for (uint32_t i = tid; i < SV_BM_WORDS; i += T) bm[i] = 0;
+  if (tid == 0) {
+    s_nq = 0; s_nL = 0; s_fail = 0; s_holes = 0;
+    for (int i = 0; i < NS; ++i) mbar_init(&bar[i], 1);
+    mbar_fence_init();
+  }
+  uint32_t w_ahead = 0;  // lane 0 of warp 0: the work item two after the current one
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w0 = 0, w1 = 0;
+    if (lane == 0) { w0 = atomicAdd(P.next, 1u); w1 = atomicAdd(P.next, 1u); w_ahead = atomicAdd(P.next, 1u); }
+    w0 = __shfl_sync(0xffffffffu, w0, 0); w1 = __shfl_sync(0xffffffffu, w1, 0);
+    uint64_t b, len;
+    fetch(w0, b, len); publish(0, w0, b, len);
+    if (lane == 0) settle();
+    fetch(w1, b, len); publish(1, w1, b, len);
+    if (lane == 0) { issue(0, 0); settle(); }
+  }
+  __syncthreads();
+
+  unsigned long long my_entries = 0;  // tid 0: distinct keys of the partitions this CTA counted
+  uint32_t ph = 0;                    // bit s: parity of key stage s's next completion
+  for (uint32_t it = 0;; ++it) {
+    const int sl = (int)(it % NM), ks = (int)(it & 1u);
+    const uint32_t work = m_work[sl];
+    if (work >= P.n_parts) break;
+    const uint32_t state = m_state[sl], npad = m_npad[sl], np = m_np[sl];
+    const unsigned long long base = m_base[sl];
+    const bool fits = base != NO_SPACE;
+    const uint32_t p = P.order ? P.order[work] : work;
+    // segment table of the partition two ahead: loads issued now, published at the end of this iteration
+    uint32_t wn = 0, handed_back = 0;
+    uint64_t nb = 0, nlen = 0;
+    if (warp == 0) {
+      wn = __shfl_sync(0xffffffffu, w_ahead, 0);
+      fetch(wn, nb, nlen);
+      if (lane == 0 && wn < P.n_parts) w_ahead = atomicAdd(P.next, 1u);
+      if (lane == 0) handed_back = *reinterpret_cast<volatile uint32_t *>(P.redo_count);  // looked at when this iteration ends
+    }
+    if (state != 1u) {
+      if (tid == 0) {
+        if (state == 0u) { P.out_seg_start[p] = 0; P.out_seg_len[p] = 0; }
+        else { const uint32_t ri = atomicAdd(P.redo_count, 1u); P.redo_list[ri] = p; P.redo_base[ri] = NO_SPACE; P.redo_len[ri] = 0; }
+        tma_wait_group_read<0>();
+        issue((int)((it + 1) % NM), ks ^ 1);  // the next partition's keys
+      }
+    } else {
+      unsigned long long *st = stage + (size_t)ks * SVT_CAP;
+      mbar_wait(&bar[ks], (ph >> ks) & 1u);
+      ph ^= 1u << ks;
+      // ---- pass 1: read the staged keys, write the counts (1 per live entry), test-and-set in the bit map
+      unsigned long long key[G];
+      uint32_t live = 0;
+      {
+        uint32_t old[G];
+        const uint32_t last = npad - 1u;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const uint32_t idx = (uint32_t)j * T + tid;
+          key[j] = st[min(idx, last)];  // rows past the end re-read the last entry and stay dead
+          const bool lv = ONE_RUN ? idx < np : (idx < npad && key[j] != EMPTY_MIX);  // not the pad entry behind a segment of odd length
+          live |= (lv ? 1u : 0u) << j;
+          if (fits && idx < npad) __stcs(P.out_counts + base + idx, lv ? 1ull : 0ull);
+          const uint32_t lo = (uint32_t)key[j];
+          old[j] = lv ? atomicOr(&bm[(lo >> 5) & (SV_BM_WORDS - 1)], __funnelshift_l(0u, 1u, lo)) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {  // a suspect (its bit was already set) marks the filter; no detour, a predicated shared atomic
+          const uint32_t lo = (uint32_t)key[j];
+          if (__funnelshift_r(old[j], 0u, lo) & 1u) atomicOr(&s_bloom[(lo >> 5) & (SVT_BLOOM_WORDS - 1)], __funnelshift_l(0u, 1u, lo));
+        }
+      }
+      if (tid == 0) {  // the other key stage: its last store has had this pass to leave shared memory
+        tma_wait_group_read<0>();
+        issue((int)((it + 1) % NM), ks ^ 1);
+      }
+      __syncthreads();  // B: bit map and filter complete
+      {
+        uint4 *bm4 = reinterpret_cast<uint4 *>(bm);
+#pragma unroll
+        for (uint32_t i = 0; i < SV_BM_WORDS / 4 / T; ++i) bm4[i * T + tid] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      // ---- pass 2: the entries the filter flags are queued
+      {
+        uint32_t hit = 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const uint32_t lo = (uint32_t)key[j];
+          hit |= ((s_bloom[(lo >> 5) & (SVT_BLOOM_WORDS - 1)] & __funnelshift_l(0u, 1u, lo)) ? 1u : 0u) << j;
+        }
+        hit &= live;
+        if (hit) {
+          uint32_t q = atomicAdd(&s_nq, (uint32_t)__popc(hit));
+          while (hit) {
+            const uint32_t j = (uint32_t)__ffs((int)hit) - 1u;
+            if (q < SVT_Q) Q[q] = (uint16_t)(j * T + tid);
+            ++q;
+            hit &= hit - 1u;
+          }
+        }
+      }
+      __syncthreads();  // C: the queue is complete
+      const uint32_t nq = s_nq;
+      // ---- resolve the queue: entry e claims a slot of L for its key or meets the entry that did
+      constexpr int E = SVT_Q / T;
+      uint32_t my_slot[E], my_idx[E], reps = 0;
+      if (nq <= SVT_Q && (uint32_t)tid < nq) {
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+          const uint32_t e = (uint32_t)u * T + tid;
+          my_slot[u] = 0; my_idx[u] = 0;
+          if (e >= nq) continue;
+          const uint32_t idx = Q[e];
+          const unsigned long long k = st[idx];
+          uint32_t s = (uint32_t)(k >> 32) & (SVT_L_SLOTS - 1);
+          for (uint32_t t = 0;; ++t) {
+            if (t > SVT_L_SLOTS) { atomicExch(&s_fail, 1u); break; }
+            uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&Lslot[s]);
+            if (cur == 0u) {
+              if (*reinterpret_cast<volatile uint32_t *>(&s_fail)) break;  // bounds the entries: every thread has at most one claim past this test
+              cur = atomicCAS(&Lslot[s], 0u, idx + 1u);
+              if (cur == 0u) {
+                if (atomicAdd(&s_nL, 1u) >= SVT_L_MAX) atomicExch(&s_fail, 1u);
+                reps |= 1u << u; my_slot[u] = s; my_idx[u] = idx;
+                break;
+              }
+            }
+            if (st[cur - 1u] == k) {  // the owner of a slot is never patched: its key stays readable
+              atomicAdd(&Lcnt[s], 1u);
+              st[idx] = EMPTY_MIX;
+              if (fits) P.out_counts[base + idx] = 0ull;  // after this entry's own 1 (two barriers ago)
+              atomicAdd(&s_holes, 1u);  // of this partition
+              break;
+            }
+            s = (s + 1u) & (SVT_L_SLOTS - 1);
+          }
+        }
+      }
+      fence_proxy_async_smem();  // this thread's patches of the stage, ahead of the bulk store
+      __syncthreads();           // D: L's counters are final
+      const bool fail = nq > SVT_Q || s_fail != 0;
+      if (!fail) {
+        if (reps)
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+          if (!(reps >> u & 1u)) continue;
+          const unsigned long long cnt = 1ull + Lcnt[my_slot[u]];
+          if (cnt > 1) {
+            if (fits) P.out_counts[base + my_idx[u]] = cnt;
+            if (P.hist) {
+              if (cnt < (unsigned long long)HIST_CTA_BINS) atomicAdd(&s_hist[cnt], 1u);
+              else if (cnt < (unsigned long long)HIST_DENSE_BINS) atomicAdd(P.hist + cnt, 1ull);
+              else { const unsigned long long o = atomicAdd(P.hist + HIST_DENSE_BINS, 1ull); if (o < P.hist_overflow_cap) P.hist_overflow[o] = cnt; }
+            }
+          }
+          Lslot[my_slot[u]] = 0; Lcnt[my_slot[u]] = 0;
+        }
+        if (tid == 0) {
+          if (fits) tma_store_1d(P.out_keys + base, st, npad * 8u);
+          P.out_seg_start[p] = fits ? base : 0; P.out_seg_len[p] = npad;
+          my_entries += np - s_holes;
+        }
+      } else {  // too many repeated keys: the partition goes to the compacting variant, which writes into the range reserved here
+        for (uint32_t i = tid; i < SVT_L_SLOTS; i += T) { Lslot[i] = 0; Lcnt[i] = 0; }
+        if (tid == 0) { const uint32_t ri = atomicAdd(P.redo_count, 1u); P.redo_list[ri] = p; P.redo_base[ri] = base; P.redo_len[ri] = npad; }
+      }
+      if (tid < (int)SVT_BLOOM_WORDS) s_bloom[tid] = 0;
+      if (tid == 0) { s_nq = 0; s_nL = 0; s_fail = 0; s_holes = 0; }
+    }
+    if (warp == 0) {
+      if (lane == 0) { tma_commit_group(); settle(); }  // settle: the partition published one iteration ago (it is processed next)
+      // a duplicate-rich input (most partitions handed back) is not this variant's business: stop early, the host repeats the launch without it
+      if (__shfl_sync(0xffffffffu, handed_back, 0) > sieve_redo_limit(P.n_parts)) { wn = 0xffffffffu; nb = 0; nlen = 0; }
+      publish((int)((it + 2) % NM), wn, nb, nlen);
+    }
+    __syncthreads();  // A
+  }
+  if (tid == 0) {
+    tma_wait_group_read<0>();
+    if (my_entries) atomicAdd(P.out_distinct, my_entries);
+  }
+  if (P.hist) hist_flush(s_hist, P, tid);
+}
+
+// behind every segment of odd length: one EMPTY_MIX entry, so that phase B may copy whole 16-byte units (the layout must have
+// room: the speculative layouts give every partition an even capacity)
+__global__ void pad_segments_kernel(uint64_t *keys, const uint64_t *__restrict__ seg_start, const uint64_t *__restrict__ seg_len, uint32_t n_parts) {
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_parts; p += gridDim.x * blockDim.x) {
+    const uint64_t len = seg_len[p];
+    if (len & 1ull) keys[seg_start[p] + len] = EMPTY_MIX;
+  }
+}
+cudaError_t launch_pad_segments(uint64_t *keys, const uint64_t *seg_start, const uint64_t *seg_len, uint32_t n_parts, cudaStream_t s) {
+  if (!n_parts) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  pad_segments_kernel<<<(unsigned)std::min<uint64_t>((n_parts + 255) / 256, (uint64_t)num_sms() * 8), 256, 0, s>>>(keys, seg_start, seg_len, n_parts);
+  return cudaGetLastError();
+}
+
+uint32_t sieve_redo_limit_host(uint32_t n_parts) { return sieve_redo_limit_impl(n_parts); }
+cudaError_t launch_count_partitions_sieve(const CountParams &P, bool padded, cudaStream_t s) {
   if (P.n_parts == 0) return cudaSuccess;
-  if (!P.redo_list || !P.redo_count) return cudaErrorInvalidValue;
+  if (!P.redo_list || !P.redo_count || !P.redo_base || !P.redo_len) return cudaErrorInvalidValue;
+  if (padded) {
+    auto kern = P.R == 1 ? count_partitions_sieve_tma_kernel<true> : count_partitions_sieve_tma_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVT_SMEM);
+    if (e != cudaSuccess) return e;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    kern<<<(unsigned)std::min<uint64_t>(P.n_parts, (uint64_t)num_sms() * 2), SVT_THREADS, SVT_SMEM, s>>>(P);
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)SV_L_SLOTS * (8 + 4 + 2) + (size_t)SV_BM_WORDS * 4 + (size_t)SV_L_MAX * 2;
   const unsigned grid = (unsigned)std::min<uint64_t>(P.n_parts, (uint64_t)num_sms() * 2);
   auto kern = P.R == 1 ? count_partitions_sieve_kernel<true> : count_partitions_sieve_kernel<false>;

@@ -491,3 +491,36 @@ def test_sharded_exchange_shapes_on_one_device(world):
     finally:
         for c in shards:
             c.close()
+
+
+@pytest.mark.parametrize("shape", ["distinct", "repeats", "triple", "few_partitions"])
+def test_phase_b_sieve_variants(shape):
+    """Phase B's sieve (bit map + small side table, keys copied in place; TMA-staged when the runs have padded segments) on
+    inputs it takes whole, inputs with a repeat fraction its side table still holds, and inputs it must hand to the compacting
+    variant (every key repeated; partitions larger than a batch) -- several runs per partition (three calls)."""
+    rng = np.random.default_rng(4242)
+    k = 21
+    n = 2_000_000
+    g = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=3 * n, dtype=np.uint8)].copy()
+    if shape == "repeats":  # ~30 % of the sequence are second copies of earlier 5 kbp blocks
+        for _ in range(180):
+            a, b = (int(x) for x in rng.integers(0, 3 * n - 5000, size=2))
+            g[b:b + 5000] = g[a:a + 5000]
+    if shape == "triple":
+        g[n:2 * n] = g[:n]
+        g[2 * n:] = g[:n]
+    chunks = [g[i * n:(i + 1) * n] for i in range(3)]
+    kw = dict(flags=PART, expected_distinct=3 * n)
+    if shape == "few_partitions":
+        kw = dict(flags=PART, parts_log2=6)   # 64 partitions of ~94 K entries: beyond a batch, beyond one table
+    with kb.GpuKmerCounter(k, **kw) as c:
+        for ch in chunks:
+            c.count_batch(ch, None, np.array([0, len(ch)], dtype=np.uint64))
+        s = c.finalize()
+        got = c.export(1, True)
+        hv, hf = c.histogram(1)
+    ok, oc, _ = orc.count_batch(k, g, None, np.array([0, n, 2 * n, 3 * n], dtype=np.uint64))   # the three calls are three records
+    assert s["path"] == 2 and s["n_windows"] == 3 * (n - k + 1) and s["n_distinct"] == len(ok)
+    assert_same(got, (ok, oc))
+    ov, of = orc.histogram(oc, 1)
+    assert (hv == ov).all() and (hf == of).all()
