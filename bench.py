@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kmix", default="", help="C5: also time kmg_save_kmix(_shard) into this path (needs ~16 B x distinct of disk)")
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--plan-bases", type=float, default=0, help="profiling aid: plan the partitions for this many bases (a slice of C4 then runs "
+                    "phase A with the full job's bin counts; phase B sees proportionally smaller partitions)")
     return ap.parse_args()
 
 
@@ -271,6 +273,8 @@ def main():
     d_seq = torch.empty(n_local + 64, dtype=torch.uint8, device=dev)[:n_local]
     d_qual = torch.empty(n_local + 64, dtype=torch.uint8, device=dev)[:n_local] if (reads and min_q is not None) else None
     hint = int(cfg["bases"] / world * 1.03) + 1024 if (not reads or min_q is None) else 0   # quality-filtered: planned from the data
+    if args.plan_bases:
+        hint = int(args.plan_bases / world * 1.03) + 1024
     CH_READS = 1 << 24   # reads per device call (2.5 GB of ASCII): every call leaves a run; large jobs consolidate while streaming
     bb = 0
     if world > 1:   # sharded: one fused scatter + exchange round moves <= batch_bases bases per rank (identical on every rank)
@@ -300,7 +304,8 @@ def main():
 
     def feed_device():
         if not reads:
-            sharded.count(d_seq, d_off if n_rec_local > 1 else None, expected_keys_per_rank=exp_windows // world + 1024)
+            sharded.count(d_seq, d_off if n_rec_local > 1 else None,
+                          expected_keys_per_rank=int(args.plan_bases) // world if args.plan_bases else exp_windows // world + 1024)
             return
         for c0 in range(0, n_rec_local, CH_READS):
             c1 = min(n_rec_local, c0 + CH_READS)

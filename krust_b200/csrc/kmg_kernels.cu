@@ -829,7 +829,9 @@ __device__ __forceinline__ void scan_octet(const TileSmem *ts, int i, int g, int
   const uint32_t vprev = ts->valid[LEAD_MASK_WORDS + i - 1], vcur = ts->valid[LEAD_MASK_WORDS + i];
   uint32_t sprev = 0, scur = 0;
   if (has_start) { sprev = ts->start[LEAD_MASK_WORDS + i - 1]; scur = ts->start[LEAD_MASK_WORDS + i]; }
-  const uint32_t ok8 = (window_ok_mask(vprev, vcur, sprev, scur, k, has_start) >> (24 - 8 * g)) & 0xffu;  // window 8g+j at bit 7-j
+  // 64 valid bases and no record start among them (the normal case inside a genome): every window ending in this word counts
+  const uint32_t okw = ((vprev & vcur) == 0xffffffffu && !(sprev | scur)) ? 0xffffffffu : window_ok_mask(vprev, vcur, sprev, scur, k, has_start);
+  const uint32_t ok8 = (okw >> (24 - 8 * g)) & 0xffu;  // window 8g+j at bit 7-j
   if (ok8 == 0) return;
   const uint64_t mask = kmer_mask(k);
   const int rc_shift = 2 * (k - 1), e0 = 8 * g;
@@ -894,12 +896,29 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
           if (g_base[p] == NO_BASE) cnt[p] = 0;  // refused: nothing of this partition is written
         }
         __syncthreads();
+        // copy-out, lanes along the rows (contiguous destinations).  Rows of up to 24 slots (more than ~680 partitions): EIGHT LANES PER
+        // ROW, the row's size and base fetched once per lane and row, up to three predicated slot copies, no slot -> row division and no
+        // loop (the flat walk over all slots cost ~20 instructions per slot visit and 1.4 of 4.4 warp-instr per window,
+        // profiles/r2_v1_lines.txt; a half-warp per row with a strided loop was worse still: 2.2).
+        // (two slots per lane through one 16-byte row load was measured SLOWER, 44.8 vs 40.9 ms of phase A on C4: the stores of a warp
+        //  then stride by 16 bytes and touch twice the sectors)
+        if (cap <= 24u) {
+          const uint32_t l = tid & 7u;
+#pragma unroll 2
+          for (uint32_t p = tid >> 3; p < n_parts; p += ROWS_THREADS / 8) {
+            const uint32_t c = min(cnt[p], cap);
+            uint64_t *dst = out + (uint64_t)g_base[p] + l;
+            const uint64_t *row = rows + p * cap + l;
+            if (l < c) __stcs(dst, row[0]);
+            if (l + 8u < c) __stcs(dst + 8, row[8]);
+            if (c > 16u && l + 16u < c) __stcs(dst + 16, row[16]);
+          }
+        } else {
 #pragma unroll 4
-        for (uint32_t x = tid; x < n_slots; x += ROWS_THREADS) {  // lanes walk along the rows: contiguous destinations
-          // (two slots per lane -- one 16-byte row load, two stores -- was measured SLOWER, 44.8 vs 40.9 ms of phase A on C4: the stores
-          //  of a warp then stride by 16 bytes and touch twice the sectors; the copy-out is bound by store sectors, not by issue slots)
-          const uint32_t p = __umulhi(x, magic), e = x - p * cap;
-          if (e < cnt[p]) __stcs(out + (uint64_t)g_base[p] + e, rows[x]);
+          for (uint32_t x = tid; x < n_slots; x += ROWS_THREADS) {
+            const uint32_t p = __umulhi(x, magic), e = x - p * cap;
+            if (e < cnt[p]) __stcs(out + (uint64_t)g_base[p] + e, rows[x]);
+          }
         }
         for (uint32_t o = tid; o < n_ov; o += ROWS_THREADS) {
           const uint32_t meta = ov_meta[o];

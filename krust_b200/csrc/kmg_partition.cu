@@ -351,16 +351,31 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
     if (g + 1 < g_end) {
       c_next = s_c[nslot];
       tile_range(g + 1, c_next, begin_next, m_next);
-      const uint64_t *kb = refine_keys_of(P, c_next) + begin_next;
+      const uint64_t *kb = refine_keys_of(P, c_next) + begin_next + tid;
+      uint32_t mn = m_next;
+      asm volatile("" : "+l"(kb), "+r"(mn));  // pinned in registers: the compiler otherwise re-derives the tile's base (segment tables, source select) for every load
 #pragma unroll
-      for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m_next ? __ldcs(kb + i) : EMPTY_KEY; }
+      for (int j = 0; j < U; ++j) key[j] = (uint32_t)(j * REFINE_ROWS_THREADS + tid) < mn ? __ldcs(kb + j * REFINE_ROWS_THREADS) : EMPTY_KEY;
     }
     __syncthreads();
     if (!exact) {
+      if (cap <= 24u) {  // eight lanes per row, lanes along the row: contiguous destinations, row size / base fetched once per row (see partition_scatter_rows_kernel)
+        const uint32_t l = tid & 7u;
+#pragma unroll 2
+        for (uint32_t s2 = tid >> 3; s2 < P.n_sub; s2 += REFINE_ROWS_THREADS / 8) {
+          const uint32_t h = min(cnt[s2], cap);
+          uint64_t *dst = P.out_keys + (uint64_t)g_base[s2] + l;
+          const uint64_t *row = rows + s2 * cap + l;
+          if (l < h) dst[0] = row[0];
+          if (l + 8u < h) dst[8] = row[8];
+          if (h > 16u && l + 16u < h) dst[16] = row[16];
+        }
+      } else {
 #pragma unroll 4
-      for (uint32_t x = tid; x < n_slots; x += REFINE_ROWS_THREADS) {  // lanes walk along the rows: contiguous destinations
-        const uint32_t s2 = __umulhi(x, magic), e = x - s2 * cap;
-        if (e < cnt[s2]) P.out_keys[(uint64_t)g_base[s2] + e] = rows[x];
+        for (uint32_t x = tid; x < n_slots; x += REFINE_ROWS_THREADS) {  // lanes walk along the rows: contiguous destinations
+          const uint32_t s2 = __umulhi(x, magic), e = x - s2 * cap;
+          if (e < cnt[s2]) P.out_keys[(uint64_t)g_base[s2] + e] = rows[x];
+        }
       }
       for (uint32_t o = tid; o < n_ov; o += REFINE_ROWS_THREADS) {
         const uint32_t meta = ov_meta[o];
