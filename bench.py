@@ -369,15 +369,24 @@ def main():
         # clears the timers, so these are the last step's kernels on this rank.  Per k-mer: A1 = 0.375 in + 8 out, A2 = 8 in + 8 out,
         # B = 8 in + 16 out per DISTINCT key.
         a_ms, b_ms = local["scan_ns"] / 1e6, local["consolidate_ns"] / 1e6
+        pt = engine.counter.phase_times()
+        a1_ms, a2_ms = pt["a1_ns"] / 1e6, pt["a2_ns"] / 1e6
         b_bytes = gpu_windows * 8.0 + 16.0 * summary["n_distinct"] / world
+        a1_bytes, a2_bytes = gpu_windows * 8.0 + input_bytes, gpu_windows * 16.0
+        gbs = lambda by, ms: by / (ms * 1e-3) / 1e9 if ms else 0.0
         pipeline = {"phase_a_ms": a_ms, "phase_b_ms": b_ms,
-                    "phase_a_gbs": (gpu_windows * 24.0 + input_bytes) / (a_ms * 1e-3) / 1e9 if a_ms else 0.0,
-                    "phase_b_gbs": b_bytes / (b_ms * 1e-3) / 1e9 if b_ms else 0.0,
+                    "phase_a_gbs": gbs(gpu_windows * 24.0 + input_bytes, a_ms), "phase_b_gbs": gbs(b_bytes, b_ms),
+                    "a1_ms": a1_ms, "a2_ms": a2_ms,
+                    "a1_frac": gbs(a1_bytes, a1_ms) / peak, "a2_frac": gbs(a2_bytes, a2_ms) / peak, "b_frac": gbs(b_bytes, b_ms) / peak,
                     "consolidations": local["n_grows"]}
-        if b_ms >= 0.4 * a_ms:
-            kern_ms, alg_bytes, kern_name = b_ms, b_bytes, "count_partitions_smem_kernel (phase B: one CTA per hash partition, upsert into a shared-memory table, compact)"
-        else:
-            kern_ms, alg_bytes, kern_name = a_ms, gpu_windows * 24.0 + input_bytes, "phase A kernels (ingest + partition_scatter_rows + refine_rows: two-level hash partitioning)"
+        # the dominant kernel = the stage with the most device time (its own algorithmic bytes; all three fractions are in `pipeline`)
+        stages = [(a1_ms, a1_bytes, "ingest + partition_scatter_rows_kernel (A1: tile scan, canonical k-mers, mix, coarse scatter through shared-memory rows; "
+                                    "0.375 B in + 8 B out per k-mer)"),
+                  (a2_ms, a2_bytes, "refine_rows_kernel (A2: coarse bins -> fine partitions through shared-memory rows, on N GPUs the pull over NVLink; "
+                                    "8 B in + 8 B out per k-mer)"),
+                  (b_ms, b_bytes, "count_partitions_sieve_tma_kernel (phase B: one CTA per hash partition, bit-map sieve + bulk copies; compacting "
+                                  "count_partitions_smem_kernel for repeat-rich input; 8 B in + 16 B out per k-mer)")]
+        kern_ms, alg_bytes, kern_name = max(stages, key=lambda t: t[0])
     else:
         kern_ms = local["kernel_ns"] / 1e6          # scan_count_kernel of the last step (reset() clears the timer)
         alg_bytes = alg_job

@@ -261,6 +261,11 @@ kmg_status kmg_progress(const kmg_ctx *ctx, uint64_t *records, uint64_t *bases);
 /* Diagnostics: number of this library's own CUDA kernels launched so far in this process. */
 uint64_t kmg_kernel_launches(void);
 
+/* Diagnostics (no reference counterpart): device time of the partitioned pipeline's stages since the last kmg_reset, CUDA events on
+ * the launching stream.  out_ns4[0] = ingest + A1 (tile scan + coarse scatter), [1] = A2 (refine to fine partitions, on N GPUs the
+ * pull over NVLink), [2] = phase B (count the partitions), [3] = everything else timed (paths 0 / 1: the scan-and-count kernel). */
+kmg_status kmg_phase_times(kmg_ctx *ctx, uint64_t *out_ns4);
+
 /* Test/bench helper: fill d_out[n] with the deterministic synthetic base stream
  * (same generator as oracle/kmer_oracle.c orc_synth_uniform). */
 kmg_status kmg_synth_uniform_device(kmg_ctx *ctx, uint64_t seed, uint64_t first_base, uint64_t n, uint8_t *d_out);

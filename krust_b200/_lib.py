@@ -80,6 +80,7 @@ SIGNATURES = {
     "kmg_index_open": (i32, [C.c_char_p, C.c_int32, C.POINTER(vp)]),
     "kmg_progress": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
     "kmg_kernel_launches": (u64, []),
+    "kmg_phase_times": (i32, [vp, C.POINTER(u64)]),
     "kmg_synth_uniform_device": (i32, [vp, u64, u64, u64, vp]),
     "kmg_synth_reads_device": (i32, [vp, u64, u32, u64, u64, vp, vp]),
     "kmg_parse_fastx": (i32, [vp, u64, i32, vp, vp, vp, u64, C.POINTER(u64), C.c_char_p, C.c_size_t]),

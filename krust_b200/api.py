@@ -346,6 +346,12 @@ class GpuKmerCounter:
         _check(self._L.kmg_finalize(self._ctx, C.byref(s)), self._ctx)
         return {f: getattr(s, f) for f, _ in KmgSummary._fields_}
 
+    def phase_times(self) -> dict:
+        """Device time (ns) of the partitioned pipeline's stages since the last reset: kmg_phase_times."""
+        out = (C.c_uint64 * 4)()
+        _check(self._L.kmg_phase_times(self._ctx, out), self._ctx)
+        return {"a1_ns": int(out[0]), "a2_ns": int(out[1]), "b_ns": int(out[2]), "other_ns": int(out[3])}
+
     def export(self, min_count: int = 1, sorted: bool = True) -> Tuple[np.ndarray, np.ndarray]:
         n = C.c_uint64(0)
         _check(self._L.kmg_export_counts(self._ctx, min_count, int(sorted), None, None, 0, C.byref(n)), self._ctx)

@@ -150,7 +150,7 @@ struct kmg_ctx {
   uint64_t n_records = 0, n_bases = 0, h2d_bytes = 0;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   double kernel_ms = 0.0;
-  double cat_ms[2] = {0.0, 0.0};  // 0: scan / partition kernels, 1: consolidation kernel
+  double cat_ms[3] = {0.0, 0.0, 0.0};  // 0: scan / partition kernels (includes 2), 1: consolidation kernel, 2: refine (A2) launches, nested inside 0
   struct Timer { cudaEvent_t a, b; int cat; };
   std::vector<Timer> pending_timers;
 };
@@ -324,7 +324,7 @@ void timer_end(kmg_ctx *c, size_t idx) { cudaEventRecord(c->pending_timers[idx].
 void timers_collect(kmg_ctx *c) {
   for (auto &p : c->pending_timers) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { c->kernel_ms += ms; c->cat_ms[p.cat] += ms; }
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { if (p.cat != 2) c->kernel_ms += ms; c->cat_ms[p.cat] += ms; }
     cudaEventDestroy(p.a); cudaEventDestroy(p.b);
   }
   c->pending_timers.clear();
@@ -481,7 +481,9 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
     uint32_t h_flag = 0;
     e = cudaMemsetAsync(rp.overflow_flag, 0, 4, c->stream);
     if (e == cudaSuccess) e = launch_fill_strided(r.d_seg_start, P, cap_f, c->stream);
+    const size_t tmr2 = timer_begin(c, 2);
     if (e == cudaSuccess) e = launch_refine(rp, true, c->stream);
+    timer_end(c, tmr2);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, rp.overflow_flag, 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { cleanup(); free_run(c, r); return cuda_fail(c, e, "refine scatter (speculative layout)"); }
@@ -502,7 +504,9 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   rp.fine_counts = reinterpret_cast<unsigned long long *>(r.d_seg_len);
   rp.fine_start = reinterpret_cast<const unsigned long long *>(r.d_seg_start);
   rp.fine_cursor = c->d_fine_cursor;
+  const size_t tmr3 = timer_begin(c, 2);
   e = launch_refine(rp, false, c->stream);
+  timer_end(c, tmr3);
   if (e == cudaSuccess && (!c->d_scan_tmp || c->scan_tmp_items < P)) {
     cudaFree(c->d_scan_tmp); c->d_scan_tmp = nullptr;
     e = exclusive_sum_u64(nullptr, nullptr, P, nullptr, &c->scan_tmp_bytes, c->stream);
@@ -516,7 +520,9 @@ kmg_status refine_to_run(kmg_ctx *c, uint64_t *d_ckeys, uint64_t *d_ccounts, con
   if (s == KMG_OK && d_ccounts) s = alloc_or_consolidate(c, reinterpret_cast<void **>(&r.d_counts), n * 8, "fine counts");
   if (s != KMG_OK) { cleanup(); free_run(c, r); return s; }
   rp.out_keys = r.d_keys; rp.out_counts = r.d_counts;
+  const size_t tmr4 = timer_begin(c, 2);
   e = launch_refine(rp, true, c->stream);
+  timer_end(c, tmr4);
   if (e == cudaSuccess && sync) e = cudaStreamSynchronize(c->stream);
   cleanup();
   if (e != cudaSuccess) { free_run(c, r); return cuda_fail(c, e, "refine scatter"); }
@@ -1291,7 +1297,7 @@ KMG_EXPORT kmg_status kmg_reset(kmg_ctx *c) {
   c->distinct_ub = 0; c->n_records = c->n_bases = c->h2d_bytes = 0;
   CU(c, cudaStreamSynchronize(c->stream));
   timers_collect(c);
-  c->kernel_ms = c->cat_ms[0] = c->cat_ms[1] = 0.0;
+  c->kernel_ms = c->cat_ms[0] = c->cat_ms[1] = c->cat_ms[2] = 0.0;
   return KMG_OK;
 }
 
@@ -2937,6 +2943,17 @@ KMG_EXPORT kmg_status kmg_progress(const kmg_ctx *c, uint64_t *records, uint64_t
 }
 
 KMG_EXPORT uint64_t kmg_kernel_launches(void) { return kernel_launches(); }
+
+KMG_EXPORT kmg_status kmg_phase_times(kmg_ctx *c, uint64_t *out_ns) {
+  if (!c || !out_ns) return KMG_ERR_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  timers_collect(c);
+  const double a2 = c->cat_ms[2], a1 = std::max(0.0, c->cat_ms[0] - a2), b = c->cat_ms[1];
+  out_ns[0] = (uint64_t)(a1 * 1e6); out_ns[1] = (uint64_t)(a2 * 1e6); out_ns[2] = (uint64_t)(b * 1e6);
+  out_ns[3] = (uint64_t)(std::max(0.0, c->kernel_ms - c->cat_ms[0] - b) * 1e6);
+  return KMG_OK;
+}
 
 KMG_EXPORT kmg_status kmg_synth_uniform_device(kmg_ctx *c, uint64_t seed, uint64_t first_base, uint64_t n, uint8_t *d_out) {
   if (!c) return KMG_ERR_INVALID_ARG;

@@ -909,6 +909,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
             const uint32_t c = min(cnt[p], cap);
             uint64_t *dst = out + (uint64_t)g_base[p] + l;
             const uint64_t *row = rows + p * cap + l;
+            if (l == 0u) cnt[p] = 0;  // all eight lanes have read it (same instruction): the row is handed back clean, no separate pass + barrier
             if (l < c) __stcs(dst, row[0]);
             if (l + 8u < c) __stcs(dst + 8, row[8]);
             if (c > 16u && l + 16u < c) __stcs(dst + 16, row[16]);
@@ -924,8 +925,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
           const uint32_t meta = ov_meta[o];
           if (g_base[meta >> 16] != NO_BASE) __stcs(out + (uint64_t)g_base[meta >> 16] + (meta & 0xffffu), ov_key[o]);
         }
-        __syncthreads();
-        for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
+        if (cap > 24u) {
+          __syncthreads();
+          for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
+        }
       }
       if (tid == 0) s_ovn = 0;
       __syncthreads();

@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
           const uint32_t h = min(cnt[s2], cap);
           uint64_t *dst = P.out_keys + (uint64_t)g_base[s2] + l;
           const uint64_t *row = rows + s2 * cap + l;
+          if (l == 0u) cnt[s2] = 0;  // read by all eight lanes in the same instruction: no separate clearing pass + barrier
           if (l < h) dst[0] = row[0];
           if (l + 8u < h) dst[8] = row[8];
           if (h > 16u && l + 16u < h) dst[16] = row[16];
@@ -381,8 +382,10 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
         const uint32_t meta = ov_meta[o];
         if (g_base[meta >> 16] != NO_BASE) P.out_keys[(uint64_t)g_base[meta >> 16] + (meta & 0xffffu)] = ov_key[o];
       }
-      __syncthreads();
-      for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
+      if (cap > 24u) {
+        __syncthreads();
+        for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
+      }
     }
     if (tid == 0) s_ovn = 0;
     __syncthreads();
