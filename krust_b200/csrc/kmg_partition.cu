@@ -1447,6 +1447,8 @@ __global__ void __launch_bounds__(SVT_THREADS, 2) count_partitions_sieve_tma_ker
       }
     } else {
       unsigned long long *st = stage + (size_t)ks * SVT_CAP;
+      // the previous partition's queue / table counters: everybody read them before barrier A, nobody touches them before barrier B
+      if (tid == 0) { s_nq = 0; s_nL = 0; s_fail = 0; s_holes = 0; }
       mbar_wait(&bar[ks], (ph >> ks) & 1u);
       ph ^= 1u << ks;
       // ---- pass 1: read the staged keys, write the counts (1 per live entry), test-and-set in the bit map
@@ -1566,7 +1568,6 @@ __global__ void __launch_bounds__(SVT_THREADS, 2) count_partitions_sieve_tma_ker
         if (tid == 0) { const uint32_t ri = atomicAdd(P.redo_count, 1u); P.redo_list[ri] = p; P.redo_base[ri] = base; P.redo_len[ri] = npad; }
       }
       if (tid < (int)SVT_BLOOM_WORDS) s_bloom[tid] = 0;
-      if (tid == 0) { s_nq = 0; s_nL = 0; s_fail = 0; s_holes = 0; }
     }
     if (warp == 0) {
       if (lane == 0) { tma_commit_group(); settle(); }  // settle: the partition published one iteration ago (it is processed next)

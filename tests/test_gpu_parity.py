@@ -493,15 +493,17 @@ def test_sharded_exchange_shapes_on_one_device(world):
             c.close()
 
 
-@pytest.mark.parametrize("shape", ["distinct", "repeats", "triple", "few_partitions"])
+@pytest.mark.parametrize("shape", ["distinct", "repeats", "triple", "few_partitions", "small"])
 def test_phase_b_sieve_variants(shape):
     """Phase B's sieve (bit map + small side table, keys copied in place; TMA-staged when the runs have padded segments) on
     inputs it takes whole, inputs with a repeat fraction its side table still holds, and inputs it must hand to the compacting
     variant (every key repeated; partitions larger than a batch) -- several runs per partition (three calls)."""
     rng = np.random.default_rng(4242)
     k = 21
-    n = 2_000_000
+    n = 100_000 if shape == "small" else 2_000_000   # "small": the same kernels at a size compute-sanitizer's racecheck finishes (tools/sanitize.sh)
     g = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=3 * n, dtype=np.uint8)].copy()
+    if shape == "small":
+        g[250_000:255_000] = g[10_000:15_000]
     if shape == "repeats":  # ~30 % of the sequence are second copies of earlier 5 kbp blocks
         for _ in range(180):
             a, b = (int(x) for x in rng.integers(0, 3 * n - 5000, size=2))
@@ -524,3 +526,38 @@ def test_phase_b_sieve_variants(shape):
     assert_same(got, (ok, oc))
     ov, of = orc.histogram(oc, 1)
     assert (hv == ov).all() and (hf == of).all()
+
+
+def test_c4_bin_geometry_on_100mbp():
+    """The bin counts of the full C4 job (~1000 x 1000: rows of 16 slots, eight lanes per row in the copy-out of both scatter
+    levels, speculative layouts with padded segments, TMA-staged sieve) on an input the oracle counts in seconds: 100 Mbp with
+    2^20 partitions, the whole table and the histogram against the oracle; then a second, overlapping call (the first result
+    re-enters phase B as a weighted run)."""
+    import torch
+    dev = torch.device("cuda:0")
+    k, n, n_rec = 21, 100_000_000, 10
+    buf = torch.empty(n, dtype=torch.uint8, device=dev)
+    offsets = torch.arange(0, n + 1, n // n_rec, dtype=torch.int64, device=dev)
+    host = orc.synth_uniform(4242, 0, n)
+    off_np = np.arange(0, n + 1, n // n_rec, dtype=np.uint64)
+    with kb.GpuKmerCounter(k, flags=PART, parts_log2=20) as c:
+        c.synth_uniform_device(4242, 0, n, buf.data_ptr())
+        c.count_device(buf.data_ptr(), n, d_offsets=offsets.data_ptr(), n_records=n_rec)
+        s = c.finalize()
+        got = c.export(1, True)
+        okeys, ocounts, owin = orc.count_batch_mt(k, host, None, off_np)
+        assert s["path"] == 2 and owin == s["n_windows"] and s["n_distinct"] == len(okeys)
+        assert_same(got, (okeys, ocounts))
+        hv, hf = c.histogram(1)
+        ov, of = orc.histogram(ocounts, 1)
+        assert (hv == ov).all() and (hf == of).all()
+        # the first 30 Mbp (3 records) once more
+        m = 3 * (n // n_rec)
+        c.count_device(buf.data_ptr(), m, d_offsets=offsets.data_ptr(), n_records=3)
+        c.finalize()
+        got2 = c.export(1, True)
+        k2, c2, _ = orc.count_batch_mt(k, host[:m], None, off_np[:4])
+        idx = np.searchsorted(okeys, k2)
+        want = ocounts.copy()
+        want[idx] += c2
+        assert_same(got2, (okeys, want))
