@@ -393,6 +393,144 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
   }
 }
 
+// Rows kernel with the reservation FUSED into the copy-out (rows of up to 24 slots; see partition_scatter_rows_fused_kernel in
+// kmg_kernels.cu for the scheme and its hazard analysis): every lane reserves for one of the eight rows its 8-lane group copies,
+// sizes and bases travel by shuffle, the next tile's loads are issued while the reservations are in flight, and the overflow
+// lists are double buffered by tile parity.  Two block barriers per tile instead of four.
+constexpr int REFINE_FUSED_OVERFLOW = 3072;  // per list (two lists)
+__global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_fused_kernel(RefineParams P) {
+  extern __shared__ __align__(16) uint8_t rsm[];
+  const uint32_t cap = P.row_cap;
+  uint64_t *rows = reinterpret_cast<uint64_t *>(rsm);  // REFINE_ROWS_SLOTS
+  uint64_t *ov_key = rows + REFINE_ROWS_SLOTS;         // 2 x REFINE_FUSED_OVERFLOW
+  uint32_t *ov_meta = reinterpret_cast<uint32_t *>(ov_key + 2 * REFINE_FUSED_OVERFLOW);
+  uint32_t *cnt = ov_meta + 2 * REFINE_FUSED_OVERFLOW, *s_off = cnt + P.n_sub, *g_base = s_off + P.n_sub;
+  __shared__ uint32_t s_c[2], s_ovn[2], s_scan[REFINE_ROWS_THREADS / 32 + 1];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t l = tid & 7u, grp = tid >> 3, lead = lane & 24u;
+  constexpr int U = REFINE_TILE / REFINE_ROWS_THREADS;
+  const uint32_t per_cta = (P.n_tiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t g_begin = blockIdx.x * per_cta, g_end = min(g_begin + per_cta, P.n_tiles);
+  if (g_begin >= g_end) return;
+  uint32_t c_hint = 0;  // thread 0: coarse partition of the tile located last
+  auto locate = [&](uint32_t g, int slot) {
+    if (tid == 0) {
+      if (P.tile_prefix[c_hint] > g || c_hint >= P.n_coarse) c_hint = 0;
+      if (P.tile_prefix[c_hint + 1] <= g) {
+        uint32_t lo = c_hint, hi = P.n_coarse;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.tile_prefix[mid] <= g) lo = mid; else hi = mid; }
+        c_hint = lo;
+      }
+      s_c[slot] = c_hint;
+    }
+  };
+  auto tile_range = [&](uint32_t g, uint32_t c, uint64_t &begin, uint32_t &m) {
+    begin = P.coarse_start[c] + (uint64_t)(g - P.tile_prefix[c]) * REFINE_TILE;
+    const uint64_t end_c = P.coarse_len ? P.coarse_start[c] + P.coarse_len[c] : P.coarse_start[c + 1];
+    m = (uint32_t)(end_c - begin < (uint64_t)REFINE_TILE ? end_c - begin : (uint64_t)REFINE_TILE);
+  };
+  for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
+  if (tid == 0) { s_ovn[0] = 0; s_ovn[1] = 0; }
+  locate(g_begin, 0);
+  __syncthreads();
+  uint32_t c = s_c[0], m;
+  uint64_t begin;
+  tile_range(g_begin, c, begin, m);
+  uint64_t key[U];
+  {
+    const uint64_t *kb = refine_keys_of(P, c) + begin;
+#pragma unroll
+    for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m ? __ldcs(kb + i) : EMPTY_KEY; }
+  }
+  uint32_t pp = 0;
+  for (uint32_t g = g_begin; g < g_end; ++g, pp ^= 1u) {
+    const uint32_t cb = P.in_group > 1 ? c / P.in_group : c;  // coarse bin of input partition c
+    const uint64_t f0 = (uint64_t)cb * P.n_sub;
+    const uint32_t sub_base = (cb % P.sub_old) * P.n_sub;
+    uint64_t *ovk = ov_key + pp * REFINE_FUSED_OVERFLOW;
+    uint32_t *ovm = ov_meta + pp * REFINE_FUSED_OVERFLOW;
+    {  // ---- rank the tile's keys into the rows
+      uint32_t sb[U], r[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (P.in_keys) key[j] = mix64(key[j]);
+        sb[j] = sub_of_mix(key[j], P.sub_total) - sub_base;
+        r[j] = 0;
+        if (j * REFINE_ROWS_THREADS + tid < m) r[j] = atomicAdd(cnt + sb[j], 1u);
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (j * REFINE_ROWS_THREADS + tid >= m) continue;
+        if (r[j] < cap) rows[sb[j] * cap + r[j]] = key[j];
+        else {
+          const uint32_t o = atomicAdd(&s_ovn[pp], 1u);
+          if (o < (uint32_t)REFINE_FUSED_OVERFLOW) { ovk[o] = key[j]; ovm[o] = (sb[j] << 16) | r[j]; }  // r < REFINE_TILE <= 65536
+        }
+      }
+    }
+    const int nslot = (g - g_begin + 1) & 1;
+    if (g + 1 < g_end) locate(g + 1, nslot);
+    __syncthreads();  // B1: rows, counters, this parity's overflow list and the next tile's partition are published
+    const uint32_t n_ov = s_ovn[pp];
+    const bool exact = n_ov > (uint32_t)REFINE_FUSED_OVERFLOW;  // block-uniform: skewed tile, take the exact route
+    uint32_t c_next = c, m_next = 0;
+    uint64_t begin_next = 0;
+    const uint64_t *kb = nullptr;
+    uint32_t mn = 0;
+    if (g + 1 < g_end) {
+      c_next = s_c[nslot];
+      tile_range(g + 1, c_next, begin_next, m_next);
+      kb = refine_keys_of(P, c_next) + begin_next + tid;
+      mn = m_next;
+      asm volatile("" : "+l"(kb), "+r"(mn));  // pinned in registers (see refine_rows_kernel)
+    }
+    if (exact) {
+      for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
+      __syncthreads();
+      refine_tile_two_pass<REFINE_ROWS_THREADS, true>(P, refine_keys_of(P, c), begin, m, f0, sub_base, rows, nullptr, cnt, s_off, g_base, s_scan);
+#pragma unroll
+      for (int j = 0; j < U; ++j) key[j] = (uint32_t)(j * REFINE_ROWS_THREADS + tid) < mn ? __ldcs(kb + j * REFINE_ROWS_THREADS) : EMPTY_KEY;
+      if (tid == 0) s_ovn[pp] = 0;
+      __syncthreads();  // the two-pass procedure ends by clearing cnt[] without a barrier
+    } else {
+      for (uint32_t t0 = 0; t0 < P.n_sub; t0 += REFINE_ROWS_THREADS) {  // one round per 1024 sub-bins
+        const uint32_t sm = t0 + grp + (REFINE_ROWS_THREADS / 8) * l;  // the row this lane reserves for
+        uint32_t hm = 0, bm = 0;
+        if (sm < P.n_sub) {
+          hm = cnt[sm];
+          cnt[sm] = 0;  // nobody else reads it: the row is handed back clean
+          bm = refine_reserve(P, f0 + sm, hm);
+          g_base[sm] = bm;
+          if (bm == NO_BASE) hm = 0;  // refused: nothing of this sub-bin is written
+        }
+        if (t0 == 0) {  // the next tile's keys are requested while the reservations are in flight; their latency hides behind the copy-out
+#pragma unroll
+          for (int j = 0; j < U; ++j) key[j] = (uint32_t)(j * REFINE_ROWS_THREADS + tid) < mn ? __ldcs(kb + j * REFINE_ROWS_THREADS) : EMPTY_KEY;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t h = min(__shfl_sync(0xffffffffu, hm, lead + i), cap);  // 0 for rows past n_sub
+          const uint32_t b = __shfl_sync(0xffffffffu, bm, lead + i);
+          uint64_t *dst = P.out_keys + (uint64_t)b + l;
+          const uint64_t *row = rows + (t0 + grp + (REFINE_ROWS_THREADS / 8) * i) * cap + l;
+          if (l < h) dst[0] = row[0];
+          if (l + 8u < h) dst[8] = row[8];
+          if (h > 16u && l + 16u < h) dst[16] = row[16];
+        }
+      }
+      __syncthreads();  // B2: rows are free for the next tile, g_base[] is complete
+      if (n_ov) {
+        for (uint32_t o = tid; o < n_ov; o += REFINE_ROWS_THREADS) {
+          const uint32_t meta = ovm[o];
+          if (g_base[meta >> 16] != NO_BASE) P.out_keys[(uint64_t)g_base[meta >> 16] + (meta & 0xffffu)] = ovk[o];
+        }
+        if (tid == 0) s_ovn[pp] = 0;
+      }
+    }
+    c = c_next; m = m_next; begin = begin_next;
+  }
+}
+
 static bool refine_legacy() {
   static const bool legacy = [] { const char *v = getenv("KMG_REFINE"); return v && v[0] == 'l'; }();  // ablation: KMG_REFINE=legacy
   return legacy;
@@ -418,6 +556,13 @@ cudaError_t launch_refine(const RefineParams &P_in, bool scatter, cudaStream_t s
   if (scatter && refine_single_pass_available(P.n_sub, P.counts || P.out_counts)) {
     P.row_cap = std::min<uint32_t>((uint32_t)REFINE_ROWS_SLOTS / P.n_sub, REFINE_TILE);  // mean fill 8192 / (n_sub * cap) ~ 0.5
     P.row_magic = (uint32_t)(((1ull << 32) + P.row_cap - 1) / P.row_cap);
+    if (rows_fused() && P.row_cap <= 24u) {  // reservation fused into the copy-out, two barriers per tile
+      const size_t fsmem = (size_t)REFINE_ROWS_SLOTS * 8 + 2 * (size_t)REFINE_FUSED_OVERFLOW * 12 + 3 * (size_t)P.n_sub * sizeof(uint32_t);
+      if ((e = cudaFuncSetAttribute(refine_rows_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)) != cudaSuccess) return e;
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      refine_rows_fused_kernel<<<(unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms()), REFINE_ROWS_THREADS, fsmem, s>>>(P);
+      return cudaGetLastError();
+    }
     const size_t smem = (size_t)REFINE_ROWS_SLOTS * 8 + (size_t)REFINE_ROWS_OVERFLOW * 12 + 3 * (size_t)P.n_sub * sizeof(uint32_t);
     if ((e = cudaFuncSetAttribute(refine_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -561,3 +561,35 @@ def test_c4_bin_geometry_on_100mbp():
         want = ocounts.copy()
         want[idx] += c2
         assert_same(got2, (okeys, want))
+
+
+def test_c4_bin_geometry_on_skewed_input():
+    """The C4 bin counts (2^10 x 2^10: rows of 16 slots, the scatter kernels with the reservation fused into the copy-out) on an
+    input whose sub-tiles overflow their rows in every way: blocks copied many times (a few overflow keys per sub-tile: the
+    double-buffered overflow lists), a 40-base satellite and poly-A stretches (thousands of equal keys per sub-tile: the
+    per-sub-tile exact route, then the job-wide exact layout once a partition outgrows its speculative share), N runs."""
+    rng = np.random.default_rng(777)
+    k, n = 21, 24_000_000
+    g = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n, dtype=np.uint8)].copy()
+    block = g[1000:1600].copy()
+    for pos in range(2_000_000, 8_000_000, 9_000):      # 600-base block every 9 kbp: ~670 copies
+        g[pos:pos + 600] = block
+    sat = g[5000:5040].copy()
+    g[9_000_000:10_000_000] = np.tile(sat, 25_000)      # satellite
+    g[12_000_000:13_500_000] = ord("A")                 # poly-A
+    g[15_000_000:15_400_000] = ord("T")                 # its reverse complement: the same canonical key
+    for pos in rng.integers(0, n - 10, size=300):
+        g[pos:pos + 10] = ord("N")
+    off_np = np.array([0, 5_000_000, 12_700_000, n], dtype=np.uint64)
+    okeys, ocounts, owin = orc.count_batch_mt(k, g, None, off_np)
+    ov, of = orc.histogram(ocounts, 1)
+    for parts_log2 in (20, 19):   # 1024 x 1024 (rows of 16 slots) and 1024 x 512 / 512 x 1024 geometry
+        with kb.GpuKmerCounter(k, flags=PART, parts_log2=parts_log2) as c:
+            c.count_batch(g[:12_700_000], None, off_np[:3])
+            c.count_batch(g[12_700_000:], None, np.array([0, n - 12_700_000], dtype=np.uint64))
+            s = c.finalize()
+            got = c.export(1, True)
+            hv, hf = c.histogram(1)
+        assert s["path"] == 2 and s["n_windows"] == owin and s["n_distinct"] == len(okeys)
+        assert_same(got, (okeys, ocounts))
+        assert (hv == ov).all() and (hf == of).all()
