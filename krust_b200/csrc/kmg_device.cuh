@@ -132,6 +132,42 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+
+// ---- shared-memory accesses by 32-bit shared-space address ----------------------------------------
+// The scatter kernels' inner loops address their shared-memory rows / counters through addresses computed ONCE per kernel
+// (smem_u32).  Through generic pointers derived from the extern array the compiler re-derived the CTA's shared window
+// (S2R SR_CgaCtaId + LEA) inside every predicated region, i.e. per key, and wrapped every conditional access into a
+// BSSY / BRA / BSYNC region; the forms below are single predicated instructions.
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+  uint32_t r;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(addr), "r"(v) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// if (pred) shared[addr] = v
+__device__ __forceinline__ void sts64_if(bool pred, uint32_t addr, uint64_t v) {
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u64 [%0], %1; }" ::"r"(addr), "l"(v), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ void sts32_if(bool pred, uint32_t addr, uint32_t v) {
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u32 [%0], %1; }" ::"r"(addr), "r"(v), "r"((uint32_t)pred) : "memory");
+}
+// if (a < b) *dst = shared[addr]   (one predicated 8-byte load + store; t is set first so that it is not live around the caller's loop; STREAM: st.global.cs, the line is not re-read soon)
+template <bool STREAM>
+__device__ __forceinline__ void copy64_if_lt(uint32_t a, uint32_t b, uint64_t *dst, uint32_t addr) {
+  if (STREAM)
+    asm volatile("{ .reg .pred p; .reg .b64 t; setp.lt.u32 p, %2, %3; mov.b64 t, 0; @p ld.shared.b64 t, [%0]; @p st.global.cs.b64 [%1], t; }" ::"r"(addr), "l"(dst),
+                 "r"(a), "r"(b)
+                 : "memory");
+  else
+    asm volatile("{ .reg .pred p; .reg .b64 t; setp.lt.u32 p, %2, %3; mov.b64 t, 0; @p ld.shared.b64 t, [%0]; @p st.global.b64 [%1], t; }" ::"r"(addr), "l"(dst),
+                 "r"(a), "r"(b)
+                 : "memory");
+}
 #endif  // __CUDACC__
 
 }  // namespace kmg

@@ -937,6 +937,134 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_kernel
   }
 }
 
+// The rows kernel with its inner loops written against 32-bit shared-space addresses (kmg_device.cuh: atoms_add / sts64_if /
+// copy64_if_lt): same phases and barriers as partition_scatter_rows_kernel.  An octet whose eight windows all count (the normal
+// case inside a record) is ranked without per-window tests, a row store is one predicated STS, overflow keys are handled after
+// the eight stores from a bit mask, the copy-out is three predicated load + store pairs per row.
+template <bool MIXED>
+struct RowsEmit2 {
+  uint32_t cnt_s, rows_s;  // shared-space addresses
+  uint64_t *ov_key;
+  uint32_t *ov_meta, *ov_n;
+  uint32_t n_parts, cap;
+  template <int G>
+  __device__ __forceinline__ void group(const uint64_t (&key)[G], uint32_t okg) {
+    uint32_t p[G], r[G], over = 0;
+    uint64_t v[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) { const uint64_t m = mix64(key[j]); p[j] = coarse_of_mix(m, n_parts); v[j] = MIXED ? m : key[j]; }
+    if (okg == (1u << G) - 1u) {
+#pragma unroll
+      for (int j = 0; j < G; ++j) r[j] = atoms_add(cnt_s + 4u * p[j], 1u);
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const bool fit = r[j] < cap;
+        sts64_if(fit, rows_s + 8u * (p[j] * cap + r[j]), v[j]);
+        over |= (fit ? 0u : 1u) << j;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < G; ++j) { r[j] = 0; if ((okg >> j) & 1u) r[j] = atoms_add(cnt_s + 4u * p[j], 1u); }
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const bool live = (okg >> j) & 1u, fit = r[j] < cap;
+        sts64_if(live && fit, rows_s + 8u * (p[j] * cap + r[j]), v[j]);
+        over |= ((live && !fit) ? 1u : 0u) << j;
+      }
+    }
+    if (over) {  // rare: keys whose row was full
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        if (!((over >> j) & 1u)) continue;
+        const uint32_t o = atomicAdd(ov_n, 1u);
+        if (o < (uint32_t)ROWS_OVERFLOW) { ov_key[o] = v[j]; ov_meta[o] = (p[j] << 16) | r[j]; }  // r < 8192, p < 2048
+      }
+    }
+  }
+};
+template <bool MIXED>
+__global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows2_kernel(ScanInput in, uint32_t n_parts, uint32_t cap, uint32_t magic,
+                                                                                   const unsigned long long *part_start,
+                                                                                   unsigned long long *part_cursor, uint64_t *out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t s_scan[ROWS_THREADS / 32 + 1], s_ovn;
+  uint64_t *rows = reinterpret_cast<uint64_t *>(smem_raw + 2 * sizeof(TileSmem));
+  uint64_t *ov_key = rows + ROWS_SLOTS;
+  uint32_t *ov_meta = reinterpret_cast<uint32_t *>(ov_key + ROWS_OVERFLOW);
+  uint32_t *cnt = ov_meta + ROWS_OVERFLOW, *s_off = cnt + n_parts, *g_base = s_off + n_parts;
+  const uint32_t rows_s = smem_u32(rows), cnt_s = smem_u32(cnt), gb_s = smem_u32(g_base);
+  const uint32_t n_slots = n_parts * cap;  // x / cap == __umulhi(x, magic) for x < 2^16
+  const int tid = threadIdx.x;
+  const bool has_start = in.start != nullptr;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); s_ovn = 0; }
+  for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
+  __syncthreads();
+  uint64_t tile = blockIdx.x;
+  int stage = 0;
+  uint32_t phase0 = 0, phase1 = 0;
+  if (tile < in.n_tiles && tid == 0) issue_tile(in, &stages[0], &bars[0], tile);
+  for (; tile < in.n_tiles; tile += gridDim.x) {
+    const uint64_t next = tile + gridDim.x;
+    if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
+    wait_stage(bars, stage, phase0, phase1);
+    const TileSmem *ts = &stages[stage];
+    for (int sub = 0; sub < TILE_WORDS / ROWS_SUB_WORDS; ++sub) {
+      const int w0 = sub * ROWS_SUB_WORDS;
+      {
+        RowsEmit2<MIXED> e{cnt_s, rows_s, ov_key, ov_meta, &s_ovn, n_parts, cap};
+        scan_octet(ts, w0 + (tid >> 2), tid & 3, in.k, has_start, e);
+      }
+      __syncthreads();
+      const uint32_t n_ov = s_ovn;
+      if (n_ov > (uint32_t)ROWS_OVERFLOW) {  // block-uniform: skewed sub-tile, take the exact route
+        for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
+        __syncthreads();
+        stage_subtile_exact<ROWS_THREADS, MIXED>(ts, w0, ROWS_SUB_WORDS, in, has_start, n_parts, part_start, part_cursor, out, rows, cnt, s_off,
+                                          g_base, s_scan);
+      } else {
+        for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) {
+          const uint32_t h = cnt[p];
+          g_base[p] = part_reserve(in, part_start, part_cursor, p, h);
+          if (g_base[p] == NO_BASE) cnt[p] = 0;  // refused: nothing of this partition is written
+        }
+        __syncthreads();
+        if (cap <= 24u) {  // eight lanes per row, lanes along the row (see partition_scatter_rows_kernel)
+          const uint32_t l = tid & 7u;
+#pragma unroll 2
+          for (uint32_t p = tid >> 3; p < n_parts; p += ROWS_THREADS / 8) {
+            const uint32_t c = min(lds32(cnt_s + 4u * p), cap);
+            uint64_t *dst = out + (uint64_t)lds32(gb_s + 4u * p) + l;
+            const uint32_t row = rows_s + 8u * (p * cap + l);
+            sts32_if(l == 0u, cnt_s + 4u * p, 0u);  // all eight lanes have read it (same instruction): the row is handed back clean
+            copy64_if_lt<true>(l, c, dst, row);
+            copy64_if_lt<true>(l + 8u, c, dst + 8, row + 64u);
+            if (c > 16u) copy64_if_lt<true>(l + 16u, c, dst + 16, row + 128u);
+          }
+        } else {
+#pragma unroll 4
+          for (uint32_t x = tid; x < n_slots; x += ROWS_THREADS) {
+            const uint32_t p = __umulhi(x, magic), e = x - p * cap;
+            if (e < cnt[p]) __stcs(out + (uint64_t)g_base[p] + e, rows[x]);
+          }
+        }
+        for (uint32_t o = tid; o < n_ov; o += ROWS_THREADS) {
+          const uint32_t meta = ov_meta[o];
+          if (g_base[meta >> 16] != NO_BASE) __stcs(out + (uint64_t)g_base[meta >> 16] + (meta & 0xffffu), ov_key[o]);
+        }
+        if (cap > 24u) {
+          __syncthreads();
+          for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
+        }
+      }
+      if (tid == 0) s_ovn = 0;
+      __syncthreads();
+    }
+    stage ^= 1;
+  }
+}
+
 // ROWS variant with the reservation FUSED into the copy-out (rows of up to 24 slots, i.e. more than ~680 partitions).
 // The plain rows kernel spends three block barriers per sub-tile: rank | reserve (one global atomic per partition, its
 // latency exposed between two barriers) | copy-out | end.  Here every lane reserves for ONE row of the eight rows its
@@ -1470,6 +1598,21 @@ bool rows_fused() {  // KMG_FUSED=1: rows kernels with the reservation fused int
   return on;
 }
 
+bool rows_v2() {
+  static const bool on = [] { const char *v = getenv("KMG_ROWS2"); return v && atoi(v) != 0; }();
+  return on;
+}
+
+bool rows_v3() {
+  static const bool on = [] { const char *v = getenv("KMG_ROWS3"); return v && atoi(v) != 0; }();
+  return on;
+}
+
+bool rows_v4() {
+  static const bool on = [] { const char *v = getenv("KMG_ROWS4"); return v && atoi(v) != 0; }();
+  return on;
+}
+
 bool scan_scatter_supports_cap(uint32_t n_parts) {  // the rows / staged kernels honour ScanInput::part_cap
   const size_t stsmem = 2 * sizeof(TileSmem) + (size_t)STAGE_KEYS * 8 + 3 * (size_t)n_parts * sizeof(uint32_t);
   const char *v = getenv("KMG_SCATTER");
@@ -1496,6 +1639,13 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
       g_launches.fetch_add(1, std::memory_order_relaxed);
       if (mixed) partition_scatter_rows_fused_kernel<true><<<grid, ROWS_THREADS, fsmem, s>>>(in, n_parts, cap, part_start, part_cursor, out);
       else partition_scatter_rows_fused_kernel<false><<<grid, ROWS_THREADS, fsmem, s>>>(in, n_parts, cap, part_start, part_cursor, out);
+      return cudaGetLastError();
+    }
+    if (rows_v2()) {
+      if ((e = mixed ? set_smem(partition_scatter_rows2_kernel<true>, rwsmem) : set_smem(partition_scatter_rows2_kernel<false>, rwsmem)) != cudaSuccess) return e;
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      if (mixed) partition_scatter_rows2_kernel<true><<<grid, ROWS_THREADS, rwsmem, s>>>(in, n_parts, cap, magic, part_start, part_cursor, out);
+      else partition_scatter_rows2_kernel<false><<<grid, ROWS_THREADS, rwsmem, s>>>(in, n_parts, cap, magic, part_start, part_cursor, out);
       return cudaGetLastError();
     }
     if ((e = mixed ? set_smem(partition_scatter_rows_kernel<true>, rwsmem) : set_smem(partition_scatter_rows_kernel<false>, rwsmem)) != cudaSuccess) return e;
