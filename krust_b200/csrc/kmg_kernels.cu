@@ -1038,9 +1038,11 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows2_kerne
             uint64_t *dst = out + (uint64_t)lds32(gb_s + 4u * p) + l;
             const uint32_t row = rows_s + 8u * (p * cap + l);
             sts32_if(l == 0u, cnt_s + 4u * p, 0u);  // all eight lanes have read it (same instruction): the row is handed back clean
-            copy64_if_lt<true>(l, c, dst, row);
-            copy64_if_lt<true>(l + 8u, c, dst + 8, row + 64u);
-            if (c > 16u) copy64_if_lt<true>(l + 16u, c, dst + 16, row + 128u);
+            // default cache policy: measured 0.3 ms faster on C4 than streaming (.cs) stores -- the lines are completed by later
+            // sub-tiles; and the third pair only when the row needs it: a predicated-off load / store pair still costs its MIO slots (0.5 ms)
+            copy64_if_lt<false>(l, c, dst, row);
+            copy64_if_lt<false>(l + 8u, c, dst + 8, row + 64u);
+            if (c > 16u) copy64_if_lt<false>(l + 16u, c, dst + 16, row + 128u);
           }
         } else {
 #pragma unroll 4
@@ -1060,96 +1062,6 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows2_kerne
       }
       if (tid == 0) s_ovn = 0;
       __syncthreads();
-    }
-    stage ^= 1;
-  }
-}
-
-// ROWS variant with the reservation FUSED into the copy-out (rows of up to 24 slots, i.e. more than ~680 partitions).
-// The plain rows kernel spends three block barriers per sub-tile: rank | reserve (one global atomic per partition, its
-// latency exposed between two barriers) | copy-out | end.  Here every lane reserves for ONE row of the eight rows its
-// 8-lane group copies (all reservations of a warp in flight together), the group learns size and base of each row through
-// shuffles -- no shared-memory round trip, no barrier between reservation and copy -- and the overflow lists are double
-// buffered by sub-tile parity, so the few overflow keys are written AFTER the second barrier while the next sub-tile is
-// already being ranked.  Two barriers per sub-tile:  rank | B1 | reserve + copy rows | B2 | overflow keys (no barrier).
-//   hazards: rows[] are read before B2 and written after it; cnt[] is cleared by the reserving lane before B2; overflow
-//   list / counter [parity] are written in the rank phase of sub-tile s, read after B2(s) and next written in the rank
-//   phase of s+2, i.e. after B1(s+1), which a thread still reading them has not reached; g_base[] is written between
-//   B1 and B2 and read after B2 (next write after B1 of the following sub-tile).
-template <bool MIXED>
-__global__ void __launch_bounds__(ROWS_THREADS, 1) partition_scatter_rows_fused_kernel(ScanInput in, uint32_t n_parts, uint32_t cap,
-                                                                                        const unsigned long long *part_start,
-                                                                                        unsigned long long *part_cursor, uint64_t *out) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  TileSmem *stages = reinterpret_cast<TileSmem *>(smem_raw);
-  __shared__ __align__(8) uint64_t bars[2];
-  __shared__ uint32_t s_scan[ROWS_THREADS / 32 + 1], s_ovn[2];
-  uint64_t *rows = reinterpret_cast<uint64_t *>(smem_raw + 2 * sizeof(TileSmem));
-  uint64_t *ov_key = rows + ROWS_SLOTS;                                             // 2 x ROWS_OVERFLOW
-  uint32_t *ov_meta = reinterpret_cast<uint32_t *>(ov_key + 2 * ROWS_OVERFLOW);     // 2 x ROWS_OVERFLOW
-  uint32_t *cnt = ov_meta + 2 * ROWS_OVERFLOW, *s_off = cnt + n_parts, *g_base = s_off + n_parts;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const uint32_t l = tid & 7u, grp = tid >> 3, lead = lane & 24u;
-  const bool has_start = in.start != nullptr;
-  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); s_ovn[0] = 0; s_ovn[1] = 0; }
-  for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
-  __syncthreads();
-  uint64_t tile = blockIdx.x;
-  int stage = 0;
-  uint32_t phase0 = 0, phase1 = 0, pp = 0;
-  if (tile < in.n_tiles && tid == 0) issue_tile(in, &stages[0], &bars[0], tile);
-  for (; tile < in.n_tiles; tile += gridDim.x) {
-    const uint64_t next = tile + gridDim.x;
-    if (next < in.n_tiles && tid == 0) issue_tile(in, &stages[stage ^ 1], &bars[stage ^ 1], next);
-    wait_stage(bars, stage, phase0, phase1);
-    const TileSmem *ts = &stages[stage];
-    for (int sub = 0; sub < TILE_WORDS / ROWS_SUB_WORDS; ++sub, pp ^= 1u) {
-      const int w0 = sub * ROWS_SUB_WORDS;
-      uint64_t *ovk = ov_key + pp * ROWS_OVERFLOW;
-      uint32_t *ovm = ov_meta + pp * ROWS_OVERFLOW;
-      {
-        RowsEmit<MIXED> e{cnt, rows, ovk, ovm, &s_ovn[pp], n_parts, cap};
-        scan_octet(ts, w0 + (tid >> 2), tid & 3, in.k, has_start, e);
-      }
-      __syncthreads();  // B1: rows, counters and this parity's overflow list are complete
-      const uint32_t n_ov = s_ovn[pp];
-      if (n_ov > (uint32_t)ROWS_OVERFLOW) {  // block-uniform: skewed sub-tile, take the exact route (ends with a barrier, cnt[] clean)
-        for (uint32_t p = tid; p < n_parts; p += ROWS_THREADS) cnt[p] = 0;
-        __syncthreads();
-        stage_subtile_exact<ROWS_THREADS, MIXED>(ts, w0, ROWS_SUB_WORDS, in, has_start, n_parts, part_start, part_cursor, out, rows, cnt, s_off,
-                                          g_base, s_scan);
-        if (tid == 0) s_ovn[pp] = 0;
-        continue;
-      }
-      for (uint32_t t0 = 0; t0 < n_parts; t0 += ROWS_THREADS) {  // one round per 1024 partitions
-        const uint32_t pm = t0 + grp + (ROWS_THREADS / 8) * l;  // the row this lane reserves for
-        uint32_t cm = 0, bm = 0;
-        if (pm < n_parts) {
-          cm = cnt[pm];
-          cnt[pm] = 0;  // nobody else reads it: the row is handed back clean
-          bm = part_reserve(in, part_start, part_cursor, pm, cm);
-          g_base[pm] = bm;
-          if (bm == NO_BASE) cm = 0;  // refused: nothing of this partition is written
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t c = min(__shfl_sync(0xffffffffu, cm, lead + i), cap);  // 0 for rows past n_parts
-          const uint32_t b = __shfl_sync(0xffffffffu, bm, lead + i);
-          uint64_t *dst = out + (uint64_t)b + l;
-          const uint64_t *row = rows + (t0 + grp + (ROWS_THREADS / 8) * i) * cap + l;
-          if (l < c) __stcs(dst, row[0]);
-          if (l + 8u < c) __stcs(dst + 8, row[8]);
-          if (c > 16u && l + 16u < c) __stcs(dst + 16, row[16]);
-        }
-      }
-      __syncthreads();  // B2: rows are free for the next sub-tile, g_base[] is complete
-      if (n_ov) {
-        for (uint32_t o = tid; o < n_ov; o += ROWS_THREADS) {
-          const uint32_t meta = ovm[o];
-          if (g_base[meta >> 16] != NO_BASE) __stcs(out + (uint64_t)g_base[meta >> 16] + (meta & 0xffffu), ovk[o]);
-        }
-        if (tid == 0) s_ovn[pp] = 0;
-      }
     }
     stage ^= 1;
   }
@@ -1593,23 +1505,8 @@ cudaError_t launch_scan_dense(const ScanInput &in, unsigned long long *dense, un
   return cudaGetLastError();
 }
 
-bool rows_fused() {  // KMG_FUSED=1: rows kernels with the reservation fused into the copy-out
-  static const bool on = [] { const char *v = getenv("KMG_FUSED"); return v && atoi(v) != 0; }();
-  return on;
-}
-
-bool rows_v2() {
-  static const bool on = [] { const char *v = getenv("KMG_ROWS2"); return v && atoi(v) != 0; }();
-  return on;
-}
-
-bool rows_v3() {
-  static const bool on = [] { const char *v = getenv("KMG_ROWS3"); return v && atoi(v) != 0; }();
-  return on;
-}
-
-bool rows_v4() {
-  static const bool on = [] { const char *v = getenv("KMG_ROWS4"); return v && atoi(v) != 0; }();
+bool rows_legacy() {  // KMG_ROWS_LEGACY=1: the round-3 rows kernels (A/B baseline)
+  static const bool on = [] { const char *v = getenv("KMG_ROWS_LEGACY"); return v && atoi(v) != 0; }();
   return on;
 }
 
@@ -1633,15 +1530,7 @@ cudaError_t launch_scan_partition(const ScanInput &in, uint32_t n_parts, bool sc
     const uint32_t cap = std::min<uint32_t>((uint32_t)ROWS_SLOTS / n_parts, ROWS_SUB_WORDS * 32);  // mean fill 8192 / (n_parts * cap) ~ 0.5
     const uint32_t magic = (uint32_t)(((1ull << 32) + cap - 1) / cap);
     const unsigned grid = (unsigned)std::min<uint64_t>(in.n_tiles, (uint64_t)num_sms());
-    if (rows_fused() && cap <= 24u) {  // reservation fused into the copy-out, two barriers per sub-tile
-      const size_t fsmem = rwsmem + (size_t)ROWS_OVERFLOW * 12;  // second overflow list
-      if ((e = mixed ? set_smem(partition_scatter_rows_fused_kernel<true>, fsmem) : set_smem(partition_scatter_rows_fused_kernel<false>, fsmem)) != cudaSuccess) return e;
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-      if (mixed) partition_scatter_rows_fused_kernel<true><<<grid, ROWS_THREADS, fsmem, s>>>(in, n_parts, cap, part_start, part_cursor, out);
-      else partition_scatter_rows_fused_kernel<false><<<grid, ROWS_THREADS, fsmem, s>>>(in, n_parts, cap, part_start, part_cursor, out);
-      return cudaGetLastError();
-    }
-    if (rows_v2()) {
+    if (!rows_legacy()) {
       if ((e = mixed ? set_smem(partition_scatter_rows2_kernel<true>, rwsmem) : set_smem(partition_scatter_rows2_kernel<false>, rwsmem)) != cudaSuccess) return e;
       g_launches.fetch_add(1, std::memory_order_relaxed);
       if (mixed) partition_scatter_rows2_kernel<true><<<grid, ROWS_THREADS, rwsmem, s>>>(in, n_parts, cap, magic, part_start, part_cursor, out);

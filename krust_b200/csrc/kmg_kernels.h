@@ -154,10 +154,7 @@ cudaError_t launch_keys_coarse(const uint64_t *d_keys, const uint64_t *d_counts,
                                unsigned long long *coarse_counts, const unsigned long long *coarse_start,
                                unsigned long long *coarse_cursor, uint64_t *out_keys, uint64_t *out_counts, cudaStream_t s);
 cudaError_t launch_refine(const RefineParams &P, bool scatter, cudaStream_t s);
-bool rows_v2();     // A1 / A2 rows kernels with shared-space addressing and predicated copies (KMG_ROWS2)
-bool rows_v3();     // A2 with two 512-thread CTAs per SM on half tiles (KMG_ROWS3)
-bool rows_v4();     // A2 with rows drained once per two tiles (KMG_ROWS4)
-bool rows_fused();  // A1 / A2 rows kernels with the reservation fused into the copy-out (KMG_FUSED)
+bool rows_legacy();  // KMG_ROWS_LEGACY=1: the round-3 rows kernels of A1 / A2 (A/B baseline)
 bool refine_single_pass_available(uint32_t n_sub, bool weighted);  // the rows kernel applies (it can run without a count pass)
 cudaError_t launch_fill_strided(uint64_t *d, uint64_t n, uint64_t stride, cudaStream_t s);  // d[i] = i * stride
 cudaError_t launch_sum_lens(const CountParams &P, unsigned long long *d_totals, unsigned long long *d_max, cudaStream_t s);

@@ -393,474 +393,23 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
   }
 }
 
-// Rows kernel with the reservation FUSED into the copy-out (rows of up to 24 slots; see partition_scatter_rows_fused_kernel in
-// kmg_kernels.cu for the scheme and its hazard analysis): every lane reserves for one of the eight rows its 8-lane group copies,
-// sizes and bases travel by shuffle, the next tile's loads are issued while the reservations are in flight, and the overflow
-// lists are double buffered by tile parity.  Two block barriers per tile instead of four.
-constexpr int REFINE_FUSED_OVERFLOW = 3072;  // per list (two lists)
-__global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_fused_kernel(RefineParams P) {
-  extern __shared__ __align__(16) uint8_t rsm[];
-  const uint32_t cap = P.row_cap;
-  uint64_t *rows = reinterpret_cast<uint64_t *>(rsm);  // REFINE_ROWS_SLOTS
-  uint64_t *ov_key = rows + REFINE_ROWS_SLOTS;         // 2 x REFINE_FUSED_OVERFLOW
-  uint32_t *ov_meta = reinterpret_cast<uint32_t *>(ov_key + 2 * REFINE_FUSED_OVERFLOW);
-  uint32_t *cnt = ov_meta + 2 * REFINE_FUSED_OVERFLOW, *s_off = cnt + P.n_sub, *g_base = s_off + P.n_sub;
-  __shared__ uint32_t s_c[2], s_ovn[2], s_scan[REFINE_ROWS_THREADS / 32 + 1];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const uint32_t l = tid & 7u, grp = tid >> 3, lead = lane & 24u;
-  constexpr int U = REFINE_TILE / REFINE_ROWS_THREADS;
-  const uint32_t per_cta = (P.n_tiles + gridDim.x - 1) / gridDim.x;
-  const uint32_t g_begin = blockIdx.x * per_cta, g_end = min(g_begin + per_cta, P.n_tiles);
-  if (g_begin >= g_end) return;
-  uint32_t c_hint = 0;  // thread 0: coarse partition of the tile located last
-  auto locate = [&](uint32_t g, int slot) {
-    if (tid == 0) {
-      if (P.tile_prefix[c_hint] > g || c_hint >= P.n_coarse) c_hint = 0;
-      if (P.tile_prefix[c_hint + 1] <= g) {
-        uint32_t lo = c_hint, hi = P.n_coarse;
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.tile_prefix[mid] <= g) lo = mid; else hi = mid; }
-        c_hint = lo;
-      }
-      s_c[slot] = c_hint;
-    }
-  };
-  auto tile_range = [&](uint32_t g, uint32_t c, uint64_t &begin, uint32_t &m) {
-    begin = P.coarse_start[c] + (uint64_t)(g - P.tile_prefix[c]) * REFINE_TILE;
-    const uint64_t end_c = P.coarse_len ? P.coarse_start[c] + P.coarse_len[c] : P.coarse_start[c + 1];
-    m = (uint32_t)(end_c - begin < (uint64_t)REFINE_TILE ? end_c - begin : (uint64_t)REFINE_TILE);
-  };
-  for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
-  if (tid == 0) { s_ovn[0] = 0; s_ovn[1] = 0; }
-  locate(g_begin, 0);
-  __syncthreads();
-  uint32_t c = s_c[0], m;
-  uint64_t begin;
-  tile_range(g_begin, c, begin, m);
-  uint64_t key[U];
-  {
-    const uint64_t *kb = refine_keys_of(P, c) + begin;
-#pragma unroll
-    for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m ? __ldcs(kb + i) : EMPTY_KEY; }
-  }
-  uint32_t pp = 0;
-  for (uint32_t g = g_begin; g < g_end; ++g, pp ^= 1u) {
-    const uint32_t cb = P.in_group > 1 ? c / P.in_group : c;  // coarse bin of input partition c
-    const uint64_t f0 = (uint64_t)cb * P.n_sub;
-    const uint32_t sub_base = (cb % P.sub_old) * P.n_sub;
-    uint64_t *ovk = ov_key + pp * REFINE_FUSED_OVERFLOW;
-    uint32_t *ovm = ov_meta + pp * REFINE_FUSED_OVERFLOW;
-    {  // ---- rank the tile's keys into the rows
-      uint32_t sb[U], r[U];
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        if (P.in_keys) key[j] = mix64(key[j]);
-        sb[j] = sub_of_mix(key[j], P.sub_total) - sub_base;
-        r[j] = 0;
-        if (j * REFINE_ROWS_THREADS + tid < m) r[j] = atomicAdd(cnt + sb[j], 1u);
-      }
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        if (j * REFINE_ROWS_THREADS + tid >= m) continue;
-        if (r[j] < cap) rows[sb[j] * cap + r[j]] = key[j];
-        else {
-          const uint32_t o = atomicAdd(&s_ovn[pp], 1u);
-          if (o < (uint32_t)REFINE_FUSED_OVERFLOW) { ovk[o] = key[j]; ovm[o] = (sb[j] << 16) | r[j]; }  // r < REFINE_TILE <= 65536
-        }
-      }
-    }
-    const int nslot = (g - g_begin + 1) & 1;
-    if (g + 1 < g_end) locate(g + 1, nslot);
-    __syncthreads();  // B1: rows, counters, this parity's overflow list and the next tile's partition are published
-    const uint32_t n_ov = s_ovn[pp];
-    const bool exact = n_ov > (uint32_t)REFINE_FUSED_OVERFLOW;  // block-uniform: skewed tile, take the exact route
-    uint32_t c_next = c, m_next = 0;
-    uint64_t begin_next = 0;
-    const uint64_t *kb = nullptr;
-    uint32_t mn = 0;
-    if (g + 1 < g_end) {
-      c_next = s_c[nslot];
-      tile_range(g + 1, c_next, begin_next, m_next);
-      kb = refine_keys_of(P, c_next) + begin_next + tid;
-      mn = m_next;
-      asm volatile("" : "+l"(kb), "+r"(mn));  // pinned in registers (see refine_rows_kernel)
-    }
-    if (exact) {
-      for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
-      __syncthreads();
-      refine_tile_two_pass<REFINE_ROWS_THREADS, true>(P, refine_keys_of(P, c), begin, m, f0, sub_base, rows, nullptr, cnt, s_off, g_base, s_scan);
-#pragma unroll
-      for (int j = 0; j < U; ++j) key[j] = (uint32_t)(j * REFINE_ROWS_THREADS + tid) < mn ? __ldcs(kb + j * REFINE_ROWS_THREADS) : EMPTY_KEY;
-      if (tid == 0) s_ovn[pp] = 0;
-      __syncthreads();  // the two-pass procedure ends by clearing cnt[] without a barrier
-    } else {
-      for (uint32_t t0 = 0; t0 < P.n_sub; t0 += REFINE_ROWS_THREADS) {  // one round per 1024 sub-bins
-        const uint32_t sm = t0 + grp + (REFINE_ROWS_THREADS / 8) * l;  // the row this lane reserves for
-        uint32_t hm = 0, bm = 0;
-        if (sm < P.n_sub) {
-          hm = cnt[sm];
-          cnt[sm] = 0;  // nobody else reads it: the row is handed back clean
-          bm = refine_reserve(P, f0 + sm, hm);
-          g_base[sm] = bm;
-          if (bm == NO_BASE) hm = 0;  // refused: nothing of this sub-bin is written
-        }
-        if (t0 == 0) {  // the next tile's keys are requested while the reservations are in flight; their latency hides behind the copy-out
-#pragma unroll
-          for (int j = 0; j < U; ++j) key[j] = (uint32_t)(j * REFINE_ROWS_THREADS + tid) < mn ? __ldcs(kb + j * REFINE_ROWS_THREADS) : EMPTY_KEY;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t h = min(__shfl_sync(0xffffffffu, hm, lead + i), cap);  // 0 for rows past n_sub
-          const uint32_t b = __shfl_sync(0xffffffffu, bm, lead + i);
-          uint64_t *dst = P.out_keys + (uint64_t)b + l;
-          const uint64_t *row = rows + (t0 + grp + (REFINE_ROWS_THREADS / 8) * i) * cap + l;
-          if (l < h) dst[0] = row[0];
-          if (l + 8u < h) dst[8] = row[8];
-          if (h > 16u && l + 16u < h) dst[16] = row[16];
-        }
-      }
-      __syncthreads();  // B2: rows are free for the next tile, g_base[] is complete
-      if (n_ov) {
-        for (uint32_t o = tid; o < n_ov; o += REFINE_ROWS_THREADS) {
-          const uint32_t meta = ovm[o];
-          if (g_base[meta >> 16] != NO_BASE) P.out_keys[(uint64_t)g_base[meta >> 16] + (meta & 0xffffu)] = ovk[o];
-        }
-        if (tid == 0) s_ovn[pp] = 0;
-      }
-    }
-    c = c_next; m = m_next; begin = begin_next;
-  }
-}
-
-// The rows kernel again, same phases and barriers, with the inner loops written against 32-bit shared-space addresses
-// (kmg_device.cuh: atoms_add / sts64_if / copy64_if_lt): a FULL tile is ranked without a per-key bounds test, the row store is
-// one predicated STS, the rare overflow keys are handled after the eight stores from a bit mask (one branch per thread and
-// tile instead of one divergent region per key), the copy-out is three predicated load + store pairs per row.  IN_KEYS
-// (plain keys in, adopted blocks) is a template parameter instead of a per-key uniform branch.
-template <bool IN_KEYS>
-__global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows2_kernel(RefineParams P) {
-  extern __shared__ __align__(16) uint8_t rsm[];
-  const uint32_t cap = P.row_cap, n_slots = P.n_sub * cap, magic = P.row_magic;
-  uint64_t *rows = reinterpret_cast<uint64_t *>(rsm);  // REFINE_ROWS_SLOTS
-  uint64_t *ov_key = rows + REFINE_ROWS_SLOTS;         // REFINE_ROWS_OVERFLOW
-  uint32_t *ov_meta = reinterpret_cast<uint32_t *>(ov_key + REFINE_ROWS_OVERFLOW);
-  uint32_t *cnt = ov_meta + REFINE_ROWS_OVERFLOW, *s_off = cnt + P.n_sub, *g_base = s_off + P.n_sub;
-  const uint32_t rows_s = smem_u32(rows), cnt_s = smem_u32(cnt), gb_s = smem_u32(g_base);
-  __shared__ uint32_t s_c[2], s_ovn, s_scan[REFINE_ROWS_THREADS / 32 + 1];
-  const int tid = threadIdx.x;
-  constexpr int U = REFINE_TILE / REFINE_ROWS_THREADS;
-  const uint32_t per_cta = (P.n_tiles + gridDim.x - 1) / gridDim.x;
-  const uint32_t g_begin = blockIdx.x * per_cta, g_end = min(g_begin + per_cta, P.n_tiles);
-  if (g_begin >= g_end) return;
-  uint32_t c_hint = 0;
-  auto locate = [&](uint32_t g, int slot) {
-    if (tid == 0) {
-      if (P.tile_prefix[c_hint] > g || c_hint >= P.n_coarse) c_hint = 0;
-      if (P.tile_prefix[c_hint + 1] <= g) {
-        uint32_t lo = c_hint, hi = P.n_coarse;
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.tile_prefix[mid] <= g) lo = mid; else hi = mid; }
-        c_hint = lo;
-      }
-      s_c[slot] = c_hint;
-    }
-  };
-  auto tile_range = [&](uint32_t g, uint32_t c, uint64_t &begin, uint32_t &m) {
-    begin = P.coarse_start[c] + (uint64_t)(g - P.tile_prefix[c]) * REFINE_TILE;
-    const uint64_t end_c = P.coarse_len ? P.coarse_start[c] + P.coarse_len[c] : P.coarse_start[c + 1];
-    m = (uint32_t)(end_c - begin < (uint64_t)REFINE_TILE ? end_c - begin : (uint64_t)REFINE_TILE);
-  };
-  for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
-  if (tid == 0) s_ovn = 0;
-  locate(g_begin, 0);
-  __syncthreads();
-  uint32_t c = s_c[0], m;
-  uint64_t begin;
-  tile_range(g_begin, c, begin, m);
-  uint64_t key[U];
-  {
-    const uint64_t *kb = refine_keys_of(P, c) + begin;
-#pragma unroll
-    for (int j = 0; j < U; ++j) { const uint32_t i = j * REFINE_ROWS_THREADS + tid; key[j] = i < m ? __ldcs(kb + i) : EMPTY_KEY; }
-  }
-
-  for (uint32_t g = g_begin; g < g_end; ++g) {
-    const uint32_t cb = P.in_group > 1 ? c / P.in_group : c;  // coarse bin of input partition c
-    const uint64_t f0 = (uint64_t)cb * P.n_sub;
-    const uint32_t sub_base = (cb % P.sub_old) * P.n_sub;
-    {  // ---- rank the tile's keys into the rows
-      uint32_t sb[U], r[U], over = 0;
-      if (m == (uint32_t)REFINE_TILE) {  // block-uniform: a full tile needs no bounds tests
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          if (IN_KEYS) key[j] = mix64(key[j]);
-          sb[j] = sub_of_mix(key[j], P.sub_total) - sub_base;
-          r[j] = atoms_add(cnt_s + 4u * sb[j], 1u);
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const bool fit = r[j] < cap;
-          sts64_if(fit, rows_s + 8u * (sb[j] * cap + r[j]), key[j]);
-          over |= (fit ? 0u : 1u) << j;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const bool live = (uint32_t)(j * REFINE_ROWS_THREADS + tid) < m;
-          if (IN_KEYS) key[j] = mix64(key[j]);
-          sb[j] = live ? sub_of_mix(key[j], P.sub_total) - sub_base : 0u;
-          r[j] = live ? atoms_add(cnt_s + 4u * sb[j], 1u) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const bool live = (uint32_t)(j * REFINE_ROWS_THREADS + tid) < m, fit = r[j] < cap;
-          sts64_if(live && fit, rows_s + 8u * (sb[j] * cap + r[j]), key[j]);
-          over |= ((live && !fit) ? 1u : 0u) << j;
-        }
-      }
-      if (over) {  // rare: this thread holds keys whose row was full
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          if (!((over >> j) & 1u)) continue;
-          const uint32_t o = atomicAdd(&s_ovn, 1u);
-          if (o < REFINE_ROWS_OVERFLOW) { ov_key[o] = key[j]; ov_meta[o] = (sb[j] << 16) | r[j]; }  // r < REFINE_TILE <= 65536
-        }
-      }
-    }
-    const int nslot = (g - g_begin + 1) & 1;
-    if (g + 1 < g_end) locate(g + 1, nslot);
-    __syncthreads();
-    const uint32_t n_ov = s_ovn;
-    const bool exact = n_ov > REFINE_ROWS_OVERFLOW;  // block-uniform: skewed tile, take the exact route
-    if (exact) {
-      for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
-      __syncthreads();
-      refine_tile_two_pass<REFINE_ROWS_THREADS, true>(P, refine_keys_of(P, c), begin, m, f0, sub_base, rows, nullptr, cnt, s_off, g_base, s_scan);
-    } else {
-      for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) {
-        const uint32_t h = cnt[s];
-        g_base[s] = refine_reserve(P, f0 + s, h);
-        if (g_base[s] == NO_BASE) cnt[s] = 0;  // refused: nothing of this sub-bin is written
-      }
-    }
-    // ---- the next tile's keys are requested now, so their latency hides behind this tile's copy-out
-    uint32_t c_next = c, m_next = 0;
-    uint64_t begin_next = 0;
-    if (g + 1 < g_end) {
-      c_next = s_c[nslot];
-      tile_range(g + 1, c_next, begin_next, m_next);
-      const uint64_t *kb = refine_keys_of(P, c_next) + begin_next + tid;
-      uint32_t mn = m_next;
-      asm volatile("" : "+l"(kb), "+r"(mn));
-#pragma unroll
-      for (int j = 0; j < U; ++j) key[j] = (uint32_t)(j * REFINE_ROWS_THREADS + tid) < mn ? __ldcs(kb + j * REFINE_ROWS_THREADS) : EMPTY_KEY;
-    }
-    __syncthreads();
-    if (!exact) {
-      if (cap <= 24u) {  // eight lanes per row, lanes along the row
-        const uint32_t l = tid & 7u;
-#pragma unroll 2
-        for (uint32_t s2 = tid >> 3; s2 < P.n_sub; s2 += REFINE_ROWS_THREADS / 8) {
-          const uint32_t h = min(lds32(cnt_s + 4u * s2), cap);
-          uint64_t *dst = P.out_keys + (uint64_t)lds32(gb_s + 4u * s2) + l;
-          const uint32_t row = rows_s + 8u * (s2 * cap + l);
-          sts32_if(l == 0u, cnt_s + 4u * s2, 0u);  // read by all eight lanes in the same instruction: the row is handed back clean
-          copy64_if_lt<false>(l, h, dst, row);
-          copy64_if_lt<false>(l + 8u, h, dst + 8, row + 64u);
-          if (h > 16u) copy64_if_lt<false>(l + 16u, h, dst + 16, row + 128u);
-        }
-      } else {
-#pragma unroll 4
-        for (uint32_t x = tid; x < n_slots; x += REFINE_ROWS_THREADS) {  // lanes walk along the rows: contiguous destinations
-          const uint32_t s2 = __umulhi(x, magic), e = x - s2 * cap;
-          if (e < cnt[s2]) P.out_keys[(uint64_t)g_base[s2] + e] = rows[x];
-        }
-      }
-      for (uint32_t o = tid; o < n_ov; o += REFINE_ROWS_THREADS) {
-        const uint32_t meta = ov_meta[o];
-        if (g_base[meta >> 16] != NO_BASE) P.out_keys[(uint64_t)g_base[meta >> 16] + (meta & 0xffffu)] = ov_key[o];
-      }
-      if (cap > 24u) {
-        __syncthreads();
-        for (uint32_t s = tid; s < P.n_sub; s += REFINE_ROWS_THREADS) cnt[s] = 0;
-      }
-    }
-    if (tid == 0) s_ovn = 0;
-    __syncthreads();
-    c = c_next; m = m_next; begin = begin_next;
-  }
-}
-
-// TWO CTAs per SM (512 threads, 64 KiB of rows each) working on HALF tiles of 4096 keys: the phases of the rows scheme are
-// separated by block barriers and each leans on a different unit (rank: shared atomics + scattered shared stores; reserve: one
-// global atomic per row, pure latency; copy-out: shared loads + global stores), so one CTA per SM leaves every unit idle most of
-// the time (ncu: issue active 35 %, stalls barrier 6.2 / mio_throttle 4.3 / long_scoreboard 3.3 cycles per instruction).  Two
-// CTAs drift out of phase and fill each other's waits.  The price: rows hold 4.4 keys on average instead of 8.8.
-constexpr int R3_THREADS = 512, R3_HALF = 4096, R3_SLOTS = 8192, R3_OVERFLOW = 2048;
-template <bool IN_KEYS>
-__global__ void __launch_bounds__(R3_THREADS, 2) refine_rows3_kernel(RefineParams P) {
-  extern __shared__ __align__(16) uint8_t rsm[];
-  const uint32_t cap = P.row_cap, n_slots = P.n_sub * cap, magic = P.row_magic;
-  uint64_t *rows = reinterpret_cast<uint64_t *>(rsm);  // R3_SLOTS
-  uint64_t *ov_key = rows + R3_SLOTS;                   // R3_OVERFLOW
-  uint32_t *ov_meta = reinterpret_cast<uint32_t *>(ov_key + R3_OVERFLOW);
-  uint32_t *cnt = ov_meta + R3_OVERFLOW, *s_off = cnt + P.n_sub, *g_base = s_off + P.n_sub;
-  const uint32_t rows_s = smem_u32(rows), cnt_s = smem_u32(cnt), gb_s = smem_u32(g_base);
-  __shared__ uint32_t s_c[2], s_ovn, s_scan[R3_THREADS / 32 + 1];
-  const int tid = threadIdx.x;
-  constexpr int U = R3_HALF / R3_THREADS;
-  static_assert(2 * R3_HALF == REFINE_TILE, "a host-side tile is two half tiles");
-  // work unit u = 2 * tile + half; a CTA owns a contiguous range of units
-  const uint32_t n_units = 2u * P.n_tiles;
-  const uint32_t per_cta = (n_units + gridDim.x - 1) / gridDim.x;
-  const uint32_t u_begin = blockIdx.x * per_cta, u_end = min(u_begin + per_cta, n_units);
-  if (u_begin >= u_end) return;
-  uint32_t c_hint = 0;
-  auto locate = [&](uint32_t u, int slot) {  // thread 0 publishes the coarse partition of unit u's tile
-    if (tid == 0) {
-      const uint32_t g = u >> 1;
-      if (P.tile_prefix[c_hint] > g || c_hint >= P.n_coarse) c_hint = 0;
-      if (P.tile_prefix[c_hint + 1] <= g) {
-        uint32_t lo = c_hint, hi = P.n_coarse;
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.tile_prefix[mid] <= g) lo = mid; else hi = mid; }
-        c_hint = lo;
-      }
-      s_c[slot] = c_hint;
-    }
-  };
-  auto unit_range = [&](uint32_t u, uint32_t c, uint64_t &begin, uint32_t &m) {
-    begin = P.coarse_start[c] + (uint64_t)((u >> 1) - P.tile_prefix[c]) * REFINE_TILE + (uint64_t)(u & 1u) * R3_HALF;
-    const uint64_t end_c = P.coarse_len ? P.coarse_start[c] + P.coarse_len[c] : P.coarse_start[c + 1];
-    m = begin >= end_c ? 0u : (uint32_t)(end_c - begin < (uint64_t)R3_HALF ? end_c - begin : (uint64_t)R3_HALF);
-  };
-  for (uint32_t s = tid; s < P.n_sub; s += R3_THREADS) cnt[s] = 0;
-  if (tid == 0) s_ovn = 0;
-  locate(u_begin, 0);
-  __syncthreads();
-  uint32_t c = s_c[0], m;
-  uint64_t begin;
-  unit_range(u_begin, c, begin, m);
-  uint64_t key[U];
-  {
-    const uint64_t *kb = refine_keys_of(P, c) + begin;
-#pragma unroll
-    for (int j = 0; j < U; ++j) { const uint32_t i = j * R3_THREADS + tid; key[j] = i < m ? __ldcs(kb + i) : EMPTY_KEY; }
-  }
-
-  for (uint32_t u = u_begin; u < u_end; ++u) {
-    const uint32_t cb = P.in_group > 1 ? c / P.in_group : c;  // coarse bin of input partition c
-    const uint64_t f0 = (uint64_t)cb * P.n_sub;
-    const uint32_t sub_base = (cb % P.sub_old) * P.n_sub;
-    {  // ---- rank the unit's keys into the rows
-      uint32_t sb[U], r[U], over = 0;
-      if (m == (uint32_t)R3_HALF) {  // block-uniform: a full unit needs no bounds tests
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          if (IN_KEYS) key[j] = mix64(key[j]);
-          sb[j] = sub_of_mix(key[j], P.sub_total) - sub_base;
-          r[j] = atoms_add(cnt_s + 4u * sb[j], 1u);
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const bool fit = r[j] < cap;
-          sts64_if(fit, rows_s + 8u * (sb[j] * cap + r[j]), key[j]);
-          over |= (fit ? 0u : 1u) << j;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const bool live = (uint32_t)(j * R3_THREADS + tid) < m;
-          if (IN_KEYS) key[j] = mix64(key[j]);
-          sb[j] = live ? sub_of_mix(key[j], P.sub_total) - sub_base : 0u;
-          r[j] = live ? atoms_add(cnt_s + 4u * sb[j], 1u) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const bool live = (uint32_t)(j * R3_THREADS + tid) < m, fit = r[j] < cap;
-          sts64_if(live && fit, rows_s + 8u * (sb[j] * cap + r[j]), key[j]);
-          over |= ((live && !fit) ? 1u : 0u) << j;
-        }
-      }
-      if (over) {  // this thread holds keys whose row was full
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          if (!((over >> j) & 1u)) continue;
-          const uint32_t o = atomicAdd(&s_ovn, 1u);
-          if (o < (uint32_t)R3_OVERFLOW) { ov_key[o] = key[j]; ov_meta[o] = (sb[j] << 16) | r[j]; }  // r < R3_HALF
-        }
-      }
-    }
-    const int nslot = (u - u_begin + 1) & 1;
-    if (u + 1 < u_end) locate(u + 1, nslot);
-    __syncthreads();
-    const uint32_t n_ov = s_ovn;
-    const bool exact = n_ov > (uint32_t)R3_OVERFLOW;  // block-uniform: skewed unit, take the exact route
-    if (exact) {
-      for (uint32_t s = tid; s < P.n_sub; s += R3_THREADS) cnt[s] = 0;
-      __syncthreads();
-      refine_tile_two_pass<R3_THREADS, true>(P, refine_keys_of(P, c), begin, m, f0, sub_base, rows, nullptr, cnt, s_off, g_base, s_scan);
-    } else {
-      for (uint32_t s = tid; s < P.n_sub; s += R3_THREADS) {
-        const uint32_t h = cnt[s];
-        g_base[s] = refine_reserve(P, f0 + s, h);
-        if (g_base[s] == NO_BASE) cnt[s] = 0;  // refused: nothing of this sub-bin is written
-      }
-    }
-    // ---- the next unit's keys are requested now, so their latency hides behind this unit's copy-out
-    uint32_t c_next = c, m_next = 0;
-    uint64_t begin_next = 0;
-    if (u + 1 < u_end) {
-      c_next = s_c[nslot];
-      unit_range(u + 1, c_next, begin_next, m_next);
-      const uint64_t *kb = refine_keys_of(P, c_next) + begin_next + tid;
-      uint32_t mn = m_next;
-      asm volatile("" : "+l"(kb), "+r"(mn));
-#pragma unroll
-      for (int j = 0; j < U; ++j) key[j] = (uint32_t)(j * R3_THREADS + tid) < mn ? __ldcs(kb + j * R3_THREADS) : EMPTY_KEY;
-    }
-    __syncthreads();
-    if (!exact) {
-      if (cap <= 24u) {  // eight lanes per row, lanes along the row
-        const uint32_t l = tid & 7u;
-#pragma unroll 2
-        for (uint32_t s2 = tid >> 3; s2 < P.n_sub; s2 += R3_THREADS / 8) {
-          const uint32_t h = min(lds32(cnt_s + 4u * s2), cap);
-          uint64_t *dst = P.out_keys + (uint64_t)lds32(gb_s + 4u * s2) + l;
-          const uint32_t row = rows_s + 8u * (s2 * cap + l);
-          sts32_if(l == 0u, cnt_s + 4u * s2, 0u);  // read by all eight lanes in the same instruction: the row is handed back clean
-          copy64_if_lt<false>(l, h, dst, row);
-          if (cap > 8u) {
-            copy64_if_lt<false>(l + 8u, h, dst + 8, row + 64u);
-            if (h > 16u) copy64_if_lt<false>(l + 16u, h, dst + 16, row + 128u);
-          }
-        }
-      } else {
-#pragma unroll 4
-        for (uint32_t x = tid; x < n_slots; x += R3_THREADS) {  // lanes walk along the rows: contiguous destinations
-          const uint32_t s2 = __umulhi(x, magic), e = x - s2 * cap;
-          if (e < cnt[s2]) P.out_keys[(uint64_t)g_base[s2] + e] = rows[x];
-        }
-      }
-      for (uint32_t o = tid; o < n_ov; o += R3_THREADS) {
-        const uint32_t meta = ov_meta[o];
-        if (g_base[meta >> 16] != NO_BASE) P.out_keys[(uint64_t)g_base[meta >> 16] + (meta & 0xffffu)] = ov_key[o];
-      }
-      if (cap > 24u) {
-        __syncthreads();
-        for (uint32_t s = tid; s < P.n_sub; s += R3_THREADS) cnt[s] = 0;
-      }
-    }
-    if (tid == 0) s_ovn = 0;
-    __syncthreads();
-    c = c_next; m = m_next; begin = begin_next;
-  }
-}
-
-// BIG ROWS: the rows scheme with the rows drained once per TWO tiles (16384 keys).  Measured on C4 (profiles/r3_summary.md): the
-// cost of the rows kernels is mostly per (row, drain) -- one global reservation, one row header, two half-filled sectors at the
-// ends of every run that is written -- and only ~40 % per key: halving the keys per drain (two 512-thread CTAs on half tiles) took
-// A2 from 20.0 to 31.6 ms.  So the rows take all the shared memory there is (176 KiB: 24 slots for 928 sub-bins, mean fill 0.74,
-// ~0.9 % of the keys overflow to the list) and a drain moves runs of ~18 keys instead of ~9.  Keys arrive in register batches of
-// four per thread; the first tile of a group is requested before the previous group's copy-out, the second one batch ahead.
-constexpr int R4_SLOTS = 22528, R4_OVERFLOW = 1024, R4_BATCH = 4096;
+// The rows scheme as it runs by default (refine_rows_kernel above stays for fewer than 128 sub-bins and as the KMG_ROWS_LEGACY=1
+// baseline).  What the measurements on C4 said (profiles/r4_summary.md), in the order they were made:
+//   * cutting the instructions per key by a third (32-bit shared-space addresses, predicated stores and copies instead of
+//     BSSY / BRA / BSYNC regions that re-derive the shared window per key) changed nothing: 20.0 -> 19.9 ms.  Not issue bound.
+//   * TILE ORDER is what mattered: with a contiguous tile range per CTA the grid appends to 148 x 928 output regions at once and
+//     DRAM sees line-sized writes all over 4 GB; with the tiles INTERLEAVED over the grid (in chunks of C tile pairs) it works in
+//     a handful of coarse bins at a time: 19.9 -> 16.0 ms at C = 1, 14.6 ms at C = 16 (C = 1 makes all CTAs reserve in the same
+//     sub-bins at the same instant, C = 64 spreads the writes too far again: 15.7 ms).
+//   * the cost per (row, drain) -- one global reservation, a row header, two half-filled sectors at the ends of every run -- is
+//     real: two 512-thread CTAs on half tiles (runs of 4.4 keys) 19.8 ms, one CTA draining once per tile (8.8) 16.7 ms, once per
+//     TWO tiles (17.7) 16.2 ms (all interleaved, C = 1).  So the rows take all the shared memory there is (27 slots for 928
+//     sub-bins, mean fill 0.65, ~0.2 % of the keys overflow to the list) and are drained once per two tiles.
+//   * the next group's two tiles are prefetched into L2 a group ahead (one line per thread): the register batches (four keys per
+//     thread; the first tile of a group requested before the previous group's copy-out, the second one batch ahead) then wait
+//     for L2 instead of DRAM: 16.2 -> 16.0 ms.
+constexpr int R4_OVERFLOW = 1024, R4_BATCH = 4096;
+constexpr size_t R4_SMEM = 226 * 1024;  // rows + overflow list + three arrays of n_sub words
 // the exact route of a skewed tile, out of line: it is rare, and inlined it costs the hot loop its registers
 __device__ __noinline__ void refine_tile_exact_1024(const RefineParams P, const uint64_t *kbase, uint64_t begin, uint32_t m, uint64_t f0, uint32_t sub_base,
                                                     uint64_t *staging, uint32_t *hist, uint32_t *s_off, uint32_t *g_base, uint32_t *s_scan) {
@@ -872,11 +421,11 @@ __host__ __device__ inline double rows_overflow_fraction(double mean, uint32_t c
   return (mean - (double)cap + s) / mean;
 }
 template <bool IN_KEYS>
-__global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows4_kernel(RefineParams P, uint32_t tiles_per_group) {
+__global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows4_kernel(RefineParams P, uint32_t tiles_per_group, uint32_t n_slots) {
   extern __shared__ __align__(16) uint8_t rsm[];
   const uint32_t cap = P.row_cap;
-  uint64_t *rows = reinterpret_cast<uint64_t *>(rsm);  // R4_SLOTS
-  uint64_t *ov_key = rows + R4_SLOTS;                   // R4_OVERFLOW
+  uint64_t *rows = reinterpret_cast<uint64_t *>(rsm);  // n_slots >= n_sub * cap
+  uint64_t *ov_key = rows + n_slots;                    // R4_OVERFLOW
   uint32_t *ov_meta = reinterpret_cast<uint32_t *>(ov_key + R4_OVERFLOW);
   uint32_t *cnt = ov_meta + R4_OVERFLOW, *s_off = cnt + P.n_sub, *g_base = s_off + P.n_sub;
   const uint32_t rows_s = smem_u32(rows), cnt_s = smem_u32(cnt), gb_s = smem_u32(g_base);
@@ -884,8 +433,16 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows4_kernel(Re
   const int tid = threadIdx.x;
   constexpr int T = REFINE_ROWS_THREADS, U = R4_BATCH / T;  // 4 keys per thread and batch
   static_assert(2 * R4_BATCH == REFINE_TILE, "a host-side tile is two batches");
+  // tile order: P.pad = C > 0 -> INTERLEAVED in chunks of C tile pairs (pair q holds tiles 2q, 2q + 1; CTA b takes pairs
+  // [b*C, b*C + C) of every block of gridDim * C pairs): the whole grid works in a handful of coarse bins and appends to the same
+  // few thousand output regions at a time, which is what DRAM wants (C4, A2: 20.0 ms with contiguous ranges, 16.7 ms interleaved);
+  // C > 1 keeps the CTAs from reserving in the same sub-bins at the same instant.  P.pad = 0: a contiguous range of tiles per CTA.
+  const uint32_t C = P.pad;
+  const bool il = C != 0;
+  uint32_t pi = 0;  // interleaved: this CTA's pair counter
+  auto pair_of = [&](uint32_t i) { return (i / C) * (gridDim.x * C) + blockIdx.x * C + (i % C); };
   const uint32_t per_cta = (P.n_tiles + gridDim.x - 1) / gridDim.x;
-  const uint32_t g_begin = blockIdx.x * per_cta, g_end = min(g_begin + per_cta, P.n_tiles);
+  const uint32_t g_begin = il ? 2u * pair_of(0) : blockIdx.x * per_cta, g_end = il ? P.n_tiles : min(g_begin + per_cta, P.n_tiles);
   if (g_begin >= g_end) return;
   uint32_t c_hint = 0;
   auto locate = [&](uint32_t g, int slot) {  // thread 0 publishes the partition of tile g
@@ -969,11 +526,17 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows4_kernel(Re
     const uint64_t f0 = (uint64_t)cb * P.n_sub;
     sub_base = (cb % P.sub_old) * P.n_sub;
     // the group: this tile and, when it lies in the same partition (and in this CTA's range), the next one
-    const bool two = tiles_per_group > 1u && g + 1 < g_end && P.tile_prefix[c + 1] > g + 1;
+    const bool two = tiles_per_group > 1u && g + 1 < g_end && P.tile_prefix[c + 1] > g + 1 && !(il && (g & 1u));
     uint64_t begin2 = 0;
     uint32_t m2 = 0;
     const uint64_t *kbase = refine_keys_of(P, c);
     if (two) tile_range(g + 1, c, begin2, m2);
+    if (!P.n_src) {  // L2 prefetch of this CTA's NEXT group (one 128-byte line per thread = two tiles), assuming it lies in the same
+                     // partition (it does for all but one group in ~200): its loads then wait for L2, not for DRAM
+      const uint64_t end_c = P.coarse_len ? P.coarse_start[c] + P.coarse_len[c] : P.coarse_start[c + 1];
+      const uint64_t pf = begin + (uint64_t)(il ? 2u * pair_of(pi + 1) - g : 2u) * REFINE_TILE + (uint64_t)tid * 16u;
+      if (pf < end_c) asm volatile("prefetch.global.L2 [%0];" ::"l"(kbase + pf));
+    }
     {  // one code instance per register batch (merged call sites would force the batches into local memory)
       uint32_t mt = m;
       for (uint32_t t = 0, nt = two ? 2u : 1u; t < nt; ++t) {
@@ -984,7 +547,9 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows4_kernel(Re
         mt = m2;
       }
     }
-    const uint32_t g_next = g + (two ? 2u : 1u);
+    // interleaved: a pair that straddles two partitions is two groups of one tile; then on to this CTA's next pair
+    uint32_t g_next = g + (two ? 2u : 1u);
+    if (il && ((g & 1u) || two || g + 1 >= g_end)) g_next = 2u * pair_of(++pi);
     slot ^= 1;
     if (g_next < g_end) locate(g_next, slot);
     __syncthreads();
@@ -1027,7 +592,7 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows4_kernel(Re
         copy64_if_lt<false>(l, h, dst, row);
         copy64_if_lt<false>(l + 8u, h, dst + 8, row + 64u);
         copy64_if_lt<false>(l + 16u, h, dst + 16, row + 128u);
-        for (uint32_t e = 24u; e < h; e += 8u) copy64_if_lt<false>(l + e, h, dst + e, row + 8u * e);  // rows of more than 24 slots (few sub-bins)
+        for (uint32_t e = 24u; e < h; e += 8u) copy64_if_lt<false>(l + e, h, dst + e, row + 8u * e);  // rows of more than 24 slots
       }
       for (uint32_t o = tid; o < n_ov; o += T) {
         const uint32_t meta = ov_meta[o];
@@ -1065,39 +630,22 @@ cudaError_t launch_refine(const RefineParams &P_in, bool scatter, cudaStream_t s
   if (scatter && refine_single_pass_available(P.n_sub, P.counts || P.out_counts)) {
     P.row_cap = std::min<uint32_t>((uint32_t)REFINE_ROWS_SLOTS / P.n_sub, REFINE_TILE);  // mean fill 8192 / (n_sub * cap) ~ 0.5
     P.row_magic = (uint32_t)(((1ull << 32) + P.row_cap - 1) / P.row_cap);
-    if (rows_fused() && P.row_cap <= 24u) {  // reservation fused into the copy-out, two barriers per tile
-      const size_t fsmem = (size_t)REFINE_ROWS_SLOTS * 8 + 2 * (size_t)REFINE_FUSED_OVERFLOW * 12 + 3 * (size_t)P.n_sub * sizeof(uint32_t);
-      if ((e = cudaFuncSetAttribute(refine_rows_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)) != cudaSuccess) return e;
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-      refine_rows_fused_kernel<<<(unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms()), REFINE_ROWS_THREADS, fsmem, s>>>(P);
-      return cudaGetLastError();
-    }
     const size_t smem = (size_t)REFINE_ROWS_SLOTS * 8 + (size_t)REFINE_ROWS_OVERFLOW * 12 + 3 * (size_t)P.n_sub * sizeof(uint32_t);
-    if (rows_v4() && P.n_sub >= 128u) {  // big rows, drained once per two tiles
-      P.row_cap = (uint32_t)R4_SLOTS / P.n_sub;
+    if (!rows_legacy() && P.n_sub >= 128u) {  // big rows, drained once per two tiles, tiles interleaved over the grid
+      const uint32_t n_slots = (uint32_t)((R4_SMEM - (size_t)R4_OVERFLOW * 12 - 3 * (size_t)P.n_sub * sizeof(uint32_t)) / 8) & ~1u;
+      P.row_cap = n_slots / P.n_sub;
       const uint32_t tg = rows_overflow_fraction(2.0 * REFINE_TILE / P.n_sub, P.row_cap) <= 0.035 ? 2u : 1u;
-      const size_t smem4 = (size_t)R4_SLOTS * 8 + (size_t)R4_OVERFLOW * 12 + 3 * (size_t)P.n_sub * sizeof(uint32_t);
+      const size_t smem4 = (size_t)n_slots * 8 + (size_t)R4_OVERFLOW * 12 + 3 * (size_t)P.n_sub * sizeof(uint32_t);
+      const unsigned grid = (unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms());
+      // chunk of the interleaved tile order: 16 pairs, less when the input is so small that some CTAs would get nothing
+      static const int chunk_env = [] { const char *v = getenv("KMG_A2_INTERLEAVE"); return v ? atoi(v) : -1; }();  // tuning: 0 = contiguous ranges
+      uint32_t chunk = 16;
+      while (chunk > 1 && (uint64_t)grid * chunk * 8 > P.n_tiles) chunk >>= 1;
+      P.pad = chunk_env >= 0 ? (uint32_t)chunk_env : chunk;
       auto kern = P.in_keys ? refine_rows4_kernel<true> : refine_rows4_kernel<false>;
       if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)) != cudaSuccess) return e;
       g_launches.fetch_add(1, std::memory_order_relaxed);
-      kern<<<(unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms()), REFINE_ROWS_THREADS, smem4, s>>>(P, tg);
-      return cudaGetLastError();
-    }
-    if (rows_v3() && P.n_sub <= (uint32_t)R3_SLOTS / 8) {  // two CTAs per SM on half tiles
-      P.row_cap = std::min<uint32_t>((uint32_t)R3_SLOTS / P.n_sub, R3_HALF);
-      P.row_magic = (uint32_t)(((1ull << 32) + P.row_cap - 1) / P.row_cap);
-      const size_t smem3 = (size_t)R3_SLOTS * 8 + (size_t)R3_OVERFLOW * 12 + 3 * (size_t)P.n_sub * sizeof(uint32_t);
-      auto kern = P.in_keys ? refine_rows3_kernel<true> : refine_rows3_kernel<false>;
-      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)) != cudaSuccess) return e;
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-      kern<<<(unsigned)std::min<uint64_t>(2 * (uint64_t)P.n_tiles, 2 * (uint64_t)num_sms()), R3_THREADS, smem3, s>>>(P);
-      return cudaGetLastError();
-    }
-    if (rows_v2()) {
-      auto kern = P.in_keys ? refine_rows2_kernel<true> : refine_rows2_kernel<false>;
-      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-      kern<<<(unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms()), REFINE_ROWS_THREADS, smem, s>>>(P);
+      kern<<<grid, REFINE_ROWS_THREADS, smem4, s>>>(P, tg, n_slots);
       return cudaGetLastError();
     }
     if ((e = cudaFuncSetAttribute(refine_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
