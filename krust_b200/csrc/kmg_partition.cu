@@ -631,10 +631,13 @@ cudaError_t launch_refine(const RefineParams &P_in, bool scatter, cudaStream_t s
     P.row_cap = std::min<uint32_t>((uint32_t)REFINE_ROWS_SLOTS / P.n_sub, REFINE_TILE);  // mean fill 8192 / (n_sub * cap) ~ 0.5
     P.row_magic = (uint32_t)(((1ull << 32) + P.row_cap - 1) / P.row_cap);
     const size_t smem = (size_t)REFINE_ROWS_SLOTS * 8 + (size_t)REFINE_ROWS_OVERFLOW * 12 + 3 * (size_t)P.n_sub * sizeof(uint32_t);
-    if (!rows_legacy() && P.n_sub >= 128u) {  // big rows, drained once per two tiles, tiles interleaved over the grid
+    // big rows, drained once per two tiles, tiles interleaved over the grid -- for LOCAL keys.  When the keys are pulled from other
+    // GPUs (n_src) the round-3 kernel stays: measured on two GPUs (profiles/r4_summary.md) it pulls and refines a step's keys in
+    // 10.4 ms against 12.4 ms (13.7 ms with one tile per drain): NVLink, not the drain pattern, sets its pace.
+    if (!rows_legacy() && P.n_sub >= 128u && P.n_src == 0) {
       const uint32_t n_slots = (uint32_t)((R4_SMEM - (size_t)R4_OVERFLOW * 12 - 3 * (size_t)P.n_sub * sizeof(uint32_t)) / 8) & ~1u;
       P.row_cap = n_slots / P.n_sub;
-      const uint32_t tg = rows_overflow_fraction(2.0 * REFINE_TILE / P.n_sub, P.row_cap) <= 0.035 ? 2u : 1u;
+      const uint32_t tg = rows_overflow_fraction(2.0 * REFINE_TILE / P.n_sub, P.row_cap) <= 0.035 ? 2u : 1u;  // two tiles per drain unless the rows would overflow too often
       const size_t smem4 = (size_t)n_slots * 8 + (size_t)R4_OVERFLOW * 12 + 3 * (size_t)P.n_sub * sizeof(uint32_t);
       const unsigned grid = (unsigned)std::min<uint64_t>(P.n_tiles, (uint64_t)num_sms());
       // chunk of the interleaved tile order: 16 pairs, less when the input is so small that some CTAs would get nothing
