@@ -365,7 +365,7 @@ def main():
         alg_job = gpu_windows * 24.0 + 8.0 * summary["n_distinct"] / world + input_bytes
     pipeline = None
     if local["path"] == 2:
-        # partitioned pipeline: phase A (ingest, A1 partition_scatter_rows, A2 refine_rows) and phase B (count_partitions_smem); reset()
+        # partitioned pipeline: phase A (ingest, A1 partition_scatter_rows2, A2 refine_rows4) and phase B (count_partitions_sieve_tma); reset()
         # clears the timers, so these are the last step's kernels on this rank.  Per k-mer: A1 = 0.375 in + 8 out, A2 = 8 in + 8 out,
         # B = 8 in + 16 out per DISTINCT key.
         a_ms, b_ms = local["scan_ns"] / 1e6, local["consolidate_ns"] / 1e6
@@ -380,9 +380,11 @@ def main():
                     "a1_frac": gbs(a1_bytes, a1_ms) / peak, "a2_frac": gbs(a2_bytes, a2_ms) / peak, "b_frac": gbs(b_bytes, b_ms) / peak,
                     "consolidations": local["n_grows"]}
         # the dominant kernel = the stage with the most device time (its own algorithmic bytes; all three fractions are in `pipeline`)
-        stages = [(a1_ms, a1_bytes, "ingest + partition_scatter_rows_kernel (A1: tile scan, canonical k-mers, mix, coarse scatter through shared-memory rows; "
+        stages = [(a1_ms, a1_bytes, "ingest + partition_scatter_rows2_kernel (A1: tile scan, canonical k-mers, mix, coarse scatter through shared-memory rows; instruction / "
+                                    "shared-memory-pipe bound, not HBM bound; "
                                     "0.375 B in + 8 B out per k-mer)"),
-                  (a2_ms, a2_bytes, "refine_rows_kernel (A2: coarse bins -> fine partitions through shared-memory rows, on N GPUs the pull over NVLink; "
+                  (a2_ms, a2_bytes, "refine_rows4_kernel (A2: coarse bins -> fine partitions through shared-memory rows, tiles interleaved over the grid; on N GPUs "
+                                    "refine_rows_kernel pulling over NVLink; "
                                     "8 B in + 8 B out per k-mer)"),
                   (b_ms, b_bytes, "count_partitions_sieve_tma_kernel (phase B: one CTA per hash partition, bit-map sieve + bulk copies; compacting "
                                   "count_partitions_smem_kernel for repeat-rich input; 8 B in + 16 B out per k-mer)")]

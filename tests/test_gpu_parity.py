@@ -563,30 +563,35 @@ def test_c4_bin_geometry_on_100mbp():
         assert_same(got2, (okeys, want))
 
 
-def test_c4_bin_geometry_on_skewed_input():
-    """The C4 bin counts (2^10 x 2^10: rows of 16 slots, the scatter kernels with the reservation fused into the copy-out) on an
-    input whose sub-tiles overflow their rows in every way: blocks copied many times (a few overflow keys per sub-tile: the
-    double-buffered overflow lists), a 40-base satellite and poly-A stretches (thousands of equal keys per sub-tile: the
-    per-sub-tile exact route, then the job-wide exact layout once a partition outgrows its speculative share), N runs."""
+@pytest.mark.parametrize("size", ["full", "small"])
+def test_c4_bin_geometry_on_skewed_input(size):
+    """The C4 bin counts (2^10 x 2^10: rows of 16 / 27 slots, the scatter kernels partition_scatter_rows2 / refine_rows4) on an input
+    whose sub-tiles overflow their rows in every way: blocks copied many times (a few overflow keys per sub-tile: the overflow
+    lists), a 40-base satellite and poly-A stretches (thousands of equal keys per sub-tile: the per-sub-tile exact route, then the
+    job-wide exact layout once a partition outgrows its speculative share), N runs.  "small": the same at a size compute-sanitizer
+    finishes (tools/sanitize.sh)."""
     rng = np.random.default_rng(777)
-    k, n = 21, 24_000_000
+    k = 21
+    n = 24_000_000 if size == "full" else 800_000
+    u = n // 24   # unit: the features below are placed in 24ths of the input
     g = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n, dtype=np.uint8)].copy()
     block = g[1000:1600].copy()
-    for pos in range(2_000_000, 8_000_000, 9_000):      # 600-base block every 9 kbp: ~670 copies
+    for pos in range(2 * u, 8 * u, 9_000):            # 600-base block every 9 kbp
         g[pos:pos + 600] = block
     sat = g[5000:5040].copy()
-    g[9_000_000:10_000_000] = np.tile(sat, 25_000)      # satellite
-    g[12_000_000:13_500_000] = ord("A")                 # poly-A
-    g[15_000_000:15_400_000] = ord("T")                 # its reverse complement: the same canonical key
-    for pos in rng.integers(0, n - 10, size=300):
+    g[9 * u:10 * u] = np.tile(sat, u // 40 + 1)[:u]   # satellite
+    g[12 * u:13 * u + u // 2] = ord("A")              # poly-A
+    g[15 * u:15 * u + (2 * u) // 5] = ord("T")        # its reverse complement: the same canonical key
+    for pos in rng.integers(0, n - 10, size=300 if size == "full" else 30):
         g[pos:pos + 10] = ord("N")
-    off_np = np.array([0, 5_000_000, 12_700_000, n], dtype=np.uint64)
+    cut = 12 * u + (7 * u) // 10
+    off_np = np.array([0, 5 * u, cut, n], dtype=np.uint64)
     okeys, ocounts, owin = orc.count_batch_mt(k, g, None, off_np)
     ov, of = orc.histogram(ocounts, 1)
-    for parts_log2 in (20, 19):   # 1024 x 1024 (rows of 16 slots) and 1024 x 512 / 512 x 1024 geometry
+    for parts_log2 in (20, 19):   # 1024 x 1024 and 512 x 1024 bins
         with kb.GpuKmerCounter(k, flags=PART, parts_log2=parts_log2) as c:
-            c.count_batch(g[:12_700_000], None, off_np[:3])
-            c.count_batch(g[12_700_000:], None, np.array([0, n - 12_700_000], dtype=np.uint64))
+            c.count_batch(g[:cut], None, off_np[:3])
+            c.count_batch(g[cut:], None, np.array([0, n - cut], dtype=np.uint64))
             s = c.finalize()
             got = c.export(1, True)
             hv, hf = c.histogram(1)
