@@ -380,7 +380,7 @@ def main():
                     "a1_frac": gbs(a1_bytes, a1_ms) / peak, "a2_frac": gbs(a2_bytes, a2_ms) / peak, "b_frac": gbs(b_bytes, b_ms) / peak,
                     "consolidations": local["n_grows"]}
         # the dominant kernel = the stage with the most device time (its own algorithmic bytes; all three fractions are in `pipeline`)
-        stages = [(a1_ms, a1_bytes, "ingest + partition_scatter_rows2_kernel (A1: tile scan, canonical k-mers, mix, coarse scatter through shared-memory rows; instruction / "
+        stages = [(a1_ms, a1_bytes, "partition_scatter_rows2_kernel (A1: tile scan, canonical k-mers, mix, coarse scatter through shared-memory rows; instruction / "
                                     "shared-memory-pipe bound, not HBM bound; "
                                     "0.375 B in + 8 B out per k-mer)"),
                   (a2_ms, a2_bytes, "refine_rows4_kernel (A2: coarse bins -> fine partitions through shared-memory rows, tiles interleaved over the grid; on N GPUs "
