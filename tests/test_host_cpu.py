@@ -273,3 +273,22 @@ def test_rust_sys_bindings_are_generated_from_the_header():
     for name, st in (("kmg_config", _lib.KmgConfig), ("kmg_summary", _lib.KmgSummary), ("kmg_batch", _lib.KmgBatch)):
         body = re.search(r"pub struct %s \{(.*?)\}" % name, committed, flags=re.S).group(1)
         assert re.findall(r"pub (\w+):", body) == [f for f, _ in st._fields_]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver times beside ours) runs without a GPU: the restated reference CPU path on a
+    bounded sample, one JSON line with the base contract's keys plus impl / cpu_baseline / e2e."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample-bases", "2e6"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["metric"] == "canonical k-mers counted/sec" and d["unit"] == "kmers/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
