@@ -784,7 +784,8 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) partition_scatter_staged_ker
   }
 }
 
-// pass 2, ROWS variant (default for up to 2048 partitions): ONE scan of the input.  Every partition owns a row of
+// pass 2, ROWS variant (up to 2048 partitions; this first form is kept as the KMG_ROWS_LEGACY=1 baseline, partition_scatter_rows2_kernel
+// below is what runs): ONE scan of the input.  Every partition owns a row of
 // 2^cl key slots in shared memory; a window's key is ranked inside its partition by one shared atomic (with return)
 // and dropped into the row, the few keys whose row is full (partition sizes per sub-tile are Poisson around 9/16 of
 // a row) go to a small overflow list with their rank.  Then one global reservation per partition and a copy-out

@@ -6,10 +6,14 @@
 // small (~3.5 K keys) that ONE CTA can count it in a SHARED-MEMORY table, compact it into the output and
 // move on -- no cross-CTA dependencies, no grid barriers, HBM sees only streams.
 //
-//   A1  scan -> mixed canonical keys -> P1 coarse bins            (partition_scatter_rows_kernel, kmg_kernels.cu)
-//   A2  coarse bin -> P2 sub-bins each (P = P1*P2 fine)           (refine_rows_kernel; refine_kernel<> = exact route)
-//   B   one CTA per fine partition: upsert, compact, histogram   (count_partitions_smem_kernel; count_partitions_kernel
-//                                                                  = L2-scratch fallback)
+//   A1  scan -> mixed canonical keys -> P1 coarse bins            (partition_scatter_rows2_kernel, kmg_kernels.cu)
+//   A2  coarse bin -> P2 sub-bins each (P = P1*P2 fine)           (refine_rows4_kernel: big rows, tiles interleaved over the grid;
+//                                                                  refine_rows_kernel: few sub-bins, and keys pulled from other GPUs;
+//                                                                  refine_kernel<> = exact route)
+//   B   one CTA per fine partition: count, emit, histogram        (count_partitions_sieve(_tma)_kernel: bit-map sieve for mostly
+//                                                                  distinct keys; count_partitions_smem_kernel: table variant for
+//                                                                  weighted / repeat-rich runs; count_partitions_kernel = L2-scratch
+//                                                                  fallback)
 //
 // The streams between the stages hold MIXED keys v = mix64(key) (kmg_device.cuh): coarse bin = top bits of v's high
 // half, sub-bin = top bits of its low half, table slot = its lowest bits.  Both scatter levels write into speculative
