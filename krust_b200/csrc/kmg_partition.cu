@@ -407,8 +407,8 @@ __global__ void __launch_bounds__(REFINE_ROWS_THREADS, 1) refine_rows_kernel(Ref
 //     sub-bins at the same instant, C = 64 spreads the writes too far again: 15.7 ms).
 //   * the cost per (row, drain) -- one global reservation, a row header, two half-filled sectors at the ends of every run -- is
 //     real: two 512-thread CTAs on half tiles (runs of 4.4 keys) 19.8 ms, one CTA draining once per tile (8.8) 16.7 ms, once per
-//     TWO tiles (17.7) 16.2 ms (all interleaved, C = 1).  So the rows take all the shared memory there is (27 slots for 928
-//     sub-bins, mean fill 0.65, ~0.2 % of the keys overflow to the list) and are drained once per two tiles.
+//     TWO tiles (17.7) 16.2 ms (all interleaved, C = 1).  So the rows take all the shared memory there is (28 slots for 928
+//     sub-bins, mean fill 0.63, ~0.1 % of the keys overflow to the list) and are drained once per two tiles.
 //   * the next group's two tiles are prefetched into L2 a group ahead (one line per thread): the register batches (four keys per
 //     thread; the first tile of a group requested before the previous group's copy-out, the second one batch ahead) then wait
 //     for L2 instead of DRAM: 16.2 -> 16.0 ms.
